@@ -1,0 +1,160 @@
+/*
+ * orcdemux.h -- C ABI of liborcdemux.so, the B200-native drop-in for the adapter/index
+ * matching, trimming and binning that the reference delegates to two `cutadapt`
+ * invocations per dataset:
+ *
+ *   round 1  /root/reference/scripts/02_cutadapt_loop.sh:64-72
+ *            cutadapt --action=trim -e 0.1 -j 24 --rc -g file:M13_amplicon_indices_forward.fa
+ *                     -o SP5/{name}_<ds>.fastq.gz IN --json=...
+ *   round 2  /root/reference/scripts/02_cutadapt_loop.sh:94-102   (once per SP5 bin)
+ *            cutadapt --action=trim -e 0.1 -j 24 --rc -a file:M13_amplicon_indices_reverse_rc.fa
+ *                     -o SP27/{name}_<SP5id>_<ds>.fastq.gz SP5/<SP5id>_<ds>.fastq.gz --json=...
+ *
+ * The reference has no in-process FFI for this path (the boundary is the cutadapt
+ * command line); this header is what a host binding (ctypes/cgo/JNI) of a
+ * cutadapt-compatible front end binds instead.  Plain pointers and sizes only.
+ *
+ * Threading: one ctx per GPU; a ctx is not thread-safe; different ctxs are independent.
+ * Errors: functions return 0 on success and a negative ORC_E* code on failure;
+ * orc_last_error() gives the text.  There is NO CPU fallback: without a usable CUDA
+ * device orc_create() fails.
+ */
+#ifndef ORCDEMUX_H
+#define ORCDEMUX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_ROUNDS 2
+#define ORC_MAX_ADAPTERS 16      /* adapters per round (x2 orientations = one warp) */
+#define ORC_MAX_ADAPTER_LEN 64   /* one 64-bit Myers word */
+
+/* adapter types == cutadapt's -g / -a / -g ^ / -a ...$ (adapters.py Front/Back/Prefix/SuffixAdapter) */
+enum { ORC_FRONT = 0, ORC_BACK = 1, ORC_PREFIX = 2, ORC_SUFFIX = 3 };
+
+enum {
+    ORC_OK = 0,
+    ORC_EINVAL = -1,       /* bad argument / unsupported option */
+    ORC_ECUDA = -2,        /* CUDA runtime error (text in orc_last_error) */
+    ORC_ECAPACITY = -3,    /* batch exceeds the capacities given to orc_create */
+    ORC_ESTATE = -4        /* call sequence error (e.g. wait on an idle slot) */
+};
+
+/* One cutadapt invocation's matching options (replaces the argv at 02:64-72 / 02:94-102). */
+typedef struct orc_round_params {
+    int32_t n_adapters;             /* records of the `file:` FASTA, file order kept */
+    int32_t type;                   /* ORC_FRONT (-g) or ORC_BACK (-a) */
+    const char *const *names;       /* [n_adapters] header.split()[0]; may be NULL */
+    const char *const *sequences;   /* [n_adapters] NUL-terminated, <= ORC_MAX_ADAPTER_LEN, ACGT */
+    double max_error_rate;          /* -e  (values >= 1 are absolute error counts, as in cutadapt) */
+    int32_t min_overlap;            /* -O  (cutadapt default 3) */
+    int32_t indels;                 /* 1; 0 == --no-indels */
+    int32_t revcomp;                /* --rc */
+} orc_round_params;
+
+typedef struct orc_params {
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t n_rounds;               /* 1 = one cutadapt call; 2 = round 1 then round 2 on assigned reads */
+    orc_round_params rounds[ORC_MAX_ROUNDS];
+    uint32_t max_reads;             /* capacity of one batch */
+    uint64_t max_bytes;             /* capacity of the seq (== qual) blob of one batch, bytes */
+    uint64_t max_name_bytes;        /* capacity of the names blob of one batch */
+    int32_t n_slots;                /* batches that may be in flight (>= 1) */
+    int32_t emit_fastq;             /* build bin-major FASTQ text on the device */
+    int32_t want_matches;           /* return the per-read match records */
+    const uint8_t *drop_bins;       /* optional [n_bins]: 1 = do not emit that bin (02:110-118) */
+} orc_params;
+
+/*
+ * One batch of reads.  Bin ids: with one round bin = adapter + 1 (0 == "unknown");
+ * with two rounds bin = (a1 + 1) + (n_adapters1 + 1) * (a2 + 1), a == -1 for unknown.
+ * Buffers stay owned by the caller and must stay valid until orc_wait() returns; pinned
+ * memory (orc_host_alloc or torch pin_memory) makes the copies asynchronous.
+ */
+typedef struct orc_batch {
+    uint32_t n_reads;
+    uint64_t n_bytes;               /* bytes of seq and of qual that are in use */
+    const uint8_t *seq;             /* ASCII bases, reads at offsets[r] .. offsets[r]+lengths[r] */
+    const uint8_t *qual;            /* ASCII qualities, same offsets */
+    const uint64_t *offsets;        /* [n_reads] */
+    const uint32_t *lengths;        /* [n_reads] */
+    const uint8_t *names;           /* FASTQ header lines without '@' and newline; NULL if !emit_fastq */
+    const uint64_t *name_offsets;   /* [n_reads + 1] */
+} orc_batch;
+
+/* What Aligner.locate returns for the adapter that won (cutadapt _align.pyx), plus which. */
+typedef struct orc_match {
+    int32_t adapter;                /* index in file order, -1 = no match ("unknown") */
+    int32_t is_rc;                  /* --rc chose the reverse complement (name gets " rc") */
+    int32_t ref_start, ref_stop;    /* adapter interval */
+    int32_t query_start, query_stop;/* read interval, in the chosen orientation */
+    int32_t score, errors;
+} orc_match;
+
+/* Host-visible results of one batch; pointers are owned by the ctx and stay valid until
+ * the next orc_submit()/orc_upload() on the same slot. */
+typedef struct orc_result {
+    uint32_t n_reads;
+    int32_t n_bins;
+    const orc_match *matches[ORC_MAX_ROUNDS]; /* [n_reads] per round; NULL unless want_matches */
+    const int32_t *bin;             /* [n_reads] bin id, -1 = dropped */
+    const uint32_t *out_len;        /* [n_reads] length of the trimmed read */
+    const uint64_t *bin_counts;     /* [n_bins] reads of this batch per bin */
+    const uint64_t *bin_offsets;    /* [n_bins + 1] byte ranges of the bins inside fastq */
+    const uint8_t *fastq;           /* bin-major FASTQ text, input order kept inside a bin */
+    uint64_t fastq_bytes;
+} orc_result;
+
+/* Device time of the stages of the last orc_launch()/orc_submit() on a slot, from CUDA
+ * events recorded on the ctx's own stream (milliseconds), and launch counts. */
+typedef struct orc_timings {
+    float pack_ms;                  /* ASCII -> 4-bit codes */
+    float scan_ms[ORC_MAX_ROUNDS];  /* bit-parallel edit-distance scan, per round */
+    float resolve_ms[ORC_MAX_ROUNDS]; /* exact banded DP of the candidate pairs + selection */
+    float bin_ms;                   /* per-bin counts, stable offsets */
+    float emit_ms;                  /* trimmed FASTQ records into their bins */
+    float total_ms;                 /* first kernel start .. last kernel end */
+    float h2d_ms, d2h_ms;
+    uint32_t kernel_launches;
+    uint32_t n_tasks[ORC_MAX_ROUNDS]; /* candidate pairs that needed the banded DP */
+    uint64_t cells[ORC_MAX_ROUNDS];   /* algorithmic DP cells: pairs * m * n   */
+    uint64_t pack_bytes, emit_bytes;  /* algorithmic bytes moved by pack / emit */
+} orc_timings;
+
+orc_ctx *orc_create(const orc_params *params, char *err, size_t err_len);
+void orc_destroy(orc_ctx *ctx);
+const char *orc_last_error(orc_ctx *ctx);
+int orc_n_bins(orc_ctx *ctx);
+
+/* whole step: H2D copies, kernels, D2H copies, all asynchronous on the slot's stream */
+int orc_submit(orc_ctx *ctx, int slot, const orc_batch *batch);
+int orc_wait(orc_ctx *ctx, int slot, orc_result *out);
+
+/* the same step in three parts, for device-resident timing */
+int orc_upload(orc_ctx *ctx, int slot, const orc_batch *batch);
+int orc_launch(orc_ctx *ctx, int slot);
+int orc_download(orc_ctx *ctx, int slot);
+int orc_sync(orc_ctx *ctx, int slot);
+
+int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *out);
+/* cumulative reads per bin over every batch waited on so far ([n_bins]) */
+int orc_counts(orc_ctx *ctx, uint64_t *bins);
+
+/* pinned host memory for callers that do not bring their own */
+void *orc_host_alloc(size_t bytes);
+void orc_host_free(void *p);
+
+/* micro-benchmark: dependent-free LOP3/IADD3 issue rate of the INT32 ALU pipe, in
+ * 32-bit integer ops per second (the DP kernel's roofline denominator) */
+double orc_measure_int32_peak(int device, double *sm_clock_mhz);
+
+const char *orc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORCDEMUX_H */

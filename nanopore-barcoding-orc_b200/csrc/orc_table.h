@@ -1,0 +1,110 @@
+// orc_table.h -- host-side construction of the per-round constant tables (RoundTable).
+// Restates cutadapt 4.9 adapters.py SingleAdapter.__init__ (sequence normalisation,
+// max_error_rate, min_overlap) and the fp64 acceptance threshold of _align.pyx
+// (`cost <= length * max_error_rate`) as an integer table per aligned length.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
+#include "orc_core.cuh"
+
+namespace orc {
+
+inline int base_code(char c)
+{
+    switch (c) {
+    case 'A': return 1;
+    case 'C': return 2;
+    case 'G': return 4;
+    case 'T': return 8;
+    default: return -1;
+    }
+}
+
+// Returns "" on success, else the reason the round is not supported.
+inline std::string build_round_table(RoundTable &T, int n_adapters, int type, const char *const *sequences,
+                                     double max_errors, int min_overlap, int indels, int revcomp)
+{
+    memset(&T, 0, sizeof(T));
+    if (n_adapters < 1 || n_adapters > MAX_AD)
+        return "unsupported: between 1 and " + std::to_string(MAX_AD) + " adapters per round";
+    if (type != TYPE_FRONT && type != TYPE_BACK)
+        return "unsupported: only regular 5' (-g) and 3' (-a) adapters take the edit-distance path";
+    if (!indels) return "unsupported: --no-indels on unanchored adapters";
+    if (min_overlap < 1) return "min_overlap must be >= 1";
+    T.n_adapters = n_adapters;
+    T.type = type;
+    T.revcomp = revcomp ? 1 : 0;
+    T.min_overlap = min_overlap;
+    T.n_lanes = 2 * n_adapters;
+    for (int a = 0; a < n_adapters; a++) {
+        const char *s = sequences[a];
+        const int m = (int)strlen(s);
+        if (m < 1 || m > MAX_M) return "unsupported: adapter length must be 1..64";
+        T.m[a] = m;
+        for (int i = 0; i < m; i++) {
+            char c = s[i];
+            if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+            if (c == 'U') c = 'T';
+            const int code = base_code(c);
+            if (code < 0) return "unsupported: adapter characters other than ACGT (IUPAC wildcards)";
+            T.code[a][i] = (uint8_t)code;
+        }
+        double rate = max_errors;
+        if (rate >= 1.0) rate /= m;                 // absolute error count (adapters.py)
+        T.k[a] = (int)(rate * m);                   // _align.pyx: k = <int>(max_error_rate * m)
+        T.min_ov[a] = min_overlap < m ? min_overlap : m;
+        for (int L = 0; L <= m; L++) {
+            // largest integer cost with (double)cost <= L * rate
+            double x = L * rate;
+            int c = (int)floor(x);
+            if (c < 0) c = 0;
+            if (c > 255) c = 255;
+            T.kmax[a][L] = (uint8_t)c;
+        }
+    }
+    for (int lane = 0; lane < T.n_lanes; lane++) {
+        const int a = lane % n_adapters, dir = lane / n_adapters;
+        const int m = T.m[a];
+        const uint64_t pad = (m == 64) ? 0ull : ((1ull << (64 - m)) - 1ull);
+        for (uint32_t c = 0; c < 16; c++) {
+            const uint32_t cc = dir ? comp4(c) : c;
+            uint64_t bits = pad;
+            for (int i = 0; i < m; i++)
+                if (T.code[a][i] & cc) bits |= 1ull << (64 - m + i);
+            T.peq[c][lane] = bits;
+        }
+        // R2: FRONT column 0 costs are all 0; BACK column 0 cost is i
+        T.pv0[lane] = (type == TYPE_FRONT) ? 0ull : ~pad;
+        T.d0[lane] = (type == TYPE_FRONT) ? 0 : m;
+    }
+    return "";
+}
+
+// ASCII -> 4-bit code used by the pack kernel.  cutadapt compares ASCII after upper()
+// when the adapter is plain ACGT, so only ACGT/acgt get a code; anything
+// else (N, U, IUPAC, '-') is 0 and matches nothing.
+inline void build_pack_lut(uint8_t lut[256])
+{
+    memset(lut, 0, 256);
+    lut[(int)'A'] = lut[(int)'a'] = 1;
+    lut[(int)'C'] = lut[(int)'c'] = 2;
+    lut[(int)'G'] = lut[(int)'g'] = 4;
+    lut[(int)'T'] = lut[(int)'t'] = 8;
+}
+
+// dnaio SequenceRecord.reverse_complement(): IUPAC complement, case preserved.
+inline void build_complement_lut(uint8_t lut[256])
+{
+    for (int i = 0; i < 256; i++) lut[i] = (uint8_t)i;
+    const char *from = "ACGTUMRWSYKVHDBN";
+    const char *to = "TGCAAKYWSRMBDHVN";
+    for (int i = 0; from[i]; i++) {
+        lut[(int)from[i]] = (uint8_t)to[i];
+        lut[(int)(from[i] | 0x20)] = (uint8_t)(to[i] | 0x20);
+    }
+}
+
+}  // namespace orc

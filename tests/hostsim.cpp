@@ -1,0 +1,80 @@
+// hostsim.cpp -- TEST HARNESS (never part of the product).
+//
+// Runs the per-lane device arithmetic of nanopore-barcoding-orc_b200/csrc/orc_core.cuh on
+// the CPU, lane by lane, in the order the kernels would, so that the exactness of the
+// scan -> candidate hull -> banded resolve -> select chain can be checked against the
+// oracle on machines without a GPU.  Built by tests/conftest.py with g++.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "orc_core.cuh"
+#include "orc_table.h"
+
+using namespace orc;
+
+extern "C" int hostsim_demux(int n_rounds,
+                             int n_ad0, int type0, const char *const *seq0, double e0, int ov0, int rc0,
+                             int n_ad1, int type1, const char *const *seq1, double e1, int ov1, int rc1,
+                             const uint8_t *seq, const uint64_t *offsets, const uint32_t *lengths,
+                             uint32_t n_reads, uint64_t n_bytes,
+                             Match *m0, Match *m1, uint64_t *out_lo, uint32_t *out_len, uint32_t *out_rc,
+                             uint64_t *n_tasks, char *err, int err_len)
+{
+    RoundTable *T = new RoundTable[2];
+    std::string e = build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, 1, rc0);
+    if (e.empty() && n_rounds > 1) e = build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, 1, rc1);
+    if (!e.empty()) {
+        strncpy(err, e.c_str(), (size_t)err_len - 1);
+        err[err_len - 1] = 0;
+        delete[] T;
+        return -1;
+    }
+    uint8_t lut[256];
+    build_pack_lut(lut);
+    // flat pack with 4 guard words on each side, like the device buffers
+    const uint64_t n_words = (n_bytes + 7) / 8;
+    std::vector<uint32_t> codes(n_words + 8, 0);
+    uint32_t *W = codes.data() + 4;
+    for (uint64_t i = 0; i < n_bytes; i++) W[i >> 3] |= (uint32_t)lut[seq[i]] << ((i & 7) * 4);
+
+    Cell col[MAX_M + 1];
+    n_tasks[0] = n_tasks[1] = 0;
+    for (uint32_t r = 0; r < n_reads; r++) {
+        View v; v.lo = offsets[r]; v.len = lengths[r]; v.rc = 0;
+        Match *out[2] = {&m0[r], &m1[r]};
+        memset(&m1[r], 0, sizeof(Match));
+        m1[r].adapter = -1;
+        for (int rd = 0; rd < n_rounds; rd++) {
+            const RoundTable &R = T[rd];
+            uint32_t mask = 0;
+            std::vector<PairResult> results;
+            for (int lane = 0; lane < R.n_lanes; lane++) {
+                const int a = lane % R.n_adapters, dir = lane / R.n_adapters;
+                const int o = dir ^ (int)(v.rc & 1u);
+                if (o == 1 && !R.revcomp) continue;
+                ScanHull h;
+                scan_lane(W, v.lo, v.len, dir, (const char *)&R.peq[0][0], lane, R.pv0[lane], R.d0[lane],
+                          R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, h);
+                if (h.jf <= h.jl || h.i1 <= h.i2) {
+                    Task t; t.read = r; t.lane = (uint32_t)lane; t.jf = h.jf; t.jl = h.jl; t.i1 = h.i1; t.i2 = h.i2;
+                    PairResult pr; memset(&pr, 0, sizeof(pr));
+                    resolve_pair(W, v, R, t, pr, col);
+                    results.push_back(pr);
+                    mask |= 1u << lane;
+                    n_tasks[rd]++;
+                }
+            }
+            View next;
+            select_read(R, v, mask, results.data(), *out[rd], next);
+            v = next;
+            if (out[rd]->adapter < 0) break;     // 02:75-80: "unknown" never enters round 2
+        }
+        out_lo[r] = v.lo; out_len[r] = v.len; out_rc[r] = v.rc;
+    }
+    delete[] T;
+    return 0;
+}
