@@ -33,6 +33,8 @@ extern "C" {
 #define ORC_MAX_ADAPTERS 16      /* adapters per round (x2 orientations = one warp) */
 #define ORC_MAX_ADAPTER_LEN 64   /* one 64-bit Myers word */
 
+typedef struct orc_ctx orc_ctx;   /* opaque; one per GPU */
+
 /* adapter types == cutadapt's -g / -a / -g ^ / -a ...$ (adapters.py Front/Back/Prefix/SuffixAdapter) */
 enum { ORC_FRONT = 0, ORC_BACK = 1, ORC_PREFIX = 2, ORC_SUFFIX = 3 };
 
@@ -141,6 +143,10 @@ int orc_download(orc_ctx *ctx, int slot);
 int orc_sync(orc_ctx *ctx, int slot);
 
 int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *out);
+/* a CUDA-event stopwatch on the slot's stream: start records an event, stop records a
+ * second one, waits for it and returns the device time between them (milliseconds) */
+int orc_timer_start(orc_ctx *ctx, int slot);
+int orc_timer_stop(orc_ctx *ctx, int slot, float *ms);
 /* cumulative reads per bin over every batch waited on so far ([n_bins]) */
 int orc_counts(orc_ctx *ctx, uint64_t *bins);
 
@@ -148,9 +154,10 @@ int orc_counts(orc_ctx *ctx, uint64_t *bins);
 void *orc_host_alloc(size_t bytes);
 void orc_host_free(void *p);
 
-/* micro-benchmark: dependent-free LOP3/IADD3 issue rate of the INT32 ALU pipe, in
- * 32-bit integer ops per second (the DP kernel's roofline denominator) */
-double orc_measure_int32_peak(int device, double *sm_clock_mhz);
+/* micro-benchmark: issue rate of dependent-free 32-bit integer instructions, in lane-ops per
+ * second (the DP kernel's roofline denominator).  mode 0: LOP3 only (the ALU
+ * pipe the Myers recurrence lives on); mode 1: LOP3 + IMAD mix (ALU and FMA pipes together) */
+double orc_measure_int32_peak(int device, int mode, double *sm_clock_mhz);
 
 const char *orc_version(void);
 

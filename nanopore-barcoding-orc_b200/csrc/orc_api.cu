@@ -1,0 +1,596 @@
+// orc_api.cu -- C ABI of liborcdemux.so (include/orcdemux.h): context, device arena,
+// streams, and the launch sequence of one batch.  Replaces the inside of the two cutadapt
+// invocations of /root/reference/scripts/02_cutadapt_loop.sh:64-72 and :94-102.
+//
+// One ctx per GPU; n_slots batches can be in flight, each on its own stream with its own
+// device arena, so that the H2D copy of batch i+1 and the D2H copy of batch i-1 overlap the
+// kernels of batch i.  No CPU fallback anywhere: every entry point needs the device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orcdemux.h"
+#include "orc_kernels.cuh"
+#include "orc_table.h"
+
+using namespace orc;
+
+static_assert(sizeof(orc_match) == sizeof(Match), "orc_match layout");
+static_assert(sizeof(View) == 16, "View layout");
+static_assert(sizeof(Task) == 32, "Task layout");
+static_assert(sizeof(PairResult) == 32, "PairResult layout");
+static_assert(ORC_MAX_ADAPTERS == MAX_AD, "adapter limit");
+
+namespace {
+
+enum { EV_START = 0, EV_H2D, EV_PACK, EV_SCAN0, EV_RES0, EV_SCAN1, EV_RES1, EV_BIN, EV_EMIT, EV_HDR, EV_END, EV_T0, EV_T1, EV_COUNT };
+enum { SLOT_IDLE = 0, SLOT_UPLOADED, SLOT_LAUNCHED, SLOT_DOWNLOADING };
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    int state = SLOT_IDLE;
+    uint32_t n_reads = 0;
+    uint64_t n_bytes = 0, name_bytes = 0, in_bases = 0;
+    bool has_names = false;
+    bool did_h2d = false, did_kernels = false, did_d2h = false, fresh_upload = false;
+    // device
+    uint8_t *d_seq = nullptr, *d_qual = nullptr, *d_names = nullptr, *d_fastq = nullptr;
+    uint32_t *d_codes_alloc = nullptr;
+    uint64_t *d_offsets = nullptr, *d_name_offsets = nullptr, *d_dest = nullptr;
+    uint32_t *d_lengths = nullptr;
+    View *d_views[3] = {nullptr, nullptr, nullptr};
+    Match *d_match[2] = {nullptr, nullptr};
+    uint32_t *d_read_mask = nullptr, *d_read_base = nullptr;
+    Task *d_tasks = nullptr;
+    PairResult *d_results = nullptr;
+    uint32_t *d_counters = nullptr;          // [0..1] work counters, [2..3] task counts
+    unsigned long long *d_cells = nullptr;   // [2] sum of view lengths entering each round
+    int32_t *d_bin = nullptr;
+    uint32_t *d_out_len = nullptr, *d_rec_bytes = nullptr, *d_hist_cnt = nullptr;
+    uint64_t *d_hist_bytes = nullptr, *d_bin_counts = nullptr, *d_bin_offsets = nullptr;
+    // pinned host
+    Match *h_match[2] = {nullptr, nullptr};
+    int32_t *h_bin = nullptr;
+    uint32_t *h_out_len = nullptr, *h_counters = nullptr;
+    uint64_t *h_bin_counts = nullptr, *h_bin_offsets = nullptr;
+    unsigned long long *h_cells = nullptr;
+    uint8_t *h_fastq = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+};
+
+}  // namespace
+
+struct orc_ctx {
+    int device = 0;
+    int n_rounds = 1, n_slots = 1, n_bins = 1, sm_count = 148;
+    int emit_fastq = 1, want_matches = 1;
+    uint32_t max_reads = 0;
+    uint64_t max_bytes = 0, max_name_bytes = 0, fastq_cap = 0;
+    RoundTable h_tab[2];
+    RoundTable *d_tab[2] = {nullptr, nullptr};
+    uint8_t *d_pack_lut = nullptr, *d_comp_lut = nullptr, *d_drop = nullptr;
+    std::vector<Slot> slots;
+    std::vector<uint64_t> total_counts;
+    std::string err;
+    int scan_blocks = 0, resolve_blocks = 0;
+};
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            return ORC_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n)
+{
+    return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T) + 64);
+}
+template <typename T>
+static cudaError_t halloc(T **p, size_t n)
+{
+    return cudaHostAlloc(reinterpret_cast<void **>(p), n * sizeof(T) + 64, cudaHostAllocDefault);
+}
+
+static int alloc_slot(orc_ctx *ctx, Slot &s)
+{
+    const size_t R = ctx->max_reads, B = (size_t)ctx->max_bytes;
+    const size_t n_chunks = (R + BIN_CHUNK - 1) / BIN_CHUNK;
+    const size_t n_tasks = R * MAX_LANES;
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_COUNT; i++) CK(cudaEventCreate(&s.ev[i]));
+    CK(dalloc(&s.d_seq, B + 64));
+    CK(dalloc(&s.d_qual, B + 64));
+    CK(dalloc(&s.d_codes_alloc, B / 8 + 16 + 2 * GUARD_WORDS));
+    CK(cudaMemset(s.d_codes_alloc, 0, (B / 8 + 16 + 2 * GUARD_WORDS) * sizeof(uint32_t)));
+    CK(dalloc(&s.d_offsets, R));
+    CK(dalloc(&s.d_lengths, R));
+    for (int i = 0; i < 3; i++) CK(dalloc(&s.d_views[i], R));
+    for (int i = 0; i < 2; i++) CK(dalloc(&s.d_match[i], R));
+    CK(dalloc(&s.d_read_mask, R));
+    CK(dalloc(&s.d_read_base, R));
+    CK(dalloc(&s.d_tasks, n_tasks));
+    CK(dalloc(&s.d_results, n_tasks));
+    CK(dalloc(&s.d_counters, 8));
+    CK(dalloc(&s.d_cells, 2));
+    CK(dalloc(&s.d_bin, R));
+    CK(dalloc(&s.d_out_len, R));
+    CK(dalloc(&s.d_rec_bytes, R));
+    CK(dalloc(&s.d_dest, R));
+    CK(dalloc(&s.d_hist_cnt, n_chunks * ctx->n_bins));
+    CK(dalloc(&s.d_hist_bytes, n_chunks * ctx->n_bins));
+    CK(dalloc(&s.d_bin_counts, (size_t)ctx->n_bins));
+    CK(dalloc(&s.d_bin_offsets, (size_t)ctx->n_bins + 1));
+    CK(halloc(&s.h_bin, R));
+    CK(halloc(&s.h_out_len, R));
+    CK(halloc(&s.h_counters, 8));
+    CK(halloc(&s.h_cells, 2));
+    CK(halloc(&s.h_bin_counts, (size_t)ctx->n_bins));
+    CK(halloc(&s.h_bin_offsets, (size_t)ctx->n_bins + 1));
+    if (ctx->want_matches)
+        for (int i = 0; i < 2; i++) CK(halloc(&s.h_match[i], R));
+    if (ctx->emit_fastq) {
+        CK(dalloc(&s.d_names, (size_t)ctx->max_name_bytes + 64));
+        CK(dalloc(&s.d_name_offsets, R + 1));
+        CK(dalloc(&s.d_fastq, (size_t)ctx->fastq_cap));
+        CK(halloc(&s.h_fastq, (size_t)ctx->fastq_cap));
+    }
+    return ORC_OK;
+}
+
+static void free_slot(Slot &s)
+{
+    cudaFree(s.d_seq); cudaFree(s.d_qual); cudaFree(s.d_names); cudaFree(s.d_fastq);
+    cudaFree(s.d_codes_alloc); cudaFree(s.d_offsets); cudaFree(s.d_name_offsets); cudaFree(s.d_dest);
+    cudaFree(s.d_lengths);
+    for (int i = 0; i < 3; i++) cudaFree(s.d_views[i]);
+    for (int i = 0; i < 2; i++) { cudaFree(s.d_match[i]); cudaFreeHost(s.h_match[i]); }
+    cudaFree(s.d_read_mask); cudaFree(s.d_read_base); cudaFree(s.d_tasks); cudaFree(s.d_results);
+    cudaFree(s.d_counters); cudaFree(s.d_cells); cudaFree(s.d_bin); cudaFree(s.d_out_len);
+    cudaFree(s.d_rec_bytes); cudaFree(s.d_hist_cnt); cudaFree(s.d_hist_bytes);
+    cudaFree(s.d_bin_counts); cudaFree(s.d_bin_offsets);
+    cudaFreeHost(s.h_bin); cudaFreeHost(s.h_out_len); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_cells);
+    cudaFreeHost(s.h_bin_counts); cudaFreeHost(s.h_bin_offsets); cudaFreeHost(s.h_fastq);
+    for (int i = 0; i < EV_COUNT; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+static int ctx_init(orc_ctx *ctx, const orc_params *p)
+{
+    if (p->n_rounds < 1 || p->n_rounds > ORC_MAX_ROUNDS) { ctx->err = "n_rounds must be 1 or 2"; return ORC_EINVAL; }
+    if (p->max_reads == 0 || p->max_bytes == 0) { ctx->err = "max_reads and max_bytes must be > 0"; return ORC_EINVAL; }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        ctx->err = std::string("no CUDA device (liborcdemux has no CPU fallback): ") + cudaGetErrorString(e);
+        return ORC_ECUDA;
+    }
+    ctx->device = p->device;
+    CK(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p->device));
+    if (prop.major < 10) {
+        ctx->err = "liborcdemux is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor);
+        return ORC_ECUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->n_rounds = p->n_rounds;
+    ctx->n_slots = p->n_slots < 1 ? 1 : p->n_slots;
+    ctx->emit_fastq = p->emit_fastq ? 1 : 0;
+    ctx->want_matches = p->want_matches ? 1 : 0;
+    ctx->max_reads = p->max_reads;
+    ctx->max_bytes = (p->max_bytes + 63) & ~63ull;
+    ctx->max_name_bytes = p->max_name_bytes ? p->max_name_bytes : 64;
+    for (int r = 0; r < p->n_rounds; r++) {
+        const orc_round_params &rp = p->rounds[r];
+        if (rp.sequences == nullptr) { ctx->err = "round without adapter sequences"; return ORC_EINVAL; }
+        std::string why = build_round_table(ctx->h_tab[r], rp.n_adapters, rp.type, rp.sequences,
+                                            rp.max_error_rate, rp.min_overlap, rp.indels, rp.revcomp);
+        if (!why.empty()) { ctx->err = why; return ORC_EINVAL; }
+    }
+    ctx->n_bins = ctx->h_tab[0].n_adapters + 1;
+    if (p->n_rounds == 2) ctx->n_bins *= ctx->h_tab[1].n_adapters + 1;
+    ctx->total_counts.assign((size_t)ctx->n_bins, 0);
+    ctx->fastq_cap = ctx->max_name_bytes + 2 * ctx->max_bytes + 16ull * ctx->max_reads + 64;
+    for (int r = 0; r < p->n_rounds; r++) {
+        CK(dalloc(&ctx->d_tab[r], 1));
+        CK(cudaMemcpy(ctx->d_tab[r], &ctx->h_tab[r], sizeof(RoundTable), cudaMemcpyHostToDevice));
+    }
+    uint8_t lut[256];
+    build_pack_lut(lut);
+    CK(dalloc(&ctx->d_pack_lut, 256));
+    CK(cudaMemcpy(ctx->d_pack_lut, lut, 256, cudaMemcpyHostToDevice));
+    build_complement_lut(lut);
+    CK(dalloc(&ctx->d_comp_lut, 256));
+    CK(cudaMemcpy(ctx->d_comp_lut, lut, 256, cudaMemcpyHostToDevice));
+    std::vector<uint8_t> drop((size_t)ctx->n_bins, 0);
+    if (p->drop_bins) memcpy(drop.data(), p->drop_bins, (size_t)ctx->n_bins);
+    CK(dalloc(&ctx->d_drop, (size_t)ctx->n_bins));
+    CK(cudaMemcpy(ctx->d_drop, drop.data(), (size_t)ctx->n_bins, cudaMemcpyHostToDevice));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel, SCAN_THREADS, 0));
+    ctx->scan_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_kernel, 128, 0));
+    ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
+    ctx->slots.resize((size_t)ctx->n_slots);
+    for (auto &s : ctx->slots) {
+        int rc = alloc_slot(ctx, s);
+        if (rc != ORC_OK) return rc;
+    }
+    return ORC_OK;
+}
+
+extern "C" orc_ctx *orc_create(const orc_params *params, char *err, size_t err_len)
+{
+    orc_ctx *ctx = new orc_ctx();
+    int rc = params ? ctx_init(ctx, params) : ORC_EINVAL;
+    if (rc != ORC_OK) {
+        if (err && err_len) {
+            snprintf(err, err_len, "%s", params ? ctx->err.c_str() : "params is NULL");
+        }
+        orc_destroy(ctx);
+        return nullptr;
+    }
+    if (err && err_len) err[0] = 0;
+    return ctx;
+}
+
+extern "C" void orc_destroy(orc_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto &s : ctx->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        free_slot(s);
+    }
+    for (int r = 0; r < 2; r++) cudaFree(ctx->d_tab[r]);
+    cudaFree(ctx->d_pack_lut); cudaFree(ctx->d_comp_lut); cudaFree(ctx->d_drop);
+    delete ctx;
+}
+
+extern "C" const char *orc_last_error(orc_ctx *ctx) { return ctx ? ctx->err.c_str() : "ctx is NULL"; }
+extern "C" int orc_n_bins(orc_ctx *ctx) { return ctx ? ctx->n_bins : ORC_EINVAL; }
+extern "C" const char *orc_version(void) { return "orcdemux 0.1.0 (sm_100a)"; }
+
+static Slot *get_slot(orc_ctx *ctx, int slot)
+{
+    if (!ctx) return nullptr;
+    if (slot < 0 || slot >= ctx->n_slots) { ctx->err = "slot out of range"; return nullptr; }
+    return &ctx->slots[(size_t)slot];
+}
+
+extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    Slot &s = *sp;
+    if (!b) { ctx->err = "batch is NULL"; return ORC_EINVAL; }
+    if (b->n_reads > ctx->max_reads || b->n_bytes > ctx->max_bytes) {
+        ctx->err = "batch exceeds max_reads/max_bytes given to orc_create";
+        return ORC_ECAPACITY;
+    }
+    if (b->n_reads && (!b->seq || !b->qual || !b->offsets || !b->lengths)) {
+        ctx->err = "batch buffers missing"; return ORC_EINVAL;
+    }
+    s.has_names = ctx->emit_fastq != 0;
+    uint64_t name_bytes = 0;
+    if (s.has_names) {
+        if (b->n_reads && (!b->names || !b->name_offsets)) {
+            ctx->err = "emit_fastq needs names and name_offsets"; return ORC_EINVAL;
+        }
+        name_bytes = b->n_reads ? b->name_offsets[b->n_reads] : 0;
+        if (name_bytes > ctx->max_name_bytes) { ctx->err = "names exceed max_name_bytes"; return ORC_ECAPACITY; }
+    }
+    CK(cudaSetDevice(ctx->device));
+    s.n_reads = b->n_reads;
+    s.n_bytes = b->n_bytes;
+    s.name_bytes = name_bytes;
+    uint64_t bases = 0;
+    for (uint32_t r = 0; r < b->n_reads; r++) {
+        if (b->offsets[r] + b->lengths[r] > b->n_bytes) { ctx->err = "read extends past n_bytes"; return ORC_EINVAL; }
+        bases += b->lengths[r];
+    }
+    s.in_bases = bases;
+    CK(cudaEventRecord(s.ev[EV_START], s.stream));
+    if (b->n_reads) {
+        CK(cudaMemcpyAsync(s.d_seq, b->seq, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_qual, b->qual, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_offsets, b->offsets, sizeof(uint64_t) * b->n_reads, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_lengths, b->lengths, sizeof(uint32_t) * b->n_reads, cudaMemcpyHostToDevice, s.stream));
+        if (s.has_names) {
+            if (name_bytes)
+                CK(cudaMemcpyAsync(s.d_names, b->names, name_bytes, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(s.d_name_offsets, b->name_offsets, sizeof(uint64_t) * (b->n_reads + 1),
+                               cudaMemcpyHostToDevice, s.stream));
+        }
+    }
+    CK(cudaEventRecord(s.ev[EV_H2D], s.stream));
+    s.state = SLOT_UPLOADED;
+    s.did_h2d = true;
+    s.fresh_upload = true;
+    s.did_kernels = false;
+    s.did_d2h = false;
+    return ORC_OK;
+}
+
+extern "C" int orc_launch(orc_ctx *ctx, int slot)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    Slot &s = *sp;
+    if (s.state == SLOT_IDLE) { ctx->err = "orc_launch on a slot without an uploaded batch"; return ORC_ESTATE; }
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = s.n_reads;
+    uint32_t *W = s.d_codes_alloc + GUARD_WORDS;
+    cudaStream_t st = s.stream;
+    CK(cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(s.d_cells, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaEventRecord(s.ev[EV_H2D], st));       // kernels start here (re-recorded when launched alone)
+    s.did_h2d = s.fresh_upload;                  // h2d_ms is only meaningful right after an upload
+    s.fresh_upload = false;
+    s.did_d2h = false;
+    if (n) {
+        init_views_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_offsets, s.d_lengths, n, s.d_views[0]);
+        const uint64_t n16 = (s.n_bytes + 15) / 16;
+        const int pack_blocks = (int)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16);
+        pack_kernel<<<pack_blocks, 256, 0, st>>>(s.d_seq, W, n16, ctx->d_pack_lut);
+    }
+    CK(cudaEventRecord(s.ev[EV_PACK], st));
+    for (int r = 0; r < ctx->n_rounds; r++) {
+        const Match *prev = r == 0 ? nullptr : s.d_match[r - 1];
+        if (n) {
+            scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
+                ctx->d_tab[r], W, s.d_views[r], prev, n, s.d_tasks, s.d_counters + 2 + r, s.d_read_mask,
+                s.d_read_base, s.d_counters + r);
+        }
+        CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
+        if (n) {
+            resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], s.d_tasks,
+                                                               s.d_counters + 2 + r, s.d_results);
+            SelectArgs A;
+            A.tab = ctx->d_tab[r];
+            A.views_in = s.d_views[r];
+            A.views_out = s.d_views[r + 1];
+            A.prev = prev;
+            A.out = s.d_match[r];
+            A.read_mask = s.d_read_mask;
+            A.read_base = s.d_read_base;
+            A.results = s.d_results;
+            A.n_reads = n;
+            A.last_round = (r == ctx->n_rounds - 1);
+            A.round_index = r;
+            A.n_ad0 = ctx->h_tab[0].n_adapters;
+            A.match0 = s.d_match[0];
+            A.drop_bins = ctx->d_drop;
+            A.name_offsets = s.has_names ? s.d_name_offsets : nullptr;
+            A.bin = s.d_bin;
+            A.out_len = s.d_out_len;
+            A.rec_bytes = s.d_rec_bytes;
+            A.next_bases = (r + 1 < ctx->n_rounds) ? s.d_cells + r + 1 : nullptr;
+            select_kernel<<<(n + 127) / 128, 128, 0, st>>>(A);
+        }
+        CK(cudaEventRecord(s.ev[r == 0 ? EV_RES0 : EV_RES1], st));
+    }
+    if (ctx->n_rounds == 1) {
+        CK(cudaEventRecord(s.ev[EV_SCAN1], st));
+        CK(cudaEventRecord(s.ev[EV_RES1], st));
+    }
+    const uint32_t n_chunks = (n + BIN_CHUNK - 1) / BIN_CHUNK;
+    if (n) {
+        bin_count_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(s.d_bin, s.d_rec_bytes, n, ctx->n_bins, n_chunks,
+                                                            s.d_hist_cnt, s.d_hist_bytes);
+    }
+    bin_scan_kernel<<<1, 1024, 0, st>>>(ctx->n_bins, n_chunks, s.d_hist_cnt, s.d_hist_bytes, s.d_bin_counts,
+                                        s.d_bin_offsets);
+    if (n) {
+        bin_place_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(s.d_bin, s.d_rec_bytes, n, ctx->n_bins, n_chunks,
+                                                            s.d_hist_bytes, s.d_bin_offsets, s.d_dest);
+    }
+    CK(cudaEventRecord(s.ev[EV_BIN], st));
+    if (n && s.has_names) {
+        emit_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(s.d_seq, s.d_qual, s.d_names, s.d_name_offsets,
+                                                       s.d_views[ctx->n_rounds], s.d_dest, n, ctx->d_comp_lut,
+                                                       s.d_fastq);
+    }
+    CK(cudaEventRecord(s.ev[EV_EMIT], st));
+    CK(cudaGetLastError());
+    s.state = SLOT_LAUNCHED;
+    s.did_kernels = true;
+    return ORC_OK;
+}
+
+extern "C" int orc_download(orc_ctx *ctx, int slot)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    Slot &s = *sp;
+    if (s.state != SLOT_LAUNCHED) { ctx->err = "orc_download before orc_launch"; return ORC_ESTATE; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = s.stream;
+    const uint32_t n = s.n_reads;
+    CK(cudaMemcpyAsync(s.h_bin_counts, s.d_bin_counts, sizeof(uint64_t) * ctx->n_bins, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_bin_offsets, s.d_bin_offsets, sizeof(uint64_t) * (ctx->n_bins + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[EV_HDR], st));
+    if (n) {
+        CK(cudaMemcpyAsync(s.h_bin, s.d_bin, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.h_out_len, s.d_out_len, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+        if (ctx->want_matches)
+            for (int r = 0; r < ctx->n_rounds; r++)
+                CK(cudaMemcpyAsync(s.h_match[r], s.d_match[r], sizeof(Match) * n, cudaMemcpyDeviceToHost, st));
+    }
+    s.state = SLOT_DOWNLOADING;
+    return ORC_OK;
+}
+
+extern "C" int orc_submit(orc_ctx *ctx, int slot, const orc_batch *batch)
+{
+    int rc = orc_upload(ctx, slot, batch);
+    if (rc != ORC_OK) return rc;
+    rc = orc_launch(ctx, slot);
+    if (rc != ORC_OK) return rc;
+    return orc_download(ctx, slot);
+}
+
+extern "C" int orc_sync(orc_ctx *ctx, int slot)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(sp->stream));
+    return ORC_OK;
+}
+
+extern "C" int orc_wait(orc_ctx *ctx, int slot, orc_result *out)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    Slot &s = *sp;
+    if (s.state != SLOT_DOWNLOADING) { ctx->err = "orc_wait on a slot with nothing submitted"; return ORC_ESTATE; }
+    CK(cudaSetDevice(ctx->device));
+    // the FASTQ size is only known once the header has landed
+    CK(cudaEventSynchronize(s.ev[EV_HDR]));
+    const uint64_t fq = s.has_names ? s.h_bin_offsets[ctx->n_bins] : 0;
+    if (fq > ctx->fastq_cap) { ctx->err = "internal: FASTQ output exceeds its arena"; return ORC_ECAPACITY; }
+    if (fq) CK(cudaMemcpyAsync(s.h_fastq, s.d_fastq, fq, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaEventRecord(s.ev[EV_END], s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    s.did_d2h = true;
+    for (int b = 0; b < ctx->n_bins; b++) ctx->total_counts[(size_t)b] += s.h_bin_counts[b];
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->n_reads = s.n_reads;
+        out->n_bins = ctx->n_bins;
+        if (ctx->want_matches)
+            for (int r = 0; r < ctx->n_rounds; r++) out->matches[r] = reinterpret_cast<const orc_match *>(s.h_match[r]);
+        out->bin = s.h_bin;
+        out->out_len = s.h_out_len;
+        out->bin_counts = s.h_bin_counts;
+        out->bin_offsets = s.h_bin_offsets;
+        out->fastq = s.h_fastq;
+        out->fastq_bytes = fq;
+    }
+    s.state = SLOT_UPLOADED;   // the batch is still resident: orc_launch may run it again
+    return ORC_OK;
+}
+
+extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp || !t) return ORC_EINVAL;
+    Slot &s = *sp;
+    memset(t, 0, sizeof(*t));
+    if (!s.did_kernels) { ctx->err = "no launch recorded on this slot"; return ORC_ESTATE; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(s.stream));
+    auto el = [&](int a, int b, float *dst) -> cudaError_t { return cudaEventElapsedTime(dst, s.ev[a], s.ev[b]); };
+    CK(el(EV_H2D, EV_PACK, &t->pack_ms));
+    CK(el(EV_PACK, EV_SCAN0, &t->scan_ms[0]));
+    CK(el(EV_SCAN0, EV_RES0, &t->resolve_ms[0]));
+    CK(el(EV_RES0, EV_SCAN1, &t->scan_ms[1]));
+    CK(el(EV_SCAN1, EV_RES1, &t->resolve_ms[1]));
+    CK(el(EV_RES1, EV_BIN, &t->bin_ms));
+    CK(el(EV_BIN, EV_EMIT, &t->emit_ms));
+    CK(el(EV_H2D, EV_EMIT, &t->total_ms));
+    if (s.did_h2d) CK(el(EV_START, EV_H2D, &t->h2d_ms));
+    if (s.did_d2h) CK(el(EV_EMIT, EV_END, &t->d2h_ms));
+    // counters need a device read when the caller never downloaded
+    uint32_t counters[8];
+    unsigned long long cells[2];
+    CK(cudaMemcpy(counters, s.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cells, s.d_cells, sizeof(cells), cudaMemcpyDeviceToHost));
+    uint64_t emit_bytes = 0;
+    CK(cudaMemcpy(&emit_bytes, s.d_bin_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 3u + (s.has_names ? 1u : 0u)) : 1u;
+    for (int r = 0; r < ctx->n_rounds; r++) {
+        t->n_tasks[r] = counters[2 + r];
+        const RoundTable &T = ctx->h_tab[r];
+        // algorithmic cells: pairs * m * n summed over the reads entering the round
+        uint64_t msum = 0;
+        for (int a = 0; a < T.n_adapters; a++) msum += (uint64_t)T.m[a];
+        const uint64_t bases = (r == 0) ? s.in_bases : (uint64_t)cells[1];
+        t->cells[r] = (T.revcomp ? 2ull : 1ull) * msum * bases;
+    }
+    t->pack_bytes = s.n_bytes + s.n_bytes / 2;
+    t->emit_bytes = 2 * emit_bytes;    // every FASTQ byte is read once and written once
+    return ORC_OK;
+}
+
+extern "C" int orc_counts(orc_ctx *ctx, uint64_t *bins)
+{
+    if (!ctx || !bins) return ORC_EINVAL;
+    memcpy(bins, ctx->total_counts.data(), sizeof(uint64_t) * (size_t)ctx->n_bins);
+    return ORC_OK;
+}
+
+extern "C" void *orc_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+extern "C" void orc_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int orc_timer_start(orc_ctx *ctx, int slot)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(sp->ev[EV_T0], sp->stream));
+    return ORC_OK;
+}
+
+extern "C" int orc_timer_stop(orc_ctx *ctx, int slot, float *ms)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp || !ms) return ORC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(sp->ev[EV_T1], sp->stream));
+    CK(cudaEventSynchronize(sp->ev[EV_T1]));
+    CK(cudaEventElapsedTime(ms, sp->ev[EV_T0], sp->ev[EV_T1]));
+    return ORC_OK;
+}
+
+extern "C" double orc_measure_int32_peak(int device, int mode, double *sm_clock_mhz)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(uint32_t)) != cudaSuccess) return -1.0;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(a);
+        if (mode == 0) int32_peak_kernel<0><<<blocks, threads>>>(d, iters, 12345u + rep);
+        else int32_peak_kernel<1><<<blocks, threads>>>(d, iters, 12345u + rep);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { best = -1.f; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    if (best <= 0) return -1.0;
+    if (sm_clock_mhz) *sm_clock_mhz = prop.clockRate / 1000.0;
+    const double ops = (double)blocks * threads * (double)iters * 64.0;   // 8 unrolled x 8 ops
+    return ops / (best * 1e-3);
+}

@@ -1,0 +1,415 @@
+// orc_kernels.cuh -- the sm_100a kernels of the demultiplexer (included by orc_api.cu).
+//
+//   pack_kernel        ASCII bases -> 4-bit codes, flat (code index == byte index).  HBM-bound.
+//   init_views_kernel  view 0 of every read = the whole read, forward.
+//   scan_kernel        one warp per read, one lane per (adapter, orientation) pair:
+//                      Myers/Hyyro bit-parallel semi-global scan (orc_core.cuh scan_lane),
+//                      index table (Peq) staged in shared memory, candidate pairs appended
+//                      to a task list with a warp ballot.  INT32-ALU-bound: this is the
+//                      kernel the roofline in bench.py is about.
+//   resolve_kernel     one thread per candidate pair: cutadapt's exact recurrence on the
+//                      band of diagonals around the candidates (orc_core.cuh resolve_pair).
+//   select_kernel      best of the adapters, --rc choice, trim -> next view, bin id.
+//   bin_count/scan/place, emit_kernel
+//                      stable multi-way partition of the trimmed reads into their
+//                      SP5 x SP27 bins and assembly of the FASTQ records.  HBM-bound.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orc_core.cuh"
+
+namespace orc {
+
+constexpr int GUARD_WORDS = 4;         // zero words before and after the code array
+constexpr int SCAN_THREADS = 128;
+constexpr int BIN_CHUNK = 256;         // reads per warp in the partition kernels
+constexpr int MAX_BINS = (MAX_AD + 1) * (MAX_AD + 1);
+
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t *__restrict__ seq, uint32_t *__restrict__ codes, uint64_t n16,
+            const uint8_t *__restrict__ lut_g)
+{
+    __shared__ uint8_t lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+    __syncthreads();
+    const uint4 *in = reinterpret_cast<const uint4 *>(seq);
+    uint2 *out = reinterpret_cast<uint2 *>(codes);
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n16;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = in[g];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t r[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const uint32_t byte = (w[2 * h + (b >> 2)] >> (8 * (b & 3))) & 0xffu;
+                acc |= (uint32_t)lut[byte] << (4 * b);
+            }
+            r[h] = acc;
+        }
+        out[g] = make_uint2(r[0], r[1]);
+    }
+}
+
+__global__ void init_views_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ lengths,
+                                  uint32_t n_reads, View *__restrict__ views)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    View v;
+    v.lo = offsets[r];
+    v.len = lengths[r];
+    v.rc = 0;
+    views[r] = v;
+}
+
+// ------------------------------------------------------------------------------------
+// scan: persistent warps pull reads from a global counter (reads differ in length).
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
+            const View *__restrict__ views, const Match *__restrict__ prev, uint32_t n_reads,
+            Task *__restrict__ tasks, uint32_t *__restrict__ task_count,
+            uint32_t *__restrict__ read_mask, uint32_t *__restrict__ read_base,
+            uint32_t *__restrict__ work_counter)
+{
+    __shared__ __align__(16) RoundTable T;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int na = T.n_adapters;
+    const bool lane_used = lane < T.n_lanes;
+    const int a = lane_used ? lane % na : 0;
+    const int dir = lane_used ? lane / na : 0;
+    const int m = T.m[a], k = T.k[a], min_ov = T.min_ov[a], type = T.type;
+    const uint64_t pv0 = T.pv0[lane_used ? lane : 0];
+    const int d0 = T.d0[lane_used ? lane : 0];
+    const uint8_t *kmax = T.kmax[a];
+    const char *peq_base = reinterpret_cast<const char *>(&T.peq[0][0]);
+
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(work_counter, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= n_reads) break;
+        uint32_t mask = 0, base = 0;
+        const bool skip = prev != nullptr && prev[r].adapter < 0;   // "unknown" never enters round 2
+        if (!skip) {
+            const View v = views[r];
+            const bool active = lane_used && (T.revcomp || ((dir ^ (int)(v.rc & 1u)) == 0));
+            ScanHull h;
+            h.jf = 1; h.jl = 0; h.i1 = 1; h.i2 = 0;
+            if (active)
+                scan_lane(W, v.lo, v.len, dir, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, h);
+            const bool has = active && (h.jf <= h.jl || h.i1 <= h.i2);
+            mask = __ballot_sync(0xffffffffu, has);
+            if (mask) {
+                if (lane == 0) base = atomicAdd(task_count, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (has) {
+                    Task t;
+                    t.read = r; t.lane = (uint32_t)lane;
+                    t.jf = h.jf; t.jl = h.jl; t.i1 = h.i1; t.i2 = h.i2;
+                    t.pad_[0] = t.pad_[1] = 0;
+                    tasks[base + __popc(mask & lanemask_lt())] = t;
+                }
+            }
+        }
+        if (lane == 0) { read_mask[r] = mask; read_base[r] = base; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
+               const View *__restrict__ views, const Task *__restrict__ tasks,
+               const uint32_t *__restrict__ task_count, PairResult *__restrict__ results)
+{
+    __shared__ __align__(16) RoundTable T;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t n = *task_count;
+    Cell col[MAX_M + 1];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const Task task = tasks[t];
+        const View v = views[task.read];
+        PairResult res;
+        res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = 0;
+        res.score = res.errors = 0; res.pad_ = 0;
+        resolve_pair(W, v, T, task, res, col);
+        results[t] = res;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// select: also derives, after the last round, the bin id and the FASTQ record size.
+struct SelectArgs {
+    const RoundTable *tab;
+    const View *views_in;
+    View *views_out;
+    const Match *prev;          // matches of the previous round (nullptr in round 1)
+    Match *out;
+    const uint32_t *read_mask, *read_base;
+    const PairResult *results;
+    uint32_t n_reads;
+    // last round only:
+    int last_round, round_index, n_ad0;
+    const Match *match0;        // round-1 matches (== out when n_rounds == 1)
+    const uint8_t *drop_bins;
+    const uint64_t *name_offsets;   // may be nullptr (no FASTQ emission)
+    int32_t *bin;
+    uint32_t *out_len, *rec_bytes;
+    unsigned long long *next_bases;   // sum of the view lengths that enter the next round (or nullptr)
+};
+
+__global__ void __launch_bounds__(128) select_kernel(SelectArgs A)
+{
+    __shared__ __align__(16) RoundTable T;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = r < A.n_reads;
+    View v;
+    v.lo = 0; v.len = 0; v.rc = 0;
+    if (valid) v = A.views_in[r];
+    Match mt;
+    View next = v;
+    if (!valid || (A.prev != nullptr && A.prev[r].adapter < 0)) {
+        mt.adapter = -1; mt.is_rc = 0;
+        mt.ref_start = mt.ref_stop = mt.query_start = mt.query_stop = mt.score = mt.errors = 0;
+    } else {
+        select_read(T, v, A.read_mask[r], A.results + A.read_base[r], mt, next);
+    }
+    if (A.next_bases != nullptr) {
+        const uint32_t add = (valid && mt.adapter >= 0) ? next.len : 0u;
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, add);
+        if ((threadIdx.x & 31) == 0 && sum) atomicAdd(A.next_bases, (unsigned long long)sum);
+    }
+    if (!valid) return;
+    A.out[r] = mt;
+    A.views_out[r] = next;
+    if (A.last_round) {
+        int b;
+        if (A.round_index == 0) b = mt.adapter + 1;
+        else b = (A.match0[r].adapter + 1) + (A.n_ad0 + 1) * (mt.adapter + 1);
+        if (A.drop_bins[b]) b = -1;
+        A.bin[r] = b;
+        A.out_len[r] = next.len;
+        uint32_t rb = 0;
+        if (b >= 0 && A.name_offsets != nullptr) {
+            const uint32_t nl = (uint32_t)(A.name_offsets[r + 1] - A.name_offsets[r]);
+            rb = 1u + nl + 3u * (next.rc >> 8) + 1u + next.len + 3u + next.len + 1u;   // @name[ rc]*\nSEQ\n+\nQUAL\n
+        }
+        A.rec_bytes[r] = rb;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Stable multi-way partition.  Chunk c = reads [c*BIN_CHUNK, (c+1)*BIN_CHUNK), one warp.
+// hist layout: [bin][chunk] so that the scan over chunks is contiguous.
+__global__ void __launch_bounds__(128)
+bin_count_kernel(const int32_t *__restrict__ bin, const uint32_t *__restrict__ rec_bytes, uint32_t n_reads,
+                 int n_bins, uint32_t n_chunks, uint32_t *__restrict__ hist_cnt, uint64_t *__restrict__ hist_bytes)
+{
+    __shared__ uint32_t s_cnt[4][MAX_BINS];
+    __shared__ unsigned long long s_bytes[4][MAX_BINS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t chunk = blockIdx.x * 4 + w;
+    for (int b = lane; b < n_bins; b += 32) { s_cnt[w][b] = 0; s_bytes[w][b] = 0; }
+    __syncwarp();
+    if (chunk < n_chunks) {
+        const uint32_t r0 = chunk * BIN_CHUNK;
+        for (int it = 0; it < BIN_CHUNK / 32; it++) {
+            const uint32_t r = r0 + it * 32 + lane;
+            if (r < n_reads) {
+                const int b = bin[r];
+                if (b >= 0) {
+                    atomicAdd(&s_cnt[w][b], 1u);
+                    atomicAdd(&s_bytes[w][b], (unsigned long long)rec_bytes[r]);
+                }
+            }
+        }
+        __syncwarp();
+        for (int b = lane; b < n_bins; b += 32) {
+            hist_cnt[(size_t)b * n_chunks + chunk] = s_cnt[w][b];
+            hist_bytes[(size_t)b * n_chunks + chunk] = s_bytes[w][b];
+        }
+    }
+}
+
+// One block.  Exclusive scan over the chunks of every bin (in place), then over the bins.
+__global__ void __launch_bounds__(1024)
+bin_scan_kernel(int n_bins, uint32_t n_chunks, uint32_t *__restrict__ hist_cnt, uint64_t *__restrict__ hist_bytes,
+                uint64_t *__restrict__ bin_counts, uint64_t *__restrict__ bin_offsets)
+{
+    __shared__ unsigned long long s_tot_bytes[MAX_BINS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int b = w; b < n_bins; b += nw) {
+        uint32_t run_c = 0;
+        unsigned long long run_b = 0;
+        for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            uint32_t vc = c < n_chunks ? hist_cnt[(size_t)b * n_chunks + c] : 0u;
+            unsigned long long vb = c < n_chunks ? hist_bytes[(size_t)b * n_chunks + c] : 0ull;
+            uint32_t ic = vc;
+            unsigned long long ib = vb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d);
+                const unsigned long long tb = __shfl_up_sync(0xffffffffu, ib, d);
+                if (lane >= d) { ic += tc; ib += tb; }
+            }
+            if (c < n_chunks) {
+                hist_cnt[(size_t)b * n_chunks + c] = run_c + ic - vc;
+                hist_bytes[(size_t)b * n_chunks + c] = run_b + ib - vb;
+            }
+            run_c += __shfl_sync(0xffffffffu, ic, 31);
+            run_b += __shfl_sync(0xffffffffu, ib, 31);
+        }
+        if (lane == 0) { bin_counts[b] = run_c; s_tot_bytes[b] = run_b; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int b = 0; b < n_bins; b++) { bin_offsets[b] = acc; acc += s_tot_bytes[b]; }
+        bin_offsets[n_bins] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+bin_place_kernel(const int32_t *__restrict__ bin, const uint32_t *__restrict__ rec_bytes, uint32_t n_reads,
+                 int n_bins, uint32_t n_chunks, const uint64_t *__restrict__ hist_bytes,
+                 const uint64_t *__restrict__ bin_offsets, uint64_t *__restrict__ dest)
+{
+    __shared__ unsigned long long s_cur[4][MAX_BINS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t chunk = blockIdx.x * 4 + w;
+    if (chunk >= n_chunks) return;
+    for (int b = lane; b < n_bins; b += 32)
+        s_cur[w][b] = bin_offsets[b] + hist_bytes[(size_t)b * n_chunks + chunk];
+    __syncwarp();
+    const uint32_t r0 = chunk * BIN_CHUNK;
+    for (int it = 0; it < BIN_CHUNK / 32; it++) {
+        const uint32_t r = r0 + it * 32 + lane;
+        const int b = r < n_reads ? bin[r] : -1;
+        const unsigned long long nb = (b >= 0) ? rec_bytes[r] : 0ull;
+        unsigned long long d = ~0ull;
+        // input order inside a bin: lanes take their slot one after the other
+        for (int l = 0; l < 32; l++) {
+            if (lane == l && b >= 0) { d = s_cur[w][b]; s_cur[w][b] = d + nb; }
+            __syncwarp();
+        }
+        if (r < n_reads) dest[r] = d;
+    }
+}
+
+// One warp per read: '@' name [' rc']* '\n' seq '\n' '+' '\n' qual '\n'
+__global__ void __launch_bounds__(256)
+emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
+            const uint8_t *__restrict__ names, const uint64_t *__restrict__ name_offsets,
+            const View *__restrict__ views, const uint64_t *__restrict__ dest, uint32_t n_reads,
+            const uint8_t *__restrict__ comp_lut_g, uint8_t *__restrict__ out)
+{
+    __shared__ uint8_t comp[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) comp[i] = comp_lut_g[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < n_reads; r += n_warps) {
+        const uint64_t d = dest[r];
+        if (d == ~0ull) continue;
+        const View v = views[r];
+        const uint64_t n0 = name_offsets[r];
+        const uint32_t nl = (uint32_t)(name_offsets[r + 1] - n0);
+        const uint32_t nrc = v.rc >> 8;
+        const uint32_t L = v.len;
+        uint8_t *o = out + d;
+        if (lane == 0) o[0] = '@';
+        for (uint32_t i = lane; i < nl; i += 32) o[1 + i] = names[n0 + i];
+        o += 1 + nl;
+        for (uint32_t i = lane; i < 3 * nrc; i += 32) o[i] = (i % 3 == 0) ? ' ' : (i % 3 == 1) ? 'r' : 'c';
+        o += 3 * nrc;
+        if (lane == 0) o[0] = '\n';
+        o += 1;
+        const uint8_t *s = seq + v.lo, *q = qual + v.lo;
+        if (v.rc & 1u) {
+            for (uint32_t i = lane; i < L; i += 32) {
+                o[i] = comp[s[L - 1 - i]];
+                o[L + 3 + i] = q[L - 1 - i];
+            }
+        } else {
+            for (uint32_t i = lane; i < L; i += 32) {
+                o[i] = s[i];
+                o[L + 3 + i] = q[i];
+            }
+        }
+        if (lane == 0) { o[L] = '\n'; o[L + 1] = '+'; o[L + 2] = '\n'; o[2 * L + 3] = '\n'; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// INT32 issue-rate micro-benchmark (roofline denominator of the scan kernel): 8 independent
+// chains per thread.  MODE 0: LOP3 only (ALU pipe).  MODE 1: 4 LOP3 + 4 IMAD (ALU + FMA pipes).
+template <int MODE>
+__global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t x0 = seed + threadIdx.x, x1 = x0 * 3u, x2 = x0 * 5u, x3 = x0 * 7u;
+    uint32_t x4 = x0 * 11u, x5 = x0 * 13u, x6 = x0 * 17u, x7 = x0 * 19u;
+    const uint32_t y = seed ^ 0x9e3779b9u, z = seed * 0x85ebca6bu + 1u;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (MODE == 0) {
+                asm volatile(
+                    "lop3.b32 %0, %0, %8, %9, 0x96;\n\t"
+                    "lop3.b32 %1, %1, %8, %9, 0x96;\n\t"
+                    "lop3.b32 %2, %2, %8, %9, 0x96;\n\t"
+                    "lop3.b32 %3, %3, %8, %9, 0x96;\n\t"
+                    "lop3.b32 %4, %4, %8, %9, 0x96;\n\t"
+                    "lop3.b32 %5, %5, %8, %9, 0x96;\n\t"
+                    "lop3.b32 %6, %6, %8, %9, 0x96;\n\t"
+                    "lop3.b32 %7, %7, %8, %9, 0x96;\n\t"
+                    : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7)
+                    : "r"(y), "r"(z));
+            } else {
+                asm volatile(
+                    "lop3.b32 %0, %0, %8, %9, 0x96;\n\t"
+                    "mad.lo.u32 %4, %4, %8, %9;\n\t"
+                    "lop3.b32 %1, %1, %8, %9, 0x96;\n\t"
+                    "mad.lo.u32 %5, %5, %8, %9;\n\t"
+                    "lop3.b32 %2, %2, %8, %9, 0x96;\n\t"
+                    "mad.lo.u32 %6, %6, %8, %9;\n\t"
+                    "lop3.b32 %3, %3, %8, %9, 0x96;\n\t"
+                    "mad.lo.u32 %7, %7, %8, %9;\n\t"
+                    : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7)
+                    : "r"(y), "r"(z));
+            }
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
+
+}  // namespace orc
