@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the two-round SP5 x SP27 demultiplex (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (B200, liborcdemux.so)
+    python bench.py --impl reference [...]                       the reference's CPU path
+
+A "step" is one pass of the whole hot path (pack, round-1 scan/resolve/select, round-2
+scan/resolve/select, bin partition, FASTQ emit) over one batch of synthetic reads.  At N=1
+the workload is BASELINE configs[1]: 1 Mi synthetic COI-length reads (300-900 nt, seed 1002),
+full two-round demux + trim.  With N>1 (torchrun, one rank per GPU) every rank runs its own
+shard of the same size (weak scaling, seeds (1005<<32)+rank as in SURVEY 8d config 5); the
+only collective is the final per-bin count gather (all_reduce of n_bins counters).
+
+`value`   reads/s with the batch resident in HBM (kernels only), CUDA events on the library's
+          stream, max over ranks.
+`e2e`     the same metric through the C ABI with host buffers: every step copies the inputs
+          from pinned host memory and the results (FASTQ text, bins, matches) back.
+`roofline` for the dominant kernel (the bit-parallel scan): algorithmic DP cells per second
+          against the INT32 ALU-pipe peak measured on this GPU by orc_measure_int32_peak().
+`cpu_baseline` / `--impl reference`: the reference's own implementation of this path is
+          cutadapt 4.9, which is neither vendored in the reference nor installable here, so the
+          CPU arm is the oracle's C restatement of it ("port"), all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "nanopore-barcoding-orc_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "reads/sec demuxed (2-round SP5xSP27)"
+UNIT = "reads/s"
+# ALU-pipe instructions per DP column of one (read, adapter, orientation) pair in
+# scan_kernel's inner loop, counted in the SASS (profiles/README.md); a column is m cells.
+SCAN_ALU_INSTR_PER_COLUMN = 24.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1 << 20)
+    ap.add_argument("--len-min", type=int, default=300)
+    ap.add_argument("--len-max", type=int, default=900)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cpu_arm(rs, n_sample, threads, steps, warmup):
+    """Time the oracle's C restatement of cutadapt on the first n_sample reads."""
+    import oracle
+    from orcdemux import m13
+    sub_n = min(n_sample, rs.n_reads)
+    end = int(rs.offsets[sub_n - 1] + rs.lengths[sub_n - 1]) if sub_n else 0
+    seq, qual = rs.seq[:end], rs.qual[:end]
+    off, ln = rs.offsets[:sub_n], rs.lengths[:sub_n]
+    sets = [(oracle.AdapterSet([q for _, q in m13.sp5_forward()], oracle.FRONT, 0.1, 3), 1),
+            (oracle.AdapterSet([q for _, q in m13.sp27_reverse_rc()], oracle.BACK, 0.1, 3), 1)]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.demux_batch(sets, seq, qual, off, ln, n_threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sub_n, times
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(args.gpus, world)
+    ncpu = os.cpu_count() or 1
+
+    from orcdemux import synth
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import oracle
+        oracle.build()
+        threads = ncpu
+        n_sample = args.cpu_sample or 16384
+        rs = synth.generate(n_sample, args.len_min, args.len_max, seed=1002, workers=min(8, ncpu))
+        warm = min(args.warmup, 1)
+        sub_n, times = cpu_arm(rs, n_sample, threads, args.steps, warm)
+        ms = 1e3 * float(np.mean(times))
+        val = sub_n / float(np.mean(times))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "configs[1]: two-round SP5->SP27 demux + trim, synthetic COI reads %d-%d nt, "
+                                   "seed 1002; each step = the first %d reads of the 1 Mi-read workload"
+                                   % (args.len_min, args.len_max, sub_n),
+                       "reads_per_step": sub_n, "note": "cutadapt 4.9 is not vendored in the reference and not "
+                       "installable here: this arm is the restated-cutadapt CPU baseline (oracle/cutadapt_oracle.c, "
+                       "Ukkonen-banded DP, pthreads), not upstream cutadapt"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "first %d reads of the workload, %d timed passes" % (sub_n, args.steps)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from orcdemux import engine as E
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: bench.py has no CPU fallback for the product arm"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    seed = 1002 if world == 1 else (1005 << 32) + rank
+    workers = max(1, min(16, ncpu // max(world, 1)))
+    t0 = time.perf_counter()
+    rs = synth.generate(args.reads, args.len_min, args.len_max, seed=seed, workers=workers)
+    gen_s = time.perf_counter() - t0
+    rs = E.pin_readset(rs)
+    n_bytes = int(rs.seq.shape[0])
+    n_slots = 1 if args.no_e2e else 3
+    eng = E.Engine(E.m13_rounds(), device=local_rank, max_reads=rs.n_reads, max_bytes=n_bytes,
+                   max_name_bytes=int(rs.names.shape[0]) + 64, n_slots=n_slots, emit_fastq=True, want_matches=True)
+
+    # ---- device-resident: `value`
+    eng.upload(0, rs)
+    eng.sync(0)
+    for _ in range(args.warmup):
+        eng.launch(0)
+    eng.sync(0)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    eng.timer_start(0)
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.launch(0)
+    dev_ms = eng.timer_stop(0)          # device time of exactly K steps on the library's stream
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    clocks = sampler.stop()
+    t = eng.timings(0)                  # stage split of the last step
+    cells = float(sum(t["cells"]))
+    scan_ms = float(sum(t["scan_ms"]))
+    stage = {"pack_ms": t["pack_ms"], "scan_ms": t["scan_ms"], "resolve_ms": t["resolve_ms"],
+             "bin_ms": t["bin_ms"], "emit_ms": t["emit_ms"], "total_ms": t["total_ms"], "n_tasks": t["n_tasks"]}
+    launches = int(t["kernel_launches"]) * args.steps
+
+    tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    max_ms = float(tm.item())
+    value = (args.reads * world * args.steps) / (max_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: `e2e`
+    e2e = None
+    if not args.no_e2e:
+        h2d = int(rs.seq.nbytes + rs.qual.nbytes + rs.offsets.nbytes + rs.lengths.nbytes + rs.names.nbytes +
+                  rs.name_offsets.nbytes)
+        for s in range(min(2, n_slots)):            # warm the copy paths
+            eng.submit(s, rs)
+        d2h = 0
+        for s in range(min(2, n_slots)):
+            r = eng.wait(s, copy=False)
+            d2h = int(r.fastq.nbytes + r.bin.nbytes + r.out_len.nbytes + r.bin_counts.nbytes +
+                      r.bin_offsets.nbytes + sum(m.nbytes for m in r.matches))
+        barrier()
+        w0 = time.perf_counter()
+        inflight = []
+        done = 0
+        checksum = 0
+        for i in range(args.steps):
+            s = i % n_slots
+            if len(inflight) == n_slots:
+                r = eng.wait(inflight.pop(0), copy=False)
+                checksum += int(r.bin_counts.sum())
+                done += 1
+            eng.submit(s, rs)
+            inflight.append(s)
+        while inflight:
+            r = eng.wait(inflight.pop(0), copy=False)
+            checksum += int(r.bin_counts.sum())
+            done += 1
+        barrier()
+        e2e_s = time.perf_counter() - w0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert done == args.steps and checksum == args.steps * args.reads
+        e2e = {"value": (args.reads * world * args.steps) / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "note": "%d batches in flight on %d streams; timed with the host clock between device syncs "
+                       "because the region includes host-side calls" % (n_slots, n_slots)}
+
+    # ---- the only collective: per-bin count gather
+    counts = torch.from_numpy(eng.counts().astype(np.int64)).cuda()
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    total_reads_binned = int(counts.sum().item())
+
+    # ---- roofline of the dominant kernel
+    roofline = None
+    cpu_baseline = None
+    extra = {}
+    if rank == 0:
+        alu_peak, sm_clk = E.measure_int32_peak(local_rank, 0)
+        mix_peak, _ = E.measure_int32_peak(local_rank, 1)
+        m_rows = 59.0
+        peak_gcups = alu_peak / SCAN_ALU_INSTR_PER_COLUMN * m_rows / 1e9
+        ach_gcups = cells / (scan_ms * 1e-3) / 1e9
+        roofline = {"bound": "int32_alu", "kernel": "scan_kernel (2 launches per step: round 1, round 2)",
+                    "achieved": ach_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": ach_gcups / peak_gcups,
+                    "traffic": None,
+                    "peak_how": "measured LOP3 issue rate %.3g lane-op/s (orc_measure_int32_peak mode 0, this GPU, "
+                                "this run) / %.0f ALU-pipe instr per column x %d rows; LOP3+IMAD mix: %.3g" %
+                                (alu_peak, SCAN_ALU_INSTR_PER_COLUMN, int(m_rows), mix_peak),
+                    "cells_per_launch_pair": cells, "scan_ms": scan_ms}
+        hbm, how = hbm_peak()
+        extra["roofline_hbm"] = [
+            {"kernel": "pack_kernel", "bound": "hbm", "achieved": t["pack_bytes"] / (t["pack_ms"] * 1e-3) / 1e9,
+             "peak": hbm, "unit": "GB/s", "frac": t["pack_bytes"] / (t["pack_ms"] * 1e-3) / 1e9 / hbm,
+             "peak_how": "of " + how},
+            {"kernel": "emit_kernel", "bound": "hbm", "achieved": t["emit_bytes"] / (t["emit_ms"] * 1e-3) / 1e9,
+             "peak": hbm, "unit": "GB/s", "frac": t["emit_bytes"] / (t["emit_ms"] * 1e-3) / 1e9 / hbm,
+             "peak_how": "of " + how}]
+        extra["gcups"] = cells * args.steps * world / (max_ms * 1e-3) / 1e9 if world == 1 else None
+    eng.close()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        oracle.build()
+        n_s = args.cpu_sample or 16384
+        sub_n, times = cpu_arm(rs, n_s, ncpu, 1, 0)
+        cpu_baseline = {"value": sub_n / times[0], "unit": UNIT, "cores": ncpu, "kind": "port",
+                        "sample": "first %d reads of the workload, one pass, %d threads (restated-cutadapt CPU "
+                                  "baseline, not upstream cutadapt)" % (sub_n, ncpu)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "configs[1]: full two-round SP5->SP27 combinatorial demux + trim on %d synthetic "
+                                   "COI-length reads (%d-%d nt) per GPU, -e 0.1 -O 3 --rc, 12+12 M13 indices"
+                                   % (args.reads, args.len_min, args.len_max),
+                       "reads_per_gpu": args.reads, "seed": seed, "l2": "inputs larger than L2 (%.2f GB resident "
+                       "per step)" % (2.5 * n_bytes / 1e9), "parallelism": "reads sharded by batch, no data-path "
+                       "collective; all_reduce of %d bin counters at the end" % int(counts.numel())},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "stages_ms_last_step": stage, "wall_ms_per_step": wall_ms / args.steps,
+            "reads_binned_all_ranks": total_reads_binned, "gen_s": gen_s,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

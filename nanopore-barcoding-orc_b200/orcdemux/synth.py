@@ -135,9 +135,14 @@ def _chunk(seed: int, chunk: int, first: int, n: int, len_min: int, len_max: int
     return seq, qual, lens.astype(np.uint32), names, truth
 
 
+def _chunk_star(args):
+    return _chunk(*args)
+
+
 def generate(n_reads: int, len_min: int = 300, len_max: int = 900, seed: int = 1002,
-             anchored: bool = False) -> ReadSet:
-    """SURVEY 8(d) read model.  anchored=True builds BASELINE config 4 inputs (bare index at offset 0)."""
+             anchored: bool = False, workers: int = 1) -> ReadSet:
+    """SURVEY 8(d) read model.  anchored=True builds BASELINE config 4 inputs (bare index at offset 0).
+    workers > 1 generates the chunks in a process pool (same bytes as workers == 1)."""
     if anchored:
         front = _codes([s for _, s in m13.variable_all()])
         back = np.zeros((1, 0), dtype=np.uint8)                  # no 3' adapter
@@ -145,15 +150,22 @@ def generate(n_reads: int, len_min: int = 300, len_max: int = 900, seed: int = 1
         front = _codes([s for _, s in m13.sp5_forward()])
         back = _codes([s for _, s in m13.sp27_reverse_rc()])
     seqs, quals, lens, names, truths = [], [], [], [], []
+    jobs = []
     first = 0
     c = 0
     while first < n_reads:
         n = min(CHUNK, n_reads - first)
-        s, q, l, nm, t = _chunk(seed, c, first, n, len_min, len_max, front, back,
-                                anchored_index=True if anchored else None)
-        seqs.append(s); quals.append(q); lens.append(l); names.extend(nm); truths.append(t)
+        jobs.append((seed, c, first, n, len_min, len_max, front, back, True if anchored else None))
         first += n
         c += 1
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            parts = pool.map(_chunk_star, jobs)
+    else:
+        parts = [_chunk(*j) for j in jobs]
+    for s, q, l, nm, t in parts:
+        seqs.append(s); quals.append(q); lens.append(l); names.extend(nm); truths.append(t)
     seq = np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)
     qual = np.concatenate(quals) if quals else np.zeros(0, np.uint8)
     lengths = np.concatenate(lens) if lens else np.zeros(0, np.uint32)

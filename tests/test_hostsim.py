@@ -1,0 +1,133 @@
+"""The device arithmetic (csrc/orc_core.cuh: bit-parallel scan -> candidate hull -> banded
+exact DP -> selection), compiled for the host by tests/hostsim.cpp, against the oracle.
+This is how the exactness of the kernels' algorithm is checked without a GPU; the `-m gpu`
+tests repeat the comparison through the real kernels and the C ABI."""
+import random
+
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle
+from orcdemux import m13, synth
+
+
+def _compare(rounds, rs, threads=8):
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=threads)
+    m0, m1, lo, ln, rc, nt = H.run_hostsim(rounds, rs)
+    idx, nbad = H.diff_matches(rec0, m0)
+    assert nbad == 0, ("round 1", idx, [rs.read(int(i))[1] for i in idx[:1]])
+    if len(rounds) > 1:
+        idx, nbad = H.diff_matches(rec1, m1)
+        assert nbad == 0, ("round 2", idx)
+    assert np.array_equal(olen, ln)
+    vb = H.view_bytes(rs, lo, ln, rc)
+    for i in range(rs.n_reads):
+        o, L = int(rs.offsets[i]), int(olen[i])
+        assert vb[i][0] == oseq[o:o + L].tobytes() and vb[i][1] == oqual[o:o + L].tobytes(), i
+    return rec0, rec1
+
+
+def test_synthetic_coi():
+    _compare(H.m13_rounds(), synth.generate(6000, 300, 900, seed=1002))
+
+
+def test_synthetic_rrna():
+    _compare(H.m13_rounds(), synth.generate(500, 1000, 3500, seed=1003))
+
+
+def test_no_rc_and_other_thresholds():
+    rs = synth.generate(1500, 300, 600, seed=5)
+    for e, ov, rc in [(0.1, 3, 0), (0.2, 5, 1), (0.0, 3, 1), (0.05, 10, 1), (0.15, 1, 1), (3, 3, 1)]:
+        _compare(H.m13_rounds(e, ov, rc), rs)
+
+
+def _adversarial_reads(rnd, adapters_f, adapters_b, n):
+    recs = []
+    comp = str.maketrans("ACGT", "TGCA")
+    for i in range(n):
+        kind = rnd.randrange(12)
+        L = rnd.randint(0, 260)
+        body = "".join(rnd.choice("ACGT") for _ in range(L))
+        a = rnd.choice(adapters_f)
+        b = rnd.choice(adapters_b)
+
+        def mutate(s, rate):
+            out = []
+            for c in s:
+                u = rnd.random()
+                if u < rate:
+                    out.append(rnd.choice("ACGT"))
+                elif u < 1.5 * rate:
+                    continue
+                elif u < 2 * rate:
+                    out.append(c); out.append(rnd.choice("ACGT"))
+                else:
+                    out.append(c)
+            return "".join(out)
+        if kind == 0:
+            s = a + body + b
+        elif kind == 1:
+            s = mutate(a, 0.06) + body + mutate(b, 0.06)
+        elif kind == 2:
+            s = a[rnd.randint(0, len(a)):] + body + b[:rnd.randint(0, len(b))]
+        elif kind == 3:
+            s = body[:L // 2] + mutate(a, 0.04) + body[L // 2:] + a + body[:7] + mutate(b, 0.05) + b
+        elif kind == 4:
+            s = rnd.choice("ACGT") * L + a[-rnd.randint(1, 12):]
+        elif kind == 5:
+            s = (a + body + b).translate(comp)[::-1]
+        elif kind == 6:
+            s = mutate(a, 0.12) + body + mutate(b, 0.12)
+        elif kind == 7:
+            s = a[:rnd.randint(1, len(a))] * 2 + body + b[-rnd.randint(1, len(b)):] * 2
+        elif kind == 8:
+            s = body + b[:rnd.randint(0, 14)]
+        elif kind == 9:
+            s = a[-rnd.randint(0, 14):] + body
+        elif kind == 10:
+            s = mutate(a + b, 0.03) * rnd.randint(1, 3)
+        else:
+            s = "".join(rnd.choice("ACGTN") for _ in range(L))
+        if rnd.random() < 0.1:
+            s = s.lower()
+        recs.append(("a%d" % i, s, "".join(chr(33 + rnd.randint(0, 40)) for _ in s)))
+    return synth.from_records(recs)
+
+
+def test_adversarial_m13():
+    rnd = random.Random(99)
+    f = [s for _, s in m13.sp5_forward()]
+    b = [s for _, s in m13.sp27_reverse_rc()]
+    _compare(H.m13_rounds(), _adversarial_reads(rnd, f, b, 4000))
+
+
+def test_random_adapter_sets():
+    rnd = random.Random(123)
+    for trial in range(12):
+        nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
+        mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([3, 8, 17, 20, 33, 57, 64])))
+        shared = mk()[:10]
+        f = [(shared if rnd.random() < 0.5 else "") + mk() for _ in range(nf)]
+        f = [x[:64] for x in f]
+        b = [(mk() + (shared if rnd.random() < 0.5 else ""))[:64] for _ in range(nb)]
+        e = rnd.choice([0.0, 0.1, 0.1, 0.2, 0.3])
+        ov = rnd.choice([1, 3, 3, 5, 8])
+        rc = rnd.choice([0, 1, 1])
+        rounds = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
+        _compare(rounds, _adversarial_reads(rnd, f, b, 400), threads=4)
+
+
+def test_single_round_back_only():
+    rnd = random.Random(5)
+    b = [s for _, s in m13.sp27_reverse_rc()]
+    rs = _adversarial_reads(rnd, b, b, 600)
+    _compare([(b, oracle.BACK, 0.1, 3, 1)], rs)
+
+
+def test_unsupported_is_refused():
+    rs = synth.from_records([("x", "ACGT", "IIII")])
+    with pytest.raises(RuntimeError, match="unsupported"):
+        H.run_hostsim([(["ACGN"], oracle.FRONT, 0.1, 3, 1)], rs)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        H.run_hostsim([(["A" * 65], oracle.FRONT, 0.1, 3, 1)], rs)

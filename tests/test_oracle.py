@@ -1,0 +1,129 @@
+"""The oracle against the known-answer vectors the reference's domain offers.
+
+The reference (a shell pipeline around un-vendored cutadapt 4.9) ships no tests, so parity
+with real cutadapt is UNPINNED; these vectors are (i) the examples of cutadapt's user guide
+for regular 3'/5' adapters, (ii) cases derivable by hand from the published algorithm
+(SURVEY.md 8c), committed as tests/golden/kat.json by tests/golden/make_golden.py.  Three
+independent restatements (C banded, C unpruned, pure-Python full matrix) must agree."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle
+from oracle import pyoracle as P
+from orcdemux import m13, synth
+
+FRONT, BACK, PREFIX, SUFFIX = 11, 14, 8, 2
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "kat.json")
+
+
+def test_golden_locate_vectors():
+    with open(GOLDEN) as fh:
+        kat = json.load(fh)
+    assert len(kat["locate"]) >= 30
+    for v in kat["locate"]:
+        exp = tuple(v["expect"]) if v["expect"] is not None else None
+        args = (v["ref"], v["query"], v["rate"], v["flags"], v["min_overlap"], v.get("indel_cost", 1))
+        assert oracle.locate(*args) == exp, v
+        assert oracle.locate(*args, unpruned=True) == exp, v
+        assert P.locate(*args) == exp, v
+
+
+def test_golden_read_vectors():
+    with open(GOLDEN) as fh:
+        kat = json.load(fh)
+    rounds = H.m13_rounds()
+    names5 = [n for n, _ in m13.sp5_forward()]
+    names27 = [n for n, _ in m13.sp27_reverse_rc()]
+    recs = [(v["name"], v["seq"], "I" * len(v["seq"])) for v in kat["reads"]]
+    rs = synth.from_records(recs)
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=2)
+    for i, v in enumerate(kat["reads"]):
+        got5 = names5[rec0["adapter"][i]] if rec0["adapter"][i] >= 0 else "unknown"
+        got27 = names27[rec1["adapter"][i]] if rec1["adapter"][i] >= 0 else "unknown"
+        assert got5 == v["sp5"], (v["name"], got5)
+        assert got27 == v["sp27"], (v["name"], got27)
+        if "r1" in v:
+            assert [int(rec0[f][i]) for f in H.FIELDS[1:]] == v["r1"], v["name"]
+        if "r2" in v:
+            assert [int(rec1[f][i]) for f in H.FIELDS[1:]] == v["r2"], v["name"]
+        o = int(rs.offsets[i])
+        assert oseq[o:o + int(olen[i])].tobytes().decode() == v["trimmed"], v["name"]
+
+
+def test_user_guide_examples():
+    for q, kept in [("MYSEQUENCEADAPTER", "MYSEQUENCE"), ("MYSEQUENCEADAP", "MYSEQUENCE"),
+                    ("MYSEQUENCEADAPTERSOMETHINGELSE", "MYSEQUENCE"), ("MYSEQUENCEAD", "MYSEQUENCEAD")]:
+        t = oracle.locate("ADAPTER", q, 0.1, BACK, 3)
+        assert (q[:t[2]] if t else q) == kept
+    for q in ["ADAPTERMYSEQUENCE", "DAPTERMYSEQUENCE", "TERMYSEQUENCE", "SOMETHINGADAPTERMYSEQUENCE"]:
+        t = oracle.locate("ADAPTER", q, 0.1, FRONT, 3)
+        assert q[t[3]:] == "MYSEQUENCE"
+
+
+def test_allowed_errors_by_length():
+    # e = 0.1: 0 errors for aligned length 0-9, 1 for 10-19, ... (cutadapt guide, "Error tolerance")
+    ad = "ACGTTGCAAGCTTAGGCATCGATCCGATTAGC"
+    for L in (9, 10, 19, 20, 29, 30):
+        read = "T" * 50 + ad[:L]
+        mut = read[:52] + ("A" if read[52] != "A" else "C") + read[53:]    # one substitution inside
+        t = oracle.locate(ad, mut, 0.1, BACK, 3)
+        if L >= 10:
+            assert t is not None and t[5] == 1 and t[1] == L
+        else:
+            assert t is None or t[5] == 0
+
+
+def test_restatements_agree_random():
+    rnd = random.Random(7)
+    for _ in range(2500):
+        m, n = rnd.randint(3, 30), rnd.randint(0, 70)
+        ref = "".join(rnd.choice("ACGT") for _ in range(m))
+        q = [rnd.choice("ACGT") for _ in range(n)]
+        if n > 5 and rnd.random() < 0.75:
+            p = rnd.randint(-m // 2, n - 1)
+            for i, c in enumerate(ref):
+                if 0 <= p + i < n and rnd.random() < 0.9:
+                    q[p + i] = c
+        q = "".join(q)
+        rate = rnd.choice([0.0, 0.1, 0.2, 0.3, 0.34])
+        flags = rnd.choice([FRONT, BACK, PREFIX, SUFFIX, 15, 10, 6, 9])
+        mo, ic = rnd.randint(1, 5), rnd.choice([1, 1, 1, 100000])
+        a = oracle.locate(ref, q, rate, flags, mo, ic)
+        assert a == oracle.locate(ref, q, rate, flags, mo, ic, unpruned=True) == P.locate(ref, q, rate, flags, mo, ic)
+
+
+def test_round_read_python_vs_c():
+    rs = synth.generate(40, 300, 500, seed=3)
+    rounds = H.m13_rounds()
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=1)
+    ads = [P.Adapter(n, s, P.FRONT) for n, s in m13.sp5_forward()]
+    for r in range(12):
+        name, seq, qual = rs.read(r)
+        idx, is_rc, t, nm, s, q = P.round_read(ads, True, name, seq, qual)
+        assert idx == rec0["adapter"][r] and int(is_rc) == rec0["is_rc"][r]
+        if t is not None:
+            assert list(t) == [int(rec0[f][r]) for f in H.FIELDS[2:]]
+
+
+def test_affix_comparers():
+    assert oracle.affix_compare("AAXAA", "AAAAATTTTTTTTT", 0.9) == (0, 5, 0, 5, 3, 1)
+    assert oracle.affix_compare("AANAA", "AACAATTTTTTTTT", 0.9, wildcard_ref=True) == (0, 5, 0, 5, 5, 0)
+    assert oracle.affix_compare("AAXAA", "TTTTTTTAAAAA", 0.9, suffix=True) == (0, 5, 7, 12, 3, 1)
+    assert oracle.affix_compare("GAGCGTCTAATCGTAAT", "GAGCGTCTTATCGTAATACGT", 0.1, min_overlap=17) == (0, 17, 0, 17, 15, 1)
+    assert oracle.affix_compare("GAGCGTCTAATCGTAAT", "GAGCGTCTTTTCGTAATACGT", 0.1, min_overlap=17) is None
+
+
+def test_synthetic_truth_agreement():
+    rs = synth.generate(3000, 300, 900, seed=11)
+    rec0, rec1, *_ = H.run_oracle(H.m13_rounds(), rs)
+    t = rs.truth
+    has5 = t["sp5"] > 0
+    assert ((rec0["adapter"] + 1 == t["sp5"]) | ~has5).mean() > 0.97
+    both = (rec0["adapter"] + 1 == t["sp5"]) & (t["sp27"] > 0) & has5
+    assert (rec1["adapter"][both] + 1 == t["sp27"][both]).mean() > 0.95
+    assert abs(rec0["is_rc"].mean() - 0.10) < 0.03
