@@ -15,10 +15,11 @@
 //                  of every column and D[i][n] of the last column, and from them the hull
 //                  of the cells that can possibly pass cutadapt's acceptance test
 //                  (R5: last row, R6: last column).  Most pairs have no such cell.
-//  resolve_pair()  For a pair that has candidate cells: cutadapt's own recurrence
-//                  (cost, score, origin per cell, R2/R3, same tie-breaks) restricted to
-//                  the band of diagonals within k of a candidate, then R5/R6/R7 verbatim.
-//                  DESIGN.md section 4 proves this reproduces the unrestricted DP exactly.
+//  resolve_pair()  For a pair that has candidate cells: re-scan the few columns around them
+//                  keeping the vertical deltas, walk cutadapt's own predecessor rule (R3,
+//                  same tie-breaks) back from each candidate that can still win to get its
+//                  (score, origin), then R5/R6/R7 verbatim.  DESIGN.md section 4 argues why
+//                  this reproduces the forward recurrence exactly.
 //  select_read()   R8 (best of the adapters) and R9 (--rc: strictly higher score wins),
 //                  R10 (trim -> the next view of the read).
 #pragma once
@@ -233,96 +234,167 @@ ORC_HD void r6_update(Best &b, int n, const Cell &c, int i, int min_ov, const ui
     }
 }
 
-// One pass of cutadapt's recurrence over the diagonals dlo..dhi (d = j - i).  Cells outside
-// the band count as cost INF.  R5 is evaluated for columns jf..jl, R6 for rows r6lo..r6hi of
-// column n.  col[] is scratch for rows 0..m.  Returns true if R5 hit the early exit.
-ORC_HD bool band_pass(const uint32_t *W, uint64_t lo, uint32_t len, int dir,
-                      const uint8_t *acode, int m, int type, int k, const uint8_t *kmax, int min_ov,
-                      int dlo, int dhi, int jf, int jl, int r6lo, int r6hi, Best &best, Cell *col)
+// The resolver re-runs the bit-parallel scan over the columns that matter for one pair and
+// keeps the vertical deltas (Pv, Mv) and D[m][j] of the last RING columns.  From them any
+// cost D[i][j'] of those columns is a popcount away, which is all that cutadapt's
+// predecessor rule (R3) looks at -- so the path that the forward recurrence would have
+// inherited score and origin along can be walked backwards from a candidate end cell
+// (DESIGN.md section 4).  A scan restarted at column ws > 0 with column costs D[i][ws] = i
+// over-estimates costs, but is exact for every cell whose optimal path starts at a column
+// >= ws, and all cells a candidate's walk looks at are of that kind (ws <= j - m - k - 1).
+constexpr int RING = 128;            // >= m + k + 2 for every supported adapter (k < m <= 64)
+struct ColRing {
+    uint64_t pv[RING], mv[RING];
+    int16_t dm[RING];
+};
+
+ORC_HD int popc64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+// D[i][j] of a stored column j, i in 0..m
+ORC_HD int ring_cost(const ColRing &R, int m, int i, int j)
+{
+    const int sh = 64 - m + i;                      // bits of the rows i+1..m start here
+    if (sh >= 64) return R.dm[j & (RING - 1)];
+    const uint64_t pv = R.pv[j & (RING - 1)] >> sh, mv = R.mv[j & (RING - 1)] >> sh;
+    return (int)R.dm[j & (RING - 1)] - popc64(pv) + popc64(mv);
+}
+
+// Walk cutadapt's path back from cell (i, j) whose cost is d.  ws is the first stored
+// column (the restart column, or 0).  Yields the score and the origin of the cell.
+ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, const uint64_t *peq_lane,
+                       int m, int type, int ws, const ColRing &R, int i, int j, int d,
+                       int &score_out, int &origin_out)
+{
+    int score = 0, origin = 0;
+    for (;;) {
+        if (i == 0) { origin = j; break; }           // row 0: cost 0, score 0, origin = column (R3)
+        if (j == 0) {                                // column 0 (R2): FRONT origin -i, BACK origin 0
+            origin = (type == TYPE_FRONT) ? -i : 0;
+            break;
+        }
+        if (j <= ws) { origin = j; break; }          // unreachable for a genuine candidate
+        const int bit = 64 - m + i - 1;
+        const uint32_t raw = dir ? nib(W, (int64_t)lo + (int64_t)len - j) : nib(W, (int64_t)lo + j - 1);
+        const uint64_t eq = peq_lane[raw * MAX_LANES];
+        if ((eq >> bit) & 1u) {                      // characters equal: diagonal, unconditionally
+            score += 1; --i; --j;
+            continue;
+        }
+        const uint64_t pvj = R.pv[j & (RING - 1)], mvj = R.mv[j & (RING - 1)];
+        const uint64_t pvl = R.pv[(j - 1) & (RING - 1)], mvl = R.mv[(j - 1) & (RING - 1)];
+        const int d_up = d - (int)((pvj >> bit) & 1u) + (int)((mvj >> bit) & 1u);
+        const int d_left = ring_cost(R, m, i, j - 1);
+        const int d_diag = d_left - (int)((pvl >> bit) & 1u) + (int)((mvl >> bit) & 1u);
+        const int c_diag = d_diag + 1, c_del = d_left + 1, c_ins = d_up + 1;
+        if (c_diag <= c_del && c_diag <= c_ins) { score -= 1; --i; --j; d = d_diag; }
+        else if (c_ins <= c_del) { score -= 2; --i; d = d_up; }
+        else { score -= 2; --j; d = d_left; }
+    }
+    score_out = score;
+    origin_out = origin;
+}
+
+// One scan over columns ws+1..we with R5 on the candidate columns jf..jl and, if the scan
+// reaches column n and r6 is set, R6 on the candidate rows.  Returns true on R5's early exit.
+ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, const uint64_t *peq_lane,
+                         int m, int type, int k, const uint8_t *kmax, int min_ov,
+                         int ws, int we, int jf, int jl, bool r6, int r6lo, int r6hi,
+                         Best &best, ColRing &R)
 {
     const int n = (int)len;
-    const int j0 = imax(0, dlo);
-    const bool want_r6 = r6lo <= r6hi;
-    int jend = want_r6 ? n : imin(n, jl);
-    if (j0 == 0) {
-        // R2, column min_n = 0: FRONT (REF_START|QUERY_START): cost 0, origin -i;
-        //                       BACK  (QUERY_START only):       cost i, origin 0
-        const int ia = imax(0, -dhi), ib = imin(m, -dlo);
-        for (int i = ia; i <= ib; i++) {
-            col[i].cost = (type == TYPE_FRONT) ? 0 : i;
-            col[i].score = 0;
-            col[i].origin = (type == TYPE_FRONT) ? -i : 0;
-        }
-    }
-    int j = j0;
-    int ilo = 1, ihi = 0;
-    for (j = j0 + 1; j <= jend; j++) {
-        ilo = imax(1, j - dhi);
-        ihi = imin(m, j - dlo);
-        if (ilo > ihi) break;                       // the band has left the matrix (j - dhi > m)
-        const uint32_t cj = lane_code(W, lo, len, dir, j - 1);
-        Cell dg, up;
-        if (ilo == 1) {                             // row 0: cost 0, score 0, origin = column
-            dg.cost = 0; dg.score = 0; dg.origin = j - 1;
-            up.cost = 0; up.score = 0; up.origin = j;
-        } else {
-            dg = col[ilo - 1];
-            up.cost = INF_COST; up.score = 0; up.origin = 0;
-        }
-        const int left_max = j - 1 - dlo;           // rows that were inside the band in column j-1
-        for (int i = ilo; i <= ihi; i++) {
-            Cell lf;
-            if (i <= left_max) lf = col[i];
-            else { lf.cost = INF_COST; lf.score = 0; lf.origin = 0; }
-            Cell nw;
-            if ((acode[i - 1] & cj) != 0) {         // R3: characters equal -> diagonal, always
-                nw.cost = dg.cost; nw.origin = dg.origin; nw.score = dg.score + 1;
-            } else {
-                const int c_diag = dg.cost + 1, c_del = lf.cost + 1, c_ins = up.cost + 1;
-                if (c_diag <= c_del && c_diag <= c_ins) {
-                    nw.cost = c_diag; nw.origin = dg.origin; nw.score = dg.score - 1;
-                } else if (c_ins <= c_del) {
-                    nw.cost = c_ins; nw.origin = up.origin; nw.score = up.score - 2;
-                } else {
-                    nw.cost = c_del; nw.origin = lf.origin; nw.score = lf.score - 2;
+    const uint64_t pad = (m == 64) ? 0ull : ((1ull << (64 - m)) - 1ull);
+    uint64_t Pv, Mv = 0;
+    int D;
+    if (ws == 0 && type == TYPE_FRONT) { Pv = 0; D = 0; }       // R2, true column 0 of a 5' adapter
+    else { Pv = ~pad; D = m; }                                  // cost i (true for BACK at 0; restart otherwise)
+    R.pv[ws & (RING - 1)] = Pv; R.mv[ws & (RING - 1)] = 0; R.dm[ws & (RING - 1)] = (int16_t)D;
+    int traced_j = -1, traced_score = 0, traced_origin = 0;
+    // Upper bound of a candidate's score: every error costs at least 2 (score <= length - 2*cost),
+    // except the errors a 3' adapter takes in column 0 (cost i, score 0: R2), reachable only if
+    // the scan starts at the true column 0; then only score <= length - cost holds.
+    const int ubw = (ws == 0 && type == TYPE_BACK) ? 1 : 2;
+    for (int j = ws + 1; j <= we; j++) {
+        const uint32_t raw = dir ? nib(W, (int64_t)lo + (int64_t)len - j) : nib(W, (int64_t)lo + j - 1);
+        const uint64_t Eq = peq_lane[raw * MAX_LANES];
+        const uint64_t Xv = Eq | Mv;
+        const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        uint64_t Ph = Mv | ~(Xh | Pv);
+        uint64_t Mh = Pv & Xh;
+        D += (int)(Ph >> 63) - (int)(Mh >> 63);
+        Ph <<= 1; Mh <<= 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+        R.pv[j & (RING - 1)] = Pv; R.mv[j & (RING - 1)] = Mv; R.dm[j & (RING - 1)] = (int16_t)D;
+        if (j >= jf && j <= jl && D <= k) {
+            const int lmax = imin(m, j + D);
+            if (lmax >= min_ov && D <= (int)kmax[lmax]) {
+                // a candidate that cannot beat the best so far cannot change it (every R5 update
+                // after the first needs a strictly higher score)
+                const int ub = lmax - ubw * D;
+                if (best.cost == m + n + 1 || ub > best.score) {
+                    Cell c;
+                    c.cost = D;
+                    trace_back(W, lo, len, dir, peq_lane, m, type, ws, R, m, j, D, c.score, c.origin);
+                    traced_j = j; traced_score = c.score; traced_origin = c.origin;
+                    if (r5_update(best, m, n, c, j, min_ov, kmax)) return true;
                 }
             }
-            dg = lf;
-            col[i] = nw;
-            up = nw;
-        }
-        if (j >= jf && j <= jl && ihi == m && col[m].cost <= k) {
-            if (r5_update(best, m, n, col[m], j, min_ov, kmax)) return true;
         }
     }
-    if (want_r6 && j == n + 1 && n > j0) {
-        // column n is complete; rows inside the band are ilo..ihi
-        for (int i = imin(r6hi, ihi); i >= imax(r6lo, ilo); i--)
-            r6_update(best, n, col[i], i, min_ov, kmax);
+    if (r6 && we == n && n > ws) {
+        // R6: rows r6hi..r6lo of column n, top row first like cutadapt
+        for (int i = imin(r6hi, m); i >= imax(r6lo, 1); i--) {
+            const int Di = ring_cost(R, m, i, n);
+            if (Di > k) continue;
+            const int lmax = (type == TYPE_FRONT) ? imin(i, n + Di) : i;
+            if (!(lmax >= min_ov && Di <= (int)kmax[lmax])) continue;
+            const int ub = lmax - ubw * Di;
+            if (ub < best.score || (ub == best.score && Di >= best.cost)) continue;
+            Cell c;
+            c.cost = Di;
+            if (i == m && traced_j == n) { c.score = traced_score; c.origin = traced_origin; }
+            else trace_back(W, lo, len, dir, peq_lane, m, type, ws, R, i, n, Di, c.score, c.origin);
+            r6_update(best, n, c, i, min_ov, kmax);
+        }
     }
     return false;
 }
 
 ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, const Task &t,
-                         PairResult &res, Cell *col)
+                         PairResult &res, ColRing &R)
 {
     const int a = (int)t.lane % T.n_adapters;
     const int dir = (int)t.lane / T.n_adapters;
     const int m = T.m[a], k = T.k[a], min_ov = T.min_ov[a];
     const uint8_t *kmax = T.kmax[a];
-    const uint8_t *acode = T.code[a];
+    const uint64_t *peq_lane = &T.peq[0][t.lane];
     const int n = (int)v.len;
     Best best;
     best.ref_stop = m; best.query_stop = n; best.cost = m + n + 1; best.origin = 0; best.score = 0;
     bool broke = false;
-    if (t.jf <= t.jl) {
-        const bool r6 = (T.type == TYPE_FRONT) && (t.jl == n);   // FRONT: only cell (m, n)
-        broke = band_pass(W, v.lo, v.len, dir, acode, m, T.type, k, kmax, min_ov,
-                          t.jf - m - k, t.jl - m + k, t.jf, t.jl, r6 ? m : 1, r6 ? m : 0, best, col);
-    }
-    if (!broke && T.type == TYPE_BACK && t.i1 <= t.i2) {
-        band_pass(W, v.lo, v.len, dir, acode, m, T.type, k, kmax, min_ov,
-                  n - t.i2 - k, n - t.i1 + k, 1, 0, t.i1, t.i2, best, col);
+    const bool has5 = t.jf <= t.jl;
+    const bool has6 = (T.type == TYPE_BACK) ? (t.i1 <= t.i2) : (has5 && t.jl == n);   // FRONT: only cell (m, n)
+    const int r6lo = (T.type == TYPE_BACK) ? t.i1 : m, r6hi = (T.type == TYPE_BACK) ? t.i2 : m;
+    const int ws6 = imax(0, n - r6hi - k - 1);
+    if (has5) {
+        const int ws = imax(0, t.jf - m - k - 1);
+        // run on to column n in the same scan when the last-column cells are close enough
+        const bool join = has6 && (ws6 <= t.jl + 1 || ws == 0 && ws6 == 0);
+        broke = resolve_scan(W, v.lo, v.len, dir, peq_lane, m, T.type, k, kmax, min_ov,
+                             ws, join ? n : t.jl, t.jf, t.jl, join, r6lo, r6hi, best, R);
+        if (!broke && has6 && !join)
+            resolve_scan(W, v.lo, v.len, dir, peq_lane, m, T.type, k, kmax, min_ov,
+                         ws6, n, 1, 0, true, r6lo, r6hi, best, R);
+    } else if (has6) {
+        resolve_scan(W, v.lo, v.len, dir, peq_lane, m, T.type, k, kmax, min_ov,
+                     ws6, n, 1, 0, true, r6lo, r6hi, best, R);
     }
     if (best.cost == m + n + 1) { res.has = 0; return; }
     res.has = 1;
@@ -362,9 +434,13 @@ ORC_HD void select_read(const RoundTable &T, const View &v, uint32_t mask, const
     const int rs = best_a[1] >= 0 ? best_r[1].score : 0;
     const int o = (T.revcomp && rs > fs) ? 1 : 0;          // R9: strictly higher score
     next = v;
+    const uint32_t eff = (v.rc & 1u) ^ (uint32_t)o;
     if (best_a[o] < 0) {
-        out.adapter = -1; out.is_rc = 0;
+        // no match.  o == 1 here means reverse_score 0 > forward_score < 0 (high error rates):
+        // cutadapt then passes on the reverse complement, name + " rc", with no match.
+        out.adapter = -1; out.is_rc = o;
         out.ref_start = out.ref_stop = out.query_start = out.query_stop = out.score = out.errors = 0;
+        next.rc = ((v.rc & ~1u) | eff) + ((uint32_t)o << 8);
         return;
     }
     const PairResult &r = best_r[o];
@@ -378,7 +454,6 @@ ORC_HD void select_read(const RoundTable &T, const View &v, uint32_t mask, const
     if (T.type == TYPE_FRONT) { a0 = (uint32_t)r.query_stop; b0 = n; }
     else { a0 = 0; b0 = (uint32_t)r.query_start; }
     if (b0 < a0) b0 = a0;
-    const uint32_t eff = (v.rc & 1u) ^ (uint32_t)o;
     next.len = b0 - a0;
     next.lo = eff ? v.lo + (n - b0) : v.lo + a0;
     next.rc = ((v.rc & ~1u) | eff) + ((uint32_t)o << 8);

@@ -147,14 +147,14 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     }
     __syncthreads();
     const uint32_t n = *task_count;
-    Cell col[MAX_M + 1];
+    ColRing ring;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const Task task = tasks[t];
         const View v = views[task.read];
         PairResult res;
         res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = 0;
         res.score = res.errors = 0; res.pad_ = 0;
-        resolve_pair(W, v, T, task, res, col);
+        resolve_pair(W, v, T, task, res, ring);
         results[t] = res;
     }
 }

@@ -54,6 +54,7 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         }
         double rate = max_errors;
         if (rate >= 1.0) rate /= m;                 // absolute error count (adapters.py)
+        if (!(rate >= 0.0) || rate >= 1.0) return "unsupported: error rate must be in [0, 1) for every adapter";
         T.k[a] = (int)(rate * m);                   // _align.pyx: k = <int>(max_error_rate * m)
         T.min_ov[a] = min_overlap < m ? min_overlap : m;
         for (int L = 0; L <= m; L++) {

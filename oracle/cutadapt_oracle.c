@@ -442,10 +442,18 @@ void oracle_round_read(const ora_adapter *adapters, int n_adapters, int revcomp,
     const int *t = use_rc ? rev : fwd;
     rec->adapter = a; rec->is_rc = use_rc;
     if (a < 0) {
+        /* no match in the chosen orientation.  With reverse_score (0) > forward_score (< 0,
+           possible at high error rates) cutadapt still hands on the reverse complement and
+           appends " rc" (modifiers.py ReverseComplementer.__call__). */
         rec->ref_start = rec->ref_stop = rec->query_start = rec->query_stop = 0;
         rec->score = 0; rec->errors = 0;
-        memcpy(out_seq, seq, (size_t)n);
-        memcpy(out_qual, qual, (size_t)n);
+        if (use_rc) {
+            memcpy(out_seq, rc, (size_t)n);
+            for (int i = 0; i < n; i++) out_qual[i] = qual[n - 1 - i];
+        } else {
+            memcpy(out_seq, seq, (size_t)n);
+            memcpy(out_qual, qual, (size_t)n);
+        }
         *out_n = n;
     } else {
         rec->ref_start = t[0]; rec->ref_stop = t[1]; rec->query_start = t[2];

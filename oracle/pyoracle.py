@@ -152,7 +152,7 @@ def round_read(adapters, revcomp, name, seq, qual):
     else:
         chosen, s, q = fwd, seq, qual
     if chosen is None:
-        return (-1, False, None, name, seq, qual)
+        return (-1, use_rc, None, name, s, q)
     idx, t = chosen
     if adapters[idx].where in (FRONT, PREFIX):
         s, q = s[t[3]:], q[t[3]:]

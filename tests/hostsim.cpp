@@ -41,7 +41,7 @@ extern "C" int hostsim_demux(int n_rounds,
     uint32_t *W = codes.data() + 4;
     for (uint64_t i = 0; i < n_bytes; i++) W[i >> 3] |= (uint32_t)lut[seq[i]] << ((i & 7) * 4);
 
-    Cell col[MAX_M + 1];
+    ColRing *ring = new ColRing;
     n_tasks[0] = n_tasks[1] = 0;
     for (uint32_t r = 0; r < n_reads; r++) {
         View v; v.lo = offsets[r]; v.len = lengths[r]; v.rc = 0;
@@ -62,7 +62,7 @@ extern "C" int hostsim_demux(int n_rounds,
                 if (h.jf <= h.jl || h.i1 <= h.i2) {
                     Task t; t.read = r; t.lane = (uint32_t)lane; t.jf = h.jf; t.jl = h.jl; t.i1 = h.i1; t.i2 = h.i2;
                     PairResult pr; memset(&pr, 0, sizeof(pr));
-                    resolve_pair(W, v, R, t, pr, col);
+                    resolve_pair(W, v, R, t, pr, *ring);
                     results.push_back(pr);
                     mask |= 1u << lane;
                     n_tasks[rd]++;
@@ -75,6 +75,7 @@ extern "C" int hostsim_demux(int n_rounds,
         }
         out_lo[r] = v.lo; out_len[r] = v.len; out_rc[r] = v.rc;
     }
+    delete ring;
     delete[] T;
     return 0;
 }

@@ -1,0 +1,46 @@
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import random, numpy as np, sys, time
+import helpers as H, oracle
+from orcdemux import synth
+import test_hostsim as T
+seed=int(sys.argv[1]); trials=int(sys.argv[2])
+rnd = random.Random(seed)
+t0=time.time(); total=0
+for trial in range(trials):
+    nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
+    mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([3, 5, 8, 12, 17, 20, 33, 40, 57, 64])))
+    shared = mk()[:10]
+    f = [((shared if rnd.random() < 0.5 else "") + mk())[:64] for _ in range(nf)]
+    b = [(mk() + (shared if rnd.random() < 0.5 else ""))[:64] for _ in range(nb)]
+    if rnd.random()<0.3:  # low complexity adapters
+        f=[ (x[:4]*16)[:len(x)] for x in f]; b=[(x[:3]*22)[:len(x)] for x in b]
+    e = rnd.choice([0.0, 0.05, 0.1, 0.1, 0.2, 0.3, 0.4, 0.6, 0.9, 2])
+    if e >= 1 and min(len(x) for x in f + b) <= e: e = 0.25
+    ov = rnd.choice([1, 2, 3, 3, 5, 8, 20]); rc = rnd.choice([0, 1, 1])
+    rounds = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
+    if rnd.random()<0.25: rounds=[rounds[1], rounds[0]]   # back first then front
+    if rnd.random()<0.15: rounds=rounds[:1]
+    rs = T._adversarial_reads(rnd, f, b, 300)
+    # add very short reads
+    recs=[rs.read(i) for i in range(rs.n_reads)]
+    for i in range(100):
+        L=rnd.randint(0,90); a=rnd.choice(f+b)
+        s="".join(rnd.choice("ACGT") for _ in range(L))
+        if rnd.random()<0.6 and len(a)>2:
+            x=rnd.randint(0,len(a)-1); y=rnd.randint(x+1,len(a)); p=rnd.randint(0,max(0,L))
+            s=s[:p]+a[x:y]+s[p:]
+        recs.append(("s%d"%i, s, "I"*len(s)))
+    rs=synth.from_records(recs)
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=8)
+    m0, m1, lo, ln, rcv, nt = H.run_hostsim(rounds, rs)
+    total+=rs.n_reads
+    for name, a, bb in (("r1", rec0, m0), ("r2", rec1, m1)):
+        if a is None: continue
+        idx, nbad = H.diff_matches(a, bb)
+        if nbad:
+            i=int(idx[0]); print("MISMATCH seed",seed,"trial", trial, name, "e", e, "ov", ov, "rc", rc, "read", i, "nbad", nbad)
+            print(" oracle", a[i]); print(" hostsim", bb[i]); print(" seq", rs.read(i)[1]); print(rounds)
+            sys.exit(1)
+    assert np.array_equal(olen, ln)
+print("ok seed",seed,"reads",total,"time",time.time()-t0)
