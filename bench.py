@@ -230,8 +230,8 @@ def main():
     clocks = sampler.stop()
     t = eng.timings(0)                  # stage split of the last step
     cells = float(sum(t["cells"]))
-    scan_ms = float(sum(t["scan_ms"]))
-    stage = {"pack_ms": t["pack_ms"], "scan_ms": t["scan_ms"], "resolve_ms": t["resolve_ms"],
+    scan_ms = float(sum(t["scan_ms"]) + sum(t["trigger_ms"]))
+    stage = {"pack_ms": t["pack_ms"], "trigger_ms": t["trigger_ms"], "scan_ms": t["scan_ms"], "resolve_ms": t["resolve_ms"],
              "bin_ms": t["bin_ms"], "emit_ms": t["emit_ms"], "total_ms": t["total_ms"], "n_tasks": t["n_tasks"]}
     launches = int(t["kernel_launches"]) * args.steps
 

@@ -115,7 +115,8 @@ typedef struct orc_result {
  * events recorded on the ctx's own stream (milliseconds), and launch counts. */
 typedef struct orc_timings {
     float pack_ms;                  /* ASCII -> 4-bit codes */
-    float scan_ms[ORC_MAX_ROUNDS];  /* bit-parallel edit-distance scan, per round */
+    float trigger_ms[ORC_MAX_ROUNDS]; /* scan stage 1: length sort + shared-prefix trigger scan (0 if off) */
+    float scan_ms[ORC_MAX_ROUNDS];  /* scan stage 2: bit-parallel edit-distance scan of the windows */
     float resolve_ms[ORC_MAX_ROUNDS]; /* exact banded DP of the candidate pairs + selection */
     float bin_ms;                   /* per-bin counts, stable offsets */
     float emit_ms;                  /* trimmed FASTQ records into their bins */

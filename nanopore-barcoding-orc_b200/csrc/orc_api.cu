@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "../../include/orcdemux.h"
+#include <cub/device/device_radix_sort.cuh>
+
 #include "orc_kernels.cuh"
 #include "orc_table.h"
 
@@ -23,11 +25,12 @@ static_assert(sizeof(orc_match) == sizeof(Match), "orc_match layout");
 static_assert(sizeof(View) == 16, "View layout");
 static_assert(sizeof(Task) == 32, "Task layout");
 static_assert(sizeof(PairResult) == 32, "PairResult layout");
+static_assert(sizeof(WinList) == 32, "WinList layout");
 static_assert(ORC_MAX_ADAPTERS == MAX_AD, "adapter limit");
 
 namespace {
 
-enum { EV_START = 0, EV_H2D, EV_PACK, EV_SCAN0, EV_RES0, EV_SCAN1, EV_RES1, EV_BIN, EV_EMIT, EV_HDR, EV_END, EV_T0, EV_T1, EV_COUNT };
+enum { EV_START = 0, EV_H2D, EV_PACK, EV_TRIG0, EV_SCAN0, EV_RES0, EV_TRIG1, EV_SCAN1, EV_RES1, EV_BIN, EV_EMIT, EV_HDR, EV_END, EV_T0, EV_T1, EV_COUNT };
 enum { SLOT_IDLE = 0, SLOT_UPLOADED, SLOT_LAUNCHED, SLOT_DOWNLOADING };
 
 struct Slot {
@@ -45,6 +48,9 @@ struct Slot {
     View *d_views[3] = {nullptr, nullptr, nullptr};
     Match *d_match[2] = {nullptr, nullptr};
     uint32_t *d_read_mask = nullptr, *d_read_base = nullptr;
+    uint32_t *d_key_in = nullptr, *d_key_out = nullptr, *d_val_in = nullptr, *d_order = nullptr;
+    void *d_sort_tmp = nullptr;
+    WinList *d_wins = nullptr;
     Task *d_tasks = nullptr;
     PairResult *d_results = nullptr;
     uint32_t *d_counters = nullptr;          // [0..1] work counters, [2..3] task counts
@@ -77,6 +83,7 @@ struct orc_ctx {
     std::vector<uint64_t> total_counts;
     std::string err;
     int scan_blocks = 0, resolve_blocks = 0;
+    size_t sort_tmp_bytes = 0;
 };
 
 #define CK(call)                                                                          \
@@ -116,6 +123,9 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     for (int i = 0; i < 2; i++) CK(dalloc(&s.d_match[i], R));
     CK(dalloc(&s.d_read_mask, R));
     CK(dalloc(&s.d_read_base, R));
+    CK(dalloc(&s.d_key_in, R)); CK(dalloc(&s.d_key_out, R)); CK(dalloc(&s.d_val_in, R)); CK(dalloc(&s.d_order, R));
+    CK(cudaMalloc(&s.d_sort_tmp, ctx->sort_tmp_bytes + 64));
+    CK(dalloc(&s.d_wins, 2 * R));
     CK(dalloc(&s.d_tasks, n_tasks));
     CK(dalloc(&s.d_results, n_tasks));
     CK(dalloc(&s.d_counters, 8));
@@ -153,6 +163,8 @@ static void free_slot(Slot &s)
     for (int i = 0; i < 3; i++) cudaFree(s.d_views[i]);
     for (int i = 0; i < 2; i++) { cudaFree(s.d_match[i]); cudaFreeHost(s.h_match[i]); }
     cudaFree(s.d_read_mask); cudaFree(s.d_read_base); cudaFree(s.d_tasks); cudaFree(s.d_results);
+    cudaFree(s.d_key_in); cudaFree(s.d_key_out); cudaFree(s.d_val_in); cudaFree(s.d_order);
+    cudaFree(s.d_sort_tmp); cudaFree(s.d_wins);
     cudaFree(s.d_counters); cudaFree(s.d_cells); cudaFree(s.d_bin); cudaFree(s.d_out_len);
     cudaFree(s.d_rec_bytes); cudaFree(s.d_hist_cnt); cudaFree(s.d_hist_bytes);
     cudaFree(s.d_bin_counts); cudaFree(s.d_bin_offsets);
@@ -220,6 +232,10 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     ctx->scan_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_kernel, 128, 0));
     ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
+    {
+        uint32_t *nk = nullptr;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, ctx->sort_tmp_bytes, nk, nk, nk, nk, (int)ctx->max_reads));
+    }
     ctx->slots.resize((size_t)ctx->n_slots);
     for (auto &s : ctx->slots) {
         int rc = alloc_slot(ctx, s);
@@ -346,10 +362,22 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     CK(cudaEventRecord(s.ev[EV_PACK], st));
     for (int r = 0; r < ctx->n_rounds; r++) {
         const Match *prev = r == 0 ? nullptr : s.d_match[r - 1];
+        const bool filter = ctx->h_tab[r].use_filter != 0;
+        if (n && filter) {
+            // stage 1: order the reads by length, then one 32-bit scan of the shared prefix per
+            // (read, direction) marks the column windows that stage 2 has to look at
+            sort_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_views[r], prev, n, s.d_key_in, s.d_val_in);
+            size_t tmp = ctx->sort_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_key_in, s.d_key_out, s.d_val_in,
+                                                         s.d_order, (int)n, 0, 32, st));
+            trigger_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], prev, s.d_order, n,
+                                                               s.d_wins);
+        }
+        CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
         if (n) {
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
-                ctx->d_tab[r], W, s.d_views[r], prev, n, s.d_tasks, s.d_counters + 2 + r, s.d_read_mask,
-                s.d_read_base, s.d_counters + r);
+                ctx->d_tab[r], W, s.d_views[r], prev, filter ? s.d_wins : nullptr, n, s.d_tasks,
+                s.d_counters + 2 + r, s.d_read_mask, s.d_read_base, s.d_counters + r);
         }
         CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         if (n) {
@@ -380,6 +408,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         CK(cudaEventRecord(s.ev[r == 0 ? EV_RES0 : EV_RES1], st));
     }
     if (ctx->n_rounds == 1) {
+        CK(cudaEventRecord(s.ev[EV_TRIG1], st));
         CK(cudaEventRecord(s.ev[EV_SCAN1], st));
         CK(cudaEventRecord(s.ev[EV_RES1], st));
     }
@@ -494,9 +523,11 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     CK(cudaStreamSynchronize(s.stream));
     auto el = [&](int a, int b, float *dst) -> cudaError_t { return cudaEventElapsedTime(dst, s.ev[a], s.ev[b]); };
     CK(el(EV_H2D, EV_PACK, &t->pack_ms));
-    CK(el(EV_PACK, EV_SCAN0, &t->scan_ms[0]));
+    CK(el(EV_PACK, EV_TRIG0, &t->trigger_ms[0]));
+    CK(el(EV_TRIG0, EV_SCAN0, &t->scan_ms[0]));
     CK(el(EV_SCAN0, EV_RES0, &t->resolve_ms[0]));
-    CK(el(EV_RES0, EV_SCAN1, &t->scan_ms[1]));
+    CK(el(EV_RES0, EV_TRIG1, &t->trigger_ms[1]));
+    CK(el(EV_TRIG1, EV_SCAN1, &t->scan_ms[1]));
     CK(el(EV_SCAN1, EV_RES1, &t->resolve_ms[1]));
     CK(el(EV_RES1, EV_BIN, &t->bin_ms));
     CK(el(EV_BIN, EV_EMIT, &t->emit_ms));
@@ -511,6 +542,9 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     uint64_t emit_bytes = 0;
     CK(cudaMemcpy(&emit_bytes, s.d_bin_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 3u + (s.has_names ? 1u : 0u)) : 1u;
+    if (s.n_reads)
+        for (int r = 0; r < ctx->n_rounds; r++)
+            if (ctx->h_tab[r].use_filter) t->kernel_launches += 2u;   // sort_keys + trigger (CUB's own launches not counted)
     for (int r = 0; r < ctx->n_rounds; r++) {
         t->n_tasks[r] = counters[2 + r];
         const RoundTable &T = ctx->h_tab[r];

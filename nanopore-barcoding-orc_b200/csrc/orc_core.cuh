@@ -59,6 +59,12 @@ struct RoundTable {
                                     // the 64-m low padding bits always 1
     uint64_t pv0[MAX_LANES];        // vertical deltas of column 0 (R2)
     int32_t d0[MAX_LANES];          // D[m][0]
+    // shared-prefix trigger filter (stage 1 of the scan)
+    int32_t use_filter;             // 1 if the adapters share a prefix long enough to filter on
+    int32_t lcp;                    // its length Lp (<= 32)
+    int32_t k_max, m_max;           // largest k and m of the round
+    uint32_t peq32[16][64];         // [read code][lane]: match bits of the prefix, row Lp at bit 31;
+                                    // even lanes: direction 0, odd lanes: direction 1 (complemented)
 };
 
 // A read (or what a previous round left of it) as a window of the packed code array:
@@ -131,76 +137,244 @@ ORC_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s)
 #endif
 
 // ------------------------------------------------------------------------------------
-// scan_lane: the hot loop.  W: packed codes (8 per word) with guard words on both sides.
-// peq_base: byte address of RoundTable::peq (shared memory on the device); the entry of
-// (code c, lane l) lives at c*256 + l*8, which one PRMT builds from a code byte and l*8.
+// The scan, in two stages.
+//
+// Stage 1 (trigger_lane): when all adapters of a round share a prefix P of Lp <= 32 characters
+// (the M13 tables do: 25 nt for SP5, 17 nt for SP27rc), rows 1..Lp of the DP matrix are the
+// same for every adapter.  One 32-bit Myers scan of P per (read, direction) gives D[Lp][j] for
+// every column.  An acceptable alignment of ANY adapter that starts in row 0 (or above row Lp
+// in column 0) passes through row Lp at some column j' with D[Lp][j'] <= k ("trigger") and ends
+// within (m - Lp) + k columns of it, so the columns that the per-adapter scan has to look at
+// are windows around the triggers, plus the first columns of a 5' adapter (alignments that
+// start below row Lp in column 0) and the last columns of a 3' adapter (rows <= Lp of the last
+// column).  The windows are a superset of what is needed; a missed window would lose matches,
+// a superfluous one only costs time.
+//
+// Stage 2 (scan_window): the 64-bit Myers scan of one (read, adapter, direction) pair over one
+// window [s, e] of columns.  A window with s > 0 starts from column costs D[i][s] = i; that
+// over-estimates, but is exact for every cell whose optimal path starts at a column >= s, and
+// every candidate inside the window is of that kind because windows reach Lp + 2k + 1 columns
+// back from their trigger.
+//
+// W: packed codes (8 per word) with guard words on both sides.  The match-bit tables live in
+// shared memory on the device; the entry of (code c, lane l) is at c*256 + l*8 (64-bit table)
+// or c*256 + l*4 (32-bit table), an address that one PRMT builds from a code byte and l*8.
 // ------------------------------------------------------------------------------------
 struct ScanHull { int32_t jf, jl, i1, i2; };
 
-ORC_HD void scan_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
-                      const char *peq_base, int lane, uint64_t Pv, int D, int m, int k,
-                      const uint8_t *kmax, int min_ov, int type, ScanHull &out)
+constexpr int MAX_WIN = 3;
+struct WinList {                    // windows of one (read, direction), increasing, disjoint
+    uint32_t n;
+    uint32_t s[MAX_WIN], e[MAX_WIN];   // columns s+1 .. e are scanned; s == 0 is the true column 0
+    uint32_t pad_;
+};
+
+ORC_HD uint32_t funnel_l1(uint32_t acc, uint32_t top)   // (acc << 1) | (top >> 31)
 {
-    uint64_t Mv = 0;
-    int jf = 0x7fffffff, jl = -1;
-    const uint32_t lane8 = (uint32_t)lane * 8u;
-    // PRMT selectors: result byte0 <- lane8.byte0, byte1 <- code byte b, bytes 2,3 <- 0
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(top, acc, 1);
+#else
+    return (acc << 1) | (top >> 31);
+#endif
+}
+
+ORC_HD int popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// Reads 8 codes of a lane's sequence, view positions p .. p+7, as two words of byte-wide
+// codes: A holds positions p, p+2, p+4, p+6 and B holds p+1, p+3, p+5, p+7, in the byte order
+// that the lane's PRMT selectors expect (reversed for direction 1).
+struct ChunkReader {
+    const uint32_t *W;
+    int64_t s;          // storage index of the lowest-addressed code of the current chunk
+    int64_t step;
+    uint32_t shA, shB;
+    ORC_HD void init(const uint32_t *W_, uint64_t lo, uint32_t len, int dir, uint32_t p0)
+    {
+        W = W_;
+        s = dir ? (int64_t)lo + (int64_t)len - 8 - (int64_t)p0 : (int64_t)lo + (int64_t)p0;
+        step = dir ? -8 : 8;
+        shA = dir ? 4u : 0u;
+        shB = dir ? 0u : 4u;
+    }
+    ORC_HD void next(uint32_t &A, uint32_t &B)
+    {
+        const int64_t wi = s >> 3;
+        const uint32_t x = funnel_r(W[wi], W[wi + 1], (uint32_t)(s & 7) * 4u);
+        A = (x >> shA) & 0x0F0F0F0Fu;
+        B = (x >> shB) & 0x0F0F0F0Fu;
+        s += step;
+    }
+};
+
+ORC_HD void win_add(WinList &L, bool &open, uint32_t &cs, uint32_t &ce, uint32_t s, uint32_t e)
+{
+    if (!open) { cs = s; ce = e; open = true; return; }
+    if (s <= ce + 1u || L.n >= (uint32_t)(MAX_WIN - 1)) {   // overlapping, or out of slots: merge
+        if (e > ce) ce = e;
+        return;
+    }
+    L.s[L.n] = cs; L.e[L.n] = ce; L.n++;
+    cs = s; ce = e;
+}
+
+// Stage 1.  peq32_base: table of the shared prefix, entry (code, lane) at code*256 + lane*4,
+// row Lp at bit 31.  kt = largest k of the round, ext = m_max - Lp + kt, back = Lp + 2*kt + 1.
+ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
+                         const char *peq32_base, int lane, int Lp, int kt, int type,
+                         uint32_t ext, uint32_t back, WinList &out)
+{
+    const uint32_t n = len;
+    out.n = 0; out.pad_ = 0;
+    for (int i = 0; i < MAX_WIN; i++) { out.s[i] = 0; out.e[i] = 0; }
+    bool open = false;
+    uint32_t cs = 0, ce = 0;
+    const uint32_t pad = (Lp == 32) ? 0u : ((1u << (32 - Lp)) - 1u);
+    uint32_t Pv, Mv = 0;
+    int D;
+    if (type == TYPE_FRONT) {
+        Pv = 0; D = 0;
+        win_add(out, open, cs, ce, 0u, ext < n ? ext : n);   // alignments starting in column 0
+    } else { Pv = ~pad; D = Lp; }
+    const uint32_t lane4 = (uint32_t)lane * 4u;
     uint32_t sel0, sel1, sel2, sel3;
     if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
     else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
-    const uint32_t shA = dir ? 4u : 0u, shB = dir ? 0u : 4u;
-    const int nchunks = (int)((len + 7u) >> 3);
-    // storage index of the lowest-addressed code of the current chunk
-    int64_t s = dir ? (int64_t)lo + (int64_t)len - 8 : (int64_t)lo;
-    const int64_t step = dir ? -8 : 8;
-    int j = 0;
-    for (int q = 0; q < nchunks; q++, s += step) {
-        const int64_t wi = s >> 3;
-        const uint32_t x = funnel_r(W[wi], W[wi + 1], (uint32_t)(s & 7) * 4u);
-        const uint32_t A = (x >> shA) & 0x0F0F0F0Fu;   // codes at even view positions of the chunk
-        const uint32_t B = (x >> shB) & 0x0F0F0F0Fu;   // codes at odd view positions
-        const int ncol = imin(8, (int)len - 8 * q);
+    ChunkReader rd;
+    rd.init(W, lo, len, dir, 0u);
+    const int nchunks = (int)((n + 7u) >> 3);
+    for (int q = 0; q < nchunks; q++) {
+        uint32_t A, B;
+        rd.next(A, B);
+        const int ncol = imin(8, (int)n - 8 * q);
+        uint32_t accP = 0, accM = 0;
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             if (t >= ncol) break;
             const uint32_t src = (t & 1) ? B : A;
             const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
-            const uint32_t addr = byte_perm(src, lane8, sel);
-            const uint64_t Eq = *reinterpret_cast<const uint64_t *>(peq_base + addr);
-            // Myers 1999 / Hyyro 2003, one column
+            const uint32_t Eq = *reinterpret_cast<const uint32_t *>(peq32_base + byte_perm(src, lane4, sel));
+            const uint32_t Xv = Eq | Mv;
+            const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint32_t Ph = Mv | ~(Xh | Pv);
+            uint32_t Mh = Pv & Xh;
+            accP = funnel_l1(accP, Ph);
+            accM = funnel_l1(accM, Mh);
+            Ph <<= 1; Mh <<= 1;
+            Pv = Mh | ~(Xv | Ph);
+            Mv = Ph & Xv;
+        }
+        if (D - popc32(accM) <= kt) {            // some column of the chunk may reach the threshold
+            for (int t = 0; t < ncol; t++) {
+                const int b = ncol - 1 - t;
+                D += (int)((accP >> b) & 1u) - (int)((accM >> b) & 1u);
+                if (D <= kt) {
+                    const uint32_t j = (uint32_t)(8 * q + t + 1);
+                    const uint32_t e = j + ext;
+                    win_add(out, open, cs, ce, j > back ? j - back : 0u, e < n ? e : n);
+                }
+            }
+        } else {
+            D += popc32(accP) - popc32(accM);
+        }
+    }
+    if (type == TYPE_BACK) {                     // rows <= Lp of the last column
+        const uint32_t r = (uint32_t)(Lp + kt + 1);
+        win_add(out, open, cs, ce, n > r ? n - r : 0u, n);
+    }
+    if (open) { out.s[out.n] = cs; out.e[out.n] = ce; out.n++; }
+}
+
+// Stage 2: columns s+1 .. e of one pair.  Widens the candidate hull in `h`.
+ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
+                        uint32_t s, uint32_t e, const char *peq_base, int lane, uint64_t pv0, int d0,
+                        int m, int k, const uint8_t *kmax, int min_ov, int type, ScanHull &h)
+{
+    const uint64_t pad = (m == 64) ? 0ull : ((1ull << (64 - m)) - 1ull);
+    uint64_t Pv, Mv = 0;
+    int D;
+    if (s == 0) { Pv = pv0; D = d0; }            // R2: the true column 0
+    else { Pv = ~pad; D = m; }                   // restart: cost i
+    int jf = h.jf, jl = h.jl;
+    const uint32_t lane8 = (uint32_t)lane * 8u;
+    // PRMT selectors: result byte0 <- lane8.byte0, byte1 <- code byte b, bytes 2,3 <- 0
+    uint32_t sel0, sel1, sel2, sel3;
+    if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
+    else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
+    ChunkReader rd;
+    rd.init(W, lo, len, dir, s);
+    const int ncols = (int)(e - s);
+    const int nchunks = (ncols + 7) >> 3;
+    for (int q = 0; q < nchunks; q++) {
+        uint32_t A, B;
+        rd.next(A, B);
+        const int ncol = imin(8, ncols - 8 * q);
+        uint32_t accP = 0, accM = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (t >= ncol) break;
+            const uint32_t src = (t & 1) ? B : A;
+            const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+            const uint64_t Eq = *reinterpret_cast<const uint64_t *>(peq_base + byte_perm(src, lane8, sel));
+            // Myers 1999 / Hyyro 2003, one column; row 0 never changes (QUERY_START): shift in 0
             const uint64_t Xv = Eq | Mv;
             const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
             uint64_t Ph = Mv | ~(Xh | Pv);
             uint64_t Mh = Pv & Xh;
-            D += (int)(Ph >> 63) - (int)(Mh >> 63);
-            Ph <<= 1;            // row 0 never changes (QUERY_START): shift in 0
-            Mh <<= 1;
+            accP = funnel_l1(accP, (uint32_t)(Ph >> 32));
+            accM = funnel_l1(accM, (uint32_t)(Mh >> 32));
+            Ph <<= 1; Mh <<= 1;
             Pv = Mh | ~(Xv | Ph);
             Mv = Ph & Xv;
-            ++j;
-            if (D <= k) {
-                // R5 necessary condition: a path with D errors ending in (m, j) aligns at most
-                // min(m, j + D) adapter characters.
-                const int lmax = imin(m, j + D);
-                if (lmax >= min_ov && D <= (int)kmax[lmax]) {
-                    jf = imin(jf, j);
-                    jl = j;
+        }
+        if (D - popc32(accM) <= k) {             // D[m][j] may reach k inside this chunk: replay it
+            for (int t = 0; t < ncol; t++) {
+                const int b = ncol - 1 - t;
+                D += (int)((accP >> b) & 1u) - (int)((accM >> b) & 1u);
+                if (D <= k) {
+                    // R5 necessary condition: a path with D errors ending in (m, j) aligns at
+                    // most min(m, j + D) adapter characters.
+                    const int j = (int)s + 8 * q + t + 1;
+                    const int lmax = imin(m, j + D);
+                    if (lmax >= min_ov && D <= (int)kmax[lmax]) { jf = imin(jf, j); jl = j; }
                 }
             }
+        } else {
+            D += popc32(accP) - popc32(accM);
         }
     }
-    out.jf = jf; out.jl = jl;
-    int i1 = 0x7fffffff, i2 = -1;
-    if (type == TYPE_BACK) {
+    h.jf = jf; h.jl = jl;
+    if (type == TYPE_BACK && e == len) {
         // R6 necessary condition for the cells (i, n): origin >= 0 for BACK, so length == i
-        int cum = 0;
+        int i1 = h.i1, i2 = h.i2, cum = 0;
         for (int i = 1; i <= m; i++) {
             const int bit = 64 - m + i - 1;
             cum += (int)((Pv >> bit) & 1u) - (int)((Mv >> bit) & 1u);
             if (i >= min_ov && cum <= (int)kmax[i]) { i1 = imin(i1, i); i2 = i; }
         }
+        h.i1 = i1; h.i2 = i2;
     }
-    out.i1 = i1; out.i2 = i2;
+}
+
+// All windows of one pair.  wl == nullptr: no prefix filter, one window over the whole view.
+ORC_HD void scan_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
+                      const WinList *wl, const char *peq_base, int lane, uint64_t pv0, int d0,
+                      int m, int k, const uint8_t *kmax, int min_ov, int type, ScanHull &out)
+{
+    out.jf = 0x7fffffff; out.jl = -1; out.i1 = 0x7fffffff; out.i2 = -1;
+    if (wl == nullptr) {
+        scan_window(W, lo, len, dir, 0u, len, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, out);
+        return;
+    }
+    const uint32_t nw = wl->n;
+    for (uint32_t w = 0; w < nw; w++)
+        scan_window(W, lo, len, dir, wl->s[w], wl->e[w], peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, out);
 }
 
 // ------------------------------------------------------------------------------------

@@ -75,10 +75,59 @@ __global__ void init_views_kernel(const uint64_t *__restrict__ offsets, const ui
 }
 
 // ------------------------------------------------------------------------------------
-// scan: persistent warps pull reads from a global counter (reads differ in length).
+// Stage 1 of the scan.  Reads are visited in order of decreasing view length (order[] comes
+// from a radix sort of the lengths), two threads per read (one per storage direction), so the
+// 32 lanes of a warp walk 16 reads of nearly the same length.
+__global__ void sort_keys_kernel(const View *__restrict__ views, const Match *__restrict__ prev,
+                                 uint32_t n_reads, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const bool skip = prev != nullptr && prev[r].adapter < 0;
+    keys[r] = skip ? 0u : views[r].len;
+    vals[r] = r;
+}
+
+__global__ void __launch_bounds__(128)
+trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
+               const View *__restrict__ views, const Match *__restrict__ prev,
+               const uint32_t *__restrict__ order, uint32_t n_reads, WinList *__restrict__ wins)
+{
+    __shared__ __align__(16) uint32_t s_peq32[16][64];
+    __shared__ int s_par[8];
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32[0][0])[i] = (&tab->peq32[0][0])[i];
+    if (threadIdx.x == 0) {
+        s_par[0] = tab->lcp; s_par[1] = tab->k_max; s_par[2] = tab->m_max; s_par[3] = tab->type;
+        s_par[4] = tab->revcomp;
+    }
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= 2u * n_reads) return;
+    const uint32_t r = order[p >> 1];
+    const int dir = (int)(p & 1u);
+    const int Lp = s_par[0], kt = s_par[1], m_max = s_par[2], type = s_par[3];
+    WinList wl;
+    wl.n = 0; wl.pad_ = 0;
+    for (int i = 0; i < MAX_WIN; i++) { wl.s[i] = 0; wl.e[i] = 0; }
+    const bool skip = prev != nullptr && prev[r].adapter < 0;
+    if (!skip) {
+        const View v = views[r];
+        if (s_par[4] || ((dir ^ (int)(v.rc & 1u)) == 0))
+            trigger_lane(W, v.lo, v.len, dir, reinterpret_cast<const char *>(&s_peq32[0][0]),
+                         (int)(threadIdx.x & 63u), Lp, kt, type, (uint32_t)(m_max - Lp + kt),
+                         (uint32_t)(Lp + 2 * kt + 1), wl);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(wins + (size_t)r * 2 + dir);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&wl);
+    dst[0] = src[0]; dst[1] = src[1];
+}
+
+// ------------------------------------------------------------------------------------
+// Stage 2 of the scan: persistent warps pull reads from a global counter.
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
-            const View *__restrict__ views, const Match *__restrict__ prev, uint32_t n_reads,
+            const View *__restrict__ views, const Match *__restrict__ prev,
+            const WinList *__restrict__ wins, uint32_t n_reads,
             Task *__restrict__ tasks, uint32_t *__restrict__ task_count,
             uint32_t *__restrict__ read_mask, uint32_t *__restrict__ read_base,
             uint32_t *__restrict__ work_counter)
@@ -113,8 +162,16 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
             const bool active = lane_used && (T.revcomp || ((dir ^ (int)(v.rc & 1u)) == 0));
             ScanHull h;
             h.jf = 1; h.jl = 0; h.i1 = 1; h.i2 = 0;
-            if (active)
-                scan_lane(W, v.lo, v.len, dir, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, h);
+            if (active) {
+                WinList wl;
+                if (wins != nullptr) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(wins + (size_t)r * 2 + dir);
+                    uint4 *dst = reinterpret_cast<uint4 *>(&wl);
+                    dst[0] = src[0]; dst[1] = src[1];
+                }
+                scan_lane(W, v.lo, v.len, dir, wins != nullptr ? &wl : nullptr, peq_base, lane, pv0, d0,
+                          m, k, kmax, min_ov, type, h);
+            }
             const bool has = active && (h.jf <= h.jl || h.i1 <= h.i2);
             mask = __ballot_sync(0xffffffffu, has);
             if (mask) {

@@ -24,8 +24,11 @@ inline int base_code(char c)
 }
 
 // Returns "" on success, else the reason the round is not supported.
+// filter_mode: 0 = never use the shared-prefix trigger filter, 1 = when it pays (prefix >= 12 and
+// > 2k), 2 = whenever it is valid (prefix > k; for tests).
 inline std::string build_round_table(RoundTable &T, int n_adapters, int type, const char *const *sequences,
-                                     double max_errors, int min_overlap, int indels, int revcomp)
+                                     double max_errors, int min_overlap, int indels, int revcomp,
+                                     int filter_mode = 1)
 {
     memset(&T, 0, sizeof(T));
     if (n_adapters < 1 || n_adapters > MAX_AD)
@@ -80,6 +83,35 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         // R2: FRONT column 0 costs are all 0; BACK column 0 cost is i
         T.pv0[lane] = (type == TYPE_FRONT) ? 0ull : ~pad;
         T.d0[lane] = (type == TYPE_FRONT) ? 0 : m;
+    }
+    // longest common prefix of the adapters (as code masks), capped at one 32-bit word
+    int lcp = T.m[0];
+    for (int a = 1; a < n_adapters; a++) {
+        int l = 0;
+        while (l < lcp && l < T.m[a] && T.code[a][l] == T.code[0][l]) l++;
+        lcp = l;
+    }
+    if (lcp > 32) lcp = 32;
+    int k_max = 0, m_max = 0;
+    for (int a = 0; a < n_adapters; a++) {
+        if (T.k[a] > k_max) k_max = T.k[a];
+        if (T.m[a] > m_max) m_max = T.m[a];
+    }
+    T.lcp = lcp; T.k_max = k_max; T.m_max = m_max;
+    const bool valid = lcp > k_max && lcp >= 1;
+    T.use_filter = (filter_mode == 2) ? valid : (filter_mode == 1 ? (valid && lcp >= 12 && lcp > 2 * k_max) : 0);
+    if (T.use_filter) {
+        const uint32_t pad32 = (lcp == 32) ? 0u : ((1u << (32 - lcp)) - 1u);
+        for (int lane = 0; lane < 64; lane++) {
+            const int dir = lane & 1;
+            for (uint32_t c = 0; c < 16; c++) {
+                const uint32_t cc = dir ? comp4(c) : c;
+                uint32_t bits = pad32;
+                for (int i = 0; i < lcp; i++)
+                    if (T.code[0][i] & cc) bits |= 1u << (32 - lcp + i);
+                T.peq32[c][lane] = bits;
+            }
+        }
     }
     return "";
 }

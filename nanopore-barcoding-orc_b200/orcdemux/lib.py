@@ -60,7 +60,8 @@ class Result(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [("pack_ms", C.c_float), ("scan_ms", C.c_float * ORC_MAX_ROUNDS),
+    _fields_ = [("pack_ms", C.c_float), ("trigger_ms", C.c_float * ORC_MAX_ROUNDS),
+                ("scan_ms", C.c_float * ORC_MAX_ROUNDS),
                 ("resolve_ms", C.c_float * ORC_MAX_ROUNDS), ("bin_ms", C.c_float), ("emit_ms", C.c_float),
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("n_tasks", C.c_uint32 * ORC_MAX_ROUNDS),

@@ -46,7 +46,7 @@ def _cstrs(seqs):
     return arr
 
 
-def run_hostsim(rounds, rs):
+def run_hostsim(rounds, rs, filter_mode=1, want_columns=False):
     """rounds: [(sequences, type, e, O, rc)].  Returns (m0, m1, lo, len, rc, n_tasks)."""
     n = rs.n_reads
     m0 = np.zeros(n, dtype=MATCH_DTYPE)
@@ -55,6 +55,7 @@ def run_hostsim(rounds, rs):
     ln = np.zeros(n, dtype=np.uint32)
     rc = np.zeros(n, dtype=np.uint32)
     nt = np.zeros(2, dtype=np.uint64)
+    ncol = np.zeros(2, dtype=np.uint64)
     err = C.create_string_buffer(256)
     r0 = rounds[0]
     r1 = rounds[1] if len(rounds) > 1 else rounds[0]
@@ -67,9 +68,12 @@ def run_hostsim(rounds, rs):
         C.c_void_p(seq.ctypes.data), C.c_void_p(rs.offsets.ctypes.data), C.c_void_p(rs.lengths.ctypes.data),
         C.c_uint32(n), C.c_uint64(seq.shape[0]),
         C.c_void_p(m0.ctypes.data), C.c_void_p(m1.ctypes.data), C.c_void_p(lo.ctypes.data),
-        C.c_void_p(ln.ctypes.data), C.c_void_p(rc.ctypes.data), C.c_void_p(nt.ctypes.data), err, C.c_int(256))
+        C.c_void_p(ln.ctypes.data), C.c_void_p(rc.ctypes.data), C.c_void_p(nt.ctypes.data), err, C.c_int(256),
+        C.c_int(filter_mode), C.c_void_p(ncol.ctypes.data))
     if ret != 0:
         raise RuntimeError(err.value.decode())
+    if want_columns:
+        return m0, m1, lo, ln, rc, nt, ncol
     return m0, m1, lo, ln, rc, nt
 
 

@@ -22,11 +22,11 @@ extern "C" int hostsim_demux(int n_rounds,
                              const uint8_t *seq, const uint64_t *offsets, const uint32_t *lengths,
                              uint32_t n_reads, uint64_t n_bytes,
                              Match *m0, Match *m1, uint64_t *out_lo, uint32_t *out_len, uint32_t *out_rc,
-                             uint64_t *n_tasks, char *err, int err_len)
+                             uint64_t *n_tasks, char *err, int err_len, int filter_mode, uint64_t *n_columns)
 {
     RoundTable *T = new RoundTable[2];
-    std::string e = build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, 1, rc0);
-    if (e.empty() && n_rounds > 1) e = build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, 1, rc1);
+    std::string e = build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, 1, rc0, filter_mode);
+    if (e.empty() && n_rounds > 1) e = build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, 1, rc1, filter_mode);
     if (!e.empty()) {
         strncpy(err, e.c_str(), (size_t)err_len - 1);
         err[err_len - 1] = 0;
@@ -43,6 +43,7 @@ extern "C" int hostsim_demux(int n_rounds,
 
     ColRing *ring = new ColRing;
     n_tasks[0] = n_tasks[1] = 0;
+    n_columns[0] = n_columns[1] = 0;
     for (uint32_t r = 0; r < n_reads; r++) {
         View v; v.lo = offsets[r]; v.len = lengths[r]; v.rc = 0;
         Match *out[2] = {&m0[r], &m1[r]};
@@ -52,13 +53,21 @@ extern "C" int hostsim_demux(int n_rounds,
             const RoundTable &R = T[rd];
             uint32_t mask = 0;
             std::vector<PairResult> results;
+            WinList wl[2];
+            if (R.use_filter) {
+                for (int dir = 0; dir < 2; dir++) {
+                    trigger_lane(W, v.lo, v.len, dir, (const char *)&R.peq32[0][0], dir, R.lcp, R.k_max, R.type,
+                                 (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + 2 * R.k_max + 1), wl[dir]);
+                    for (uint32_t w = 0; w < wl[dir].n; w++) n_columns[rd] += wl[dir].e[w] - wl[dir].s[w];
+                }
+            } else n_columns[rd] += 2ull * v.len;
             for (int lane = 0; lane < R.n_lanes; lane++) {
                 const int a = lane % R.n_adapters, dir = lane / R.n_adapters;
                 const int o = dir ^ (int)(v.rc & 1u);
                 if (o == 1 && !R.revcomp) continue;
                 ScanHull h;
-                scan_lane(W, v.lo, v.len, dir, (const char *)&R.peq[0][0], lane, R.pv0[lane], R.d0[lane],
-                          R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, h);
+                scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, (const char *)&R.peq[0][0], lane,
+                          R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, h);
                 if (h.jf <= h.jl || h.i1 <= h.i2) {
                     Task t; t.read = r; t.lane = (uint32_t)lane; t.jf = h.jf; t.jl = h.jl; t.i1 = h.i1; t.i2 = h.i2;
                     PairResult pr; memset(&pr, 0, sizeof(pr));

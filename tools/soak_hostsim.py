@@ -10,9 +10,10 @@ t0=time.time(); total=0
 for trial in range(trials):
     nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
     mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([3, 5, 8, 12, 17, 20, 33, 40, 57, 64])))
-    shared = mk()[:10]
-    f = [((shared if rnd.random() < 0.5 else "") + mk())[:64] for _ in range(nf)]
-    b = [(mk() + (shared if rnd.random() < 0.5 else ""))[:64] for _ in range(nb)]
+    shared = mk()[:rnd.choice([4, 10, 17, 25, 32, 40])]
+    pshare = rnd.choice([0.5, 1.0, 1.0])
+    f = [((shared if rnd.random() < pshare else "") + mk())[:64] for _ in range(nf)]
+    b = [((shared if rnd.random() < pshare else "") + mk() + (shared if rnd.random() < 0.5 else ""))[:64] for _ in range(nb)]
     if rnd.random()<0.3:  # low complexity adapters
         f=[ (x[:4]*16)[:len(x)] for x in f]; b=[(x[:3]*22)[:len(x)] for x in b]
     e = rnd.choice([0.0, 0.05, 0.1, 0.1, 0.2, 0.3, 0.4, 0.6, 0.9, 2])
@@ -33,13 +34,14 @@ for trial in range(trials):
         recs.append(("s%d"%i, s, "I"*len(s)))
     rs=synth.from_records(recs)
     rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=8)
-    m0, m1, lo, ln, rcv, nt = H.run_hostsim(rounds, rs)
+    fmode = rnd.choice([0, 1, 2, 2, 2])
+    m0, m1, lo, ln, rcv, nt = H.run_hostsim(rounds, rs, fmode)
     total+=rs.n_reads
     for name, a, bb in (("r1", rec0, m0), ("r2", rec1, m1)):
         if a is None: continue
         idx, nbad = H.diff_matches(a, bb)
         if nbad:
-            i=int(idx[0]); print("MISMATCH seed",seed,"trial", trial, name, "e", e, "ov", ov, "rc", rc, "read", i, "nbad", nbad)
+            i=int(idx[0]); print("MISMATCH seed",seed,"trial", trial, name, "fmode", fmode, "e", e, "ov", ov, "rc", rc, "read", i, "nbad", nbad)
             print(" oracle", a[i]); print(" hostsim", bb[i]); print(" seq", rs.read(i)[1]); print(rounds)
             sys.exit(1)
     assert np.array_equal(olen, ln)
