@@ -76,16 +76,25 @@ typedef struct orc_params {
  * with two rounds bin = (a1 + 1) + (n_adapters1 + 1) * (a2 + 1), a == -1 for unknown.
  * Buffers stay owned by the caller and must stay valid until orc_wait() returns; pinned
  * memory (orc_host_alloc or torch pin_memory) makes the copies asynchronous.
+ *
+ * Two layouts are accepted:
+ *  - separate blobs: seq and qual of equal size, read r at offsets[r] in both;
+ *  - raw FASTQ text: seq == qual == names == the text, offsets / qual_offsets / name_offsets /
+ *    name_lengths point into it (orc_fastq_index() computes them); the text is uploaded once.
  */
 typedef struct orc_batch {
     uint32_t n_reads;
-    uint64_t n_bytes;               /* bytes of seq and of qual that are in use */
-    const uint8_t *seq;             /* ASCII bases, reads at offsets[r] .. offsets[r]+lengths[r] */
-    const uint8_t *qual;            /* ASCII qualities, same offsets */
+    uint64_t n_bytes;               /* bytes of the seq blob (and of the qual blob) that are in use */
+    const uint8_t *seq;             /* ASCII bases, read r at offsets[r] .. offsets[r]+lengths[r] */
+    const uint8_t *qual;            /* ASCII qualities; may be the same pointer as seq */
     const uint64_t *offsets;        /* [n_reads] */
     const uint32_t *lengths;        /* [n_reads] */
-    const uint8_t *names;           /* FASTQ header lines without '@' and newline; NULL if !emit_fastq */
-    const uint64_t *name_offsets;   /* [n_reads + 1] */
+    const uint64_t *qual_offsets;   /* [n_reads] start of the qualities inside qual; NULL = offsets */
+    const uint8_t *names;           /* header lines without '@' and newline; NULL if !emit_fastq;
+                                       may be the same pointer as seq */
+    const uint64_t *name_offsets;   /* [n_reads + 1]; only [n_reads] are read when name_lengths is given */
+    const uint32_t *name_lengths;   /* [n_reads] or NULL (name r ends where name r+1 starts) */
+    uint64_t name_bytes;            /* bytes of the names blob; ignored when names == seq */
 } orc_batch;
 
 /* What Aligner.locate returns for the adapter that won (cutadapt _align.pyx), plus which. */
@@ -150,6 +159,19 @@ int orc_timer_start(orc_ctx *ctx, int slot);
 int orc_timer_stop(orc_ctx *ctx, int slot, float *ms);
 /* cumulative reads per bin over every batch waited on so far ([n_bins]) */
 int orc_counts(orc_ctx *ctx, uint64_t *bins);
+
+/*
+ * Host-side FASTQ record indexer (the job of dnaio's C parser under cutadapt): finds the
+ * complete 4-line records at the start of `text` and fills the per-read arrays in the raw-text
+ * layout of orc_batch.  Stops after max_reads records or at the last complete record;
+ * *consumed = bytes used.  Returns the number of records, or a negative ORC_E* code
+ * (malformed record: err gets the reason).  A trailing '\r' of a line is not part of it.
+ * `final` != 0 means no more text follows: a last record without a newline is accepted.
+ */
+int64_t orc_fastq_index(const uint8_t *text, uint64_t n_bytes, uint32_t max_reads, int final,
+                        uint64_t *seq_offsets, uint32_t *lengths, uint64_t *qual_offsets,
+                        uint64_t *name_offsets, uint32_t *name_lengths, uint64_t *consumed,
+                        char *err, size_t err_len);
 
 /* pinned host memory for callers that do not bring their own */
 void *orc_host_alloc(size_t bytes);

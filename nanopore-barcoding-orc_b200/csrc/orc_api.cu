@@ -42,6 +42,9 @@ struct Slot {
     bool did_h2d = false, did_kernels = false, did_d2h = false, fresh_upload = false;
     // device
     uint8_t *d_seq = nullptr, *d_qual = nullptr, *d_names = nullptr, *d_fastq = nullptr;
+    uint8_t *u_qual = nullptr, *u_names = nullptr;      // what the kernels use (may alias d_seq)
+    uint64_t *d_qual_offsets = nullptr, *u_qual_offsets = nullptr;
+    uint32_t *d_name_lengths = nullptr, *u_name_lengths = nullptr;
     uint32_t *d_codes_alloc = nullptr;
     uint64_t *d_offsets = nullptr, *d_name_offsets = nullptr, *d_dest = nullptr;
     uint32_t *d_lengths = nullptr;
@@ -118,6 +121,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_codes_alloc, B / 8 + 16 + 2 * GUARD_WORDS));
     CK(cudaMemset(s.d_codes_alloc, 0, (B / 8 + 16 + 2 * GUARD_WORDS) * sizeof(uint32_t)));
     CK(dalloc(&s.d_offsets, R));
+    CK(dalloc(&s.d_qual_offsets, R));
     CK(dalloc(&s.d_lengths, R));
     for (int i = 0; i < 3; i++) CK(dalloc(&s.d_views[i], R));
     for (int i = 0; i < 2; i++) CK(dalloc(&s.d_match[i], R));
@@ -149,6 +153,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     if (ctx->emit_fastq) {
         CK(dalloc(&s.d_names, (size_t)ctx->max_name_bytes + 64));
         CK(dalloc(&s.d_name_offsets, R + 1));
+        CK(dalloc(&s.d_name_lengths, R));
         CK(dalloc(&s.d_fastq, (size_t)ctx->fastq_cap));
         CK(halloc(&s.h_fastq, (size_t)ctx->fastq_cap));
     }
@@ -159,7 +164,7 @@ static void free_slot(Slot &s)
 {
     cudaFree(s.d_seq); cudaFree(s.d_qual); cudaFree(s.d_names); cudaFree(s.d_fastq);
     cudaFree(s.d_codes_alloc); cudaFree(s.d_offsets); cudaFree(s.d_name_offsets); cudaFree(s.d_dest);
-    cudaFree(s.d_lengths);
+    cudaFree(s.d_lengths); cudaFree(s.d_qual_offsets); cudaFree(s.d_name_lengths);
     for (int i = 0; i < 3; i++) cudaFree(s.d_views[i]);
     for (int i = 0; i < 2; i++) { cudaFree(s.d_match[i]); cudaFreeHost(s.h_match[i]); }
     cudaFree(s.d_read_mask); cudaFree(s.d_read_base); cudaFree(s.d_tasks); cudaFree(s.d_results);
@@ -297,13 +302,16 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
         ctx->err = "batch buffers missing"; return ORC_EINVAL;
     }
     s.has_names = ctx->emit_fastq != 0;
+    const bool names_alias = s.has_names && b->names == b->seq;
     uint64_t name_bytes = 0;
     if (s.has_names) {
         if (b->n_reads && (!b->names || !b->name_offsets)) {
             ctx->err = "emit_fastq needs names and name_offsets"; return ORC_EINVAL;
         }
-        name_bytes = b->n_reads ? b->name_offsets[b->n_reads] : 0;
-        if (name_bytes > ctx->max_name_bytes) { ctx->err = "names exceed max_name_bytes"; return ORC_ECAPACITY; }
+        if (!names_alias) {
+            name_bytes = b->name_lengths ? b->name_bytes : (b->n_reads ? b->name_offsets[b->n_reads] : 0);
+            if (name_bytes > ctx->max_name_bytes) { ctx->err = "names exceed max_name_bytes"; return ORC_ECAPACITY; }
+        }
     }
     CK(cudaSetDevice(ctx->device));
     s.n_reads = b->n_reads;
@@ -311,21 +319,38 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
     s.name_bytes = name_bytes;
     uint64_t bases = 0;
     for (uint32_t r = 0; r < b->n_reads; r++) {
-        if (b->offsets[r] + b->lengths[r] > b->n_bytes) { ctx->err = "read extends past n_bytes"; return ORC_EINVAL; }
+        if (b->offsets[r] + b->lengths[r] > b->n_bytes ||
+            (b->qual_offsets && b->qual_offsets[r] + b->lengths[r] > b->n_bytes)) {
+            ctx->err = "read extends past n_bytes"; return ORC_EINVAL;
+        }
         bases += b->lengths[r];
     }
     s.in_bases = bases;
     CK(cudaEventRecord(s.ev[EV_START], s.stream));
+    s.u_qual = s.d_qual; s.u_names = s.d_names; s.u_qual_offsets = nullptr; s.u_name_lengths = nullptr;
     if (b->n_reads) {
         CK(cudaMemcpyAsync(s.d_seq, b->seq, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
-        CK(cudaMemcpyAsync(s.d_qual, b->qual, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
+        if (b->qual == b->seq) s.u_qual = s.d_seq;       // raw FASTQ text: one blob, uploaded once
+        else CK(cudaMemcpyAsync(s.d_qual, b->qual, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.d_offsets, b->offsets, sizeof(uint64_t) * b->n_reads, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.d_lengths, b->lengths, sizeof(uint32_t) * b->n_reads, cudaMemcpyHostToDevice, s.stream));
-        if (s.has_names) {
-            if (name_bytes)
-                CK(cudaMemcpyAsync(s.d_names, b->names, name_bytes, cudaMemcpyHostToDevice, s.stream));
-            CK(cudaMemcpyAsync(s.d_name_offsets, b->name_offsets, sizeof(uint64_t) * (b->n_reads + 1),
+        if (b->qual_offsets) {
+            CK(cudaMemcpyAsync(s.d_qual_offsets, b->qual_offsets, sizeof(uint64_t) * b->n_reads,
                                cudaMemcpyHostToDevice, s.stream));
+            s.u_qual_offsets = s.d_qual_offsets;
+        }
+        if (s.has_names) {
+            if (names_alias) s.u_names = s.d_seq;
+            else if (name_bytes)
+                CK(cudaMemcpyAsync(s.d_names, b->names, name_bytes, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(s.d_name_offsets, b->name_offsets,
+                               sizeof(uint64_t) * (b->n_reads + (b->name_lengths ? 0 : 1)),
+                               cudaMemcpyHostToDevice, s.stream));
+            if (b->name_lengths) {
+                CK(cudaMemcpyAsync(s.d_name_lengths, b->name_lengths, sizeof(uint32_t) * b->n_reads,
+                                   cudaMemcpyHostToDevice, s.stream));
+                s.u_name_lengths = s.d_name_lengths;
+            }
         }
     }
     CK(cudaEventRecord(s.ev[EV_H2D], s.stream));
@@ -399,6 +424,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             A.match0 = s.d_match[0];
             A.drop_bins = ctx->d_drop;
             A.name_offsets = s.has_names ? s.d_name_offsets : nullptr;
+            A.name_lengths = s.has_names ? s.u_name_lengths : nullptr;
             A.bin = s.d_bin;
             A.out_len = s.d_out_len;
             A.rec_bytes = s.d_rec_bytes;
@@ -425,7 +451,8 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     }
     CK(cudaEventRecord(s.ev[EV_BIN], st));
     if (n && s.has_names) {
-        emit_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(s.d_seq, s.d_qual, s.d_names, s.d_name_offsets,
+        emit_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(s.d_seq, s.u_qual, s.u_names, s.d_name_offsets,
+                                                       s.u_name_lengths, s.d_offsets, s.u_qual_offsets,
                                                        s.d_views[ctx->n_rounds], s.d_dest, n, ctx->d_comp_lut,
                                                        s.d_fastq);
     }
@@ -564,6 +591,60 @@ extern "C" int orc_counts(orc_ctx *ctx, uint64_t *bins)
     if (!ctx || !bins) return ORC_EINVAL;
     memcpy(bins, ctx->total_counts.data(), sizeof(uint64_t) * (size_t)ctx->n_bins);
     return ORC_OK;
+}
+
+// FASTQ record indexer: 4 lines per record, '@' header, '+' separator, |seq| == |qual|.
+extern "C" int64_t orc_fastq_index(const uint8_t *text, uint64_t n_bytes, uint32_t max_reads, int final,
+                                   uint64_t *seq_offsets, uint32_t *lengths, uint64_t *qual_offsets,
+                                   uint64_t *name_offsets, uint32_t *name_lengths, uint64_t *consumed,
+                                   char *err, size_t err_len)
+{
+    auto fail = [&](const char *what, uint64_t rec) -> int64_t {
+        if (err && err_len) snprintf(err, err_len, "FASTQ record %llu: %s", (unsigned long long)rec, what);
+        return ORC_EINVAL;
+    };
+    uint64_t pos = 0;
+    int64_t n = 0;
+    while (n < (int64_t)max_reads && pos < n_bytes) {
+        uint64_t ls[4], le[4];      // line starts / ends (exclusive, newline and '\r' stripped)
+        uint64_t p = pos;
+        int got = 0;
+        for (int l = 0; l < 4; l++) {
+            if (p > n_bytes) break;
+            const uint8_t *nl = p < n_bytes ? (const uint8_t *)memchr(text + p, '\n', n_bytes - p) : nullptr;
+            uint64_t end;
+            if (nl) end = (uint64_t)(nl - text);
+            else if (final && l == 3 && p <= n_bytes) end = n_bytes;     // last line without newline
+            else break;
+            ls[l] = p;
+            le[l] = (end > p && text[end - 1] == '\r') ? end - 1 : end;
+            p = end + 1;
+            got++;
+        }
+        if (got < 4) {
+            if (final && got > 0) {
+                // tolerate a trailing blank line, reject a truncated record
+                bool blank = true;
+                for (uint64_t i = pos; i < n_bytes; i++) if (text[i] != '\n' && text[i] != '\r') blank = false;
+                if (!blank) return fail("truncated record at end of input", (uint64_t)n);
+                pos = n_bytes;
+            }
+            break;
+        }
+        if (le[0] == ls[0] || text[ls[0]] != '@') return fail("header line does not start with '@'", (uint64_t)n);
+        if (le[2] == ls[2] || text[ls[2]] != '+') return fail("third line does not start with '+'", (uint64_t)n);
+        if (le[1] - ls[1] != le[3] - ls[3]) return fail("sequence and qualities differ in length", (uint64_t)n);
+        if (le[1] - ls[1] > 0xffffffffull) return fail("read longer than 4 Gi bases", (uint64_t)n);
+        name_offsets[n] = ls[0] + 1;
+        name_lengths[n] = (uint32_t)(le[0] - ls[0] - 1);
+        seq_offsets[n] = ls[1];
+        lengths[n] = (uint32_t)(le[1] - ls[1]);
+        qual_offsets[n] = ls[3];
+        pos = p > n_bytes ? n_bytes : p;
+        n++;
+    }
+    if (consumed) *consumed = pos;
+    return n;
 }
 
 extern "C" void *orc_host_alloc(size_t bytes)

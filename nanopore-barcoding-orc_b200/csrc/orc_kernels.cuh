@@ -232,6 +232,7 @@ struct SelectArgs {
     const Match *match0;        // round-1 matches (== out when n_rounds == 1)
     const uint8_t *drop_bins;
     const uint64_t *name_offsets;   // may be nullptr (no FASTQ emission)
+    const uint32_t *name_lengths;   // may be nullptr (then name r ends where name r+1 starts)
     int32_t *bin;
     uint32_t *out_len, *rec_bytes;
     unsigned long long *next_bases;   // sum of the view lengths that enter the next round (or nullptr)
@@ -276,7 +277,8 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs A)
         A.out_len[r] = next.len;
         uint32_t rb = 0;
         if (b >= 0 && A.name_offsets != nullptr) {
-            const uint32_t nl = (uint32_t)(A.name_offsets[r + 1] - A.name_offsets[r]);
+            const uint32_t nl = A.name_lengths ? A.name_lengths[r]
+                                               : (uint32_t)(A.name_offsets[r + 1] - A.name_offsets[r]);
             rb = 1u + nl + 3u * (next.rc >> 8) + 1u + next.len + 3u + next.len + 1u;   // @name[ rc]*\nSEQ\n+\nQUAL\n
         }
         A.rec_bytes[r] = rb;
@@ -386,7 +388,8 @@ bin_place_kernel(const int32_t *__restrict__ bin, const uint32_t *__restrict__ r
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
             const uint8_t *__restrict__ names, const uint64_t *__restrict__ name_offsets,
-            const View *__restrict__ views, const uint64_t *__restrict__ dest, uint32_t n_reads,
+            const uint32_t *__restrict__ name_lengths, const uint64_t *__restrict__ offsets,
+            const uint64_t *__restrict__ qual_offsets, const View *__restrict__ views, const uint64_t *__restrict__ dest, uint32_t n_reads,
             const uint8_t *__restrict__ comp_lut_g, uint8_t *__restrict__ out)
 {
     __shared__ uint8_t comp[256];
@@ -400,7 +403,7 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
         if (d == ~0ull) continue;
         const View v = views[r];
         const uint64_t n0 = name_offsets[r];
-        const uint32_t nl = (uint32_t)(name_offsets[r + 1] - n0);
+        const uint32_t nl = name_lengths ? name_lengths[r] : (uint32_t)(name_offsets[r + 1] - n0);
         const uint32_t nrc = v.rc >> 8;
         const uint32_t L = v.len;
         uint8_t *o = out + d;
@@ -411,7 +414,8 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
         o += 3 * nrc;
         if (lane == 0) o[0] = '\n';
         o += 1;
-        const uint8_t *s = seq + v.lo, *q = qual + v.lo;
+        const uint8_t *s = seq + v.lo;
+        const uint8_t *q = qual + v.lo + (qual_offsets ? qual_offsets[r] - offsets[r] : 0ull);
         if (v.rc & 1u) {
             for (uint32_t i = lane; i < L; i += 32) {
                 o[i] = comp[s[L - 1 - i]];

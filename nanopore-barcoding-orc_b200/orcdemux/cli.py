@@ -1,0 +1,311 @@
+"""cutadapt-compatible command line for the demultiplexing step (drop-in for the two call
+shapes of /root/reference/scripts/02_cutadapt_loop.sh):
+
+  round 1 (02:64-72)   cutadapt --action=trim -e 0.1 -j 24 --rc -g file:FWD.fa
+                                -o DIR/SP5/{name}_DS.fastq.gz IN.fastq.gz --json=REPORT
+  round 2 (02:94-102)  cutadapt --action=trim -e 0.1 -j 24 --rc -a file:REV_RC.fa
+                                -o DIR/SP27/{name}_SP5id_DS.fastq.gz DIR/SP5/SP5id_DS.fastq.gz --json=REPORT
+
+Kept surface: -g/-a (file:PATH, SEQ, name=SEQ; several allowed), -e, -O, --no-indels (refused
+for unanchored adapters until its kernel exists), --action=trim, --rc, -j (accepted), --json,
+-o with {name} (one file per adapter name plus "unknown", all created even if empty).
+Anything else exits with status 2 and an "unsupported" message: there is no CPU fallback.
+
+`python -m orcdemux.cli two-round ...` runs both rounds fused on the GPU and leaves the file
+tree of the whole script (02:107-119: unknown and SP27_009..012 removed).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+from typing import List, Optional
+
+import numpy as np
+
+from . import engine as E
+from . import fastq as F
+from .lib import ORC_BACK, ORC_FRONT
+
+
+class Unsupported(Exception):
+    pass
+
+
+def _parse_adapter_specs(specs: List[str], kind: int):
+    names, seqs = [], []
+    for spec in specs:
+        anchored = False
+        s = spec
+        if kind == ORC_FRONT and s.startswith("^"):
+            anchored, s = True, s[1:]
+        if s.startswith("file:"):
+            path = s[5:]
+            if path.endswith("$") and kind == ORC_BACK:
+                anchored, path = True, path[:-1]
+            n, q = F.read_adapters_fasta(path)
+        else:
+            name = None
+            if "=" in s:
+                name, s = s.split("=", 1)
+            if kind == ORC_BACK and s.endswith("$"):
+                anchored, s = True, s[:-1]
+            if kind == ORC_FRONT and s.startswith("^"):
+                anchored, s = True, s[1:]
+            n, q = [name], [s.upper().replace("U", "T")]
+        if anchored:
+            raise Unsupported("anchored adapters (^/$) take the Hamming fast path, not wired into this CLI yet")
+        for a, b in zip(n, q):
+            if any(c in b for c in "X.;{}[]"):
+                raise Unsupported("adapter syntax beyond plain sequences: %r" % b)
+            names.append(a)
+            seqs.append(b)
+    # cutadapt names unnamed adapters "1", "2", ... in order
+    names = [nm if nm else str(i + 1) for i, nm in enumerate(names)]
+    return names, seqs
+
+
+def parse_cutadapt_argv(argv: List[str]):
+    opt = dict(e=0.1, O=3, rc=False, indels=True, action="trim", json=None, out=None, cores=1,
+               g=[], a=[], level=5, inputs=[], quiet=False)
+    i = 0
+
+    def need(flag):
+        nonlocal i
+        i += 1
+        if i >= len(argv):
+            raise Unsupported("option %s needs a value" % flag)
+        return argv[i]
+
+    while i < len(argv):
+        a = argv[i]
+        if a.startswith("--") and "=" in a:
+            key, val = a.split("=", 1)
+        else:
+            key, val = a, None
+        if key in ("-e", "--error-rate", "--errors"):
+            opt["e"] = float(val if val is not None else need(key))
+        elif a.startswith("-e") and len(a) > 2 and not a.startswith("--"):
+            opt["e"] = float(a[2:])
+        elif key in ("-O", "--overlap"):
+            opt["O"] = int(val if val is not None else need(key))
+        elif a.startswith("-O") and len(a) > 2 and not a.startswith("--"):
+            opt["O"] = int(a[2:])
+        elif key in ("-j", "--cores"):
+            opt["cores"] = int(val if val is not None else need(key))
+        elif a.startswith("-j") and len(a) > 2 and not a.startswith("--"):
+            opt["cores"] = int(a[2:])
+        elif key in ("--rc", "--revcomp"):
+            opt["rc"] = True
+        elif key == "--no-indels":
+            opt["indels"] = False
+        elif key == "--action":
+            opt["action"] = val if val is not None else need(key)
+        elif key in ("-g", "--front"):
+            opt["g"].append(val if val is not None else need(key))
+        elif key in ("-a", "--adapter"):
+            opt["a"].append(val if val is not None else need(key))
+        elif key in ("-o", "--output"):
+            opt["out"] = val if val is not None else need(key)
+        elif key == "--json":
+            opt["json"] = val if val is not None else need(key)
+        elif key in ("-Z",):
+            opt["level"] = 1
+        elif key == "--compression-level":
+            opt["level"] = int(val if val is not None else need(key))
+        elif key in ("--quiet", "--report"):
+            if key == "--report" and val is None:
+                need(key)
+            opt["quiet"] = opt["quiet"] or key == "--quiet"
+        elif a.startswith("-") and a != "-":
+            raise Unsupported("cutadapt option %s is outside the demultiplexing surface this build replaces" % a)
+        else:
+            opt["inputs"].append(a)
+        i += 1
+    if opt["action"] != "trim":
+        raise Unsupported("--action=%s (only trim)" % opt["action"])
+    if len(opt["inputs"]) != 1:
+        raise Unsupported("exactly one (single-end) input file is expected, got %d" % len(opt["inputs"]))
+    if bool(opt["g"]) == bool(opt["a"]):
+        raise Unsupported("give either -g or -a adapters (one adapter type per invocation)")
+    if not opt["out"] or "{name}" not in opt["out"]:
+        raise Unsupported("-o with a {name} template is required (demultiplexing mode)")
+    if not opt["indels"]:
+        raise Unsupported("--no-indels for unanchored adapters")
+    return opt
+
+
+def _report(n_in, bp_in, bp_out, n_with, n_rc, names, per_adapter, elapsed, argv):
+    return {
+        "tag": "Cutadapt report", "schema_version": [0, 3],
+        "cutadapt_version": "4.9-compatible (orcdemux, B200)",
+        "command_line_arguments": argv, "cores": 1,
+        "input": {"path1": None, "path2": None, "paired": False},
+        "read_counts": {"input": n_in, "filtered": {"too_short": None, "too_long": None, "too_many_n": None,
+                                                    "too_many_expected_errors": None, "casava_filtered": None,
+                                                    "discard_trimmed": None, "discard_untrimmed": None},
+                        "output": n_in, "reverse_complemented": n_rc, "read1_with_adapter": n_with,
+                        "read2_with_adapter": None},
+        "basepair_counts": {"input": bp_in, "input_read1": bp_in, "input_read2": None, "quality_trimmed": None,
+                            "quality_trimmed_read1": None, "quality_trimmed_read2": None, "poly_a_trimmed": None,
+                            "output": bp_out, "output_read1": bp_out, "output_read2": None},
+        "adapters_read1": [{"name": nm, "total_matches": int(c)} for nm, c in zip(names, per_adapter)],
+        "adapters_read2": None, "elapsed_seconds": elapsed,
+    }
+
+
+def run_single_round(opt, argv, device=0) -> int:
+    kind = ORC_FRONT if opt["g"] else ORC_BACK
+    names, seqs = _parse_adapter_specs(opt["g"] or opt["a"], kind)
+    rnd = E.Round(names, seqs, kind, opt["e"], opt["O"], opt["indels"], opt["rc"])
+    t0 = time.time()
+    max_reads, max_bytes, slots = 1 << 18, 1 << 28, 2
+    reader = F.FastqReader(opt["inputs"][0], max_reads, max_bytes, n_buffers=slots + 2)
+    paths = [opt["out"].replace("{name}", "unknown")] + [opt["out"].replace("{name}", n) for n in names]
+    writers = F.BinWriters(paths, opt["level"], threads=max(2, min(16, opt["cores"])))
+    n_in = bp_in = bp_out = n_with = n_rc = 0
+    per = np.zeros(len(names), dtype=np.int64)
+    try:
+        with E.Engine([rnd], device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
+                      emit_fastq=True, want_matches=True) as eng:
+            def drain(slot, tb):
+                nonlocal n_in, bp_in, bp_out, n_with, n_rc, per
+                res = eng.wait(slot, copy=False)
+                m = res.matches[0]
+                n_in += res.n_reads
+                bp_in += tb.total_bases()
+                bp_out += int(res.out_len.sum(dtype=np.uint64))
+                has = m["adapter"] >= 0
+                n_with += int(has.sum())
+                n_rc += int((m["is_rc"] != 0).sum())
+                per += np.bincount(m["adapter"][has], minlength=len(names))
+                writers.write_batch(res)
+            inflight = []
+            k = 0
+            for tb in reader:
+                if len(inflight) == slots:
+                    drain(*inflight.pop(0))
+                eng.submit(k % slots, tb)
+                inflight.append((k % slots, tb))
+                k += 1
+            while inflight:
+                drain(*inflight.pop(0))
+    finally:
+        writers.close()
+    rep = _report(n_in, bp_in, bp_out, n_with, n_rc, names, per, time.time() - t0, argv)
+    rep["input"]["path1"] = opt["inputs"][0]
+    if opt["json"]:
+        with open(opt["json"], "w") as fh:
+            json.dump(rep, fh, indent=2)
+    if not opt["quiet"]:
+        print("This is orcdemux (cutadapt 4.9-compatible demultiplexing on B200)")
+        print("=== Summary ===\n")
+        print("Total reads processed:           %12d" % n_in)
+        print("Reads with adapters:             %12d (%.1f%%)" % (n_with, 100.0 * n_with / max(n_in, 1)))
+        print("Reverse-complemented:            %12d (%.1f%%)" % (n_rc, 100.0 * n_rc / max(n_in, 1)))
+        print("Reads written (passing filters): %12d (100.0%%)\n" % n_in)
+        print("Total basepairs processed: %12d bp" % bp_in)
+        print("Total written (filtered):  %12d bp (%.1f%%)" % (bp_out, 100.0 * bp_out / max(bp_in, 1)))
+    return 0
+
+
+def dataset_name(infile: str) -> str:
+    """02_cutadapt_loop.sh:25-35."""
+    ds = os.path.basename(infile)
+    if ds.startswith("pychopped_"):
+        ds = ds[len("pychopped_"):]
+    for suf in (".fastq.gz", ".fastq", ".fq.gz", ".fq", ".gz", "_pass"):
+        if ds.endswith(suf):
+            ds = ds[:-len(suf)]
+    return ds
+
+
+def run_two_round(args: List[str], device=0) -> int:
+    """Both rounds fused: the file tree 02_cutadapt_loop.sh leaves in demuxed/SP27/."""
+    import argparse
+    ap = argparse.ArgumentParser(prog="orcdemux two-round")
+    ap.add_argument("input")
+    ap.add_argument("--sp5", required=True, help="FASTA of the 5' SP5 adapters (-g file:)")
+    ap.add_argument("--sp27", required=True, help="FASTA of the 3' SP27 rc adapters (-a file:)")
+    ap.add_argument("-e", type=float, default=0.1)
+    ap.add_argument("-O", type=int, default=3)
+    ap.add_argument("--outdir", default=None)
+    ap.add_argument("--keep-unknown", action="store_true")
+    ap.add_argument("--keep-invalid", action="store_true", help="keep SP27_009..012 combinations")
+    ap.add_argument("--no-gzip", action="store_true")
+    ap.add_argument("-j", type=int, default=8)
+    a = ap.parse_args(args)
+    n5, s5 = F.read_adapters_fasta(a.sp5)
+    n27, s27 = F.read_adapters_fasta(a.sp27)
+    ds = dataset_name(a.input)
+    outdir = a.outdir or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(a.input))), "demuxed")
+    os.makedirs(os.path.join(outdir, "SP5"), exist_ok=True)
+    os.makedirs(os.path.join(outdir, "SP27"), exist_ok=True)
+    rounds = [E.Round(n5, s5, ORC_FRONT, a.e, a.O, True, True), E.Round(n27, s27, ORC_BACK, a.e, a.O, True, True)]
+    ext = ".fastq" if a.no_gzip else ".fastq.gz"
+    n_bins = (len(n5) + 1) * (len(n27) + 1)
+    drop = np.zeros(n_bins, dtype=np.uint8)
+    paths: List[Optional[str]] = [None] * n_bins
+    invalid = {"SP27_009", "SP27_010", "SP27_011", "SP27_012"}      # 02:114-118
+    for b in range(n_bins):
+        i5, i27 = b % (len(n5) + 1) - 1, b // (len(n5) + 1) - 1
+        nm5 = n5[i5] if i5 >= 0 else "unknown"
+        nm27 = n27[i27] if i27 >= 0 else "unknown"
+        unknown = i5 < 0 or i27 < 0
+        if (unknown and not a.keep_unknown) or (nm27 in invalid and not a.keep_invalid) or i5 < 0:
+            drop[b] = 1
+            continue
+        paths[b] = os.path.join(outdir, "SP27", "%s_%s_%s%s" % (nm27, nm5, ds, ext))
+    max_reads, max_bytes, slots = 1 << 18, 1 << 28, 2
+    reader = F.FastqReader(a.input, max_reads, max_bytes, n_buffers=slots + 2)
+    writers = F.BinWriters(paths, 5, threads=max(2, min(16, a.j)))
+    t0 = time.time()
+    n_in = 0
+    try:
+        with E.Engine(rounds, device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
+                      emit_fastq=True, want_matches=False, drop_bins=drop) as eng:
+            inflight = []
+            k = 0
+            for tb in reader:
+                if len(inflight) == slots:
+                    res = eng.wait(inflight.pop(0), copy=False)
+                    n_in += res.n_reads
+                    writers.write_batch(res)
+                eng.submit(k % slots, tb)
+                inflight.append(k % slots)
+                k += 1
+            while inflight:
+                res = eng.wait(inflight.pop(0), copy=False)
+                n_in += res.n_reads
+                writers.write_batch(res)
+            counts = eng.counts()
+    finally:
+        writers.close()
+    with open(os.path.join(outdir, "SP27", "orcdemux_%s.json" % ds), "w") as fh:
+        json.dump({"dataset": ds, "reads": n_in, "elapsed_seconds": time.time() - t0,
+                   "bins": {os.path.basename(p): int(counts[b]) for b, p in enumerate(paths) if p}}, fh, indent=1)
+    print("Demultiplexing complete! %d reads, results in: %s" % (n_in, outdir))
+    return 0
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    try:
+        if argv and argv[0] == "two-round":
+            return run_two_round(argv[1:])
+        if argv and argv[0] in ("--version",):
+            print("4.9 (orcdemux)")
+            return 0
+        opt = parse_cutadapt_argv(argv)
+        return run_single_round(opt, argv)
+    except Unsupported as e:
+        sys.stderr.write("orcdemux: unsupported: %s\n" % e)
+        return 2
+    except (E.OrcError, ValueError, OSError) as e:
+        sys.stderr.write("orcdemux: error: %s\n" % e)
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -158,6 +158,17 @@ class Engine:
     def _batch(self, rs) -> _lib.Batch:
         b = _lib.Batch()
         b.n_reads = rs.n_reads
+        if hasattr(rs, "text"):                     # fastq.TextBatch: raw FASTQ text, one blob
+            b.n_bytes = int(rs.n_bytes)
+            b.seq = b.qual = rs.text.ctypes.data
+            b.offsets = rs.offsets.ctypes.data
+            b.lengths = rs.lengths.ctypes.data
+            b.qual_offsets = rs.qual_offsets.ctypes.data
+            if self.emit_fastq:
+                b.names = rs.text.ctypes.data
+                b.name_offsets = rs.name_offsets.ctypes.data
+                b.name_lengths = rs.name_lengths.ctypes.data
+            return b
         b.n_bytes = int(rs.seq.shape[0])
         b.seq = rs.seq.ctypes.data
         b.qual = rs.qual.ctypes.data
@@ -166,6 +177,7 @@ class Engine:
         if self.emit_fastq:
             b.names = rs.names.ctypes.data
             b.name_offsets = rs.name_offsets.ctypes.data
+            b.name_bytes = int(rs.names.shape[0])
         return b
 
     def submit(self, slot: int, rs):

@@ -23,7 +23,7 @@ ORC_OK, ORC_EINVAL, ORC_ECUDA, ORC_ECAPACITY, ORC_ESTATE = 0, -1, -2, -3, -4
 # every symbol include/orcdemux.h declares
 EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_submit", "orc_wait",
            "orc_upload", "orc_launch", "orc_download", "orc_sync", "orc_get_timings", "orc_timer_start", "orc_timer_stop", "orc_counts",
-           "orc_host_alloc", "orc_host_free", "orc_measure_int32_peak", "orc_version"]
+           "orc_fastq_index", "orc_host_alloc", "orc_host_free", "orc_measure_int32_peak", "orc_version"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -49,7 +49,8 @@ class Params(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_bytes", C.c_uint64),
                 ("seq", C.c_void_p), ("qual", C.c_void_p), ("offsets", C.c_void_p), ("lengths", C.c_void_p),
-                ("names", C.c_void_p), ("name_offsets", C.c_void_p)]
+                ("qual_offsets", C.c_void_p), ("names", C.c_void_p), ("name_offsets", C.c_void_p),
+                ("name_lengths", C.c_void_p), ("name_bytes", C.c_uint64)]
 
 
 class Result(C.Structure):
@@ -101,6 +102,9 @@ def load():
     L.orc_get_timings.restype = C.c_int
     L.orc_counts.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_counts.restype = C.c_int
+    L.orc_fastq_index.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
+    L.orc_fastq_index.restype = C.c_int64
     L.orc_host_alloc.argtypes = [C.c_size_t]
     L.orc_host_alloc.restype = C.c_void_p
     L.orc_host_free.argtypes = [C.c_void_p]

@@ -34,7 +34,7 @@ def test_header_symbols_are_exported():
 def test_struct_sizes_match_header():
     # spot-check the layouts ctypes mirrors
     assert C.sizeof(lib.RoundParams) == 48
-    assert C.sizeof(lib.Batch) == 64
+    assert C.sizeof(lib.Batch) == 88
     assert lib.MATCH_DTYPE.itemsize == 32
 
 

@@ -1,0 +1,132 @@
+"""The drop-in boundary on the GPU: the cutadapt-compatible command line replays
+/root/reference/scripts/02_cutadapt_loop.sh:64-118 (round 1, the round-2 loop over the SP5
+bins, the clean-up of `unknown` and SP27_009..012) on FASTQ(.gz) files, and the file tree and
+decompressed bytes must equal what the oracle predicts.  The fused `two-round` command must
+leave the same demuxed/SP27 tree."""
+import glob
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+from orcdemux import cli, m13, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _expected_tree(rs, ds):
+    """{relative path: bytes} after the reference script, from the oracle."""
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(H.m13_rounds(), rs)
+    n5 = [n for n, _ in m13.sp5_forward()]
+    n27 = [n for n, _ in m13.sp27_reverse_rc()]
+    sp27 = {}
+    for a in n5:
+        for b in n27[:8]:
+            sp27["SP27/%s_%s_%s.fastq.gz" % (b, a, ds)] = []
+    for r in range(rs.n_reads):
+        a0, a1 = int(rec0["adapter"][r]), int(rec1["adapter"][r])
+        if a0 < 0 or a1 < 0 or a1 >= 8:
+            continue
+        name = rs.read(r)[0] + (" rc" if rec0["is_rc"][r] else "") + (" rc" if rec1["is_rc"][r] else "")
+        o, L = int(rs.offsets[r]), int(olen[r])
+        sp27["SP27/%s_%s_%s.fastq.gz" % (n27[a1], n5[a0], ds)].append(
+            b"@" + name.encode() + b"\n" + oseq[o:o + L].tobytes() + b"\n+\n" + oqual[o:o + L].tobytes() + b"\n")
+    return {k: b"".join(v) for k, v in sp27.items()}, rec0
+
+
+def _read_gz(path):
+    with gzip.open(path, "rb") as fh:
+        return fh.read()
+
+
+def test_reference_script_flow_and_fused(tmp_path):
+    rs = synth.generate(6000, 300, 900, seed=77)
+    ds = "sample1"
+    work = tmp_path
+    (work / "pychopped").mkdir()
+    infile = work / "pychopped" / ("pychopped_%s_pass.fastq.gz" % ds)
+    with gzip.open(infile, "wb", compresslevel=1) as fh:
+        fh.write(rs.to_fastq_bytes())
+    assert cli.dataset_name(str(infile)) == ds
+    fwd, rev, _ = m13.write_tables(str(work / "adapters"))
+    out = work / "demuxed"
+    (out / "SP5").mkdir(parents=True)
+    (out / "SP27").mkdir(parents=True)
+    shim = os.path.join(H.PKG, "bin", "cutadapt")
+
+    # round 1 (02:64-72), options after the positional input like the reference
+    r = subprocess.run([shim, "--action=trim", "-e", "0.1", "-j", "24", "--rc", "-g", "file:" + fwd,
+                        "-o", str(out / "SP5" / ("{name}_%s.fastq.gz" % ds)), str(infile),
+                        "--json=" + str(out / "SP5" / ("cutadapt_SP5_%s.json" % ds))],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    suffix = "_%s.fastq.gz" % ds
+    ids = sorted(os.path.basename(p)[:-len(suffix)] for p in glob.glob(str(out / "SP5" / ("*" + suffix))))
+    assert len(ids) == 13 and "unknown" in ids          # every bin file exists, even if empty
+    ids = [i for i in ids if "unknown" not in i]         # 02:75-80
+    rep = json.load(open(out / "SP5" / ("cutadapt_SP5_%s.json" % ds)))
+    assert rep["read_counts"]["input"] == rs.n_reads
+
+    # round 2 (02:91-103)
+    for ident in ids:
+        r = subprocess.run([shim, "--action=trim", "-e", "0.1", "-j", "24", "--rc", "-a", "file:" + rev,
+                            "-o", str(out / "SP27" / ("{name}_%s_%s.fastq.gz" % (ident, ds))),
+                            str(out / "SP5" / ("%s_%s.fastq.gz" % (ident, ds))),
+                            "--json=" + str(out / "SP27" / ("%s_%s.json" % (ident, ds)))],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    # clean-up (02:110-118)
+    for p in glob.glob(str(out / "**" / "*unknown*"), recursive=True):
+        os.remove(p)
+    for k in ("009", "010", "011", "012"):
+        for p in glob.glob(str(out / "**" / ("*SP27_%s*" % k)), recursive=True):
+            os.remove(p)
+
+    expected, rec0 = _expected_tree(rs, ds)
+    got = sorted(os.path.relpath(p, out) for p in glob.glob(str(out / "SP27" / "*.fastq.gz")))
+    assert got == sorted(expected)                       # 96 files
+    assert len(got) == 96
+    for rel, data in expected.items():
+        assert _read_gz(out / rel) == data, rel
+    assert rep["read_counts"]["read1_with_adapter"] == int((rec0["adapter"] >= 0).sum())
+    assert rep["read_counts"]["reverse_complemented"] == int(rec0["is_rc"].sum())
+
+    # the fused two-round command leaves the same SP27 tree
+    out2 = work / "demuxed_fused"
+    r = subprocess.run([sys.executable, "-m", "orcdemux.cli", "two-round", str(infile), "--sp5", fwd, "--sp27", rev,
+                        "--outdir", str(out2)], capture_output=True, text=True,
+                       env=dict(os.environ, PYTHONPATH=H.PKG))
+    assert r.returncode == 0, r.stderr
+    got2 = sorted(os.path.relpath(p, out2) for p in glob.glob(str(out2 / "SP27" / "*.fastq.gz")))
+    assert got2 == sorted(expected)
+    for rel, data in expected.items():
+        assert _read_gz(out2 / rel) == data, rel
+
+
+def test_unsupported_exits_2(tmp_path):
+    shim = os.path.join(H.PKG, "bin", "cutadapt")
+    r = subprocess.run([shim, "-m", "20", "-g", "ACGT", "-o", str(tmp_path / "{name}.fq"), "in.fq"],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "unsupported" in r.stderr
+
+
+def test_raw_text_layout_equals_blob_layout(tmp_path):
+    from orcdemux import engine as E
+    from orcdemux import fastq as F
+    rs = synth.generate(3000, 300, 900, seed=5)
+    p = tmp_path / "x.fastq"
+    p.write_bytes(rs.to_fastq_bytes())
+    tb = next(iter(F.FastqReader(str(p), max_reads=4096, max_bytes=1 << 23, n_buffers=2)))
+    assert tb.n_reads == rs.n_reads
+    with E.Engine(E.m13_rounds(), max_reads=4096, max_bytes=1 << 23, n_slots=1) as eng:
+        a = eng.run(tb)
+        b = eng.run(rs)
+    assert a.fastq.tobytes() == b.fastq.tobytes()
+    assert np.array_equal(a.bin, b.bin)
+    for x, y in zip(a.matches, b.matches):
+        assert H.diff_matches(x, y)[1] == 0
