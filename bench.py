@@ -191,6 +191,8 @@ def main():
         print(json.dumps({"error": "no CUDA device: bench.py has no CPU fallback for the product arm"}))
         return 2
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

@@ -431,13 +431,17 @@ ORC_HD int popc64(uint64_t x)
 #endif
 }
 
+// The ring is indexed by the column's distance from the scan start ws: the lanes of a warp
+// scan in lockstep, so they touch the same slot at the same time and the lane-interleaved
+// local memory sees one coalesced access per column instead of 32 scattered ones.
 // D[i][j] of a stored column j, i in 0..m
-ORC_HD int ring_cost(const ColRing &R, int m, int i, int j)
+ORC_HD int ring_cost(const ColRing &R, int m, int i, int j, int ws)
 {
     const int sh = 64 - m + i;                      // bits of the rows i+1..m start here
-    if (sh >= 64) return R.dm[j & (RING - 1)];
-    const uint64_t pv = R.pv[j & (RING - 1)] >> sh, mv = R.mv[j & (RING - 1)] >> sh;
-    return (int)R.dm[j & (RING - 1)] - popc64(pv) + popc64(mv);
+    const int x = (j - ws) & (RING - 1);
+    if (sh >= 64) return R.dm[x];
+    const uint64_t pv = R.pv[x] >> sh, mv = R.mv[x] >> sh;
+    return (int)R.dm[x] - popc64(pv) + popc64(mv);
 }
 
 // Walk cutadapt's path back from cell (i, j) whose cost is d.  ws is the first stored
@@ -461,10 +465,10 @@ ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, co
             score += 1; --i; --j;
             continue;
         }
-        const uint64_t pvj = R.pv[j & (RING - 1)], mvj = R.mv[j & (RING - 1)];
-        const uint64_t pvl = R.pv[(j - 1) & (RING - 1)], mvl = R.mv[(j - 1) & (RING - 1)];
+        const uint64_t pvj = R.pv[(j - ws) & (RING - 1)], mvj = R.mv[(j - ws) & (RING - 1)];
+        const uint64_t pvl = R.pv[(j - 1 - ws) & (RING - 1)], mvl = R.mv[(j - 1 - ws) & (RING - 1)];
         const int d_up = d - (int)((pvj >> bit) & 1u) + (int)((mvj >> bit) & 1u);
-        const int d_left = ring_cost(R, m, i, j - 1);
+        const int d_left = ring_cost(R, m, i, j - 1, ws);
         const int d_diag = d_left - (int)((pvl >> bit) & 1u) + (int)((mvl >> bit) & 1u);
         const int c_diag = d_diag + 1, c_del = d_left + 1, c_ins = d_up + 1;
         if (c_diag <= c_del && c_diag <= c_ins) { score -= 1; --i; --j; d = d_diag; }
@@ -488,7 +492,7 @@ ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, 
     int D;
     if (ws == 0 && type == TYPE_FRONT) { Pv = 0; D = 0; }       // R2, true column 0 of a 5' adapter
     else { Pv = ~pad; D = m; }                                  // cost i (true for BACK at 0; restart otherwise)
-    R.pv[ws & (RING - 1)] = Pv; R.mv[ws & (RING - 1)] = 0; R.dm[ws & (RING - 1)] = (int16_t)D;
+    R.pv[0] = Pv; R.mv[0] = 0; R.dm[0] = (int16_t)D;
     int traced_j = -1, traced_score = 0, traced_origin = 0;
     // Upper bound of a candidate's score: every error costs at least 2 (score <= length - 2*cost),
     // except the errors a 3' adapter takes in column 0 (cost i, score 0: R2), reachable only if
@@ -505,7 +509,7 @@ ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, 
         Ph <<= 1; Mh <<= 1;
         Pv = Mh | ~(Xv | Ph);
         Mv = Ph & Xv;
-        R.pv[j & (RING - 1)] = Pv; R.mv[j & (RING - 1)] = Mv; R.dm[j & (RING - 1)] = (int16_t)D;
+        { const int x = (j - ws) & (RING - 1); R.pv[x] = Pv; R.mv[x] = Mv; R.dm[x] = (int16_t)D; }
         if (j >= jf && j <= jl && D <= k) {
             const int lmax = imin(m, j + D);
             if (lmax >= min_ov && D <= (int)kmax[lmax]) {
@@ -525,7 +529,7 @@ ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, 
     if (r6 && we == n && n > ws) {
         // R6: rows r6hi..r6lo of column n, top row first like cutadapt
         for (int i = imin(r6hi, m); i >= imax(r6lo, 1); i--) {
-            const int Di = ring_cost(R, m, i, n);
+            const int Di = ring_cost(R, m, i, n, ws);
             if (Di > k) continue;
             const int lmax = (type == TYPE_FRONT) ? imin(i, n + Di) : i;
             if (!(lmax >= min_ov && Di <= (int)kmax[lmax])) continue;
