@@ -50,7 +50,8 @@ struct Slot {
     uint32_t *d_lengths = nullptr;
     View *d_views[3] = {nullptr, nullptr, nullptr};
     Match *d_match[2] = {nullptr, nullptr};
-    uint32_t *d_read_mask = nullptr, *d_read_base = nullptr;
+    uint32_t *d_wcols = nullptr, *d_wcols_sorted = nullptr, *d_item_in = nullptr, *d_item_order = nullptr;
+    unsigned long long *d_best_key = nullptr;
     uint32_t *d_key_in = nullptr, *d_key_out = nullptr, *d_val_in = nullptr, *d_order = nullptr;
     void *d_sort_tmp = nullptr;
     WinList *d_wins = nullptr;
@@ -125,8 +126,9 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_lengths, R));
     for (int i = 0; i < 3; i++) CK(dalloc(&s.d_views[i], R));
     for (int i = 0; i < 2; i++) CK(dalloc(&s.d_match[i], R));
-    CK(dalloc(&s.d_read_mask, R));
-    CK(dalloc(&s.d_read_base, R));
+    CK(dalloc(&s.d_wcols, 2 * R)); CK(dalloc(&s.d_wcols_sorted, 2 * R));
+    CK(dalloc(&s.d_item_in, 2 * R)); CK(dalloc(&s.d_item_order, 2 * R));
+    CK(dalloc(&s.d_best_key, 2 * R));
     CK(dalloc(&s.d_key_in, R)); CK(dalloc(&s.d_key_out, R)); CK(dalloc(&s.d_val_in, R)); CK(dalloc(&s.d_order, R));
     CK(cudaMalloc(&s.d_sort_tmp, ctx->sort_tmp_bytes + 64));
     CK(dalloc(&s.d_wins, 2 * R));
@@ -167,7 +169,8 @@ static void free_slot(Slot &s)
     cudaFree(s.d_lengths); cudaFree(s.d_qual_offsets); cudaFree(s.d_name_lengths);
     for (int i = 0; i < 3; i++) cudaFree(s.d_views[i]);
     for (int i = 0; i < 2; i++) { cudaFree(s.d_match[i]); cudaFreeHost(s.h_match[i]); }
-    cudaFree(s.d_read_mask); cudaFree(s.d_read_base); cudaFree(s.d_tasks); cudaFree(s.d_results);
+    cudaFree(s.d_wcols); cudaFree(s.d_wcols_sorted); cudaFree(s.d_item_in); cudaFree(s.d_item_order);
+    cudaFree(s.d_best_key); cudaFree(s.d_tasks); cudaFree(s.d_results);
     cudaFree(s.d_key_in); cudaFree(s.d_key_out); cudaFree(s.d_val_in); cudaFree(s.d_order);
     cudaFree(s.d_sort_tmp); cudaFree(s.d_wins);
     cudaFree(s.d_counters); cudaFree(s.d_cells); cudaFree(s.d_bin); cudaFree(s.d_out_len);
@@ -239,7 +242,7 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     {
         uint32_t *nk = nullptr;
-        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, ctx->sort_tmp_bytes, nk, nk, nk, nk, (int)ctx->max_reads));
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, ctx->sort_tmp_bytes, nk, nk, nk, nk, 2 * (int)ctx->max_reads));
     }
     ctx->slots.resize((size_t)ctx->n_slots);
     for (auto &s : ctx->slots) {
@@ -388,34 +391,42 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     for (int r = 0; r < ctx->n_rounds; r++) {
         const Match *prev = r == 0 ? nullptr : s.d_match[r - 1];
         const bool filter = ctx->h_tab[r].use_filter != 0;
-        if (n && filter) {
-            // stage 1: order the reads by length, then one 32-bit scan of the shared prefix per
-            // (read, direction) marks the column windows that stage 2 has to look at
-            sort_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_views[r], prev, n, s.d_key_in, s.d_val_in);
+        uint32_t *cnt = s.d_counters + 4 * r;       // job counter, result slots, resolver tasks
+        if (n) {
+            CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
+            // stage 1: (with a usable shared prefix) order the reads by length and let one 32-bit
+            // scan of the prefix per (read, direction) mark the column windows stage 2 must look at
             size_t tmp = ctx->sort_tmp_bytes;
-            CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_key_in, s.d_key_out, s.d_val_in,
-                                                         s.d_order, (int)n, 0, 32, st));
-            trigger_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], prev, s.d_order, n,
-                                                               s.d_wins);
+            if (filter) {
+                sort_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_views[r], prev, n, s.d_key_in, s.d_val_in);
+                CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_key_in, s.d_key_out, s.d_val_in,
+                                                             s.d_order, (int)n, 0, 32, st));
+            }
+            trigger_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], prev,
+                                                               filter ? s.d_order : nullptr, n, s.d_wins,
+                                                               s.d_wcols, s.d_item_in);
+            // order the (read, direction) items by the columns they have to scan
+            tmp = ctx->sort_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_wcols, s.d_wcols_sorted, s.d_item_in,
+                                                         s.d_item_order, 2 * (int)n, 0, 32, st));
         }
         CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
         if (n) {
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
-                ctx->d_tab[r], W, s.d_views[r], prev, filter ? s.d_wins : nullptr, n, s.d_tasks,
-                s.d_counters + 2 + r, s.d_read_mask, s.d_read_base, s.d_counters + r);
+                ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_results,
+                s.d_tasks, s.d_best_key, cnt);
         }
         CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         if (n) {
-            resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], s.d_tasks,
-                                                               s.d_counters + 2 + r, s.d_results);
+            resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2,
+                                                               s.d_results, s.d_best_key);
             SelectArgs A;
             A.tab = ctx->d_tab[r];
             A.views_in = s.d_views[r];
             A.views_out = s.d_views[r + 1];
             A.prev = prev;
             A.out = s.d_match[r];
-            A.read_mask = s.d_read_mask;
-            A.read_base = s.d_read_base;
+            A.best_key = s.d_best_key;
             A.results = s.d_results;
             A.n_reads = n;
             A.last_round = (r == ctx->n_rounds - 1);
@@ -570,10 +581,11 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     CK(cudaMemcpy(&emit_bytes, s.d_bin_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 3u + (s.has_names ? 1u : 0u)) : 1u;
     if (s.n_reads)
-        for (int r = 0; r < ctx->n_rounds; r++)
-            if (ctx->h_tab[r].use_filter) t->kernel_launches += 2u;   // sort_keys + trigger (CUB's own launches not counted)
+        for (int r = 0; r < ctx->n_rounds; r++)     // trigger (+ sort_keys); CUB's own launches are not counted
+            t->kernel_launches += ctx->h_tab[r].use_filter ? 2u : 1u;
     for (int r = 0; r < ctx->n_rounds; r++) {
-        t->n_tasks[r] = counters[2 + r];
+        t->n_tasks[r] = counters[4 * r + 2];
+        t->n_candidates[r] = counters[4 * r + 1];
         const RoundTable &T = ctx->h_tab[r];
         // algorithmic cells: pairs * m * n summed over the reads entering the round
         uint64_t msum = 0;

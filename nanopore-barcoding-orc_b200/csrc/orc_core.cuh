@@ -81,7 +81,8 @@ struct Task {
     uint32_t lane;      // adapter + n_adapters * storage direction
     int32_t jf, jl;     // columns (1-based) of the last row that may be acceptable; jf > jl: none
     int32_t i1, i2;     // rows of the last column that may be acceptable (BACK); i1 > i2: none
-    int32_t pad_[2];
+    uint32_t slot;      // where the pair's PairResult goes
+    int32_t pad_;
 };
 
 // Aligner.locate's return value (R7) for one pair.
@@ -135,6 +136,35 @@ ORC_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s)
     return r;
 }
 #endif
+
+// cutadapt's running best match of one Aligner.locate call (R5-R7) and one DP cell.
+struct Best { int32_t score, cost, origin, ref_stop, query_stop; };
+struct Cell { int32_t cost, score, origin; };
+
+// R5 update (last row).  Returns true when cutadapt stops scanning (exact full match).
+ORC_HD bool r5_update(Best &b, int m, int n, const Cell &c, int j, int min_ov, const uint8_t *kmax)
+{
+    const int length = m + imin(c.origin, 0);
+    if (!(length >= min_ov && c.cost <= (int)kmax[length])) return false;
+    const int best_length = m + imin(b.origin, 0);
+    if (b.cost == m + n + 1 ||
+        (c.origin <= b.origin + m / 2 && c.score > b.score) ||
+        (length > best_length && c.score > b.score)) {
+        b.score = c.score; b.cost = c.cost; b.origin = c.origin; b.ref_stop = m; b.query_stop = j;
+        return c.cost == 0 && c.origin >= 0;
+    }
+    return false;
+}
+
+// R6 update (last column, row i)
+ORC_HD void r6_update(Best &b, int n, const Cell &c, int i, int min_ov, const uint8_t *kmax)
+{
+    const int length = i + imin(c.origin, 0);
+    if (!(length >= min_ov && c.cost <= (int)kmax[length])) return;
+    if (c.score > b.score || (c.score == b.score && c.cost < b.cost)) {
+        b.score = c.score; b.cost = c.cost; b.origin = c.origin; b.ref_stop = i; b.query_stop = n;
+    }
+}
 
 // ------------------------------------------------------------------------------------
 // The scan, in two stages.
@@ -225,7 +255,8 @@ ORC_HD void win_add(WinList &L, bool &open, uint32_t &cs, uint32_t &ce, uint32_t
 }
 
 // Stage 1.  peq32_base: table of the shared prefix, entry (code, lane) at code*256 + lane*4,
-// row Lp at bit 31.  kt = largest k of the round, ext = m_max - Lp + kt, back = Lp + 2*kt + 1.
+// row Lp at bit 31.  kt = largest k of the round, ext = m_max - Lp + kt, back = Lp + kt + 1
+// (an alignment through (Lp, j') with <= kt errors starts at a column >= j' - Lp - kt).
 ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                          const char *peq32_base, int lane, int Lp, int kt, int type,
                          uint32_t ext, uint32_t back, WinList &out)
@@ -291,17 +322,43 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     if (open) { out.s[out.n] = cs; out.e[out.n] = ce; out.n++; }
 }
 
-// Stage 2: columns s+1 .. e of one pair.  Widens the candidate hull in `h`.
+ORC_HD uint32_t win_columns(const WinList &w)
+{
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < w.n; i++) c += w.e[i] - w.s[i];
+    return c;
+}
+
+// Per-pair state of stage 2.  Candidates of cost 0 are settled on the spot: their path is a
+// pure diagonal of matches (a zero-cost cell has equal characters and a zero-cost diagonal
+// predecessor, all the way to row 0 or column 0), so score = min(j, m) and origin = j - m.
+// Only pairs that meet a candidate of cost > 0 (`need`) go to the resolver, which redoes the
+// whole pair from its hull.
+struct LaneScan {
+    ScanHull h;
+    Best best;
+    int32_t need;       // a candidate with cost > 0 was seen: the resolver decides
+    int32_t broke;      // R5 hit its early exit (exact full match) while settling inline
+};
+
+ORC_HD void lane_scan_init(LaneScan &L, int m, int n)
+{
+    L.h.jf = 0x7fffffff; L.h.jl = -1; L.h.i1 = 0x7fffffff; L.h.i2 = -1;
+    L.best.ref_stop = m; L.best.query_stop = n; L.best.cost = m + n + 1; L.best.origin = 0; L.best.score = 0;
+    L.need = 0; L.broke = 0;
+}
+
+// Stage 2: columns s+1 .. e of one pair.
 ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                         uint32_t s, uint32_t e, const char *peq_base, int lane, uint64_t pv0, int d0,
-                        int m, int k, const uint8_t *kmax, int min_ov, int type, ScanHull &h)
+                        int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L)
 {
     const uint64_t pad = (m == 64) ? 0ull : ((1ull << (64 - m)) - 1ull);
+    const int n = (int)len;
     uint64_t Pv, Mv = 0;
     int D;
     if (s == 0) { Pv = pv0; D = d0; }            // R2: the true column 0
     else { Pv = ~pad; D = m; }                   // restart: cost i
-    int jf = h.jf, jl = h.jl;
     const uint32_t lane8 = (uint32_t)lane * 8u;
     // PRMT selectors: result byte0 <- lane8.byte0, byte1 <- code byte b, bytes 2,3 <- 0
     uint32_t sel0, sel1, sel2, sel3;
@@ -311,6 +368,7 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
     rd.init(W, lo, len, dir, s);
     const int ncols = (int)(e - s);
     const int nchunks = (ncols + 7) >> 3;
+    int last_d = -1;                             // D[m][n] if column n was a candidate
     for (int q = 0; q < nchunks; q++) {
         uint32_t A, B;
         rd.next(A, B);
@@ -342,72 +400,98 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
                     // most min(m, j + D) adapter characters.
                     const int j = (int)s + 8 * q + t + 1;
                     const int lmax = imin(m, j + D);
-                    if (lmax >= min_ov && D <= (int)kmax[lmax]) { jf = imin(jf, j); jl = j; }
+                    if (lmax >= min_ov && D <= (int)kmax[lmax]) {
+                        L.h.jf = imin(L.h.jf, j);
+                        L.h.jl = j;
+                        if (j == n) last_d = D;
+                        if (D == 0) {
+                            if (!L.need && !L.broke) {
+                                Cell c;
+                                c.cost = 0; c.score = imin(j, m); c.origin = j - m;
+                                if (r5_update(L.best, m, n, c, j, min_ov, kmax)) L.broke = 1;
+                            }
+                        } else {
+                            L.need = 1;
+                        }
+                    }
                 }
             }
         } else {
             D += popc32(accP) - popc32(accM);
         }
     }
-    h.jf = jf; h.jl = jl;
-    if (type == TYPE_BACK && e == len) {
+    if (e != len) return;
+    if (type == TYPE_BACK) {
         // R6 necessary condition for the cells (i, n): origin >= 0 for BACK, so length == i
-        int i1 = h.i1, i2 = h.i2, cum = 0;
+        int cum = 0;
+        uint64_t zero_rows = 0;
         for (int i = 1; i <= m; i++) {
             const int bit = 64 - m + i - 1;
             cum += (int)((Pv >> bit) & 1u) - (int)((Mv >> bit) & 1u);
-            if (i >= min_ov && cum <= (int)kmax[i]) { i1 = imin(i1, i); i2 = i; }
+            if (i >= min_ov && cum <= (int)kmax[i]) {
+                L.h.i1 = imin(L.h.i1, i);
+                L.h.i2 = i;
+                if (cum == 0) zero_rows |= 1ull << (i - 1);
+                else L.need = 1;
+            }
         }
-        h.i1 = i1; h.i2 = i2;
+        if (!L.need && !L.broke) {
+            for (int i = m; i >= 1; i--) {       // top row first, like cutadapt
+                if (!((zero_rows >> (i - 1)) & 1ull)) continue;
+                Cell c;
+                c.cost = 0; c.score = i; c.origin = n - i;
+                r6_update(L.best, n, c, i, min_ov, kmax);
+            }
+        }
+    } else if (last_d == 0 && !L.need && !L.broke) {
+        // FRONT: R6 looks at the single cell (m, n)
+        Cell c;
+        c.cost = 0; c.score = imin(n, m); c.origin = n - m;
+        r6_update(L.best, n, c, m, min_ov, kmax);
     }
 }
 
 // All windows of one pair.  wl == nullptr: no prefix filter, one window over the whole view.
 ORC_HD void scan_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                       const WinList *wl, const char *peq_base, int lane, uint64_t pv0, int d0,
-                      int m, int k, const uint8_t *kmax, int min_ov, int type, ScanHull &out)
+                      int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L)
 {
-    out.jf = 0x7fffffff; out.jl = -1; out.i1 = 0x7fffffff; out.i2 = -1;
+    lane_scan_init(L, m, (int)len);
     if (wl == nullptr) {
-        scan_window(W, lo, len, dir, 0u, len, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, out);
+        scan_window(W, lo, len, dir, 0u, len, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, L);
         return;
     }
     const uint32_t nw = wl->n;
     for (uint32_t w = 0; w < nw; w++)
-        scan_window(W, lo, len, dir, wl->s[w], wl->e[w], peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, out);
+        scan_window(W, lo, len, dir, wl->s[w], wl->e[w], peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, L);
+}
+
+// Aligner.locate's return value (R7) from the running best
+ORC_HD void best_to_result(const Best &best, int m, int n, PairResult &res)
+{
+    res.pad_ = 0;
+    if (best.cost == m + n + 1) {
+        res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = res.score = res.errors = 0;
+        return;
+    }
+    res.has = 1;
+    if (best.origin >= 0) { res.ref_start = 0; res.query_start = best.origin; }
+    else { res.ref_start = -best.origin; res.query_start = 0; }
+    res.ref_stop = best.ref_stop; res.query_stop = best.query_stop;
+    res.score = best.score; res.errors = best.cost;
+}
+
+// R8 as one unsigned 64-bit maximum per (read, orientation): higher score, then fewer errors,
+// then the adapter that comes first in the file; the low word says where the result lives.
+ORC_HD uint64_t pack_key(int score, int errors, int adapter, uint32_t slot)
+{
+    return ((uint64_t)(uint32_t)(score + 512) << 42) | ((uint64_t)(uint32_t)(63 - errors) << 36) |
+           ((uint64_t)(uint32_t)(15 - adapter) << 32) | (uint64_t)slot;
 }
 
 // ------------------------------------------------------------------------------------
 // resolve_pair: exact (cost, score, origin) on a diagonal band, then R5/R6/R7.
 // ------------------------------------------------------------------------------------
-struct Best { int32_t score, cost, origin, ref_stop, query_stop; };
-struct Cell { int32_t cost, score, origin; };
-
-// R5 update (last row).  Returns true when cutadapt stops scanning (exact full match).
-ORC_HD bool r5_update(Best &b, int m, int n, const Cell &c, int j, int min_ov, const uint8_t *kmax)
-{
-    const int length = m + imin(c.origin, 0);
-    if (!(length >= min_ov && c.cost <= (int)kmax[length])) return false;
-    const int best_length = m + imin(b.origin, 0);
-    if (b.cost == m + n + 1 ||
-        (c.origin <= b.origin + m / 2 && c.score > b.score) ||
-        (length > best_length && c.score > b.score)) {
-        b.score = c.score; b.cost = c.cost; b.origin = c.origin; b.ref_stop = m; b.query_stop = j;
-        return c.cost == 0 && c.origin >= 0;
-    }
-    return false;
-}
-
-// R6 update (last column, row i)
-ORC_HD void r6_update(Best &b, int n, const Cell &c, int i, int min_ov, const uint8_t *kmax)
-{
-    const int length = i + imin(c.origin, 0);
-    if (!(length >= min_ov && c.cost <= (int)kmax[length])) return;
-    if (c.score > b.score || (c.score == b.score && c.cost < b.cost)) {
-        b.score = c.score; b.cost = c.cost; b.origin = c.origin; b.ref_stop = i; b.query_stop = n;
-    }
-}
-
 // The resolver re-runs the bit-parallel scan over the columns that matter for one pair and
 // keeps the vertical deltas (Pv, Mv) and D[m][j] of the last RING columns.  From them any
 // cost D[i][j'] of those columns is a popcount away, which is all that cutadapt's
@@ -574,46 +658,22 @@ ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, 
         resolve_scan(W, v.lo, v.len, dir, peq_lane, m, T.type, k, kmax, min_ov,
                      ws6, n, 1, 0, true, r6lo, r6hi, best, R);
     }
-    if (best.cost == m + n + 1) { res.has = 0; return; }
-    res.has = 1;
-    if (best.origin >= 0) { res.ref_start = 0; res.query_start = best.origin; }
-    else { res.ref_start = -best.origin; res.query_start = 0; }
-    res.ref_stop = best.ref_stop; res.query_stop = best.query_stop;
-    res.score = best.score; res.errors = best.cost;
+    best_to_result(best, m, n, res);
 }
 
 // ------------------------------------------------------------------------------------
-// select_read: R8, R9, R10.  `mask` has one bit per lane that produced a task; the
-// results of those lanes are res[0..popc(mask)) in lane order.
+// select_read: R9, R10 from the per-orientation winners of R8.  key[o] is the maximum of
+// pack_key() over the pairs of logical orientation o that matched (0 = none).
 // ------------------------------------------------------------------------------------
-ORC_HD void select_read(const RoundTable &T, const View &v, uint32_t mask, const PairResult *res,
+ORC_HD void select_read(const RoundTable &T, const View &v, const uint64_t key[2], const PairResult *results,
                         Match &out, View &next)
 {
-    const int na = T.n_adapters;
-    int best_a[2] = {-1, -1};
-    PairResult best_r[2];
-    best_r[0].score = best_r[1].score = 0;
-    best_r[0].errors = best_r[1].errors = 0;
-    int idx = 0;
-    for (int lane = 0; lane < T.n_lanes; lane++) {
-        if (!((mask >> lane) & 1u)) continue;
-        const PairResult r = res[idx++];
-        if (!r.has) continue;
-        const int a = lane % na;
-        const int o = (lane / na) ^ (int)(v.rc & 1u);     // logical orientation searched by the lane
-        // R8: score, then errors, then file order (lanes of one direction ascend with a)
-        if (best_a[o] < 0 || r.score > best_r[o].score ||
-            (r.score == best_r[o].score && r.errors < best_r[o].errors)) {
-            best_a[o] = a;
-            best_r[o] = r;
-        }
-    }
-    const int fs = best_a[0] >= 0 ? best_r[0].score : 0;
-    const int rs = best_a[1] >= 0 ? best_r[1].score : 0;
+    const int fs = key[0] ? (int)(key[0] >> 42) - 512 : 0;
+    const int rs = key[1] ? (int)(key[1] >> 42) - 512 : 0;
     const int o = (T.revcomp && rs > fs) ? 1 : 0;          // R9: strictly higher score
     next = v;
     const uint32_t eff = (v.rc & 1u) ^ (uint32_t)o;
-    if (best_a[o] < 0) {
+    if (!key[o]) {
         // no match.  o == 1 here means reverse_score 0 > forward_score < 0 (high error rates):
         // cutadapt then passes on the reverse complement, name + " rc", with no match.
         out.adapter = -1; out.is_rc = o;
@@ -621,8 +681,8 @@ ORC_HD void select_read(const RoundTable &T, const View &v, uint32_t mask, const
         next.rc = ((v.rc & ~1u) | eff) + ((uint32_t)o << 8);
         return;
     }
-    const PairResult &r = best_r[o];
-    out.adapter = best_a[o]; out.is_rc = o;
+    const PairResult r = results[(uint32_t)key[o]];
+    out.adapter = 15 - (int)((key[o] >> 32) & 15u); out.is_rc = o;
     out.ref_start = r.ref_start; out.ref_stop = r.ref_stop;
     out.query_start = r.query_start; out.query_stop = r.query_stop;
     out.score = r.score; out.errors = r.errors;

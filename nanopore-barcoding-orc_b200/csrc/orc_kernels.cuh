@@ -91,46 +91,62 @@ __global__ void sort_keys_kernel(const View *__restrict__ views, const Match *__
 __global__ void __launch_bounds__(128)
 trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                const View *__restrict__ views, const Match *__restrict__ prev,
-               const uint32_t *__restrict__ order, uint32_t n_reads, WinList *__restrict__ wins)
+               const uint32_t *__restrict__ order, uint32_t n_reads, WinList *__restrict__ wins,
+               uint32_t *__restrict__ wcols, uint32_t *__restrict__ item_ids)
 {
     __shared__ __align__(16) uint32_t s_peq32[16][64];
     __shared__ int s_par[8];
     for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32[0][0])[i] = (&tab->peq32[0][0])[i];
     if (threadIdx.x == 0) {
         s_par[0] = tab->lcp; s_par[1] = tab->k_max; s_par[2] = tab->m_max; s_par[3] = tab->type;
-        s_par[4] = tab->revcomp;
+        s_par[4] = tab->revcomp; s_par[5] = tab->use_filter;
     }
     __syncthreads();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= 2u * n_reads) return;
-    const uint32_t r = order[p >> 1];
+    const uint32_t r = order ? order[p >> 1] : (p >> 1);
     const int dir = (int)(p & 1u);
     const int Lp = s_par[0], kt = s_par[1], m_max = s_par[2], type = s_par[3];
     WinList wl;
     wl.n = 0; wl.pad_ = 0;
     for (int i = 0; i < MAX_WIN; i++) { wl.s[i] = 0; wl.e[i] = 0; }
+    uint32_t cols = 0;
     const bool skip = prev != nullptr && prev[r].adapter < 0;
     if (!skip) {
         const View v = views[r];
-        if (s_par[4] || ((dir ^ (int)(v.rc & 1u)) == 0))
-            trigger_lane(W, v.lo, v.len, dir, reinterpret_cast<const char *>(&s_peq32[0][0]),
-                         (int)(threadIdx.x & 63u), Lp, kt, type, (uint32_t)(m_max - Lp + kt),
-                         (uint32_t)(Lp + 2 * kt + 1), wl);
+        if (s_par[4] || ((dir ^ (int)(v.rc & 1u)) == 0)) {
+            if (s_par[5]) {
+                trigger_lane(W, v.lo, v.len, dir, reinterpret_cast<const char *>(&s_peq32[0][0]),
+                             (int)(threadIdx.x & 63u), Lp, kt, type, (uint32_t)(m_max - Lp + kt),
+                             (uint32_t)(Lp + kt + 1), wl);
+                cols = win_columns(wl);
+            } else {
+                wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything
+                cols = v.len;
+            }
+            cols += 1;      // an active pair with nothing to scan (empty read) still has its last column
+        }
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(wins + (size_t)r * 2 + dir);
+    const uint32_t item = r * 2u + (uint32_t)dir;
+    uint4 *dst = reinterpret_cast<uint4 *>(wins + item);
     const uint4 *src = reinterpret_cast<const uint4 *>(&wl);
     dst[0] = src[0]; dst[1] = src[1];
+    wcols[item] = cols;
+    item_ids[item] = item;
 }
 
 // ------------------------------------------------------------------------------------
-// Stage 2 of the scan: persistent warps pull reads from a global counter.
+// Stage 2 of the scan.  A job is one (read, direction, adapter) pair; the (read, direction)
+// items come sorted by the number of window columns they have to scan, so the 32 lanes of a
+// warp -- 32 consecutive jobs, i.e. the adapters of two or three items -- run the same number
+// of columns.  Persistent warps pull 32 jobs at a time from a global counter.  A pair whose
+// candidates all have cost 0 is finished here; the others go to the resolver's work list.
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
-            const View *__restrict__ views, const Match *__restrict__ prev,
-            const WinList *__restrict__ wins, uint32_t n_reads,
-            Task *__restrict__ tasks, uint32_t *__restrict__ task_count,
-            uint32_t *__restrict__ read_mask, uint32_t *__restrict__ read_base,
-            uint32_t *__restrict__ work_counter)
+            const View *__restrict__ views, const WinList *__restrict__ wins,
+            const uint32_t *__restrict__ wcols_sorted, const uint32_t *__restrict__ item_order,
+            uint32_t n_items, PairResult *__restrict__ results, Task *__restrict__ work,
+            unsigned long long *__restrict__ best_key, uint32_t *__restrict__ counters)
 {
     __shared__ __align__(16) RoundTable T;
     {
@@ -140,61 +156,87 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int na = T.n_adapters;
-    const bool lane_used = lane < T.n_lanes;
-    const int a = lane_used ? lane % na : 0;
-    const int dir = lane_used ? lane / na : 0;
-    const int m = T.m[a], k = T.k[a], min_ov = T.min_ov[a], type = T.type;
-    const uint64_t pv0 = T.pv0[lane_used ? lane : 0];
-    const int d0 = T.d0[lane_used ? lane : 0];
-    const uint8_t *kmax = T.kmax[a];
+    const uint32_t na = (uint32_t)T.n_adapters;
+    const uint32_t n_jobs = n_items * na;
     const char *peq_base = reinterpret_cast<const char *>(&T.peq[0][0]);
+    const int type = T.type;
+    uint32_t *job_counter = counters + 0, *res_count = counters + 1, *work_count = counters + 2;
 
     for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(job_counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_jobs) break;
+        const uint32_t p = base + (uint32_t)lane;
+        bool active = p < n_jobs;
+        uint32_t it = 0, item = 0;
+        int a = 0;
+        if (active) {
+            it = p / na;
+            a = (int)(p - it * na);
+            active = wcols_sorted[it] != 0u;     // sorted descending: inactive items are at the end
+            item = item_order[it];
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        bool has = false, need = false;
+        LaneScan L;
         uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(work_counter, 1u);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= n_reads) break;
-        uint32_t mask = 0, base = 0;
-        const bool skip = prev != nullptr && prev[r].adapter < 0;   // "unknown" never enters round 2
-        if (!skip) {
+        int o = 0, m = 0;
+        uint32_t n = 0;
+        if (active) {
+            r = item >> 1;
+            const int dir = (int)(item & 1u);
             const View v = views[r];
-            const bool active = lane_used && (T.revcomp || ((dir ^ (int)(v.rc & 1u)) == 0));
-            ScanHull h;
-            h.jf = 1; h.jl = 0; h.i1 = 1; h.i2 = 0;
-            if (active) {
-                WinList wl;
-                if (wins != nullptr) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(wins + (size_t)r * 2 + dir);
-                    uint4 *dst = reinterpret_cast<uint4 *>(&wl);
-                    dst[0] = src[0]; dst[1] = src[1];
-                }
-                scan_lane(W, v.lo, v.len, dir, wins != nullptr ? &wl : nullptr, peq_base, lane, pv0, d0,
-                          m, k, kmax, min_ov, type, h);
+            o = dir ^ (int)(v.rc & 1u);
+            n = v.len;
+            const int tl = a + (int)na * dir;
+            m = T.m[a];
+            WinList wl;
+            {
+                const uint4 *src = reinterpret_cast<const uint4 *>(wins + item);
+                uint4 *dst = reinterpret_cast<uint4 *>(&wl);
+                dst[0] = src[0]; dst[1] = src[1];
             }
-            const bool has = active && (h.jf <= h.jl || h.i1 <= h.i2);
-            mask = __ballot_sync(0xffffffffu, has);
-            if (mask) {
-                if (lane == 0) base = atomicAdd(task_count, (uint32_t)__popc(mask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (has) {
-                    Task t;
-                    t.read = r; t.lane = (uint32_t)lane;
-                    t.jf = h.jf; t.jl = h.jl; t.i1 = h.i1; t.i2 = h.i2;
-                    t.pad_[0] = t.pad_[1] = 0;
-                    tasks[base + __popc(mask & lanemask_lt())] = t;
-                }
+            scan_lane(W, v.lo, v.len, dir, &wl, peq_base, tl, T.pv0[tl], T.d0[tl], m, T.k[a], T.kmax[a],
+                      T.min_ov[a], type, L);
+            has = L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2;
+            need = has && L.need != 0;
+        }
+        const uint32_t mh = __ballot_sync(0xffffffffu, has);
+        if (mh) {
+            uint32_t rb = 0;
+            if (lane == 0) rb = atomicAdd(res_count, (uint32_t)__popc(mh));
+            rb = __shfl_sync(0xffffffffu, rb, 0);
+            const uint32_t slot = rb + (uint32_t)__popc(mh & lanemask_lt());
+            const uint32_t mn = __ballot_sync(0xffffffffu, need);
+            uint32_t wb = 0;
+            if (mn) {
+                if (lane == 0) wb = atomicAdd(work_count, (uint32_t)__popc(mn));
+                wb = __shfl_sync(0xffffffffu, wb, 0);
+            }
+            if (need) {
+                Task t;
+                t.read = r; t.lane = (uint32_t)(a + (int)na * (int)(item & 1u));
+                t.jf = L.h.jf; t.jl = L.h.jl; t.i1 = L.h.i1; t.i2 = L.h.i2;
+                t.slot = slot; t.pad_ = 0;
+                work[wb + (uint32_t)__popc(mn & lanemask_lt())] = t;
+            } else if (has) {
+                PairResult res;
+                best_to_result(L.best, m, (int)n, res);
+                results[slot] = res;
+                if (res.has)
+                    atomicMax(best_key + (size_t)r * 2 + o, (unsigned long long)pack_key(res.score, res.errors, a, slot));
             }
         }
-        if (lane == 0) { read_mask[r] = mask; read_base[r] = base; }
     }
 }
 
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
-               const View *__restrict__ views, const Task *__restrict__ tasks,
-               const uint32_t *__restrict__ task_count, PairResult *__restrict__ results)
+               const View *__restrict__ views, const Task *__restrict__ work,
+               const uint32_t *__restrict__ work_count, PairResult *__restrict__ results,
+               unsigned long long *__restrict__ best_key)
 {
     __shared__ __align__(16) RoundTable T;
     {
@@ -203,16 +245,22 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
         for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const uint32_t n = *task_count;
+    const uint32_t n = *work_count;
     ColRing ring;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const Task task = tasks[t];
+        const Task task = work[t];
         const View v = views[task.read];
         PairResult res;
         res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = 0;
         res.score = res.errors = 0; res.pad_ = 0;
         resolve_pair(W, v, T, task, res, ring);
-        results[t] = res;
+        results[task.slot] = res;
+        if (res.has) {
+            const int a = (int)task.lane % T.n_adapters;
+            const int o = ((int)task.lane / T.n_adapters) ^ (int)(v.rc & 1u);
+            atomicMax(best_key + (size_t)task.read * 2 + o,
+                      (unsigned long long)pack_key(res.score, res.errors, a, task.slot));
+        }
     }
 }
 
@@ -224,7 +272,7 @@ struct SelectArgs {
     View *views_out;
     const Match *prev;          // matches of the previous round (nullptr in round 1)
     Match *out;
-    const uint32_t *read_mask, *read_base;
+    const unsigned long long *best_key;   // [n_reads][2]
     const PairResult *results;
     uint32_t n_reads;
     // last round only:
@@ -258,7 +306,10 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs A)
         mt.adapter = -1; mt.is_rc = 0;
         mt.ref_start = mt.ref_stop = mt.query_start = mt.query_stop = mt.score = mt.errors = 0;
     } else {
-        select_read(T, v, A.read_mask[r], A.results + A.read_base[r], mt, next);
+        uint64_t key[2];
+        key[0] = A.best_key[(size_t)r * 2];
+        key[1] = A.best_key[(size_t)r * 2 + 1];
+        select_read(T, v, key, A.results, mt, next);
     }
     if (A.next_bases != nullptr) {
         const uint32_t add = (valid && mt.adapter >= 0) ? next.len : 0u;

@@ -51,34 +51,42 @@ extern "C" int hostsim_demux(int n_rounds,
         m1[r].adapter = -1;
         for (int rd = 0; rd < n_rounds; rd++) {
             const RoundTable &R = T[rd];
-            uint32_t mask = 0;
             std::vector<PairResult> results;
+            uint64_t keys[2] = {0, 0};
             WinList wl[2];
             if (R.use_filter) {
                 for (int dir = 0; dir < 2; dir++) {
                     trigger_lane(W, v.lo, v.len, dir, (const char *)&R.peq32[0][0], dir, R.lcp, R.k_max, R.type,
-                                 (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + 2 * R.k_max + 1), wl[dir]);
-                    for (uint32_t w = 0; w < wl[dir].n; w++) n_columns[rd] += wl[dir].e[w] - wl[dir].s[w];
+                                 (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + R.k_max + 1), wl[dir]);
+                    n_columns[rd] += win_columns(wl[dir]);
                 }
             } else n_columns[rd] += 2ull * v.len;
             for (int lane = 0; lane < R.n_lanes; lane++) {
                 const int a = lane % R.n_adapters, dir = lane / R.n_adapters;
                 const int o = dir ^ (int)(v.rc & 1u);
                 if (o == 1 && !R.revcomp) continue;
-                ScanHull h;
+                LaneScan L;
                 scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, (const char *)&R.peq[0][0], lane,
-                          R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, h);
-                if (h.jf <= h.jl || h.i1 <= h.i2) {
-                    Task t; t.read = r; t.lane = (uint32_t)lane; t.jf = h.jf; t.jl = h.jl; t.i1 = h.i1; t.i2 = h.i2;
+                          R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, L);
+                if (L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2) {
                     PairResult pr; memset(&pr, 0, sizeof(pr));
-                    resolve_pair(W, v, R, t, pr, *ring);
+                    if (!L.need) {
+                        best_to_result(L.best, R.m[a], (int)v.len, pr);
+                    } else {
+                        Task t; t.read = r; t.lane = (uint32_t)lane;
+                        t.jf = L.h.jf; t.jl = L.h.jl; t.i1 = L.h.i1; t.i2 = L.h.i2; t.slot = (uint32_t)results.size();
+                        resolve_pair(W, v, R, t, pr, *ring);
+                        n_tasks[rd]++;
+                    }
+                    if (pr.has) {
+                        const uint64_t key = pack_key(pr.score, pr.errors, a, (uint32_t)results.size());
+                        if (key > keys[o]) keys[o] = key;
+                    }
                     results.push_back(pr);
-                    mask |= 1u << lane;
-                    n_tasks[rd]++;
                 }
             }
             View next;
-            select_read(R, v, mask, results.data(), *out[rd], next);
+            select_read(R, v, keys, results.data(), *out[rd], next);
             v = next;
             if (out[rd]->adapter < 0) break;     // 02:75-80: "unknown" never enters round 2
         }
