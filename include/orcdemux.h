@@ -135,6 +135,7 @@ typedef struct orc_timings {
     uint32_t n_tasks[ORC_MAX_ROUNDS]; /* candidate pairs that needed the resolver's exact walk */
     uint32_t n_candidates[ORC_MAX_ROUNDS]; /* pairs with any candidate cell (incl. those settled in the scan) */
     uint64_t cells[ORC_MAX_ROUNDS];   /* algorithmic DP cells: pairs * m * n   */
+    uint64_t cells_executed[ORC_MAX_ROUNDS]; /* DP cells the two scan stages really updated */
     uint64_t pack_bytes, emit_bytes;  /* algorithmic bytes moved by pack / emit */
 } orc_timings;
 

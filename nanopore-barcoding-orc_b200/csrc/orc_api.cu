@@ -38,6 +38,7 @@ struct Slot {
     int state = SLOT_IDLE;
     uint32_t n_reads = 0;
     uint64_t n_bytes = 0, name_bytes = 0, in_bases = 0;
+    int len_bits = 32;                       // bits needed for the longest read of the batch (+1)
     bool has_names = false;
     bool did_h2d = false, did_kernels = false, did_d2h = false, fresh_upload = false;
     // device
@@ -58,7 +59,7 @@ struct Slot {
     Task *d_tasks = nullptr;
     PairResult *d_results = nullptr;
     uint32_t *d_counters = nullptr;          // [0..1] work counters, [2..3] task counts
-    unsigned long long *d_cells = nullptr;   // [2] sum of view lengths entering each round
+    unsigned long long *d_cells = nullptr;   // [0..1] sum of view lengths entering each round, [2..3] window columns
     int32_t *d_bin = nullptr;
     uint32_t *d_out_len = nullptr, *d_rec_bytes = nullptr, *d_hist_cnt = nullptr;
     uint64_t *d_hist_bytes = nullptr, *d_bin_counts = nullptr, *d_bin_offsets = nullptr;
@@ -135,7 +136,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_tasks, n_tasks));
     CK(dalloc(&s.d_results, n_tasks));
     CK(dalloc(&s.d_counters, 8));
-    CK(dalloc(&s.d_cells, 2));
+    CK(dalloc(&s.d_cells, 4));
     CK(dalloc(&s.d_bin, R));
     CK(dalloc(&s.d_out_len, R));
     CK(dalloc(&s.d_rec_bytes, R));
@@ -147,7 +148,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(halloc(&s.h_bin, R));
     CK(halloc(&s.h_out_len, R));
     CK(halloc(&s.h_counters, 8));
-    CK(halloc(&s.h_cells, 2));
+    CK(halloc(&s.h_cells, 4));
     CK(halloc(&s.h_bin_counts, (size_t)ctx->n_bins));
     CK(halloc(&s.h_bin_offsets, (size_t)ctx->n_bins + 1));
     if (ctx->want_matches)
@@ -321,7 +322,9 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
     s.n_bytes = b->n_bytes;
     s.name_bytes = name_bytes;
     uint64_t bases = 0;
+    uint32_t max_len = 0;
     for (uint32_t r = 0; r < b->n_reads; r++) {
+        if (b->lengths[r] > max_len) max_len = b->lengths[r];
         if (b->offsets[r] + b->lengths[r] > b->n_bytes ||
             (b->qual_offsets && b->qual_offsets[r] + b->lengths[r] > b->n_bytes)) {
             ctx->err = "read extends past n_bytes"; return ORC_EINVAL;
@@ -329,6 +332,8 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
         bases += b->lengths[r];
     }
     s.in_bases = bases;
+    s.len_bits = 1;
+    while (s.len_bits < 32 && (((uint64_t)max_len + 2) >> s.len_bits) != 0) s.len_bits++;
     CK(cudaEventRecord(s.ev[EV_START], s.stream));
     s.u_qual = s.d_qual; s.u_names = s.d_names; s.u_qual_offsets = nullptr; s.u_name_lengths = nullptr;
     if (b->n_reads) {
@@ -376,7 +381,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     uint32_t *W = s.d_codes_alloc + GUARD_WORDS;
     cudaStream_t st = s.stream;
     CK(cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(s.d_cells, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(s.d_cells, 0, 4 * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));       // kernels start here (re-recorded when launched alone)
     s.did_h2d = s.fresh_upload;                  // h2d_ms is only meaningful right after an upload
     s.fresh_upload = false;
@@ -400,15 +405,15 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             if (filter) {
                 sort_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_views[r], prev, n, s.d_key_in, s.d_val_in);
                 CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_key_in, s.d_key_out, s.d_val_in,
-                                                             s.d_order, (int)n, 0, 32, st));
+                                                             s.d_order, (int)n, 0, s.len_bits, st));
             }
             trigger_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], prev,
                                                                filter ? s.d_order : nullptr, n, s.d_wins,
-                                                               s.d_wcols, s.d_item_in);
+                                                               s.d_wcols, s.d_item_in, s.d_cells + 2 + r);
             // order the (read, direction) items by the columns they have to scan
             tmp = ctx->sort_tmp_bytes;
             CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_wcols, s.d_wcols_sorted, s.d_item_in,
-                                                         s.d_item_order, 2 * (int)n, 0, 32, st));
+                                                         s.d_item_order, 2 * (int)n, 0, s.len_bits, st));
         }
         CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
         if (n) {
@@ -486,7 +491,7 @@ extern "C" int orc_download(orc_ctx *ctx, int slot)
     CK(cudaMemcpyAsync(s.h_bin_counts, s.d_bin_counts, sizeof(uint64_t) * ctx->n_bins, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_bin_offsets, s.d_bin_offsets, sizeof(uint64_t) * (ctx->n_bins + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_HDR], st));
     if (n) {
         CK(cudaMemcpyAsync(s.h_bin, s.d_bin, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
@@ -574,7 +579,7 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     if (s.did_d2h) CK(el(EV_EMIT, EV_END, &t->d2h_ms));
     // counters need a device read when the caller never downloaded
     uint32_t counters[8];
-    unsigned long long cells[2];
+    unsigned long long cells[4];
     CK(cudaMemcpy(counters, s.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cells, s.d_cells, sizeof(cells), cudaMemcpyDeviceToHost));
     uint64_t emit_bytes = 0;
@@ -592,6 +597,10 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
         for (int a = 0; a < T.n_adapters; a++) msum += (uint64_t)T.m[a];
         const uint64_t bases = (r == 0) ? s.in_bases : (uint64_t)cells[1];
         t->cells[r] = (T.revcomp ? 2ull : 1ull) * msum * bases;
+        // cells actually updated: stage 1 (Lp rows, every column, both directions) + stage 2 (every
+        // adapter's m rows over the window columns)
+        t->cells_executed[r] = (T.use_filter ? (uint64_t)T.lcp * (T.revcomp ? 2ull : 1ull) * bases : 0ull) +
+                               msum * (uint64_t)cells[2 + r];
     }
     t->pack_bytes = s.n_bytes + s.n_bytes / 2;
     t->emit_bytes = 2 * emit_bytes;    // every FASTQ byte is read once and written once

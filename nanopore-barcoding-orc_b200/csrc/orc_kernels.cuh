@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(128)
 trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                const View *__restrict__ views, const Match *__restrict__ prev,
                const uint32_t *__restrict__ order, uint32_t n_reads, WinList *__restrict__ wins,
-               uint32_t *__restrict__ wcols, uint32_t *__restrict__ item_ids)
+               uint32_t *__restrict__ wcols, uint32_t *__restrict__ item_ids,
+               unsigned long long *__restrict__ col_sum)
 {
     __shared__ __align__(16) uint32_t s_peq32[16][64];
     __shared__ int s_par[8];
@@ -103,15 +104,15 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     }
     __syncthreads();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= 2u * n_reads) return;
-    const uint32_t r = order ? order[p >> 1] : (p >> 1);
+    const bool valid = p < 2u * n_reads;
+    const uint32_t r = valid ? (order ? order[p >> 1] : (p >> 1)) : 0u;
     const int dir = (int)(p & 1u);
     const int Lp = s_par[0], kt = s_par[1], m_max = s_par[2], type = s_par[3];
     WinList wl;
     wl.n = 0; wl.pad_ = 0;
     for (int i = 0; i < MAX_WIN; i++) { wl.s[i] = 0; wl.e[i] = 0; }
     uint32_t cols = 0;
-    const bool skip = prev != nullptr && prev[r].adapter < 0;
+    const bool skip = !valid || (prev != nullptr && prev[r].adapter < 0);
     if (!skip) {
         const View v = views[r];
         if (s_par[4] || ((dir ^ (int)(v.rc & 1u)) == 0)) {
@@ -127,6 +128,11 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
             cols += 1;      // an active pair with nothing to scan (empty read) still has its last column
         }
     }
+    {   // columns stage 2 will scan (for the executed-cells figure of the roofline)
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, cols ? cols - 1u : 0u);
+        if ((threadIdx.x & 31) == 0 && sum) atomicAdd(col_sum, (unsigned long long)sum);
+    }
+    if (!valid) return;
     const uint32_t item = r * 2u + (uint32_t)dir;
     uint4 *dst = reinterpret_cast<uint4 *>(wins + item);
     const uint4 *src = reinterpret_cast<const uint4 *>(&wl);

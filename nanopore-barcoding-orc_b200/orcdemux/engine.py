@@ -233,7 +233,7 @@ class Engine:
         self._check(self._L.orc_get_timings(self._ctx, slot, C.byref(t)), "orc_get_timings")
         return dict(pack_ms=t.pack_ms, trigger_ms=list(t.trigger_ms), scan_ms=list(t.scan_ms), resolve_ms=list(t.resolve_ms), bin_ms=t.bin_ms,
                     emit_ms=t.emit_ms, total_ms=t.total_ms, h2d_ms=t.h2d_ms, d2h_ms=t.d2h_ms,
-                    kernel_launches=t.kernel_launches, n_tasks=list(t.n_tasks), n_candidates=list(t.n_candidates), cells=list(t.cells),
+                    kernel_launches=t.kernel_launches, n_tasks=list(t.n_tasks), n_candidates=list(t.n_candidates), cells=list(t.cells), cells_executed=list(t.cells_executed),
                     pack_bytes=t.pack_bytes, emit_bytes=t.emit_bytes)
 
     def timer_start(self, slot: int = 0):

@@ -67,7 +67,7 @@ class Timings(C.Structure):
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("n_tasks", C.c_uint32 * ORC_MAX_ROUNDS),
                 ("n_candidates", C.c_uint32 * ORC_MAX_ROUNDS),
-                ("cells", C.c_uint64 * ORC_MAX_ROUNDS), ("pack_bytes", C.c_uint64), ("emit_bytes", C.c_uint64)]
+                ("cells", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_executed", C.c_uint64 * ORC_MAX_ROUNDS), ("pack_bytes", C.c_uint64), ("emit_bytes", C.c_uint64)]
 
 
 _lib = None
