@@ -30,7 +30,8 @@ extern "C" {
 #endif
 
 #define ORC_MAX_ROUNDS 2
-#define ORC_MAX_ADAPTERS 16      /* adapters per round (x2 orientations = one warp) */
+#define ORC_MAX_ADAPTERS 16      /* unanchored adapters per round (x2 orientations = one warp) */
+#define ORC_MAX_ANCHORED 64      /* anchored no-indel adapters per round */
 #define ORC_MAX_ADAPTER_LEN 64   /* one 64-bit Myers word */
 
 typedef struct orc_ctx orc_ctx;   /* opaque; one per GPU */
@@ -49,7 +50,8 @@ enum {
 /* One cutadapt invocation's matching options (replaces the argv at 02:64-72 / 02:94-102). */
 typedef struct orc_round_params {
     int32_t n_adapters;             /* records of the `file:` FASTA, file order kept */
-    int32_t type;                   /* ORC_FRONT (-g) or ORC_BACK (-a) */
+    int32_t type;                   /* ORC_FRONT (-g), ORC_BACK (-a); ORC_PREFIX (-g ^) / ORC_SUFFIX (-a ...$)
+                                       only with indels == 0 (Hamming fast path, up to 64 adapters) */
     const char *const *names;       /* [n_adapters] header.split()[0]; may be NULL */
     const char *const *sequences;   /* [n_adapters] NUL-terminated, <= ORC_MAX_ADAPTER_LEN, ACGT */
     double max_error_rate;          /* -e  (values >= 1 are absolute error counts, as in cutadapt) */

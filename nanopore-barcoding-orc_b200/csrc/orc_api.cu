@@ -83,6 +83,9 @@ struct orc_ctx {
     uint64_t max_bytes = 0, max_name_bytes = 0, fastq_cap = 0;
     RoundTable h_tab[2];
     RoundTable *d_tab[2] = {nullptr, nullptr};
+    AnchoredTable h_anch[2];
+    AnchoredTable *d_anch[2] = {nullptr, nullptr};
+    bool anchored[2] = {false, false};
     uint8_t *d_pack_lut = nullptr, *d_comp_lut = nullptr, *d_drop = nullptr;
     std::vector<Slot> slots;
     std::vector<uint64_t> total_counts;
@@ -213,17 +216,28 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     for (int r = 0; r < p->n_rounds; r++) {
         const orc_round_params &rp = p->rounds[r];
         if (rp.sequences == nullptr) { ctx->err = "round without adapter sequences"; return ORC_EINVAL; }
-        std::string why = build_round_table(ctx->h_tab[r], rp.n_adapters, rp.type, rp.sequences,
-                                            rp.max_error_rate, rp.min_overlap, rp.indels, rp.revcomp);
+        std::string why;
+        ctx->anchored[r] = (rp.type == ORC_PREFIX || rp.type == ORC_SUFFIX);
+        if (ctx->anchored[r])
+            why = build_anchored_table(ctx->h_anch[r], ctx->h_tab[r], rp.n_adapters, rp.type == ORC_SUFFIX,
+                                       rp.sequences, rp.max_error_rate, rp.indels, rp.revcomp);
+        else
+            why = build_round_table(ctx->h_tab[r], rp.n_adapters, rp.type, rp.sequences,
+                                    rp.max_error_rate, rp.min_overlap, rp.indels, rp.revcomp);
         if (!why.empty()) { ctx->err = why; return ORC_EINVAL; }
     }
     ctx->n_bins = ctx->h_tab[0].n_adapters + 1;
     if (p->n_rounds == 2) ctx->n_bins *= ctx->h_tab[1].n_adapters + 1;
+    if (ctx->n_bins > MAX_BINS) { ctx->err = "unsupported: more than 512 bins"; return ORC_EINVAL; }
     ctx->total_counts.assign((size_t)ctx->n_bins, 0);
     ctx->fastq_cap = ctx->max_name_bytes + 2 * ctx->max_bytes + 16ull * ctx->max_reads + 64;
     for (int r = 0; r < p->n_rounds; r++) {
         CK(dalloc(&ctx->d_tab[r], 1));
         CK(cudaMemcpy(ctx->d_tab[r], &ctx->h_tab[r], sizeof(RoundTable), cudaMemcpyHostToDevice));
+        if (ctx->anchored[r]) {
+            CK(dalloc(&ctx->d_anch[r], 1));
+            CK(cudaMemcpy(ctx->d_anch[r], &ctx->h_anch[r], sizeof(AnchoredTable), cudaMemcpyHostToDevice));
+        }
     }
     uint8_t lut[256];
     build_pack_lut(lut);
@@ -276,7 +290,7 @@ extern "C" void orc_destroy(orc_ctx *ctx)
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
-    for (int r = 0; r < 2; r++) cudaFree(ctx->d_tab[r]);
+    for (int r = 0; r < 2; r++) { cudaFree(ctx->d_tab[r]); cudaFree(ctx->d_anch[r]); }
     cudaFree(ctx->d_pack_lut); cudaFree(ctx->d_comp_lut); cudaFree(ctx->d_drop);
     delete ctx;
 }
@@ -397,7 +411,14 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         const Match *prev = r == 0 ? nullptr : s.d_match[r - 1];
         const bool filter = ctx->h_tab[r].use_filter != 0;
         uint32_t *cnt = s.d_counters + 4 * r;       // job counter, result slots, resolver tasks
-        if (n) {
+        if (n && ctx->anchored[r]) {
+            // anchored adapters without indels: Hamming compare of the anchored end, no alignment
+            CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
+            CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
+            anchored_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_anch[r], s.d_seq, ctx->d_comp_lut, s.d_views[r],
+                                                                prev, n, s.d_results, s.d_best_key);
+            CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
+        } else if (n) {
             CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
             // stage 1: (with a usable shared prefix) order the reads by length and let one 32-bit
             // scan of the prefix per (read, direction) mark the column windows stage 2 must look at
@@ -415,16 +436,17 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_wcols, s.d_wcols_sorted, s.d_item_in,
                                                          s.d_item_order, 2 * (int)n, 0, s.len_bits, st));
         }
-        CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
-        if (n) {
+        if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
+        if (n && !ctx->anchored[r]) {
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_results,
                 s.d_tasks, s.d_best_key, cnt);
         }
-        CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
+        if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         if (n) {
-            resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2,
-                                                               s.d_results, s.d_best_key);
+            if (!ctx->anchored[r])
+                resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2,
+                                                                   s.d_results, s.d_best_key);
             SelectArgs A;
             A.tab = ctx->d_tab[r];
             A.views_in = s.d_views[r];
@@ -587,13 +609,22 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 3u + (s.has_names ? 1u : 0u)) : 1u;
     if (s.n_reads)
         for (int r = 0; r < ctx->n_rounds; r++)     // trigger (+ sort_keys); CUB's own launches are not counted
-            t->kernel_launches += ctx->h_tab[r].use_filter ? 2u : 1u;
+            t->kernel_launches += ctx->anchored[r] ? 0u : (ctx->h_tab[r].use_filter ? 2u : 1u);
+    if (s.n_reads)
+        for (int r = 0; r < ctx->n_rounds; r++)
+            if (ctx->anchored[r]) t->kernel_launches -= 1u;   // anchored + select instead of scan + resolve + select
     for (int r = 0; r < ctx->n_rounds; r++) {
         t->n_tasks[r] = counters[4 * r + 2];
         t->n_candidates[r] = counters[4 * r + 1];
         const RoundTable &T = ctx->h_tab[r];
         // algorithmic cells: pairs * m * n summed over the reads entering the round
         uint64_t msum = 0;
+        if (ctx->anchored[r]) {
+            // Hamming path: m characters per adapter and orientation, independent of the read length
+            for (int a = 0; a < ctx->h_anch[r].n_adapters; a++) msum += (uint64_t)ctx->h_anch[r].m[a];
+            t->cells[r] = t->cells_executed[r] = (T.revcomp ? 2ull : 1ull) * msum * (uint64_t)s.n_reads;
+            continue;
+        }
         for (int a = 0; a < T.n_adapters; a++) msum += (uint64_t)T.m[a];
         const uint64_t bases = (r == 0) ? s.in_bases : (uint64_t)cells[1];
         t->cells[r] = (T.revcomp ? 2ull : 1ull) * msum * bases;

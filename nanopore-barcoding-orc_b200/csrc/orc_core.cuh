@@ -485,8 +485,8 @@ ORC_HD void best_to_result(const Best &best, int m, int n, PairResult &res)
 // then the adapter that comes first in the file; the low word says where the result lives.
 ORC_HD uint64_t pack_key(int score, int errors, int adapter, uint32_t slot)
 {
-    return ((uint64_t)(uint32_t)(score + 512) << 42) | ((uint64_t)(uint32_t)(63 - errors) << 36) |
-           ((uint64_t)(uint32_t)(15 - adapter) << 32) | (uint64_t)slot;
+    return ((uint64_t)(uint32_t)(score + 512) << 44) | ((uint64_t)(uint32_t)(63 - errors) << 38) |
+           ((uint64_t)(uint32_t)(63 - adapter) << 32) | (uint64_t)slot;
 }
 
 // ------------------------------------------------------------------------------------
@@ -668,8 +668,8 @@ ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, 
 ORC_HD void select_read(const RoundTable &T, const View &v, const uint64_t key[2], const PairResult *results,
                         Match &out, View &next)
 {
-    const int fs = key[0] ? (int)(key[0] >> 42) - 512 : 0;
-    const int rs = key[1] ? (int)(key[1] >> 42) - 512 : 0;
+    const int fs = key[0] ? (int)(key[0] >> 44) - 512 : 0;
+    const int rs = key[1] ? (int)(key[1] >> 44) - 512 : 0;
     const int o = (T.revcomp && rs > fs) ? 1 : 0;          // R9: strictly higher score
     next = v;
     const uint32_t eff = (v.rc & 1u) ^ (uint32_t)o;
@@ -682,7 +682,7 @@ ORC_HD void select_read(const RoundTable &T, const View &v, const uint64_t key[2
         return;
     }
     const PairResult r = results[(uint32_t)key[o]];
-    out.adapter = 15 - (int)((key[o] >> 32) & 15u); out.is_rc = o;
+    out.adapter = 63 - (int)((key[o] >> 32) & 63u); out.is_rc = o;
     out.ref_start = r.ref_start; out.ref_stop = r.ref_stop;
     out.query_start = r.query_start; out.query_stop = r.query_stop;
     out.score = r.score; out.errors = r.errors;
@@ -695,6 +695,80 @@ ORC_HD void select_read(const RoundTable &T, const View &v, const uint64_t key[2
     next.len = b0 - a0;
     next.lo = eff ? v.lo + (n - b0) : v.lo + a0;
     next.rc = ((v.rc & ~1u) | eff) + ((uint32_t)o << 8);
+}
+
+// ------------------------------------------------------------------------------------
+// Anchored adapters without indels (-g ^file: / -a file$: with --no-indels; BASELINE config 4).
+// cutadapt does not align these: PrefixComparer/SuffixComparer count mismatches of the first /
+// last m characters, and >= 2 such adapters with k <= 2 are looked up in a dict of their Hamming
+// neighbourhoods (adapters.py IndexedPrefixAdapters).  Only the m characters at
+// the anchored end of a read are touched.
+// ------------------------------------------------------------------------------------
+constexpr int MAX_ANCH = 64;
+struct AnchoredTable {
+    int32_t n_adapters;
+    int32_t suffix;                 // 0: 5' anchored (prefix), 1: 3' anchored (suffix)
+    int32_t revcomp;
+    int32_t indexed;                // dict semantics (>= 2 adapters, one length, every k <= 2)
+    int32_t m[MAX_ANCH];
+    int32_t k[MAX_ANCH];            // int(rate * m)
+    uint8_t seq[MAX_ANCH][MAX_M];   // upper-case ASCII
+};
+
+// Best adapter for logical orientation o of the view.  seq: ASCII bases; comp: complement LUT.
+// Returns the adapter index or -1 and fills res.
+ORC_HD int anchored_match(const uint8_t *seq, const uint8_t *comp, const View &v, int o,
+                          const AnchoredTable &T, PairResult &res)
+{
+    const int n = (int)v.len;
+    const uint32_t eff = (v.rc & 1u) ^ (uint32_t)o;
+    res.has = 0; res.pad_ = 0;
+    res.ref_start = res.ref_stop = res.query_start = res.query_stop = res.score = res.errors = 0;
+    int best = -1, best_score = 0, best_e = 0, best_m = 0;
+    bool use_index = T.indexed != 0;
+    if (use_index) {
+        const int L = T.m[0];
+        if (n < L) return -1;
+        bool has_n = false, other = false;
+        for (int i = 0; i < L; i++) {
+            const int p = T.suffix ? n - L + i : i;
+            uint8_t c = eff ? comp[seq[v.lo + (uint64_t)(n - 1 - p)]] : seq[v.lo + (uint64_t)p];
+            if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+            if (c == 'N') has_n = true;
+            else if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) other = true;
+        }
+        if (has_n) use_index = false;           // "N" in the affix: the plain comparer loop decides
+        else if (other) return -1;              // not a key of the dict
+    }
+    for (int a = 0; a < T.n_adapters; a++) {
+        const int m = T.m[a];
+        if (n < m) continue;                    // anchored adapters need the whole adapter (min_overlap = m)
+        int e = 0;
+        for (int i = 0; i < m; i++) {
+            const int p = T.suffix ? n - m + i : i;
+            uint8_t c = eff ? comp[seq[v.lo + (uint64_t)(n - 1 - p)]] : seq[v.lo + (uint64_t)p];
+            if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+            e += (c != T.seq[a][i]);
+        }
+        if (e > T.k[a]) continue;
+        bool take;
+        int score;
+        if (use_index) {                        // most matches; the later adapter wins equal matches
+            score = m - e;
+            take = best < 0 || !(m - e < best_m - best_e);
+        } else {                                // R8 over the comparers: score, errors, file order
+            score = (m - e) - e;
+            take = best < 0 || score > best_score || (score == best_score && e < best_e);
+        }
+        if (take) { best = a; best_score = score; best_e = e; best_m = m; }
+    }
+    if (best < 0) return -1;
+    res.has = 1;
+    res.ref_start = 0; res.ref_stop = best_m;
+    res.query_start = T.suffix ? n - best_m : 0;
+    res.query_stop = T.suffix ? n : best_m;
+    res.score = best_score; res.errors = best_e;
+    return best;
 }
 
 }  // namespace orc

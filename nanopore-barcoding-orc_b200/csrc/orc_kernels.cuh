@@ -24,7 +24,7 @@ namespace orc {
 constexpr int GUARD_WORDS = 4;         // zero words before and after the code array
 constexpr int SCAN_THREADS = 128;
 constexpr int BIN_CHUNK = 256;         // reads per warp in the partition kernels
-constexpr int MAX_BINS = (MAX_AD + 1) * (MAX_AD + 1);
+constexpr int MAX_BINS = 512;           // bins = product of (adapters + 1) over the rounds
 
 __device__ __forceinline__ uint32_t lanemask_lt()
 {
@@ -267,6 +267,38 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
             atomicMax(best_key + (size_t)task.read * 2 + o,
                       (unsigned long long)pack_key(res.score, res.errors, a, task.slot));
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Anchored no-indel round: one thread per (read, orientation); touches m bytes per read.
+__global__ void __launch_bounds__(128)
+anchored_kernel(const AnchoredTable *__restrict__ tab, const uint8_t *__restrict__ seq,
+                const uint8_t *__restrict__ comp_lut_g, const View *__restrict__ views,
+                const Match *__restrict__ prev, uint32_t n_reads, PairResult *__restrict__ results,
+                unsigned long long *__restrict__ best_key)
+{
+    __shared__ __align__(16) AnchoredTable T;
+    __shared__ uint8_t comp[256];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(AnchoredTable) / 4); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) comp[i] = comp_lut_g[i];
+    }
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= 2u * n_reads) return;
+    const uint32_t r = p >> 1;
+    const int o = (int)(p & 1u);
+    if (prev != nullptr && prev[r].adapter < 0) return;
+    if (o == 1 && !T.revcomp) return;
+    const View v = views[r];
+    PairResult res;
+    const int a = anchored_match(seq, comp, v, o, T, res);
+    if (a >= 0) {
+        results[p] = res;
+        best_key[p] = (unsigned long long)pack_key(res.score, res.errors, a, p);
     }
 }
 

@@ -116,6 +116,47 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
     return "";
 }
 
+// Anchored, no-indel round (ORC_PREFIX / ORC_SUFFIX).  Also fills the few RoundTable fields the
+// selection kernel reads (type as trimming side, revcomp, n_adapters).
+inline std::string build_anchored_table(AnchoredTable &A, RoundTable &T, int n_adapters, int suffix,
+                                        const char *const *sequences, double max_errors, int indels, int revcomp)
+{
+    memset(&A, 0, sizeof(A));
+    memset(&T, 0, sizeof(T));
+    if (n_adapters < 1 || n_adapters > MAX_ANCH)
+        return "unsupported: between 1 and " + std::to_string(MAX_ANCH) + " anchored adapters per round";
+    if (indels) return "unsupported: anchored adapters need --no-indels (the indel variant is not built)";
+    A.n_adapters = n_adapters; A.suffix = suffix ? 1 : 0; A.revcomp = revcomp ? 1 : 0;
+    bool one_length = true, small_k = true;
+    for (int a = 0; a < n_adapters; a++) {
+        const char *s = sequences[a];
+        const int m = (int)strlen(s);
+        if (m < 1 || m > MAX_M) return "unsupported: adapter length must be 1..64";
+        A.m[a] = m;
+        for (int i = 0; i < m; i++) {
+            char c = s[i];
+            if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+            if (c == 'U') c = 'T';
+            if (base_code(c) < 0) return "unsupported: adapter characters other than ACGT (IUPAC wildcards)";
+            A.seq[a][i] = (uint8_t)c;
+        }
+        double rate = max_errors;
+        if (rate >= 1.0) rate /= m;
+        if (!(rate >= 0.0) || rate >= 1.0) return "unsupported: error rate must be in [0, 1) for every adapter";
+        A.k[a] = (int)(rate * m);
+        if (m != A.m[0]) one_length = false;
+        if (A.k[a] > 2) small_k = false;
+    }
+    if (n_adapters >= 2 && small_k && !one_length)
+        return "unsupported: anchored adapters of several lengths (cutadapt's multi-length index)";
+    A.indexed = (n_adapters >= 2 && small_k && one_length) ? 1 : 0;
+    T.n_adapters = n_adapters;
+    T.type = suffix ? TYPE_BACK : TYPE_FRONT;       // which side the selection trims
+    T.revcomp = revcomp ? 1 : 0;
+    T.n_lanes = 0;
+    return "";
+}
+
 // ASCII -> 4-bit code used by the pack kernel.  cutadapt compares ASCII after upper()
 // when the adapter is plain ACGT, so only ACGT/acgt get a code; anything
 // else (N, U, IUPAC, '-') is 0 and matches nothing.

@@ -6,8 +6,9 @@ shapes of /root/reference/scripts/02_cutadapt_loop.sh):
   round 2 (02:94-102)  cutadapt --action=trim -e 0.1 -j 24 --rc -a file:REV_RC.fa
                                 -o DIR/SP27/{name}_SP5id_DS.fastq.gz DIR/SP5/SP5id_DS.fastq.gz --json=REPORT
 
-Kept surface: -g/-a (file:PATH, SEQ, name=SEQ; several allowed), -e, -O, --no-indels (refused
-for unanchored adapters until its kernel exists), --action=trim, --rc, -j (accepted), --json,
+Kept surface: -g/-a (file:PATH, SEQ, name=SEQ; several allowed), -e, -O, --action=trim, --rc,
+-j (accepted), --json, anchored ^file: / file$: adapters together with --no-indels (the Hamming
+fast path; --no-indels on unanchored adapters and anchored adapters with indels are refused),
 -o with {name} (one file per adapter name plus "unknown", all created even if empty).
 Anything else exits with status 2 and an "unsupported" message: there is no CPU fallback.
 
@@ -26,7 +27,7 @@ import numpy as np
 
 from . import engine as E
 from . import fastq as F
-from .lib import ORC_BACK, ORC_FRONT
+from .lib import ORC_BACK, ORC_FRONT, ORC_PREFIX, ORC_SUFFIX
 
 
 class Unsupported(Exception):
@@ -34,17 +35,18 @@ class Unsupported(Exception):
 
 
 def _parse_adapter_specs(specs: List[str], kind: int):
-    names, seqs = [], []
+    """-> (names, sequences, anchored).  Syntax kept: SEQ, name=SEQ, file:PATH, and the anchored
+    forms ^SEQ / ^file:PATH (5') and SEQ$ / file$:PATH (3')."""
+    names, seqs, flags = [], [], []
     for spec in specs:
         anchored = False
         s = spec
         if kind == ORC_FRONT and s.startswith("^"):
             anchored, s = True, s[1:]
+        if s.startswith("file$:") and kind == ORC_BACK:
+            anchored, s = True, "file:" + s[6:]
         if s.startswith("file:"):
-            path = s[5:]
-            if path.endswith("$") and kind == ORC_BACK:
-                anchored, path = True, path[:-1]
-            n, q = F.read_adapters_fasta(path)
+            n, q = F.read_adapters_fasta(s[5:])
         else:
             name = None
             if "=" in s:
@@ -54,16 +56,17 @@ def _parse_adapter_specs(specs: List[str], kind: int):
             if kind == ORC_FRONT and s.startswith("^"):
                 anchored, s = True, s[1:]
             n, q = [name], [s.upper().replace("U", "T")]
-        if anchored:
-            raise Unsupported("anchored adapters (^/$) take the Hamming fast path, not wired into this CLI yet")
         for a, b in zip(n, q):
-            if any(c in b for c in "X.;{}[]"):
+            if any(c in b for c in "X.;{}[]$^"):
                 raise Unsupported("adapter syntax beyond plain sequences: %r" % b)
             names.append(a)
             seqs.append(b)
+            flags.append(anchored)
+    if any(flags) and not all(flags):
+        raise Unsupported("a mix of anchored and regular adapters in one invocation")
     # cutadapt names unnamed adapters "1", "2", ... in order
     names = [nm if nm else str(i + 1) for i, nm in enumerate(names)]
-    return names, seqs
+    return names, seqs, bool(flags and flags[0])
 
 
 def parse_cutadapt_argv(argv: List[str]):
@@ -131,8 +134,6 @@ def parse_cutadapt_argv(argv: List[str]):
         raise Unsupported("give either -g or -a adapters (one adapter type per invocation)")
     if not opt["out"] or "{name}" not in opt["out"]:
         raise Unsupported("-o with a {name} template is required (demultiplexing mode)")
-    if not opt["indels"]:
-        raise Unsupported("--no-indels for unanchored adapters")
     return opt
 
 
@@ -157,7 +158,13 @@ def _report(n_in, bp_in, bp_out, n_with, n_rc, names, per_adapter, elapsed, argv
 
 def run_single_round(opt, argv, device=0) -> int:
     kind = ORC_FRONT if opt["g"] else ORC_BACK
-    names, seqs = _parse_adapter_specs(opt["g"] or opt["a"], kind)
+    names, seqs, anchored = _parse_adapter_specs(opt["g"] or opt["a"], kind)
+    if anchored and opt["indels"]:
+        raise Unsupported("anchored adapters need --no-indels (the indel variant is not built)")
+    if not anchored and not opt["indels"]:
+        raise Unsupported("--no-indels for unanchored adapters")
+    if anchored:
+        kind = ORC_PREFIX if kind == ORC_FRONT else ORC_SUFFIX
     rnd = E.Round(names, seqs, kind, opt["e"], opt["O"], opt["indels"], opt["rc"])
     t0 = time.time()
     max_reads, max_bytes, slots = 1 << 18, 1 << 28, 2

@@ -68,6 +68,8 @@ def lib():
         L.oracle_adapter_init.restype = None
         L.oracle_adapter_match.argtypes = [C.POINTER(OraAdapter), C.c_char_p, C.c_int, C.POINTER(C.c_int)]
         L.oracle_adapter_match.restype = C.c_int
+        L.oracle_best_of.argtypes = [C.POINTER(OraAdapter), C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        L.oracle_best_of.restype = C.c_int
         L.oracle_demux_batch.argtypes = [
             C.c_int,
             C.POINTER(OraAdapter), C.c_int, C.c_int,
@@ -111,6 +113,12 @@ class AdapterSet:
             lib().oracle_adapter_init(C.byref(self.arr[i]), s.encode(), where, float(max_errors),
                                       int(min_overlap), int(indels), int(adapter_wildcards),
                                       int(read_wildcards))
+
+    def best_of(self, query_upper: str):
+        """MultipleAdapters / IndexedPrefixAdapters.match_to -> (adapter index, 6-tuple) or None."""
+        out = (C.c_int * 6)()
+        a = lib().oracle_best_of(self.arr, self.n, query_upper.encode(), len(query_upper), out)
+        return (a, tuple(out)) if a >= 0 else None
 
     def match(self, idx: int, query_upper: str):
         out = (C.c_int * 6)()

@@ -388,7 +388,7 @@ int oracle_adapter_match(const ora_adapter *a, const char *query_upper, int n, i
 
 /* MultipleAdapters.match_to (R8): higher score, then fewer errors, then file order.
  * Returns adapter index or -1; fills out[6]. */
-int oracle_best_of(const ora_adapter *adapters, int n_adapters, const char *query_upper, int n, int out[6])
+static int best_of_loop(const ora_adapter *adapters, int n_adapters, const char *query_upper, int n, int out[6])
 {
     int best = -1, cur[6];
     for (int a = 0; a < n_adapters; a++) {
@@ -399,6 +399,66 @@ int oracle_best_of(const ora_adapter *adapters, int n_adapters, const char *quer
         }
     }
     return best;
+}
+
+/*
+ * adapters.py IndexedPrefixAdapters / IndexedSuffixAdapters: AdapterCutter
+ * regroups >= 2 anchored adapters of one type into a dict over hamming_environment(seq, k)
+ * when none has wildcards and every k = int(rate * m) <= 2.  Restated for the case this build
+ * accepts: --no-indels and one common adapter length L (`_match_to_one_length`):
+ *   affix = read[:L] (prefix) / read[-L:] (suffix), upper-cased;
+ *   "N" in affix  -> fall back to the plain MultipleAdapters loop over the comparers;
+ *   otherwise the dict entry of affix: among the adapters within their k mismatches the one
+ *   with the most matches, the LATER adapter on equal matches (index[s] is overwritten unless
+ *   matches < other_matches); an affix that is shorter than L or holds any character outside
+ *   ACGT is not a key -> no match.
+ *   Match = (0, m, 0, L, score = matches, errors) / suffix: read interval (n - L, n).
+ */
+static int indexed_applicable(const ora_adapter *ad, int n_adapters)
+{
+    if (n_adapters < 2) return 0;
+    for (int a = 0; a < n_adapters; a++) {
+        if (ad[a].type != ad[0].type || (ad[a].type != ORA_PREFIX && ad[a].type != ORA_SUFFIX)) return 0;
+        if (ad[a].indels || ad[a].adapter_wildcards || ad[a].read_wildcards) return 0;
+        if ((int)(ad[a].m * ad[a].max_error_rate) > 2) return 0;
+        if (ad[a].m != ad[0].m) return 0;     /* several lengths: _match_to_multiple_lengths, not restated */
+    }
+    return 1;
+}
+
+static int indexed_match(const ora_adapter *ad, int n_adapters, const char *query_upper, int n, int out[6])
+{
+    const int L = ad[0].m;
+    const int suffix = ad[0].type == ORA_SUFFIX;
+    if (n < L) return -1;
+    const char *affix = suffix ? query_upper + (n - L) : query_upper;
+    int has_n = 0, other = 0;
+    for (int i = 0; i < L; i++) {
+        char c = affix[i];
+        if (c == 'N') has_n = 1;
+        else if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) other = 1;
+    }
+    if (has_n) return best_of_loop(ad, n_adapters, query_upper, n, out);
+    if (other) return -1;
+    int best = -1, best_m = -1, best_e = 0;
+    for (int a = 0; a < n_adapters; a++) {
+        int e = 0;
+        for (int i = 0; i < L; i++) e += ad[a].seq[i] != affix[i];
+        if (e > (int)(ad[a].m * ad[a].max_error_rate)) continue;
+        if (L - e < best_m) continue;          /* matches < other_matches: keep the earlier entry */
+        best = a; best_m = L - e; best_e = e;  /* equal or more matches: the later adapter overwrites */
+    }
+    if (best < 0) return -1;
+    out[0] = 0; out[1] = L;
+    out[2] = suffix ? n - L : 0; out[3] = suffix ? n : L;
+    out[4] = best_m; out[5] = best_e;
+    return best;
+}
+
+int oracle_best_of(const ora_adapter *adapters, int n_adapters, const char *query_upper, int n, int out[6])
+{
+    if (indexed_applicable(adapters, n_adapters)) return indexed_match(adapters, n_adapters, query_upper, n, out);
+    return best_of_loop(adapters, n_adapters, query_upper, n, out);
 }
 
 /* One per-read record of one round.  Layout mirrors orc_match in include/orcdemux.h. */

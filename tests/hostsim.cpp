@@ -25,12 +25,20 @@ extern "C" int hostsim_demux(int n_rounds,
                              uint64_t *n_tasks, char *err, int err_len, int filter_mode, uint64_t *n_columns)
 {
     RoundTable *T = new RoundTable[2];
-    std::string e = build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, 1, rc0, filter_mode);
-    if (e.empty() && n_rounds > 1) e = build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, 1, rc1, filter_mode);
+    AnchoredTable *AT = new AnchoredTable[2];
+    bool anch[2] = {type0 >= 2, n_rounds > 1 && type1 >= 2};
+    std::string e = anch[0] ? build_anchored_table(AT[0], T[0], n_ad0, type0 == 3, seq0, e0, 0, rc0)
+                            : build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, 1, rc0, filter_mode);
+    if (e.empty() && n_rounds > 1)
+        e = anch[1] ? build_anchored_table(AT[1], T[1], n_ad1, type1 == 3, seq1, e1, 0, rc1)
+                    : build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, 1, rc1, filter_mode);
+    uint8_t comp_lut[256];
+    build_complement_lut(comp_lut);
     if (!e.empty()) {
         strncpy(err, e.c_str(), (size_t)err_len - 1);
         err[err_len - 1] = 0;
         delete[] T;
+        delete[] AT;
         return -1;
     }
     uint8_t lut[256];
@@ -53,6 +61,20 @@ extern "C" int hostsim_demux(int n_rounds,
             const RoundTable &R = T[rd];
             std::vector<PairResult> results;
             uint64_t keys[2] = {0, 0};
+            if (anch[rd]) {
+                for (int o = 0; o < 2; o++) {
+                    if (o == 1 && !AT[rd].revcomp) continue;
+                    PairResult pr;
+                    const int a = anchored_match(seq, comp_lut, v, o, AT[rd], pr);
+                    if (a >= 0) keys[o] = pack_key(pr.score, pr.errors, a, (uint32_t)results.size());
+                    results.push_back(pr);
+                }
+                View next;
+                select_read(R, v, keys, results.data(), *out[rd], next);
+                v = next;
+                if (out[rd]->adapter < 0) break;
+                continue;
+            }
             WinList wl[2];
             if (R.use_filter) {
                 for (int dir = 0; dir < 2; dir++) {
@@ -94,5 +116,6 @@ extern "C" int hostsim_demux(int n_rounds,
     }
     delete ring;
     delete[] T;
+    delete[] AT;
     return 0;
 }

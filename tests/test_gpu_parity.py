@@ -166,3 +166,31 @@ def test_full_size_properties():
     t5 = rs.truth["sp5"]
     ok = (m0["adapter"] + 1 == t5) | (t5 == 0)
     assert ok.mean() > 0.95
+
+
+def test_anchored_hamming_path_config4():
+    """BASELINE config 4: anchored -g ^file:M13_variable_indices_all.fa --no-indels (24 x 17-mers)."""
+    import oracle
+    from orcdemux import m13
+    from orcdemux.lib import ORC_PREFIX
+    var = m13.variable_all()
+    rs = synth.generate(50000, 300, 900, seed=1004, anchored=True)
+    rnd = E.Round([n for n, _ in var], [s for _, s in var], ORC_PREFIX, 0.1, 3, False, True)
+    with E.Engine([rnd], max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]), n_slots=1) as eng:
+        res = eng.run(rs)
+        t = eng.timings(0)
+        assert eng.n_bins == 25
+    sets = [(oracle.AdapterSet([s for _, s in var], oracle.PREFIX, 0.1, 3, indels=False), 1)]
+    rec0, _, oseq, oqual, olen = oracle.demux_batch(sets, rs.seq, rs.qual, rs.offsets, rs.lengths, n_threads=8)
+    assert H.diff_matches(rec0, res.matches[0])[1] == 0
+    assert np.array_equal(res.out_len, olen)
+    exp_bin = (rec0["adapter"] + 1).astype(np.int32)
+    assert np.array_equal(res.bin, exp_bin)
+    # bytes of one bin
+    b = int(np.bincount(exp_bin).argmax())
+    exp = b"".join(b"@" + rs.read(int(r))[0].encode() + (b" rc" if rec0["is_rc"][r] else b"") + b"\n" +
+                   oseq[int(rs.offsets[r]):int(rs.offsets[r]) + int(olen[r])].tobytes() + b"\n+\n" +
+                   oqual[int(rs.offsets[r]):int(rs.offsets[r]) + int(olen[r])].tobytes() + b"\n"
+                   for r in np.flatnonzero(exp_bin == b))
+    assert res.bin_bytes(b) == exp
+    assert (rec0["adapter"] >= 0).mean() > 0.5 and t["total_ms"] > 0

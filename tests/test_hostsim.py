@@ -125,6 +125,63 @@ def test_single_round_back_only():
     _compare([(b, oracle.BACK, 0.1, 3, 1)], rs)
 
 
+def _anchored_reads(rnd, seqs, n, suffix):
+    recs = []
+    comp = str.maketrans("ACGT", "TGCA")
+    for i in range(n):
+        a = list(rnd.choice(seqs))
+        kind = rnd.randrange(9)
+        if kind == 1:
+            a[rnd.randrange(len(a))] = rnd.choice("ACGT")
+        elif kind == 2:
+            for _ in range(2):
+                a[rnd.randrange(len(a))] = rnd.choice("ACGT")
+        elif kind == 3:
+            a[rnd.randrange(len(a))] = "N"
+        elif kind == 4:
+            a[rnd.randrange(len(a))] = rnd.choice("RYKMSW-")
+        elif kind == 5:
+            a = a[:rnd.randrange(len(a))]
+        elif kind == 6:
+            a[rnd.randrange(len(a))] = "N"; a[rnd.randrange(len(a))] = rnd.choice("ACGT")
+        a = "".join(a)
+        body = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(0, 60)))
+        s = body + a if suffix else a + body
+        if kind == 7:
+            s = s.translate(comp)[::-1]
+        if kind == 8:
+            s = s.lower()
+        recs.append(("h%d" % i, s, "I" * len(s)))
+    return synth.from_records(recs)
+
+
+def test_anchored_no_indel_path():
+    """BASELINE config 4 shape: -g ^file: / -a file$: with --no-indels (indexed Hamming lookup)."""
+    rnd = random.Random(4)
+    var = [s for _, s in m13.variable_all()]
+    close = ["ACGTACGTACGTACGTA", "ACGTACGTACGTACGTC", "ACGAACGTACGTACGTA", "TTGTACGTACGTACGTA"]   # ties / collisions
+    for seqs in (var, close, var[:1], ["ACGTAC", "ACGTTC", "TCGTAC"]):
+        for typ in (oracle.PREFIX, oracle.SUFFIX):
+            for e, rc in ((0.1, 1), (0.12, 0), (0.34, 1), (0.0, 1)):
+                rs = _anchored_reads(rnd, seqs, 500, typ == oracle.SUFFIX)
+                sets = [(oracle.AdapterSet(seqs, typ, e, 3, indels=False), rc)]
+                rec0, _, oseq, oqual, olen = oracle.demux_batch(sets, rs.seq, rs.qual, rs.offsets, rs.lengths, n_threads=2)
+                m0, m1, lo, ln, rcv, nt = H.run_hostsim([(seqs, typ, e, 3, rc)], rs)
+                idx, nbad = H.diff_matches(rec0, m0)
+                assert nbad == 0, (seqs[:2], typ, e, rc, idx, rs.read(int(idx[0]))[1], rec0[idx[0]], m0[idx[0]])
+                assert np.array_equal(olen, ln)
+                vb = H.view_bytes(rs, lo, ln, rcv)
+                for i in range(rs.n_reads):
+                    o, L = int(rs.offsets[i]), int(olen[i])
+                    assert vb[i][0] == oseq[o:o + L].tobytes()
+    rs = synth.generate(3000, 300, 600, seed=1004, anchored=True)
+    sets = [(oracle.AdapterSet(var, oracle.PREFIX, 0.1, 3, indels=False), 1)]
+    rec0, *_ = oracle.demux_batch(sets, rs.seq, rs.qual, rs.offsets, rs.lengths, n_threads=4)
+    m0, *_ = H.run_hostsim([(var, oracle.PREFIX, 0.1, 3, 1)], rs)
+    assert H.diff_matches(rec0, m0)[1] == 0
+    assert (rec0["adapter"] >= 0).mean() > 0.5
+
+
 def test_unsupported_is_refused():
     rs = synth.from_records([("x", "ACGT", "IIII")])
     with pytest.raises(RuntimeError, match="unsupported"):
