@@ -7,6 +7,7 @@
 // kernels of batch i.  No CPU fallback anywhere: every entry point needs the device.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -62,7 +63,7 @@ struct Slot {
     unsigned long long *d_cells = nullptr;   // [0..1] sum of view lengths entering each round, [2..3] window columns
     int32_t *d_bin = nullptr;
     uint32_t *d_out_len = nullptr, *d_rec_bytes = nullptr, *d_hist_cnt = nullptr;
-    uint64_t *d_hist_bytes = nullptr, *d_bin_counts = nullptr, *d_bin_offsets = nullptr;
+    uint64_t *d_hist_bytes = nullptr, *d_bin_counts = nullptr, *d_bin_offsets = nullptr, *d_bin_bytes = nullptr;
     // pinned host
     Match *h_match[2] = {nullptr, nullptr};
     int32_t *h_bin = nullptr;
@@ -147,6 +148,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_hist_cnt, n_chunks * ctx->n_bins));
     CK(dalloc(&s.d_hist_bytes, n_chunks * ctx->n_bins));
     CK(dalloc(&s.d_bin_counts, (size_t)ctx->n_bins));
+    CK(dalloc(&s.d_bin_bytes, (size_t)ctx->n_bins));
     CK(dalloc(&s.d_bin_offsets, (size_t)ctx->n_bins + 1));
     CK(halloc(&s.h_bin, R));
     CK(halloc(&s.h_out_len, R));
@@ -179,7 +181,7 @@ static void free_slot(Slot &s)
     cudaFree(s.d_sort_tmp); cudaFree(s.d_wins);
     cudaFree(s.d_counters); cudaFree(s.d_cells); cudaFree(s.d_bin); cudaFree(s.d_out_len);
     cudaFree(s.d_rec_bytes); cudaFree(s.d_hist_cnt); cudaFree(s.d_hist_bytes);
-    cudaFree(s.d_bin_counts); cudaFree(s.d_bin_offsets);
+    cudaFree(s.d_bin_counts); cudaFree(s.d_bin_offsets); cudaFree(s.d_bin_bytes);
     cudaFreeHost(s.h_bin); cudaFreeHost(s.h_out_len); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_cells);
     cudaFreeHost(s.h_bin_counts); cudaFreeHost(s.h_bin_offsets); cudaFreeHost(s.h_fastq);
     for (int i = 0; i < EV_COUNT; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
@@ -481,8 +483,8 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         bin_count_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(s.d_bin, s.d_rec_bytes, n, ctx->n_bins, n_chunks,
                                                             s.d_hist_cnt, s.d_hist_bytes);
     }
-    bin_scan_kernel<<<1, 1024, 0, st>>>(ctx->n_bins, n_chunks, s.d_hist_cnt, s.d_hist_bytes, s.d_bin_counts,
-                                        s.d_bin_offsets);
+    bin_scan_kernel<<<ctx->n_bins, 256, 0, st>>>(n_chunks, s.d_hist_cnt, s.d_hist_bytes, s.d_bin_counts, s.d_bin_bytes);
+    bin_offsets_kernel<<<1, 32, 0, st>>>(ctx->n_bins, s.d_bin_bytes, s.d_bin_offsets);
     if (n) {
         bin_place_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(s.d_bin, s.d_rec_bytes, n, ctx->n_bins, n_chunks,
                                                             s.d_hist_bytes, s.d_bin_offsets, s.d_dest);
@@ -606,7 +608,7 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     CK(cudaMemcpy(cells, s.d_cells, sizeof(cells), cudaMemcpyDeviceToHost));
     uint64_t emit_bytes = 0;
     CK(cudaMemcpy(&emit_bytes, s.d_bin_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 3u + (s.has_names ? 1u : 0u)) : 1u;
+    t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 4u + (s.has_names ? 1u : 0u)) : 2u;
     if (s.n_reads)
         for (int r = 0; r < ctx->n_rounds; r++)     // trigger (+ sort_keys); CUB's own launches are not counted
             t->kernel_launches += ctx->anchored[r] ? 0u : (ctx->h_tab[r].use_filter ? 2u : 1u);

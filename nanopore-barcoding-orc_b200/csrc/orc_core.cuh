@@ -285,9 +285,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         rd.next(A, B);
         const int ncol = imin(8, (int)n - 8 * q);
         uint32_t accP = 0, accM = 0;
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-            if (t >= ncol) break;
+        auto column = [&](int t) {
             const uint32_t src = (t & 1) ? B : A;
             const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
             const uint32_t Eq = *reinterpret_cast<const uint32_t *>(peq32_base + byte_perm(src, lane4, sel));
@@ -300,6 +298,13 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
             Ph <<= 1; Mh <<= 1;
             Pv = Mh | ~(Xv | Ph);
             Mv = Ph & Xv;
+        };
+        if (ncol == 8) {                         // full chunk: no per-column bound test
+#pragma unroll
+            for (int t = 0; t < 8; t++) column(t);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) if (t < ncol) column(t);
         }
         if (D - popc32(accM) <= kt) {            // some column of the chunk may reach the threshold
             for (int t = 0; t < ncol; t++) {
@@ -374,9 +379,7 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
         rd.next(A, B);
         const int ncol = imin(8, ncols - 8 * q);
         uint32_t accP = 0, accM = 0;
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-            if (t >= ncol) break;
+        auto column = [&](int t) {
             const uint32_t src = (t & 1) ? B : A;
             const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
             const uint64_t Eq = *reinterpret_cast<const uint64_t *>(peq_base + byte_perm(src, lane8, sel));
@@ -390,6 +393,13 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
             Ph <<= 1; Mh <<= 1;
             Pv = Mh | ~(Xv | Ph);
             Mv = Ph & Xv;
+        };
+        if (ncol == 8) {                         // full chunk: no per-column bound test
+#pragma unroll
+            for (int t = 0; t < 8; t++) column(t);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) if (t < ncol) column(t);
         }
         if (D - popc32(accM) <= k) {             // D[m][j] may reach k inside this chunk: replay it
             for (int t = 0; t < ncol; t++) {

@@ -407,41 +407,51 @@ bin_count_kernel(const int32_t *__restrict__ bin, const uint32_t *__restrict__ r
     }
 }
 
-// One block.  Exclusive scan over the chunks of every bin (in place), then over the bins.
-__global__ void __launch_bounds__(1024)
-bin_scan_kernel(int n_bins, uint32_t n_chunks, uint32_t *__restrict__ hist_cnt, uint64_t *__restrict__ hist_bytes,
-                uint64_t *__restrict__ bin_counts, uint64_t *__restrict__ bin_offsets)
+// One block per bin: exclusive scan over the chunks of the bin (in place) and the bin's totals.
+__global__ void __launch_bounds__(256)
+bin_scan_kernel(uint32_t n_chunks, uint32_t *__restrict__ hist_cnt, uint64_t *__restrict__ hist_bytes,
+                uint64_t *__restrict__ bin_counts, uint64_t *__restrict__ bin_bytes)
 {
-    __shared__ unsigned long long s_tot_bytes[MAX_BINS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int b = w; b < n_bins; b += nw) {
-        uint32_t run_c = 0;
-        unsigned long long run_b = 0;
-        for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            uint32_t vc = c < n_chunks ? hist_cnt[(size_t)b * n_chunks + c] : 0u;
-            unsigned long long vb = c < n_chunks ? hist_bytes[(size_t)b * n_chunks + c] : 0ull;
-            uint32_t ic = vc;
-            unsigned long long ib = vb;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d);
-                const unsigned long long tb = __shfl_up_sync(0xffffffffu, ib, d);
-                if (lane >= d) { ic += tc; ib += tb; }
-            }
-            if (c < n_chunks) {
-                hist_cnt[(size_t)b * n_chunks + c] = run_c + ic - vc;
-                hist_bytes[(size_t)b * n_chunks + c] = run_b + ib - vb;
-            }
-            run_c += __shfl_sync(0xffffffffu, ic, 31);
-            run_b += __shfl_sync(0xffffffffu, ib, 31);
-        }
-        if (lane == 0) { bin_counts[b] = run_c; s_tot_bytes[b] = run_b; }
-    }
+    __shared__ uint32_t s_c[8];
+    __shared__ unsigned long long s_b[8];
+    __shared__ uint32_t s_run_c;
+    __shared__ unsigned long long s_run_b;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t *hc = hist_cnt + (size_t)b * n_chunks;
+    uint64_t *hb = hist_bytes + (size_t)b * n_chunks;
+    if (threadIdx.x == 0) { s_run_c = 0; s_run_b = 0; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 256) {
+        const uint32_t c = c0 + threadIdx.x;
+        const uint32_t vc = c < n_chunks ? hc[c] : 0u;
+        const unsigned long long vb = c < n_chunks ? hb[c] : 0ull;
+        uint32_t ic = vc;
+        unsigned long long ib = vb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d);
+            const unsigned long long tb = __shfl_up_sync(0xffffffffu, ib, d);
+            if (lane >= d) { ic += tc; ib += tb; }
+        }
+        if (lane == 31) { s_c[w] = ic; s_b[w] = ib; }
+        __syncthreads();
+        uint32_t oc = s_run_c;
+        unsigned long long ob = s_run_b;
+        for (int i = 0; i < w; i++) { oc += s_c[i]; ob += s_b[i]; }
+        if (c < n_chunks) { hc[c] = oc + ic - vc; hb[c] = ob + ib - vb; }
+        __syncthreads();
+        if (threadIdx.x == 255) { s_run_c = oc + ic; s_run_b = ob + ib; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { bin_counts[b] = s_run_c; bin_bytes[b] = s_run_b; }
+}
+
+// exclusive scan of the bin byte totals -> where each bin starts in the FASTQ output
+__global__ void bin_offsets_kernel(int n_bins, const uint64_t *__restrict__ bin_bytes, uint64_t *__restrict__ bin_offsets)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long acc = 0;
-        for (int b = 0; b < n_bins; b++) { bin_offsets[b] = acc; acc += s_tot_bytes[b]; }
+        for (int b = 0; b < n_bins; b++) { bin_offsets[b] = acc; acc += bin_bytes[b]; }
         bin_offsets[n_bins] = acc;
     }
 }
