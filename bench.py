@@ -58,7 +58,17 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json configs[]: 2 = 1 Mi COI reads two-round (default, the metric's config), "
+                         "3 = rRNA-cistron reads 1-3.5 kb two-round, 4 = anchored --no-indels Hamming path "
+                         "(24 M13 variable indices) on reads with the bare index at offset 0")
+    ap.add_argument("--sub-batches", type=int, default=8)
+    a = ap.parse_args()
+    if a.config == 3 and a.len_min == 300 and a.len_max == 900:
+        a.len_min, a.len_max = 1000, 3500
+        if a.reads == 1 << 20:
+            a.reads = 1 << 18
+    return a
 
 
 class ClockSampler:
@@ -202,15 +212,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    seed = 1002 if world == 1 else (1005 << 32) + rank
+    seed = {2: 1002, 3: 1003, 4: 1004}[args.config] if world == 1 else (1005 << 32) + rank
     workers = max(1, min(16, ncpu // max(world, 1)))
     t0 = time.perf_counter()
-    rs = synth.generate(args.reads, args.len_min, args.len_max, seed=seed, workers=workers)
+    rs = synth.generate(args.reads, args.len_min, args.len_max, seed=seed, workers=workers,
+                        anchored=(args.config == 4))
+    if args.config == 4:
+        from orcdemux import m13
+        from orcdemux.lib import ORC_PREFIX
+        var = m13.variable_all()
+        rounds = [E.Round([n for n, _ in var], [q for _, q in var], ORC_PREFIX, 0.1, 3, False, True)]
+    else:
+        rounds = E.m13_rounds()
     gen_s = time.perf_counter() - t0
     rs = E.pin_readset(rs)
     n_bytes = int(rs.seq.shape[0])
     n_slots = 1
-    eng = E.Engine(E.m13_rounds(), device=local_rank, max_reads=rs.n_reads, max_bytes=n_bytes,
+    eng = E.Engine(rounds, device=local_rank, max_reads=rs.n_reads, max_bytes=n_bytes,
                    max_name_bytes=int(rs.names.shape[0]) + 64, n_slots=n_slots, emit_fastq=True, want_matches=True)
 
     # ---- device-resident: `value`
@@ -251,7 +269,7 @@ def main():
     e2e = None
     eng.close()
     if not args.no_e2e:
-        SUB, S = 8, 4
+        SUB, S = max(1, args.sub_batches), 4
         per = (args.reads + SUB - 1) // SUB
         subs = []
         for i in range(SUB):
@@ -266,7 +284,7 @@ def main():
             noff = E.pinned_empty(hi - lo + 1, np.uint64)
             noff[...] = rs.name_offsets[lo:hi + 1] - np.uint64(n0)
             subs.append(synth.ReadSet(rs.seq[b0:b1], rs.qual[b0:b1], off, rs.lengths[lo:hi], rs.names[n0:n1], noff, {}))
-        eng2 = E.Engine(E.m13_rounds(), device=local_rank, max_reads=per,
+        eng2 = E.Engine(rounds, device=local_rank, max_reads=per,
                         max_bytes=max(int(x.seq.shape[0]) for x in subs) + 64,
                         max_name_bytes=max(int(x.names.shape[0]) for x in subs) + 64, n_slots=S,
                         emit_fastq=True, want_matches=True)
@@ -320,7 +338,7 @@ def main():
         counts_np = None
 
     # ---- the only collective: per-bin count gather
-    counts = torch.from_numpy(counts_np if counts_np is not None else np.zeros(169, np.int64)).cuda()
+    counts = torch.from_numpy(counts_np if counts_np is not None else np.zeros(1, np.int64)).cuda()
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     total_reads_binned = int(counts.sum().item())
@@ -359,7 +377,7 @@ def main():
              "peak_how": "of " + how}]
         extra["gcups"] = cells * args.steps * world / (max_ms * 1e-3) / 1e9 if world == 1 else None
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config != 4:
         import oracle
         oracle.build()
         n_s = args.cpu_sample or 16384
@@ -373,8 +391,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "configs[1]: full two-round SP5->SP27 combinatorial demux + trim on %d synthetic "
-                                   "COI-length reads (%d-%d nt) per GPU, -e 0.1 -O 3 --rc, 12+12 M13 indices"
+            "config": {"workload": {2: "configs[1]: full two-round SP5->SP27 combinatorial demux + trim on %d synthetic "
+                                       "COI-length reads (%d-%d nt) per GPU, -e 0.1 -O 3 --rc, 12+12 M13 indices",
+                                    3: "configs[2]: two-round demux on %d synthetic rRNA-cistron reads (%d-%d nt) per GPU",
+                                    4: "configs[3]: anchored --no-indels Hamming path, 24 M13 variable indices, %d reads "
+                                       "(%d-%d nt) per GPU, index at read offset 0"}[args.config]
                                    % (args.reads, args.len_min, args.len_max),
                        "reads_per_gpu": args.reads, "seed": seed, "l2": "inputs larger than L2 (%.2f GB resident "
                        "per step)" % (2.5 * n_bytes / 1e9), "parallelism": "reads sharded by batch, no data-path "

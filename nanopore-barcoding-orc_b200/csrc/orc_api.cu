@@ -404,9 +404,13 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     s.did_d2h = false;
     if (n) {
         init_views_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_offsets, s.d_lengths, n, s.d_views[0]);
-        const uint64_t n16 = (s.n_bytes + 15) / 16;
-        const int pack_blocks = (int)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16);
-        pack_kernel<<<pack_blocks, 256, 0, st>>>(s.d_seq, W, n16, ctx->d_pack_lut);
+        bool need_codes = false;        // anchored rounds read the ASCII bases directly
+        for (int r = 0; r < ctx->n_rounds; r++) need_codes = need_codes || !ctx->anchored[r];
+        if (need_codes) {
+            const uint64_t n16 = (s.n_bytes + 15) / 16;
+            const int pack_blocks = (int)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16);
+            pack_kernel<<<pack_blocks, 256, 0, st>>>(s.d_seq, W, n16, ctx->d_pack_lut);
+        }
     }
     CK(cudaEventRecord(s.ev[EV_PACK], st));
     for (int r = 0; r < ctx->n_rounds; r++) {
