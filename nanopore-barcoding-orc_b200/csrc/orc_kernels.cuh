@@ -483,12 +483,32 @@ bin_place_kernel(const int32_t *__restrict__ bin, const uint32_t *__restrict__ r
     }
 }
 
+// Warp-cooperative copy of n bytes with arbitrary source and destination alignment: the
+// destination is written in aligned 32-bit words assembled from two aligned source words by a
+// funnel shift (head and tail bytes singly).  src may be over-read by up to 7 bytes (the blobs
+// have slack).
+__device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                          uint32_t n, int lane)
+{
+    const uint32_t head = min(n, (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u));
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    const uint32_t nw = (n - head) >> 2;
+    const uint8_t *sp = src + head;
+    const uint32_t sh = (uint32_t)((uintptr_t)sp & 3u) * 8u;
+    const uint32_t *sa = reinterpret_cast<const uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
+    uint32_t *da = reinterpret_cast<uint32_t *>(dst + head);
+    for (uint32_t w = lane; w < nw; w += 32) da[w] = __funnelshift_r(sa[w], sa[w + 1], sh);
+    const uint32_t done = head + 4u * nw;
+    if (done + (uint32_t)lane < n) dst[done + lane] = src[done + lane];
+}
+
 // One warp per read: '@' name [' rc']* '\n' seq '\n' '+' '\n' qual '\n'
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
             const uint8_t *__restrict__ names, const uint64_t *__restrict__ name_offsets,
             const uint32_t *__restrict__ name_lengths, const uint64_t *__restrict__ offsets,
-            const uint64_t *__restrict__ qual_offsets, const View *__restrict__ views, const uint64_t *__restrict__ dest, uint32_t n_reads,
+            const uint64_t *__restrict__ qual_offsets, const View *__restrict__ views,
+            const uint64_t *__restrict__ dest, uint32_t n_reads,
             const uint8_t *__restrict__ comp_lut_g, uint8_t *__restrict__ out)
 {
     __shared__ uint8_t comp[256];
@@ -507,7 +527,7 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
         const uint32_t L = v.len;
         uint8_t *o = out + d;
         if (lane == 0) o[0] = '@';
-        for (uint32_t i = lane; i < nl; i += 32) o[1 + i] = names[n0 + i];
+        warp_copy(o + 1, names + n0, nl, lane);
         o += 1 + nl;
         for (uint32_t i = lane; i < 3 * nrc; i += 32) o[i] = (i % 3 == 0) ? ' ' : (i % 3 == 1) ? 'r' : 'c';
         o += 3 * nrc;
@@ -521,10 +541,8 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
                 o[L + 3 + i] = q[L - 1 - i];
             }
         } else {
-            for (uint32_t i = lane; i < L; i += 32) {
-                o[i] = s[i];
-                o[L + 3 + i] = q[i];
-            }
+            warp_copy(o, s, L, lane);
+            warp_copy(o + L + 3, q, L, lane);
         }
         if (lane == 0) { o[L] = '\n'; o[L + 1] = '+'; o[L + 2] = '\n'; o[2 * L + 3] = '\n'; }
     }
