@@ -194,3 +194,61 @@ def test_anchored_hamming_path_config4():
                    for r in np.flatnonzero(exp_bin == b))
     assert res.bin_bytes(b) == exp
     assert (rec0["adapter"] >= 0).mean() > 0.5 and t["total_ms"] > 0
+
+
+def test_adversarial_and_random_adapter_sets():
+    """The kernels (not only their host simulation) on adversarial reads and random adapter sets:
+    shared prefixes of any length (trigger filter on or off), 1..16 adapters of 3..64 nt, error
+    rates up to 0.4, both adapter types in either round order, with and without --rc."""
+    import random
+    import oracle
+    import test_hostsim as TH
+    from orcdemux.lib import ORC_BACK, ORC_FRONT
+    rnd = random.Random(2024)
+    for trial in range(10):
+        nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
+        mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([3, 8, 17, 20, 33, 57, 64])))
+        shared = mk()[:rnd.choice([4, 10, 17, 25, 32])]
+        f = [((shared if rnd.random() < 0.8 else "") + mk())[:64] for _ in range(nf)]
+        b = [((shared if rnd.random() < 0.8 else "") + mk())[:64] for _ in range(nb)]
+        e = rnd.choice([0.0, 0.1, 0.1, 0.2, 0.3, 0.4])
+        ov = rnd.choice([1, 3, 3, 5, 8])
+        rc = rnd.choice([0, 1, 1])
+        spec = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
+        if trial % 3 == 1:
+            spec = spec[::-1]
+        if trial % 4 == 3:
+            spec = spec[:1]
+        rs = TH._adversarial_reads(rnd, f, b, 3000)
+        rounds = [E.Round([str(i) for i in range(len(x[0]))], x[0], ORC_FRONT if x[1] == oracle.FRONT else ORC_BACK,
+                          x[2], x[3], True, bool(x[4])) for x in spec]
+        with E.Engine(rounds, max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]) + 64, n_slots=1) as eng:
+            res = eng.run(rs)
+        rec = H.run_oracle(spec, rs)
+        idx, nbad = H.diff_matches(rec[0], res.matches[0])
+        assert nbad == 0, (trial, "round 1", idx[:3], rs.read(int(idx[0]))[1])
+        if len(spec) > 1:
+            idx, nbad = H.diff_matches(rec[1], res.matches[1])
+            assert nbad == 0, (trial, "round 2", idx[:3])
+        assert np.array_equal(res.out_len, rec[4])
+
+
+def test_long_reads_and_capacity_errors():
+    from orcdemux.engine import OrcError
+    sp5 = [s for _, s in synth.m13.sp5_forward()]
+    sp27 = [s for _, s in synth.m13.sp27_reverse_rc()]
+    import random
+    rnd = random.Random(1)
+    body = "".join(rnd.choice("ACGT") for _ in range(150000))
+    recs = [("long_fwd", sp5[3] + body + sp27[4], "I" * (59 + 150000 + 57)),
+            ("long_rc", synth.m13.revcomp(sp5[3] + body + sp27[4]), "I" * (59 + 150000 + 57)),
+            ("short", sp5[0] + "ACGT" * 30 + sp27[1], "I" * (59 + 120 + 57))]
+    rs = synth.from_records(recs)
+    res = _check(rs)
+    assert list(res.matches[0]["adapter"]) == [3, 3, 0] and list(res.matches[1]["adapter"]) == [4, 4, 1]
+    eng = _engine(2, 1024)
+    try:
+        with pytest.raises(OrcError, match="exceeds"):
+            eng.run(rs)
+    finally:
+        eng.close()
