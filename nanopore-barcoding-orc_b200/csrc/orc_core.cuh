@@ -65,6 +65,11 @@ struct RoundTable {
     int32_t k_max, m_max;           // largest k and m of the round
     uint32_t peq32[16][64];         // [read code][lane]: match bits of the prefix, row Lp at bit 31;
                                     // even lanes: direction 0, odd lanes: direction 1 (complemented)
+    // what decides whether the mandatory first (5') / last (3') window is needed at all
+    int32_t lcs;                    // length Ls of the suffix all adapters share (<= 32, 0: none)
+    int32_t min_ov_min;             // smallest min_ov of the round
+    uint8_t kmax_any[MAX_M + 8];    // max over the adapters of kmax[a][L]
+    uint32_t peq32s[16][64];        // like peq32, for the shared suffix (5' rounds only)
 };
 
 // A read (or what a previous round left of it) as a window of the packed code array:
@@ -257,9 +262,13 @@ ORC_HD void win_add(WinList &L, bool &open, uint32_t &cs, uint32_t &ce, uint32_t
 // Stage 1.  peq32_base: table of the shared prefix, entry (code, lane) at code*256 + lane*4,
 // row Lp at bit 31.  kt = largest k of the round, ext = m_max - Lp + kt, back = Lp + kt + 1
 // (an alignment through (Lp, j') with <= kt errors starts at a column >= j' - Lp - kt).
+// `suffix_base` (5' rounds, may be nullptr) is the table of the suffix S all adapters share, Ls
+// its length; kmax_any / min_ov_min are the loosest acceptance limits of the round.
 ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                          const char *peq32_base, int lane, int Lp, int kt, int type,
-                         uint32_t ext, uint32_t back, WinList &out)
+                         uint32_t ext, uint32_t back, WinList &out,
+                         const char *suffix_base = nullptr, int Ls = 0,
+                         const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0)
 {
     const uint32_t n = len;
     out.n = 0; out.pad_ = 0;
@@ -269,14 +278,61 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     const uint32_t pad = (Lp == 32) ? 0u : ((1u << (32 - Lp)) - 1u);
     uint32_t Pv, Mv = 0;
     int D;
-    if (type == TYPE_FRONT) {
-        Pv = 0; D = 0;
-        win_add(out, open, cs, ce, 0u, ext < n ? ext : n);   // alignments starting in column 0
-    } else { Pv = ~pad; D = Lp; }
     const uint32_t lane4 = (uint32_t)lane * 4u;
     uint32_t sel0, sel1, sel2, sel3;
     if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
     else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
+    // The prefix scan itself never uses column 0 for free (column costs i, also for 5' adapters):
+    // it only has to find alignments that start in row 0, which cost the same in either matrix.
+    Pv = ~pad; D = Lp;
+    if (type == TYPE_FRONT) {
+        // Alignments of a 5' adapter that start in column 0 (origin < 0: the read begins inside
+        // the adapter) end within the first m + k columns and end with (a suffix of) the suffix S
+        // all adapters share, so the last row of S's own matrix (column 0 free, REF_START) must
+        // pass the candidate condition at the column where they end.  No such column -> no such
+        // alignment for any adapter -> the window [0, m_max + k] is not needed.
+        const uint32_t wmax = (uint32_t)(m_max + kt);
+        const uint32_t w0 = wmax < n ? wmax : n;
+        bool need = true;
+        if (suffix_base != nullptr && Ls > 0) {
+            need = false;
+            uint32_t sPv = 0, sMv = 0;
+            int sD = 0;
+            ChunkReader rs;
+            rs.init(W, lo, len, dir, 0u);
+            for (uint32_t c0 = 0; c0 < w0 && !need; c0 += 8) {
+                uint32_t A, B;
+                rs.next(A, B);
+                const int ncol = imin(8, (int)(w0 - c0));
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (t < ncol) {
+                        const uint32_t src = (t & 1) ? B : A;
+                        const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+                        const uint32_t Eq = *reinterpret_cast<const uint32_t *>(suffix_base + byte_perm(src, lane4, sel));
+                        const uint32_t Xv = Eq | sMv;
+                        const uint32_t Xh = (((Eq & sPv) + sPv) ^ sPv) | Eq;
+                        uint32_t Ph = sMv | ~(Xh | sPv);
+                        uint32_t Mh = sPv & Xh;
+                        sD += (int)(Ph >> 31) - (int)(Mh >> 31);
+                        Ph <<= 1; Mh <<= 1;
+                        sPv = Mh | ~(Xv | Ph);
+                        sMv = Ph & Xv;
+                        if (sD <= kt) {
+                            const int j = (int)c0 + t + 1;
+                            // an alignment ending here has cost c >= sD and aligns at most
+                            // min(m_max, j + c) adapter characters
+                            for (int c = sD; c <= kt; c++) {
+                                const int lmax = imin(m_max, j + c);
+                                if (lmax >= min_ov_min && c <= (int)kmax_any[lmax]) need = true;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (need) win_add(out, open, cs, ce, 0u, w0);          // alignments starting in column 0
+    }
     ChunkReader rd;
     rd.init(W, lo, len, dir, 0u);
     const int nchunks = (int)((n + 7u) >> 3);
@@ -320,9 +376,24 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
             D += popc32(accP) - popc32(accM);
         }
     }
-    if (type == TYPE_BACK) {                     // rows <= Lp of the last column
-        const uint32_t r = (uint32_t)(Lp + kt + 1);
-        win_add(out, open, cs, ce, n > r ? n - r : 0u, n);
+    if (type == TYPE_BACK) {
+        // The last window is for the cells (i, n) with i <= Lp: an adapter prefix of at most Lp
+        // characters at the read end.  Those rows are the same for every adapter and this scan
+        // (true column 0) has them exactly: if none of them passes R6's necessary condition under
+        // the loosest limits of the round, no adapter has such a candidate and the window is moot.
+        bool need = kmax_any == nullptr;
+        if (!need) {
+            int cum = 0;
+            for (int i = 1; i <= Lp; i++) {
+                const int bit = 32 - Lp + i - 1;
+                cum += (int)((Pv >> bit) & 1u) - (int)((Mv >> bit) & 1u);
+                if (i >= min_ov_min && cum <= (int)kmax_any[i]) need = true;
+            }
+        }
+        if (need) {
+            const uint32_t r = (uint32_t)(Lp + kt + 1);
+            win_add(out, open, cs, ce, n > r ? n - r : 0u, n);
+        }
     }
     if (open) { out.s[out.n] = cs; out.e[out.n] = ce; out.n++; }
 }

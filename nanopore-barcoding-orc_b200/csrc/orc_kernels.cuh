@@ -96,11 +96,17 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                unsigned long long *__restrict__ col_sum)
 {
     __shared__ __align__(16) uint32_t s_peq32[16][64];
+    __shared__ __align__(16) uint32_t s_peq32s[16][64];
+    __shared__ uint8_t s_kmax_any[MAX_M + 8];
     __shared__ int s_par[8];
-    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32[0][0])[i] = (&tab->peq32[0][0])[i];
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+        (&s_peq32[0][0])[i] = (&tab->peq32[0][0])[i];
+        (&s_peq32s[0][0])[i] = (&tab->peq32s[0][0])[i];
+    }
+    for (int i = threadIdx.x; i < MAX_M + 8; i += blockDim.x) s_kmax_any[i] = tab->kmax_any[i];
     if (threadIdx.x == 0) {
         s_par[0] = tab->lcp; s_par[1] = tab->k_max; s_par[2] = tab->m_max; s_par[3] = tab->type;
-        s_par[4] = tab->revcomp; s_par[5] = tab->use_filter;
+        s_par[4] = tab->revcomp; s_par[5] = tab->use_filter; s_par[6] = tab->lcs; s_par[7] = tab->min_ov_min;
     }
     __syncthreads();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,7 +125,9 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
             if (s_par[5]) {
                 trigger_lane(W, v.lo, v.len, dir, reinterpret_cast<const char *>(&s_peq32[0][0]),
                              (int)(threadIdx.x & 63u), Lp, kt, type, (uint32_t)(m_max - Lp + kt),
-                             (uint32_t)(Lp + kt + 1), wl);
+                             (uint32_t)(Lp + kt + 1), wl,
+                             (type == TYPE_FRONT && s_par[6] > 0) ? reinterpret_cast<const char *>(&s_peq32s[0][0]) : nullptr,
+                             s_par[6], s_kmax_any, s_par[7], m_max);
                 cols = win_columns(wl);
             } else {
                 wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything

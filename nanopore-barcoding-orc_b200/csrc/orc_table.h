@@ -100,6 +100,38 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
     T.lcp = lcp; T.k_max = k_max; T.m_max = m_max;
     const bool valid = lcp > k_max && lcp >= 1;
     T.use_filter = (filter_mode == 2) ? valid : (filter_mode == 1 ? (valid && lcp >= 12 && lcp > 2 * k_max) : 0);
+    // shared suffix and the loosest acceptance limits (decide the mandatory windows in stage 1)
+    int lcs = T.m[0];
+    for (int a = 1; a < n_adapters; a++) {
+        int l = 0;
+        while (l < lcs && l < T.m[a] && T.code[a][T.m[a] - 1 - l] == T.code[0][T.m[0] - 1 - l]) l++;
+        lcs = l;
+    }
+    if (lcs > 32) lcs = 32;
+    T.lcs = lcs;
+    T.min_ov_min = T.min_ov[0];
+    for (int a = 1; a < n_adapters; a++) if (T.min_ov[a] < T.min_ov_min) T.min_ov_min = T.min_ov[a];
+    for (int L = 0; L <= MAX_M; L++) {
+        int v = 0;
+        for (int a = 0; a < n_adapters; a++) {
+            const int l = L < T.m[a] ? L : T.m[a];
+            if (T.kmax[a][l] > v) v = T.kmax[a][l];
+        }
+        T.kmax_any[L] = (uint8_t)v;
+    }
+    if (T.use_filter && type == TYPE_FRONT && lcs > 0) {
+        const uint32_t pad32 = (lcs == 32) ? 0u : ((1u << (32 - lcs)) - 1u);
+        for (int lane = 0; lane < 64; lane++) {
+            const int dir = lane & 1;
+            for (uint32_t c = 0; c < 16; c++) {
+                const uint32_t cc = dir ? comp4(c) : c;
+                uint32_t bits = pad32;
+                for (int i = 0; i < lcs; i++)
+                    if (T.code[0][T.m[0] - lcs + i] & cc) bits |= 1u << (32 - lcs + i);
+                T.peq32s[c][lane] = bits;
+            }
+        }
+    }
     if (T.use_filter) {
         const uint32_t pad32 = (lcp == 32) ? 0u : ((1u << (32 - lcp)) - 1u);
         for (int lane = 0; lane < 64; lane++) {

@@ -12,7 +12,8 @@ for trial in range(trials):
     mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([3, 5, 8, 12, 17, 20, 33, 40, 57, 64])))
     shared = mk()[:rnd.choice([4, 10, 17, 25, 32, 40])]
     pshare = rnd.choice([0.5, 1.0, 1.0])
-    f = [((shared if rnd.random() < pshare else "") + mk())[:64] for _ in range(nf)]
+    sfx = mk()[:rnd.choice([0, 3, 8, 17, 30])]
+    f = [(((shared if rnd.random() < pshare else "") + mk())[:64 - len(sfx)] + (sfx if rnd.random() < pshare else "")) for _ in range(nf)]
     b = [((shared if rnd.random() < pshare else "") + mk() + (shared if rnd.random() < 0.5 else ""))[:64] for _ in range(nb)]
     if rnd.random()<0.3:  # low complexity adapters
         f=[ (x[:4]*16)[:len(x)] for x in f]; b=[(x[:3]*22)[:len(x)] for x in b]
