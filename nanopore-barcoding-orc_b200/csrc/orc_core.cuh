@@ -63,6 +63,7 @@ struct RoundTable {
     int32_t use_filter;             // 1 if the adapters share a prefix long enough to filter on
     int32_t lcp;                    // its length Lp (<= 32)
     int32_t k_max, m_max;           // largest k and m of the round
+    int32_t m_min, pad2_;           // shortest adapter
     uint32_t peq32[16][64];         // [read code][lane]: match bits of the prefix, row Lp at bit 31;
                                     // even lanes: direction 0, odd lanes: direction 1 (complemented)
     // what decides whether the mandatory first (5') / last (3') window is needed at all
@@ -268,7 +269,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                          const char *peq32_base, int lane, int Lp, int kt, int type,
                          uint32_t ext, uint32_t back, WinList &out,
                          const char *suffix_base = nullptr, int Ls = 0,
-                         const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0)
+                         const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0, int m_min = 0)
 {
     const uint32_t n = len;
     out.n = 0; out.pad_ = 0;
@@ -333,6 +334,74 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         }
         if (need) win_add(out, open, cs, ce, 0u, w0);          // alignments starting in column 0
     }
+    // Triggers are collected into clusters (runs with gaps <= 2k).  A cluster of a 3' round is
+    // confirmed before it opens a window: a full-length alignment through (Lp, j') ends between
+    // j' + (m_min - Lp) - k and j' + (m_max - Lp) + k with the suffix S all adapters share fully
+    // aligned, i.e. S's own matrix has a last-row cost <= k at that end column.  One short scan of
+    // S over that range decides; random hits of the 17-nt SP27 prefix (0.2 % of the columns) almost
+    // never survive it.  A cluster whose window would reach the read end is kept unconditionally
+    // (partial adapters at the 3' end do not contain S).
+    // The confirming scans run after the main loop, cluster by cluster, so that the lanes of a warp
+    // (32 different reads) do them at the same time; during the main loop clusters are only noted.
+    const bool confirm = type == TYPE_BACK && suffix_base != nullptr && Ls > 0;
+    constexpr int MAX_CLU = 12;
+    uint32_t clu_fs[MAX_CLU], clu_ls[MAX_CLU];
+    int n_clu = 0;
+    bool noted_all = true;              // false once a cluster had to be added without being noted
+    uint32_t clu_f = 0, clu_l = 0;      // first / last trigger column of the open cluster (0: none)
+    auto add_cluster = [&](uint32_t f, uint32_t l, bool check) {
+        const uint32_t wl_s = f > back ? f - back : 0u;
+        const uint32_t wl_e = (l + ext) < n ? (l + ext) : n;
+        bool ok = true;
+        const uint32_t hi = l + (uint32_t)(m_max - Lp + kt);
+        if (check && hi < n) {
+            ok = false;
+            const int lo_end = imax(1, (int)f + (m_min - Lp) - kt);
+            const uint32_t s0 = (uint32_t)imax(0, lo_end - Ls - kt - 1);
+            const uint32_t spad = (Ls == 32) ? 0u : ((1u << (32 - Ls)) - 1u);
+            uint32_t sPv = ~spad, sMv = 0;
+            int sD = Ls;
+            ChunkReader rs;
+            rs.init(W, lo, len, dir, s0);
+            for (uint32_t c0 = s0; c0 < hi && !ok; c0 += 8) {
+                uint32_t A, B;
+                rs.next(A, B);
+                const int ncol = imin(8, (int)(hi - c0));
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (t < ncol) {
+                        const uint32_t src = (t & 1) ? B : A;
+                        const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+                        const uint32_t Eq = *reinterpret_cast<const uint32_t *>(suffix_base + byte_perm(src, lane4, sel));
+                        const uint32_t Xv = Eq | sMv;
+                        const uint32_t Xh = (((Eq & sPv) + sPv) ^ sPv) | Eq;
+                        uint32_t Ph = sMv | ~(Xh | sPv);
+                        uint32_t Mh = sPv & Xh;
+                        sD += (int)(Ph >> 31) - (int)(Mh >> 31);
+                        Ph <<= 1; Mh <<= 1;
+                        sPv = Mh | ~(Xv | Ph);
+                        sMv = Ph & Xv;
+                        if (sD <= kt && (int)c0 + t + 1 >= lo_end) ok = true;
+                    }
+                }
+            }
+        }
+        if (ok) win_add(out, open, cs, ce, wl_s, wl_e);
+    };
+    auto flush_cluster = [&]() {
+        if (clu_f == 0) return;
+        if (!confirm) add_cluster(clu_f, clu_l, false);
+        else if (noted_all && n_clu < MAX_CLU) { clu_fs[n_clu] = clu_f; clu_ls[n_clu] = clu_l; n_clu++; }
+        else {
+            // out of slots: from here on clusters open their windows unconfirmed; the noted ones are
+            // earlier in the read and must be added first to keep the windows in order
+            for (int c = 0; c < n_clu; c++) add_cluster(clu_fs[c], clu_ls[c], false);
+            n_clu = 0;
+            noted_all = false;
+            add_cluster(clu_f, clu_l, false);
+        }
+        clu_f = 0;
+    };
     ChunkReader rd;
     rd.init(W, lo, len, dir, 0u);
     const int nchunks = (int)((n + 7u) >> 3);
@@ -368,14 +437,17 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                 D += (int)((accP >> b) & 1u) - (int)((accM >> b) & 1u);
                 if (D <= kt) {
                     const uint32_t j = (uint32_t)(8 * q + t + 1);
-                    const uint32_t e = j + ext;
-                    win_add(out, open, cs, ce, j > back ? j - back : 0u, e < n ? e : n);
+                    if (clu_f != 0 && j - clu_l > (uint32_t)(2 * kt)) flush_cluster();
+                    if (clu_f == 0) clu_f = j;
+                    clu_l = j;
                 }
             }
         } else {
             D += popc32(accP) - popc32(accM);
         }
     }
+    flush_cluster();
+    for (int c = 0; c < n_clu; c++) add_cluster(clu_fs[c], clu_ls[c], true);
     if (type == TYPE_BACK) {
         // The last window is for the cells (i, n) with i <= Lp: an adapter prefix of at most Lp
         // characters at the read end.  Those rows are the same for every adapter and this scan

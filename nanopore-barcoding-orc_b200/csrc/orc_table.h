@@ -98,6 +98,8 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         if (T.m[a] > m_max) m_max = T.m[a];
     }
     T.lcp = lcp; T.k_max = k_max; T.m_max = m_max;
+    T.m_min = T.m[0];
+    for (int a = 1; a < n_adapters; a++) if (T.m[a] < T.m_min) T.m_min = T.m[a];
     const bool valid = lcp > k_max && lcp >= 1;
     T.use_filter = (filter_mode == 2) ? valid : (filter_mode == 1 ? (valid && lcp >= 12 && lcp > 2 * k_max) : 0);
     // shared suffix and the loosest acceptance limits (decide the mandatory windows in stage 1)
@@ -119,7 +121,7 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         }
         T.kmax_any[L] = (uint8_t)v;
     }
-    if (T.use_filter && type == TYPE_FRONT && lcs > 0) {
+    if (T.use_filter && lcs > 0) {
         const uint32_t pad32 = (lcs == 32) ? 0u : ((1u << (32 - lcs)) - 1u);
         for (int lane = 0; lane < 64; lane++) {
             const int dir = lane & 1;

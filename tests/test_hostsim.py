@@ -46,7 +46,7 @@ def _adversarial_reads(rnd, adapters_f, adapters_b, n):
     recs = []
     comp = str.maketrans("ACGT", "TGCA")
     for i in range(n):
-        kind = rnd.randrange(12)
+        kind = rnd.randrange(14)
         L = rnd.randint(0, 260)
         body = "".join(rnd.choice("ACGT") for _ in range(L))
         a = rnd.choice(adapters_f)
@@ -87,6 +87,12 @@ def _adversarial_reads(rnd, adapters_f, adapters_b, n):
             s = a[-rnd.randint(0, 14):] + body
         elif kind == 10:
             s = mutate(a + b, 0.03) * rnd.randint(1, 3)
+        elif kind == 12:      # 3' adapter in the middle of the read, near the error limit
+            tail = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(40, 200)))
+            s = body + mutate(b, rnd.choice([0.03, 0.08, 0.12])) + tail
+        elif kind == 13:      # 5' adapter in the middle of the read
+            tail = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(40, 200)))
+            s = body + mutate(a, rnd.choice([0.03, 0.08, 0.12])) + tail
         else:
             s = "".join(rnd.choice("ACGTN") for _ in range(L))
         if rnd.random() < 0.1:
