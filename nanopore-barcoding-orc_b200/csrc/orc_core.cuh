@@ -55,6 +55,11 @@ struct RoundTable {
     int32_t min_ov[MAX_AD];         // min(min_overlap, m)
     uint8_t kmax[MAX_AD][MAX_M + 8];// kmax[a][L] = max cost with cost <= L * rate (fp64, R5/R6)
     uint8_t code[MAX_AD][MAX_M];    // adapter as 4-bit IUPAC masks (A1 C2 G4 T8)
+    // the same, 8 codes per word, for the resolver's 16-cells-at-a-time diagonal walk:
+    // code4: nibble 16+q = adapter[q] (16 zero nibbles in front); rcode4: nibble q =
+    // comp(adapter[m-1-q]) (zero nibbles behind) -- what a direction-1 lane compares raw codes with
+    uint32_t code4[MAX_AD][12];
+    uint32_t rcode4[MAX_AD][12];
     uint64_t peq[16][MAX_LANES];    // [read code][lane]: match bits, row i at bit 64-m+i-1,
                                     // the 64-m low padding bits always 1
     uint64_t pv0[MAX_LANES];        // vertical deltas of column 0 (R2)
@@ -681,9 +686,42 @@ ORC_HD int ring_cost(const ColRing &R, int m, int i, int j, int ws)
     return (int)R.dm[x] - popc64(pv) + popc64(mv);
 }
 
+ORC_HD int clz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+
+ORC_HD int ctz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return x ? __ffsll((long long)x) - 1 : 64;
+#else
+    return x ? __builtin_ctzll(x) : 64;
+#endif
+}
+
+// 16 consecutive 4-bit codes starting at code index idx of a word array (idx may be unaligned)
+ORC_HD uint64_t nib16(const uint32_t *A, int64_t idx)
+{
+    const int64_t w = idx >> 3;
+    const uint32_t sh = (uint32_t)(idx & 7) * 4u;
+    const uint32_t a = A[w], b = A[w + 1], c = A[w + 2];
+    return (uint64_t)funnel_r(a, b, sh) | ((uint64_t)funnel_r(b, c, sh) << 32);
+}
+
 // Walk cutadapt's path back from cell (i, j) whose cost is d.  ws is the first stored
 // column (the restart column, or 0).  Yields the score and the origin of the cell.
+//
+// On equal characters cutadapt always takes the diagonal, so most of a path is runs of matches
+// along a diagonal -- consecutive characters of both strings.  A run is measured 16 cells at a
+// time: 16 packed read codes AND 16 packed adapter codes, first all-zero nibble = first mismatch.
+// Only at a mismatch cell (at most k per path) are the neighbour costs looked up in the ring.
 ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, const uint64_t *peq_lane,
+                       const uint32_t *code4, const uint32_t *rcode4,
                        int m, int type, int ws, const ColRing &R, int i, int j, int d,
                        int &score_out, int &origin_out)
 {
@@ -695,13 +733,33 @@ ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, co
             break;
         }
         if (j <= ws) { origin = j; break; }          // unreachable for a genuine candidate
-        const int bit = 64 - m + i - 1;
-        const uint32_t raw = dir ? nib(W, (int64_t)lo + (int64_t)len - j) : nib(W, (int64_t)lo + j - 1);
-        const uint64_t eq = peq_lane[raw * MAX_LANES];
-        if ((eq >> bit) & 1u) {                      // characters equal: diagonal, unconditionally
-            score += 1; --i; --j;
+        // matches along the diagonal from (i, j) up-left, at most min(16, i, j - ws) of them
+        const int avail = imin(16, imin(i, j - ws));
+        int run;
+        if (!dir) {
+            // read codes j-16..j-1 (view) = storage lo+j-16 .. lo+j-1; adapter codes i-16..i-1
+            const uint64_t r = nib16(W, (int64_t)lo + j - 16);
+            const uint64_t a = nib16(code4, (int64_t)i);          // 16 pad nibbles in front
+            uint64_t x = r & a;
+            x |= x >> 1; x |= x >> 2;
+            const uint64_t mis = ~x & 0x1111111111111111ull;
+            run = clz64(mis) >> 2;                                // from the top nibble (cell (i, j)) down
+        } else {
+            // view position p = storage lo+len-1-p, complemented: positions j-1, j-2, ... are
+            // storage lo+len-j, +1, ...; compare raw codes with the reverse-complemented adapter
+            const uint64_t r = nib16(W, (int64_t)lo + (int64_t)len - j);
+            const uint64_t a = nib16(rcode4, (int64_t)(m - i));
+            uint64_t x = r & a;
+            x |= x >> 1; x |= x >> 2;
+            const uint64_t mis = ~x & 0x1111111111111111ull;
+            run = ctz64(mis) >> 2;
+        }
+        if (run > avail) run = avail;
+        if (run > 0) {                               // characters equal: diagonal, unconditionally
+            score += run; i -= run; j -= run;
             continue;
         }
+        const int bit = 64 - m + i - 1;
         const uint64_t pvj = R.pv[(j - ws) & (RING - 1)], mvj = R.mv[(j - ws) & (RING - 1)];
         const uint64_t pvl = R.pv[(j - 1 - ws) & (RING - 1)], mvl = R.mv[(j - 1 - ws) & (RING - 1)];
         const int d_up = d - (int)((pvj >> bit) & 1u) + (int)((mvj >> bit) & 1u);
@@ -719,7 +777,7 @@ ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, co
 // One scan over columns ws+1..we with R5 on the candidate columns jf..jl and, if the scan
 // reaches column n and r6 is set, R6 on the candidate rows.  Returns true on R5's early exit.
 ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, const uint64_t *peq_lane,
-                         int m, int type, int k, const uint8_t *kmax, int min_ov,
+                         const uint32_t *code4, const uint32_t *rcode4, int m, int type, int k, const uint8_t *kmax, int min_ov,
                          int ws, int we, int jf, int jl, bool r6, int r6lo, int r6hi,
                          Best &best, ColRing &R)
 {
@@ -756,7 +814,7 @@ ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, 
                 if (best.cost == m + n + 1 || ub > best.score) {
                     Cell c;
                     c.cost = D;
-                    trace_back(W, lo, len, dir, peq_lane, m, type, ws, R, m, j, D, c.score, c.origin);
+                    trace_back(W, lo, len, dir, peq_lane, code4, rcode4, m, type, ws, R, m, j, D, c.score, c.origin);
                     traced_j = j; traced_score = c.score; traced_origin = c.origin;
                     if (r5_update(best, m, n, c, j, min_ov, kmax)) return true;
                 }
@@ -775,7 +833,7 @@ ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, 
             Cell c;
             c.cost = Di;
             if (i == m && traced_j == n) { c.score = traced_score; c.origin = traced_origin; }
-            else trace_back(W, lo, len, dir, peq_lane, m, type, ws, R, i, n, Di, c.score, c.origin);
+            else trace_back(W, lo, len, dir, peq_lane, code4, rcode4, m, type, ws, R, i, n, Di, c.score, c.origin);
             r6_update(best, n, c, i, min_ov, kmax);
         }
     }
@@ -802,13 +860,13 @@ ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, 
         const int ws = imax(0, t.jf - m - k - 1);
         // run on to column n in the same scan when the last-column cells are close enough
         const bool join = has6 && (ws6 <= t.jl + 1 || ws == 0 && ws6 == 0);
-        broke = resolve_scan(W, v.lo, v.len, dir, peq_lane, m, T.type, k, kmax, min_ov,
+        broke = resolve_scan(W, v.lo, v.len, dir, peq_lane, T.code4[a], T.rcode4[a], m, T.type, k, kmax, min_ov,
                              ws, join ? n : t.jl, t.jf, t.jl, join, r6lo, r6hi, best, R);
         if (!broke && has6 && !join)
-            resolve_scan(W, v.lo, v.len, dir, peq_lane, m, T.type, k, kmax, min_ov,
+            resolve_scan(W, v.lo, v.len, dir, peq_lane, T.code4[a], T.rcode4[a], m, T.type, k, kmax, min_ov,
                          ws6, n, 1, 0, true, r6lo, r6hi, best, R);
     } else if (has6) {
-        resolve_scan(W, v.lo, v.len, dir, peq_lane, m, T.type, k, kmax, min_ov,
+        resolve_scan(W, v.lo, v.len, dir, peq_lane, T.code4[a], T.rcode4[a], m, T.type, k, kmax, min_ov,
                      ws6, n, 1, 0, true, r6lo, r6hi, best, R);
     }
     best_to_result(best, m, n, res);

@@ -55,6 +55,11 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
             if (code < 0) return "unsupported: adapter characters other than ACGT (IUPAC wildcards)";
             T.code[a][i] = (uint8_t)code;
         }
+        for (int q = 0; q < m; q++) {
+            const int f = 16 + q;                   // code4: 16 pad nibbles, then the adapter
+            T.code4[a][f >> 3] |= (uint32_t)T.code[a][q] << ((f & 7) * 4);
+            T.rcode4[a][q >> 3] |= comp4(T.code[a][m - 1 - q]) << ((q & 7) * 4);
+        }
         double rate = max_errors;
         if (rate >= 1.0) rate /= m;                 // absolute error count (adapters.py)
         if (!(rate >= 0.0) || rate >= 1.0) return "unsupported: error rate must be in [0, 1) for every adapter";
