@@ -135,11 +135,12 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                 wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything
                 cols = v.len;
             }
-            cols += 1;      // an active pair with nothing to scan (empty read) still has its last column
+            // an item without any column to scan has no candidate cell (R6's last-column cells are
+            // only ever reached through a window that ends at n): cols == 0 drops it from stage 2
         }
     }
     {   // columns stage 2 will scan (for the executed-cells figure of the roofline)
-        const uint32_t sum = __reduce_add_sync(0xffffffffu, cols ? cols - 1u : 0u);
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, cols);
         if ((threadIdx.x & 31) == 0 && sum) atomicAdd(col_sum, (unsigned long long)sum);
     }
     if (!valid) return;
