@@ -44,6 +44,10 @@ UNIT = "reads/s"
 # ALU-pipe instructions per DP column of one (read, adapter, orientation) pair in
 # scan_kernel's inner loop, counted in the SASS (profiles/README.md); a column is m cells.
 SCAN_ALU_INSTR_PER_COLUMN = 24.0
+# DRAM traffic of the two scan stages (trigger_kernel + scan_kernel, both rounds) per read, from the
+# ncu --set full capture profiles/r1e_main_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum
+# of the four launches at 262 144 COI reads, divided by the reads)
+SCAN_DRAM_BYTES_PER_READ = 1.354e3
 
 
 def parse_args():
@@ -357,7 +361,9 @@ def main():
         roofline = {"bound": "int32_alu",
                     "kernel": "scan = trigger_kernel (stage 1) + scan_kernel (stage 2), both rounds",
                     "achieved": ach_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": ach_gcups / peak_gcups,
-                    "traffic": None,
+                    "traffic": SCAN_DRAM_BYTES_PER_READ * args.reads if args.config == 2 else None,
+                    "traffic_how": "ncu dram bytes of the scan launches per read (profiles/r1e_main_raw.csv) x reads; "
+                                   "ALU-bound kernel: traffic is the packed codes read twice, far below HBM limits",
                     "executed": {"achieved": exe_gcups, "frac": exe_gcups / peak_gcups,
                                  "note": "DP cells the kernels really update; the rest of the algorithmic cells "
                                          "(2*12*m*n per read and round, SURVEY 8d) are skipped exactly by the "

@@ -439,7 +439,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         // Lowest cost inside the chunk, bounded from its two halves (the older columns are the
         // high bits of accP/accM): D can only fall by the M bits, and the second half starts from
         // what the first half left.  Only a chunk that may reach the threshold is replayed.
-        const int h2 = ncol >> 1, h1 = ncol - h2;                    // columns in the first / second half
+        const int h2 = ncol >> 1;                                     // columns in the second (newer) half
         const int m1 = popc32(accM >> h2), p1 = popc32(accP >> h2);
         const int m2 = popc32(accM & ((1u << h2) - 1u));
         const int low = D - imax(m1, m1 - p1 + m2);
