@@ -205,8 +205,7 @@ def main():
         print(json.dumps({"error": "no CUDA device: bench.py has no CPU fallback for the product arm"}))
         return 2
     torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
