@@ -68,7 +68,8 @@ struct RoundTable {
     int32_t use_filter;             // 1 if the adapters share a prefix long enough to filter on
     int32_t lcp;                    // its length Lp (<= 32)
     int32_t k_max, m_max;           // largest k and m of the round
-    int32_t m_min, pad2_;           // shortest adapter
+    int32_t m_min;                  // shortest adapter
+    int32_t indels;                 // 0: --no-indels (only diagonal moves; Hamming distance along diagonals)
     uint32_t peq32[16][64];         // [read code][lane]: match bits of the prefix, row Lp at bit 31;
                                     // even lanes: direction 0, odd lanes: direction 1 (complemented)
     // what decides whether the mandatory first (5') / last (3') window is needed at all
@@ -147,6 +148,43 @@ ORC_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s)
     return r;
 }
 #endif
+
+ORC_HD int popc64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+ORC_HD int clz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+
+ORC_HD int ctz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return x ? __ffsll((long long)x) - 1 : 64;
+#else
+    return x ? __builtin_ctzll(x) : 64;
+#endif
+}
+
+// 16 consecutive 4-bit codes starting at code index idx of a word array (idx may be unaligned)
+ORC_HD uint64_t nib16(const uint32_t *A, int64_t idx)
+{
+    const int64_t w = idx >> 3;
+    const uint32_t sh = (uint32_t)(idx & 7) * 4u;
+    const uint32_t a = A[w], b = A[w + 1], c = A[w + 2];
+    return (uint64_t)funnel_r(a, b, sh) | ((uint64_t)funnel_r(b, c, sh) << 32);
+}
+
 
 // cutadapt's running best match of one Aligner.locate call (R5-R7) and one DP cell.
 struct Best { int32_t score, cost, origin, ref_stop, query_stop; };
@@ -617,19 +655,98 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
     }
 }
 
+// Mismatches between adapter positions [a_from, a_to) and the view positions that start at
+// view_start, 16 packed codes per step (see trace_back for the two code layouts).
+ORC_HD int diag_mismatches(const uint32_t *W, uint64_t lo, uint32_t len, int dir,
+                           const uint32_t *code4, const uint32_t *rcode4, int m,
+                           int a_from, int a_to, int view_start)
+{
+    const int cnt = a_to - a_from;
+    int matches = 0;
+    if (!dir) {
+        for (int o = 0; o < cnt; o += 16) {
+            const uint64_t r = nib16(W, (int64_t)lo + view_start + o);
+            const uint64_t a = nib16(code4, (int64_t)(16 + a_from + o));
+            uint64_t x = r & a;
+            x |= x >> 1; x |= x >> 2;
+            x &= 0x1111111111111111ull;
+            const int c = imin(16, cnt - o);
+            if (c < 16) x &= (1ull << (4 * c)) - 1ull;
+            matches += popc64(x);
+        }
+    } else {
+        const int q_from = m - a_to;
+        const int64_t base = (int64_t)lo + (int64_t)len - view_start - m + a_from;
+        for (int o = 0; o < cnt; o += 16) {
+            const uint64_t r = nib16(W, base + q_from + o);
+            const uint64_t a = nib16(rcode4, (int64_t)(q_from + o));
+            uint64_t x = r & a;
+            x |= x >> 1; x |= x >> 2;
+            x &= 0x1111111111111111ull;
+            const int c = imin(16, cnt - o);
+            if (c < 16) x &= (1ull << (4 * c)) - 1ull;
+            matches += popc64(x);
+        }
+    }
+    return cnt - matches;
+}
+
+// --no-indels (cutadapt prices indels at 100000): within k errors only diagonal moves remain,
+// so D[m][j] is the number of mismatches along the diagonal that ends in (m, j) -- from row 0
+// (origin j - m >= 0) or, for a 5' adapter, from column 0 (origin j - m < 0, the adapter's last
+// j characters) -- score = matches - mismatches and origin = j - m, all in closed form: every
+// candidate is settled here and no pair of such a round ever needs the resolver.
+ORC_HD void scan_window_noindel(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
+                                uint32_t s, uint32_t e, const uint32_t *code4, const uint32_t *rcode4,
+                                int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L)
+{
+    const int n = (int)len;
+    bool last_cand = false;
+    Cell last;
+    last.cost = last.score = last.origin = 0;
+    for (int j = (int)s + 1; j <= (int)e; j++) {
+        if (j < m && type == TYPE_BACK) continue;          // column 0 of a 3' adapter costs 100000 * i
+        const int ov = imin(j, m);
+        const int mis = diag_mismatches(W, lo, len, dir, code4, rcode4, m, m - ov, m, j - ov);
+        if (mis <= k && ov >= min_ov && mis <= (int)kmax[ov]) {
+            L.h.jf = imin(L.h.jf, j);
+            L.h.jl = j;
+            Cell c;
+            c.cost = mis; c.score = ov - 2 * mis; c.origin = j - m;
+            if (j == n) { last_cand = true; last = c; }
+            if (!L.broke && r5_update(L.best, m, n, c, j, min_ov, kmax)) L.broke = 1;
+        }
+    }
+    if (e != len || L.broke) return;
+    if (type == TYPE_BACK) {
+        for (int i = imin(m, n); i >= 1; i--) {            // top row first, like cutadapt
+            const int mis = diag_mismatches(W, lo, len, dir, code4, rcode4, m, 0, i, n - i);
+            if (mis <= k && i >= min_ov && mis <= (int)kmax[i]) {
+                L.h.i1 = imin(L.h.i1, i);
+                L.h.i2 = imax(L.h.i2, i);
+                Cell c;
+                c.cost = mis; c.score = i - 2 * mis; c.origin = n - i;
+                r6_update(L.best, n, c, i, min_ov, kmax);
+            }
+        }
+    } else if (last_cand) {
+        r6_update(L.best, n, last, m, min_ov, kmax);       // FRONT: R6 looks at the single cell (m, n)
+    }
+}
+
 // All windows of one pair.  wl == nullptr: no prefix filter, one window over the whole view.
 ORC_HD void scan_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                       const WinList *wl, const char *peq_base, int lane, uint64_t pv0, int d0,
-                      int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L)
+                      int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L,
+                      int indels = 1, const uint32_t *code4 = nullptr, const uint32_t *rcode4 = nullptr)
 {
     lane_scan_init(L, m, (int)len);
-    if (wl == nullptr) {
-        scan_window(W, lo, len, dir, 0u, len, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, L);
-        return;
+    const uint32_t nw = wl ? wl->n : 1u;
+    for (uint32_t w = 0; w < nw; w++) {
+        const uint32_t s = wl ? wl->s[w] : 0u, e = wl ? wl->e[w] : len;
+        if (indels) scan_window(W, lo, len, dir, s, e, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, L);
+        else scan_window_noindel(W, lo, len, dir, s, e, code4, rcode4, m, k, kmax, min_ov, type, L);
     }
-    const uint32_t nw = wl->n;
-    for (uint32_t w = 0; w < nw; w++)
-        scan_window(W, lo, len, dir, wl->s[w], wl->e[w], peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, L);
 }
 
 // Aligner.locate's return value (R7) from the running best
@@ -672,15 +789,6 @@ struct ColRing {
     int16_t dm[RING];
 };
 
-ORC_HD int popc64(uint64_t x)
-{
-#if defined(__CUDA_ARCH__)
-    return __popcll(x);
-#else
-    return __builtin_popcountll(x);
-#endif
-}
-
 // The ring is indexed by the column's distance from the scan start ws: the lanes of a warp
 // scan in lockstep, so they touch the same slot at the same time and the lane-interleaved
 // local memory sees one coalesced access per column instead of 32 scattered ones.
@@ -692,33 +800,6 @@ ORC_HD int ring_cost(const ColRing &R, int m, int i, int j, int ws)
     if (sh >= 64) return R.dm[x];
     const uint64_t pv = R.pv[x] >> sh, mv = R.mv[x] >> sh;
     return (int)R.dm[x] - popc64(pv) + popc64(mv);
-}
-
-ORC_HD int clz64(uint64_t x)
-{
-#if defined(__CUDA_ARCH__)
-    return __clzll((long long)x);
-#else
-    return x ? __builtin_clzll(x) : 64;
-#endif
-}
-
-ORC_HD int ctz64(uint64_t x)
-{
-#if defined(__CUDA_ARCH__)
-    return x ? __ffsll((long long)x) - 1 : 64;
-#else
-    return x ? __builtin_ctzll(x) : 64;
-#endif
-}
-
-// 16 consecutive 4-bit codes starting at code index idx of a word array (idx may be unaligned)
-ORC_HD uint64_t nib16(const uint32_t *A, int64_t idx)
-{
-    const int64_t w = idx >> 3;
-    const uint32_t sh = (uint32_t)(idx & 7) * 4u;
-    const uint32_t a = A[w], b = A[w + 1], c = A[w + 2];
-    return (uint64_t)funnel_r(a, b, sh) | ((uint64_t)funnel_r(b, c, sh) << 32);
 }
 
 // Walk cutadapt's path back from cell (i, j) whose cost is d.  ws is the first stored

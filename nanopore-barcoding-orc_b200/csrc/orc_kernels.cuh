@@ -215,7 +215,7 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                 dst[0] = src[0]; dst[1] = src[1];
             }
             scan_lane(W, v.lo, v.len, dir, &wl, peq_base, tl, T.pv0[tl], T.d0[tl], m, T.k[a], T.kmax[a],
-                      T.min_ov[a], type, L);
+                      T.min_ov[a], type, L, T.indels, T.code4[a], T.rcode4[a]);
             has = L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2;
             need = has && L.need != 0;
         }

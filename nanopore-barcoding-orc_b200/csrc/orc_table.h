@@ -35,11 +35,11 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         return "unsupported: between 1 and " + std::to_string(MAX_AD) + " adapters per round";
     if (type != TYPE_FRONT && type != TYPE_BACK)
         return "unsupported: only regular 5' (-g) and 3' (-a) adapters take the edit-distance path";
-    if (!indels) return "unsupported: --no-indels on unanchored adapters";
     if (min_overlap < 1) return "min_overlap must be >= 1";
     T.n_adapters = n_adapters;
     T.type = type;
     T.revcomp = revcomp ? 1 : 0;
+    T.indels = indels ? 1 : 0;
     T.min_overlap = min_overlap;
     T.n_lanes = 2 * n_adapters;
     for (int a = 0; a < n_adapters; a++) {

@@ -7,8 +7,8 @@ shapes of /root/reference/scripts/02_cutadapt_loop.sh):
                                 -o DIR/SP27/{name}_SP5id_DS.fastq.gz DIR/SP5/SP5id_DS.fastq.gz --json=REPORT
 
 Kept surface: -g/-a (file:PATH, SEQ, name=SEQ; several allowed), -e, -O, --action=trim, --rc,
--j (accepted), --json, anchored ^file: / file$: adapters together with --no-indels (the Hamming
-fast path; --no-indels on unanchored adapters and anchored adapters with indels are refused),
+-j (accepted), --json, --no-indels (regular adapters: Hamming distance along diagonals; anchored
+^file: / file$: adapters: the indexed Hamming fast path; anchored adapters WITH indels are refused),
 -o with {name} (one file per adapter name plus "unknown", all created even if empty).
 Anything else exits with status 2 and an "unsupported" message: there is no CPU fallback.
 
@@ -161,8 +161,6 @@ def run_single_round(opt, argv, device=0) -> int:
     names, seqs, anchored = _parse_adapter_specs(opt["g"] or opt["a"], kind)
     if anchored and opt["indels"]:
         raise Unsupported("anchored adapters need --no-indels (the indel variant is not built)")
-    if not anchored and not opt["indels"]:
-        raise Unsupported("--no-indels for unanchored adapters")
     if anchored:
         kind = ORC_PREFIX if kind == ORC_FRONT else ORC_SUFFIX
     rnd = E.Round(names, seqs, kind, opt["e"], opt["O"], opt["indels"], opt["rc"])

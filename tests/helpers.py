@@ -46,7 +46,7 @@ def _cstrs(seqs):
     return arr
 
 
-def run_hostsim(rounds, rs, filter_mode=1, want_columns=False):
+def run_hostsim(rounds, rs, filter_mode=1, want_columns=False, indels=1):
     """rounds: [(sequences, type, e, O, rc)].  Returns (m0, m1, lo, len, rc, n_tasks)."""
     n = rs.n_reads
     m0 = np.zeros(n, dtype=MATCH_DTYPE)
@@ -69,7 +69,7 @@ def run_hostsim(rounds, rs, filter_mode=1, want_columns=False):
         C.c_uint32(n), C.c_uint64(seq.shape[0]),
         C.c_void_p(m0.ctypes.data), C.c_void_p(m1.ctypes.data), C.c_void_p(lo.ctypes.data),
         C.c_void_p(ln.ctypes.data), C.c_void_p(rc.ctypes.data), C.c_void_p(nt.ctypes.data), err, C.c_int(256),
-        C.c_int(filter_mode), C.c_void_p(ncol.ctypes.data))
+        C.c_int(filter_mode), C.c_void_p(ncol.ctypes.data), C.c_int(indels))
     if ret != 0:
         raise RuntimeError(err.value.decode())
     if want_columns:
@@ -77,8 +77,8 @@ def run_hostsim(rounds, rs, filter_mode=1, want_columns=False):
     return m0, m1, lo, ln, rc, nt
 
 
-def run_oracle(rounds, rs, n_threads=8):
-    sets = [(oracle.AdapterSet(r[0], r[1], r[2], r[3]), r[4]) for r in rounds]
+def run_oracle(rounds, rs, n_threads=8, indels=True):
+    sets = [(oracle.AdapterSet(r[0], r[1], r[2], r[3], indels=indels), r[4]) for r in rounds]
     return oracle.demux_batch(sets, rs.seq, rs.qual, rs.offsets, rs.lengths, n_threads=n_threads)
 
 

@@ -22,16 +22,17 @@ extern "C" int hostsim_demux(int n_rounds,
                              const uint8_t *seq, const uint64_t *offsets, const uint32_t *lengths,
                              uint32_t n_reads, uint64_t n_bytes,
                              Match *m0, Match *m1, uint64_t *out_lo, uint32_t *out_len, uint32_t *out_rc,
-                             uint64_t *n_tasks, char *err, int err_len, int filter_mode, uint64_t *n_columns)
+                             uint64_t *n_tasks, char *err, int err_len, int filter_mode, uint64_t *n_columns,
+                             int indels)
 {
     RoundTable *T = new RoundTable[2];
     AnchoredTable *AT = new AnchoredTable[2];
     bool anch[2] = {type0 >= 2, n_rounds > 1 && type1 >= 2};
     std::string e = anch[0] ? build_anchored_table(AT[0], T[0], n_ad0, type0 == 3, seq0, e0, 0, rc0)
-                            : build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, 1, rc0, filter_mode);
+                            : build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, indels, rc0, filter_mode);
     if (e.empty() && n_rounds > 1)
         e = anch[1] ? build_anchored_table(AT[1], T[1], n_ad1, type1 == 3, seq1, e1, 0, rc1)
-                    : build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, 1, rc1, filter_mode);
+                    : build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, indels, rc1, filter_mode);
     uint8_t comp_lut[256];
     build_complement_lut(comp_lut);
     if (!e.empty()) {
@@ -91,7 +92,8 @@ extern "C" int hostsim_demux(int n_rounds,
                 if (o == 1 && !R.revcomp) continue;
                 LaneScan L;
                 scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, (const char *)&R.peq[0][0], lane,
-                          R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, L);
+                          R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, L,
+                          R.indels, R.code4[a], R.rcode4[a]);
                 if (L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2) {
                     PairResult pr; memset(&pr, 0, sizeof(pr));
                     if (!L.need) {

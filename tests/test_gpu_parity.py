@@ -252,3 +252,18 @@ def test_long_reads_and_capacity_errors():
             eng.run(rs)
     finally:
         eng.close()
+
+
+def test_no_indels_unanchored_gpu():
+    rs = synth.generate(20000, 300, 900, seed=21)
+    rounds = E.m13_rounds()
+    for r in rounds:
+        r.indels = False
+    with E.Engine(rounds, max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]), n_slots=1) as eng:
+        res = eng.run(rs)
+        t = eng.timings(0)
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(H.m13_rounds(), rs, indels=False)
+    assert H.diff_matches(rec0, res.matches[0])[1] == 0
+    assert H.diff_matches(rec1, res.matches[1])[1] == 0
+    assert np.array_equal(res.out_len, olen)
+    assert t["n_tasks"] == [0, 0]

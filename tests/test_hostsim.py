@@ -124,6 +124,20 @@ def test_random_adapter_sets():
         _compare(rounds, _adversarial_reads(rnd, f, b, 400), threads=4)
 
 
+def test_no_indels_unanchored():
+    """--no-indels on regular adapters: Hamming distance along diagonals, settled in the scan."""
+    rnd = random.Random(17)
+    f = [s for _, s in m13.sp5_forward()]
+    b = [s for _, s in m13.sp27_reverse_rc()]
+    for rs in (synth.generate(2500, 300, 600, seed=9), _adversarial_reads(rnd, f, b, 2500)):
+        rounds = H.m13_rounds()
+        rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, indels=False)
+        for fm in (0, 1):
+            m0, m1, lo, ln, rc, nt = H.run_hostsim(rounds, rs, fm, indels=0)
+            assert H.diff_matches(rec0, m0)[1] == 0 and H.diff_matches(rec1, m1)[1] == 0
+            assert np.array_equal(olen, ln) and int(nt.sum()) == 0
+
+
 def test_single_round_back_only():
     rnd = random.Random(5)
     b = [s for _, s in m13.sp27_reverse_rc()]

@@ -34,15 +34,17 @@ for trial in range(trials):
             s=s[:p]+a[x:y]+s[p:]
         recs.append(("s%d"%i, s, "I"*len(s)))
     rs=synth.from_records(recs)
-    rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=8)
+    rec0, rec1, oseq, oqual, olen = None, None, None, None, None
     fmode = rnd.choice([0, 1, 2, 2, 2])
-    m0, m1, lo, ln, rcv, nt = H.run_hostsim(rounds, rs, fmode)
+    indels = rnd.choice([1, 1, 1, 0])
+    m0, m1, lo, ln, rcv, nt = H.run_hostsim(rounds, rs, fmode, indels=indels)
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=8, indels=bool(indels))
     total+=rs.n_reads
     for name, a, bb in (("r1", rec0, m0), ("r2", rec1, m1)):
         if a is None: continue
         idx, nbad = H.diff_matches(a, bb)
         if nbad:
-            i=int(idx[0]); print("MISMATCH seed",seed,"trial", trial, name, "fmode", fmode, "e", e, "ov", ov, "rc", rc, "read", i, "nbad", nbad)
+            i=int(idx[0]); print("MISMATCH seed",seed,"trial", trial, name, "fmode", fmode, "indels", indels, "e", e, "ov", ov, "rc", rc, "read", i, "nbad", nbad)
             print(" oracle", a[i]); print(" hostsim", bb[i]); print(" seq", rs.read(i)[1]); print(rounds)
             sys.exit(1)
     assert np.array_equal(olen, ln)
