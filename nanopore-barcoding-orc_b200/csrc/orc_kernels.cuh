@@ -111,10 +111,14 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
         s_par[4] = tab->revcomp; s_par[5] = tab->use_filter; s_par[6] = tab->lcs; s_par[7] = tab->min_ov_min;
     }
     __syncthreads();
+    // threads 0..n-1 take direction 0 of the reads (in length order), threads n..2n-1 direction 1:
+    // the lanes of a warp then all look at the same strand, so the ones that meet the adapter (and
+    // leave the fast path to replay a chunk) do so together
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = p < 2u * n_reads;
-    const uint32_t r = valid ? (order ? order[p >> 1] : (p >> 1)) : 0u;
-    const int dir = (int)(p & 1u);
+    const int dir = (valid && p >= n_reads) ? 1 : 0;
+    const uint32_t pr = dir ? p - n_reads : p;
+    const uint32_t r = valid ? (order ? order[pr] : pr) : 0u;
     const int Lp = s_par[0], kt = s_par[1], m_max = s_par[2], type = s_par[3];
     WinList wl;
     wl.n = 0; wl.pad_ = 0;
@@ -126,7 +130,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
         if (s_par[4] || ((dir ^ (int)(v.rc & 1u)) == 0)) {
             if (s_par[5]) {
                 trigger_lane(W, v.lo, v.len, dir, reinterpret_cast<const char *>(&s_peq32[0][0]),
-                             (int)(threadIdx.x & 63u), Lp, kt, type, (uint32_t)(m_max - Lp + kt),
+                             (int)(2u * (threadIdx.x & 31u)) + dir, Lp, kt, type, (uint32_t)(m_max - Lp + kt),
                              (uint32_t)(Lp + kt + 1), wl,
                              s_par[6] > 0 ? reinterpret_cast<const char *>(&s_peq32s[0][0]) : nullptr,
                              s_par[6], s_kmax_any, s_par[7], m_max, s_mmin);
