@@ -158,6 +158,18 @@ def cpu_arm(rs, n_sample, threads, steps, warmup):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: everything else (NCCL's version banner, library
+    # chatter) goes to stderr until the line is printed
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,7 +205,7 @@ def main():
                              "sample": "first %d reads of the workload, %d timed passes" % (sub_n, args.steps)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -202,10 +214,9 @@ def main():
     from orcdemux import engine as E
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: bench.py has no CPU fallback for the product arm"}))
+        emit({"error": "no CUDA device: bench.py has no CPU fallback for the product arm"})
         return 2
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -410,7 +421,7 @@ def main():
             "reads_binned_all_ranks": total_reads_binned, "gen_s": gen_s,
         }
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

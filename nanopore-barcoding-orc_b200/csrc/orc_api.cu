@@ -256,6 +256,7 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel, SCAN_THREADS, 0));
     ctx->scan_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_kernel, 128, 0));
+    if (occ > 6) occ = 6;       // more resident threads only thrash the per-thread ring (measured)
     ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     {
         uint32_t *nk = nullptr;

@@ -70,6 +70,7 @@ struct RoundTable {
     int32_t k_max, m_max;           // largest k and m of the round
     int32_t m_min;                  // shortest adapter
     int32_t indels;                 // 0: --no-indels (only diagonal moves; Hamming distance along diagonals)
+    int32_t sfx_primary;            // 3' round: stage 1 scans the shared suffix, not the shared prefix
     uint32_t peq32[16][64];         // [read code][lane]: match bits of the prefix, row Lp at bit 31;
                                     // even lanes: direction 0, odd lanes: direction 1 (complemented)
     // what decides whether the mandatory first (5') / last (3') window is needed at all
@@ -297,6 +298,7 @@ ORC_HD void win_add(WinList &L, bool &open, uint32_t &cs, uint32_t &ce, uint32_t
     if (!open) { cs = s; ce = e; open = true; return; }
     if (s <= ce + 1u || L.n >= (uint32_t)(MAX_WIN - 1)) {   // overlapping, or out of slots: merge
         if (e > ce) ce = e;
+        if (s < cs) cs = s;
         return;
     }
     L.s[L.n] = cs; L.e[L.n] = ce; L.n++;
@@ -312,14 +314,25 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                          const char *peq32_base, int lane, int Lp, int kt, int type,
                          uint32_t ext, uint32_t back, WinList &out,
                          const char *suffix_base = nullptr, int Ls = 0,
-                         const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0, int m_min = 0)
+                         const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0, int m_min = 0,
+                         int sfx_primary = 0)
 {
     const uint32_t n = len;
     out.n = 0; out.pad_ = 0;
     for (int i = 0; i < MAX_WIN; i++) { out.s[i] = 0; out.e[i] = 0; }
     bool open = false;
     uint32_t cs = 0, ce = 0;
-    const uint32_t pad = (Lp == 32) ? 0u : ((1u << (32 - Lp)) - 1u);
+    // 3' rounds whose adapters share a suffix S longer than their shared prefix scan S instead
+    // (sfx_primary): a full-length alignment ends with S fully aligned at <= k errors, so the
+    // columns where S's last row is <= k mark where alignments END; the window then reaches
+    // m_max + k + 1 columns back.  For the M13 tables that is the 23-nt SP27 flank, which random
+    // sequence almost never approaches, against 0.2 % of the columns for the 17-nt prefix.
+    // Partial adapters at the read end (no S in them) are found by a prefix scan of the last
+    // m_max + 2k + 1 columns only.
+    const bool sp = sfx_primary != 0 && type == TYPE_BACK && suffix_base != nullptr;
+    const char *main_base = sp ? suffix_base : peq32_base;
+    const int Lmain = sp ? Ls : Lp;
+    const uint32_t pad = (Lmain == 32) ? 0u : ((1u << (32 - Lmain)) - 1u);
     uint32_t Pv, Mv = 0;
     int D;
     const uint32_t lane4 = (uint32_t)lane * 4u;
@@ -328,7 +341,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
     // The prefix scan itself never uses column 0 for free (column costs i, also for 5' adapters):
     // it only has to find alignments that start in row 0, which cost the same in either matrix.
-    Pv = ~pad; D = Lp;
+    Pv = ~pad; D = Lmain;
     if (type == TYPE_FRONT) {
         // Alignments of a 5' adapter that start in column 0 (origin < 0: the read begins inside
         // the adapter) end within the first m + k columns and end with (a suffix of) the suffix S
@@ -386,7 +399,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     // (partial adapters at the 3' end do not contain S).
     // The confirming scans run after the main loop, cluster by cluster, so that the lanes of a warp
     // (32 different reads) do them at the same time; during the main loop clusters are only noted.
-    const bool confirm = type == TYPE_BACK && suffix_base != nullptr && Ls > 0;
+    const bool confirm = !sp && type == TYPE_BACK && suffix_base != nullptr && Ls > 0;
     constexpr int MAX_CLU = 12;
     uint32_t clu_fs[MAX_CLU], clu_ls[MAX_CLU];
     int n_clu = 0;
@@ -433,7 +446,10 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     };
     auto flush_cluster = [&]() {
         if (clu_f == 0) return;
-        if (!confirm) add_cluster(clu_f, clu_l, false);
+        if (sp) {                       // triggers are END columns: the window reaches back m_max + k + 1
+            const uint32_t rb = (uint32_t)(m_max + kt + 1);
+            win_add(out, open, cs, ce, clu_f > rb ? clu_f - rb : 0u, clu_l);
+        } else if (!confirm) add_cluster(clu_f, clu_l, false);
         else if (noted_all && n_clu < MAX_CLU) { clu_fs[n_clu] = clu_f; clu_ls[n_clu] = clu_l; n_clu++; }
         else {
             // out of slots: from here on clusters open their windows unconfirmed; the noted ones are
@@ -456,7 +472,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         auto column = [&](int t) {
             const uint32_t src = (t & 1) ? B : A;
             const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
-            const uint32_t Eq = *reinterpret_cast<const uint32_t *>(peq32_base + byte_perm(src, lane4, sel));
+            const uint32_t Eq = *reinterpret_cast<const uint32_t *>(main_base + byte_perm(src, lane4, sel));
             const uint32_t Xv = Eq | Mv;
             const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
             uint32_t Ph = Mv | ~(Xh | Pv);
@@ -500,16 +516,57 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     flush_cluster();
     for (int c = 0; c < n_clu; c++) add_cluster(clu_fs[c], clu_ls[c], true);
     if (type == TYPE_BACK) {
+        uint32_t ePv = Pv, eMv = Mv;    // prefix rows 1..Lp of the last column
+        if (sp) {
+            // prefix scan of the last m_max + 2k + 1 columns (restart: exact for every alignment
+            // that can still reach the read end as a partial adapter)
+            const uint32_t T = (uint32_t)(m_max + 2 * kt + 1);
+            const uint32_t s1 = n > T ? n - T : 0u;
+            const uint32_t jmin = n > (uint32_t)(m_max - Lp + kt) ? n - (uint32_t)(m_max - Lp + kt) : 0u;
+            const uint32_t ppad = (Lp == 32) ? 0u : ((1u << (32 - Lp)) - 1u);
+            ePv = ~ppad; eMv = 0;
+            int eD = Lp;
+            uint32_t first_trig = 0;
+            ChunkReader re;
+            re.init(W, lo, len, dir, s1);
+            for (uint32_t c0 = s1; c0 < n; c0 += 8) {
+                uint32_t A, B;
+                re.next(A, B);
+                const int ncol = imin(8, (int)(n - c0));
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (t < ncol) {
+                        const uint32_t src = (t & 1) ? B : A;
+                        const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+                        const uint32_t Eq = *reinterpret_cast<const uint32_t *>(peq32_base + byte_perm(src, lane4, sel));
+                        const uint32_t Xv = Eq | eMv;
+                        const uint32_t Xh = (((Eq & ePv) + ePv) ^ ePv) | Eq;
+                        uint32_t Ph = eMv | ~(Xh | ePv);
+                        uint32_t Mh = ePv & Xh;
+                        eD += (int)(Ph >> 31) - (int)(Mh >> 31);
+                        Ph <<= 1; Mh <<= 1;
+                        ePv = Mh | ~(Xv | Ph);
+                        eMv = Ph & Xv;
+                        const uint32_t j = c0 + (uint32_t)t + 1u;
+                        if (eD <= kt && j >= jmin && first_trig == 0) first_trig = j;
+                    }
+                }
+            }
+            if (first_trig != 0) {
+                const uint32_t rb = (uint32_t)(Lp + kt + 1);
+                win_add(out, open, cs, ce, first_trig > rb ? first_trig - rb : 0u, n);
+            }
+        }
         // The last window is for the cells (i, n) with i <= Lp: an adapter prefix of at most Lp
-        // characters at the read end.  Those rows are the same for every adapter and this scan
-        // (true column 0) has them exactly: if none of them passes R6's necessary condition under
-        // the loosest limits of the round, no adapter has such a candidate and the window is moot.
+        // characters at the read end.  Those rows are the same for every adapter and the prefix
+        // scan has them exactly: if none of them passes R6's necessary condition under the
+        // loosest limits of the round, no adapter has such a candidate and the window is moot.
         bool need = kmax_any == nullptr;
         if (!need) {
             int cum = 0;
             for (int i = 1; i <= Lp; i++) {
                 const int bit = 32 - Lp + i - 1;
-                cum += (int)((Pv >> bit) & 1u) - (int)((Mv >> bit) & 1u);
+                cum += (int)((ePv >> bit) & 1u) - (int)((eMv >> bit) & 1u);
                 if (i >= min_ov_min && cum <= (int)kmax_any[i]) need = true;
             }
         }

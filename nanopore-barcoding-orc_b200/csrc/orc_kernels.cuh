@@ -99,8 +99,8 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     __shared__ __align__(16) uint32_t s_peq32s[16][64];
     __shared__ uint8_t s_kmax_any[MAX_M + 8];
     __shared__ int s_par[8];
-    __shared__ int s_mmin;
-    if (threadIdx.x == 0) s_mmin = tab->m_min;
+    __shared__ int s_mmin, s_sfxp;
+    if (threadIdx.x == 0) { s_mmin = tab->m_min; s_sfxp = tab->sfx_primary; }
     for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
         (&s_peq32[0][0])[i] = (&tab->peq32[0][0])[i];
         (&s_peq32s[0][0])[i] = (&tab->peq32s[0][0])[i];
@@ -133,7 +133,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                              (int)(2u * (threadIdx.x & 31u)) + dir, Lp, kt, type, (uint32_t)(m_max - Lp + kt),
                              (uint32_t)(Lp + kt + 1), wl,
                              s_par[6] > 0 ? reinterpret_cast<const char *>(&s_peq32s[0][0]) : nullptr,
-                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin);
+                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp);
                 cols = win_columns(wl);
             } else {
                 wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything

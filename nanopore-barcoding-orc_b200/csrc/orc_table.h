@@ -107,6 +107,15 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
     for (int a = 1; a < n_adapters; a++) if (T.m[a] < T.m_min) T.m_min = T.m[a];
     const bool valid = lcp > k_max && lcp >= 1;
     T.use_filter = (filter_mode == 2) ? valid : (filter_mode == 1 ? (valid && lcp >= 12 && lcp > 2 * k_max) : 0);
+    int lcs_ = T.m[0];
+    for (int a = 1; a < n_adapters; a++) {
+        int l = 0;
+        while (l < lcs_ && l < T.m[a] && T.code[a][T.m[a] - 1 - l] == T.code[0][T.m[0] - 1 - l]) l++;
+        lcs_ = l;
+    }
+    if (lcs_ > 32) lcs_ = 32;
+    // a 3' round scans its shared suffix instead when that is the longer (more selective) flank
+    T.sfx_primary = (T.use_filter && type == TYPE_BACK && lcs_ > lcp && lcs_ > k_max) ? 1 : 0;
     // shared suffix and the loosest acceptance limits (decide the mandatory windows in stage 1)
     int lcs = T.m[0];
     for (int a = 1; a < n_adapters; a++) {

@@ -82,7 +82,7 @@ extern "C" int hostsim_demux(int n_rounds,
                     trigger_lane(W, v.lo, v.len, dir, (const char *)&R.peq32[0][0], dir, R.lcp, R.k_max, R.type,
                                  (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + R.k_max + 1), wl[dir],
                                  R.lcs > 0 ? (const char *)&R.peq32s[0][0] : nullptr, R.lcs,
-                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min);
+                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary);
                     n_columns[rd] += win_columns(wl[dir]);
                 }
             } else n_columns[rd] += 2ull * v.len;

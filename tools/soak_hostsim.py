@@ -14,7 +14,9 @@ for trial in range(trials):
     pshare = rnd.choice([0.5, 1.0, 1.0])
     sfx = mk()[:rnd.choice([0, 3, 8, 17, 30])]
     f = [(((shared if rnd.random() < pshare else "") + mk())[:64 - len(sfx)] + (sfx if rnd.random() < pshare else "")) for _ in range(nf)]
-    b = [((shared if rnd.random() < pshare else "") + mk() + (shared if rnd.random() < 0.5 else ""))[:64] for _ in range(nb)]
+    sfx_b = mk()[:rnd.choice([0, 6, 13, 23, 30])]
+    psfx = rnd.choice([0.5, 1.0, 1.0])
+    b = [(((shared if rnd.random() < pshare else "") + mk())[:64 - len(sfx_b)] + (sfx_b if rnd.random() < psfx else "")) for _ in range(nb)]
     if rnd.random()<0.3:  # low complexity adapters
         f=[ (x[:4]*16)[:len(x)] for x in f]; b=[(x[:3]*22)[:len(x)] for x in b]
     e = rnd.choice([0.0, 0.05, 0.1, 0.1, 0.2, 0.3, 0.4, 0.6, 0.9, 2])
