@@ -130,3 +130,58 @@ def test_raw_text_layout_equals_blob_layout(tmp_path):
     assert np.array_equal(a.bin, b.bin)
     for x, y in zip(a.matches, b.matches):
         assert H.diff_matches(x, y)[1] == 0
+
+
+def test_cli_anchored_and_no_indels(tmp_path):
+    """config 4 call shape (-g ^file: --no-indels) and --no-indels on regular adapters via the shim."""
+    import oracle
+    shim = os.path.join(H.PKG, "bin", "cutadapt")
+    fwd, rev, var = m13.write_tables(str(tmp_path / "adapters"))
+    # anchored Hamming path
+    rs = synth.generate(4000, 300, 600, seed=1004, anchored=True)
+    infile = tmp_path / "a.fastq"
+    infile.write_bytes(rs.to_fastq_bytes())
+    out = tmp_path / "anch"
+    out.mkdir()
+    r = subprocess.run([shim, "--action=trim", "-e", "0.1", "--no-indels", "--rc", "-g", "^file:" + var,
+                        "-o", str(out / "{name}.fastq"), str(infile), "--json=" + str(out / "r.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    names = [n for n, _ in m13.variable_all()]
+    seqs = [q for _, q in m13.variable_all()]
+    sets = [(oracle.AdapterSet(seqs, oracle.PREFIX, 0.1, 3, indels=False), 1)]
+    rec0, _, oseq, oqual, olen = oracle.demux_batch(sets, rs.seq, rs.qual, rs.offsets, rs.lengths, n_threads=4)
+    exp = {n: [] for n in names + ["unknown"]}
+    for i in range(rs.n_reads):
+        a = int(rec0["adapter"][i])
+        nm = rs.read(i)[0] + (" rc" if rec0["is_rc"][i] else "")
+        o, L = int(rs.offsets[i]), int(olen[i])
+        exp[names[a] if a >= 0 else "unknown"].append(
+            b"@" + nm.encode() + b"\n" + oseq[o:o + L].tobytes() + b"\n+\n" + oqual[o:o + L].tobytes() + b"\n")
+    assert sorted(os.listdir(out)) == sorted([n + ".fastq" for n in exp] + ["r.json"])
+    for n, recs in exp.items():
+        assert (out / (n + ".fastq")).read_bytes() == b"".join(recs), n
+    # anchored adapters with indels are refused, loudly
+    r = subprocess.run([shim, "-g", "^file:" + var, "-o", str(out / "{name}.fq"), str(infile)],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "unsupported" in r.stderr
+    # --no-indels on the regular 5' adapters
+    rs2 = synth.generate(3000, 300, 600, seed=8)
+    in2 = tmp_path / "b.fastq.gz"
+    with gzip.open(in2, "wb", compresslevel=1) as fh:
+        fh.write(rs2.to_fastq_bytes())
+    out2 = tmp_path / "noindel"
+    out2.mkdir()
+    r = subprocess.run([shim, "--action=trim", "-e", "0.1", "--no-indels", "--rc", "-g", "file:" + fwd,
+                        "-o", str(out2 / "{name}.fastq.gz"), str(in2)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n5 = [n for n, _ in m13.sp5_forward()]
+    s5 = [q for _, q in m13.sp5_forward()]
+    sets = [(oracle.AdapterSet(s5, oracle.FRONT, 0.1, 3, indels=False), 1)]
+    rec0, _, oseq, oqual, olen = oracle.demux_batch(sets, rs2.seq, rs2.qual, rs2.offsets, rs2.lengths, n_threads=4)
+    for a, nm in enumerate(n5):
+        exp = b"".join(b"@" + (rs2.read(int(i))[0] + (" rc" if rec0["is_rc"][i] else "")).encode() + b"\n" +
+                       oseq[int(rs2.offsets[i]):int(rs2.offsets[i]) + int(olen[i])].tobytes() + b"\n+\n" +
+                       oqual[int(rs2.offsets[i]):int(rs2.offsets[i]) + int(olen[i])].tobytes() + b"\n"
+                       for i in np.flatnonzero(rec0["adapter"] == a))
+        assert _read_gz(out2 / (nm + ".fastq.gz")) == exp, nm
