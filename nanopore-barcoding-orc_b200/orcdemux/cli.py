@@ -156,6 +156,68 @@ def _report(n_in, bp_in, bp_out, n_with, n_rc, names, per_adapter, elapsed, argv
     }
 
 
+class EndStats:
+    """Per-adapter statistics of cutadapt's report (report.py / adapters.py EndStatistics as far as
+    they derive from the match records): histogram of removed lengths split by error count, the
+    expected number of random matches per length (gc_content 0.5), matches found on the reverse
+    complement, and for 3' adapters the base preceding the match."""
+
+    def __init__(self, names, seqs, kind, max_error_rate, indels, revcomp):
+        self.names, self.seqs, self.kind = names, seqs, kind
+        self.rate, self.indels, self.revcomp = max_error_rate, indels, revcomp
+        self.front = kind in (ORC_FRONT, ORC_PREFIX)
+        self.hist = [dict() for _ in names]            # removed length -> {errors: count}
+        self.on_rc = np.zeros(len(names), dtype=np.int64)
+        self.adjacent = [dict() for _ in names]
+
+    def add(self, m, in_len, tb=None):
+        """m: orc_match records of the round; in_len: read lengths before the round."""
+        has = m["adapter"] >= 0
+        if not has.any():
+            return
+        a = m["adapter"][has].astype(np.int64)
+        err = m["errors"][has].astype(np.int64)
+        L = in_len[has].astype(np.int64)
+        removed = m["query_stop"][has].astype(np.int64) if self.front else L - m["query_start"][has]
+        self.on_rc += np.bincount(a[m["is_rc"][has] != 0], minlength=len(self.names))
+        key = (a << 40) | (removed << 8) | err
+        ks, cs = np.unique(key, return_counts=True)
+        for k, c in zip(ks.tolist(), cs.tolist()):
+            h = self.hist[k >> 40].setdefault((k >> 8) & 0xFFFFFFFF, {})
+            h[k & 0xFF] = h.get(k & 0xFF, 0) + c
+
+    def _end(self, i, n_reads):
+        seq = self.seqs[i]
+        walk = seq[::-1] if self.front else seq
+        p, probs = 1.0, [1.0]
+        for c in walk:
+            p *= 0.25                                  # gc_content 0.5: every base 0.25
+            probs.append(p)
+        kmax = int(len(seq) * self.rate)
+        lengths = []
+        for ln in sorted(self.hist[i]):
+            h = self.hist[i][ln]
+            lengths.append({"len": ln, "expect": n_reads * probs[min(len(seq), ln)],
+                            "counts": [h.get(e, 0) for e in range(max(kmax, max(h)) + 1)]})
+        typ = {ORC_FRONT: "regular_five_prime", ORC_BACK: "regular_three_prime",
+               ORC_PREFIX: "anchored_five_prime", ORC_SUFFIX: "anchored_three_prime"}[self.kind]
+        return {"type": typ, "sequence": seq, "error_rate": self.rate, "indels": bool(self.indels),
+                "error_lengths": [int(e / self.rate) - 1 if e else 0 for e in range(kmax + 1)][1:] + [len(seq)]
+                if self.rate > 0 else [len(seq)],
+                "matches": int(sum(sum(h.values()) for h in self.hist[i].values())),
+                "adjacent_bases": None, "dominant_adjacent_base": None, "trimmed_lengths": lengths}
+
+    def as_json(self, n_reads):
+        out = []
+        for i, nm in enumerate(self.names):
+            end = self._end(i, n_reads)
+            out.append({"name": nm, "total_matches": end["matches"],
+                        "on_reverse_complement": int(self.on_rc[i]) if self.revcomp else None, "linked": False,
+                        "five_prime_end": end if self.front else None,
+                        "three_prime_end": None if self.front else end})
+        return out
+
+
 def run_single_round(opt, argv, device=0) -> int:
     kind = ORC_FRONT if opt["g"] else ORC_BACK
     names, seqs, anchored = _parse_adapter_specs(opt["g"] or opt["a"], kind)
@@ -171,6 +233,7 @@ def run_single_round(opt, argv, device=0) -> int:
     writers = F.BinWriters(paths, opt["level"], threads=max(2, min(16, opt["cores"])))
     n_in = bp_in = bp_out = n_with = n_rc = 0
     per = np.zeros(len(names), dtype=np.int64)
+    stats = EndStats(names, seqs, kind, opt["e"], opt["indels"], opt["rc"])
     try:
         with E.Engine([rnd], device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
                       emit_fastq=True, want_matches=True) as eng:
@@ -185,6 +248,7 @@ def run_single_round(opt, argv, device=0) -> int:
                 n_with += int(has.sum())
                 n_rc += int((m["is_rc"] != 0).sum())
                 per += np.bincount(m["adapter"][has], minlength=len(names))
+                stats.add(m, tb.lengths[:res.n_reads])
                 writers.write_batch(res)
             inflight = []
             k = 0
@@ -200,6 +264,7 @@ def run_single_round(opt, argv, device=0) -> int:
         writers.close()
     rep = _report(n_in, bp_in, bp_out, n_with, n_rc, names, per, time.time() - t0, argv)
     rep["input"]["path1"] = opt["inputs"][0]
+    rep["adapters_read1"] = stats.as_json(n_in)
     if opt["json"]:
         with open(opt["json"], "w") as fh:
             json.dump(rep, fh, indent=2)

@@ -161,6 +161,21 @@ def test_cli_anchored_and_no_indels(tmp_path):
     assert sorted(os.listdir(out)) == sorted([n + ".fastq" for n in exp] + ["r.json"])
     for n, recs in exp.items():
         assert (out / (n + ".fastq")).read_bytes() == b"".join(recs), n
+    rep = json.load(open(out / "r.json"))
+    assert rep["read_counts"]["input"] == rs.n_reads
+    assert rep["read_counts"]["read1_with_adapter"] == int((rec0["adapter"] >= 0).sum())
+    assert rep["read_counts"]["reverse_complemented"] == int((rec0["is_rc"] != 0).sum())
+    for a, ad in enumerate(rep["adapters_read1"]):
+        sel = rec0["adapter"] == a
+        assert ad["name"] == names[a] and ad["total_matches"] == int(sel.sum())
+        assert ad["on_reverse_complement"] == int((rec0["is_rc"][sel] != 0).sum())
+        end = ad["five_prime_end"]
+        assert end["type"] == "anchored_five_prime" and end["sequence"] == seqs[a] and ad["three_prime_end"] is None
+        hist = {}
+        for q, e in zip(rec0["query_stop"][sel].tolist(), rec0["errors"][sel].tolist()):
+            hist.setdefault(q, {}).setdefault(e, 0)
+            hist[q][e] += 1
+        assert {t["len"]: {e: c for e, c in enumerate(t["counts"]) if c} for t in end["trimmed_lengths"]} == hist
     # anchored adapters with indels are refused, loudly
     r = subprocess.run([shim, "-g", "^file:" + var, "-o", str(out / "{name}.fq"), str(infile)],
                        capture_output=True, text=True)
