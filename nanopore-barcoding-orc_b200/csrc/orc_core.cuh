@@ -177,6 +177,18 @@ ORC_HD int ctz64(uint64_t x)
 #endif
 }
 
+ORC_HD uint64_t brev64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    return __builtin_bswap64(x);
+#endif
+}
+
 // 16 consecutive 4-bit codes starting at code index idx of a word array (idx may be unaligned)
 ORC_HD uint64_t nib16(const uint32_t *A, int64_t idx)
 {
@@ -879,32 +891,23 @@ ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, co
             break;
         }
         if (j <= ws) { origin = j; break; }          // unreachable for a genuine candidate
-        // matches along the diagonal from (i, j) up-left, at most min(16, i, j - ws) of them
+        // matches along the diagonal from (i, j) up-left, at most min(16, i, j - ws) of them.
+        // Forward lane: read codes j-16..j-1 of the view = storage lo+j-16.., adapter codes
+        // i-16..i-1 (16 pad nibbles in front of code4), cell (i, j) in the top nibble.  Reverse
+        // lane: view position p = storage lo+len-1-p, complemented, so positions j-1, j-2, ... are
+        // storage lo+len-j, +1, ... compared raw with the reverse-complemented adapter; cell
+        // (i, j) is in the bottom nibble, brought to the top by a bit reversal.  Both kinds of
+        // lane run the same instructions.
         const int avail = imin(16, imin(i, j - ws));
-        int run;
-        if (!dir) {
-            // read codes j-16..j-1 (view) = storage lo+j-16 .. lo+j-1; adapter codes i-16..i-1
-            const uint64_t r = nib16(W, (int64_t)lo + j - 16);
-            const uint64_t a = nib16(code4, (int64_t)i);          // 16 pad nibbles in front
-            uint64_t x = r & a;
-            x |= x >> 1; x |= x >> 2;
-            const uint64_t mis = ~x & 0x1111111111111111ull;
-            run = clz64(mis) >> 2;                                // from the top nibble (cell (i, j)) down
-        } else {
-            // view position p = storage lo+len-1-p, complemented: positions j-1, j-2, ... are
-            // storage lo+len-j, +1, ...; compare raw codes with the reverse-complemented adapter
-            const uint64_t r = nib16(W, (int64_t)lo + (int64_t)len - j);
-            const uint64_t a = nib16(rcode4, (int64_t)(m - i));
-            uint64_t x = r & a;
-            x |= x >> 1; x |= x >> 2;
-            const uint64_t mis = ~x & 0x1111111111111111ull;
-            run = ctz64(mis) >> 2;
-        }
-        if (run > avail) run = avail;
-        if (run > 0) {                               // characters equal: diagonal, unconditionally
-            score += run; i -= run; j -= run;
-            continue;
-        }
+        const uint64_t r = nib16(W, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
+        const uint64_t a = nib16(dir ? rcode4 : code4, dir ? (int64_t)(m - i) : (int64_t)i);
+        uint64_t x = r & a;
+        x |= x >> 1; x |= x >> 2;
+        uint64_t mis = ~x & 0x1111111111111111ull;
+        if (dir) mis = brev64(mis);                              // nibble q -> nibble 15-q
+        const int run = imin(clz64(mis) >> 2, avail);
+        score += run; i -= run; j -= run;                        // characters equal: diagonal, unconditionally
+        if (run == avail) continue;                              // cap or border reached: look again
         const int bit = 64 - m + i - 1;
         const uint64_t pvj = R.pv[(j - ws) & (RING - 1)], mvj = R.mv[(j - ws) & (RING - 1)];
         const uint64_t pvl = R.pv[(j - 1 - ws) & (RING - 1)], mvl = R.mv[(j - 1 - ws) & (RING - 1)];
