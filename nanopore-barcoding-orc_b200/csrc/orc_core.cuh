@@ -78,6 +78,12 @@ struct RoundTable {
     int32_t min_ov_min;             // smallest min_ov of the round
     uint8_t kmax_any[MAX_M + 8];    // max over the adapters of kmax[a][L]
     uint32_t peq32s[16][64];        // like peq32, for the shared suffix (5' rounds only)
+    // 5' rounds: bit c of first_mask[j] = an alignment that starts in column 0, ends in column j
+    // and costs c could be acceptable for some adapter (c <= k_max < 16 when the filter is on)
+    uint32_t first_mask[MAX_M + 32];
+    // chunk_lut[P | M << 4], P / M = the Ph / Mh top bits of four consecutive columns (oldest in
+    // bit 3): low nibble = 4 + the lowest prefix sum of the four deltas, high nibble = 4 + their sum
+    uint8_t chunk_lut[256];
 };
 
 // A read (or what a previous round left of it) as a window of the packed code array:
@@ -279,6 +285,19 @@ ORC_HD int popc32(uint32_t x)
 #endif
 }
 
+// Lowest D[row][j] over the (up to eight) columns of a chunk, exactly, and the total change:
+// accP / accM hold one Ph / Mh top bit per column, newest in bit 0.  Columns a short chunk does
+// not have are zero deltas in the older half; they only add the chunk's starting cost to the
+// minimum, which can trigger a replay that finds nothing but never hides a column.
+ORC_HD int chunk_min(const uint8_t *lut, uint32_t accP, uint32_t accM, int D, int &sum)
+{
+    const uint32_t e1 = lut[(accP >> 4) | (accM & 0xF0u)];            // the older four columns
+    const uint32_t e2 = lut[(accP & 15u) | ((accM << 4) & 0xF0u)];    // the newer four
+    const int s1 = (int)(e1 >> 4) - 4;
+    sum = s1 + (int)(e2 >> 4) - 4;
+    return D + imin((int)(e1 & 15u), s1 + (int)(e2 & 15u)) - 4;
+}
+
 // Reads 8 codes of a lane's sequence, view positions p .. p+7, as two words of byte-wide
 // codes: A holds positions p, p+2, p+4, p+6 and B holds p+1, p+3, p+5, p+7, in the byte order
 // that the lane's PRMT selectors expect (reversed for direction 1).
@@ -327,7 +346,8 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                          uint32_t ext, uint32_t back, WinList &out,
                          const char *suffix_base = nullptr, int Ls = 0,
                          const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0, int m_min = 0,
-                         int sfx_primary = 0)
+                         int sfx_primary = 0, const uint32_t *first_mask = nullptr,
+                         const uint8_t *lut = nullptr)
 {
     const uint32_t n = len;
     out.n = 0; out.pad_ = 0;
@@ -363,7 +383,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         const uint32_t wmax = (uint32_t)(m_max + kt);
         const uint32_t w0 = wmax < n ? wmax : n;
         bool need = true;
-        if (suffix_base != nullptr && Ls > 0) {
+        if (suffix_base != nullptr && Ls > 0 && first_mask != nullptr) {
             need = false;
             uint32_t sPv = 0, sMv = 0;
             int sD = 0;
@@ -387,15 +407,9 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                         Ph <<= 1; Mh <<= 1;
                         sPv = Mh | ~(Xv | Ph);
                         sMv = Ph & Xv;
-                        if (sD <= kt) {
-                            const int j = (int)c0 + t + 1;
-                            // an alignment ending here has cost c >= sD and aligns at most
-                            // min(m_max, j + c) adapter characters
-                            for (int c = sD; c <= kt; c++) {
-                                const int lmax = imin(m_max, j + c);
-                                if (lmax >= min_ov_min && c <= (int)kmax_any[lmax]) need = true;
-                            }
-                        }
+                        // an alignment ending here has cost c >= sD and aligns at most
+                        // min(m_max, j + c) adapter characters: first_mask[j] has the costs that pass
+                        if (sD <= kt && (first_mask[c0 + t + 1] >> sD) != 0u) need = true;
                     }
                 }
             }
@@ -502,14 +516,9 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
 #pragma unroll
             for (int t = 0; t < 8; t++) if (t < ncol) column(t);
         }
-        // Lowest cost inside the chunk, bounded from its two halves (the older columns are the
-        // high bits of accP/accM): D can only fall by the M bits, and the second half starts from
-        // what the first half left.  Only a chunk that may reach the threshold is replayed.
-        const int h2 = ncol >> 1;                                     // columns in the second (newer) half
-        const int m1 = popc32(accM >> h2), p1 = popc32(accP >> h2);
-        const int m2 = popc32(accM & ((1u << h2) - 1u));
-        const int low = D - imax(m1, m1 - p1 + m2);
-        if (low <= kt) {
+        // Only a chunk in which the cost really reaches the threshold is replayed column by column.
+        int dsum;
+        if (chunk_min(lut, accP, accM, D, dsum) <= kt) {
 #pragma unroll 1
             for (int t = 0; t < ncol; t++) {
                 const int b = ncol - 1 - t;
@@ -522,7 +531,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                 }
             }
         } else {
-            D += popc32(accP) - popc32(accM);
+            D += dsum;
         }
     }
     flush_cluster();
@@ -619,7 +628,8 @@ ORC_HD void lane_scan_init(LaneScan &L, int m, int n)
 // Stage 2: columns s+1 .. e of one pair.
 ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                         uint32_t s, uint32_t e, const char *peq_base, int lane, uint64_t pv0, int d0,
-                        int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L)
+                        int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L,
+                        const uint8_t *lut)
 {
     const uint64_t pad = (m == 64) ? 0ull : ((1ull << (64 - m)) - 1ull);
     const int n = (int)len;
@@ -664,7 +674,11 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
 #pragma unroll
             for (int t = 0; t < 8; t++) if (t < ncol) column(t);
         }
-        if (D - popc32(accM) <= k) {             // D[m][j] may reach k inside this chunk: replay it
+        // D[m][j] can only fall by the M bits; a chunk that might reach k is tested exactly, and
+        // replayed column by column only if it does
+        bool replay = false;
+        if (D - popc32(accM) <= k) { int dsum; replay = chunk_min(lut, accP, accM, D, dsum) <= k; }
+        if (replay) {
             for (int t = 0; t < ncol; t++) {
                 const int b = ncol - 1 - t;
                 D += (int)((accP >> b) & 1u) - (int)((accM >> b) & 1u);
@@ -807,13 +821,13 @@ ORC_HD void scan_window_noindel(const uint32_t *__restrict__ W, uint64_t lo, uin
 ORC_HD void scan_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                       const WinList *wl, const char *peq_base, int lane, uint64_t pv0, int d0,
                       int m, int k, const uint8_t *kmax, int min_ov, int type, LaneScan &L,
-                      int indels = 1, const uint32_t *code4 = nullptr, const uint32_t *rcode4 = nullptr)
+                      int indels, const uint32_t *code4, const uint32_t *rcode4, const uint8_t *lut)
 {
     lane_scan_init(L, m, (int)len);
     const uint32_t nw = wl ? wl->n : 1u;
     for (uint32_t w = 0; w < nw; w++) {
         const uint32_t s = wl ? wl->s[w] : 0u, e = wl ? wl->e[w] : len;
-        if (indels) scan_window(W, lo, len, dir, s, e, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, L);
+        if (indels) scan_window(W, lo, len, dir, s, e, peq_base, lane, pv0, d0, m, k, kmax, min_ov, type, L, lut);
         else scan_window_noindel(W, lo, len, dir, s, e, code4, rcode4, m, k, kmax, min_ov, type, L);
     }
 }

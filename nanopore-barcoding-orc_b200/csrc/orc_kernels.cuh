@@ -98,6 +98,8 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     __shared__ __align__(16) uint32_t s_peq32[16][64];
     __shared__ __align__(16) uint32_t s_peq32s[16][64];
     __shared__ uint8_t s_kmax_any[MAX_M + 8];
+    __shared__ uint32_t s_first_mask[MAX_M + 32];
+    __shared__ uint8_t s_lut[256];
     __shared__ int s_par[8];
     __shared__ int s_mmin, s_sfxp;
     if (threadIdx.x == 0) { s_mmin = tab->m_min; s_sfxp = tab->sfx_primary; }
@@ -106,6 +108,8 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
         (&s_peq32s[0][0])[i] = (&tab->peq32s[0][0])[i];
     }
     for (int i = threadIdx.x; i < MAX_M + 8; i += blockDim.x) s_kmax_any[i] = tab->kmax_any[i];
+    for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_mask[i] = tab->first_mask[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = tab->chunk_lut[i];
     if (threadIdx.x == 0) {
         s_par[0] = tab->lcp; s_par[1] = tab->k_max; s_par[2] = tab->m_max; s_par[3] = tab->type;
         s_par[4] = tab->revcomp; s_par[5] = tab->use_filter; s_par[6] = tab->lcs; s_par[7] = tab->min_ov_min;
@@ -133,7 +137,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                              (int)(2u * (threadIdx.x & 31u)) + dir, Lp, kt, type, (uint32_t)(m_max - Lp + kt),
                              (uint32_t)(Lp + kt + 1), wl,
                              s_par[6] > 0 ? reinterpret_cast<const char *>(&s_peq32s[0][0]) : nullptr,
-                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp);
+                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp, s_first_mask, s_lut);
                 cols = win_columns(wl);
             } else {
                 wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything
@@ -219,7 +223,7 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                 dst[0] = src[0]; dst[1] = src[1];
             }
             scan_lane(W, v.lo, v.len, dir, &wl, peq_base, tl, T.pv0[tl], T.d0[tl], m, T.k[a], T.kmax[a],
-                      T.min_ov[a], type, L, T.indels, T.code4[a], T.rcode4[a]);
+                      T.min_ov[a], type, L, T.indels, T.code4[a], T.rcode4[a], T.chunk_lut);
             has = L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2;
             need = has && L.need != 0;
         }

@@ -135,6 +135,23 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         }
         T.kmax_any[L] = (uint8_t)v;
     }
+    for (int P = 0; P < 16; P++)
+        for (int M = 0; M < 16; M++) {
+            int sum = 0, low = 9;
+            for (int u = 3; u >= 0; u--) {               // bit 3 is the oldest column
+                sum += ((P >> u) & 1) - ((M >> u) & 1);
+                if (sum < low) low = sum;
+            }
+            T.chunk_lut[P | (M << 4)] = (uint8_t)((low + 4) | ((sum + 4) << 4));
+        }
+    for (int j = 0; j < MAX_M + 32; j++) {
+        uint32_t bits = 0;
+        for (int c = 0; c <= T.k_max && c < 32; c++) {
+            const int lmax = (j + c < T.m_max) ? j + c : T.m_max;
+            if (lmax >= T.min_ov_min && c <= (int)T.kmax_any[lmax]) bits |= 1u << c;
+        }
+        T.first_mask[j] = bits;
+    }
     if (T.use_filter && lcs > 0) {
         const uint32_t pad32 = (lcs == 32) ? 0u : ((1u << (32 - lcs)) - 1u);
         for (int lane = 0; lane < 64; lane++) {

@@ -82,7 +82,7 @@ extern "C" int hostsim_demux(int n_rounds,
                     trigger_lane(W, v.lo, v.len, dir, (const char *)&R.peq32[0][0], dir, R.lcp, R.k_max, R.type,
                                  (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + R.k_max + 1), wl[dir],
                                  R.lcs > 0 ? (const char *)&R.peq32s[0][0] : nullptr, R.lcs,
-                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary);
+                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary, R.first_mask, R.chunk_lut);
                     n_columns[rd] += win_columns(wl[dir]);
                 }
             } else n_columns[rd] += 2ull * v.len;
@@ -93,7 +93,7 @@ extern "C" int hostsim_demux(int n_rounds,
                 LaneScan L;
                 scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, (const char *)&R.peq[0][0], lane,
                           R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, L,
-                          R.indels, R.code4[a], R.rcode4[a]);
+                          R.indels, R.code4[a], R.rcode4[a], R.chunk_lut);
                 if (L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2) {
                     PairResult pr; memset(&pr, 0, sizeof(pr));
                     if (!L.need) {
