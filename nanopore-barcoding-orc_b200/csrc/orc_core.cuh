@@ -494,7 +494,14 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         uint32_t A, B;
         rd.next(A, B);
         const int ncol = imin(8, (int)n - 8 * q);
-        uint32_t accP = 0, accM = 0;
+        // Row 0 costs 0 in every column, so D[Lmain][j] is the sum of the column's vertical deltas:
+        // popc(Pv) - popc(Mv) (the padding rows below bit 32 - Lmain keep both bits clear).  The
+        // eight columns of a chunk therefore run without any bookkeeping.  The cost moves by at most
+        // one per column, so between two columns c apart with costs Da and Db it stays above
+        // (Da + Db - c) / 2: only a (half-)chunk where that can reach the threshold is run again,
+        // column by column, from the state saved at its start.
+        const uint32_t Pv0 = Pv, Mv0 = Mv;
+        uint32_t Pv4 = 0, Mv4 = 0;
         auto column = [&](int t) {
             const uint32_t src = (t & 1) ? B : A;
             const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
@@ -503,36 +510,54 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
             const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
             uint32_t Ph = Mv | ~(Xh | Pv);
             uint32_t Mh = Pv & Xh;
-            accP = funnel_l1(accP, Ph);
-            accM = funnel_l1(accM, Mh);
             Ph <<= 1; Mh <<= 1;
             Pv = Mh | ~(Xv | Ph);
             Mv = Ph & Xv;
         };
-        if (ncol == 8) {                         // full chunk: no per-column bound test
+        if (ncol == 8) {
 #pragma unroll
-            for (int t = 0; t < 8; t++) column(t);
+            for (int t = 0; t < 4; t++) column(t);
+            Pv4 = Pv; Mv4 = Mv;
+#pragma unroll
+            for (int t = 4; t < 8; t++) column(t);
         } else {
 #pragma unroll
             for (int t = 0; t < 8; t++) if (t < ncol) column(t);
         }
-        // Only a chunk in which the cost really reaches the threshold is replayed column by column.
-        int dsum;
-        if (chunk_min(lut, accP, accM, D, dsum) <= kt) {
+        const uint32_t Pv8 = Pv, Mv8 = Mv;
+        const int Dend = popc32(Pv8) - popc32(Mv8);
+        auto replay = [&](int t0, int t1, uint32_t pv, uint32_t mv, int d) {
 #pragma unroll 1
-            for (int t = 0; t < ncol; t++) {
-                const int b = ncol - 1 - t;
-                D += (int)((accP >> b) & 1u) - (int)((accM >> b) & 1u);
-                if (D <= kt) {
+            for (int t = t0; t < t1; t++) {
+                const uint32_t src = (t & 1) ? B : A;
+                const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+                const uint32_t Eq = *reinterpret_cast<const uint32_t *>(main_base + byte_perm(src, lane4, sel));
+                const uint32_t Xv = Eq | mv;
+                const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                uint32_t Ph = mv | ~(Xh | pv);
+                uint32_t Mh = pv & Xh;
+                d += (int)(Ph >> 31) - (int)(Mh >> 31);
+                Ph <<= 1; Mh <<= 1;
+                pv = Mh | ~(Xv | Ph);
+                mv = Ph & Xv;
+                if (d <= kt) {
                     const uint32_t j = (uint32_t)(8 * q + t + 1);
                     if (clu_f != 0 && j - clu_l > (uint32_t)(2 * kt)) flush_cluster();
                     if (clu_f == 0) clu_f = j;
                     clu_l = j;
                 }
             }
-        } else {
-            D += dsum;
+        };
+        if (D + Dend <= ncol + 2 * kt) {
+            if (ncol == 8) {
+                const int Dmid = popc32(Pv4) - popc32(Mv4);
+                if (D + Dmid <= 4 + 2 * kt) replay(0, 4, Pv0, Mv0, D);
+                if (Dmid + Dend <= 4 + 2 * kt) replay(4, 8, Pv4, Mv4, Dmid);
+            } else {
+                replay(0, ncol, Pv0, Mv0, D);
+            }
         }
+        D = Dend;
     }
     flush_cluster();
     for (int c = 0; c < n_clu; c++) add_cluster(clu_fs[c], clu_ls[c], true);
