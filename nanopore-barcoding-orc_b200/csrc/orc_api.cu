@@ -58,6 +58,7 @@ struct Slot {
     void *d_sort_tmp = nullptr;
     WinList *d_wins = nullptr;
     Task *d_tasks = nullptr;
+    uint32_t *d_jobs = nullptr;              // stage 2a survivors: job numbers (item * n_adapters + adapter)
     PairResult *d_results = nullptr;
     uint32_t *d_counters = nullptr;          // [0..1] work counters, [2..3] task counts
     unsigned long long *d_cells = nullptr;   // [0..1] sum of view lengths entering each round, [2..3] window columns
@@ -91,7 +92,7 @@ struct orc_ctx {
     std::vector<Slot> slots;
     std::vector<uint64_t> total_counts;
     std::string err;
-    int scan_blocks = 0, resolve_blocks = 0;
+    int scan_blocks = 0, resolve_blocks = 0, filter_blocks = 0;
     size_t sort_tmp_bytes = 0;
 };
 
@@ -138,8 +139,9 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(cudaMalloc(&s.d_sort_tmp, ctx->sort_tmp_bytes + 64));
     CK(dalloc(&s.d_wins, 2 * R));
     CK(dalloc(&s.d_tasks, n_tasks));
+    CK(dalloc(&s.d_jobs, 2 * R * MAX_AD));
     CK(dalloc(&s.d_results, n_tasks));
-    CK(dalloc(&s.d_counters, 8));
+    CK(dalloc(&s.d_counters, 16));
     CK(dalloc(&s.d_cells, 4));
     CK(dalloc(&s.d_bin, R));
     CK(dalloc(&s.d_out_len, R));
@@ -152,7 +154,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_bin_offsets, (size_t)ctx->n_bins + 1));
     CK(halloc(&s.h_bin, R));
     CK(halloc(&s.h_out_len, R));
-    CK(halloc(&s.h_counters, 8));
+    CK(halloc(&s.h_counters, 16));
     CK(halloc(&s.h_cells, 4));
     CK(halloc(&s.h_bin_counts, (size_t)ctx->n_bins));
     CK(halloc(&s.h_bin_offsets, (size_t)ctx->n_bins + 1));
@@ -176,7 +178,7 @@ static void free_slot(Slot &s)
     for (int i = 0; i < 3; i++) cudaFree(s.d_views[i]);
     for (int i = 0; i < 2; i++) { cudaFree(s.d_match[i]); cudaFreeHost(s.h_match[i]); }
     cudaFree(s.d_wcols); cudaFree(s.d_wcols_sorted); cudaFree(s.d_item_in); cudaFree(s.d_item_order);
-    cudaFree(s.d_best_key); cudaFree(s.d_tasks); cudaFree(s.d_results);
+    cudaFree(s.d_best_key); cudaFree(s.d_tasks); cudaFree(s.d_results); cudaFree(s.d_jobs);
     cudaFree(s.d_key_in); cudaFree(s.d_key_out); cudaFree(s.d_val_in); cudaFree(s.d_order);
     cudaFree(s.d_sort_tmp); cudaFree(s.d_wins);
     cudaFree(s.d_counters); cudaFree(s.d_cells); cudaFree(s.d_bin); cudaFree(s.d_out_len);
@@ -255,6 +257,8 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel, SCAN_THREADS, 0));
     ctx->scan_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel, SCAN_THREADS, 0));
+    ctx->filter_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_kernel, 128, 0));
     if (occ > 6) occ = 6;       // more resident threads only thrash the per-thread ring (measured)
     ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
@@ -397,7 +401,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     const uint32_t n = s.n_reads;
     uint32_t *W = s.d_codes_alloc + GUARD_WORDS;
     cudaStream_t st = s.stream;
-    CK(cudaMemsetAsync(s.d_counters, 0, 8 * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(s.d_counters, 0, 16 * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(s.d_cells, 0, 4 * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));       // kernels start here (re-recorded when launched alone)
     s.did_h2d = s.fresh_upload;                  // h2d_ms is only meaningful right after an upload
@@ -417,7 +421,9 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     for (int r = 0; r < ctx->n_rounds; r++) {
         const Match *prev = r == 0 ? nullptr : s.d_match[r - 1];
         const bool filter = ctx->h_tab[r].use_filter != 0;
-        uint32_t *cnt = s.d_counters + 4 * r;       // job counter, result slots, resolver tasks
+        // per round: [0] stage-2b job counter, [1] result slots, [2] resolver tasks, [4] stage-2a job
+        // counter, [5] pairs that passed stage 2a
+        uint32_t *cnt = s.d_counters + 8 * r;
         if (n && ctx->anchored[r]) {
             // anchored adapters without indels: Hamming compare of the anchored end, no alignment
             CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
@@ -445,9 +451,14 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         }
         if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
         if (n && !ctx->anchored[r]) {
+            // stage 2a drops the pairs that cannot hold a candidate, stage 2b scans the rest
+            const bool prefilter = ctx->h_tab[r].indels != 0;
+            if (prefilter)
+                filter_kernel<<<ctx->filter_blocks, SCAN_THREADS, 0, st>>>(
+                    ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_jobs, cnt);
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_results,
-                s.d_tasks, s.d_best_key, cnt);
+                s.d_tasks, s.d_best_key, cnt, prefilter ? s.d_jobs : nullptr);
         }
         if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         if (n) {
@@ -519,7 +530,7 @@ extern "C" int orc_download(orc_ctx *ctx, int slot)
     const uint32_t n = s.n_reads;
     CK(cudaMemcpyAsync(s.h_bin_counts, s.d_bin_counts, sizeof(uint64_t) * ctx->n_bins, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_bin_offsets, s.d_bin_offsets, sizeof(uint64_t) * (ctx->n_bins + 1), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_HDR], st));
     if (n) {
@@ -607,7 +618,7 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     if (s.did_h2d) CK(el(EV_START, EV_H2D, &t->h2d_ms));
     if (s.did_d2h) CK(el(EV_EMIT, EV_END, &t->d2h_ms));
     // counters need a device read when the caller never downloaded
-    uint32_t counters[8];
+    uint32_t counters[16];
     unsigned long long cells[4];
     CK(cudaMemcpy(counters, s.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cells, s.d_cells, sizeof(cells), cudaMemcpyDeviceToHost));
@@ -620,9 +631,10 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     if (s.n_reads)
         for (int r = 0; r < ctx->n_rounds; r++)
             if (ctx->anchored[r]) t->kernel_launches -= 1u;   // anchored + select instead of scan + resolve + select
+            else if (ctx->h_tab[r].indels) t->kernel_launches += 1u;   // stage 2a (filter_kernel)
     for (int r = 0; r < ctx->n_rounds; r++) {
-        t->n_tasks[r] = counters[4 * r + 2];
-        t->n_candidates[r] = counters[4 * r + 1];
+        t->n_tasks[r] = counters[8 * r + 2];
+        t->n_candidates[r] = counters[8 * r + 1];
         const RoundTable &T = ctx->h_tab[r];
         // algorithmic cells: pairs * m * n summed over the reads entering the round
         uint64_t msum = 0;

@@ -84,6 +84,10 @@ struct RoundTable {
     // chunk_lut[P | M << 4], P / M = the Ph / Mh top bits of four consecutive columns (oldest in
     // bit 3): low nibble = 4 + the lowest prefix sum of the four deltas, high nibble = 4 + their sum
     uint8_t chunk_lut[256];
+    // Stage 2a: per lane, the match bits of a block of Lb = min(32, m) adapter rows -- the LAST
+    // rows of a 5' adapter, the FIRST rows of a 3' adapter -- row Lb at bit 31, like peq32.
+    uint32_t peq32b[16][64];
+    int32_t block_len[MAX_AD];    // Lb, or 0: no block test for this adapter (k >= Lb)
 };
 
 // A read (or what a previous round left of it) as a window of the packed code array:
@@ -629,6 +633,120 @@ ORC_HD uint32_t win_columns(const WinList &w)
     uint32_t c = 0;
     for (uint32_t i = 0; i < w.n; i++) c += w.e[i] - w.s[i];
     return c;
+}
+
+// ------------------------------------------------------------------------------------
+// Stage 2a (block_test): may this (read, direction, adapter) have a candidate cell inside the
+// windows at all?  A 32-bit Myers scan of a block B of Lb = min(32, m) adapter rows over the
+// window columns answers with a necessary condition, at well under half the price of the
+// 64-bit scan; only the pairs that pass go on to scan_window.  The adapters of a round differ
+// in a few rows only, so for the reads that carry one of them the other adapters stop here.
+//
+//  * 5' adapter, B = its last Lb rows.  An acceptable alignment ending in (m, j) with cost c
+//    spends at most c on B, and B's own matrix (row 0 free) has D_B[Lb][j] <= c <= k in that
+//    same column.  If the window starts at the true column 0 the alignment may begin inside B
+//    (the read starts within the adapter): B's column 0 is free as well (cost 0 in every row),
+//    and for the first columns, where nearly any cost is "<= k", the acceptance limit of the
+//    alignment's largest possible length decides instead (first_mask, the loosest of the round).
+//  * 3' adapter, B = its first Lb rows, the same rows of the same matrix (same start costs).  A
+//    path to (m, j) or to a last-column cell (i, n) with i > Lb crosses row Lb inside the window
+//    at cost <= k; a last-column cell with i <= Lb is a cell of B's matrix itself and is tested
+//    against R6's necessary condition directly.
+//
+// Away from the true column 0 the columns run without bookkeeping, as in stage 1: the cost is a
+// popcount away and moves by at most one per column, so (Da + Db - c) / 2 bounds it between two
+// columns c apart.  Passing a pair that has no candidate only costs time.
+ORC_HD bool block_test(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
+                       const WinList *wl, const char *peq32b_base, int lane, int Lb, int k, int type,
+                       const uint8_t *kmax, int min_ov, const uint32_t *first_mask)
+{
+    if (Lb <= 0) return true;
+    const uint32_t n = len;
+    const uint32_t pad = (Lb == 32) ? 0u : ((1u << (32 - Lb)) - 1u);
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    uint32_t sel0, sel1, sel2, sel3;
+    if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
+    else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
+    const uint32_t nw = wl ? wl->n : 1u;
+    for (uint32_t w = 0; w < nw; w++) {
+        const uint32_t s = wl ? wl->s[w] : 0u, e = wl ? wl->e[w] : n;
+        const bool free0 = s == 0u && type == TYPE_FRONT;
+        uint32_t Pv, Mv = 0;
+        int D;
+        if (free0) { Pv = 0; D = 0; }
+        else { Pv = ~pad; D = Lb; }
+        ChunkReader rd;
+        rd.init(W, lo, len, dir, s);
+        const int ncols = (int)(e - s);
+        const int nchunks = (ncols + 7) >> 3;
+        for (int q = 0; q < nchunks; q++) {
+            uint32_t A, B;
+            rd.next(A, B);
+            const int ncol = imin(8, ncols - 8 * q);
+            if (free0 && q < 2) {
+                // the first sixteen columns after a free column 0: cost and limit column by column
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (t < ncol) {
+                        const uint32_t src = (t & 1) ? B : A;
+                        const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+                        const uint32_t Eq = *reinterpret_cast<const uint32_t *>(peq32b_base + byte_perm(src, lane4, sel));
+                        const uint32_t Xv = Eq | Mv;
+                        const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                        uint32_t Ph = Mv | ~(Xh | Pv);
+                        uint32_t Mh = Pv & Xh;
+                        D += (int)(Ph >> 31) - (int)(Mh >> 31);
+                        Ph <<= 1; Mh <<= 1;
+                        Pv = Mh | ~(Xv | Ph);
+                        Mv = Ph & Xv;
+                        if (D <= k && (first_mask[8 * q + t + 1] >> D) != 0u) return true;
+                    }
+                }
+                continue;
+            }
+            uint32_t Pv4 = 0, Mv4 = 0;
+            auto column = [&](int t) {
+                const uint32_t src = (t & 1) ? B : A;
+                const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+                const uint32_t Eq = *reinterpret_cast<const uint32_t *>(peq32b_base + byte_perm(src, lane4, sel));
+                const uint32_t Xv = Eq | Mv;
+                const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                uint32_t Ph = Mv | ~(Xh | Pv);
+                uint32_t Mh = Pv & Xh;
+                Ph <<= 1; Mh <<= 1;
+                Pv = Mh | ~(Xv | Ph);
+                Mv = Ph & Xv;
+            };
+            if (ncol == 8) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) column(t);
+                Pv4 = Pv; Mv4 = Mv;
+#pragma unroll
+                for (int t = 4; t < 8; t++) column(t);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; t++) if (t < ncol) column(t);
+            }
+            // the free column 0 leaves set bits of Pv / Mv only in the block's own rows as well
+            const int Dend = popc32(Pv) - popc32(Mv);
+            if (D + Dend <= ncol + 2 * k) {
+                if (ncol < 8) return true;
+                const int Dmid = popc32(Pv4) - popc32(Mv4);
+                if (D + Dmid <= 4 + 2 * k || Dmid + Dend <= 4 + 2 * k) return true;
+            }
+            D = Dend;
+        }
+        if (type == TYPE_BACK && e == n) {
+            // R6's necessary condition for the cells (i, n), i <= Lb (as in scan_window)
+            int cum = 0;
+            for (int i = 1; i <= Lb; i++) {
+                const int bit = 32 - Lb + i - 1;
+                cum += (int)((Pv >> bit) & 1u) - (int)((Mv >> bit) & 1u);
+                if (i >= min_ov && cum <= (int)kmax[i]) return true;
+            }
+        }
+    }
+    return false;
 }
 
 // Per-pair state of stage 2.  Candidates of cost 0 are settled on the spot: their path is a

@@ -14,6 +14,7 @@
 //                      stable multi-way partition of the trimmed reads into their
 //                      SP5 x SP27 bins and assembly of the FASTQ records.  HBM-bound.
 #pragma once
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -161,32 +162,37 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------
-// Stage 2 of the scan.  A job is one (read, direction, adapter) pair; the (read, direction)
-// items come sorted by the number of window columns they have to scan, so the 32 lanes of a
-// warp -- 32 consecutive jobs, i.e. the adapters of two or three items -- run the same number
-// of columns.  Persistent warps pull 32 jobs at a time from a global counter.  A pair whose
-// candidates all have cost 0 is finished here; the others go to the resolver's work list.
+// Stage 2a.  A job is one (read, direction, adapter) pair, numbered item * n_adapters + adapter
+// over the items in sorted order.  block_test() drops the pairs that cannot have a candidate;
+// the survivors' job numbers go to `jobs` (warp-aggregated append), which stage 2b consumes.
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
-            const View *__restrict__ views, const WinList *__restrict__ wins,
-            const uint32_t *__restrict__ wcols_sorted, const uint32_t *__restrict__ item_order,
-            uint32_t n_items, PairResult *__restrict__ results, Task *__restrict__ work,
-            unsigned long long *__restrict__ best_key, uint32_t *__restrict__ counters)
+filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
+              const View *__restrict__ views, const WinList *__restrict__ wins,
+              const uint32_t *__restrict__ wcols_sorted, const uint32_t *__restrict__ item_order,
+              uint32_t n_items, uint32_t *__restrict__ jobs, uint32_t *__restrict__ counters)
 {
-    __shared__ __align__(16) RoundTable T;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(tab);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
-        for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
+    __shared__ __align__(16) uint32_t s_peq32b[16][64];
+    __shared__ uint32_t s_first_mask[MAX_M + 32];
+    __shared__ uint8_t s_kmax[MAX_AD][MAX_M + 8];
+    __shared__ int s_k[MAX_AD], s_min_ov[MAX_AD], s_lb[MAX_AD];
+    __shared__ int s_na, s_type;
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32b[0][0])[i] = (&tab->peq32b[0][0])[i];
+    for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_mask[i] = tab->first_mask[i];
+    for (int i = threadIdx.x; i < MAX_AD * (MAX_M + 8); i += blockDim.x)
+        (&s_kmax[0][0])[i] = tab->kmax[i / (MAX_M + 8)][i % (MAX_M + 8)];
+    if (threadIdx.x < MAX_AD) {
+        s_k[threadIdx.x] = tab->k[threadIdx.x];
+        s_min_ov[threadIdx.x] = tab->min_ov[threadIdx.x];
+        s_lb[threadIdx.x] = tab->block_len[threadIdx.x];
     }
+    if (threadIdx.x == 0) { s_na = tab->n_adapters; s_type = tab->type; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint32_t na = (uint32_t)T.n_adapters;
+    const uint32_t na = (uint32_t)s_na;
     const uint32_t n_jobs = n_items * na;
-    const char *peq_base = reinterpret_cast<const char *>(&T.peq[0][0]);
-    const int type = T.type;
-    uint32_t *job_counter = counters + 0, *res_count = counters + 1, *work_count = counters + 2;
-
+    const int type = s_type;
+    const char *base_b = reinterpret_cast<const char *>(&s_peq32b[0][0]);
+    uint32_t *job_counter = counters + 4, *n_out = counters + 5;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(job_counter, 32u);
@@ -203,6 +209,75 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
             item = item_order[it];
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        bool keep = false;
+        if (active) {
+            const int dir = (int)(item & 1u);
+            const View v = views[item >> 1];
+            WinList wl;
+            {
+                const uint4 *src = reinterpret_cast<const uint4 *>(wins + item);
+                uint4 *dst = reinterpret_cast<uint4 *>(&wl);
+                dst[0] = src[0]; dst[1] = src[1];
+            }
+            keep = block_test(W, v.lo, v.len, dir, &wl, base_b, a + (int)na * dir, s_lb[a], s_k[a], type,
+                              s_kmax[a], s_min_ov[a], s_first_mask);
+        }
+        const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+        if (mk) {
+            uint32_t ob = 0;
+            if (lane == 0) ob = atomicAdd(n_out, (uint32_t)__popc(mk));
+            ob = __shfl_sync(0xffffffffu, ob, 0);
+            if (keep) jobs[ob + (uint32_t)__popc(mk & lanemask_lt())] = p;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Stage 2 of the scan.  A job is one (read, direction, adapter) pair; the (read, direction)
+// items come sorted by the number of window columns they have to scan, so the 32 lanes of a
+// warp -- 32 consecutive jobs, i.e. the adapters of two or three items -- run the same number
+// of columns.  Persistent warps pull 32 jobs at a time from a global counter.  A pair whose
+// candidates all have cost 0 is finished here; the others go to the resolver's work list.
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
+            const View *__restrict__ views, const WinList *__restrict__ wins,
+            const uint32_t *__restrict__ wcols_sorted, const uint32_t *__restrict__ item_order,
+            uint32_t n_items, PairResult *__restrict__ results, Task *__restrict__ work,
+            unsigned long long *__restrict__ best_key, uint32_t *__restrict__ counters,
+            const uint32_t *__restrict__ jobs)
+{
+    __shared__ __align__(16) RoundTable T;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t na = (uint32_t)T.n_adapters;
+    // with a job list (stage 2a ran) the jobs are its entries, else every pair of every item
+    const uint32_t n_jobs = jobs ? counters[5] : n_items * na;
+    const char *peq_base = reinterpret_cast<const char *>(&T.peq[0][0]);
+    const int type = T.type;
+    uint32_t *job_counter = counters + 0, *res_count = counters + 1, *work_count = counters + 2;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(job_counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_jobs) break;
+        uint32_t p = base + (uint32_t)lane;
+        bool active = p < n_jobs;
+        if (active && jobs) p = jobs[p];
+        uint32_t it = 0, item = 0;
+        int a = 0;
+        if (active) {
+            it = p / na;
+            a = (int)(p - it * na);
+            active = wcols_sorted[it] != 0u;     // sorted descending: inactive items are at the end
+            item = item_order[it];
+        }
+        if (!jobs && __ballot_sync(0xffffffffu, active) == 0u) break;
         bool has = false, need = false;
         LaneScan L;
         uint32_t r = 0;
@@ -263,13 +338,17 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                const uint32_t *__restrict__ work_count, PairResult *__restrict__ results,
                unsigned long long *__restrict__ best_key)
 {
-    __shared__ __align__(16) RoundTable T;
+    // Only the head of the table (everything up to and including peq) is used here; the rest
+    // stays out of shared memory so that L1 keeps more room for the local-memory column rings.
+    constexpr int HEAD = (int)offsetof(RoundTable, pv0);
+    __shared__ __align__(16) unsigned char s_tab[HEAD];
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(tab);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
-        for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_tab);
+        for (int i = threadIdx.x; i < HEAD / 4; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    const RoundTable &T = *reinterpret_cast<const RoundTable *>(s_tab);
     const uint32_t n = *work_count;
     ColRing ring;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {

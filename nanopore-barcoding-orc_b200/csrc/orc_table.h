@@ -88,6 +88,19 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         // R2: FRONT column 0 costs are all 0; BACK column 0 cost is i
         T.pv0[lane] = (type == TYPE_FRONT) ? 0ull : ~pad;
         T.d0[lane] = (type == TYPE_FRONT) ? 0 : m;
+        // stage 2a block: the last Lb rows of a 5' adapter, the first Lb rows of a 3' adapter
+        const int Lb = m < 32 ? m : 32;
+        const int first = (type == TYPE_FRONT) ? m - Lb : 0;
+        const uint32_t pad32 = (Lb == 32) ? 0u : ((1u << (32 - Lb)) - 1u);
+        for (uint32_t c = 0; c < 16; c++) {
+            const uint32_t cc = dir ? comp4(c) : c;
+            uint32_t bits = pad32;
+            for (int i = 0; i < Lb; i++)
+                if (T.code[a][first + i] & cc) bits |= 1u << (32 - Lb + i);
+            T.peq32b[c][lane] = bits;
+        }
+        // with k >= Lb a path may cross the block for free; with k_max >= 32 first_mask has no room
+        T.block_len[a] = (indels && T.k[a] < Lb && T.k[a] < 16) ? Lb : 0;
     }
     // longest common prefix of the adapters (as code masks), capped at one 32-bit word
     int lcp = T.m[0];

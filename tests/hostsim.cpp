@@ -16,6 +16,8 @@
 
 using namespace orc;
 
+static uint64_t g_pairs[2], g_kept[2];
+extern "C" void hostsim_stats(uint64_t *out) { out[0] = g_pairs[0]; out[1] = g_kept[0]; out[2] = g_pairs[1]; out[3] = g_kept[1]; }
 extern "C" int hostsim_demux(int n_rounds,
                              int n_ad0, int type0, const char *const *seq0, double e0, int ov0, int rc0,
                              int n_ad1, int type1, const char *const *seq1, double e1, int ov1, int rc1,
@@ -90,6 +92,11 @@ extern "C" int hostsim_demux(int n_rounds,
                 const int a = lane % R.n_adapters, dir = lane / R.n_adapters;
                 const int o = dir ^ (int)(v.rc & 1u);
                 if (o == 1 && !R.revcomp) continue;
+                g_pairs[rd]++;
+                if (R.indels && !block_test(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr,
+                                            (const char *)&R.peq32b[0][0], lane, R.block_len[a], R.k[a], R.type,
+                                            R.kmax[a], R.min_ov[a], R.first_mask)) continue;
+                g_kept[rd]++;
                 LaneScan L;
                 scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, (const char *)&R.peq[0][0], lane,
                           R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, L,
