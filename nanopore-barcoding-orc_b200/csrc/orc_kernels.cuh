@@ -583,8 +583,9 @@ bin_place_kernel(const int32_t *__restrict__ bin, const uint32_t *__restrict__ r
 
 // Warp-cooperative copy of n bytes with arbitrary source and destination alignment: the
 // destination is written in aligned 32-bit words assembled from two aligned source words by a
-// funnel shift (head and tail bytes singly).  src may be over-read by up to 7 bytes (the blobs
-// have slack).
+// funnel shift (head and tail bytes singly).  The loads of two rounds (256 bytes per warp) are
+// issued before the first store, so that a warp keeps several requests in flight.  src may be
+// over-read by up to 7 bytes (the blobs have slack).
 __device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
                                           uint32_t n, int lane)
 {
@@ -595,13 +596,62 @@ __device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8
     const uint32_t sh = (uint32_t)((uintptr_t)sp & 3u) * 8u;
     const uint32_t *sa = reinterpret_cast<const uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
     uint32_t *da = reinterpret_cast<uint32_t *>(dst + head);
-    for (uint32_t w = lane; w < nw; w += 32) da[w] = __funnelshift_r(sa[w], sa[w + 1], sh);
+    for (uint32_t base = lane; base < nw; base += 64) {
+        const uint32_t w1 = base + 32u;
+        const bool two = w1 < nw;
+        const uint32_t a0 = sa[base], a1 = sa[base + 1];
+        uint32_t b0 = 0, b1 = 0;
+        if (two) { b0 = sa[w1]; b1 = sa[w1 + 1]; }
+        da[base] = __funnelshift_r(a0, a1, sh);
+        if (two) da[w1] = __funnelshift_r(b0, b1, sh);
+    }
     const uint32_t done = head + 4u * nw;
     if (done + (uint32_t)lane < n) dst[done + lane] = src[done + lane];
 }
 
+// The same in reverse: dst[i] = f(src[n - 1 - i]) with f = the complement table (bases) or the
+// identity (qualities, comp == nullptr).  Output word w holds the source bytes e, e-1, e-2, e-3
+// (e = n - 1 - head - 4w): an unaligned 4-byte window read as above, bytes swapped.
+__device__ __forceinline__ void warp_copy_rev(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                              uint32_t n, int lane, const uint8_t *comp)
+{
+    const uint32_t head = min(n, (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u));
+    if ((uint32_t)lane < head) {
+        const uint8_t b = src[n - 1 - lane];
+        dst[lane] = comp ? comp[b] : b;
+    }
+    const uint32_t nw = (n - head) >> 2;
+    uint32_t *da = reinterpret_cast<uint32_t *>(dst + head);
+    const uint8_t *top = src + (n - head);           // one past the source byte of output byte `head`
+    auto put = [&](uint32_t w, uint32_t x) {            // x = bytes src[e-3] .. src[e] of output word w
+        uint32_t y;
+        if (comp) y = (uint32_t)comp[x >> 24] | ((uint32_t)comp[(x >> 16) & 255u] << 8) |
+                      ((uint32_t)comp[(x >> 8) & 255u] << 16) | ((uint32_t)comp[x & 255u] << 24);
+        else y = __byte_perm(x, 0u, 0x0123u);
+        da[w] = y;
+    };
+    // all output words read the source at the same byte phase: (top - 4(w+1)) & 3 == top & 3
+    const uint32_t sh = (uint32_t)((uintptr_t)top & 3u) * 8u;
+    const uint32_t *ta = reinterpret_cast<const uint32_t *>((uintptr_t)top & ~(uintptr_t)3);
+    for (uint32_t base = lane; base < nw; base += 64) {
+        const uint32_t w1 = base + 32u;
+        const bool two = w1 < nw;
+        const uint32_t *pa = ta - (base + 1u);
+        const uint32_t a0 = pa[0], a1 = pa[1];
+        uint32_t b0 = 0, b1 = 0;
+        if (two) { b0 = pa[-32]; b1 = pa[-31]; }
+        put(base, __funnelshift_r(a0, a1, sh));
+        if (two) put(w1, __funnelshift_r(b0, b1, sh));
+    }
+    const uint32_t done = head + 4u * nw;
+    if (done + (uint32_t)lane < n) {
+        const uint8_t b = src[n - 1 - (done + lane)];
+        dst[done + lane] = comp ? comp[b] : b;
+    }
+}
+
 // One warp per read: '@' name [' rc']* '\n' seq '\n' '+' '\n' qual '\n'
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
             const uint8_t *__restrict__ names, const uint64_t *__restrict__ name_offsets,
             const uint32_t *__restrict__ name_lengths, const uint64_t *__restrict__ offsets,
@@ -634,10 +684,8 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
         const uint8_t *s = seq + v.lo;
         const uint8_t *q = qual + v.lo + (qual_offsets ? qual_offsets[r] - offsets[r] : 0ull);
         if (v.rc & 1u) {
-            for (uint32_t i = lane; i < L; i += 32) {
-                o[i] = comp[s[L - 1 - i]];
-                o[L + 3 + i] = q[L - 1 - i];
-            }
+            warp_copy_rev(o, s, L, lane, comp);
+            warp_copy_rev(o + L + 3, q, L, lane, nullptr);
         } else {
             warp_copy(o, s, L, lane);
             warp_copy(o + L + 3, q, L, lane);
