@@ -1080,28 +1080,53 @@ ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, co
     origin_out = origin;
 }
 
-// One scan over columns ws+1..we with R5 on the candidate columns jf..jl and, if the scan
-// reaches column n and r6 is set, R6 on the candidate rows.  Returns true on R5's early exit.
-ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, const uint64_t *peq_lane,
-                         const uint32_t *code4, const uint32_t *rcode4, int m, int type, int k, const uint8_t *kmax, int min_ov,
-                         int ws, int we, int jf, int jl, bool r6, int r6lo, int r6hi,
-                         Best &best, ColRing &R)
+// The resolver's state for one task.  The work is cut in two so that the kernel can bring the
+// lanes of a warp back together in between: resolve_begin() runs the column scan (lanes differ
+// in the number of columns), resolve_end() does the walks, which then start together.
+struct ResolveCtx {
+    const uint64_t *peq_lane;
+    const uint32_t *code4, *rcode4;
+    const uint8_t *kmax;
+    int32_t dir, m, k, min_ov, n, type;
+    int32_t has6, join, second;         // second: a separate scan of the last columns follows
+    int32_t r6lo, r6hi, ws6;
+    // the scan in progress
+    int32_t ws, we, jf, jl, r6, narrow, ubw, broke;
+    int32_t top_j, traced_j, traced_score, traced_origin;
+    Best best;
+};
+
+// Columns ws+1..we of one scan: the ring is filled, R5 runs on the candidate columns jf..jl.
+// Narrow hull: when all candidate columns lie within m/2 - 2k of each other, so do the origins
+// of any two candidates (origin is within k of j - m; a negative origin only ever helps the
+// second clause), and R5's update rule reduces to "the first acceptable candidate, then any with
+// a strictly higher score": the winner is the acceptable candidate of highest score, leftmost
+// among equals, in whatever order they are looked at.  Their walks are left to resolve_finish();
+// here only the candidate with the highest score bound is noted.  (The whole scan must still be
+// in the ring by then.)  Otherwise the walks happen on the spot, in column order.
+ORC_HD void resolve_columns(const uint32_t *W, uint64_t lo, uint32_t len, ResolveCtx &C, ColRing &R)
 {
-    const int n = (int)len;
+    const int m = C.m, n = C.n, k = C.k, ws = C.ws, we = C.we, jf = C.jf, jl = C.jl, dir = C.dir;
     const uint64_t pad = (m == 64) ? 0ull : ((1ull << (64 - m)) - 1ull);
     uint64_t Pv, Mv = 0;
     int D;
-    if (ws == 0 && type == TYPE_FRONT) { Pv = 0; D = 0; }       // R2, true column 0 of a 5' adapter
+    if (ws == 0 && C.type == TYPE_FRONT) { Pv = 0; D = 0; }     // R2, true column 0 of a 5' adapter
     else { Pv = ~pad; D = m; }                                  // cost i (true for BACK at 0; restart otherwise)
     R.pv[0] = Pv; R.mv[0] = 0; R.dm[0] = (int16_t)D;
-    int traced_j = -1, traced_score = 0, traced_origin = 0;
+    C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
+    C.narrow = (jf <= jl && (jl - jf) + 2 * k <= m / 2 && we - ws < RING) ? 1 : 0;
+    C.top_j = -1;
+    C.broke = 0;
+    int top_ub = -(1 << 20);
     // Upper bound of a candidate's score: every error costs at least 2 (score <= length - 2*cost),
     // except the errors a 3' adapter takes in column 0 (cost i, score 0: R2), reachable only if
     // the scan starts at the true column 0; then only score <= length - cost holds.
-    const int ubw = (ws == 0 && type == TYPE_BACK) ? 1 : 2;
+    C.ubw = (ws == 0 && C.type == TYPE_BACK) ? 1 : 2;
+    const int ubw = C.ubw;
+    const bool narrow = C.narrow != 0;
     for (int j = ws + 1; j <= we; j++) {
         const uint32_t raw = dir ? nib(W, (int64_t)lo + (int64_t)len - j) : nib(W, (int64_t)lo + j - 1);
-        const uint64_t Eq = peq_lane[raw * MAX_LANES];
+        const uint64_t Eq = C.peq_lane[raw * MAX_LANES];
         const uint64_t Xv = Eq | Mv;
         const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
         uint64_t Ph = Mv | ~(Xh | Pv);
@@ -1113,69 +1138,133 @@ ORC_HD bool resolve_scan(const uint32_t *W, uint64_t lo, uint32_t len, int dir, 
         { const int x = (j - ws) & (RING - 1); R.pv[x] = Pv; R.mv[x] = Mv; R.dm[x] = (int16_t)D; }
         if (j >= jf && j <= jl && D <= k) {
             const int lmax = imin(m, j + D);
-            if (lmax >= min_ov && D <= (int)kmax[lmax]) {
-                // a candidate that cannot beat the best so far cannot change it (every R5 update
-                // after the first needs a strictly higher score)
+            if (lmax >= C.min_ov && D <= (int)C.kmax[lmax]) {
                 const int ub = lmax - ubw * D;
-                if (best.cost == m + n + 1 || ub > best.score) {
+                if (narrow) {
+                    if (ub > top_ub) { top_ub = ub; C.top_j = j; }     // highest bound, leftmost
+                } else if (C.best.cost == m + n + 1 || ub > C.best.score) {
+                    // a candidate that cannot beat the best so far cannot change it (every R5
+                    // update after the first needs a strictly higher score)
                     Cell c;
                     c.cost = D;
-                    trace_back(W, lo, len, dir, peq_lane, code4, rcode4, m, type, ws, R, m, j, D, c.score, c.origin);
-                    traced_j = j; traced_score = c.score; traced_origin = c.origin;
-                    if (r5_update(best, m, n, c, j, min_ov, kmax)) return true;
+                    trace_back(W, lo, len, dir, C.peq_lane, C.code4, C.rcode4, m, C.type, ws, R, m, j, D, c.score, c.origin);
+                    C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin;
+                    if (r5_update(C.best, m, n, c, j, C.min_ov, C.kmax)) { C.broke = 1; return; }
                 }
             }
         }
     }
-    if (r6 && we == n && n > ws) {
+}
+
+// After resolve_columns(): the walks of a narrow hull, then R6 on the rows r6lo..r6hi of column
+// n if the scan reached it.
+ORC_HD void resolve_finish(const uint32_t *W, uint64_t lo, uint32_t len, ResolveCtx &C, ColRing &R)
+{
+    if (C.broke) return;
+    const int m = C.m, n = C.n, k = C.k, ws = C.ws, dir = C.dir, ubw = C.ubw;
+    Best &best = C.best;
+    if (C.narrow && C.top_j >= 0) {
+        auto look = [&](int j) {
+            const int Dj = (int)R.dm[(j - ws) & (RING - 1)];
+            Cell c;
+            c.cost = Dj;
+            trace_back(W, lo, len, dir, C.peq_lane, C.code4, C.rcode4, m, C.type, ws, R, m, j, Dj, c.score, c.origin);
+            if (j == n) { C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin; }
+            const int length = m + imin(c.origin, 0);
+            if (!(length >= C.min_ov && c.cost <= (int)C.kmax[length])) return;
+            if (best.cost == m + n + 1 || c.score > best.score || (c.score == best.score && j < best.query_stop)) {
+                best.score = c.score; best.cost = c.cost; best.origin = c.origin; best.ref_stop = m; best.query_stop = j;
+            }
+        };
+        // one loop for all of them, the noted one first, so that the lanes of a warp walk together
+        for (int q = C.jf - 1; q <= C.jl; q++) {
+            const int j = q < C.jf ? C.top_j : q;
+            if (q >= C.jf) {
+                if (j == C.top_j) continue;
+                const int Dj = (int)R.dm[(j - ws) & (RING - 1)];
+                if (Dj > k) continue;
+                const int lmax = imin(m, j + Dj);
+                if (!(lmax >= C.min_ov && Dj <= (int)C.kmax[lmax])) continue;
+                const int ub = lmax - ubw * Dj;
+                if (!(best.cost == m + n + 1 || ub > best.score || (ub == best.score && j < best.query_stop))) continue;
+            }
+            look(j);
+        }
+        if (best.cost == 0 && best.origin >= 0) { C.broke = 1; return; }       // R5's early exit
+    }
+    if (C.r6 && C.we == n && n > ws) {
         // R6: rows r6hi..r6lo of column n, top row first like cutadapt
-        for (int i = imin(r6hi, m); i >= imax(r6lo, 1); i--) {
+        for (int i = imin(C.r6hi, m); i >= imax(C.r6lo, 1); i--) {
             const int Di = ring_cost(R, m, i, n, ws);
             if (Di > k) continue;
-            const int lmax = (type == TYPE_FRONT) ? imin(i, n + Di) : i;
-            if (!(lmax >= min_ov && Di <= (int)kmax[lmax])) continue;
+            const int lmax = (C.type == TYPE_FRONT) ? imin(i, n + Di) : i;
+            if (!(lmax >= C.min_ov && Di <= (int)C.kmax[lmax])) continue;
             const int ub = lmax - ubw * Di;
             if (ub < best.score || (ub == best.score && Di >= best.cost)) continue;
             Cell c;
             c.cost = Di;
-            if (i == m && traced_j == n) { c.score = traced_score; c.origin = traced_origin; }
-            else trace_back(W, lo, len, dir, peq_lane, code4, rcode4, m, type, ws, R, i, n, Di, c.score, c.origin);
-            r6_update(best, n, c, i, min_ov, kmax);
+            if (i == m && C.traced_j == n) { c.score = C.traced_score; c.origin = C.traced_origin; }
+            else trace_back(W, lo, len, dir, C.peq_lane, C.code4, C.rcode4, m, C.type, ws, R, i, n, Di, c.score, c.origin);
+            r6_update(best, n, c, i, C.min_ov, C.kmax);
         }
     }
-    return false;
+}
+
+// First half of a task: set up, run the column scan.
+ORC_HD void resolve_begin(const uint32_t *W, const View &v, const RoundTable &T, const Task &t,
+                          ResolveCtx &C, ColRing &R)
+{
+    const int a = (int)t.lane % T.n_adapters;
+    C.dir = (int)t.lane / T.n_adapters;
+    C.m = T.m[a]; C.k = T.k[a]; C.min_ov = T.min_ov[a];
+    C.kmax = T.kmax[a];
+    C.peq_lane = &T.peq[0][t.lane];
+    C.code4 = T.code4[a]; C.rcode4 = T.rcode4[a];
+    C.n = (int)v.len;
+    C.type = T.type;
+    const int m = C.m, n = C.n, k = C.k;
+    C.best.ref_stop = m; C.best.query_stop = n; C.best.cost = m + n + 1; C.best.origin = 0; C.best.score = 0;
+    const bool has5 = t.jf <= t.jl;
+    const bool has6 = (T.type == TYPE_BACK) ? (t.i1 <= t.i2) : (has5 && t.jl == n);   // FRONT: only cell (m, n)
+    C.has6 = has6 ? 1 : 0;
+    C.r6lo = (T.type == TYPE_BACK) ? t.i1 : m;
+    C.r6hi = (T.type == TYPE_BACK) ? t.i2 : m;
+    C.ws6 = imax(0, n - C.r6hi - k - 1);
+    C.second = 0; C.join = 0; C.broke = 0; C.narrow = 0; C.top_j = -1; C.r6 = 0;
+    C.ws = 0; C.we = 0; C.jf = 1; C.jl = 0; C.ubw = 2;
+    C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
+    if (has5) {
+        C.ws = imax(0, t.jf - m - k - 1);
+        // run on to column n in the same scan when the last-column cells are close enough
+        const bool join = has6 && (C.ws6 <= t.jl + 1 || C.ws == 0 && C.ws6 == 0);
+        C.join = join ? 1 : 0;
+        C.second = (has6 && !join) ? 1 : 0;
+        C.we = join ? n : t.jl; C.jf = t.jf; C.jl = t.jl; C.r6 = join ? 1 : 0;
+        resolve_columns(W, v.lo, v.len, C, R);
+    } else if (has6) {
+        C.ws = C.ws6; C.we = n; C.jf = 1; C.jl = 0; C.r6 = 1;
+        resolve_columns(W, v.lo, v.len, C, R);
+    }
+}
+
+// Second half: the walks, the last-column cells, the result.
+ORC_HD void resolve_end(const uint32_t *W, const View &v, ResolveCtx &C, PairResult &res, ColRing &R)
+{
+    resolve_finish(W, v.lo, v.len, C, R);
+    if (C.second && !C.broke) {
+        C.ws = C.ws6; C.we = C.n; C.jf = 1; C.jl = 0; C.r6 = 1;
+        resolve_columns(W, v.lo, v.len, C, R);
+        resolve_finish(W, v.lo, v.len, C, R);
+    }
+    best_to_result(C.best, C.m, C.n, res);
 }
 
 ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, const Task &t,
                          PairResult &res, ColRing &R)
 {
-    const int a = (int)t.lane % T.n_adapters;
-    const int dir = (int)t.lane / T.n_adapters;
-    const int m = T.m[a], k = T.k[a], min_ov = T.min_ov[a];
-    const uint8_t *kmax = T.kmax[a];
-    const uint64_t *peq_lane = &T.peq[0][t.lane];
-    const int n = (int)v.len;
-    Best best;
-    best.ref_stop = m; best.query_stop = n; best.cost = m + n + 1; best.origin = 0; best.score = 0;
-    bool broke = false;
-    const bool has5 = t.jf <= t.jl;
-    const bool has6 = (T.type == TYPE_BACK) ? (t.i1 <= t.i2) : (has5 && t.jl == n);   // FRONT: only cell (m, n)
-    const int r6lo = (T.type == TYPE_BACK) ? t.i1 : m, r6hi = (T.type == TYPE_BACK) ? t.i2 : m;
-    const int ws6 = imax(0, n - r6hi - k - 1);
-    if (has5) {
-        const int ws = imax(0, t.jf - m - k - 1);
-        // run on to column n in the same scan when the last-column cells are close enough
-        const bool join = has6 && (ws6 <= t.jl + 1 || ws == 0 && ws6 == 0);
-        broke = resolve_scan(W, v.lo, v.len, dir, peq_lane, T.code4[a], T.rcode4[a], m, T.type, k, kmax, min_ov,
-                             ws, join ? n : t.jl, t.jf, t.jl, join, r6lo, r6hi, best, R);
-        if (!broke && has6 && !join)
-            resolve_scan(W, v.lo, v.len, dir, peq_lane, T.code4[a], T.rcode4[a], m, T.type, k, kmax, min_ov,
-                         ws6, n, 1, 0, true, r6lo, r6hi, best, R);
-    } else if (has6) {
-        resolve_scan(W, v.lo, v.len, dir, peq_lane, T.code4[a], T.rcode4[a], m, T.type, k, kmax, min_ov,
-                     ws6, n, 1, 0, true, r6lo, r6hi, best, R);
-    }
-    best_to_result(best, m, n, res);
+    ResolveCtx C;
+    resolve_begin(W, v, T, t, C, R);
+    resolve_end(W, v, C, res, R);
 }
 
 // ------------------------------------------------------------------------------------

@@ -351,19 +351,34 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     const RoundTable &T = *reinterpret_cast<const RoundTable *>(s_tab);
     const uint32_t n = *work_count;
     ColRing ring;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const Task task = work[t];
-        const View v = views[task.read];
-        PairResult res;
-        res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = 0;
-        res.score = res.errors = 0; res.pad_ = 0;
-        resolve_pair(W, v, T, task, res, ring);
-        results[task.slot] = res;
-        if (res.has) {
-            const int a = (int)task.lane % T.n_adapters;
-            const int o = ((int)task.lane / T.n_adapters) ^ (int)(v.rc & 1u);
-            atomicMax(best_key + (size_t)task.read * 2 + o,
-                      (unsigned long long)pack_key(res.score, res.errors, a, task.slot));
+    // every lane of a warp makes the same number of trips, so the warp can be brought back together
+    // between the column scan (lanes differ in length) and the walks (which then start together)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    for (uint32_t base = first; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t t = base + lane;
+        const bool act = t < n;
+        Task task;
+        View v;
+        ResolveCtx C;
+        if (act) {
+            task = work[t];
+            v = views[task.read];
+            resolve_begin(W, v, T, task, C, ring);
+        }
+        __syncwarp();
+        if (act) {
+            PairResult res;
+            res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = 0;
+            res.score = res.errors = 0; res.pad_ = 0;
+            resolve_end(W, v, C, res, ring);
+            results[task.slot] = res;
+            if (res.has) {
+                const int a = (int)task.lane % T.n_adapters;
+                const int o = ((int)task.lane / T.n_adapters) ^ (int)(v.rc & 1u);
+                atomicMax(best_key + (size_t)task.read * 2 + o,
+                          (unsigned long long)pack_key(res.score, res.errors, a, task.slot));
+            }
         }
     }
 }
