@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -260,7 +261,11 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel, SCAN_THREADS, 0));
     ctx->filter_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_kernel, 128, 0));
-    if (occ > 6) occ = 6;       // more resident threads only thrash the per-thread ring (measured)
+    {   // more resident threads can thrash the per-thread ring in L1/L2 (ORC_RESOLVE_OCC: tuning knob)
+        const char *e = getenv("ORC_RESOLVE_OCC");
+        const int cap = e ? atoi(e) : 6;
+        if (cap > 0 && occ > cap) occ = cap;
+    }
     ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     {
         uint32_t *nk = nullptr;

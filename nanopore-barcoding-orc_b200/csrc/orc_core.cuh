@@ -30,6 +30,13 @@
 #else
 #define ORC_HD inline
 #endif
+// "does any lane of the group still want to go on?" -- a warp vote on the device, which also
+// brings the lanes of `mask` back together at this point; the single-lane answer on the host.
+#if defined(__CUDA_ARCH__)
+#define ORC_ANY(mask, p) (__any_sync((mask), (p)) != 0)
+#else
+#define ORC_ANY(mask, p) (p)
+#endif
 
 namespace orc {
 
@@ -1012,20 +1019,19 @@ ORC_HD uint64_t pack_key(int score, int errors, int adapter, uint32_t slot)
 constexpr int RING = 128;            // >= m + k + 2 for every supported adapter (k < m <= 64)
 struct ColRing {
     uint64_t pv[RING], mv[RING];
-    int16_t dm[RING];
 };
 
 // The ring is indexed by the column's distance from the scan start ws: the lanes of a warp
 // scan in lockstep, so they touch the same slot at the same time and the lane-interleaved
 // local memory sees one coalesced access per column instead of 32 scattered ones.
-// D[i][j] of a stored column j, i in 0..m
+// D[i][j] of a stored column j, i in 0..m: row 0 costs 0 in every column, so the cost is the sum
+// of the vertical deltas of rows 1..i (the padding bits below row 1 are clear in both words).
 ORC_HD int ring_cost(const ColRing &R, int m, int i, int j, int ws)
 {
-    const int sh = 64 - m + i;                      // bits of the rows i+1..m start here
+    if (i <= 0) return 0;
     const int x = (j - ws) & (RING - 1);
-    if (sh >= 64) return R.dm[x];
-    const uint64_t pv = R.pv[x] >> sh, mv = R.mv[x] >> sh;
-    return (int)R.dm[x] - popc64(pv) + popc64(mv);
+    const int sh = m - i;                           // drops rows i+1..m off the top
+    return popc64(R.pv[x] << sh) - popc64(R.mv[x] << sh);
 }
 
 // Walk cutadapt's path back from cell (i, j) whose cost is d.  ws is the first stored
@@ -1080,6 +1086,49 @@ ORC_HD void trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir, co
     origin_out = origin;
 }
 
+// trace_back() for a group of lanes that walk at the same time (all lanes of `mask` call this,
+// `on` says which of them have a walk to do): every trip of the loop starts with a vote, so the
+// lanes take their steps side by side instead of drifting apart at the first branch.
+ORC_HD void trace_back_group(uint32_t mask, bool on, const uint32_t *W, uint64_t lo, uint32_t len, int dir,
+                             const uint32_t *code4, const uint32_t *rcode4,
+                             int m, int type, int ws, const ColRing &R, int i, int j, int d,
+                             int &score_out, int &origin_out)
+{
+    int score = 0, origin = 0;
+    while (ORC_ANY(mask, on)) {
+        if (on) {
+            if (i == 0) { origin = j; on = false; }                  // row 0 (R3)
+            else if (j == 0) { origin = (type == TYPE_FRONT) ? -i : 0; on = false; }   // column 0 (R2)
+            else if (j <= ws) { origin = j; on = false; }            // unreachable for a genuine candidate
+            else {
+                const int avail = imin(16, imin(i, j - ws));
+                const uint64_t r = nib16(W, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
+                const uint64_t a = nib16(dir ? rcode4 : code4, dir ? (int64_t)(m - i) : (int64_t)i);
+                uint64_t x = r & a;
+                x |= x >> 1; x |= x >> 2;
+                uint64_t mis = ~x & 0x1111111111111111ull;
+                if (dir) mis = brev64(mis);
+                const int run = imin(clz64(mis) >> 2, avail);
+                score += run; i -= run; j -= run;
+                if (run < avail) {                                   // a mismatch cell inside the matrix
+                    const int bit = 64 - m + i - 1;
+                    const uint64_t pvj = R.pv[(j - ws) & (RING - 1)], mvj = R.mv[(j - ws) & (RING - 1)];
+                    const uint64_t pvl = R.pv[(j - 1 - ws) & (RING - 1)], mvl = R.mv[(j - 1 - ws) & (RING - 1)];
+                    const int d_up = d - (int)((pvj >> bit) & 1u) + (int)((mvj >> bit) & 1u);
+                    const int d_left = ring_cost(R, m, i, j - 1, ws);
+                    const int d_diag = d_left - (int)((pvl >> bit) & 1u) + (int)((mvl >> bit) & 1u);
+                    const int c_diag = d_diag + 1, c_del = d_left + 1, c_ins = d_up + 1;
+                    if (c_diag <= c_del && c_diag <= c_ins) { score -= 1; --i; --j; d = d_diag; }
+                    else if (c_ins <= c_del) { score -= 2; --i; d = d_up; }
+                    else { score -= 2; --j; d = d_left; }
+                }
+            }
+        }
+    }
+    score_out = score;
+    origin_out = origin;
+}
+
 // The resolver's state for one task.  The work is cut in two so that the kernel can bring the
 // lanes of a warp back together in between: resolve_begin() runs the column scan (lanes differ
 // in the number of columns), resolve_end() does the walks, which then start together.
@@ -1087,7 +1136,7 @@ struct ResolveCtx {
     const uint64_t *peq_lane;
     const uint32_t *code4, *rcode4;
     const uint8_t *kmax;
-    int32_t dir, m, k, min_ov, n, type;
+    int32_t dir, lane, m, k, min_ov, n, type;
     int32_t has6, join, second;         // second: a separate scan of the last columns follows
     int32_t r6lo, r6hi, ws6;
     // the scan in progress
@@ -1109,10 +1158,9 @@ ORC_HD void resolve_columns(const uint32_t *W, uint64_t lo, uint32_t len, Resolv
     const int m = C.m, n = C.n, k = C.k, ws = C.ws, we = C.we, jf = C.jf, jl = C.jl, dir = C.dir;
     const uint64_t pad = (m == 64) ? 0ull : ((1ull << (64 - m)) - 1ull);
     uint64_t Pv, Mv = 0;
-    int D;
-    if (ws == 0 && C.type == TYPE_FRONT) { Pv = 0; D = 0; }     // R2, true column 0 of a 5' adapter
-    else { Pv = ~pad; D = m; }                                  // cost i (true for BACK at 0; restart otherwise)
-    R.pv[0] = Pv; R.mv[0] = 0; R.dm[0] = (int16_t)D;
+    if (ws == 0 && C.type == TYPE_FRONT) Pv = 0;                // R2, true column 0 of a 5' adapter
+    else Pv = ~pad;                                             // cost i (true for BACK at 0; restart otherwise)
+    R.pv[0] = Pv; R.mv[0] = 0;
     C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
     C.narrow = (jf <= jl && (jl - jf) + 2 * k <= m / 2 && we - ws < RING) ? 1 : 0;
     C.top_j = -1;
@@ -1124,32 +1172,71 @@ ORC_HD void resolve_columns(const uint32_t *W, uint64_t lo, uint32_t len, Resolv
     C.ubw = (ws == 0 && C.type == TYPE_BACK) ? 1 : 2;
     const int ubw = C.ubw;
     const bool narrow = C.narrow != 0;
-    for (int j = ws + 1; j <= we; j++) {
-        const uint32_t raw = dir ? nib(W, (int64_t)lo + (int64_t)len - j) : nib(W, (int64_t)lo + j - 1);
-        const uint64_t Eq = C.peq_lane[raw * MAX_LANES];
-        const uint64_t Xv = Eq | Mv;
-        const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-        uint64_t Ph = Mv | ~(Xh | Pv);
-        uint64_t Mh = Pv & Xh;
-        D += (int)(Ph >> 63) - (int)(Mh >> 63);
-        Ph <<= 1; Mh <<= 1;
-        Pv = Mh | ~(Xv | Ph);
-        Mv = Ph & Xv;
-        { const int x = (j - ws) & (RING - 1); R.pv[x] = Pv; R.mv[x] = Mv; R.dm[x] = (int16_t)D; }
-        if (j >= jf && j <= jl && D <= k) {
-            const int lmax = imin(m, j + D);
-            if (lmax >= C.min_ov && D <= (int)C.kmax[lmax]) {
-                const int ub = lmax - ubw * D;
-                if (narrow) {
-                    if (ub > top_ub) { top_ub = ub; C.top_j = j; }     // highest bound, leftmost
-                } else if (C.best.cost == m + n + 1 || ub > C.best.score) {
-                    // a candidate that cannot beat the best so far cannot change it (every R5
-                    // update after the first needs a strictly higher score)
-                    Cell c;
-                    c.cost = D;
-                    trace_back(W, lo, len, dir, C.peq_lane, C.code4, C.rcode4, m, C.type, ws, R, m, j, D, c.score, c.origin);
-                    C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin;
-                    if (r5_update(C.best, m, n, c, j, C.min_ov, C.kmax)) { C.broke = 1; return; }
+    // eight columns per packed word, table address by PRMT, as in scan_window
+    const char *peq_base = reinterpret_cast<const char *>(C.peq_lane - C.lane);
+    const uint32_t lane8 = (uint32_t)C.lane * 8u;
+    uint32_t sel0, sel1, sel2, sel3;
+    if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
+    else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
+    ChunkReader rd;
+    rd.init(W, lo, len, dir, (uint32_t)ws);
+    const int ncols = we - ws;
+    const int nchunks = (ncols + 7) >> 3;
+    for (int q = 0; q < nchunks; q++) {
+        uint32_t A, B;
+        rd.next(A, B);
+        const int ncol = imin(8, ncols - 8 * q);
+        const int jb = ws + 8 * q;                              // this chunk: columns jb+1 .. jb+ncol
+        if (ncol == 8 && (jb + 8 < jf || jb + 1 > jl)) {
+            // no candidate column in here: just the recurrence and the ring
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const uint32_t src = (t & 1) ? B : A;
+                const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+                const uint64_t Eq = *reinterpret_cast<const uint64_t *>(peq_base + byte_perm(src, lane8, sel));
+                const uint64_t Xv = Eq | Mv;
+                const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                uint64_t Ph = Mv | ~(Xh | Pv);
+                uint64_t Mh = Pv & Xh;
+                Ph <<= 1; Mh <<= 1;
+                Pv = Mh | ~(Xv | Ph);
+                Mv = Ph & Xv;
+                const int x = (8 * q + t + 1) & (RING - 1);
+                R.pv[x] = Pv; R.mv[x] = Mv;
+            }
+            continue;
+        }
+        int D = popc64(Pv) - popc64(Mv);                        // D[m][jb]
+#pragma unroll 1
+        for (int t = 0; t < ncol; t++) {
+            const int j = jb + t + 1;
+            const uint32_t src = (t & 1) ? B : A;
+            const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+            const uint64_t Eq = *reinterpret_cast<const uint64_t *>(peq_base + byte_perm(src, lane8, sel));
+            const uint64_t Xv = Eq | Mv;
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint64_t Ph = Mv | ~(Xh | Pv);
+            uint64_t Mh = Pv & Xh;
+            D += (int)(Ph >> 63) - (int)(Mh >> 63);
+            Ph <<= 1; Mh <<= 1;
+            Pv = Mh | ~(Xv | Ph);
+            Mv = Ph & Xv;
+            { const int x = (j - ws) & (RING - 1); R.pv[x] = Pv; R.mv[x] = Mv; }
+            if (j >= jf && j <= jl && D <= k) {
+                const int lmax = imin(m, j + D);
+                if (lmax >= C.min_ov && D <= (int)C.kmax[lmax]) {
+                    const int ub = lmax - ubw * D;
+                    if (narrow) {
+                        if (ub > top_ub) { top_ub = ub; C.top_j = j; }     // highest bound, leftmost
+                    } else if (C.best.cost == m + n + 1 || ub > C.best.score) {
+                        // a candidate that cannot beat the best so far cannot change it (every R5
+                        // update after the first needs a strictly higher score)
+                        Cell c;
+                        c.cost = D;
+                        trace_back(W, lo, len, dir, C.peq_lane, C.code4, C.rcode4, m, C.type, ws, R, m, j, D, c.score, c.origin);
+                        C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin;
+                        if (r5_update(C.best, m, n, c, j, C.min_ov, C.kmax)) { C.broke = 1; return; }
+                    }
                 }
             }
         }
@@ -1158,40 +1245,48 @@ ORC_HD void resolve_columns(const uint32_t *W, uint64_t lo, uint32_t len, Resolv
 
 // After resolve_columns(): the walks of a narrow hull, then R6 on the rows r6lo..r6hi of column
 // n if the scan reached it.
-ORC_HD void resolve_finish(const uint32_t *W, uint64_t lo, uint32_t len, ResolveCtx &C, ColRing &R)
+ORC_HD void resolve_finish(const uint32_t *W, uint64_t lo, uint32_t len, ResolveCtx &C, ColRing &R,
+                           uint32_t mask, bool grouped)
 {
-    if (C.broke) return;
     const int m = C.m, n = C.n, k = C.k, ws = C.ws, dir = C.dir, ubw = C.ubw;
     Best &best = C.best;
-    if (C.narrow && C.top_j >= 0) {
-        auto look = [&](int j) {
-            const int Dj = (int)R.dm[(j - ws) & (RING - 1)];
+    if (grouped) {
+        // The walks of a narrow hull, the noted candidate first.  All lanes of `mask` are here;
+        // each picks its next candidate worth a walk (none: it only keeps voting), then they walk
+        // together, until no lane has one left.
+        bool more = !C.broke && C.narrow && C.top_j >= 0;
+        int q = C.jf - 1;
+        while (ORC_ANY(mask, more)) {
+            int j = 0, Dj = 0;
+            bool have = false;
+            if (more) {
+                for (; q <= C.jl && !have; q++) {
+                    j = q < C.jf ? C.top_j : q;
+                    Dj = ring_cost(R, m, m, j, ws);
+                    if (q < C.jf) { have = true; continue; }
+                    if (j == C.top_j || Dj > k) continue;
+                    const int lmax = imin(m, j + Dj);
+                    if (!(lmax >= C.min_ov && Dj <= (int)C.kmax[lmax])) continue;
+                    const int ub = lmax - ubw * Dj;
+                    have = best.cost == m + n + 1 || ub > best.score || (ub == best.score && j < best.query_stop);
+                }
+                if (!have) more = false;
+            }
             Cell c;
-            c.cost = Dj;
-            trace_back(W, lo, len, dir, C.peq_lane, C.code4, C.rcode4, m, C.type, ws, R, m, j, Dj, c.score, c.origin);
-            if (j == n) { C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin; }
-            const int length = m + imin(c.origin, 0);
-            if (!(length >= C.min_ov && c.cost <= (int)C.kmax[length])) return;
-            if (best.cost == m + n + 1 || c.score > best.score || (c.score == best.score && j < best.query_stop)) {
-                best.score = c.score; best.cost = c.cost; best.origin = c.origin; best.ref_stop = m; best.query_stop = j;
+            c.cost = Dj; c.score = 0; c.origin = 0;
+            trace_back_group(mask, have, W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, m, j, Dj, c.score, c.origin);
+            if (have) {
+                if (j == n) { C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin; }
+                const int length = m + imin(c.origin, 0);
+                if (length >= C.min_ov && c.cost <= (int)C.kmax[length] &&
+                    (best.cost == m + n + 1 || c.score > best.score || (c.score == best.score && j < best.query_stop))) {
+                    best.score = c.score; best.cost = c.cost; best.origin = c.origin; best.ref_stop = m; best.query_stop = j;
+                }
             }
-        };
-        // one loop for all of them, the noted one first, so that the lanes of a warp walk together
-        for (int q = C.jf - 1; q <= C.jl; q++) {
-            const int j = q < C.jf ? C.top_j : q;
-            if (q >= C.jf) {
-                if (j == C.top_j) continue;
-                const int Dj = (int)R.dm[(j - ws) & (RING - 1)];
-                if (Dj > k) continue;
-                const int lmax = imin(m, j + Dj);
-                if (!(lmax >= C.min_ov && Dj <= (int)C.kmax[lmax])) continue;
-                const int ub = lmax - ubw * Dj;
-                if (!(best.cost == m + n + 1 || ub > best.score || (ub == best.score && j < best.query_stop))) continue;
-            }
-            look(j);
         }
-        if (best.cost == 0 && best.origin >= 0) { C.broke = 1; return; }       // R5's early exit
+        if (!C.broke && C.narrow && best.cost == 0 && best.origin >= 0) C.broke = 1;     // R5's early exit
     }
+    if (C.broke) return;
     if (C.r6 && C.we == n && n > ws) {
         // R6: rows r6hi..r6lo of column n, top row first like cutadapt
         for (int i = imin(C.r6hi, m); i >= imax(C.r6lo, 1); i--) {
@@ -1219,6 +1314,7 @@ ORC_HD void resolve_begin(const uint32_t *W, const View &v, const RoundTable &T,
     C.m = T.m[a]; C.k = T.k[a]; C.min_ov = T.min_ov[a];
     C.kmax = T.kmax[a];
     C.peq_lane = &T.peq[0][t.lane];
+    C.lane = (int)t.lane;
     C.code4 = T.code4[a]; C.rcode4 = T.rcode4[a];
     C.n = (int)v.len;
     C.type = T.type;
@@ -1248,13 +1344,14 @@ ORC_HD void resolve_begin(const uint32_t *W, const View &v, const RoundTable &T,
 }
 
 // Second half: the walks, the last-column cells, the result.
-ORC_HD void resolve_end(const uint32_t *W, const View &v, ResolveCtx &C, PairResult &res, ColRing &R)
+ORC_HD void resolve_end(const uint32_t *W, const View &v, ResolveCtx &C, PairResult &res, ColRing &R,
+                        uint32_t mask = 0xffffffffu)
 {
-    resolve_finish(W, v.lo, v.len, C, R);
+    resolve_finish(W, v.lo, v.len, C, R, mask, true);
     if (C.second && !C.broke) {
         C.ws = C.ws6; C.we = C.n; C.jf = 1; C.jl = 0; C.r6 = 1;
         resolve_columns(W, v.lo, v.len, C, R);
-        resolve_finish(W, v.lo, v.len, C, R);
+        resolve_finish(W, v.lo, v.len, C, R, mask, false);      // no R5 candidates in this scan
     }
     best_to_result(C.best, C.m, C.n, res);
 }

@@ -366,12 +366,12 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
             v = views[task.read];
             resolve_begin(W, v, T, task, C, ring);
         }
-        __syncwarp();
+        const uint32_t mask = __ballot_sync(0xffffffffu, act);      // also the meeting point
         if (act) {
             PairResult res;
             res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = 0;
             res.score = res.errors = 0; res.pad_ = 0;
-            resolve_end(W, v, C, res, ring);
+            resolve_end(W, v, C, res, ring, mask);
             results[task.slot] = res;
             if (res.has) {
                 const int a = (int)task.lane % T.n_adapters;
