@@ -275,7 +275,7 @@ constexpr int MAX_WIN = 3;
 struct WinList {                    // windows of one (read, direction), increasing, disjoint
     uint32_t n;
     uint32_t s[MAX_WIN], e[MAX_WIN];   // columns s+1 .. e are scanned; s == 0 is the true column 0
-    uint32_t pad_;
+    uint32_t flags;                    // bit 0: a last-column cell (i, n) with i <= 32 may be a candidate (3' rounds)
 };
 
 ORC_HD uint32_t funnel_l1(uint32_t acc, uint32_t top)   // (acc << 1) | (top >> 31)
@@ -313,25 +313,32 @@ ORC_HD int chunk_min(const uint8_t *lut, uint32_t accP, uint32_t accM, int D, in
 // codes: A holds positions p, p+2, p+4, p+6 and B holds p+1, p+3, p+5, p+7, in the byte order
 // that the lane's PRMT selectors expect (reversed for direction 1).
 struct ChunkReader {
-    const uint32_t *W;
-    int64_t s;          // storage index of the lowest-addressed code of the current chunk
-    int64_t step;
-    uint32_t shA, shB;
+    // Eight codes per step, one packed word apart: the bit offset inside the word never changes
+    // and consecutive steps share a word, so a step costs one load and one funnel shift.
+    const uint32_t *p;  // the word after (direction 0) / before (direction 1) the ones held
+    uint32_t lo_, hi_;  // the two words the current chunk straddles
+    uint32_t sh, shA, shB;
+    int32_t dir_;
     ORC_HD void init(const uint32_t *W_, uint64_t lo, uint32_t len, int dir, uint32_t p0)
     {
-        W = W_;
-        s = dir ? (int64_t)lo + (int64_t)len - 8 - (int64_t)p0 : (int64_t)lo + (int64_t)p0;
-        step = dir ? -8 : 8;
+        // storage index of the lowest-addressed code of the first chunk
+        const int64_t s = dir ? (int64_t)lo + (int64_t)len - 8 - (int64_t)p0 : (int64_t)lo + (int64_t)p0;
+        const uint32_t *w = W_ + (s >> 3);
+        sh = (uint32_t)(s & 7) * 4u;
         shA = dir ? 4u : 0u;
         shB = dir ? 0u : 4u;
+        dir_ = dir;
+        if (!dir) { hi_ = w[0]; p = w + 1; }        // next(): lo_ <- hi_, hi_ <- *p++
+        else      { lo_ = w[1]; p = w; }            // next(): hi_ <- lo_, lo_ <- *p--
     }
     ORC_HD void next(uint32_t &A, uint32_t &B)
     {
-        const int64_t wi = s >> 3;
-        const uint32_t x = funnel_r(W[wi], W[wi + 1], (uint32_t)(s & 7) * 4u);
+        const uint32_t nw = *p;
+        if (!dir_) { lo_ = hi_; hi_ = nw; p += 1; }
+        else       { hi_ = lo_; lo_ = nw; p -= 1; }
+        const uint32_t x = funnel_r(lo_, hi_, sh);
         A = (x >> shA) & 0x0F0F0F0Fu;
         B = (x >> shB) & 0x0F0F0F0Fu;
-        s += step;
     }
 };
 
@@ -361,7 +368,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                          const uint8_t *lut = nullptr)
 {
     const uint32_t n = len;
-    out.n = 0; out.pad_ = 0;
+    out.n = 0; out.flags = 0;
     for (int i = 0; i < MAX_WIN; i++) { out.s[i] = 0; out.e[i] = 0; }
     bool open = false;
     uint32_t cs = 0, ce = 0;
@@ -574,6 +581,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     for (int c = 0; c < n_clu; c++) add_cluster(clu_fs[c], clu_ls[c], true);
     if (type == TYPE_BACK) {
         uint32_t ePv = Pv, eMv = Mv;    // prefix rows 1..Lp of the last column
+        bool r6_near = !sp;             // prefix-primary rounds: not tracked, assume yes
         if (sp) {
             // prefix scan of the last m_max + 2k + 1 columns (restart: exact for every alignment
             // that can still reach the read end as a partial adapter)
@@ -584,6 +592,8 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
             ePv = ~ppad; eMv = 0;
             int eD = Lp;
             uint32_t first_trig = 0;
+            // a cell (i, n) with Lp < i <= 32 is reached through row Lp within 32 - Lp + k columns of n
+            const uint32_t jr6 = n > (uint32_t)(32 - Lp + kt) ? n - (uint32_t)(32 - Lp + kt) : 0u;
             ChunkReader re;
             re.init(W, lo, len, dir, s1);
             for (uint32_t c0 = s1; c0 < n; c0 += 8) {
@@ -606,6 +616,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                         eMv = Ph & Xv;
                         const uint32_t j = c0 + (uint32_t)t + 1u;
                         if (eD <= kt && j >= jmin && first_trig == 0) first_trig = j;
+                        if (eD <= kt && j >= jr6) r6_near = true;
                     }
                 }
             }
@@ -631,6 +642,10 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
             const uint32_t r = (uint32_t)(Lp + kt + 1);
             win_add(out, open, cs, ce, n > r ? n - r : 0u, n);
         }
+        // stage 2a looks at the last-column rows i <= 32 of each adapter only if one of them can be
+        // a candidate: a shared row (need), or a row further down reached through a prefix trigger
+        // close to the read end
+        if (need || r6_near) out.flags |= 1u;
     }
     if (open) { out.s[out.n] = cs; out.e[out.n] = ce; out.n++; }
 }
@@ -743,7 +758,7 @@ ORC_HD bool block_test(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len
             }
             D = Dend;
         }
-        if (type == TYPE_BACK && e == n) {
+        if (type == TYPE_BACK && e == n && (wl == nullptr || (wl->flags & 1u))) {
             // R6's necessary condition for the cells (i, n), i <= Lb (as in scan_window)
             int cum = 0;
             for (int i = 1; i <= Lb; i++) {

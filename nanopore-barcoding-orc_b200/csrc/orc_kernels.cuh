@@ -126,7 +126,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     const uint32_t r = valid ? (order ? order[pr] : pr) : 0u;
     const int Lp = s_par[0], kt = s_par[1], m_max = s_par[2], type = s_par[3];
     WinList wl;
-    wl.n = 0; wl.pad_ = 0;
+    wl.n = 0; wl.flags = 0;
     for (int i = 0; i < MAX_WIN; i++) { wl.s[i] = 0; wl.e[i] = 0; }
     uint32_t cols = 0;
     const bool skip = !valid || (prev != nullptr && prev[r].adapter < 0);
@@ -142,6 +142,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                 cols = win_columns(wl);
             } else {
                 wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything
+                wl.flags = 1u;                               // ... and test the last-column rows too
                 cols = v.len;
             }
             // an item without any column to scan has no candidate cell (R6's last-column cells are
