@@ -62,7 +62,8 @@ struct Slot {
     uint32_t *d_jobs = nullptr;              // stage 2a survivors: job numbers (item * n_adapters + adapter)
     PairResult *d_results = nullptr;
     uint32_t *d_counters = nullptr;          // [0..1] work counters, [2..3] task counts
-    unsigned long long *d_cells = nullptr;   // [0..1] sum of view lengths entering each round, [2..3] window columns
+    unsigned long long *d_cells = nullptr;   // [0..1] sum of view lengths entering each round, [2..3] window columns,
+                                             // [4..5] cells stage 2b updated (rows x columns of the pairs that passed 2a)
     int32_t *d_bin = nullptr;
     uint32_t *d_out_len = nullptr, *d_rec_bytes = nullptr, *d_hist_cnt = nullptr;
     uint64_t *d_hist_bytes = nullptr, *d_bin_counts = nullptr, *d_bin_offsets = nullptr, *d_bin_bytes = nullptr;
@@ -143,7 +144,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_jobs, 2 * R * MAX_AD));
     CK(dalloc(&s.d_results, n_tasks));
     CK(dalloc(&s.d_counters, 16));
-    CK(dalloc(&s.d_cells, 4));
+    CK(dalloc(&s.d_cells, 6));
     CK(dalloc(&s.d_bin, R));
     CK(dalloc(&s.d_out_len, R));
     CK(dalloc(&s.d_rec_bytes, R));
@@ -156,7 +157,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(halloc(&s.h_bin, R));
     CK(halloc(&s.h_out_len, R));
     CK(halloc(&s.h_counters, 16));
-    CK(halloc(&s.h_cells, 4));
+    CK(halloc(&s.h_cells, 6));
     CK(halloc(&s.h_bin_counts, (size_t)ctx->n_bins));
     CK(halloc(&s.h_bin_offsets, (size_t)ctx->n_bins + 1));
     if (ctx->want_matches)
@@ -407,7 +408,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     uint32_t *W = s.d_codes_alloc + GUARD_WORDS;
     cudaStream_t st = s.stream;
     CK(cudaMemsetAsync(s.d_counters, 0, 16 * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(s.d_cells, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(s.d_cells, 0, 6 * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));       // kernels start here (re-recorded when launched alone)
     s.did_h2d = s.fresh_upload;                  // h2d_ms is only meaningful right after an upload
     s.fresh_upload = false;
@@ -460,7 +461,8 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             const bool prefilter = ctx->h_tab[r].indels != 0;
             if (prefilter)
                 filter_kernel<<<ctx->filter_blocks, SCAN_THREADS, 0, st>>>(
-                    ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_jobs, cnt);
+                    ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_jobs, cnt,
+                    s.d_cells + 4 + r);
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_results,
                 s.d_tasks, s.d_best_key, cnt, prefilter ? s.d_jobs : nullptr);
@@ -536,7 +538,7 @@ extern "C" int orc_download(orc_ctx *ctx, int slot)
     CK(cudaMemcpyAsync(s.h_bin_counts, s.d_bin_counts, sizeof(uint64_t) * ctx->n_bins, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_bin_offsets, s.d_bin_offsets, sizeof(uint64_t) * (ctx->n_bins + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_HDR], st));
     if (n) {
         CK(cudaMemcpyAsync(s.h_bin, s.d_bin, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
@@ -624,7 +626,7 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     if (s.did_d2h) CK(el(EV_EMIT, EV_END, &t->d2h_ms));
     // counters need a device read when the caller never downloaded
     uint32_t counters[16];
-    unsigned long long cells[4];
+    unsigned long long cells[6];
     CK(cudaMemcpy(counters, s.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cells, s.d_cells, sizeof(cells), cudaMemcpyDeviceToHost));
     uint64_t emit_bytes = 0;
@@ -652,10 +654,15 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
         for (int a = 0; a < T.n_adapters; a++) msum += (uint64_t)T.m[a];
         const uint64_t bases = (r == 0) ? s.in_bases : (uint64_t)cells[1];
         t->cells[r] = (T.revcomp ? 2ull : 1ull) * msum * bases;
-        // cells actually updated: stage 1 (Lp rows, every column, both directions) + stage 2 (every
-        // adapter's m rows over the window columns)
-        t->cells_executed[r] = (T.use_filter ? (uint64_t)T.lcp * (T.revcomp ? 2ull : 1ull) * bases : 0ull) +
-                               msum * (uint64_t)cells[2 + r];
+        // cells actually updated: stage 1 (the shared flank's rows, every column, both directions) +
+        // stage 2a (every adapter's block rows over the window columns) + stage 2b (the m rows of
+        // the pairs that passed); without stage 2a every adapter's m rows over the window columns
+        uint64_t bsum = 0;
+        for (int a = 0; a < T.n_adapters; a++) bsum += (uint64_t)(T.m[a] < 32 ? T.m[a] : 32);
+        const uint64_t rows1 = (uint64_t)(T.sfx_primary ? T.lcs : T.lcp);
+        t->cells_executed[r] = (T.use_filter ? rows1 * (T.revcomp ? 2ull : 1ull) * bases : 0ull) +
+                               (T.indels ? bsum * (uint64_t)cells[2 + r] + (uint64_t)cells[4 + r]
+                                         : msum * (uint64_t)cells[2 + r]);
     }
     t->pack_bytes = s.n_bytes + s.n_bytes / 2;
     t->emit_bytes = 2 * emit_bytes;    // every FASTQ byte is read once and written once

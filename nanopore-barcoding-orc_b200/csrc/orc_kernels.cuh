@@ -170,12 +170,13 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
               const View *__restrict__ views, const WinList *__restrict__ wins,
               const uint32_t *__restrict__ wcols_sorted, const uint32_t *__restrict__ item_order,
-              uint32_t n_items, uint32_t *__restrict__ jobs, uint32_t *__restrict__ counters)
+              uint32_t n_items, uint32_t *__restrict__ jobs, uint32_t *__restrict__ counters,
+              unsigned long long *__restrict__ cells_2b)
 {
     __shared__ __align__(16) uint32_t s_peq32b[16][64];
     __shared__ uint32_t s_first_mask[MAX_M + 32];
     __shared__ uint8_t s_kmax[MAX_AD][MAX_M + 8];
-    __shared__ int s_k[MAX_AD], s_min_ov[MAX_AD], s_lb[MAX_AD];
+    __shared__ int s_k[MAX_AD], s_min_ov[MAX_AD], s_lb[MAX_AD], s_m[MAX_AD];
     __shared__ int s_na, s_type;
     for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32b[0][0])[i] = (&tab->peq32b[0][0])[i];
     for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_mask[i] = tab->first_mask[i];
@@ -185,6 +186,7 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
         s_k[threadIdx.x] = tab->k[threadIdx.x];
         s_min_ov[threadIdx.x] = tab->min_ov[threadIdx.x];
         s_lb[threadIdx.x] = tab->block_len[threadIdx.x];
+        s_m[threadIdx.x] = tab->m[threadIdx.x];
     }
     if (threadIdx.x == 0) { s_na = tab->n_adapters; s_type = tab->type; }
     __syncthreads();
@@ -225,6 +227,9 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
         }
         const uint32_t mk = __ballot_sync(0xffffffffu, keep);
         if (mk) {
+            // cells stage 2b will update for these pairs (the roofline's executed-cells figure)
+            const uint32_t c2 = __reduce_add_sync(0xffffffffu, keep ? wcols_sorted[it] * (uint32_t)s_m[a] : 0u);
+            if (lane == 0) atomicAdd(cells_2b, (unsigned long long)c2);
             uint32_t ob = 0;
             if (lane == 0) ob = atomicAdd(n_out, (uint32_t)__popc(mk));
             ob = __shfl_sync(0xffffffffu, ob, 0);
