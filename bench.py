@@ -26,7 +26,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -53,7 +52,7 @@ SCAN_DRAM_BYTES_PER_READ = 2.367e3
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1 << 20)
@@ -76,55 +75,60 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled by
+    a thread every millisecond (the timed region is tens of milliseconds, far shorter than one
+    `nvidia-smi -lms` period); the device is found by UUID so CUDA_VISIBLE_DEVICES does not matter."""
+    NAMES = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+             ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+             ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+             ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.h = None
+        self.sm, self.bits, self.power = [], 0, []
+        self._stop = threading.Event()
+        self.t = None
+        try:
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = nv
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:          # no NVML: say so in the line instead of inventing clocks
+            self.h = None
+            self.why = "NVML unavailable: %s" % e
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.why]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        reasons = [nm for nm, attr in self.NAMES if self.bits & int(getattr(self.nv, attr))]
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def hbm_peak():

@@ -177,6 +177,55 @@ int64_t orc_fastq_index(const uint8_t *text, uint64_t n_bytes, uint32_t max_read
                         uint64_t *name_offsets, uint32_t *name_lengths, uint64_t *consumed,
                         char *err, size_t err_len);
 
+/*
+ * Host-side FASTQ(.gz) streaming (csrc/orc_io.cpp): the reader -> workers -> ordered-writer
+ * plumbing cutadapt's ParallelPipelineRunner, dnaio and xopen provide around the matching
+ * (02_cutadapt_loop.sh:64-72 `-j 24`, input IN.fastq.gz, outputs {name}_<ds>.fastq.gz).
+ *
+ * Reader: a thread inflates `path` ("-" = stdin; gzip or plain) into a ring of n_buffers text
+ * buffers (page-locked when pinned != 0 and a CUDA device is present) and indexes the records.
+ * orc_reader_next() hands out the next batch in the raw-text layout of orc_batch (returns 1, or
+ * 0 at the end of the input, or a negative ORC_E* code: text in orc_reader_error()); the batch
+ * stays valid until its `buffer` is given back with orc_reader_release().
+ */
+typedef struct orc_reader orc_reader;
+typedef struct orc_text_batch {
+    uint8_t *text;                  /* the first n_bytes bytes are n_reads complete records */
+    uint64_t n_bytes;
+    uint32_t n_reads;
+    int32_t buffer;                 /* ring slot, for orc_reader_release() */
+    uint64_t *offsets;              /* [n_reads] start of the bases inside text */
+    uint32_t *lengths;              /* [n_reads] */
+    uint64_t *qual_offsets;         /* [n_reads] */
+    uint64_t *name_offsets;         /* [n_reads] header without '@' */
+    uint32_t *name_lengths;         /* [n_reads] */
+    uint64_t total_bases;
+} orc_text_batch;
+
+orc_reader *orc_reader_open(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
+                            int pinned, char *err, size_t err_len);
+int orc_reader_next(orc_reader *r, orc_text_batch *out);
+int orc_reader_release(orc_reader *r, int buffer);
+const char *orc_reader_error(orc_reader *r);
+void orc_reader_close(orc_reader *r);
+
+/*
+ * Writer: one file per bin (paths[b] == NULL: bin not written), all created by orc_writer_open()
+ * even if they stay empty (the reference's round-2 loop lists them, 02_cutadapt_loop.sh:75-85);
+ * a path ending in ".gz" is written as gzip members of `level`, deflated by `threads` workers.
+ * orc_writer_write() queues the bin-major FASTQ text of one batch (orc_result.fastq /
+ * bin_offsets) and returns a ticket >= 0 at once; the text must stay untouched until
+ * orc_writer_wait(ticket) returns.  Files receive their batches in submission order.
+ * orc_writer_close() drains, closes the files and optionally reports the uncompressed bytes per bin.
+ */
+typedef struct orc_writer orc_writer;
+orc_writer *orc_writer_open(const char *const *paths, int n_bins, int level, int threads, char *err,
+                            size_t err_len);
+int64_t orc_writer_write(orc_writer *w, const uint8_t *fastq, const uint64_t *bin_offsets);
+int orc_writer_wait(orc_writer *w, int64_t ticket);
+const char *orc_writer_error(orc_writer *w);
+int orc_writer_close(orc_writer *w, uint64_t *bytes_per_bin);
+
 /* pinned host memory for callers that do not bring their own */
 void *orc_host_alloc(size_t bytes);
 void orc_host_free(void *p);

@@ -1,0 +1,519 @@
+// orc_io.cpp -- host-side FASTQ(.gz) streaming of liborcdemux.so: what dnaio's C parser and
+// xopen's gzip pipes do under cutadapt (the reader -> workers -> ordered
+// writer of cutadapt's ParallelPipelineRunner, /root/reference/scripts/02_cutadapt_loop.sh:64-72
+// `-j 24`).
+//
+//   orc_reader   one thread inflates the input straight into a ring of page-locked text buffers
+//                and indexes the records (orc_fastq_index); the text itself is the batch that
+//                goes to the GPU (raw-text layout of orc_batch), so the host never copies a read.
+//   orc_writer   one output file per bin; the bin-major FASTQ text of a batch is cut into
+//                chunks, a thread pool deflates them as independent gzip members and every file
+//                receives its members in submission order (a concatenation of gzip members is a
+//                valid .gz stream; the decompressed bytes are what the reference's tools read).
+//
+// No matching arithmetic lives here: bytes in, bytes out.
+#include "../../include/orcdemux.h"
+
+#include <cuda_runtime_api.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+void set_err(char *err, size_t err_len, const std::string &s)
+{
+    if (err && err_len) snprintf(err, err_len, "%s", s.c_str());
+}
+
+void *host_alloc(size_t bytes, bool want_pinned, bool *pinned)
+{
+    void *p = nullptr;
+    *pinned = false;
+    if (want_pinned && cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess) {
+        *pinned = true;
+        return p;
+    }
+    cudaGetLastError();                 // page-locking is an optimisation of the copies only
+    if (posix_memalign(&p, 4096, bytes ? bytes : 1) != 0) return nullptr;
+    return p;
+}
+
+void host_free(void *p, bool pinned)
+{
+    if (!p) return;
+    if (pinned) cudaFreeHost(p);
+    else free(p);
+}
+
+struct ReaderBuf {
+    uint8_t *text = nullptr;
+    uint64_t *off = nullptr, *qoff = nullptr, *noff = nullptr;
+    uint32_t *len = nullptr, *nlen = nullptr;
+    bool pinned[6] = {false, false, false, false, false, false};
+    uint64_t n_bytes = 0, bases = 0;
+    uint32_t n_reads = 0;
+};
+
+}  // namespace
+
+struct orc_reader {
+    gzFile gz = nullptr;
+    uint32_t max_reads = 0;
+    uint64_t max_bytes = 0;
+    std::vector<ReaderBuf> bufs;
+    std::deque<int> free_q, ready_q;
+    std::mutex mu;
+    std::condition_variable cv_free, cv_ready;
+    std::thread th;
+    bool stop = false, done = false;
+    int error = 0;
+    std::string err;
+    std::vector<uint8_t> carry;
+
+    void fail(const std::string &what)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        error = ORC_EINVAL;
+        err = what;
+        done = true;
+        cv_ready.notify_all();
+    }
+
+    void finish()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        done = true;
+        cv_ready.notify_all();
+    }
+
+    void run()
+    {
+        bool eof = false;
+        for (;;) {
+            int b;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_free.wait(lk, [&] { return stop || !free_q.empty(); });
+                if (stop) return;
+                b = free_q.front();
+                free_q.pop_front();
+            }
+            ReaderBuf &rb = bufs[b];
+            uint64_t fill = carry.size();
+            if (fill) memcpy(rb.text, carry.data(), fill);
+            carry.clear();
+            while (fill < max_bytes && !eof) {
+                uint64_t want = max_bytes - fill;
+                if (want > (1u << 30)) want = 1u << 30;
+                int got = gzread(gz, rb.text + fill, (unsigned)want);
+                if (got < 0) {
+                    int zerr = 0;
+                    const char *msg = gzerror(gz, &zerr);
+                    return fail(std::string("reading the input: ") + (msg ? msg : "gzread failed"));
+                }
+                if (got == 0) {
+                    int zerr = Z_OK;
+                    const char *msg = gzerror(gz, &zerr);       // a truncated .gz ends "cleanly" with Z_BUF_ERROR
+                    if (zerr != Z_OK && zerr != Z_STREAM_END)
+                        return fail(std::string("reading the input: ") + (msg && *msg ? msg : "truncated gzip stream"));
+                    eof = true;
+                }
+                fill += (uint64_t)got;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (stop) return;
+                }
+            }
+            if (fill == 0) return finish();
+            uint64_t consumed = 0;
+            char ebuf[256] = {0};
+            int64_t n = orc_fastq_index(rb.text, fill, max_reads, eof ? 1 : 0, rb.off, rb.len, rb.qoff, rb.noff,
+                                        rb.nlen, &consumed, ebuf, sizeof ebuf);
+            if (n < 0) return fail(ebuf);
+            if (n == 0) {
+                if (eof) return finish();       // nothing but blank lines
+                return fail("FASTQ record larger than the batch buffer");
+            }
+            carry.assign(rb.text + consumed, rb.text + fill);
+            rb.n_bytes = consumed;
+            rb.n_reads = (uint32_t)n;
+            uint64_t bases = 0;
+            for (int64_t i = 0; i < n; i++) bases += rb.len[i];
+            rb.bases = bases;
+            bool last = eof && carry.empty();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready_q.push_back(b);
+                if (last) done = true;
+                cv_ready.notify_all();
+            }
+            if (last) return;
+        }
+    }
+};
+
+extern "C" orc_reader *orc_reader_open(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
+                                       int pinned, char *err, size_t err_len)
+{
+    if (!path || !max_reads || max_bytes < 16 || n_buffers < 1 || n_buffers > 64) {
+        set_err(err, err_len, "orc_reader_open: bad argument");
+        return nullptr;
+    }
+    orc_reader *r = new orc_reader();
+    r->max_reads = max_reads;
+    r->max_bytes = max_bytes;
+    if (strcmp(path, "-") == 0) r->gz = gzdopen(dup(0), "rb");
+    else r->gz = gzopen(path, "rb");        // transparent for files that are not gzip
+    if (!r->gz) {
+        set_err(err, err_len, std::string("cannot open ") + path + ": " + strerror(errno));
+        delete r;
+        return nullptr;
+    }
+    gzbuffer(r->gz, 1u << 20);
+    r->bufs.resize(n_buffers);
+    bool ok = true;
+    for (int b = 0; b < n_buffers && ok; b++) {
+        ReaderBuf &rb = r->bufs[b];
+        rb.text = (uint8_t *)host_alloc(max_bytes, pinned != 0, &rb.pinned[0]);
+        rb.off = (uint64_t *)host_alloc(8ull * max_reads, pinned != 0, &rb.pinned[1]);
+        rb.qoff = (uint64_t *)host_alloc(8ull * max_reads, pinned != 0, &rb.pinned[2]);
+        rb.noff = (uint64_t *)host_alloc(8ull * max_reads, pinned != 0, &rb.pinned[3]);
+        rb.len = (uint32_t *)host_alloc(4ull * max_reads, pinned != 0, &rb.pinned[4]);
+        rb.nlen = (uint32_t *)host_alloc(4ull * max_reads, pinned != 0, &rb.pinned[5]);
+        ok = rb.text && rb.off && rb.qoff && rb.noff && rb.len && rb.nlen;
+        r->free_q.push_back(b);
+    }
+    if (!ok) {
+        set_err(err, err_len, "orc_reader_open: out of host memory");
+        orc_reader_close(r);
+        return nullptr;
+    }
+    r->th = std::thread([r] { r->run(); });
+    return r;
+}
+
+extern "C" int orc_reader_next(orc_reader *r, orc_text_batch *out)
+{
+    if (!r || !out) return ORC_EINVAL;
+    std::unique_lock<std::mutex> lk(r->mu);
+    r->cv_ready.wait(lk, [&] { return !r->ready_q.empty() || r->done; });
+    if (r->ready_q.empty()) return r->error ? r->error : 0;
+    int b = r->ready_q.front();
+    r->ready_q.pop_front();
+    const ReaderBuf &rb = r->bufs[b];
+    out->text = rb.text;
+    out->n_bytes = rb.n_bytes;
+    out->n_reads = rb.n_reads;
+    out->buffer = b;
+    out->offsets = rb.off;
+    out->lengths = rb.len;
+    out->qual_offsets = rb.qoff;
+    out->name_offsets = rb.noff;
+    out->name_lengths = rb.nlen;
+    out->total_bases = rb.bases;
+    return 1;
+}
+
+extern "C" int orc_reader_release(orc_reader *r, int buffer)
+{
+    if (!r || buffer < 0 || buffer >= (int)r->bufs.size()) return ORC_EINVAL;
+    std::lock_guard<std::mutex> lk(r->mu);
+    for (int b : r->free_q) if (b == buffer) return ORC_ESTATE;
+    for (int b : r->ready_q) if (b == buffer) return ORC_ESTATE;
+    r->free_q.push_back(buffer);
+    r->cv_free.notify_all();
+    return ORC_OK;
+}
+
+extern "C" const char *orc_reader_error(orc_reader *r)
+{
+    return r ? r->err.c_str() : "null reader";
+}
+
+extern "C" void orc_reader_close(orc_reader *r)
+{
+    if (!r) return;
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        r->stop = true;
+        r->cv_free.notify_all();
+    }
+    if (r->th.joinable()) r->th.join();
+    if (r->gz) gzclose(r->gz);
+    for (ReaderBuf &rb : r->bufs) {
+        host_free(rb.text, rb.pinned[0]);
+        host_free(rb.off, rb.pinned[1]);
+        host_free(rb.qoff, rb.pinned[2]);
+        host_free(rb.noff, rb.pinned[3]);
+        host_free(rb.len, rb.pinned[4]);
+        host_free(rb.nlen, rb.pinned[5]);
+    }
+    delete r;
+}
+
+// ------------------------------------------------------------------------------------ writer
+
+namespace {
+
+struct Chunk {
+    int bin = 0;
+    const uint8_t *src = nullptr;
+    size_t len = 0;
+    int64_t ticket = 0;
+    uint8_t *out = nullptr;         // deflated member (or nullptr for plain files: src is copied)
+    size_t out_len = 0;
+    bool done = false;
+};
+
+struct BinFile {
+    int fd = -1;
+    bool gz = false;
+    bool writing = false;           // one thread at a time appends to the file
+    uint64_t bytes_in = 0;
+    std::deque<Chunk *> q;          // submission order == file order
+};
+
+}  // namespace
+
+struct orc_writer {
+    std::vector<BinFile> bins;
+    int level = 5;
+    size_t chunk_bytes = 4u << 20;
+    std::vector<std::thread> pool;
+    std::deque<Chunk *> tasks;
+    std::mutex mu;
+    std::condition_variable cv_task, cv_done;
+    bool stop = false;
+    int error = 0;
+    std::string err;
+    int64_t next_ticket = 0;
+    std::deque<int64_t> pending;    // chunks of ticket (first_ticket + i) not yet deflated
+    int64_t first_ticket = 0;
+    size_t unwritten = 0;           // chunks not yet in their file
+
+    void set_error(const std::string &what)
+    {
+        if (!error) {
+            error = ORC_EINVAL;
+            err = what;
+        }
+    }
+
+    bool deflate_chunk(z_stream &zs, bool &zs_ready, Chunk *c, std::string &why)
+    {
+        if (!zs_ready) {
+            memset(&zs, 0, sizeof zs);
+            if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+                why = "deflateInit2 failed";
+                return false;
+            }
+            zs_ready = true;
+        } else {
+            deflateReset(&zs);
+        }
+        size_t bound = deflateBound(&zs, (uLong)c->len) + 64;
+        c->out = (uint8_t *)malloc(bound);
+        if (!c->out) {
+            why = "out of memory";
+            return false;
+        }
+        zs.next_in = const_cast<Bytef *>(c->src);
+        zs.avail_in = (uInt)c->len;
+        zs.next_out = c->out;
+        zs.avail_out = (uInt)bound;
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) {
+            why = "deflate failed";
+            return false;
+        }
+        c->out_len = bound - zs.avail_out;
+        return true;
+    }
+
+    static bool write_all(int fd, const uint8_t *p, size_t n)
+    {
+        while (n) {
+            ssize_t w = ::write(fd, p, n);
+            if (w < 0) {
+                if (errno == EINTR) continue;
+                return false;
+            }
+            p += w;
+            n -= (size_t)w;
+        }
+        return true;
+    }
+
+    void worker()
+    {
+        z_stream zs;
+        bool zs_ready = false;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_task.wait(lk, [&] { return stop || !tasks.empty(); });
+            if (tasks.empty()) break;       // stop is only set once everything is written
+            Chunk *c = tasks.front();
+            tasks.pop_front();
+            BinFile &bf = bins[c->bin];
+            lk.unlock();
+            std::string why;
+            bool ok = true;
+            if (bf.gz) {
+                ok = deflate_chunk(zs, zs_ready, c, why);
+            } else {
+                c->out = (uint8_t *)malloc(c->len ? c->len : 1);
+                ok = c->out != nullptr;
+                if (ok) memcpy(c->out, c->src, c->len);
+                else why = "out of memory";
+                c->out_len = c->len;
+            }
+            lk.lock();
+            if (!ok) set_error(why);
+            c->done = true;
+            pending[(size_t)(c->ticket - first_ticket)]--;      // the source bytes are no longer needed
+            cv_done.notify_all();
+            if (!bf.writing) {
+                bf.writing = true;
+                while (!bf.q.empty() && bf.q.front()->done) {
+                    Chunk *w = bf.q.front();
+                    bf.q.pop_front();
+                    lk.unlock();
+                    bool wok = !w->out || write_all(bf.fd, w->out, w->out_len);
+                    free(w->out);
+                    lk.lock();
+                    if (!wok) set_error(std::string("write failed: ") + strerror(errno));
+                    delete w;
+                    unwritten--;
+                }
+                bf.writing = false;
+                cv_done.notify_all();
+            }
+        }
+        lk.unlock();
+        if (zs_ready) deflateEnd(&zs);
+    }
+};
+
+extern "C" orc_writer *orc_writer_open(const char *const *paths, int n_bins, int level, int threads, char *err,
+                                       size_t err_len)
+{
+    if (!paths || n_bins < 1 || level < 0 || level > 9) {
+        set_err(err, err_len, "orc_writer_open: bad argument");
+        return nullptr;
+    }
+    orc_writer *w = new orc_writer();
+    w->level = level;
+    w->bins.resize(n_bins);
+    for (int b = 0; b < n_bins; b++) {
+        if (!paths[b]) continue;
+        // created up front even if the bin stays empty: the reference's round-2 loop lists them
+        // (02_cutadapt_loop.sh:75-85)
+        int fd = open(paths[b], O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) {
+            set_err(err, err_len, std::string("cannot create ") + paths[b] + ": " + strerror(errno));
+            for (BinFile &bf : w->bins) if (bf.fd >= 0) close(bf.fd);
+            delete w;
+            return nullptr;
+        }
+        size_t n = strlen(paths[b]);
+        w->bins[b].fd = fd;
+        w->bins[b].gz = n >= 3 && strcmp(paths[b] + n - 3, ".gz") == 0;
+    }
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    for (int t = 0; t < threads; t++) w->pool.emplace_back([w] { w->worker(); });
+    return w;
+}
+
+extern "C" int64_t orc_writer_write(orc_writer *w, const uint8_t *fastq, const uint64_t *bin_offsets)
+{
+    if (!w || !bin_offsets) return ORC_EINVAL;
+    std::lock_guard<std::mutex> lk(w->mu);
+    if (w->error) return w->error;
+    int64_t ticket = w->next_ticket++;
+    w->pending.push_back(0);
+    for (size_t b = 0; b < w->bins.size(); b++) {
+        BinFile &bf = w->bins[b];
+        if (bf.fd < 0) continue;
+        uint64_t lo = bin_offsets[b], hi = bin_offsets[b + 1];
+        if (hi <= lo) continue;
+        if (!fastq) return ORC_EINVAL;
+        bf.bytes_in += hi - lo;
+        for (uint64_t p = lo; p < hi; p += w->chunk_bytes) {
+            Chunk *c = new Chunk();
+            c->bin = (int)b;
+            c->src = fastq + p;
+            c->len = (size_t)((hi - p < w->chunk_bytes) ? hi - p : w->chunk_bytes);
+            c->ticket = ticket;
+            bf.q.push_back(c);
+            w->tasks.push_back(c);
+            w->pending.back()++;
+            w->unwritten++;
+        }
+    }
+    w->cv_task.notify_all();
+    return ticket;
+}
+
+extern "C" int orc_writer_wait(orc_writer *w, int64_t ticket)
+{
+    if (!w) return ORC_EINVAL;
+    std::unique_lock<std::mutex> lk(w->mu);
+    if (ticket < 0 || ticket >= w->next_ticket) return ORC_EINVAL;
+    if (ticket >= w->first_ticket)
+        w->cv_done.wait(lk, [&] { return w->pending[(size_t)(ticket - w->first_ticket)] == 0; });
+    while (!w->pending.empty() && w->pending.front() == 0 && w->first_ticket < w->next_ticket) {
+        w->pending.pop_front();
+        w->first_ticket++;
+    }
+    return w->error;
+}
+
+extern "C" const char *orc_writer_error(orc_writer *w)
+{
+    return w ? w->err.c_str() : "null writer";
+}
+
+extern "C" int orc_writer_close(orc_writer *w, uint64_t *bytes_per_bin)
+{
+    if (!w) return ORC_EINVAL;
+    {
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv_done.wait(lk, [&] { return w->unwritten == 0; });
+        w->stop = true;
+        w->cv_task.notify_all();
+    }
+    for (std::thread &t : w->pool) t.join();
+    int rc = w->error;
+    for (size_t b = 0; b < w->bins.size(); b++) {
+        BinFile &bf = w->bins[b];
+        if (bytes_per_bin) bytes_per_bin[b] = bf.bytes_in;
+        if (bf.fd < 0) continue;
+        if (bf.gz && bf.bytes_in == 0) {
+            // an empty but valid .gz, as xopen leaves for a bin without reads
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            uint8_t out[64];
+            if (deflateInit2(&zs, w->level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) == Z_OK) {
+                zs.next_out = out;
+                zs.avail_out = sizeof out;
+                deflate(&zs, Z_FINISH);
+                if (!orc_writer::write_all(bf.fd, out, sizeof out - zs.avail_out)) rc = ORC_EINVAL;
+                deflateEnd(&zs);
+            }
+        }
+        if (close(bf.fd) != 0 && !rc) rc = ORC_EINVAL;
+    }
+    delete w;
+    return rc;
+}

@@ -218,6 +218,41 @@ class EndStats:
         return out
 
 
+def _batch_shape():
+    """(reads, bytes) of one batch; ORCDEMUX_BATCH_READS shrinks it (tests, small-memory hosts)."""
+    reads = int(os.environ.get("ORCDEMUX_BATCH_READS", 1 << 18))
+    if reads < 1:
+        raise Unsupported("ORCDEMUX_BATCH_READS must be positive")
+    return reads, max(1 << 20, min(1 << 28, reads * 4096))
+
+
+def _stream(reader, eng, writers, slots, on_result):
+    """reader -> GPU -> writers with `slots` batches between the stages: while batch k is on the
+    GPU the bins of batches k-1 and k-2 are being deflated and the reader inflates k+1, k+2.
+    A slot is submitted again only after the writer has let go of its result buffers."""
+    tickets = [None] * slots
+    pending = []
+
+    def drain(slot, tb):
+        res = eng.wait(slot, copy=False)
+        on_result(res, tb)
+        tickets[slot] = writers.write_batch(res)
+
+    k = 0
+    for tb in reader:
+        slot = k % slots
+        if tickets[slot] is not None:
+            writers.wait(tickets[slot])
+            tickets[slot] = None
+        eng.submit(slot, tb)
+        pending.append((slot, tb))
+        if len(pending) > 1:
+            drain(*pending.pop(0))
+        k += 1
+    while pending:
+        drain(*pending.pop(0))
+
+
 def run_single_round(opt, argv, device=0) -> int:
     kind = ORC_FRONT if opt["g"] else ORC_BACK
     names, seqs, anchored = _parse_adapter_specs(opt["g"] or opt["a"], kind)
@@ -227,41 +262,37 @@ def run_single_round(opt, argv, device=0) -> int:
         kind = ORC_PREFIX if kind == ORC_FRONT else ORC_SUFFIX
     rnd = E.Round(names, seqs, kind, opt["e"], opt["O"], opt["indels"], opt["rc"])
     t0 = time.time()
-    max_reads, max_bytes, slots = 1 << 18, 1 << 28, 2
-    reader = F.FastqReader(opt["inputs"][0], max_reads, max_bytes, n_buffers=slots + 2)
+    (max_reads, max_bytes), slots = _batch_shape(), 3
+    threads = max(2, min(os.cpu_count() or 2, opt["cores"] if opt["cores"] > 0 else (os.cpu_count() or 2)))
+    reader = F.FastqReader(opt["inputs"][0], max_reads, max_bytes, keep=3, ahead=2)
     paths = [opt["out"].replace("{name}", "unknown")] + [opt["out"].replace("{name}", n) for n in names]
-    writers = F.BinWriters(paths, opt["level"], threads=max(2, min(16, opt["cores"])))
+    writers = F.BinWriters(paths, opt["level"], threads=threads)
     n_in = bp_in = bp_out = n_with = n_rc = 0
     per = np.zeros(len(names), dtype=np.int64)
     stats = EndStats(names, seqs, kind, opt["e"], opt["indels"], opt["rc"])
+
+    def on_result(res, tb):
+        nonlocal n_in, bp_in, bp_out, n_with, n_rc, per
+        m = res.matches[0]
+        n_in += res.n_reads
+        bp_in += tb.total_bases()
+        bp_out += int(res.out_len.sum(dtype=np.uint64))
+        has = m["adapter"] >= 0
+        n_with += int(has.sum())
+        n_rc += int((m["is_rc"] != 0).sum())
+        per += np.bincount(m["adapter"][has], minlength=len(names))
+        stats.add(m, tb.lengths[:res.n_reads])
+
     try:
         with E.Engine([rnd], device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
                       emit_fastq=True, want_matches=True) as eng:
-            def drain(slot, tb):
-                nonlocal n_in, bp_in, bp_out, n_with, n_rc, per
-                res = eng.wait(slot, copy=False)
-                m = res.matches[0]
-                n_in += res.n_reads
-                bp_in += tb.total_bases()
-                bp_out += int(res.out_len.sum(dtype=np.uint64))
-                has = m["adapter"] >= 0
-                n_with += int(has.sum())
-                n_rc += int((m["is_rc"] != 0).sum())
-                per += np.bincount(m["adapter"][has], minlength=len(names))
-                stats.add(m, tb.lengths[:res.n_reads])
-                writers.write_batch(res)
-            inflight = []
-            k = 0
-            for tb in reader:
-                if len(inflight) == slots:
-                    drain(*inflight.pop(0))
-                eng.submit(k % slots, tb)
-                inflight.append((k % slots, tb))
-                k += 1
-            while inflight:
-                drain(*inflight.pop(0))
+            try:
+                _stream(reader, eng, writers, slots, on_result)
+            finally:
+                writers.close()         # drains: the result buffers belong to the engine
     finally:
         writers.close()
+        reader.close()
     rep = _report(n_in, bp_in, bp_out, n_with, n_rc, names, per, time.time() - t0, argv)
     rep["input"]["path1"] = opt["inputs"][0]
     rep["adapters_read1"] = stats.as_json(n_in)
@@ -327,31 +358,27 @@ def run_two_round(args: List[str], device=0) -> int:
             drop[b] = 1
             continue
         paths[b] = os.path.join(outdir, "SP27", "%s_%s_%s%s" % (nm27, nm5, ds, ext))
-    max_reads, max_bytes, slots = 1 << 18, 1 << 28, 2
-    reader = F.FastqReader(a.input, max_reads, max_bytes, n_buffers=slots + 2)
-    writers = F.BinWriters(paths, 5, threads=max(2, min(16, a.j)))
+    (max_reads, max_bytes), slots = _batch_shape(), 3
+    reader = F.FastqReader(a.input, max_reads, max_bytes, keep=3, ahead=2)
+    writers = F.BinWriters(paths, 5, threads=max(2, min(os.cpu_count() or 2, a.j)))
     t0 = time.time()
     n_in = 0
+
+    def on_result(res, tb):
+        nonlocal n_in
+        n_in += res.n_reads
+
     try:
         with E.Engine(rounds, device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
                       emit_fastq=True, want_matches=False, drop_bins=drop) as eng:
-            inflight = []
-            k = 0
-            for tb in reader:
-                if len(inflight) == slots:
-                    res = eng.wait(inflight.pop(0), copy=False)
-                    n_in += res.n_reads
-                    writers.write_batch(res)
-                eng.submit(k % slots, tb)
-                inflight.append(k % slots)
-                k += 1
-            while inflight:
-                res = eng.wait(inflight.pop(0), copy=False)
-                n_in += res.n_reads
-                writers.write_batch(res)
+            try:
+                _stream(reader, eng, writers, slots, on_result)
+            finally:
+                writers.close()         # drains: the result buffers belong to the engine
             counts = eng.counts()
     finally:
         writers.close()
+        reader.close()
     with open(os.path.join(outdir, "SP27", "orcdemux_%s.json" % ds), "w") as fh:
         json.dump({"dataset": ds, "reads": n_in, "elapsed_seconds": time.time() - t0,
                    "bins": {os.path.basename(p): int(counts[b]) for b, p in enumerate(paths) if p}}, fh, indent=1)

@@ -1,20 +1,17 @@
 """FASTQ(.gz) streaming in and out (what dnaio + xopen do under cutadapt).
 
-Reader: the file is read (inflated) straight into a ring of pinned text buffers; the record
-boundaries are found by orc_fastq_index() in liborcdemux.so (C, memchr); the raw text itself
-is the batch that goes to the GPU (orc_batch raw-text layout), so no per-read copies are made
-on the host.  Writer: one file per bin, created up front even if it stays empty (the
-reference's round-2 loop discovers its inputs by listing them, 02_cutadapt_loop.sh:75-85);
-gzip members are compressed by a thread pool, one bin per task, batch order preserved.
+Both directions are native (csrc/orc_io.cpp inside liborcdemux.so); this module only wraps them.
+Reader: a thread inflates the file straight into a ring of pinned text buffers and finds the
+record boundaries (orc_fastq_index, memchr); the raw text itself is the batch that goes to the
+GPU (orc_batch raw-text layout), so no per-read copies are made on the host.  Writer: one file
+per bin, created up front even if it stays empty (the reference's round-2 loop discovers its
+inputs by listing them, 02_cutadapt_loop.sh:75-85); the bins' text is cut into chunks that a
+thread pool deflates as gzip members, written in batch order.
 """
 from __future__ import annotations
 
 import ctypes as C
-import gzip
 import os
-import sys
-import zlib
-from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Iterator, List, Optional
 
@@ -42,7 +39,8 @@ class TextBatch:
         return (t[n0:n0 + nl].tobytes().decode(), t[o:o + L].tobytes().decode(), t[q:q + L].tobytes().decode())
 
     def total_bases(self) -> int:
-        return int(self.lengths[:self.n_reads].sum(dtype=np.uint64))
+        b = getattr(self, "bases", None)
+        return b if b is not None else int(self.lengths[:self.n_reads].sum(dtype=np.uint64))
 
 
 def _pinned(n: int, dtype) -> np.ndarray:
@@ -66,117 +64,112 @@ def index_text(text: np.ndarray, n_bytes: int, max_reads: int, final: bool, arra
     return int(n), int(consumed.value), arrays
 
 
-def open_maybe_gzip(path: str):
-    if path == "-":
-        return sys.stdin.buffer
-    with open(path, "rb") as fh:
-        magic = fh.read(2)
-    if magic == b"\x1f\x8b":
-        return gzip.open(path, "rb")
-    return open(path, "rb", buffering=0)
+def _view(ptr, count, dtype):
+    dt = np.dtype(dtype)
+    if not ptr or count == 0:
+        return np.zeros(0, dtype=dt)
+    buf = (C.c_uint8 * (count * dt.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=count)
 
 
 class FastqReader:
-    """Iterates over TextBatch objects.  `n_buffers` batches stay valid at any time: a batch may
-    be handed to the GPU while the next ones are being read (use n_buffers >= slots + 1)."""
+    """Iterates over TextBatch objects produced by liborcdemux.so's reader thread (orc_reader_*,
+    csrc/orc_io.cpp): the input is inflated and indexed ahead of the consumer, straight into
+    page-locked buffers.  The `keep` most recent batches (the one just returned included) stay
+    valid; older ones go back to the reader, which owns `keep + ahead` buffers."""
 
-    def __init__(self, path: str, max_reads: int = 1 << 18, max_bytes: int = 1 << 28, n_buffers: int = 4):
-        self.path = path
-        self.max_reads = max_reads
-        self.max_bytes = max_bytes
-        self.n_buffers = n_buffers
-        self._bufs = [_pinned(max_bytes, np.uint8) for _ in range(n_buffers)]
-        self._idx = [(_pinned(max_reads, np.uint64), _pinned(max_reads, np.uint32), _pinned(max_reads, np.uint64),
-                      _pinned(max_reads, np.uint64), _pinned(max_reads, np.uint32)) for _ in range(n_buffers)]
+    def __init__(self, path: str, max_reads: int = 1 << 18, max_bytes: int = 1 << 28, keep: int = 3,
+                 ahead: int = 2, pinned: bool = True):
+        self._L = _lib.load()
+        self.path, self.max_reads, self.max_bytes, self.keep = path, max_reads, max_bytes, max(1, keep)
+        err = C.create_string_buffer(512)
+        self._r = self._L.orc_reader_open(os.fsencode(path), max_reads, max_bytes, self.keep + max(1, ahead),
+                                          int(pinned), err, 512)
+        if not self._r:
+            raise OSError(err.value.decode(errors="replace"))
+        self._held: List[int] = []
 
     def __iter__(self) -> Iterator[TextBatch]:
-        fh = open_maybe_gzip(self.path)
+        L = self._L
+        while self._r:
+            while len(self._held) >= self.keep:
+                L.orc_reader_release(self._r, self._held.pop(0))
+            tb = _lib.TextBatchC()
+            rc = L.orc_reader_next(self._r, C.byref(tb))
+            if rc == 0:
+                return
+            if rc < 0:
+                raise ValueError(L.orc_reader_error(self._r).decode(errors="replace"))
+            self._held.append(int(tb.buffer))
+            n = int(tb.n_reads)
+            out = TextBatch(_view(tb.text, int(tb.n_bytes), np.uint8), int(tb.n_bytes), n,
+                            _view(tb.offsets, n, np.uint64), _view(tb.lengths, n, np.uint32),
+                            _view(tb.qual_offsets, n, np.uint64), _view(tb.name_offsets, n, np.uint64),
+                            _view(tb.name_lengths, n, np.uint32))
+            out.bases = int(tb.total_bases)
+            yield out
+
+    def close(self):
+        if getattr(self, "_r", None):
+            self._L.orc_reader_close(self._r)
+            self._r = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
         try:
-            carry = b""
-            eof = False
-            k = 0
-            while True:
-                buf = self._bufs[k % self.n_buffers]
-                arrays = self._idx[k % self.n_buffers]
-                fill = len(carry)
-                if fill:
-                    buf[:fill] = np.frombuffer(carry, dtype=np.uint8)
-                mv = memoryview(buf)
-                while fill < self.max_bytes and not eof:
-                    got = fh.readinto(mv[fill:])
-                    if not got:
-                        eof = True
-                        break
-                    fill += got
-                if fill == 0:
-                    break
-                n, consumed, arrays = index_text(buf, fill, self.max_reads, eof, arrays)
-                if n == 0:
-                    if eof:
-                        break
-                    raise ValueError("FASTQ record larger than the %d-byte batch buffer" % self.max_bytes)
-                carry = buf[consumed:fill].tobytes()
-                k += 1
-                yield TextBatch(buf, consumed, n, *arrays)
-                if eof and not carry:
-                    break
-        finally:
-            if fh is not sys.stdin.buffer:
-                fh.close()
+            self.close()
+        except Exception:
+            pass
 
 
 class BinWriters:
-    """One output file per bin name, opened (and so created) up front."""
+    """One output file per bin name, created up front (orc_writer_*, csrc/orc_io.cpp): gzip
+    members are deflated by a native thread pool while the GPU works on the next batches."""
 
     def __init__(self, paths: List[Optional[str]], compresslevel: int = 5, threads: int = 8):
+        self._L = _lib.load()
         self.paths = paths
-        self.level = compresslevel
-        self._fh = []
-        self._gz = []
-        for p in paths:
-            if p is None:
-                self._fh.append(None)
-                self._gz.append(None)
-                continue
-            self._fh.append(open(p, "wb"))
-            self._gz.append(p.endswith(".gz"))
-        self._pool = ThreadPoolExecutor(max_workers=max(1, threads))
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) if p is not None else None for p in paths])
+        err = C.create_string_buffer(512)
+        self._w = self._L.orc_writer_open(arr, len(paths), int(compresslevel), int(threads), err, 512)
+        if not self._w:
+            raise OSError(err.value.decode(errors="replace"))
+        self._live = {}
         self.bytes_written = [0] * len(paths)
 
-    def _one(self, b: int, data: bytes):
-        if not data:
-            return
-        fh = self._fh[b]
-        if self._gz[b]:
-            # one gzip member per batch: a concatenation of members is a valid .gz stream
-            co = zlib.compressobj(self.level, zlib.DEFLATED, 31)
-            fh.write(co.compress(data) + co.flush())
-        else:
-            fh.write(data)
-        self.bytes_written[b] += len(data)
+    def write_batch(self, result) -> int:
+        """Queue every bin's FASTQ text of one BatchResult; returns a ticket.  The result's
+        buffers must not be reused (no new submit on its slot) before wait(ticket)."""
+        off = np.ascontiguousarray(result.bin_offsets, dtype=np.uint64)
+        t = int(self._L.orc_writer_write(self._w, result.fastq.ctypes.data if result.fastq.size else None,
+                                         off.ctypes.data))
+        if t < 0:
+            raise OSError("orc_writer_write: " + self._L.orc_writer_error(self._w).decode(errors="replace"))
+        self._live[t] = (result, off)
+        return t
 
-    def write_batch(self, result):
-        """Append every bin's FASTQ text of one BatchResult (bins are written in parallel,
-        successive batches in order)."""
-        futs = []
-        for b, fh in enumerate(self._fh):
-            if fh is None:
-                continue
-            lo, hi = int(result.bin_offsets[b]), int(result.bin_offsets[b + 1])
-            if hi > lo:
-                futs.append(self._pool.submit(self._one, b, result.fastq[lo:hi].tobytes()))
-        for f in futs:
-            f.result()
+    def wait(self, ticket: int):
+        if ticket in self._live:
+            rc = self._L.orc_writer_wait(self._w, ticket)
+            del self._live[ticket]
+            if rc:
+                raise OSError("orc_writer_wait: " + self._L.orc_writer_error(self._w).decode(errors="replace"))
 
     def close(self):
-        self._pool.shutdown(wait=True)
-        for b, fh in enumerate(self._fh):
-            if fh is None:
-                continue
-            if self._gz[b] and self.bytes_written[b] == 0:
-                co = zlib.compressobj(self.level, zlib.DEFLATED, 31)     # an empty but valid .gz
-                fh.write(co.flush())
-            fh.close()
+        if getattr(self, "_w", None):
+            n = np.zeros(len(self.paths), dtype=np.uint64)
+            msg = self._L.orc_writer_error(self._w)
+            rc = self._L.orc_writer_close(self._w, n.ctypes.data)
+            self._w = None
+            self._live.clear()
+            self.bytes_written = [int(x) for x in n]
+            if rc:
+                raise OSError("writing the bins failed: " + (msg or b"").decode(errors="replace"))
 
 
 def read_adapters_fasta(path: str):

@@ -23,7 +23,9 @@ ORC_OK, ORC_EINVAL, ORC_ECUDA, ORC_ECAPACITY, ORC_ESTATE = 0, -1, -2, -3, -4
 # every symbol include/orcdemux.h declares
 EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_submit", "orc_wait",
            "orc_upload", "orc_launch", "orc_download", "orc_sync", "orc_get_timings", "orc_timer_start", "orc_timer_stop", "orc_counts",
-           "orc_fastq_index", "orc_host_alloc", "orc_host_free", "orc_measure_int32_peak", "orc_version"]
+           "orc_fastq_index", "orc_host_alloc", "orc_host_free", "orc_measure_int32_peak", "orc_version",
+           "orc_reader_open", "orc_reader_next", "orc_reader_release", "orc_reader_error", "orc_reader_close",
+           "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -68,6 +70,12 @@ class Timings(C.Structure):
                 ("kernel_launches", C.c_uint32), ("n_tasks", C.c_uint32 * ORC_MAX_ROUNDS),
                 ("n_candidates", C.c_uint32 * ORC_MAX_ROUNDS),
                 ("cells", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_executed", C.c_uint64 * ORC_MAX_ROUNDS), ("pack_bytes", C.c_uint64), ("emit_bytes", C.c_uint64)]
+
+
+class TextBatchC(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("n_bytes", C.c_uint64), ("n_reads", C.c_uint32), ("buffer", C.c_int32),
+                ("offsets", C.c_void_p), ("lengths", C.c_void_p), ("qual_offsets", C.c_void_p),
+                ("name_offsets", C.c_void_p), ("name_lengths", C.c_void_p), ("total_bases", C.c_uint64)]
 
 
 _lib = None
@@ -116,6 +124,26 @@ def load():
     L.orc_timer_stop.restype = C.c_int
     L.orc_measure_int32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.orc_measure_int32_peak.restype = C.c_double
+    L.orc_reader_open.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.orc_reader_open.restype = C.c_void_p
+    L.orc_reader_next.argtypes = [C.c_void_p, C.POINTER(TextBatchC)]
+    L.orc_reader_next.restype = C.c_int
+    L.orc_reader_release.argtypes = [C.c_void_p, C.c_int]
+    L.orc_reader_release.restype = C.c_int
+    L.orc_reader_error.argtypes = [C.c_void_p]
+    L.orc_reader_error.restype = C.c_char_p
+    L.orc_reader_close.argtypes = [C.c_void_p]
+    L.orc_reader_close.restype = None
+    L.orc_writer_open.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.orc_writer_open.restype = C.c_void_p
+    L.orc_writer_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_writer_write.restype = C.c_int64
+    L.orc_writer_wait.argtypes = [C.c_void_p, C.c_int64]
+    L.orc_writer_wait.restype = C.c_int
+    L.orc_writer_error.argtypes = [C.c_void_p]
+    L.orc_writer_error.restype = C.c_char_p
+    L.orc_writer_close.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_writer_close.restype = C.c_int
     L.orc_version.argtypes = []
     L.orc_version.restype = C.c_char_p
     _lib = L

@@ -107,6 +107,16 @@ def test_reference_script_flow_and_fused(tmp_path):
     for rel, data in expected.items():
         assert _read_gz(out2 / rel) == data, rel
 
+    # the same in many small batches: reader thread -> 3 slots -> writer pool, order kept per bin
+    out3 = work / "demuxed_fused_small"
+    r = subprocess.run([sys.executable, "-m", "orcdemux.cli", "two-round", str(infile), "--sp5", fwd, "--sp27", rev,
+                        "--outdir", str(out3), "-j", "3"], capture_output=True, text=True,
+                       env=dict(os.environ, PYTHONPATH=H.PKG, ORCDEMUX_BATCH_READS="700"))
+    assert r.returncode == 0, r.stderr
+    for rel, data in expected.items():
+        assert _read_gz(out3 / rel) == data, rel
+    assert json.load(open(out3 / "SP27" / ("orcdemux_%s.json" % ds)))["reads"] == rs.n_reads
+
 
 def test_unsupported_exits_2(tmp_path):
     shim = os.path.join(H.PKG, "bin", "cutadapt")
@@ -121,7 +131,8 @@ def test_raw_text_layout_equals_blob_layout(tmp_path):
     rs = synth.generate(3000, 300, 900, seed=5)
     p = tmp_path / "x.fastq"
     p.write_bytes(rs.to_fastq_bytes())
-    tb = next(iter(F.FastqReader(str(p), max_reads=4096, max_bytes=1 << 23, n_buffers=2)))
+    rd = F.FastqReader(str(p), max_reads=4096, max_bytes=1 << 23, keep=1, ahead=1)
+    tb = next(iter(rd))
     assert tb.n_reads == rs.n_reads
     with E.Engine(E.m13_rounds(), max_reads=4096, max_bytes=1 << 23, n_slots=1) as eng:
         a = eng.run(tb)
