@@ -168,10 +168,19 @@ class EndStats:
         self.front = kind in (ORC_FRONT, ORC_PREFIX)
         self.hist = [dict() for _ in names]            # removed length -> {errors: count}
         self.on_rc = np.zeros(len(names), dtype=np.int64)
-        self.adjacent = [dict() for _ in names]
+        # 3' adapters: the base preceding the match, columns A C G T none/other (RemoveAfterMatch.adjacent_base)
+        self.adjacent = np.zeros((len(names), 5), dtype=np.int64)
+
+    _COMP = np.arange(256, dtype=np.uint8)
+    for _a, _b in zip(b"ACGT", b"TGCA"):
+        _COMP[_a] = _b
+    _BASE_COL = np.full(256, 4, dtype=np.int64)
+    for _i, _a in enumerate(b"ACGT"):
+        _BASE_COL[_a] = _i
 
     def add(self, m, in_len, tb=None):
-        """m: orc_match records of the round; in_len: read lengths before the round."""
+        """m: orc_match records of the round; in_len: read lengths before the round; tb: the batch
+        (its text gives the bases next to 3' matches)."""
         has = m["adapter"] >= 0
         if not has.any():
             return
@@ -180,6 +189,18 @@ class EndStats:
         L = in_len[has].astype(np.int64)
         removed = m["query_stop"][has].astype(np.int64) if self.front else L - m["query_start"][has]
         self.on_rc += np.bincount(a[m["is_rc"][has] != 0], minlength=len(self.names))
+        if not self.front and tb is not None:
+            qs = m["query_start"][has].astype(np.int64)
+            rc = m["is_rc"][has] != 0
+            off = tb.offsets[:m.shape[0]][has].astype(np.int64)
+            # read[qs - 1] in the orientation that matched: on the reverse complement that is the
+            # complement of the stored base at n - qs
+            pos = np.where(rc, off + (L - qs), off + qs - 1)
+            ok = qs > 0
+            base = tb.text[np.where(ok, pos, off)]
+            base = np.where(rc, self._COMP[base], base)
+            col = np.where(ok, self._BASE_COL[base], 4)
+            np.add.at(self.adjacent, (a, col), 1)
         key = (a << 40) | (removed << 8) | err
         ks, cs = np.unique(key, return_counts=True)
         for k, c in zip(ks.tolist(), cs.tolist()):
@@ -205,7 +226,59 @@ class EndStats:
                 "error_lengths": [int(e / self.rate) - 1 if e else 0 for e in range(kmax + 1)][1:] + [len(seq)]
                 if self.rate > 0 else [len(seq)],
                 "matches": int(sum(sum(h.values()) for h in self.hist[i].values())),
-                "adjacent_bases": None, "dominant_adjacent_base": None, "trimmed_lengths": lengths}
+                "adjacent_bases": None if self.front else
+                {k: int(v) for k, v in zip(("A", "C", "G", "T", ""), self.adjacent[i])},
+                "dominant_adjacent_base": None if self.front else self._dominant(i), "trimmed_lengths": lengths}
+
+    def _dominant(self, i):
+        """report.py: a base that precedes > 80 % of at least 20 matches is flagged."""
+        total = int(self.adjacent[i].sum())
+        if total < 20:
+            return None
+        j = int(np.argmax(self.adjacent[i][:4]))
+        return "ACGT"[j] if self.adjacent[i][j] / total > 0.8 else None
+
+    def text(self, n_reads, min_overlap):
+        """The per-adapter sections of cutadapt's text report (report.py full_report)."""
+        out = []
+        typ = {ORC_FRONT: "regular 5'", ORC_BACK: "regular 3'", ORC_PREFIX: "anchored 5'",
+               ORC_SUFFIX: "anchored 3'"}[self.kind]
+        for i, nm in enumerate(self.names):
+            end = self._end(i, n_reads)
+            seq = self.seqs[i]
+            out.append("=== Adapter %s ===\n" % nm)
+            line = "Sequence: %s; Type: %s; Length: %d; Trimmed: %d times" % (seq, typ, len(seq), end["matches"])
+            if self.revcomp:
+                line += "; Reverse-complemented: %d times" % int(self.on_rc[i])
+            out.append(line + "\n")
+            out.append("Minimum overlap: %d" % min(min_overlap, len(seq)))
+            out.append("No. of allowed errors:")
+            lo, parts = 1, []
+            for e, hi in enumerate(end["error_lengths"]):
+                parts.append(("%d-%d bp: %d" % (lo, hi, e)) if hi > lo else ("%d bp: %d" % (hi, e)))
+                lo = hi + 1
+            out.append("; ".join(parts) + "\n")
+            if end["matches"] == 0:
+                continue
+            if not self.front:
+                tot = max(int(self.adjacent[i].sum()), 1)
+                out.append("Bases preceding removed adapters:")
+                for k, lab in enumerate(("A", "C", "G", "T", "none/other")):
+                    out.append("  %s: %.1f%%" % (lab, 100.0 * self.adjacent[i][k] / tot))
+                dom = self._dominant(i)
+                if dom:
+                    out.append("WARNING:\n    The adapter is preceded by '%s' extremely often.\n"
+                               "    The provided adapter sequence could be incomplete at its 5' end." % dom)
+                out.append("")
+            out.append("Overview of removed sequences")
+            out.append("length\tcount\texpect\tmax.err\terror counts")
+            for t in end["trimmed_lengths"]:
+                ln = t["len"]
+                out.append("%d\t%d\t%.1f\t%d\t%s" % (ln, sum(t["counts"]), t["expect"],
+                                                       int(self.rate * min(ln, len(seq))),
+                                                       " ".join(str(c) for c in t["counts"])))
+            out.append("")
+        return "\n".join(out)
 
     def as_json(self, n_reads):
         out = []
@@ -281,7 +354,7 @@ def run_single_round(opt, argv, device=0) -> int:
         n_with += int(has.sum())
         n_rc += int((m["is_rc"] != 0).sum())
         per += np.bincount(m["adapter"][has], minlength=len(names))
-        stats.add(m, tb.lengths[:res.n_reads])
+        stats.add(m, tb.lengths[:res.n_reads], tb)
 
     try:
         with E.Engine([rnd], device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
@@ -300,14 +373,21 @@ def run_single_round(opt, argv, device=0) -> int:
         with open(opt["json"], "w") as fh:
             json.dump(rep, fh, indent=2)
     if not opt["quiet"]:
+        el = rep["elapsed_seconds"]
         print("This is orcdemux (cutadapt 4.9-compatible demultiplexing on B200)")
+        print("Command line parameters: " + " ".join(argv))
+        print("Processing single-end reads on 1 GPU, %d host threads ..." % threads)
+        print("Finished in %.3f s (%.3f us/read; %.2f M reads/minute).\n" %
+              (el, 1e6 * el / max(n_in, 1), n_in / max(el, 1e-9) * 60e-6))
         print("=== Summary ===\n")
-        print("Total reads processed:           %12d" % n_in)
-        print("Reads with adapters:             %12d (%.1f%%)" % (n_with, 100.0 * n_with / max(n_in, 1)))
-        print("Reverse-complemented:            %12d (%.1f%%)" % (n_rc, 100.0 * n_rc / max(n_in, 1)))
-        print("Reads written (passing filters): %12d (100.0%%)\n" % n_in)
-        print("Total basepairs processed: %12d bp" % bp_in)
-        print("Total written (filtered):  %12d bp (%.1f%%)" % (bp_out, 100.0 * bp_out / max(bp_in, 1)))
+        print("Total reads processed:           %15s" % format(n_in, ","))
+        print("Reads with adapters:             %15s (%.1f%%)" % (format(n_with, ","), 100.0 * n_with / max(n_in, 1)))
+        if opt["rc"]:
+            print("Reverse-complemented:            %15s (%.1f%%)" % (format(n_rc, ","), 100.0 * n_rc / max(n_in, 1)))
+        print("Reads written (passing filters): %15s (100.0%%)\n" % format(n_in, ","))
+        print("Total basepairs processed: %15s bp" % format(bp_in, ","))
+        print("Total written (filtered):  %15s bp (%.1f%%)\n" % (format(bp_out, ","), 100.0 * bp_out / max(bp_in, 1)))
+        print(stats.text(n_in, opt["O"]))
     return 0
 
 
