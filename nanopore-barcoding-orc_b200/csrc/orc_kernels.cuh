@@ -630,105 +630,49 @@ __device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8
     if (done + (uint32_t)lane < n) dst[done + lane] = src[done + lane];
 }
 
-// Sequence and qualities are copied 16 bytes per lane and trip: the destination in aligned
-// 128-bit stores, each assembled from two aligned 128-bit loads of the source by a word select
-// (the source's word offset inside its 16-byte line, the same for every quad of a copy) and a
-// funnel shift (its byte offset inside the word).  One trip of a warp moves 512 bytes per stream,
-// and the loads of both streams are issued before the first store, so a warp keeps 2 KB of
-// requests in flight -- the copy is bound by bytes in flight per SM, not by instructions.
-// Sources may be over-read by up to 31 bytes (the blobs carry 128 bytes of slack).
-struct Copy16 {
-    const uint4 *sa;    // forward: aligned quad holding the first source byte; reverse: the one holding `top`
-    uint4 *da;
-    uint32_t nq, sh, wo;
-};
-
-__device__ __forceinline__ uint4 realign16(const uint4 lo, const uint4 hi, uint32_t wo, uint32_t sh)
+// The same in reverse: dst[i] = f(src[n - 1 - i]) with f = the complement table (bases) or the
+// identity (qualities, comp == nullptr).  Output word w holds the source bytes e, e-1, e-2, e-3
+// (e = n - 1 - head - 4w): an unaligned 4-byte window read as above, bytes swapped.
+__device__ __forceinline__ void warp_copy_rev(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                              uint32_t n, int lane, const uint8_t *comp)
 {
-    uint32_t w0, w1, w2, w3, w4;
-    if (wo == 0u)      { w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; }
-    else if (wo == 1u) { w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; }
-    else if (wo == 2u) { w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; }
-    else               { w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; }
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                      __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-}
-
-// head and tail bytes singly, the quads in between are left to the caller's loop
-__device__ __forceinline__ void copy16_begin(Copy16 &c, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
-                                             uint32_t n, int lane)
-{
-    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u));
-    if ((uint32_t)lane < head) dst[lane] = src[lane];
-    c.nq = (n - head) >> 4;
-    const uint8_t *sp = src + head;
-    c.sh = (uint32_t)((uintptr_t)sp & 3u) * 8u;
-    c.wo = (uint32_t)(((uintptr_t)sp >> 2) & 3u);
-    c.sa = reinterpret_cast<const uint4 *>((uintptr_t)sp & ~(uintptr_t)15);
-    c.da = reinterpret_cast<uint4 *>(dst + head);
-    const uint32_t done = head + 16u * c.nq;
-    if (done + (uint32_t)lane < n) dst[done + lane] = src[done + lane];
-}
-
-// dst[i] = f(src[n - 1 - i]), f = complement table or identity: quad q of the destination is the
-// 16 source bytes below top - 16 q, byte-reversed; every quad reads the source at the same phase
-__device__ __forceinline__ void copy16_begin_rev(Copy16 &c, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
-                                                 uint32_t n, int lane, const uint8_t *comp)
-{
-    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u));
+    const uint32_t head = min(n, (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u));
     if ((uint32_t)lane < head) {
         const uint8_t b = src[n - 1 - lane];
         dst[lane] = comp ? comp[b] : b;
     }
-    c.nq = (n - head) >> 4;
-    const uint8_t *top = src + (n - head);
-    c.sh = (uint32_t)((uintptr_t)top & 3u) * 8u;
-    c.wo = (uint32_t)(((uintptr_t)top >> 2) & 3u);
-    c.sa = reinterpret_cast<const uint4 *>((uintptr_t)top & ~(uintptr_t)15);
-    c.da = reinterpret_cast<uint4 *>(dst + head);
-    const uint32_t done = head + 16u * c.nq;
+    const uint32_t nw = (n - head) >> 2;
+    uint32_t *da = reinterpret_cast<uint32_t *>(dst + head);
+    const uint8_t *top = src + (n - head);           // one past the source byte of output byte `head`
+    auto put = [&](uint32_t w, uint32_t x) {            // x = bytes src[e-3] .. src[e] of output word w
+        uint32_t y;
+        if (comp) y = (uint32_t)comp[x >> 24] | ((uint32_t)comp[(x >> 16) & 255u] << 8) |
+                      ((uint32_t)comp[(x >> 8) & 255u] << 16) | ((uint32_t)comp[x & 255u] << 24);
+        else y = __byte_perm(x, 0u, 0x0123u);
+        da[w] = y;
+    };
+    // all output words read the source at the same byte phase: (top - 4(w+1)) & 3 == top & 3
+    const uint32_t sh = (uint32_t)((uintptr_t)top & 3u) * 8u;
+    const uint32_t *ta = reinterpret_cast<const uint32_t *>((uintptr_t)top & ~(uintptr_t)3);
+    for (uint32_t base = lane; base < nw; base += 64) {
+        const uint32_t w1 = base + 32u;
+        const bool two = w1 < nw;
+        const uint32_t *pa = ta - (base + 1u);
+        const uint32_t a0 = pa[0], a1 = pa[1];
+        uint32_t b0 = 0, b1 = 0;
+        if (two) { b0 = pa[-32]; b1 = pa[-31]; }
+        put(base, __funnelshift_r(a0, a1, sh));
+        if (two) put(w1, __funnelshift_r(b0, b1, sh));
+    }
+    const uint32_t done = head + 4u * nw;
     if (done + (uint32_t)lane < n) {
         const uint8_t b = src[n - 1 - (done + lane)];
         dst[done + lane] = comp ? comp[b] : b;
     }
 }
 
-__device__ __forceinline__ uint32_t rev_word(uint32_t x, const uint8_t *comp)
-{
-    if (comp) return (uint32_t)comp[x >> 24] | ((uint32_t)comp[(x >> 16) & 255u] << 8) |
-                     ((uint32_t)comp[(x >> 8) & 255u] << 16) | ((uint32_t)comp[x & 255u] << 24);
-    return __byte_perm(x, 0u, 0x0123u);
-}
-
-template <bool REV>
-__device__ __forceinline__ void copy16_pair(const Copy16 &a, const Copy16 &b, int lane, const uint8_t *comp_a)
-{
-    const uint32_t nmax = max(a.nq, b.nq);
-    for (uint32_t q = lane; q < nmax; q += 32) {
-        const bool pa = q < a.nq, pb = q < b.nq;
-        uint4 alo = make_uint4(0, 0, 0, 0), ahi = alo, blo = alo, bhi = alo;
-        if (REV) {
-            if (pa) { alo = *(a.sa - (q + 1u)); ahi = *(a.sa - q); }
-            if (pb) { blo = *(b.sa - (q + 1u)); bhi = *(b.sa - q); }
-        } else {
-            if (pa) { alo = a.sa[q]; ahi = a.sa[q + 1u]; }
-            if (pb) { blo = b.sa[q]; bhi = b.sa[q + 1u]; }
-        }
-        if (pa) {
-            uint4 x = realign16(alo, ahi, a.wo, a.sh);
-            if (REV) x = make_uint4(rev_word(x.w, comp_a), rev_word(x.z, comp_a), rev_word(x.y, comp_a), rev_word(x.x, comp_a));
-            a.da[q] = x;
-        }
-        if (pb) {
-            uint4 x = realign16(blo, bhi, b.wo, b.sh);
-            if (REV) x = make_uint4(rev_word(x.w, nullptr), rev_word(x.z, nullptr), rev_word(x.y, nullptr), rev_word(x.x, nullptr));
-            b.da[q] = x;
-        }
-    }
-}
-
 // One warp per read: '@' name [' rc']* '\n' seq '\n' '+' '\n' qual '\n'
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 8)
 emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
             const uint8_t *__restrict__ names, const uint64_t *__restrict__ name_offsets,
             const uint32_t *__restrict__ name_lengths, const uint64_t *__restrict__ offsets,
@@ -760,15 +704,12 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
         o += 1;
         const uint8_t *s = seq + v.lo;
         const uint8_t *q = qual + v.lo + (qual_offsets ? qual_offsets[r] - offsets[r] : 0ull);
-        Copy16 cs, cq;
         if (v.rc & 1u) {
-            copy16_begin_rev(cs, o, s, L, lane, comp);
-            copy16_begin_rev(cq, o + L + 3, q, L, lane, nullptr);
-            copy16_pair<true>(cs, cq, lane, comp);
+            warp_copy_rev(o, s, L, lane, comp);
+            warp_copy_rev(o + L + 3, q, L, lane, nullptr);
         } else {
-            copy16_begin(cs, o, s, L, lane);
-            copy16_begin(cq, o + L + 3, q, L, lane);
-            copy16_pair<false>(cs, cq, lane, nullptr);
+            warp_copy(o, s, L, lane);
+            warp_copy(o + L + 3, q, L, lane);
         }
         if (lane == 0) { o[L] = '\n'; o[L + 1] = '+'; o[L + 2] = '\n'; o[2 * L + 3] = '\n'; }
     }
