@@ -58,6 +58,7 @@ struct Slot {
     uint32_t *d_key_in = nullptr, *d_key_out = nullptr, *d_val_in = nullptr, *d_order = nullptr;
     void *d_sort_tmp = nullptr;
     WinList *d_wins = nullptr;
+    SeedWins *d_seedwins = nullptr;  // stage 1s: seed windows per (read, direction)
     Task *d_tasks = nullptr;
     uint32_t *d_jobs = nullptr;              // stage 2a survivors: job numbers (item * n_adapters + adapter)
     PairResult *d_results = nullptr;
@@ -86,6 +87,8 @@ struct orc_ctx {
     uint32_t max_reads = 0;
     uint64_t max_bytes = 0, max_name_bytes = 0, fastq_cap = 0;
     RoundTable h_tab[2];
+    SeedTable h_seed[2];             // stage 1s (on == 0: the round keeps the flank scan)
+    SeedTable *d_seed[2] = {nullptr, nullptr};
     RoundTable *d_tab[2] = {nullptr, nullptr};
     AnchoredTable h_anch[2];
     AnchoredTable *d_anch[2] = {nullptr, nullptr};
@@ -140,6 +143,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_key_in, R)); CK(dalloc(&s.d_key_out, R)); CK(dalloc(&s.d_val_in, R)); CK(dalloc(&s.d_order, R));
     CK(cudaMalloc(&s.d_sort_tmp, ctx->sort_tmp_bytes + 64));
     CK(dalloc(&s.d_wins, 2 * R));
+    CK(dalloc(&s.d_seedwins, 2 * R));
     CK(dalloc(&s.d_tasks, n_tasks));
     CK(dalloc(&s.d_jobs, 2 * R * MAX_AD));
     CK(dalloc(&s.d_results, n_tasks));
@@ -182,7 +186,7 @@ static void free_slot(Slot &s)
     cudaFree(s.d_wcols); cudaFree(s.d_wcols_sorted); cudaFree(s.d_item_in); cudaFree(s.d_item_order);
     cudaFree(s.d_best_key); cudaFree(s.d_tasks); cudaFree(s.d_results); cudaFree(s.d_jobs);
     cudaFree(s.d_key_in); cudaFree(s.d_key_out); cudaFree(s.d_val_in); cudaFree(s.d_order);
-    cudaFree(s.d_sort_tmp); cudaFree(s.d_wins);
+    cudaFree(s.d_sort_tmp); cudaFree(s.d_wins); cudaFree(s.d_seedwins);
     cudaFree(s.d_counters); cudaFree(s.d_cells); cudaFree(s.d_bin); cudaFree(s.d_out_len);
     cudaFree(s.d_rec_bytes); cudaFree(s.d_hist_cnt); cudaFree(s.d_hist_bytes);
     cudaFree(s.d_bin_counts); cudaFree(s.d_bin_offsets); cudaFree(s.d_bin_bytes);
@@ -231,6 +235,11 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
             why = build_round_table(ctx->h_tab[r], rp.n_adapters, rp.type, rp.sequences,
                                     rp.max_error_rate, rp.min_overlap, rp.indels, rp.revcomp);
         if (!why.empty()) { ctx->err = why; return ORC_EINVAL; }
+        ctx->h_seed[r].on = 0;
+        if (!ctx->anchored[r]) {
+            const char *off = getenv("ORC_NO_SEED");        // A/B measurements: keep the flank scan
+            build_seed_table(ctx->h_tab[r], ctx->h_seed[r], !(off && off[0] == '1'));
+        }
     }
     ctx->n_bins = ctx->h_tab[0].n_adapters + 1;
     if (p->n_rounds == 2) ctx->n_bins *= ctx->h_tab[1].n_adapters + 1;
@@ -240,6 +249,10 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     for (int r = 0; r < p->n_rounds; r++) {
         CK(dalloc(&ctx->d_tab[r], 1));
         CK(cudaMemcpy(ctx->d_tab[r], &ctx->h_tab[r], sizeof(RoundTable), cudaMemcpyHostToDevice));
+        if (!ctx->anchored[r] && ctx->h_seed[r].on) {
+            CK(dalloc(&ctx->d_seed[r], 1));
+            CK(cudaMemcpy(ctx->d_seed[r], &ctx->h_seed[r], sizeof(SeedTable), cudaMemcpyHostToDevice));
+        }
         if (ctx->anchored[r]) {
             CK(dalloc(&ctx->d_anch[r], 1));
             CK(cudaMemcpy(ctx->d_anch[r], &ctx->h_anch[r], sizeof(AnchoredTable), cudaMemcpyHostToDevice));
@@ -303,7 +316,7 @@ extern "C" void orc_destroy(orc_ctx *ctx)
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
-    for (int r = 0; r < 2; r++) { cudaFree(ctx->d_tab[r]); cudaFree(ctx->d_anch[r]); }
+    for (int r = 0; r < 2; r++) { cudaFree(ctx->d_tab[r]); cudaFree(ctx->d_anch[r]); cudaFree(ctx->d_seed[r]); }
     cudaFree(ctx->d_pack_lut); cudaFree(ctx->d_comp_lut); cudaFree(ctx->d_drop);
     delete ctx;
 }
@@ -447,9 +460,14 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
                 CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_key_in, s.d_key_out, s.d_val_in,
                                                              s.d_order, (int)n, 0, s.len_bits, st));
             }
+            const bool seeded = filter && ctx->h_seed[r].on != 0;
+            if (seeded)
+                seed_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_seed[r], W, s.d_views[r], prev, s.d_order, n,
+                                                            s.d_seedwins);
             trigger_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], prev,
                                                                filter ? s.d_order : nullptr, n, s.d_wins,
-                                                               s.d_wcols, s.d_item_in, s.d_cells + 2 + r);
+                                                               s.d_wcols, s.d_item_in, s.d_cells + 2 + r,
+                                                               seeded ? s.d_seedwins : nullptr);
             // order the (read, direction) items by the columns they have to scan
             tmp = ctx->sort_tmp_bytes;
             CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_wcols, s.d_wcols_sorted, s.d_item_in,
@@ -633,8 +651,10 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     CK(cudaMemcpy(&emit_bytes, s.d_bin_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 4u + (s.has_names ? 1u : 0u)) : 2u;
     if (s.n_reads)
-        for (int r = 0; r < ctx->n_rounds; r++)     // trigger (+ sort_keys); CUB's own launches are not counted
+        for (int r = 0; r < ctx->n_rounds; r++) {   // trigger (+ sort_keys); CUB's own launches are not counted
             t->kernel_launches += ctx->anchored[r] ? 0u : (ctx->h_tab[r].use_filter ? 2u : 1u);
+            if (!ctx->anchored[r] && ctx->h_tab[r].use_filter && ctx->h_seed[r].on) t->kernel_launches += 1u;   // seed_kernel
+        }
     if (s.n_reads)
         for (int r = 0; r < ctx->n_rounds; r++)
             if (ctx->anchored[r]) t->kernel_launches -= 1u;   // anchored + select instead of scan + resolve + select
@@ -659,7 +679,9 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
         // the pairs that passed); without stage 2a every adapter's m rows over the window columns
         uint64_t bsum = 0;
         for (int a = 0; a < T.n_adapters; a++) bsum += (uint64_t)(T.m[a] < 32 ? T.m[a] : 32);
-        const uint64_t rows1 = (uint64_t)(T.sfx_primary ? T.lcs : T.lcp);
+        // (a seeded stage 1 updates no DP cells in its main pass; the short flank scans at the read
+        // ends are not counted)
+        const uint64_t rows1 = ctx->h_seed[r].on ? 0ull : (uint64_t)(T.sfx_primary ? T.lcs : T.lcp);
         t->cells_executed[r] = (T.use_filter ? rows1 * (T.revcomp ? 2ull : 1ull) * bases : 0ull) +
                                (T.indels ? bsum * (uint64_t)cells[2 + r] + (uint64_t)cells[4 + r]
                                          : msum * (uint64_t)cells[2 + r]);

@@ -354,6 +354,163 @@ ORC_HD void win_add(WinList &L, bool &open, uint32_t &cs, uint32_t &ce, uint32_t
     cs = s; ce = e;
 }
 
+// ------------------------------------------------------------------------------------
+// Stage 1s: exact seeds instead of the column-by-column flank scan of the main loop below.
+//
+// Cut every adapter into its floor(m / 8) leading pieces of 8 rows.  An alignment of the whole
+// adapter (rows 1..m) with at most k errors damages at most k pieces (a substitution or deletion
+// the piece of its row, an insertion the piece it falls inside), so at least np - k pieces appear
+// in the read exactly and contiguously, and the diagonals of two such pieces differ by at most k
+// (the indels between them).  A piece of 8 codes is one 32-bit window of the packed code array,
+// so "does a piece start here" is one probe of a perfect hash table per column -- for both
+// directions at once, because a piece found in the reverse complement of the read is the
+// reverse-complemented piece found in the read.  Where np - k >= 2 a hit only counts together
+// with a second one (another piece of the same adapter, same direction, diagonal within k):
+// random 8-mers practically never come in such pairs.
+//
+// Every confirmed hit with diagonal c0 (row i of the adapter at column c0 + i) opens the window
+// [c0 - 2k - 1, c0 + m_max + k]: the candidates end within k of c0 + m, and any optimal path to
+// them starts within m + k columns before its end, i.e. at or after c0 - 2k; such a path is
+// itself an alignment with <= k errors, so it has seeds of its own whose window overlaps this
+// one and is merged with it -- inside the merged windows every candidate's cost is exact
+// (DESIGN.md section 4, item 5b).  Alignments that do NOT span the whole adapter are the ones
+// that run off an end of the read; trigger_lane() decides those windows exactly as before
+// (first window of a 5' round, last windows of a 3' round).
+// ------------------------------------------------------------------------------------
+constexpr int SEED_SLOTS = 4096;        // 32 KB of shared memory
+constexpr int SEED_SHIFT = 20;          // slot = (key * mult) >> SEED_SHIFT
+constexpr int SEED_LIST_MAX = 512;
+constexpr int SEED_RAW_MAX = 12;        // raw hits kept per direction before giving up (-> scan everything)
+constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;    // no packed window ever has an all-ones nibble
+
+
+// slot of a key: the top 12 bits of key * mult (multiply-high keeps the index arithmetic off the
+// ALU pipe, which the funnel shifts and compares of the probe loop already fill)
+ORC_HD uint32_t seed_slot(uint32_t key, uint32_t mult)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(key * mult, 1u << (32 - SEED_SHIFT));
+#else
+    return (key * mult) >> SEED_SHIFT;
+#endif
+}
+
+struct SeedTable {
+    int32_t on;                     // 0: the round keeps the flank scan
+    int32_t need;                   // hits an occurrence is guaranteed to have: 1 or 2
+    uint32_t mult;
+    int32_t n_list;
+    int32_t kt, m_max, pad_[2];
+    uint32_t key[SEED_SLOTS];       // SEED_EMPTY: free slot
+    uint32_t val[SEED_SLOTS];       // first list entry | count << 16
+    uint32_t list[SEED_LIST_MAX];   // adapter mask (16 bits) | piece << 16 | direction << 20
+};
+
+struct SeedWins {                   // the seed windows of one (read, direction), increasing, disjoint
+    uint32_t n;
+    uint32_t s[MAX_WIN], e[MAX_WIN];
+    uint32_t all;                   // too many hits to keep apart: scan every column
+};
+
+struct Quad { uint32_t w[4]; };
+ORC_HD Quad load_quad(const uint32_t *__restrict__ W, int64_t q)     // words 4q .. 4q+3 (W is 16-byte aligned)
+{
+    Quad r;
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4 *>(W + 4 * q);
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+#else
+    for (int i = 0; i < 4; i++) r.w[i] = W[4 * q + i];
+#endif
+    return r;
+}
+
+// keys: the SEED_SLOTS keys alone (shared memory on the device); vals / list are only read on a hit
+ORC_HD void seed_scan(const uint32_t *__restrict__ W, uint64_t lo, uint32_t n, const uint32_t *keys,
+                      const uint32_t *__restrict__ vals, uint32_t mult, const uint32_t *__restrict__ list,
+                      int need, int kt, int m_max, SeedWins out[2])
+{
+    for (int d = 0; d < 2; d++) {
+        out[d].n = 0; out[d].all = 0;
+        for (int i = 0; i < MAX_WIN; i++) { out[d].s[i] = 0; out[d].e[i] = 0; }
+    }
+    if (n < 8u) return;             // no piece fits, and no whole adapter either
+    int32_t rc0[2][SEED_RAW_MAX];   // diagonals of the hits, per direction, kept sorted
+    int nraw[2] = {0, 0};
+    // 32 columns per 16-byte load, the next load in flight while these are probed.  Windows that
+    // start before lo or reach past lo + n (the neighbours' codes) are discarded when they hit.
+    const int64_t q_first = (int64_t)(lo >> 5), q_last = (int64_t)((lo + n - 8u) >> 5);
+    Quad cur = load_quad(W, q_first);
+    Quad nxt = load_quad(W, q_first + 1);       // at most one quad past the read: guard words
+    for (int64_t q = q_first; q <= q_last; q++) {
+        const Quad nn = load_quad(W, q + 2 <= q_last + 1 ? q + 2 : q_last + 1);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t a = cur.w[u], b = u < 3 ? cur.w[u + 1] : nxt.w[0];
+            bool any = false;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const uint32_t x = t ? funnel_r(a, b, 4u * (uint32_t)t) : a;
+                any |= (keys[seed_slot(x, mult)] == x);
+            }
+            if (any) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const uint32_t x = t ? funnel_r(a, b, 4u * (uint32_t)t) : a;
+                    mask |= (keys[seed_slot(x, mult)] == x ? 1u : 0u) << t;
+                }
+                while (mask) {
+#if defined(__CUDA_ARCH__)
+                    const int t = __ffs((int)mask) - 1;
+#else
+                    const int t = __builtin_ctz(mask);
+#endif
+                    mask &= mask - 1u;
+                    const uint64_t pos = 32ull * (uint64_t)q + 8ull * (uint64_t)u + (uint64_t)t;
+                    if (pos < lo || pos + 8u > lo + n) continue;         // the window must lie inside the read
+                    const uint32_t x = t ? funnel_r(a, b, 4u * (uint32_t)t) : a;
+                    const uint32_t val = vals[seed_slot(x, mult)];
+                    const uint32_t first = val & 0xFFFFu, cnt = val >> 16;
+                    for (uint32_t z = 0; z < cnt; z++) {
+                        const uint32_t e = list[first + z];
+                        const int d = (int)((e >> 20) & 1u);
+                        const int32_t p0 = d ? (int32_t)(lo + n - 8u - pos) : (int32_t)(pos - lo);
+                        const int32_t c0 = p0 - 8 * (int32_t)((e >> 16) & 15u);
+                        if (nraw[d] < SEED_RAW_MAX) {
+                            int i = nraw[d]++;
+                            while (i > 0 && rc0[d][i - 1] > c0) { rc0[d][i] = rc0[d][i - 1]; i--; }
+                            rc0[d][i] = c0;
+                        } else out[d].all = 1u;
+                    }
+                }
+            }
+        }
+        cur = nxt; nxt = nn;
+    }
+    // A hit counts if need == 1, or if another hit lies within kt diagonals of it: the two exact
+    // pieces an occurrence is guaranteed to have are at most kt diagonals apart, so each of them
+    // has a neighbour that close in the sorted list.  (Which pieces and adapters the neighbours
+    // belong to is not checked: a superfluous window only costs time.)
+    for (int d = 0; d < 2; d++) {
+        if (out[d].all) continue;
+        SeedWins &o = out[d];
+        for (int i = 0; i < nraw[d]; i++) {
+            const int32_t c = rc0[d][i];
+            const bool ok = need <= 1 || (i > 0 && c - rc0[d][i - 1] <= kt) || (i + 1 < nraw[d] && rc0[d][i + 1] - c <= kt);
+            if (!ok) continue;
+            const int32_t ws = c - 2 * kt - 1, we = c + m_max + kt;
+            const uint32_t s = ws > 0 ? (uint32_t)ws : 0u;
+            const uint32_t e = we < (int32_t)n ? (uint32_t)we : n;
+            if (o.n > 0 && (s <= o.e[o.n - 1] + 1u || o.n == (uint32_t)MAX_WIN)) {
+                if (e > o.e[o.n - 1]) o.e[o.n - 1] = e;
+            } else {
+                o.s[o.n] = s; o.e[o.n] = e; o.n++;
+            }
+        }
+    }
+}
+
 // Stage 1.  peq32_base: table of the shared prefix, entry (code, lane) at code*256 + lane*4,
 // row Lp at bit 31.  kt = largest k of the round, ext = m_max - Lp + kt, back = Lp + kt + 1
 // (an alignment through (Lp, j') with <= kt errors starts at a column >= j' - Lp - kt).
@@ -365,7 +522,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                          const char *suffix_base = nullptr, int Ls = 0,
                          const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0, int m_min = 0,
                          int sfx_primary = 0, const uint32_t *first_mask = nullptr,
-                         const uint8_t *lut = nullptr)
+                         const uint8_t *lut = nullptr, const SeedWins *seeded = nullptr)
 {
     const uint32_t n = len;
     out.n = 0; out.flags = 0;
@@ -505,9 +662,16 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         }
         clu_f = 0;
     };
+    // Stage 1s: whole-adapter alignments were found through their seeds (seed_scan); only the
+    // windows of the alignments that run off an end of the read are decided here
+    const bool seeds = seeded != nullptr;
+    if (seeds) {
+        if (seeded->all) win_add(out, open, cs, ce, 0u, n);
+        for (uint32_t i = 0; i < seeded->n; i++) win_add(out, open, cs, ce, seeded->s[i], seeded->e[i]);
+    }
     ChunkReader rd;
     rd.init(W, lo, len, dir, 0u);
-    const int nchunks = (int)((n + 7u) >> 3);
+    const int nchunks = seeds ? 0 : (int)((n + 7u) >> 3);
     for (int q = 0; q < nchunks; q++) {
         uint32_t A, B;
         rd.next(A, B);
@@ -581,8 +745,9 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     for (int c = 0; c < n_clu; c++) add_cluster(clu_fs[c], clu_ls[c], true);
     if (type == TYPE_BACK) {
         uint32_t ePv = Pv, eMv = Mv;    // prefix rows 1..Lp of the last column
-        bool r6_near = !sp;             // prefix-primary rounds: not tracked, assume yes
-        if (sp) {
+        const bool restart = sp || seeds;   // the main loop did not scan the prefix: do its last columns here
+        bool r6_near = !restart;        // prefix-primary rounds: not tracked, assume yes
+        if (restart) {
             // prefix scan of the last m_max + 2k + 1 columns (restart: exact for every alignment
             // that can still reach the read end as a partial adapter)
             const uint32_t T = (uint32_t)(m_max + 2 * kt + 1);

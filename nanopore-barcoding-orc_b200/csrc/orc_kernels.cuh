@@ -89,12 +89,43 @@ __global__ void sort_keys_kernel(const View *__restrict__ views, const Match *__
     vals[r] = r;
 }
 
+// Stage 1s: one thread per read (in length order), both directions in one pass over the packed
+// codes: every 8-code window is looked up in the round's seed table (orc_core.cuh seed_scan).
+// The result, the windows of the whole-adapter alignments, goes to trigger_kernel, which then
+// only decides the windows at the read's ends.
+#ifndef SEED_BLOCKS
+#define SEED_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(256, SEED_BLOCKS)
+seed_kernel(const SeedTable *__restrict__ st, const uint32_t *__restrict__ W, const View *__restrict__ views,
+            const Match *__restrict__ prev, const uint32_t *__restrict__ order, uint32_t n_reads,
+            SeedWins *__restrict__ out)
+{
+    __shared__ __align__(16) uint32_t s_key[SEED_SLOTS];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&st->key[0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(&s_key[0]);
+        for (int i = threadIdx.x; i < SEED_SLOTS / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_reads) return;
+    const uint32_t r = order ? order[p] : p;
+    if (prev != nullptr && prev[r].adapter < 0) return;     // trigger_kernel skips these reads, too
+    const View v = views[r];
+    SeedWins sw[2];
+    seed_scan(W, v.lo, v.len, s_key, st->val, st->mult, st->list, st->need, st->kt, st->m_max, sw);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + 2u * r);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&sw[0]);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
 __global__ void __launch_bounds__(128)
 trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                const View *__restrict__ views, const Match *__restrict__ prev,
                const uint32_t *__restrict__ order, uint32_t n_reads, WinList *__restrict__ wins,
                uint32_t *__restrict__ wcols, uint32_t *__restrict__ item_ids,
-               unsigned long long *__restrict__ col_sum)
+               unsigned long long *__restrict__ col_sum, const SeedWins *__restrict__ seedwins)
 {
     __shared__ __align__(16) uint32_t s_peq32[16][64];
     __shared__ __align__(16) uint32_t s_peq32s[16][64];
@@ -138,7 +169,8 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                              (int)(2u * (threadIdx.x & 31u)) + dir, Lp, kt, type, (uint32_t)(m_max - Lp + kt),
                              (uint32_t)(Lp + kt + 1), wl,
                              s_par[6] > 0 ? reinterpret_cast<const char *>(&s_peq32s[0][0]) : nullptr,
-                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp, s_first_mask, s_lut);
+                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp, s_first_mask, s_lut,
+                             seedwins ? seedwins + (2u * r + (uint32_t)dir) : nullptr);
                 cols = win_columns(wl);
             } else {
                 wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything

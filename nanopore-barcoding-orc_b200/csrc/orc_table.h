@@ -194,6 +194,76 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
     return "";
 }
 
+// Stage 1s seed table (orc_core.cuh seed_scan): the leading floor(m / 8) eight-row pieces of every
+// adapter, in both directions, behind a perfect hash.  Off (S.on == 0) when the round has no
+// stage-1 filter, when some adapter has fewer pieces than errors + 1, or when no collision-free
+// multiplier turns up.
+inline void build_seed_table(const RoundTable &T, SeedTable &S, bool enable)
+{
+    memset(&S, 0, sizeof(S));
+    for (int i = 0; i < SEED_SLOTS; i++) S.key[i] = SEED_EMPTY;
+    if (!enable || !T.use_filter) return;
+    int need = 2;
+    for (int a = 0; a < T.n_adapters; a++) {
+        const int avail = T.m[a] / 8 - T.k[a];
+        if (avail < 1) return;
+        if (avail < need) need = avail;
+    }
+    struct Ent { uint32_t key, info; };
+    Ent ents[2 * MAX_AD * (MAX_M / 8)];
+    int n_ent = 0;
+    for (int a = 0; a < T.n_adapters; a++)
+        for (int t = 0; t < T.m[a] / 8; t++)
+            for (int d = 0; d < 2; d++) {
+                uint32_t key = 0;
+                for (int u = 0; u < 8; u++) {
+                    // direction 0: storage codes == adapter codes; direction 1: the storage holds the
+                    // reverse complement of what the lane reads
+                    const uint32_t c = d ? comp4(T.code[a][8 * t + 7 - u]) : (uint32_t)T.code[a][8 * t + u];
+                    key |= c << (4 * u);
+                }
+                const uint32_t info = ((uint32_t)t << 16) | ((uint32_t)d << 20);
+                int f = -1;
+                for (int i = 0; i < n_ent; i++) if (ents[i].key == key && (ents[i].info & 0x1F0000u) == info) f = i;
+                if (f >= 0) ents[f].info |= 1u << a;
+                else { ents[n_ent].key = key; ents[n_ent].info = info | (1u << a); n_ent++; }
+            }
+    // group the entries by key
+    uint32_t keys[2 * MAX_AD * (MAX_M / 8)];
+    int n_keys = 0;
+    for (int i = 0; i < n_ent; i++) {
+        bool seen = false;
+        for (int j = 0; j < n_keys; j++) if (keys[j] == ents[i].key) seen = true;
+        if (!seen) keys[n_keys++] = ents[i].key;
+    }
+    if (n_ent > SEED_LIST_MAX) return;
+    uint32_t mult = 0;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    static int stamp[SEED_SLOTS];
+    for (int attempt = 1; attempt <= 200000 && !mult; attempt++) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        const uint32_t cand = (uint32_t)(rng >> 32) | 1u;
+        bool ok = true;
+        for (int j = 0; j < n_keys && ok; j++) {
+            const uint32_t h = (keys[j] * cand) >> SEED_SHIFT;
+            if (stamp[h] == attempt) ok = false;
+            stamp[h] = attempt;
+        }
+        if (ok) mult = cand;
+    }
+    for (int i = 0; i < SEED_SLOTS; i++) stamp[i] = 0;
+    if (!mult) return;
+    int n_list = 0;
+    for (int j = 0; j < n_keys; j++) {
+        const uint32_t h = (keys[j] * mult) >> SEED_SHIFT;
+        const int first = n_list;
+        for (int i = 0; i < n_ent; i++) if (ents[i].key == keys[j]) S.list[n_list++] = ents[i].info;
+        S.key[h] = keys[j];
+        S.val[h] = (uint32_t)first | ((uint32_t)(n_list - first) << 16);
+    }
+    S.on = 1; S.need = need; S.mult = mult; S.n_list = n_list; S.kt = T.k_max; S.m_max = T.m_max;
+}
+
 // Anchored, no-indel round (ORC_PREFIX / ORC_SUFFIX).  Also fills the few RoundTable fields the
 // selection kernel reads (type as trimming side, revcomp, n_adapters).
 inline std::string build_anchored_table(AnchoredTable &A, RoundTable &T, int n_adapters, int suffix,

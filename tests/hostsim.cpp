@@ -16,17 +16,20 @@
 
 using namespace orc;
 
-static uint64_t g_pairs[2], g_kept[2];
+static uint64_t g_pairs[2], g_kept[2], g_seeded[2];
 extern "C" void hostsim_stats(uint64_t *out) { out[0] = g_pairs[0]; out[1] = g_kept[0]; out[2] = g_pairs[1]; out[3] = g_kept[1]; }
+// reads whose stage 1 went through the seed table, per round
+extern "C" void hostsim_seeded(uint64_t *out) { out[0] = g_seeded[0]; out[1] = g_seeded[1]; }
 extern "C" int hostsim_demux(int n_rounds,
                              int n_ad0, int type0, const char *const *seq0, double e0, int ov0, int rc0,
                              int n_ad1, int type1, const char *const *seq1, double e1, int ov1, int rc1,
                              const uint8_t *seq, const uint64_t *offsets, const uint32_t *lengths,
                              uint32_t n_reads, uint64_t n_bytes,
                              Match *m0, Match *m1, uint64_t *out_lo, uint32_t *out_len, uint32_t *out_rc,
-                             uint64_t *n_tasks, char *err, int err_len, int filter_mode, uint64_t *n_columns,
+                             uint64_t *n_tasks, char *err, int err_len, int filter_mode_in, uint64_t *n_columns,
                              int indels)
 {
+    const int filter_mode = filter_mode_in & 3;
     RoundTable *T = new RoundTable[2];
     AnchoredTable *AT = new AnchoredTable[2];
     bool anch[2] = {type0 >= 2, n_rounds > 1 && type1 >= 2};
@@ -35,6 +38,12 @@ extern "C" int hostsim_demux(int n_rounds,
     if (e.empty() && n_rounds > 1)
         e = anch[1] ? build_anchored_table(AT[1], T[1], n_ad1, type1 == 3, seq1, e1, 0, rc1)
                     : build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, indels, rc1, filter_mode);
+    // filter_mode bit 2 (value 4) keeps the flank scan of stage 1 although seeds would be usable
+    SeedTable *ST = new SeedTable[2];
+    for (int rd = 0; rd < n_rounds; rd++) {
+        ST[rd].on = 0;
+        if (e.empty() && !anch[rd]) build_seed_table(T[rd], ST[rd], (filter_mode_in & 4) == 0);
+    }
     uint8_t comp_lut[256];
     build_complement_lut(comp_lut);
     if (!e.empty()) {
@@ -42,13 +51,14 @@ extern "C" int hostsim_demux(int n_rounds,
         err[err_len - 1] = 0;
         delete[] T;
         delete[] AT;
+        delete[] ST;
         return -1;
     }
     uint8_t lut[256];
     build_pack_lut(lut);
-    // flat pack with 4 guard words on each side, like the device buffers
+    // flat pack with 4 guard words in front and 16 + 4 behind, like the device buffers
     const uint64_t n_words = (n_bytes + 7) / 8;
-    std::vector<uint32_t> codes(n_words + 8, 0);
+    std::vector<uint32_t> codes(n_words + 24, 0);
     uint32_t *W = codes.data() + 4;
     for (uint64_t i = 0; i < n_bytes; i++) W[i >> 3] |= (uint32_t)lut[seq[i]] << ((i & 7) * 4);
 
@@ -79,12 +89,19 @@ extern "C" int hostsim_demux(int n_rounds,
                 continue;
             }
             WinList wl[2];
+            SeedWins sw[2];
+            if (R.use_filter && ST[rd].on) {
+                seed_scan(W, v.lo, v.len, ST[rd].key, ST[rd].val, ST[rd].mult, ST[rd].list, ST[rd].need, ST[rd].kt,
+                          ST[rd].m_max, sw);
+                g_seeded[rd]++;
+            }
             if (R.use_filter) {
                 for (int dir = 0; dir < 2; dir++) {
                     trigger_lane(W, v.lo, v.len, dir, (const char *)&R.peq32[0][0], dir, R.lcp, R.k_max, R.type,
                                  (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + R.k_max + 1), wl[dir],
                                  R.lcs > 0 ? (const char *)&R.peq32s[0][0] : nullptr, R.lcs,
-                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary, R.first_mask, R.chunk_lut);
+                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary, R.first_mask, R.chunk_lut,
+                                 ST[rd].on ? &sw[dir] : nullptr);
                     n_columns[rd] += win_columns(wl[dir]);
                 }
             } else n_columns[rd] += 2ull * v.len;
@@ -128,5 +145,6 @@ extern "C" int hostsim_demux(int n_rounds,
     delete ring;
     delete[] T;
     delete[] AT;
+    delete[] ST;
     return 0;
 }

@@ -119,7 +119,7 @@ def test_slots_and_resident_relaunch():
         assert ra.fastq.tobytes() == ra2.fastq.tobytes()
         assert np.array_equal(ra.bin, ra2.bin)
         t = eng.timings(0)
-        assert t["kernel_launches"] == 19 and t["total_ms"] > 0
+        assert t["kernel_launches"] == 21 and t["total_ms"] > 0      # 19 + one seed_kernel per round
         tot = eng.counts()
         assert int(tot.sum()) == 2 * a.n_reads + b.n_reads
     finally:

@@ -9,7 +9,9 @@ rnd = random.Random(seed)
 t0=time.time(); total=0
 for trial in range(trials):
     nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
-    mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([3, 5, 8, 12, 17, 20, 33, 40, 57, 64])))
+    long_only = rnd.random() < 0.45       # long adapters at low error rates: stage 1 goes through the seed table
+    lens = [40, 48, 57, 59, 64, 64] if long_only else [3, 5, 8, 12, 17, 20, 33, 40, 57, 64]
+    mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice(lens)))
     shared = mk()[:rnd.choice([4, 10, 17, 25, 32, 40])]
     pshare = rnd.choice([0.5, 1.0, 1.0])
     sfx = mk()[:rnd.choice([0, 3, 8, 17, 30])]
@@ -20,6 +22,7 @@ for trial in range(trials):
     if rnd.random()<0.3:  # low complexity adapters
         f=[ (x[:4]*16)[:len(x)] for x in f]; b=[(x[:3]*22)[:len(x)] for x in b]
     e = rnd.choice([0.0, 0.05, 0.1, 0.1, 0.2, 0.3, 0.4, 0.6, 0.9, 2])
+    if long_only: e = rnd.choice([0.0, 0.03, 0.05, 0.08, 0.1, 0.1, 0.12, 3])
     if e >= 1 and min(len(x) for x in f + b) <= e: e = 0.25
     ov = rnd.choice([1, 2, 3, 3, 5, 8, 20]); rc = rnd.choice([0, 1, 1])
     rounds = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
@@ -37,7 +40,7 @@ for trial in range(trials):
         recs.append(("s%d"%i, s, "I"*len(s)))
     rs=synth.from_records(recs)
     rec0, rec1, oseq, oqual, olen = None, None, None, None, None
-    fmode = rnd.choice([0, 1, 2, 2, 2])
+    fmode = rnd.choice([0, 1, 2, 2, 2]) | rnd.choice([0, 0, 0, 4])      # bit 2: keep the flank scan
     indels = rnd.choice([1, 1, 1, 0])
     m0, m1, lo, ln, rcv, nt = H.run_hostsim(rounds, rs, fmode, indels=indels)
     rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=8, indels=bool(indels))
@@ -50,4 +53,7 @@ for trial in range(trials):
             print(" oracle", a[i]); print(" hostsim", bb[i]); print(" seq", rs.read(i)[1]); print(rounds)
             sys.exit(1)
     assert np.array_equal(olen, ln)
-print("ok seed",seed,"reads",total,"time",time.time()-t0)
+import ctypes
+sd = (ctypes.c_uint64 * 2)()
+H.hostsim().hostsim_seeded(sd)
+print("ok seed",seed,"reads",total,"seeded (read, round) passes",sd[0],sd[1],"time",time.time()-t0)
