@@ -43,10 +43,10 @@ UNIT = "reads/s"
 # ALU-pipe instructions per DP column of one (read, adapter, orientation) pair in
 # scan_kernel's inner loop, counted in the SASS (profiles/README.md); a column is m cells.
 SCAN_ALU_INSTR_PER_COLUMN = 24.0
-# DRAM traffic of the scan stages (trigger_kernel + filter_kernel + scan_kernel, both rounds) per read, from the
-# ncu --set full capture profiles/r1m_main_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum
-# of the six launches at 262 144 COI reads, divided by the reads)
-SCAN_DRAM_BYTES_PER_READ = 2.367e3
+# DRAM traffic of the scan stages (seed_kernel + trigger_kernel + filter_kernel + scan_kernel, both rounds)
+# per read, from the ncu --set full capture profiles/r1n_main_raw.csv (dram__bytes_read.sum +
+# dram__bytes_write.sum of the eight launches at 262 144 COI reads, divided by the reads)
+SCAN_DRAM_BYTES_PER_READ = 3.157e3
 
 
 def parse_args():
@@ -373,16 +373,16 @@ def main():
         ach_gcups = cells / (scan_ms * 1e-3) / 1e9
         exe_gcups = float(sum(t["cells_executed"])) / (scan_ms * 1e-3) / 1e9
         roofline = {"bound": "int32_alu",
-                    "kernel": "scan = trigger_kernel (stage 1) + filter_kernel (stage 2a) + scan_kernel (stage 2b), both rounds",
+                    "kernel": "scan = seed_kernel + trigger_kernel (stage 1) + filter_kernel (stage 2a) + scan_kernel (stage 2b), both rounds",
                     "achieved": ach_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": ach_gcups / peak_gcups,
                     "traffic": SCAN_DRAM_BYTES_PER_READ * args.reads if args.config == 2 else None,
-                    "traffic_how": "ncu dram bytes of the scan launches per read (profiles/r1m_main_raw.csv) x reads; "
+                    "traffic_how": "ncu dram bytes of the scan launches per read (profiles/r1n_main_raw.csv) x reads; "
                                    "ALU-bound kernels: traffic is the packed codes read once per stage, far below HBM limits",
                     "executed": {"achieved": exe_gcups, "frac": exe_gcups / peak_gcups,
                                  "note": "DP cells the kernels really update; the rest of the algorithmic cells "
                                          "(2*12*m*n per read and round, SURVEY 8d) are skipped exactly by the "
-                                         "shared-flank trigger filter (stage 1) and the 32-row block test "
-                                         "(stage 2a), which is why `frac` exceeds 1"},
+                                         "seed filter (stage 1, no DP cells at all in its main pass) and the "
+                                         "32-row block test (stage 2a), which is why `frac` exceeds 1"},
                     "peak_how": "measured LOP3 issue rate %.3g lane-op/s (orc_measure_int32_peak mode 0, this GPU, this "
                                 "run) / %.0f ALU-pipe instr per 64-bit Myers column x %d rows = what an exhaustive "
                                 "per-pair scan can reach; LOP3+IMAD mix: %.3g" %
