@@ -221,6 +221,22 @@ def main():
         emit({"error": "no CUDA device: bench.py has no CPU fallback for the product arm"})
         return 2
     torch.cuda.set_device(local_rank)
+    # pinned buffers should live on the GPU's own NUMA node: bind this rank to the CPUs NVML names
+    # for the device before anything page-locked is allocated (undone for the CPU baseline)
+    all_cpus = os.sched_getaffinity(0)
+    numa = "unbound"
+    if os.environ.get("ORC_BENCH_AFFINITY", "1") == "1":
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)).encode())
+            words = nv.nvmlDeviceGetCpuAffinity(h, (max(all_cpus) // 64) + 1)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & all_cpus
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = "%d of %d cpus" % (len(cpus), len(all_cpus))
+        except Exception as e:
+            numa = "unbound (%s)" % type(e).__name__
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -402,6 +418,7 @@ def main():
         import oracle
         oracle.build()
         n_s = args.cpu_sample or 16384
+        os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core
         sub_n, times = cpu_arm(rs, n_s, ncpu, 1, 0)
         cpu_baseline = {"value": sub_n / times[0], "unit": UNIT, "cores": ncpu, "kind": "port",
                         "sample": "first %d reads of the workload, one pass, %d threads (restated-cutadapt CPU "
@@ -423,7 +440,7 @@ def main():
                        "collective; all_reduce of %d bin counters at the end" % int(counts.numel())},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "stages_ms_last_step": stage, "wall_ms_per_step": wall_ms / args.steps,
-            "reads_binned_all_ranks": total_reads_binned, "gen_s": gen_s,
+            "reads_binned_all_ranks": total_reads_binned, "gen_s": gen_s, "cpu_affinity": numa,
         }
         line.update(extra)
         emit(line)
