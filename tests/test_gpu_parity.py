@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path, called through the C ABI (orcdemux.Engine is a thin
 ctypes wrapper), against the CPU oracle on the same seeded inputs.  Bit-exact: adapter,
 orientation, all six alignment fields, bin, trimmed bytes, order inside each bin."""
+import os
+
 import numpy as np
 import pytest
 
@@ -231,6 +233,39 @@ def test_adversarial_and_random_adapter_sets():
             idx, nbad = H.diff_matches(rec[1], res.matches[1])
             assert nbad == 0, (trial, "round 2", idx[:3])
         assert np.array_equal(res.out_len, rec[4])
+
+
+def test_seeded_stage1_random_adapter_sets():
+    """Adapter sets stage 1 can seed (long adapters, long shared prefix, low error rates; pieces per
+    adapter minus errors 1 or 2) through the kernels, with and without the seed table."""
+    import random
+    import oracle
+    import test_hostsim as TH
+    from orcdemux.lib import ORC_BACK, ORC_FRONT
+    rnd = random.Random(777)
+    for trial in range(8):
+        f, b, e, ov, rc = TH._seed_friendly_sets(rnd)
+        spec = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
+        if trial % 3 == 2:
+            spec = spec[::-1]
+        rs = TH._adversarial_reads(rnd, f, b, 3000)
+        rounds = [E.Round([str(i) for i in range(len(x[0]))], x[0], ORC_FRONT if x[1] == oracle.FRONT else ORC_BACK,
+                          x[2], x[3], True, bool(x[4])) for x in spec]
+        rec = H.run_oracle(spec, rs)
+        for no_seed in ("0", "1"):
+            os.environ["ORC_NO_SEED"] = no_seed
+            try:
+                with E.Engine(rounds, max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]) + 64, n_slots=1) as eng:
+                    res = eng.run(rs)
+                    launches = eng.timings(0)["kernel_launches"]
+            finally:
+                os.environ.pop("ORC_NO_SEED", None)
+            assert H.diff_matches(rec[0], res.matches[0])[1] == 0, (trial, no_seed, "round 1")
+            assert H.diff_matches(rec[1], res.matches[1])[1] == 0, (trial, no_seed, "round 2")
+            assert np.array_equal(res.out_len, rec[4])
+            if no_seed == "1":
+                assert launches == 19
+        # (with seeds the count is 19 + the rounds whose table could be built: checked for M13 above)
 
 
 def test_long_reads_and_capacity_errors():

@@ -124,6 +124,51 @@ def test_random_adapter_sets():
         _compare(rounds, _adversarial_reads(rnd, f, b, 400), threads=4)
 
 
+def _seed_friendly_sets(rnd):
+    """Adapter sets stage 1 can seed: every adapter at least 8 (k + 1) long, a long shared prefix."""
+    nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
+    mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([40, 48, 57, 59, 64])))
+    shared = mk()[:rnd.choice([17, 25, 32])]
+    sfx = mk()[:rnd.choice([0, 8, 17, 23])]
+    f = [(shared + mk())[:64 - len(sfx)] + sfx for _ in range(nf)]
+    b = [(shared + mk())[:64 - len(sfx)] + sfx for _ in range(nb)]
+    e = rnd.choice([0.0, 0.03, 0.05, 0.08, 0.1, 0.1])       # floor(m / 8) - k is 1 or more, often exactly 1 or 2
+    return f, b, e, rnd.choice([1, 3, 3, 8]), rnd.choice([0, 1, 1])
+
+
+def _seeded_passes():
+    import ctypes
+    sd = (ctypes.c_uint64 * 2)()
+    H.hostsim().hostsim_seeded(sd)
+    return int(sd[0]) + int(sd[1])
+
+
+def test_seeded_stage1_m13_and_random_sets():
+    """Stage 1s (exact 8-mer seeds): the seeded path, the flank scan
+    it replaces (filter_mode bit 2) and the oracle agree; the seeded path is really taken."""
+    rnd = random.Random(4242)
+    f = [s for _, s in m13.sp5_forward()]
+    b = [s for _, s in m13.sp27_reverse_rc()]
+    rs = _adversarial_reads(rnd, f, b, 3000)
+    before = _seeded_passes()
+    rec0, rec1 = _compare(H.m13_rounds(), rs)
+    assert _seeded_passes() - before >= rs.n_reads          # round 1 of every read, round 2 of the assigned ones
+    mid = _seeded_passes()
+    m0, m1, lo, ln, rc, nt = H.run_hostsim(H.m13_rounds(), rs, filter_mode=1 | 4)
+    assert _seeded_passes() == mid                          # bit 2: no seeds
+    assert H.diff_matches(rec0, m0)[1] == 0 and H.diff_matches(rec1, m1)[1] == 0
+    seeded = 0
+    for trial in range(10):
+        f, b, e, ov, rc_ = _seed_friendly_sets(rnd)
+        rounds = [(f, oracle.FRONT, e, ov, rc_), (b, oracle.BACK, e, ov, rc_)]
+        if trial % 3 == 2:
+            rounds = rounds[::-1]
+        before = _seeded_passes()
+        _compare(rounds, _adversarial_reads(rnd, f, b, 400), threads=4)
+        seeded += _seeded_passes() - before
+    assert seeded > 2000
+
+
 def test_no_indels_unanchored():
     """--no-indels on regular adapters: Hamming distance along diagonals, settled in the scan."""
     rnd = random.Random(17)
