@@ -409,7 +409,7 @@ struct SeedTable {
 struct SeedWins {                   // the seed windows of one (read, direction), increasing, disjoint
     uint32_t n;
     uint32_t s[MAX_WIN], e[MAX_WIN];
-    uint32_t all;                   // too many hits to keep apart: scan every column
+    uint32_t all;                   // too many hits to keep apart: this (read, direction) takes the flank scan
 };
 
 struct Quad { uint32_t w[4]; };
@@ -664,11 +664,11 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     };
     // Stage 1s: whole-adapter alignments were found through their seeds (seed_scan); only the
     // windows of the alignments that run off an end of the read are decided here
-    const bool seeds = seeded != nullptr;
-    if (seeds) {
-        if (seeded->all) win_add(out, open, cs, ce, 0u, n);
+    // (a read with more key matches than seed_scan keeps apart -- tens of kilobases of sequence --
+    // takes the flank scan below instead)
+    const bool seeds = seeded != nullptr && !seeded->all;
+    if (seeds)
         for (uint32_t i = 0; i < seeded->n; i++) win_add(out, open, cs, ce, seeded->s[i], seeded->e[i]);
-    }
     ChunkReader rd;
     rd.init(W, lo, len, dir, 0u);
     const int nchunks = seeds ? 0 : (int)((n + 7u) >> 3);

@@ -157,6 +157,10 @@ def test_seeded_stage1_m13_and_random_sets():
     m0, m1, lo, ln, rc, nt = H.run_hostsim(H.m13_rounds(), rs, filter_mode=1 | 4)
     assert _seeded_passes() == mid                          # bit 2: no seeds
     assert H.diff_matches(rec0, m0)[1] == 0 and H.diff_matches(rec1, m1)[1] == 0
+    # tens of kilobases: more chance key matches than the seed scan keeps apart -> flank scan
+    body = "".join(rnd.choice("ACGT") for _ in range(40000))
+    long_recs = [("l0", f[3] + body + b[4]), ("l1", m13.revcomp(f[5] + body + b[1])), ("l2", body[:20000] + f[2] + body[20000:])]
+    _compare(H.m13_rounds(), synth.from_records([(nm, sq, "I" * len(sq)) for nm, sq in long_recs]))
     seeded = 0
     for trial in range(10):
         f, b, e, ov, rc_ = _seed_friendly_sets(rnd)
