@@ -71,7 +71,7 @@ def _parse_adapter_specs(specs: List[str], kind: int):
 
 def parse_cutadapt_argv(argv: List[str]):
     opt = dict(e=0.1, O=3, rc=False, indels=True, action="trim", json=None, out=None, cores=1,
-               g=[], a=[], level=5, inputs=[], quiet=False)
+               g=[], a=[], level=1, inputs=[], quiet=False)      # cutadapt 4.x: gzip level 1 unless --compression-level
     i = 0
 
     def need(flag):
@@ -416,6 +416,7 @@ def run_two_round(args: List[str], device=0) -> int:
     ap.add_argument("--keep-invalid", action="store_true", help="keep SP27_009..012 combinations")
     ap.add_argument("--no-gzip", action="store_true")
     ap.add_argument("-j", type=int, default=8)
+    ap.add_argument("--compression-level", type=int, default=1, help="gzip level of the bin files (cutadapt 4.x default: 1)")
     a = ap.parse_args(args)
     n5, s5 = F.read_adapters_fasta(a.sp5)
     n27, s27 = F.read_adapters_fasta(a.sp27)
@@ -440,7 +441,7 @@ def run_two_round(args: List[str], device=0) -> int:
         paths[b] = os.path.join(outdir, "SP27", "%s_%s_%s%s" % (nm27, nm5, ds, ext))
     (max_reads, max_bytes), slots = _batch_shape(), 3
     reader = F.FastqReader(a.input, max_reads, max_bytes, keep=3, ahead=2)
-    writers = F.BinWriters(paths, 5, threads=max(2, min(os.cpu_count() or 2, a.j)))
+    writers = F.BinWriters(paths, a.compression_level, threads=max(2, min(os.cpu_count() or 2, a.j)))
     t0 = time.time()
     n_in = 0
 
