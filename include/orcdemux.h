@@ -226,6 +226,23 @@ int orc_writer_wait(orc_writer *w, int64_t ticket);
 const char *orc_writer_error(orc_writer *w);
 int orc_writer_close(orc_writer *w, uint64_t *bytes_per_bin);
 
+/*
+ * Pairwise unit-cost edit distance of whole sequences (csrc/orc_edit.cuh), the drop-in for what
+ * amplicon_sorter asks of edlib for every pair it compares
+ * (/root/reference/scripts/auxiliary_code/amplicon_sorter.py:225-235 distance(), mode NW;
+ *  :838-849 distance_finetune(), mode HW):
+ *      edlib.align(A1, A2, task='distance', mode=mode)['editDistance'], A1 the shorter sequence.
+ * seqs/offsets/lengths: n_seqs sequences in one blob (any bytes, compared for equality; at most 8
+ * distinct bytes per call); pair k compares sequences pair_a[k] and pair_b[k] (the shorter one is
+ * the query; on equal lengths pair_a[k] is) and dist[k] receives the distance.  Host buffers in
+ * and out; *kernel_ms (optional) = device time of the kernels.  Returns 0 or a negative ORC_E*
+ * code with the reason in err.  Queries longer than 8192 are refused; no CPU fallback.
+ */
+enum { ORC_EDIT_NW = 0, ORC_EDIT_HW = 1 };
+int orc_edit_distances(int device, const uint8_t *seqs, const uint64_t *offsets, const uint32_t *lengths,
+                       uint32_t n_seqs, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n_pairs,
+                       int mode, uint32_t *dist, float *kernel_ms, char *err, size_t err_len);
+
 /* pinned host memory for callers that do not bring their own */
 void *orc_host_alloc(size_t bytes);
 void orc_host_free(void *p);

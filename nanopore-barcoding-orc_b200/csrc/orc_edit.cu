@@ -1,0 +1,126 @@
+// orc_edit.cu -- C ABI of the pairwise edit-distance kernel (orc_edit.cuh): the drop-in for
+// amplicon_sorter's distance() / distance_finetune() (amplicon_sorter.py:225-235, :838-849).
+#include "../../include/orcdemux.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "orc_edit.cuh"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+int fail(char *err, size_t err_len, int code, const std::string &what)
+{
+    if (err && err_len) snprintf(err, err_len, "%s", what.c_str());
+    return code;
+}
+
+}  // namespace
+
+#define ECK(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(err, err_len, ORC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_t *offsets, const uint32_t *lengths,
+                                  uint32_t n_seqs, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n_pairs,
+                                  int mode, uint32_t *dist, float *kernel_ms, char *err, size_t err_len)
+{
+    using namespace orc;
+    if ((n_seqs && (!seqs || !offsets || !lengths)) || (n_pairs && (!pair_a || !pair_b || !dist)) ||
+        (mode != ORC_EDIT_NW && mode != ORC_EDIT_HW) || n_pairs > 0xFFFFFFFFull)
+        return fail(err, err_len, ORC_EINVAL, "orc_edit_distances: bad argument");
+    if (kernel_ms) *kernel_ms = 0.0f;
+    if (n_pairs == 0) return ORC_OK;
+    // the batch's alphabet: every distinct byte is its own symbol (edlib compares bytes)
+    uint64_t n_bytes = 0;
+    for (uint32_t i = 0; i < n_seqs; i++)
+        if (offsets[i] + lengths[i] > n_bytes) n_bytes = offsets[i] + lengths[i];
+    int map[256];
+    for (int i = 0; i < 256; i++) map[i] = -1;
+    int n_sym = 0;
+    std::vector<uint8_t> sym(n_bytes);
+    for (uint32_t i = 0; i < n_seqs; i++)
+        for (uint64_t p = offsets[i]; p < offsets[i] + lengths[i]; p++) {
+            const uint8_t c = seqs[p];
+            if (map[c] < 0) {
+                if (n_sym == EDIT_SYMS)
+                    return fail(err, err_len, ORC_EINVAL, "unsupported: more than 8 distinct characters in the batch");
+                map[c] = n_sym++;
+            }
+            sym[p] = (uint8_t)map[c];
+        }
+    // pairs by the number of 64-row blocks a lane has to hold
+    std::vector<uint32_t> todo[3];
+    for (uint64_t k = 0; k < n_pairs; k++) {
+        if (pair_a[k] >= n_seqs || pair_b[k] >= n_seqs)
+            return fail(err, err_len, ORC_EINVAL, "orc_edit_distances: pair index out of range");
+        const uint32_t la = lengths[pair_a[k]], lb = lengths[pair_b[k]];
+        const uint32_t m = la < lb ? la : lb;
+        if (m > 32u * 64u * EDIT_MAX_WB)
+            return fail(err, err_len, ORC_EINVAL, "unsupported: sequences longer than 8192 on both sides of a pair");
+        todo[m <= 2048u ? 0 : m <= 4096u ? 1 : 2].push_back((uint32_t)k);
+    }
+    if (cudaSetDevice(device) != cudaSuccess)
+        return fail(err, err_len, ORC_ECUDA, "no usable CUDA device (there is no CPU fallback)");
+    cudaDeviceProp prop;
+    ECK(cudaGetDeviceProperties(&prop, device));
+    DevBuf d_sym, d_off, d_len, d_pa, d_pb, d_out, d_todo;
+    ECK(d_sym.alloc(n_bytes + 64));
+    ECK(d_off.alloc(8ull * n_seqs));
+    ECK(d_len.alloc(4ull * n_seqs));
+    ECK(d_pa.alloc(4ull * n_pairs));
+    ECK(d_pb.alloc(4ull * n_pairs));
+    ECK(d_out.alloc(4ull * n_pairs));
+    ECK(d_todo.alloc(4ull * n_pairs));
+    ECK(cudaMemcpy(d_sym.p, sym.data(), n_bytes, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(d_off.p, offsets, 8ull * n_seqs, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(d_len.p, lengths, 4ull * n_seqs, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(d_pa.p, pair_a, 4ull * n_pairs, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(d_pb.p, pair_b, 4ull * n_pairs, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    ECK(cudaEventCreate(&e0));
+    ECK(cudaEventCreate(&e1));
+    ECK(cudaEventRecord(e0, 0));
+    uint64_t done = 0;
+    for (int cls = 0; cls < 3; cls++) {
+        const uint32_t nt = (uint32_t)todo[cls].size();
+        if (!nt) continue;
+        uint32_t *d_list = (uint32_t *)d_todo.p + done;
+        ECK(cudaMemcpyAsync(d_list, todo[cls].data(), 4ull * nt, cudaMemcpyHostToDevice, 0));
+        const int wb = cls == 0 ? 1 : cls == 1 ? 2 : 4;
+        const size_t smem = 4u * EDIT_SYMS * wb * 32u * sizeof(uint64_t);
+        const uint32_t want = (nt + 3u) / 4u, cap = (uint32_t)prop.multiProcessorCount * 8u;
+        const uint32_t blocks = want < cap ? want : cap;
+        const uint8_t *ds = (const uint8_t *)d_sym.p;
+        const uint64_t *dof = (const uint64_t *)d_off.p;
+        const uint32_t *dl = (const uint32_t *)d_len.p, *da = (const uint32_t *)d_pa.p, *db = (const uint32_t *)d_pb.p;
+        uint32_t *dout = (uint32_t *)d_out.p;
+        if (wb == 1) edit_kernel<1><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        else if (wb == 2) edit_kernel<2><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        else edit_kernel<4><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        ECK(cudaGetLastError());
+        done += nt;
+    }
+    ECK(cudaEventRecord(e1, 0));
+    ECK(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    ECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (kernel_ms) *kernel_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ECK(cudaMemcpy(dist, d_out.p, 4ull * n_pairs, cudaMemcpyDeviceToHost));
+    return ORC_OK;
+}

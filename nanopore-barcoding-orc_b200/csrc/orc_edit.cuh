@@ -1,0 +1,157 @@
+// orc_edit.cuh -- pairwise unit-cost edit distance of whole reads, the arithmetic amplicon_sorter
+// delegates to edlib ("next" row N3):
+//
+//   /root/reference/scripts/auxiliary_code/amplicon_sorter.py:225-235   distance()          mode NW
+//   /root/reference/scripts/auxiliary_code/amplicon_sorter.py:838-849   distance_finetune() mode HW
+//       edlib.align(shorter, longer, task='distance', mode=...)['editDistance']
+//
+// Myers' bit-vector algorithm in blocks of 64 query rows (the formulation edlib itself uses): a
+// block takes the horizontal delta hin in {-1, 0, +1} that enters its top row in a column and
+// hands the one leaving its bottom row to the block below.  One warp works on one pair: lane l
+// owns WB consecutive blocks and, at step t, is in column t - l, so the delta a lane needs from
+// the lane above was produced one step earlier and travels by a single shuffle -- the warp sweeps
+// the matrix as a skewed wavefront, every lane busy except while the pipeline fills and drains.
+// NW: row 0 costs j (hin = +1 into block 0), the answer is D[m][n].  HW: row 0 is free (hin = 0),
+// the answer is the minimum of D[m][j] over the columns.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ORC_EHD __host__ __device__ __forceinline__
+#else
+#define ORC_EHD inline
+#endif
+
+namespace orc {
+
+constexpr int EDIT_SYMS = 8;            // distinct bytes a batch may contain (ACGT, N, three more)
+constexpr int EDIT_MAX_WB = 4;          // blocks per lane: queries up to 32 * 4 * 64 = 8192 rows
+
+// One block, one column.  Returns hout; hrow = the horizontal delta at bit `rbit` (the query's
+// last row when this is its last block).
+ORC_EHD int myers_block_step(uint64_t &Pv, uint64_t &Mv, uint64_t Eq, int hin, int rbit, int &hrow)
+{
+    const uint64_t neg = hin < 0 ? 1ull : 0ull;
+    const uint64_t Xv = Eq | Mv;
+    Eq |= neg;
+    const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    uint64_t Ph = Mv | ~(Xh | Pv);
+    uint64_t Mh = Pv & Xh;
+    const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+    hrow = (int)((Ph >> rbit) & 1ull) - (int)((Mh >> rbit) & 1ull);
+    Ph <<= 1; Mh <<= 1;
+    Mh |= neg;
+    Ph |= hin > 0 ? 1ull : 0ull;
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+    return hout;
+}
+
+// match bits of query rows 64 blk .. 64 blk + 63 against symbol s
+ORC_EHD uint64_t edit_eq_word(const uint8_t *q, uint32_t m, uint32_t blk, uint32_t s)
+{
+    uint64_t w = 0;
+    const uint32_t base = 64u * blk;
+    for (uint32_t i = 0; i < 64u && base + i < m; i++)
+        if (q[base + i] == s) w |= 1ull << i;
+    return w;
+}
+
+// The same computation block after block, column after column (no skew): what the kernel must
+// produce, used by the host simulation.
+inline uint32_t edit_distance_blocks(const uint8_t *q, uint32_t m, const uint8_t *t, uint32_t n, int mode)
+{
+    if (m == 0) return mode ? 0u : n;
+    const uint32_t nb = (m + 63u) / 64u;
+    uint64_t *Pv = new uint64_t[nb], *Mv = new uint64_t[nb];
+    for (uint32_t b = 0; b < nb; b++) { Pv[b] = ~0ull; Mv[b] = 0; }
+    const int rbit = (int)((m - 1u) & 63u);
+    uint32_t score = m, best = m;
+    for (uint32_t j = 0; j < n; j++) {
+        int hin = mode ? 0 : 1;
+        for (uint32_t b = 0; b < nb; b++) {
+            int hrow;
+            hin = myers_block_step(Pv[b], Mv[b], edit_eq_word(q, m, b, t[j]), hin, rbit, hrow);
+            if (b == nb - 1u) score = (uint32_t)((int)score + hrow);
+        }
+        if (score < best) best = score;
+    }
+    delete[] Pv;
+    delete[] Mv;
+    return mode ? best : score;
+}
+
+#if defined(__CUDACC__)
+// sym: the batch's bytes mapped to 0 .. EDIT_SYMS-1.  Dynamic shared memory: per warp
+// EDIT_SYMS * WB * 32 match words, laid out [symbol][k][lane].
+template <int WB>
+__global__ void __launch_bounds__(128, 8)
+edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, const uint32_t *__restrict__ len,
+            const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b,
+            const uint32_t *__restrict__ todo, uint32_t n_todo, int mode, uint32_t *__restrict__ out)
+{
+    extern __shared__ uint64_t s_eq_all[];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t *s_eq = s_eq_all + (size_t)(threadIdx.x >> 5) * (EDIT_SYMS * WB * 32);
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = warp; w < n_todo; w += n_warps) {
+        const uint32_t pair = todo[w];
+        uint32_t a = pair_a[pair], b = pair_b[pair];
+        if (len[a] > len[b]) { const uint32_t x = a; a = b; b = x; }   // the longer one is the target
+        const uint32_t m = len[a], n = len[b];
+        const uint8_t *q = sym + off[a];
+        const uint8_t *t = sym + off[b];
+        if (m == 0) {
+            if (lane == 0) out[pair] = mode ? 0u : n;
+            continue;
+        }
+        const uint32_t nb = (m + 63u) >> 6;
+        const uint32_t lanes_used = (nb + WB - 1) / WB;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < WB; k++)
+            for (uint32_t s = 0; s < (uint32_t)EDIT_SYMS; s++)
+                s_eq[(s * WB + k) * 32 + lane] = edit_eq_word(q, m, lane * WB + k, s);
+        __syncwarp();
+        uint64_t Pv[WB], Mv[WB];
+#pragma unroll
+        for (int k = 0; k < WB; k++) { Pv[k] = ~0ull; Mv[k] = 0; }
+        const int rbit = (int)((m - 1u) & 63u);
+        const uint32_t last_lane = (nb - 1u) / WB;
+        const int last_k = (int)((nb - 1u) % WB);
+        int score = (int)m, best = (int)m;
+        int carry = 0;                                  // hout of this lane's last block, previous step
+        const int hin0 = mode ? 0 : 1;
+        const uint32_t steps = n + lanes_used - 1u;
+        uint32_t c_next = lane == 0 && n > 0 ? t[0] : 0u;
+        for (uint32_t step = 0; step < steps; step++) {
+            const int from_above = __shfl_up_sync(0xffffffffu, carry, 1);
+            const int32_t j = (int32_t)step - (int32_t)lane;
+            const bool active = lane < lanes_used && j >= 0 && j < (int32_t)n;
+            const uint32_t c = c_next;
+            // the symbol of the next step's column, loaded a step ahead
+            const int32_t jn = j + 1;
+            if (lane < lanes_used && jn >= 0 && jn < (int32_t)n) c_next = t[jn];
+            if (active) {
+                int hin = lane == 0 ? hin0 : from_above;
+#pragma unroll
+                for (int k = 0; k < WB; k++) {
+                    if (lane * WB + k < nb) {
+                        int hrow;
+                        hin = myers_block_step(Pv[k], Mv[k], s_eq[(c * WB + k) * 32 + lane], hin, rbit, hrow);
+                        if (lane == last_lane && k == last_k) {
+                            score += hrow;
+                            best = min(best, score);
+                        }
+                    }
+                }
+                carry = hin;
+            }
+        }
+        if (lane == last_lane) out[pair] = (uint32_t)(mode ? best : score);
+    }
+}
+#endif
+
+}  // namespace orc

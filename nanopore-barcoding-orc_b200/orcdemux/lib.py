@@ -25,7 +25,8 @@ EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_sub
            "orc_upload", "orc_launch", "orc_download", "orc_sync", "orc_get_timings", "orc_timer_start", "orc_timer_stop", "orc_counts",
            "orc_fastq_index", "orc_host_alloc", "orc_host_free", "orc_measure_int32_peak", "orc_version",
            "orc_reader_open", "orc_reader_next", "orc_reader_release", "orc_reader_error", "orc_reader_close",
-           "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close"]
+           "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close",
+           "orc_edit_distances"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -144,6 +145,9 @@ def load():
     L.orc_writer_error.restype = C.c_char_p
     L.orc_writer_close.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_writer_close.restype = C.c_int
+    L.orc_edit_distances.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_char_p, C.c_size_t]
+    L.orc_edit_distances.restype = C.c_int
     L.orc_version.argtypes = []
     L.orc_version.restype = C.c_char_p
     _lib = L

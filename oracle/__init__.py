@@ -39,8 +39,8 @@ class OraAdapter(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (oracle/Makefile).  Returns the .so path."""
-    src = os.path.join(_HERE, "cutadapt_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("cutadapt_oracle.c", "edit_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return _SO
 
@@ -155,3 +155,21 @@ def demux_batch(rounds, seq: np.ndarray, qual: np.ndarray, offsets: np.ndarray, 
                              rec0.ctypes.data, rec1.ctypes.data, out_seq.ctypes.data, out_qual.ctypes.data,
                              out_len.ctypes.data, int(n_threads))
     return rec0, (rec1 if len(rounds) > 1 else None), out_seq, out_qual, out_len
+
+
+def edit_distances(seqs: np.ndarray, offsets: np.ndarray, lengths: np.ndarray, pair_a: np.ndarray,
+                   pair_b: np.ndarray, mode: str = "NW", n_threads: int = 8) -> np.ndarray:
+    """edit_oracle.c: what edlib.align(shorter, longer, task='distance', mode=mode)['editDistance'] returns for
+    every listed pair (amplicon_sorter.py:225-235, :838-849)."""
+    L = lib()
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    out = np.zeros(pa.shape[0], dtype=np.uint32)
+    L.oracle_edit_distances.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_int, C.c_void_p, C.c_int]
+    L.oracle_edit_distances.restype = None
+    L.oracle_edit_distances(seqs.ctypes.data, offsets.ctypes.data, lengths.ctypes.data, pa.ctypes.data,
+                            pb.ctypes.data, pa.shape[0], {"NW": 0, "HW": 1}[mode], out.ctypes.data, n_threads)
+    return out

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "orc_core.cuh"
+#include "orc_edit.cuh"
 #include "orc_table.h"
 
 using namespace orc;
@@ -147,4 +148,10 @@ extern "C" int hostsim_demux(int n_rounds,
     delete[] AT;
     delete[] ST;
     return 0;
+}
+
+// the block formulation of orc_edit.cuh (what edit_kernel computes, without the lane skew)
+extern "C" uint32_t hostsim_edit_distance(const uint8_t *q, uint32_t m, const uint8_t *t, uint32_t n, int mode)
+{
+    return orc::edit_distance_blocks(q, m, t, n, mode);
 }
