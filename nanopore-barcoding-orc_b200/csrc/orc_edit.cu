@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -62,8 +63,10 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
             }
             sym[p] = (uint8_t)map[c];
         }
-    // pairs by the number of 64-row blocks a lane has to hold
-    std::vector<uint32_t> todo[3];
+    // pairs by the lanes a query needs (8, 16 or 32, one 64-row block per lane) and, beyond 2048
+    // rows, by the blocks a lane has to hold (2 or 4); longest target first inside a class
+    constexpr int N_CLS = 5;
+    std::vector<uint32_t> todo[N_CLS];
     for (uint64_t k = 0; k < n_pairs; k++) {
         if (pair_a[k] >= n_seqs || pair_b[k] >= n_seqs)
             return fail(err, err_len, ORC_EINVAL, "orc_edit_distances: pair index out of range");
@@ -71,8 +74,14 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
         const uint32_t m = la < lb ? la : lb;
         if (m > 32u * 64u * EDIT_MAX_WB)
             return fail(err, err_len, ORC_EINVAL, "unsupported: sequences longer than 8192 on both sides of a pair");
-        todo[m <= 2048u ? 0 : m <= 4096u ? 1 : 2].push_back((uint32_t)k);
+        todo[m <= 512u ? 0 : m <= 1024u ? 1 : m <= 2048u ? 2 : m <= 4096u ? 3 : 4].push_back((uint32_t)k);
     }
+    for (int cls = 0; cls < N_CLS; cls++)
+        std::sort(todo[cls].begin(), todo[cls].end(), [&](uint32_t x, uint32_t y) {
+            const uint32_t nx = std::max(lengths[pair_a[x]], lengths[pair_b[x]]);
+            const uint32_t ny = std::max(lengths[pair_a[y]], lengths[pair_b[y]]);
+            return nx != ny ? nx > ny : x < y;
+        });
     if (cudaSetDevice(device) != cudaSuccess)
         return fail(err, err_len, ORC_ECUDA, "no usable CUDA device (there is no CPU fallback)");
     cudaDeviceProp prop;
@@ -95,22 +104,25 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
     ECK(cudaEventCreate(&e1));
     ECK(cudaEventRecord(e0, 0));
     uint64_t done = 0;
-    for (int cls = 0; cls < 3; cls++) {
+    for (int cls = 0; cls < N_CLS; cls++) {
         const uint32_t nt = (uint32_t)todo[cls].size();
         if (!nt) continue;
         uint32_t *d_list = (uint32_t *)d_todo.p + done;
         ECK(cudaMemcpyAsync(d_list, todo[cls].data(), 4ull * nt, cudaMemcpyHostToDevice, 0));
-        const int wb = cls == 0 ? 1 : cls == 1 ? 2 : 4;
+        const int wb = cls <= 2 ? 1 : cls == 3 ? 2 : 4;
+        const uint32_t per_warp = cls == 0 ? 4u : cls == 1 ? 2u : 1u;
         const size_t smem = 4u * EDIT_SYMS * wb * 32u * sizeof(uint64_t);
-        const uint32_t want = (nt + 3u) / 4u, cap = (uint32_t)prop.multiProcessorCount * 8u;
+        const uint32_t want = (nt + 4u * per_warp - 1u) / (4u * per_warp), cap = (uint32_t)prop.multiProcessorCount * 8u;
         const uint32_t blocks = want < cap ? want : cap;
         const uint8_t *ds = (const uint8_t *)d_sym.p;
         const uint64_t *dof = (const uint64_t *)d_off.p;
         const uint32_t *dl = (const uint32_t *)d_len.p, *da = (const uint32_t *)d_pa.p, *db = (const uint32_t *)d_pb.p;
         uint32_t *dout = (uint32_t *)d_out.p;
-        if (wb == 1) edit_kernel<1><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
-        else if (wb == 2) edit_kernel<2><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
-        else edit_kernel<4><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        if (cls == 0) edit_kernel<1, 8><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        else if (cls == 1) edit_kernel<1, 16><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        else if (cls == 2) edit_kernel<1, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        else if (cls == 3) edit_kernel<2, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+        else edit_kernel<4, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
         ECK(cudaGetLastError());
         done += nt;
     }

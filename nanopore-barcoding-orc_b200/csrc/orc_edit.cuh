@@ -82,65 +82,96 @@ inline uint32_t edit_distance_blocks(const uint8_t *q, uint32_t m, const uint8_t
 }
 
 #if defined(__CUDACC__)
-// sym: the batch's bytes mapped to 0 .. EDIT_SYMS-1.  Dynamic shared memory: per warp
-// EDIT_SYMS * WB * 32 match words, laid out [symbol][k][lane].
-template <int WB>
+// sym: the batch's bytes mapped to 0 .. EDIT_SYMS-1.  G lanes work on one pair (G = 8, 16 or 32:
+// short queries leave most of a warp idle otherwise), so a warp sweeps 32 / G pairs side by side;
+// todo lists the pairs of this (WB, G) class, longest target first, so that the pairs of a warp
+// take about the same number of steps.  Dynamic shared memory: per warp EDIT_SYMS * WB * 32 match
+// words, laid out [symbol][k][lane]; a lane only ever reads its own.
+template <int WB, int G>
 __global__ void __launch_bounds__(128, 8)
 edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, const uint32_t *__restrict__ len,
             const uint32_t *__restrict__ pair_a, const uint32_t *__restrict__ pair_b,
             const uint32_t *__restrict__ todo, uint32_t n_todo, int mode, uint32_t *__restrict__ out)
 {
     extern __shared__ uint64_t s_eq_all[];
+    constexpr uint32_t PER_WARP = 32u / G;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gl = lane % G, grp = lane / G;
     uint64_t *s_eq = s_eq_all + (size_t)(threadIdx.x >> 5) * (EDIT_SYMS * WB * 32);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = warp; w < n_todo; w += n_warps) {
-        const uint32_t pair = todo[w];
-        uint32_t a = pair_a[pair], b = pair_b[pair];
-        if (len[a] > len[b]) { const uint32_t x = a; a = b; b = x; }   // the longer one is the target
-        const uint32_t m = len[a], n = len[b];
-        const uint8_t *q = sym + off[a];
-        const uint8_t *t = sym + off[b];
-        if (m == 0) {
-            if (lane == 0) out[pair] = mode ? 0u : n;
-            continue;
+    const uint32_t n_rounds = (n_todo + PER_WARP - 1u) / PER_WARP;
+    for (uint32_t w = warp; w < n_rounds; w += n_warps) {
+        const uint32_t slot = w * PER_WARP + grp;
+        const bool have = slot < n_todo;
+        const uint32_t pair = have ? todo[slot] : 0u;
+        uint32_t a = have ? pair_a[pair] : 0u, b = have ? pair_b[pair] : 0u;
+        uint32_t m = 0, n = 0;
+        const uint8_t *q = sym, *t = sym;
+        if (have) {
+            if (len[a] > len[b]) { const uint32_t x = a; a = b; b = x; }   // the longer one is the target
+            m = len[a]; n = len[b];
+            q = sym + off[a]; t = sym + off[b];
         }
+        const bool work = have && m > 0;
+        if (have && m == 0 && gl == 0) out[pair] = mode ? 0u : n;
         const uint32_t nb = (m + 63u) >> 6;
         const uint32_t lanes_used = (nb + WB - 1) / WB;
         __syncwarp();
+        // the lane's match words: every query byte is read once and sets its bit in one of the
+        // EDIT_SYMS words of its block (two 32-bit halves)
 #pragma unroll
-        for (int k = 0; k < WB; k++)
-            for (uint32_t s = 0; s < (uint32_t)EDIT_SYMS; s++)
-                s_eq[(s * WB + k) * 32 + lane] = edit_eq_word(q, m, lane * WB + k, s);
+        for (int k = 0; k < WB; k++) {
+            const uint32_t base = 64u * (gl * WB + k);
+            uint32_t lo[EDIT_SYMS], hi[EDIT_SYMS];
+#pragma unroll
+            for (int s = 0; s < EDIT_SYMS; s++) { lo[s] = 0; hi[s] = 0; }
+            if (base < m) {
+#pragma unroll 2
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t c0 = base + i < m ? q[base + i] : 0xFFu;
+                    const uint32_t c1 = base + 32u + i < m ? q[base + 32u + i] : 0xFFu;
+#pragma unroll
+                    for (int s = 0; s < EDIT_SYMS; s++) {
+                        lo[s] |= (c0 == (uint32_t)s ? 1u : 0u) << i;
+                        hi[s] |= (c1 == (uint32_t)s ? 1u : 0u) << i;
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < EDIT_SYMS; s++)
+                s_eq[(s * WB + k) * 32 + lane] = ((uint64_t)hi[s] << 32) | lo[s];
+        }
         __syncwarp();
         uint64_t Pv[WB], Mv[WB];
 #pragma unroll
         for (int k = 0; k < WB; k++) { Pv[k] = ~0ull; Mv[k] = 0; }
         const int rbit = (int)((m - 1u) & 63u);
-        const uint32_t last_lane = (nb - 1u) / WB;
-        const int last_k = (int)((nb - 1u) % WB);
+        const uint32_t last_gl = work ? (nb - 1u) / WB : 0u;
+        const int last_k = work ? (int)((nb - 1u) % WB) : 0;
         int score = (int)m, best = (int)m;
         int carry = 0;                                  // hout of this lane's last block, previous step
         const int hin0 = mode ? 0 : 1;
-        const uint32_t steps = n + lanes_used - 1u;
-        uint32_t c_next = lane == 0 && n > 0 ? t[0] : 0u;
+        const uint32_t my_steps = work ? n + lanes_used - 1u : 0u;
+        const uint32_t steps = __reduce_max_sync(0xffffffffu, my_steps);
+        uint32_t c_next = (work && gl == 0 && n > 0) ? t[0] : 0u;
         for (uint32_t step = 0; step < steps; step++) {
-            const int from_above = __shfl_up_sync(0xffffffffu, carry, 1);
-            const int32_t j = (int32_t)step - (int32_t)lane;
-            const bool active = lane < lanes_used && j >= 0 && j < (int32_t)n;
+            const int from_above = __shfl_up_sync(0xffffffffu, carry, 1, G);
+            const int32_t j = (int32_t)step - (int32_t)gl;
+            const bool mine = work && gl < lanes_used;
+            const bool active = mine && j >= 0 && j < (int32_t)n;
             const uint32_t c = c_next;
             // the symbol of the next step's column, loaded a step ahead
             const int32_t jn = j + 1;
-            if (lane < lanes_used && jn >= 0 && jn < (int32_t)n) c_next = t[jn];
+            if (mine && jn >= 0 && jn < (int32_t)n) c_next = t[jn];
             if (active) {
-                int hin = lane == 0 ? hin0 : from_above;
+                int hin = gl == 0 ? hin0 : from_above;
 #pragma unroll
                 for (int k = 0; k < WB; k++) {
-                    if (lane * WB + k < nb) {
+                    if (gl * WB + k < nb) {
                         int hrow;
                         hin = myers_block_step(Pv[k], Mv[k], s_eq[(c * WB + k) * 32 + lane], hin, rbit, hrow);
-                        if (lane == last_lane && k == last_k) {
+                        if (gl == last_gl && k == last_k) {
                             score += hrow;
                             best = min(best, score);
                         }
@@ -149,7 +180,7 @@ edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, c
                 carry = hin;
             }
         }
-        if (lane == last_lane) out[pair] = (uint32_t)(mode ? best : score);
+        if (work && gl == last_gl) out[pair] = (uint32_t)(mode ? best : score);
     }
 }
 #endif
