@@ -56,10 +56,50 @@ def identities(dist: np.ndarray, lengths: np.ndarray, pair_a, pair_b) -> np.ndar
     """amplicon_sorter's similarity: round(1 - distance / len(longer), 3)."""
     la = lengths[np.asarray(pair_a)].astype(np.float64)
     lb = lengths[np.asarray(pair_b)].astype(np.float64)
-    return np.round(1.0 - dist / np.maximum(np.maximum(la, lb), 1.0), 3)
+    x = 1.0 - dist / np.maximum(np.maximum(la, lb), 1.0)
+    r = np.round(x, 3)
+    # Python's round() rounds the exact binary value, numpy rounds x * 1000: they can differ next to
+    # a tie, so those few values go through Python's
+    y = x * 1000.0
+    for i in np.flatnonzero(np.abs(y - np.floor(y) - 0.5) < 1e-6):
+        r[i] = round(float(x[i]), 3)
+    return r
 
 
 def all_pairs(n: int) -> Tuple[np.ndarray, np.ndarray]:
     """Every unordered pair i < j of n sequences (amplicon_sorter's compare-all mode)."""
     a, b = np.triu_indices(n, k=1)
     return a.astype(np.uint32), b.astype(np.uint32)
+
+
+_COMPL = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b"ATCGRYKMSW", b"TAGCYRMKSW"):        # amplicon_sorter.py:237-242 compl_reverse
+    _COMPL[_a] = _b
+
+
+def compl_reverse(seq: bytes) -> bytes:
+    """amplicon_sorter.py:237-242: reverse, then complement ATCGRYKMSW (other characters unchanged)."""
+    return _COMPL[np.frombuffer(seq, dtype=np.uint8)[::-1]].tobytes()
+
+
+def similarity(seqs: Sequence[bytes], pair_a, pair_b, similar_genes: float = 80.0, device: int = 0):
+    """What amplicon_sorter's similarity() worker writes for the listed pairs
+    (amplicon_sorter.py:777-808): (i, j, iden, reversed) for every pair whose identity reaches
+    similar_genes per cent; a pair below 0.5 is tried again against the reverse complement of
+    its second sequence and kept, flagged 'reverse', if that reaches the threshold."""
+    n = len(seqs)
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    blob, off, ln = pack(bs + [compl_reverse(b) for b in bs])     # sequence n + i = reverse complement of i
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    thr = similar_genes / 100.0
+    iden = identities(edit_distances(blob, off, ln, pa, pb, "NW", device), ln, pa, pb)
+    out = [(int(a), int(b), float(i), False) for a, b, i in zip(pa[iden >= thr], pb[iden >= thr], iden[iden >= thr])]
+    low = np.flatnonzero(iden < 0.5)
+    if low.size:
+        ra, rb = pa[low], pb[low] + np.uint32(n)
+        riden = identities(edit_distances(blob, off, ln, ra, rb, "NW", device), ln, ra, rb)
+        keep = riden >= thr
+        out += [(int(a), int(b), float(i), True) for a, b, i in zip(pa[low][keep], pb[low][keep], riden[keep])]
+    out.sort(key=lambda r: (r[0], r[1]))
+    return out

@@ -105,3 +105,35 @@ def test_kernel_refuses_what_it_cannot_do():
     assert list(D.edit_distances(blob, off, ln, [0], [1], "NW")) == [8999]
     with pytest.raises(OrcError, match="out of range"):
         D.edit_distances(blob, off, ln, [0], [5])
+
+
+@pytest.mark.gpu
+def test_similarity_worker_semantics():
+    """amplicon_sorter.py:777-808: threshold on the forward identity, reverse-complement retry below 0.5."""
+    from orcdemux import synth
+    rnd = random.Random(3)
+    fam = []
+    for _ in range(4):                                   # four families of similar reads
+        base = bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(400, 600)))
+        for _ in range(6):
+            s = bytearray(base)
+            for _ in range(rnd.randint(0, 40)):
+                s[rnd.randrange(len(s))] = rnd.choice(b"ACGT")
+            fam.append(bytes(s) if rnd.random() < 0.7 else D.compl_reverse(bytes(s)))
+    pa, pb = D.all_pairs(len(fam))
+    got = D.similarity(fam, pa, pb, similar_genes=85.0)
+    exp = []
+    for a, b in zip(pa.tolist(), pb.tolist()):
+        def iden(x, y):
+            blob, off, ln = D.pack([x, y])
+            d = int(oracle.edit_distances(blob, off, ln, [0], [1], "NW", n_threads=1)[0])
+            return round(1 - d / max(len(x), len(y)), 3)
+        i = iden(fam[a], fam[b])
+        if i >= 0.85:
+            exp.append((a, b, i, False))
+        elif i < 0.5:
+            i = iden(fam[a], D.compl_reverse(fam[b]))
+            if i >= 0.85:
+                exp.append((a, b, i, True))
+    assert got == exp and any(r[3] for r in got) and any(not r[3] for r in got)
+    assert D.compl_reverse(b"AACGTN") == b"NACGTT"
