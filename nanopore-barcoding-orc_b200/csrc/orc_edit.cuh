@@ -29,6 +29,7 @@ constexpr int EDIT_MAX_WB = 4;          // blocks per lane: queries up to 32 * 4
 
 // One block, one column.  Returns hout; hrow = the horizontal delta at bit `rbit` (the query's
 // last row when this is its last block).
+template <bool ROW = true>
 ORC_EHD int myers_block_step(uint64_t &Pv, uint64_t &Mv, uint64_t Eq, int hin, int rbit, int &hrow)
 {
     const uint64_t neg = hin < 0 ? 1ull : 0ull;
@@ -38,7 +39,8 @@ ORC_EHD int myers_block_step(uint64_t &Pv, uint64_t &Mv, uint64_t Eq, int hin, i
     uint64_t Ph = Mv | ~(Xh | Pv);
     uint64_t Mh = Pv & Xh;
     const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-    hrow = (int)((Ph >> rbit) & 1ull) - (int)((Mh >> rbit) & 1ull);
+    if (ROW) hrow = (int)((Ph >> rbit) & 1ull) - (int)((Mh >> rbit) & 1ull);
+    else hrow = 0;
     Ph <<= 1; Mh <<= 1;
     Mh |= neg;
     Ph |= hin > 0 ? 1ull : 0ull;
@@ -151,34 +153,66 @@ edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, c
         const int last_k = work ? (int)((nb - 1u) % WB) : 0;
         int score = (int)m, best = (int)m;
         int carry = 0;                                  // hout of this lane's last block, previous step
-        const int hin0 = mode ? 0 : 1;
         const uint32_t my_steps = work ? n + lanes_used - 1u : 0u;
         const uint32_t steps = __reduce_max_sync(0xffffffffu, my_steps);
-        uint32_t c_next = (work && gl == 0 && n > 0) ? t[0] : 0u;
-        for (uint32_t step = 0; step < steps; step++) {
-            const int from_above = __shfl_up_sync(0xffffffffu, carry, 1, G);
-            const int32_t j = (int32_t)step - (int32_t)gl;
-            const bool mine = work && gl < lanes_used;
-            const bool active = mine && j >= 0 && j < (int32_t)n;
-            const uint32_t c = c_next;
-            // the symbol of the next step's column, loaded a step ahead
-            const int32_t jn = j + 1;
-            if (mine && jn >= 0 && jn < (int32_t)n) c_next = t[jn];
-            if (active) {
-                int hin = gl == 0 ? hin0 : from_above;
+        const bool mine = work && gl < lanes_used;
+        // column of this lane at step s: s - gl; its symbol is loaded a step ahead
+        const uint8_t *tp = t - gl;
+        uint32_t c_next = (mine && gl == 0 && n > 0) ? t[0] : 0u;
+        if (mode) {
+            // HW: D[m][j] of every column, through the horizontal delta at the query's last row
+            for (uint32_t step = 0; step < steps; step++) {
+                const int from_above = __shfl_up_sync(0xffffffffu, carry, 1, G);
+                const uint32_t j = step - gl;                   // wraps below column 0: >= n
+                const uint32_t c = c_next;
+                if (mine && j + 1u < n) c_next = tp[step + 1u];
+                if (mine && j < n) {
+                    int hin = gl == 0 ? 0 : from_above;
 #pragma unroll
-                for (int k = 0; k < WB; k++) {
-                    if (gl * WB + k < nb) {
-                        int hrow;
-                        hin = myers_block_step(Pv[k], Mv[k], s_eq[(c * WB + k) * 32 + lane], hin, rbit, hrow);
-                        if (gl == last_gl && k == last_k) {
-                            score += hrow;
-                            best = min(best, score);
+                    for (int k = 0; k < WB; k++) {
+                        if (gl * WB + k < nb) {
+                            int hrow;
+                            hin = myers_block_step<true>(Pv[k], Mv[k], s_eq[(c * WB + k) * 32 + lane], hin, rbit, hrow);
+                            if (gl == last_gl && k == last_k) {
+                                score += hrow;
+                                best = min(best, score);
+                            }
                         }
                     }
+                    carry = hin;
                 }
-                carry = hin;
             }
+        } else {
+            // NW: only D[m][n] is wanted, and that is n plus the vertical deltas of the last column
+            for (uint32_t step = 0; step < steps; step++) {
+                const int from_above = __shfl_up_sync(0xffffffffu, carry, 1, G);
+                const uint32_t j = step - gl;
+                const uint32_t c = c_next;
+                if (mine && j + 1u < n) c_next = tp[step + 1u];
+                if (mine && j < n) {
+                    int hin = gl == 0 ? 1 : from_above;
+#pragma unroll
+                    for (int k = 0; k < WB; k++) {
+                        if (gl * WB + k < nb) {
+                            int hrow;
+                            hin = myers_block_step<false>(Pv[k], Mv[k], s_eq[(c * WB + k) * 32 + lane], hin, rbit, hrow);
+                        }
+                    }
+                    carry = hin;
+                }
+            }
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < WB; k++) {
+                const uint32_t blk = gl * WB + k;
+                if (mine && blk < nb) {
+                    const uint64_t keep = (blk == nb - 1u && rbit < 63) ? ((1ull << (rbit + 1)) - 1ull) : ~0ull;
+                    sum += __popcll(Pv[k] & keep) - __popcll(Mv[k] & keep);
+                }
+            }
+#pragma unroll
+            for (int d = G / 2; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d, G);
+            score = (int)n + sum;
         }
         if (work && gl == last_gl) out[pair] = (uint32_t)(mode ? best : score);
     }
