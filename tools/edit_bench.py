@@ -43,10 +43,20 @@ def main():
     cpu_s = time.perf_counter() - t0
     assert np.array_equal(exp, dist[sel]), "kernel and recurrence differ"
     cpu_cells = float((np.minimum(L[pa[sel]], L[pb[sel]]) * np.maximum(L[pa[sel]], L[pb[sel]])).sum())
+    from orcdemux import engine as E
+    alu_peak, _ = E.measure_int32_peak(0, 0)
+    # 27 ALU-pipe instructions per 64-row block and column in edit_kernel's loop (SASS: 17 LOP3, 3 IADD3,
+    # 2 SHF, 2 SEL, 2 ISETP, 1 LEA) + about 3 of the step's own -> 30
+    peak_gcups = alu_peak / 30.0 * 64.0 / 1e9
     print(json.dumps({
         "what": "all-vs-all %s edit distance, %d synthetic reads %d-%d nt" % (a.mode, rs.n_reads, a.len_min, a.len_max),
         "pairs": int(pa.shape[0]), "kernel_ms": ms, "pairs_per_s": pa.shape[0] / (ms * 1e-3),
         "gcups": cells / (ms * 1e-3) / 1e9, "call_wall_s": wall,
+        "roofline": {"bound": "int32_alu", "achieved": cells / (ms * 1e-3) / 1e9, "peak": peak_gcups, "unit": "GCUPS",
+                     "frac": cells / (ms * 1e-3) / 1e9 / peak_gcups,
+                     "peak_how": "measured LOP3 rate %.3g lane-op/s / 30 ALU-pipe instr per block step x 64 cells, "
+                                 "every lane busy; the kernel leaves lanes idle while a pair's wavefront fills and "
+                                 "drains and where a query has fewer blocks than its 8/16/32 lanes" % alu_peak},
         "cpu_port": {"pairs": int(k), "seconds": cpu_s, "pairs_per_s": k / cpu_s, "gcups": cpu_cells / cpu_s / 1e9,
                      "cores": ncpu, "note": "oracle/edit_oracle.c scalar recurrence, not edlib"},
         "checked_against_oracle": int(k)}))
