@@ -66,22 +66,29 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
     // pairs by the lanes a query needs (8, 16 or 32, one 64-row block per lane) and, beyond 2048
     // rows, by the blocks a lane has to hold (2 or 4); longest target first inside a class
     constexpr int N_CLS = 5;
-    std::vector<uint32_t> todo[N_CLS];
+    constexpr uint32_t KEY_CAP = 1u << 16;          // targets beyond 65535 share the first bucket
+    auto cls_of = [](uint32_t m) { return m <= 512u ? 0 : m <= 1024u ? 1 : m <= 2048u ? 2 : m <= 4096u ? 3 : 4; };
+    // counting sort by (class, target length descending), stable
+    std::vector<uint64_t> count((size_t)N_CLS * (KEY_CAP + 1u) + 1u, 0);
     for (uint64_t k = 0; k < n_pairs; k++) {
         if (pair_a[k] >= n_seqs || pair_b[k] >= n_seqs)
             return fail(err, err_len, ORC_EINVAL, "orc_edit_distances: pair index out of range");
         const uint32_t la = lengths[pair_a[k]], lb = lengths[pair_b[k]];
-        const uint32_t m = la < lb ? la : lb;
+        const uint32_t m = la < lb ? la : lb, n = la < lb ? lb : la;
         if (m > 32u * 64u * EDIT_MAX_WB)
             return fail(err, err_len, ORC_EINVAL, "unsupported: sequences longer than 8192 on both sides of a pair");
-        todo[m <= 512u ? 0 : m <= 1024u ? 1 : m <= 2048u ? 2 : m <= 4096u ? 3 : 4].push_back((uint32_t)k);
+        count[(size_t)cls_of(m) * (KEY_CAP + 1u) + (KEY_CAP - (n < KEY_CAP ? n : KEY_CAP)) + 1u]++;
     }
-    for (int cls = 0; cls < N_CLS; cls++)
-        std::sort(todo[cls].begin(), todo[cls].end(), [&](uint32_t x, uint32_t y) {
-            const uint32_t nx = std::max(lengths[pair_a[x]], lengths[pair_b[x]]);
-            const uint32_t ny = std::max(lengths[pair_a[y]], lengths[pair_b[y]]);
-            return nx != ny ? nx > ny : x < y;
-        });
+    for (size_t i = 1; i < count.size(); i++) count[i] += count[i - 1];
+    std::vector<uint32_t> order(n_pairs);
+    for (uint64_t k = 0; k < n_pairs; k++) {
+        const uint32_t la = lengths[pair_a[k]], lb = lengths[pair_b[k]];
+        const uint32_t m = la < lb ? la : lb, n = la < lb ? lb : la;
+        order[count[(size_t)cls_of(m) * (KEY_CAP + 1u) + (KEY_CAP - (n < KEY_CAP ? n : KEY_CAP))]++] = (uint32_t)k;
+    }
+    uint64_t cls_begin[N_CLS + 1];
+    cls_begin[0] = 0;
+    for (int c = 0; c < N_CLS; c++) cls_begin[c + 1] = count[(size_t)c * (KEY_CAP + 1u) + KEY_CAP];
     if (cudaSetDevice(device) != cudaSuccess)
         return fail(err, err_len, ORC_ECUDA, "no usable CUDA device (there is no CPU fallback)");
     cudaDeviceProp prop;
@@ -99,16 +106,15 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
     ECK(cudaMemcpy(d_len.p, lengths, 4ull * n_seqs, cudaMemcpyHostToDevice));
     ECK(cudaMemcpy(d_pa.p, pair_a, 4ull * n_pairs, cudaMemcpyHostToDevice));
     ECK(cudaMemcpy(d_pb.p, pair_b, 4ull * n_pairs, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(d_todo.p, order.data(), 4ull * n_pairs, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1;
     ECK(cudaEventCreate(&e0));
     ECK(cudaEventCreate(&e1));
     ECK(cudaEventRecord(e0, 0));
-    uint64_t done = 0;
     for (int cls = 0; cls < N_CLS; cls++) {
-        const uint32_t nt = (uint32_t)todo[cls].size();
+        const uint32_t nt = (uint32_t)(cls_begin[cls + 1] - cls_begin[cls]);
         if (!nt) continue;
-        uint32_t *d_list = (uint32_t *)d_todo.p + done;
-        ECK(cudaMemcpyAsync(d_list, todo[cls].data(), 4ull * nt, cudaMemcpyHostToDevice, 0));
+        uint32_t *d_list = (uint32_t *)d_todo.p + cls_begin[cls];
         const int wb = cls <= 2 ? 1 : cls == 3 ? 2 : 4;
         const uint32_t per_warp = cls == 0 ? 4u : cls == 1 ? 2u : 1u;
         const size_t smem = 4u * EDIT_SYMS * wb * 32u * sizeof(uint64_t);
@@ -124,7 +130,6 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
         else if (cls == 3) edit_kernel<2, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
         else edit_kernel<4, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
         ECK(cudaGetLastError());
-        done += nt;
     }
     ECK(cudaEventRecord(e1, 0));
     ECK(cudaEventSynchronize(e1));
