@@ -65,9 +65,17 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
         }
     // pairs by the lanes a query needs (8, 16 or 32, one 64-row block per lane) and, beyond 2048
     // rows, by the blocks a lane has to hold (2 or 4); longest target first inside a class
-    constexpr int N_CLS = 5;
+    // classes by the 64-row blocks of the query: G lanes per pair with one block each up to 32 blocks,
+    // then 2 and 4 blocks per lane
+    constexpr int N_CLS = 9;
+    static const int cls_g[N_CLS] = {5, 6, 7, 8, 10, 16, 32, 32, 32};
+    static const int cls_wb[N_CLS] = {1, 1, 1, 1, 1, 1, 1, 2, 4};
     constexpr uint32_t KEY_CAP = 1u << 16;          // targets beyond 65535 share the first bucket
-    auto cls_of = [](uint32_t m) { return m <= 512u ? 0 : m <= 1024u ? 1 : m <= 2048u ? 2 : m <= 4096u ? 3 : 4; };
+    auto cls_of = [](uint32_t m) {
+        const uint32_t nb = (m + 63u) / 64u;
+        return nb <= 5u ? 0 : nb == 6u ? 1 : nb == 7u ? 2 : nb == 8u ? 3 : nb <= 10u ? 4 : nb <= 16u ? 5 : nb <= 32u ? 6
+                                                                                             : nb <= 64u ? 7 : 8;
+    };
     // counting sort by (class, target length descending), stable
     std::vector<uint64_t> count((size_t)N_CLS * (KEY_CAP + 1u) + 1u, 0);
     for (uint64_t k = 0; k < n_pairs; k++) {
@@ -115,8 +123,8 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
         const uint32_t nt = (uint32_t)(cls_begin[cls + 1] - cls_begin[cls]);
         if (!nt) continue;
         uint32_t *d_list = (uint32_t *)d_todo.p + cls_begin[cls];
-        const int wb = cls <= 2 ? 1 : cls == 3 ? 2 : 4;
-        const uint32_t per_warp = cls == 0 ? 4u : cls == 1 ? 2u : 1u;
+        const int wb = cls_wb[cls];
+        const uint32_t per_warp = 32u / (uint32_t)cls_g[cls];
         const size_t smem = 4u * EDIT_SYMS * wb * 32u * sizeof(uint64_t);
         const uint32_t want = (nt + 4u * per_warp - 1u) / (4u * per_warp), cap = (uint32_t)prop.multiProcessorCount * 8u;
         const uint32_t blocks = want < cap ? want : cap;
@@ -124,11 +132,19 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
         const uint64_t *dof = (const uint64_t *)d_off.p;
         const uint32_t *dl = (const uint32_t *)d_len.p, *da = (const uint32_t *)d_pa.p, *db = (const uint32_t *)d_pb.p;
         uint32_t *dout = (uint32_t *)d_out.p;
-        if (cls == 0) edit_kernel<1, 8><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
-        else if (cls == 1) edit_kernel<1, 16><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
-        else if (cls == 2) edit_kernel<1, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
-        else if (cls == 3) edit_kernel<2, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
-        else edit_kernel<4, 32><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout);
+#define ORC_EDIT_LAUNCH(WB, G) edit_kernel<WB, G><<<blocks, 128, smem, 0>>>(ds, dof, dl, da, db, d_list, nt, mode, dout)
+        switch (cls) {
+        case 0: ORC_EDIT_LAUNCH(1, 5); break;
+        case 1: ORC_EDIT_LAUNCH(1, 6); break;
+        case 2: ORC_EDIT_LAUNCH(1, 7); break;
+        case 3: ORC_EDIT_LAUNCH(1, 8); break;
+        case 4: ORC_EDIT_LAUNCH(1, 10); break;
+        case 5: ORC_EDIT_LAUNCH(1, 16); break;
+        case 6: ORC_EDIT_LAUNCH(1, 32); break;
+        case 7: ORC_EDIT_LAUNCH(2, 32); break;
+        default: ORC_EDIT_LAUNCH(4, 32); break;
+        }
+#undef ORC_EDIT_LAUNCH
         ECK(cudaGetLastError());
     }
     ECK(cudaEventRecord(e1, 0));

@@ -84,8 +84,8 @@ inline uint32_t edit_distance_blocks(const uint8_t *q, uint32_t m, const uint8_t
 }
 
 #if defined(__CUDACC__)
-// sym: the batch's bytes mapped to 0 .. EDIT_SYMS-1.  G lanes work on one pair (G = 8, 16 or 32:
-// short queries leave most of a warp idle otherwise), so a warp sweeps 32 / G pairs side by side;
+// sym: the batch's bytes mapped to 0 .. EDIT_SYMS-1.  G lanes work on one pair (G = 5 .. 32, any
+// size: short queries leave most of a warp idle otherwise), so a warp sweeps 32 / G pairs side by side;
 // todo lists the pairs of this (WB, G) class, longest target first, so that the pairs of a warp
 // take about the same number of steps.  Dynamic shared memory: per warp EDIT_SYMS * WB * 32 match
 // words, laid out [symbol][k][lane]; a lane only ever reads its own.
@@ -105,7 +105,7 @@ edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, c
     const uint32_t n_rounds = (n_todo + PER_WARP - 1u) / PER_WARP;
     for (uint32_t w = warp; w < n_rounds; w += n_warps) {
         const uint32_t slot = w * PER_WARP + grp;
-        const bool have = slot < n_todo;
+        const bool have = grp < PER_WARP && slot < n_todo;       // lanes past the last whole group idle
         const uint32_t pair = have ? todo[slot] : 0u;
         uint32_t a = have ? pair_a[pair] : 0u, b = have ? pair_b[pair] : 0u;
         uint32_t m = 0, n = 0;
@@ -162,7 +162,7 @@ edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, c
         if (mode) {
             // HW: D[m][j] of every column, through the horizontal delta at the query's last row
             for (uint32_t step = 0; step < steps; step++) {
-                const int from_above = __shfl_up_sync(0xffffffffu, carry, 1, G);
+                const int from_above = __shfl_up_sync(0xffffffffu, carry, 1);      // lane 0 of a group ignores it
                 const uint32_t j = step - gl;                   // wraps below column 0: >= n
                 const uint32_t c = c_next;
                 if (mine && j + 1u < n) c_next = tp[step + 1u];
@@ -185,7 +185,7 @@ edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, c
         } else {
             // NW: only D[m][n] is wanted, and that is n plus the vertical deltas of the last column
             for (uint32_t step = 0; step < steps; step++) {
-                const int from_above = __shfl_up_sync(0xffffffffu, carry, 1, G);
+                const int from_above = __shfl_up_sync(0xffffffffu, carry, 1);      // lane 0 of a group ignores it
                 const uint32_t j = step - gl;
                 const uint32_t c = c_next;
                 if (mine && j + 1u < n) c_next = tp[step + 1u];
@@ -210,8 +210,13 @@ edit_kernel(const uint8_t *__restrict__ sym, const uint64_t *__restrict__ off, c
                     sum += __popcll(Pv[k] & keep) - __popcll(Mv[k] & keep);
                 }
             }
+            // inclusive prefix sum inside the group: the lane that writes the result (the last one
+            // with a block) then holds the total
 #pragma unroll
-            for (int d = G / 2; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d, G);
+            for (int d = 1; d < G; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, sum, d);
+                if (gl >= (uint32_t)d) sum += v;
+            }
             score = (int)n + sum;
         }
         if (work && gl == last_gl) out[pair] = (uint32_t)(mode ? best : score);

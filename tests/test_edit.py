@@ -68,7 +68,8 @@ def test_kernel_equals_the_recurrence():
     mk = lambda n: bytes(rnd.choice(b"ACGT") for _ in range(n))
     base = mk(5000)
     # lengths around the lane / block-count boundaries: 1, 2 and 4 blocks per lane
-    for n in (2047, 2048, 2049, 3000, 4096, 4097, 5000):
+    # every lanes-per-pair class (5, 6, 7, 8, 10, 16, 32 lanes), then 2 and 4 blocks per lane
+    for n in (320, 321, 384, 385, 448, 449, 512, 513, 600, 640, 641, 1000, 1024, 1025, 2047, 2048, 2049, 3000, 4096, 4097, 5000):
         s = bytearray(base[:n])
         for _ in range(40):
             s[rnd.randrange(n)] = rnd.choice(b"ACGTN")
