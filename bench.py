@@ -39,6 +39,7 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 METRIC = "reads/sec demuxed (2-round SP5xSP27)"
+METRIC_R1 = "reads/sec demuxed (round 1, SP5 5' indices)"        # --config 1 only
 UNIT = "reads/s"
 # ALU-pipe instructions per DP column of one (read, adapter, orientation) pair in
 # scan_kernel's inner loop, counted in the SASS (profiles/README.md); a column is m cells.
@@ -61,12 +62,15 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
-                    help="BASELINE.json configs[]: 2 = 1 Mi COI reads two-round (default, the metric's config), "
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[]: 1 = round 1 only (SP5 5' demux) on 100 k reads, the reference's "
+                         "own CPU-runnable case; 2 = 1 Mi COI reads two-round (default, the metric's config), "
                          "3 = rRNA-cistron reads 1-3.5 kb two-round, 4 = anchored --no-indels Hamming path "
                          "(24 M13 variable indices) on reads with the bare index at offset 0")
     ap.add_argument("--sub-batches", type=int, default=8)
     a = ap.parse_args()
+    if a.config == 1 and a.reads == 1 << 20:
+        a.reads = 100000
     if a.config == 3 and a.len_min == 300 and a.len_max == 900:
         a.len_min, a.len_max = 1000, 3500
         if a.reads == 1 << 20:
@@ -140,7 +144,7 @@ def hbm_peak():
         return 6650.0, "fallback"
 
 
-def cpu_arm(rs, n_sample, threads, steps, warmup):
+def cpu_arm(rs, n_sample, threads, steps, warmup, n_rounds=2):
     """Time the oracle's C restatement of cutadapt on the first n_sample reads."""
     import oracle
     from orcdemux import m13
@@ -149,7 +153,7 @@ def cpu_arm(rs, n_sample, threads, steps, warmup):
     seq, qual = rs.seq[:end], rs.qual[:end]
     off, ln = rs.offsets[:sub_n], rs.lengths[:sub_n]
     sets = [(oracle.AdapterSet([q for _, q in m13.sp5_forward()], oracle.FRONT, 0.1, 3), 1),
-            (oracle.AdapterSet([q for _, q in m13.sp27_reverse_rc()], oracle.BACK, 0.1, 3), 1)]
+            (oracle.AdapterSet([q for _, q in m13.sp27_reverse_rc()], oracle.BACK, 0.1, 3), 1)][:n_rounds]
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -189,19 +193,23 @@ def main():
         import oracle
         oracle.build()
         threads = ncpu
-        n_sample = args.cpu_sample or 16384
-        rs = synth.generate(n_sample, args.len_min, args.len_max, seed=1002, workers=min(8, ncpu))
+        one_round = args.config == 1
+        n_sample = args.cpu_sample or (100000 if one_round else 16384)
+        rs = synth.generate(n_sample, args.len_min, args.len_max, seed=1001 if one_round else 1002, workers=min(8, ncpu))
         warm = min(args.warmup, 1)
-        sub_n, times = cpu_arm(rs, n_sample, threads, args.steps, warm)
+        sub_n, times = cpu_arm(rs, n_sample, threads, args.steps, warm, 1 if one_round else 2)
         ms = 1e3 * float(np.mean(times))
         val = sub_n / float(np.mean(times))
         line = {
-            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus,
+            "impl": "reference", "metric": METRIC_R1 if one_round else METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "configs[1]: two-round SP5->SP27 demux + trim, synthetic COI reads %d-%d nt, "
-                                   "seed 1002; each step = the first %d reads of the 1 Mi-read workload"
-                                   % (args.len_min, args.len_max, sub_n),
+            "config": {"workload": ("configs[0]: round-1 SP5 5' demux (-g file:M13_amplicon_indices_forward.fa -e 0.1 --rc), "
+                                    "%d synthetic reads %d-%d nt, seed 1001" % (sub_n, args.len_min, args.len_max))
+                       if one_round else
+                       "configs[1]: two-round SP5->SP27 demux + trim, synthetic COI reads %d-%d nt, "
+                       "seed 1002; each step = the first %d reads of the 1 Mi-read workload"
+                       % (args.len_min, args.len_max, sub_n),
                        "reads_per_step": sub_n, "note": "cutadapt 4.9 is not vendored in the reference and not "
                        "installable here: this arm is the restated-cutadapt CPU baseline (oracle/cutadapt_oracle.c, "
                        "Ukkonen-banded DP, pthreads), not upstream cutadapt"},
@@ -209,6 +217,8 @@ def main():
                              "sample": "first %d reads of the workload, %d timed passes" % (sub_n, args.steps)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
+        if one_round:       # algorithmic cells of round 1: 2 orientations x 12 adapters x 59 rows x bases
+            line["gcups"] = 2 * 12 * 59 * float(rs.lengths[:sub_n].sum()) / float(np.mean(times)) / 1e9
         emit(line)
         return 0
 
@@ -246,7 +256,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    seed = {2: 1002, 3: 1003, 4: 1004}[args.config] if world == 1 else (1005 << 32) + rank
+    seed = {1: 1001, 2: 1002, 3: 1003, 4: 1004}[args.config] if world == 1 else (1005 << 32) + rank
     workers = max(1, min(16, ncpu // max(world, 1)))
     t0 = time.perf_counter()
     rs = synth.generate(args.reads, args.len_min, args.len_max, seed=seed, workers=workers,
@@ -256,6 +266,8 @@ def main():
         from orcdemux.lib import ORC_PREFIX
         var = m13.variable_all()
         rounds = [E.Round([n for n, _ in var], [q for _, q in var], ORC_PREFIX, 0.1, 3, False, True)]
+    elif args.config == 1:
+        rounds = E.m13_rounds()[:1]
     else:
         rounds = E.m13_rounds()
     gen_s = time.perf_counter() - t0
@@ -419,17 +431,19 @@ def main():
         oracle.build()
         n_s = args.cpu_sample or 16384
         os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core
-        sub_n, times = cpu_arm(rs, n_s, ncpu, 2, 1)
+        sub_n, times = cpu_arm(rs, n_s, ncpu, 2, 1, 1 if args.config == 1 else 2)
         cpu_baseline = {"value": sub_n / float(np.mean(times)), "unit": UNIT, "cores": ncpu, "kind": "port",
                         "sample": "first %d reads of the workload, one warm-up and two timed passes, %d threads "
                                   "(restated-cutadapt CPU baseline, not upstream cutadapt)" % (sub_n, ncpu)}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_R1 if args.config == 1 else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": {2: "configs[1]: full two-round SP5->SP27 combinatorial demux + trim on %d synthetic "
+            "config": {"workload": {1: "configs[0]: round-1 SP5 5' demux + trim only, %d synthetic reads (%d-%d nt) per GPU, "
+                                       "-g file:M13_amplicon_indices_forward.fa -e 0.1 --rc",
+                                    2: "configs[1]: full two-round SP5->SP27 combinatorial demux + trim on %d synthetic "
                                        "COI-length reads (%d-%d nt) per GPU, -e 0.1 -O 3 --rc, 12+12 M13 indices",
                                     3: "configs[2]: two-round demux on %d synthetic rRNA-cistron reads (%d-%d nt) per GPU",
                                     4: "configs[3]: anchored --no-indels Hamming path, 24 M13 variable indices, %d reads "
