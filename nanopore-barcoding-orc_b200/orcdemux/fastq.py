@@ -43,11 +43,6 @@ class TextBatch:
         return b if b is not None else int(self.lengths[:self.n_reads].sum(dtype=np.uint64))
 
 
-def _pinned(n: int, dtype) -> np.ndarray:
-    from .engine import pinned_empty
-    return pinned_empty(n, dtype)
-
-
 def index_text(text: np.ndarray, n_bytes: int, max_reads: int, final: bool, arrays=None):
     """Run orc_fastq_index over text[:n_bytes].  Returns (n_reads, consumed, arrays)."""
     L = _lib.load()
