@@ -244,6 +244,12 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     ctx->n_bins = ctx->h_tab[0].n_adapters + 1;
     if (p->n_rounds == 2) ctx->n_bins *= ctx->h_tab[1].n_adapters + 1;
     if (ctx->n_bins > MAX_BINS) { ctx->err = "unsupported: more than 512 bins"; return ORC_EINVAL; }
+    // one code array serves both rounds, and the IUPAC comparison reads U as T where the plain one does not
+    for (int r = 1; r < p->n_rounds; r++)
+        if (ctx->h_tab[r].wild != ctx->h_tab[0].wild) {
+            ctx->err = "unsupported: one round with and one without IUPAC wildcards in its adapters";
+            return ORC_EINVAL;
+        }
     ctx->total_counts.assign((size_t)ctx->n_bins, 0);
     ctx->fastq_cap = ctx->max_name_bytes + 2 * ctx->max_bytes + 16ull * ctx->max_reads + 64;
     for (int r = 0; r < p->n_rounds; r++) {
@@ -259,7 +265,7 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         }
     }
     uint8_t lut[256];
-    build_pack_lut(lut);
+    build_pack_lut(lut, ctx->h_tab[0].wild != 0);
     CK(dalloc(&ctx->d_pack_lut, 256));
     CK(cudaMemcpy(ctx->d_pack_lut, lut, 256, cudaMemcpyHostToDevice));
     build_complement_lut(lut);

@@ -95,6 +95,7 @@ struct RoundTable {
     // rows of a 5' adapter, the FIRST rows of a 3' adapter -- row Lb at bit 31, like peq32.
     uint32_t peq32b[16][64];
     int32_t block_len[MAX_AD];    // Lb, or 0: no block test for this adapter (k >= Lb)
+    int32_t wild;                 // 1: the adapters hold IUPAC wildcards (reads compared through the ACGT masks, U = T)
 };
 
 // A read (or what a previous round left of it) as a window of the packed code array:

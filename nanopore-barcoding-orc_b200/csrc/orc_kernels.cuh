@@ -742,6 +742,15 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
         } else {
             warp_copy(o, s, L, lane);
             warp_copy(o + L + 3, q, L, lane);
+            if (nrc >= 2u) {
+                // reverse-complemented in both rounds: dnaio's table sends U to A and A to T, so a read
+                // that is back in its own orientation has T where it had U
+                __syncwarp();
+                for (uint32_t i = lane; i < L; i += 32) {
+                    const uint8_t c = s[i];
+                    if (c == 'U' || c == 'u') o[i] = (uint8_t)(c - 1);
+                }
+            }
         }
         if (lane == 0) { o[L] = '\n'; o[L + 1] = '+'; o[L + 2] = '\n'; o[2 * L + 3] = '\n'; }
     }

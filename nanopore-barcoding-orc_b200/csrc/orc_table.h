@@ -23,6 +23,18 @@ inline int base_code(char c)
     }
 }
 
+// Adapter character -> 4-bit mask, cutadapt's _iupac_table() (X matches nothing, N everything).
+inline int iupac_code(char c)
+{
+    switch (c) {
+    case 'X': return 0;  case 'A': return 1;  case 'C': return 2;  case 'M': return 3;
+    case 'G': return 4;  case 'R': return 5;  case 'S': return 6;  case 'V': return 7;
+    case 'T': return 8;  case 'W': return 9;  case 'Y': return 10; case 'H': return 11;
+    case 'K': return 12; case 'D': return 13; case 'B': return 14; case 'N': return 15;
+    default: return -1;
+    }
+}
+
 // Returns "" on success, else the reason the round is not supported.
 // filter_mode: 0 = never use the shared-prefix trigger filter, 1 = when it pays (prefix >= 12 and
 // > 2k), 2 = whenever it is valid (prefix > k; for tests).
@@ -42,38 +54,65 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
     T.indels = indels ? 1 : 0;
     T.min_overlap = min_overlap;
     T.n_lanes = 2 * n_adapters;
+    int n_wild = 0;
     for (int a = 0; a < n_adapters; a++) {
         const char *s = sequences[a];
         const int m = (int)strlen(s);
         if (m < 1 || m > MAX_M) return "unsupported: adapter length must be 1..64";
         T.m[a] = m;
+        // n_counts[i] = number of N in adapter[0 : i] (_align.pyx _set_reference); an adapter with any
+        // character outside ACGT is compared through the IUPAC masks (adapters.py adapter_wildcards)
+        int n_counts[MAX_M + 1];
+        bool wild = false;
+        int nN = 0;
         for (int i = 0; i < m; i++) {
             char c = s[i];
             if (c >= 'a' && c <= 'z') c = (char)(c - 32);
             if (c == 'U') c = 'T';
-            const int code = base_code(c);
-            if (code < 0) return "unsupported: adapter characters other than ACGT (IUPAC wildcards)";
+            if (c == 'I') c = 'N';
+            const int code = iupac_code(c);
+            if (code < 0) return "unsupported: adapter character outside the IUPAC alphabet";
             T.code[a][i] = (uint8_t)code;
+            n_counts[i] = nN;
+            if (base_code(c) < 0) wild = true;
+            if (c == 'N') nN++;
         }
+        n_counts[m] = nN;
+        if (wild) n_wild++;
         for (int q = 0; q < m; q++) {
             const int f = 16 + q;                   // code4: 16 pad nibbles, then the adapter
             T.code4[a][f >> 3] |= (uint32_t)T.code[a][q] << ((f & 7) * 4);
             T.rcode4[a][q >> 3] |= comp4(T.code[a][m - 1 - q]) << ((q & 7) * 4);
         }
         double rate = max_errors;
-        if (rate >= 1.0) rate /= m;                 // absolute error count (adapters.py)
+        if (rate >= 1.0) {                          // absolute error count (adapters.py)
+            if (m - nN < 1) return "unsupported: an absolute error count for an adapter made of N only";
+            rate /= (m - nN);
+        }
         if (!(rate >= 0.0) || rate >= 1.0) return "unsupported: error rate must be in [0, 1) for every adapter";
         T.k[a] = (int)(rate * m);                   // _align.pyx: k = <int>(max_error_rate * m)
         T.min_ov[a] = min_overlap < m ? min_overlap : m;
         for (int L = 0; L <= m; L++) {
-            // largest integer cost with (double)cost <= L * rate
-            double x = L * rate;
+            // largest integer cost with (double)cost <= effective_length * rate.  _align.pyx takes the
+            // N of adapter[0 : L] off an overlap of L < m characters in the last-row test (R5) and the N
+            // of the aligned adapter part in the last-column test (R6).  A 3' adapter always aligns
+            // from its first character, so the two agree; a 5' adapter reaches R6 with L < m only for
+            // its last L characters, and the round is refused when that would need a second table.
+            const int eff5 = L - n_counts[L];
+            const int eff6 = (type == TYPE_BACK) ? eff5 : L - (n_counts[m] - n_counts[m - L]);
+            double x = eff5 * rate;
             int c = (int)floor(x);
             if (c < 0) c = 0;
             if (c > 255) c = 255;
+            if (L >= T.min_ov[a] && (int)floor(eff6 * rate) != (int)floor(x))
+                return "unsupported: N wildcards placed so that a 5' adapter's partial overlaps would need "
+                       "different error limits at the read start and the read end";
             T.kmax[a][L] = (uint8_t)c;
         }
     }
+    if (n_wild != 0 && n_wild != n_adapters)
+        return "unsupported: adapters with and without IUPAC wildcards in one round";
+    T.wild = n_wild ? 1 : 0;
     for (int lane = 0; lane < T.n_lanes; lane++) {
         const int a = lane % n_adapters, dir = lane / n_adapters;
         const int m = T.m[a];
@@ -202,7 +241,7 @@ inline void build_seed_table(const RoundTable &T, SeedTable &S, bool enable)
 {
     memset(&S, 0, sizeof(S));
     for (int i = 0; i < SEED_SLOTS; i++) S.key[i] = SEED_EMPTY;
-    if (!enable || !T.use_filter) return;
+    if (!enable || !T.use_filter || T.wild) return;      // a piece with a wildcard equals no read 8-mer
     int need = 2;
     for (int a = 0; a < T.n_adapters; a++) {
         const int avail = T.m[a] / 8 - T.k[a];
@@ -308,13 +347,15 @@ inline std::string build_anchored_table(AnchoredTable &A, RoundTable &T, int n_a
 // ASCII -> 4-bit code used by the pack kernel.  cutadapt compares ASCII after upper()
 // when the adapter is plain ACGT, so only ACGT/acgt get a code; anything
 // else (N, U, IUPAC, '-') is 0 and matches nothing.
-inline void build_pack_lut(uint8_t lut[256])
+// Adapters with IUPAC wildcards are compared through _acgt_table() instead, which also knows U = T.
+inline void build_pack_lut(uint8_t lut[256], bool wild = false)
 {
     memset(lut, 0, 256);
     lut[(int)'A'] = lut[(int)'a'] = 1;
     lut[(int)'C'] = lut[(int)'c'] = 2;
     lut[(int)'G'] = lut[(int)'g'] = 4;
     lut[(int)'T'] = lut[(int)'t'] = 8;
+    if (wild) lut[(int)'U'] = lut[(int)'u'] = 8;
 }
 
 // dnaio SequenceRecord.reverse_complement(): IUPAC complement, case preserved.

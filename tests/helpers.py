@@ -108,5 +108,10 @@ def view_bytes(rs, lo, ln, rc):
         if rc[i] & 1:
             s = comp[s[::-1]]
             q = q[::-1]
+        elif (int(rc[i]) >> 8) >= 2:
+            # flipped in both rounds: dnaio's table sends U to A and A to T
+            s = s.copy()
+            s[s == ord("U")] = ord("T")
+            s[s == ord("u")] = ord("t")
         out.append((s.tobytes(), q.tobytes()))
     return out

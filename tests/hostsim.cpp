@@ -55,8 +55,16 @@ extern "C" int hostsim_demux(int n_rounds,
         delete[] ST;
         return -1;
     }
+    if (n_rounds > 1 && T[0].wild != T[1].wild) {
+        strncpy(err, "unsupported: one round with and one without IUPAC wildcards in its adapters", (size_t)err_len - 1);
+        err[err_len - 1] = 0;
+        delete[] T;
+        delete[] AT;
+        delete[] ST;
+        return -1;
+    }
     uint8_t lut[256];
-    build_pack_lut(lut);
+    build_pack_lut(lut, T[0].wild != 0);
     // flat pack with 4 guard words in front and 16 + 4 behind, like the device buffers
     const uint64_t n_words = (n_bytes + 7) / 8;
     std::vector<uint32_t> codes(n_words + 24, 0);

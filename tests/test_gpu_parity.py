@@ -235,6 +235,48 @@ def test_adversarial_and_random_adapter_sets():
         assert np.array_equal(res.out_len, rec[4])
 
 
+def test_iupac_adapter_sets_gpu():
+    """Adapters with IUPAC wildcards through the kernels (mask comparison, N taken out of the effective
+    length, U read as T), FASTQ bytes included: reads with U that both rounds reverse-complement come
+    out with T (dnaio's complement table), which the emit kernel has to reproduce."""
+    import random
+    import oracle
+    import test_hostsim as TH
+    from orcdemux.lib import ORC_BACK, ORC_FRONT
+    rnd = random.Random(4040)
+    done = 0
+    for trial in range(8):
+        f, b = TH._iupac_sets(rnd, n_in_front=False)
+        e = rnd.choice([0.0, 0.1, 0.1, 0.15, 0.2])
+        ov = rnd.choice([1, 3, 3, 5])
+        spec = [(f, oracle.FRONT, e, ov, 1), (b, oracle.BACK, e, ov, 1)]
+        if trial % 4 == 3:
+            spec = spec[::-1]
+        rs = TH._adversarial_reads(rnd, TH._instances(rnd, f), TH._instances(rnd, b), 1500)
+        recs = [rs.read(i) for i in range(rs.n_reads)]
+        recs = [(nm, sq.replace("T", "U").replace("t", "u") if i % 5 == 0 else sq, q) for i, (nm, sq, q) in enumerate(recs)]
+        rs = synth.from_records(recs)
+        rounds = [E.Round([str(i) for i in range(len(x[0]))], x[0], ORC_FRONT if x[1] == oracle.FRONT else ORC_BACK,
+                          x[2], x[3], True, bool(x[4])) for x in spec]
+        with E.Engine(rounds, max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]) + 64,
+                      max_name_bytes=int(rs.names.shape[0]) + 64, n_slots=1, emit_fastq=True, want_matches=True) as eng:
+            res = eng.run(rs)
+            rec0, rec1, oseq, oqual, olen = H.run_oracle(spec, rs)
+            idx, nbad = H.diff_matches(rec0, res.matches[0])
+            assert nbad == 0, (trial, "round 1", idx[:3], rs.read(int(idx[0]))[1])
+            idx, nbad = H.diff_matches(rec1, res.matches[1])
+            assert nbad == 0, (trial, "round 2", idx[:3])
+            assert np.array_equal(res.out_len, olen)
+            exp = _expected_fastq(rs, rec0, rec1, oseq, oqual, olen, eng.n_bins, eng.bin_id)
+            for bb in range(eng.n_bins):
+                assert res.bin_bytes(bb) == exp[bb], "trial %d bin %d bytes differ" % (trial, bb)
+        both = (rec0["is_rc"] == 1) & (rec1["is_rc"] == 1)
+        done += int(both.sum())
+    assert done > 0         # some reads were flipped twice
+    with pytest.raises(E.OrcError, match="unsupported"):
+        E.Engine([E.Round(["a", "b"], ["ACGTACGT", "ACGNACGT"], ORC_BACK, 0.1, 3, True, True)], max_reads=16, max_bytes=1024)
+
+
 def test_seeded_stage1_random_adapter_sets():
     """Adapter sets stage 1 can seed (long adapters, long shared prefix, low error rates; pieces per
     adapter minus errors 1 or 2) through the kernels, with and without the seed table."""
