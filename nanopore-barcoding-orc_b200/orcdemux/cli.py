@@ -30,6 +30,9 @@ from . import fastq as F
 from .lib import ORC_BACK, ORC_FRONT, ORC_PREFIX, ORC_SUFFIX
 
 
+from .primers import Unsupported as _PrimersUnsupported
+
+
 class Unsupported(Exception):
     pass
 
@@ -71,7 +74,8 @@ def _parse_adapter_specs(specs: List[str], kind: int):
 
 def parse_cutadapt_argv(argv: List[str]):
     opt = dict(e=0.1, O=3, rc=False, indels=True, action="trim", json=None, out=None, cores=1,
-               g=[], a=[], level=1, inputs=[], quiet=False)      # cutadapt 4.x: gzip level 1 unless --compression-level
+               g=[], a=[], level=1, inputs=[], quiet=False,      # cutadapt 4.x: gzip level 1 unless --compression-level
+               untrimmed_output=None, discard_untrimmed=False)
     i = 0
 
     def need(flag):
@@ -111,6 +115,10 @@ def parse_cutadapt_argv(argv: List[str]):
             opt["a"].append(val if val is not None else need(key))
         elif key in ("-o", "--output"):
             opt["out"] = val if val is not None else need(key)
+        elif key == "--untrimmed-output":
+            opt["untrimmed_output"] = val if val is not None else need(key)
+        elif key in ("--discard-untrimmed", "--trimmed-only"):
+            opt["discard_untrimmed"] = True
         elif key == "--json":
             opt["json"] = val if val is not None else need(key)
         elif key in ("-Z",):
@@ -130,11 +138,45 @@ def parse_cutadapt_argv(argv: List[str]):
         raise Unsupported("--action=%s (only trim)" % opt["action"])
     if len(opt["inputs"]) != 1:
         raise Unsupported("exactly one (single-end) input file is expected, got %d" % len(opt["inputs"]))
+    if not opt["out"]:
+        raise Unsupported("-o is required")
+    if "{name}" not in opt["out"]:
+        # one output file: the primer-trimming call shapes of 04_cleaning_primers.sh (orcdemux/primers.py)
+        if not (opt["g"] or opt["a"]):
+            raise Unsupported("no adapters given")
+        return opt
+    if opt["untrimmed_output"] or opt["discard_untrimmed"]:
+        raise Unsupported("--untrimmed-output / --discard-untrimmed together with a {name} template")
+    if any("..." in x for x in opt["g"] + opt["a"]):
+        raise Unsupported("linked adapters together with a {name} template")
     if bool(opt["g"]) == bool(opt["a"]):
         raise Unsupported("give either -g or -a adapters (one adapter type per invocation)")
-    if not opt["out"] or "{name}" not in opt["out"]:
-        raise Unsupported("-o with a {name} template is required (demultiplexing mode)")
     return opt
+
+
+def run_primer_trim(opt, argv, device=0) -> int:
+    """One output file (no {name}): linked -g FWD...REV pairs or one plain adapter type, optional
+    --untrimmed-output / --discard-untrimmed, FASTA or FASTQ (04_cleaning_primers.sh:371-388, 468-507)."""
+    from . import primers
+    t0 = time.time()
+    c = primers.run(opt, device=device)
+    rep = _report(c["n_in"], c["bp_in"], c["bp_out"], c["n_with"], 0, list(c["per_adapter"]),
+                  np.array(list(c["per_adapter"].values()), dtype=np.int64), time.time() - t0, argv)
+    rep["input"]["path1"] = opt["inputs"][0]
+    rep["read_counts"]["output"] = c["n_written"]
+    if opt["json"]:
+        with open(opt["json"], "w") as fh:
+            json.dump(rep, fh, indent=2)
+    if not opt["quiet"]:
+        print("This is orcdemux (cutadapt 4.9-compatible primer trimming on B200)")
+        print("Command line parameters: " + " ".join(argv))
+        print("=== Summary ===\n")
+        print("Total reads processed:           %15s" % format(c["n_in"], ","))
+        print("Reads with adapters:             %15s (%.1f%%)" % (format(c["n_with"], ","), 100.0 * c["n_with"] / max(c["n_in"], 1)))
+        print("Reads written (passing filters): %15s (%.1f%%)\n" % (format(c["n_written"], ","), 100.0 * c["n_written"] / max(c["n_in"], 1)))
+        for nm, k in c["per_adapter"].items():
+            print("=== Adapter %s ===\n\nTrimmed: %d times\n" % (nm, k))
+    return 0
 
 
 def _report(n_in, bp_in, bp_out, n_with, n_rc, names, per_adapter, elapsed, argv):
@@ -476,8 +518,10 @@ def main(argv: Optional[List[str]] = None) -> int:
             print("4.9 (orcdemux)")
             return 0
         opt = parse_cutadapt_argv(argv)
+        if "{name}" not in opt["out"]:
+            return run_primer_trim(opt, argv)
         return run_single_round(opt, argv)
-    except Unsupported as e:
+    except (Unsupported, _PrimersUnsupported) as e:
         sys.stderr.write("orcdemux: unsupported: %s\n" % e)
         return 2
     except (E.OrcError, ValueError, OSError) as e:

@@ -1,0 +1,229 @@
+"""Primer trimming with one output file: the cutadapt call shapes of the reference's
+scripts/04_cleaning_primers.sh.
+
+  round 1 (04:371-388)  cutadapt -j N -g FWD...REV [-g FWD2...REV2 ...]
+                                 --untrimmed-output=UNTRIMMED.fasta -o TRIMMED.fasta CONSENSUS.fasta
+  round 2 (04:468-507)  cutadapt -j N -g FWD ... -o OUT.fasta UNTRIMMED.fasta      (one adapter type only)
+
+A linked adapter given with -g is cutadapt's LinkedAdapter with both parts required and neither
+anchored (parser.py _parse_linked): the 5' part is located in the read, the 3' part in what is left
+behind it, and the read counts as trimmed only when both are found; score and errors of the pair are
+the sums (LinkedMatch), and of several pairs the best wins by MultipleAdapters' rule (score, then
+fewer errors, then order).  Each pair is one two-round pass of the GPU engine (5' round, 3' round on
+the remainder) -- the same kernels as the demultiplexer, with IUPAC wildcards in the primers; the
+selection over the pairs and the FASTA/FASTQ files are handled here.  These inputs are consensus
+sequences (thousands of records), so the records are read and written in Python; the streaming
+native reader/writers are the demultiplexer's.
+
+Not supported here (exit 2): --rc, -g and -a mixed without linking (needs a best-of across adapter
+types in one pass), anchored parts, per-adapter parameters (;e=...), `required`/`optional`."""
+from __future__ import annotations
+
+import gzip
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine as E
+from . import synth
+from .lib import MATCH_DTYPE, ORC_BACK, ORC_FRONT
+
+Record = Tuple[str, str, Optional[str]]          # name (header without @ or >), sequence, qualities or None
+
+
+class Unsupported(Exception):
+    pass
+
+
+def parse_linked_specs(specs: Sequence[str]):
+    """-g values -> [(name, fwd, rev)] if every one is linked, [] if none is."""
+    out = []
+    n_linked = 0
+    for i, spec in enumerate(specs):
+        name, s = None, spec
+        if "=" in s and "..." in s.split("=", 1)[1]:
+            name, s = s.split("=", 1)
+        if "..." not in s:
+            continue
+        n_linked += 1
+        fwd, rev = s.split("...", 1)
+        for part in (fwd, rev):
+            if not part or any(c in part for c in "^$;{}[]. ") or part.startswith("file:"):
+                raise Unsupported("linked adapter syntax beyond SEQ1...SEQ2: %r" % spec)
+        out.append((name or str(i + 1), fwd.upper().replace("U", "T"), rev.upper().replace("U", "T")))
+    if n_linked and n_linked != len(specs):
+        raise Unsupported("linked and plain adapters in one invocation")
+    return out
+
+
+def _open(path: str, mode: str):
+    return gzip.open(path, mode) if path.endswith(".gz") else open(path, mode)
+
+
+def read_sequences(path: str) -> Tuple[List[Record], str]:
+    """FASTA (multi-line allowed) or FASTQ (four-line), optionally gzipped -> (records, format)."""
+    with _open(path, "rt") as fh:
+        text = fh.read()
+    if not text.strip():
+        return [], "fasta"
+    first = text.lstrip()[0]
+    recs: List[Record] = []
+    if first == ">":
+        name, parts = None, []
+        for line in text.splitlines():
+            if line.startswith(">"):
+                if name is not None:
+                    recs.append((name, "".join(parts), None))
+                name, parts = line[1:], []
+            elif name is not None:
+                parts.append(line.strip())
+        if name is not None:
+            recs.append((name, "".join(parts), None))
+        return recs, "fasta"
+    if first != "@":
+        raise ValueError("%s is neither FASTA nor FASTQ" % path)
+    lines = text.splitlines()
+    if len(lines) % 4:
+        raise ValueError("%s: FASTQ record cut short" % path)
+    for i in range(0, len(lines), 4):
+        if not lines[i].startswith("@") or not lines[i + 2].startswith("+") or len(lines[i + 1]) != len(lines[i + 3]):
+            raise ValueError("%s: malformed FASTQ record at line %d" % (path, i + 1))
+        recs.append((lines[i][1:], lines[i + 1], lines[i + 3]))
+    return recs, "fastq"
+
+
+def output_format(path: str, input_format: str) -> str:
+    base = path[:-3] if path.endswith(".gz") else path
+    ext = os.path.splitext(base)[1].lower()
+    if ext in (".fasta", ".fa", ".fna"):
+        return "fasta"
+    if ext in (".fastq", ".fq"):
+        return "fastq"
+    return input_format
+
+
+def write_sequences(path: str, recs: Sequence[Record], fmt: str) -> None:
+    with _open(path, "wt") as fh:
+        for name, seq, qual in recs:
+            if fmt == "fasta":
+                fh.write(">%s\n%s\n" % (name, seq))          # dnaio FastaWriter: one line per sequence
+            else:
+                if qual is None:
+                    raise Unsupported("FASTQ output from FASTA input (no qualities)")
+                fh.write("@%s\n%s\n+\n%s\n" % (name, seq, qual))
+
+
+def select_linked(m0s: Sequence[np.ndarray], m1s: Sequence[np.ndarray]) -> np.ndarray:
+    """Per read the index of the winning linked pair, -1 if no pair has both parts.
+    MultipleAdapters.match_to over LinkedMatch objects: higher summed score, then fewer summed
+    errors, then the first in command-line order."""
+    n = m0s[0].shape[0]
+    best = np.full(n, -1, dtype=np.int32)
+    bscore = np.zeros(n, dtype=np.int64)
+    berr = np.zeros(n, dtype=np.int64)
+    for i, (m0, m1) in enumerate(zip(m0s, m1s)):
+        ok = (m0["adapter"] >= 0) & (m1["adapter"] >= 0)
+        score = m0["score"].astype(np.int64) + m1["score"]
+        err = m0["errors"].astype(np.int64) + m1["errors"]
+        take = ok & ((best < 0) | (score > bscore) | ((score == bscore) & (err < berr)))
+        best[take] = i
+        bscore[take] = score[take]
+        berr[take] = err[take]
+    return best
+
+
+def trim_linked(recs: Sequence[Record], m0s, m1s, best: np.ndarray):
+    """-> (trimmed-or-unchanged records in input order, boolean mask of the trimmed ones)."""
+    out: List[Record] = []
+    for r, (name, seq, qual) in enumerate(recs):
+        i = int(best[r])
+        if i < 0:
+            out.append((name, seq, qual))
+            continue
+        a = int(m0s[i]["query_stop"][r])                    # RemoveBeforeMatch
+        b = a + int(m1s[i]["query_start"][r])               # RemoveAfterMatch on the remainder
+        out.append((name, seq[a:b], qual[a:b] if qual is not None else None))
+    return out, best >= 0
+
+
+def trim_single(recs: Sequence[Record], m: np.ndarray, front: bool):
+    out: List[Record] = []
+    for r, (name, seq, qual) in enumerate(recs):
+        if m["adapter"][r] < 0:
+            out.append((name, seq, qual))
+        elif front:
+            a = int(m["query_stop"][r])
+            out.append((name, seq[a:], qual[a:] if qual is not None else None))
+        else:
+            b = int(m["query_start"][r])
+            out.append((name, seq[:b], qual[:b] if qual is not None else None))
+    return out, m["adapter"] >= 0
+
+
+def _match_batches(rounds, recs: Sequence[Record], device: int, batch: int = 1 << 16):
+    """Run `rounds` over the records on the GPU -> one match-record array per round."""
+    sets = []
+    for lo in range(0, len(recs), batch):
+        part = recs[lo:lo + batch]
+        sets.append(synth.from_records([(nm, sq, q if q is not None else "I" * len(sq)) for nm, sq, q in part]))
+    outs: List[List[np.ndarray]] = [[] for _ in rounds]
+    with E.Engine(rounds, device=device, max_reads=max(rs.n_reads for rs in sets),
+                  max_bytes=max(int(rs.seq.shape[0]) for rs in sets) + 64,
+                  max_name_bytes=max(int(rs.names.shape[0]) for rs in sets) + 64, n_slots=1,
+                  emit_fastq=False, want_matches=True) as eng:
+        for rs in sets:
+            res = eng.run(rs)
+            for k in range(len(rounds)):
+                outs[k].append(np.array(res.matches[k], copy=True))
+    return [np.concatenate(x) for x in outs]
+
+
+def run(opt, device: int = 0):
+    """opt: the dict of cli.parse_cutadapt_argv.  Returns the counters for the report."""
+    if opt["rc"]:
+        raise Unsupported("--rc together with a single output file")
+    recs, fmt = read_sequences(opt["inputs"][0])
+    pairs = parse_linked_specs(opt["g"])
+    e, ov, indels = opt["e"], opt["O"], opt["indels"]
+    if pairs:
+        if opt["a"]:
+            raise Unsupported("-a next to linked -g adapters")
+        m0s, m1s = [], []
+        for name, fwd, rev in pairs:
+            rounds = [E.Round([name], [fwd], ORC_FRONT, e, ov, indels, False),
+                      E.Round([name], [rev], ORC_BACK, e, ov, indels, False)]
+            m0, m1 = _match_batches(rounds, recs, device) if recs else (np.zeros(0, MATCH_DTYPE),) * 2
+            m0s.append(m0)
+            m1s.append(m1)
+        best = select_linked(m0s, m1s) if recs else np.zeros(0, np.int32)
+        out, trimmed = trim_linked(recs, m0s, m1s, best)
+        per_adapter = {p[0]: int((best == i).sum()) for i, p in enumerate(pairs)}
+    else:
+        if bool(opt["g"]) == bool(opt["a"]):
+            raise Unsupported("-g and -a in one invocation without linking them (FWD...REV)")
+        from .cli import _parse_adapter_specs
+        kind = ORC_FRONT if opt["g"] else ORC_BACK
+        names, seqs, anchored = _parse_adapter_specs(opt["g"] or opt["a"], kind)
+        if anchored:
+            raise Unsupported("anchored adapters together with a single output file")
+        rounds = [E.Round(names, seqs, kind, e, ov, indels, False)]
+        m = _match_batches(rounds, recs, device)[0] if recs else np.zeros(0, MATCH_DTYPE)
+        out, trimmed = trim_single(recs, m, kind == ORC_FRONT)
+        per_adapter = {nm: int((m["adapter"] == i).sum()) for i, nm in enumerate(names)}
+    ofmt = output_format(opt["out"], fmt)
+    if opt["untrimmed_output"]:
+        write_sequences(opt["out"], [x for x, t in zip(out, trimmed) if t], ofmt)
+        write_sequences(opt["untrimmed_output"], [x for x, t in zip(out, trimmed) if not t],
+                        output_format(opt["untrimmed_output"], fmt))
+        written = int(trimmed.sum())
+    elif opt["discard_untrimmed"]:
+        write_sequences(opt["out"], [x for x, t in zip(out, trimmed) if t], ofmt)
+        written = int(trimmed.sum())
+    else:
+        write_sequences(opt["out"], out, ofmt)
+        written = len(out)
+    return {"n_in": len(recs), "n_with": int(trimmed.sum()), "n_written": written,
+            "bp_in": sum(len(x[1]) for x in recs), "bp_out": sum(len(x[1]) for x, t in zip(out, trimmed)
+                                                                 if t or not (opt["untrimmed_output"] or opt["discard_untrimmed"])),
+            "per_adapter": per_adapter}
