@@ -10,6 +10,9 @@ Kept surface: -g/-a (file:PATH, SEQ, name=SEQ; several allowed), -e, -O, --actio
 -j (accepted), --json, --no-indels (regular adapters: Hamming distance along diagonals; anchored
 ^file: / file$: adapters: the indexed Hamming fast path; anchored adapters WITH indels are refused),
 -o with {name} (one file per adapter name plus "unknown", all created even if empty).
+Adapters may hold IUPAC wildcards.  Without {name} in -o: one output file, linked -g FWD...REV pairs or
+one plain adapter type, --untrimmed-output / --discard-untrimmed, FASTA or FASTQ (primers.py; the
+call shapes of 04_cleaning_primers.sh:371-388, 468-507).
 Anything else exits with status 2 and an "unsupported" message: there is no CPU fallback.
 
 `python -m orcdemux.cli two-round ...` runs both rounds fused on the GPU and leaves the file
