@@ -71,10 +71,11 @@ def test_cli_surface_parsing():
     assert opt["g"] == ["file:x.fa"] and opt["inputs"] == ["in.fastq.gz"]
     opt = cli.parse_cutadapt_argv("-a file:y.fa -O 5 --no-indels -e0.2 -o {name}.fq in.fq".split())
     assert opt["O"] == 5 and not opt["indels"] and opt["e"] == 0.2 and opt["a"] == ["file:y.fa"]
-    for bad in ("-m 10 -g AAA -o {name}.fq in.fq", "-g AAA -a CCC -o {name} in", "-g AAA -o out.fq in",
+    for bad in ("-m 10 -g AAA -o {name}.fq in.fq", "-g AAA -a CCC -o {name} in", "-g AAA --discard-untrimmed -o {name}.fq in", "-g AAA in",
                 "--action=mask -g AAA -o {name} in", "-g AAA -o {name} a.fq b.fq"):
         with pytest.raises(cli.Unsupported):
             cli.parse_cutadapt_argv(bad.split())
+    assert cli.parse_cutadapt_argv("-g AAA -o out.fq in".split())["out"] == "out.fq"      # one output: primers.py
     assert cli.dataset_name("/x/pychopped/pychopped_s1_pass.fastq.gz") == "s1"
     names, seqs, anchored = cli._parse_adapter_specs(["first=ACGT", "TTGCA"], 0)
     assert names == ["first", "2"] and seqs == ["ACGT", "TTGCA"] and not anchored
