@@ -23,6 +23,7 @@
 //  select_read()   R8 (best of the adapters) and R9 (--rc: strictly higher score wins),
 //                  R10 (trim -> the next view of the read).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -60,7 +61,14 @@ struct RoundTable {
     int32_t m[MAX_AD];              // adapter length
     int32_t k[MAX_AD];              // int(max_error_rate * m)
     int32_t min_ov[MAX_AD];         // min(min_overlap, m)
-    uint8_t kmax[MAX_AD][MAX_M + 8];// kmax[a][L] = max cost with cost <= L * rate (fp64, R5/R6)
+    uint8_t kmax[MAX_AD][MAX_M + 8];// kmax[a][L] = max cost with cost <= L * rate (fp64, R5/R6); with N wildcards in a
+                                    // 5' adapter the larger of the two tables below: what every pruning test reads
+    // The exact limits of the last-row test (R5) and the last-column test (R6): _align.pyx takes different N
+    // counts off the overlap length in the two.  They differ from kmax only for 5' adapters with N wildcards.
+    // r5_update / r6_update find them at a fixed distance behind the kmax row they are handed (KMAX_R5 / KMAX_R6),
+    // so the three arrays must stay adjacent, also in the shared-memory copies of the table head.
+    uint8_t kmax_r5[MAX_AD][MAX_M + 8];
+    uint8_t kmax_r6[MAX_AD][MAX_M + 8];
     uint8_t code[MAX_AD][MAX_M];    // adapter as 4-bit IUPAC masks (A1 C2 G4 T8)
     // the same, 8 codes per word, for the resolver's 16-cells-at-a-time diagonal walk:
     // code4: nibble 16+q = adapter[q] (16 zero nibbles in front); rcode4: nibble q =
@@ -217,6 +225,11 @@ ORC_HD uint64_t nib16(const uint32_t *A, int64_t idx)
 }
 
 
+// distance from kmax[a] to kmax_r5[a] / kmax_r6[a]
+constexpr int KMAX_R5 = MAX_AD * (MAX_M + 8), KMAX_R6 = 2 * KMAX_R5;
+static_assert(offsetof(RoundTable, kmax_r5) == offsetof(RoundTable, kmax) + KMAX_R5 &&
+              offsetof(RoundTable, kmax_r6) == offsetof(RoundTable, kmax) + KMAX_R6, "kmax, kmax_r5, kmax_r6 must be adjacent");
+
 // cutadapt's running best match of one Aligner.locate call (R5-R7) and one DP cell.
 struct Best { int32_t score, cost, origin, ref_stop, query_stop; };
 struct Cell { int32_t cost, score, origin; };
@@ -225,7 +238,7 @@ struct Cell { int32_t cost, score, origin; };
 ORC_HD bool r5_update(Best &b, int m, int n, const Cell &c, int j, int min_ov, const uint8_t *kmax)
 {
     const int length = m + imin(c.origin, 0);
-    if (!(length >= min_ov && c.cost <= (int)kmax[length])) return false;
+    if (!(length >= min_ov && c.cost <= (int)kmax[KMAX_R5 + length])) return false;
     const int best_length = m + imin(b.origin, 0);
     if (b.cost == m + n + 1 ||
         (c.origin <= b.origin + m / 2 && c.score > b.score) ||
@@ -240,7 +253,7 @@ ORC_HD bool r5_update(Best &b, int m, int n, const Cell &c, int j, int min_ov, c
 ORC_HD void r6_update(Best &b, int n, const Cell &c, int i, int min_ov, const uint8_t *kmax)
 {
     const int length = i + imin(c.origin, 0);
-    if (!(length >= min_ov && c.cost <= (int)kmax[length])) return;
+    if (!(length >= min_ov && c.cost <= (int)kmax[KMAX_R6 + length])) return;
     if (c.score > b.score || (c.score == b.score && c.cost < b.cost)) {
         b.score = c.score; b.cost = c.cost; b.origin = c.origin; b.ref_stop = i; b.query_stop = n;
     }
@@ -1459,7 +1472,7 @@ ORC_HD void resolve_finish(const uint32_t *W, uint64_t lo, uint32_t len, Resolve
             if (have) {
                 if (j == n) { C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin; }
                 const int length = m + imin(c.origin, 0);
-                if (length >= C.min_ov && c.cost <= (int)C.kmax[length] &&
+                if (length >= C.min_ov && c.cost <= (int)C.kmax[KMAX_R5 + length] &&
                     (best.cost == m + n + 1 || c.score > best.score || (c.score == best.score && j < best.query_stop))) {
                     best.score = c.score; best.cost = c.cost; best.origin = c.origin; best.ref_stop = m; best.query_stop = j;
                 }

@@ -96,18 +96,16 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
             // largest integer cost with (double)cost <= effective_length * rate.  _align.pyx takes the
             // N of adapter[0 : L] off an overlap of L < m characters in the last-row test (R5) and the N
             // of the aligned adapter part in the last-column test (R6).  A 3' adapter always aligns
-            // from its first character, so the two agree; a 5' adapter reaches R6 with L < m only for
-            // its last L characters, and the round is refused when that would need a second table.
+            // from its first character, so the two agree; a 5' adapter reaches R6 with L < m only with
+            // its last L characters (a read that lies inside the adapter).
             const int eff5 = L - n_counts[L];
             const int eff6 = (type == TYPE_BACK) ? eff5 : L - (n_counts[m] - n_counts[m - L]);
-            double x = eff5 * rate;
-            int c = (int)floor(x);
-            if (c < 0) c = 0;
-            if (c > 255) c = 255;
-            if (L >= T.min_ov[a] && (int)floor(eff6 * rate) != (int)floor(x))
-                return "unsupported: N wildcards placed so that a 5' adapter's partial overlaps would need "
-                       "different error limits at the read start and the read end";
-            T.kmax[a][L] = (uint8_t)c;
+            int c5 = (int)floor(eff5 * rate), c6 = (int)floor(eff6 * rate);
+            c5 = c5 < 0 ? 0 : (c5 > 255 ? 255 : c5);
+            c6 = c6 < 0 ? 0 : (c6 > 255 ? 255 : c6);
+            T.kmax_r5[a][L] = (uint8_t)c5;
+            T.kmax_r6[a][L] = (uint8_t)c6;
+            T.kmax[a][L] = (uint8_t)(c5 > c6 ? c5 : c6);
         }
     }
     if (n_wild != 0 && n_wild != n_adapters)

@@ -246,7 +246,7 @@ def test_iupac_adapter_sets_gpu():
     rnd = random.Random(4040)
     done = 0
     for trial in range(8):
-        f, b = TH._iupac_sets(rnd, n_in_front=False)
+        f, b = TH._iupac_sets(rnd, n_in_front=(trial % 2 == 1))
         e = rnd.choice([0.0, 0.1, 0.1, 0.15, 0.2])
         ov = rnd.choice([1, 3, 3, 5])
         spec = [(f, oracle.FRONT, e, ov, 1), (b, oracle.BACK, e, ov, 1)]
@@ -255,6 +255,10 @@ def test_iupac_adapter_sets_gpu():
         rs = TH._adversarial_reads(rnd, TH._instances(rnd, f), TH._instances(rnd, b), 1500)
         recs = [rs.read(i) for i in range(rs.n_reads)]
         recs = [(nm, sq.replace("T", "U").replace("t", "u") if i % 5 == 0 else sq, q) for i, (nm, sq, q) in enumerate(recs)]
+        for a in TH._instances(rnd, f, per=1):         # reads inside a 5' adapter (last-column test, own N count)
+            for _ in range(6):
+                cut = a[-rnd.randint(1, len(a)):]
+                recs.append(("in%d" % len(recs), cut, "I" * len(cut)))
         rs = synth.from_records(recs)
         rounds = [E.Round([str(i) for i in range(len(x[0]))], x[0], ORC_FRONT if x[1] == oracle.FRONT else ORC_BACK,
                           x[2], x[3], True, bool(x[4])) for x in spec]

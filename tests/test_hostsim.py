@@ -289,7 +289,7 @@ def test_iupac_adapter_sets():
     rnd = random.Random(404)
     done = refused = 0
     for trial in range(16):
-        f, b = _iupac_sets(rnd, n_in_front=(trial % 4 == 3))
+        f, b = _iupac_sets(rnd, n_in_front=(trial % 2 == 1))
         e = rnd.choice([0.0, 0.1, 0.1, 0.15, 0.2, 2.0])
         ov = rnd.choice([1, 3, 3, 5, 8])
         rc = rnd.choice([0, 1, 1])
@@ -299,12 +299,21 @@ def test_iupac_adapter_sets():
         rs = _adversarial_reads(rnd, _instances(rnd, f), _instances(rnd, b), 300)
         recs = [rs.read(i) for i in range(rs.n_reads)]
         recs = [(nm, sq.replace("T", "U", 1) if i % 9 == 0 else sq, q) for i, (nm, sq, q) in enumerate(recs)]
+        # reads that lie inside a 5' adapter: the only place where the last-column test sees a partial
+        # overlap of a 5' adapter, with its own N count
+        for a in _instances(rnd, f, per=1):
+            for _ in range(6):
+                cut = a[-rnd.randint(1, len(a)):]
+                if rnd.random() < 0.5 and len(cut) > 2:
+                    p = rnd.randrange(len(cut))
+                    cut = cut[:p] + rnd.choice("ACGT") + cut[p + 1:]
+                recs.append(("in%d" % len(recs), cut, "I" * len(cut)))
         rs = synth.from_records(recs)
         try:
             rec0, rec1 = _compare(rounds, rs, threads=4)
         except RuntimeError as ex:
-            # N placed asymmetrically in a 5' adapter, or an absolute error count that is too large
-            assert "unsupported" in str(ex) and ("error limits" in str(ex) or "error rate" in str(ex)), str(ex)
+            # an absolute error count that is too large for some adapter
+            assert "unsupported" in str(ex) and "error rate" in str(ex), str(ex)
             refused += 1
             continue
         done += 1
