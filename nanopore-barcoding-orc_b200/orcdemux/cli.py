@@ -33,11 +33,7 @@ from . import fastq as F
 from .lib import ORC_BACK, ORC_FRONT, ORC_PREFIX, ORC_SUFFIX
 
 
-from .primers import Unsupported as _PrimersUnsupported
-
-
-class Unsupported(Exception):
-    pass
+from .primers import Unsupported        # one exception type for everything outside the surface (exit status 2)
 
 
 def _parse_adapter_specs(specs: List[str], kind: int):
@@ -78,7 +74,7 @@ def _parse_adapter_specs(specs: List[str], kind: int):
 def parse_cutadapt_argv(argv: List[str]):
     opt = dict(e=0.1, O=3, rc=False, indels=True, action="trim", json=None, out=None, cores=1,
                g=[], a=[], level=1, inputs=[], quiet=False,      # cutadapt 4.x: gzip level 1 unless --compression-level
-               untrimmed_output=None, discard_untrimmed=False)
+               untrimmed_output=None, discard_untrimmed=False, order=[])      # order: "g"/"a" as given
     i = 0
 
     def need(flag):
@@ -114,8 +110,10 @@ def parse_cutadapt_argv(argv: List[str]):
             opt["action"] = val if val is not None else need(key)
         elif key in ("-g", "--front"):
             opt["g"].append(val if val is not None else need(key))
+            opt["order"].append("g")
         elif key in ("-a", "--adapter"):
             opt["a"].append(val if val is not None else need(key))
+            opt["order"].append("a")
         elif key in ("-o", "--output"):
             opt["out"] = val if val is not None else need(key)
         elif key == "--untrimmed-output":
@@ -524,7 +522,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         if "{name}" not in opt["out"]:
             return run_primer_trim(opt, argv)
         return run_single_round(opt, argv)
-    except (Unsupported, _PrimersUnsupported) as e:
+    except Unsupported as e:
         sys.stderr.write("orcdemux: unsupported: %s\n" % e)
         return 2
     except (E.OrcError, ValueError, OSError) as e:

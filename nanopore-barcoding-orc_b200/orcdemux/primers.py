@@ -3,7 +3,7 @@ scripts/04_cleaning_primers.sh.
 
   round 1 (04:371-388)  cutadapt -j N -g FWD...REV [-g FWD2...REV2 ...]
                                  --untrimmed-output=UNTRIMMED.fasta -o TRIMMED.fasta CONSENSUS.fasta
-  round 2 (04:468-507)  cutadapt -j N -g FWD ... -o OUT.fasta UNTRIMMED.fasta      (one adapter type only)
+  round 2 (04:468-507)  cutadapt -j N -g FWD [-g ...] -a REV [-a ...] -o OUT.fasta UNTRIMMED.fasta
 
 A linked adapter given with -g is cutadapt's LinkedAdapter with both parts required and neither
 anchored (parser.py _parse_linked): the 5' part is located in the read, the 3' part in what is left
@@ -15,8 +15,12 @@ selection over the pairs and the FASTA/FASTQ files are handled here.  These inpu
 sequences (thousands of records), so the records are read and written in Python; the streaming
 native reader/writers are the demultiplexer's.
 
-Not supported here (exit 2): --rc, -g and -a mixed without linking (needs a best-of across adapter
-types in one pass), anchored parts, per-adapter parameters (;e=...), `required`/`optional`."""
+Plain adapters, also 5' and 3' ones side by side (round 2 of the script), keep cutadapt's one match
+per read: the best over all adapters in command-line order, found by comparing the winners of the GPU
+passes (one per adapter type and wildcard class, select_best).
+
+Not supported here (exit 2): --rc, anchored parts, per-adapter parameters (;e=...),
+`required`/`optional`, -n / --times above 1."""
 from __future__ import annotations
 
 import gzip
@@ -161,6 +165,31 @@ def trim_single(recs: Sequence[Record], m: np.ndarray, front: bool):
     return out, m["adapter"] >= 0
 
 
+def select_best(ms: Sequence[np.ndarray], poss: Sequence[np.ndarray]):
+    """Plain adapters of both types side by side (04:468-507 gives the forward primers with -g and the
+    reverse ones with -a): cutadapt keeps ONE match per read, the best over all adapters in
+    command-line order (MultipleAdapters.match_to: higher score, then fewer errors, then the first).
+    The adapters are matched in groups on the GPU (one pass per adapter type, and per pass either all or
+    none with IUPAC wildcards); the overall winner is the winner of its group, so the group results are
+    compared by the same rule.  poss[g] maps an adapter index of group g to its place on the command
+    line.  -> (winning group per read or -1, its command-line position or -1)."""
+    n = ms[0].shape[0]
+    best = np.full(n, -1, dtype=np.int32)
+    bpos = np.full(n, -1, dtype=np.int64)
+    bs = np.zeros(n, dtype=np.int64)
+    be = np.zeros(n, dtype=np.int64)
+    for g, (m, pos) in enumerate(zip(ms, poss)):
+        ok = m["adapter"] >= 0
+        p = pos[np.where(ok, m["adapter"], 0)]
+        s_, e_ = m["score"].astype(np.int64), m["errors"].astype(np.int64)
+        take = ok & ((best < 0) | (s_ > bs) | ((s_ == bs) & (e_ < be)) | ((s_ == bs) & (e_ == be) & (p < bpos)))
+        best[take] = g
+        bpos[take] = p[take]
+        bs[take] = s_[take]
+        be[take] = e_[take]
+    return best, bpos
+
+
 def _match_batches(rounds, recs: Sequence[Record], device: int, batch: int = 1 << 16):
     """Run `rounds` over the records on the GPU -> one match-record array per round."""
     sets = []
@@ -200,17 +229,35 @@ def run(opt, device: int = 0):
         out, trimmed = trim_linked(recs, m0s, m1s, best)
         per_adapter = {p[0]: int((best == i).sum()) for i, p in enumerate(pairs)}
     else:
-        if bool(opt["g"]) == bool(opt["a"]):
-            raise Unsupported("-g and -a in one invocation without linking them (FWD...REV)")
         from .cli import _parse_adapter_specs
-        kind = ORC_FRONT if opt["g"] else ORC_BACK
-        names, seqs, anchored = _parse_adapter_specs(opt["g"] or opt["a"], kind)
-        if anchored:
-            raise Unsupported("anchored adapters together with a single output file")
-        rounds = [E.Round(names, seqs, kind, e, ov, indels, False)]
-        m = _match_batches(rounds, recs, device)[0] if recs else np.zeros(0, MATCH_DTYPE)
-        out, trimmed = trim_single(recs, m, kind == ORC_FRONT)
-        per_adapter = {nm: int((m["adapter"] == i).sum()) for i, nm in enumerate(names)}
+        order = opt["order"] or ["g"] * len(opt["g"]) + ["a"] * len(opt["a"])
+        it = {"g": iter(opt["g"]), "a": iter(opt["a"])}
+        groups = {}                         # (adapter type, has wildcards) -> names, sequences, positions
+        all_names = []
+        for t in order:
+            kind = ORC_FRONT if t == "g" else ORC_BACK
+            nm, sq, anchored = _parse_adapter_specs([next(it[t])], kind)
+            if anchored:
+                raise Unsupported("anchored adapters together with a single output file")
+            for a_, b_ in zip(nm, sq):
+                pos = len(all_names)
+                all_names.append(str(pos + 1) if (a_ == "1" and len(nm) == 1) else a_)
+                g = groups.setdefault((kind, any(c not in "ACGT" for c in b_)), ([], [], []))
+                g[0].append(all_names[-1]); g[1].append(b_); g[2].append(pos)
+        kinds, ms, poss = [], [], []
+        for (kind, _), (nm, sq, ps) in groups.items():
+            kinds.append(kind)
+            poss.append(np.array(ps, dtype=np.int64))
+            ms.append(_match_batches([E.Round(nm, sq, kind, e, ov, indels, False)], recs, device)[0]
+                      if recs else np.zeros(0, MATCH_DTYPE))
+        best, bpos = select_best(ms, poss)
+        out = list(recs)
+        for g, kind in enumerate(kinds):
+            mg = ms[g].copy()
+            mg["adapter"][best != g] = -1
+            out, _ = trim_single(out, mg, kind == ORC_FRONT)
+        trimmed = best >= 0
+        per_adapter = {nm: int((bpos == i).sum()) for i, nm in enumerate(all_names)}
     ofmt = output_format(opt["out"], fmt)
     if opt["untrimmed_output"]:
         write_sequences(opt["out"], [x for x, t in zip(out, trimmed) if t], ofmt)

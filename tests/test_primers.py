@@ -112,6 +112,11 @@ def test_select_and_trim():
     out, trimmed = primers.trim_linked(recs, [m0a, m0b], [m1a, m1b], best)
     assert trimmed.tolist() == [True, True, True, True, False]
     assert out[0][1:] == ("EFGHIJ", "456789") and out[1][1:] == ("FGH", "567") and out[2][1] == "FG" and out[4][1] == "ABCDEFGHIJKLMNOP"
+    # plain adapters in groups: group 0 holds command-line positions 0 and 2, group 1 position 1
+    ga = rec([(0, 0, 4, 4, 0), (1, 0, 4, 4, 0), (0, 0, 4, 4, 1), (-1, 0, 0, 0, 0), (-1, 0, 0, 0, 0)])
+    gb = rec([(0, 6, 9, 4, 0), (0, 6, 9, 4, 0), (0, 6, 9, 4, 0), (0, 6, 9, 1, 0), (-1, 0, 0, 0, 0)])
+    best, bpos = primers.select_best([ga, gb], [np.array([0, 2]), np.array([1])])
+    assert best.tolist() == [0, 1, 1, 1, -1] and bpos.tolist() == [0, 1, 1, 1, -1]
     out, trimmed = primers.trim_single(recs, m0b, True)
     assert out[0][1] == "FGHIJKLMNOP" and out[4][1] == "ABCDEFGHIJKLMNOP" and not trimmed[4]
     out, _ = primers.trim_single(recs, m1b, False)
@@ -145,6 +150,26 @@ def test_linked_primers_cli_gpu(tmp_path, capsys):
         m = fs.best_of(seq.upper())
         exp2.append((name, seq[m[1][3]:] if m else seq, None))
     assert primers.read_sequences(str(out2))[0] == exp2
+    # round 2 as the script writes it: forward primers with -g, reverse ones with -a, interleaved, one plain
+    # adapter among the IUPAC ones; one match per read, the best over all of them in command-line order
+    out3 = tmp_path / "round2_mixed.fasta"
+    plain = "ACGTTGCAACGT"
+    argv = ["-j", "8", "-g", FWD, "-a", REV, "-g", "p=" + plain, "-g", FWD2, "-a", REV2, "-o", str(out3), str(src)]
+    assert cli.main(argv) == 0
+    ads = [(FWD, oracle.FRONT), (REV, oracle.BACK), (plain, oracle.FRONT), (FWD2, oracle.FRONT), (REV2, oracle.BACK)]
+    sets = [oracle.AdapterSet([s_], w, 0.1, 3) for s_, w in ads]
+    exp3 = []
+    for name, seq, _ in recs:
+        best = None
+        for (s_, w), st in zip(ads, sets):
+            m = st.match(0, seq.upper())
+            if m is not None and (best is None or m[4] > best[0][4] or (m[4] == best[0][4] and m[5] < best[0][5])):
+                best = (m, w)
+        if best is None:
+            exp3.append((name, seq, None))
+        else:
+            exp3.append((name, seq[best[0][3]:] if best[1] == oracle.FRONT else seq[:best[0][2]], None))
+    assert primers.read_sequences(str(out3))[0] == exp3
+    assert sum(1 for a, b in zip(exp3, recs) if a[1] != b[1]) > 300
     # refused shapes exit 2
-    assert cli.main(["-g", FWD, "-a", REV, "-o", str(out2), str(src)]) == 2
     assert cli.main(["--rc", "-g", "%s...%s" % (FWD, REV), "-o", str(out2), str(src)]) == 2
