@@ -69,7 +69,6 @@ struct RoundTable {
     // so the three arrays must stay adjacent, also in the shared-memory copies of the table head.
     uint8_t kmax_r5[MAX_AD][MAX_M + 8];
     uint8_t kmax_r6[MAX_AD][MAX_M + 8];
-    uint8_t code[MAX_AD][MAX_M];    // adapter as 4-bit IUPAC masks (A1 C2 G4 T8)
     // the same, 8 codes per word, for the resolver's 16-cells-at-a-time diagonal walk:
     // code4: nibble 16+q = adapter[q] (16 zero nibbles in front); rcode4: nibble q =
     // comp(adapter[m-1-q]) (zero nibbles behind) -- what a direction-1 lane compares raw codes with
@@ -104,6 +103,9 @@ struct RoundTable {
     uint32_t peq32b[16][64];
     int32_t block_len[MAX_AD];    // Lb, or 0: no block test for this adapter (k >= Lb)
     int32_t wild;                 // 1: the adapters hold IUPAC wildcards (reads compared through the ACGT masks, U = T)
+    // the adapters as 4-bit IUPAC masks (A1 C2 G4 T8), one per byte: read by the table builders only, kept out
+    // of the head that resolve_kernel stages in shared memory
+    uint8_t code[MAX_AD][MAX_M];
 };
 
 // A read (or what a previous round left of it) as a window of the packed code array:
