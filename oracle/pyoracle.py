@@ -28,14 +28,33 @@ def reverse_complement(seq: str) -> str:
     return "".join(_COMP.get(c, c) for c in reversed(seq))
 
 
+_IUPAC = {"X": 0, "A": 1, "C": 2, "M": 3, "G": 4, "R": 5, "S": 6, "V": 7, "T": 8, "U": 8, "W": 9, "Y": 10,
+          "H": 11, "K": 12, "D": 13, "B": 14, "N": 15}
+_ACGT = {"A": 1, "C": 2, "G": 4, "T": 8, "U": 8}
+
+
 def locate(ref: str, query: str, max_error_rate: float, flags: int, min_overlap: int = 1,
-           indel_cost: int = 1):
-    """Aligner.locate for ASCII comparison (adapter made of ACGT only, no read wildcards).
+           indel_cost: int = 1, wildcard_ref: bool = False):
+    """Aligner.locate for ASCII comparison (adapter made of ACGT only, no read wildcards), or with
+    wildcard_ref for an adapter with IUPAC characters: adapter through _iupac_table(), read through
+    _acgt_table(), characters match when the masks intersect, and the N of the adapter do not count
+    towards the length the error rate applies to (_set_reference n_counts, R5/R6).
 
     Returns (ref_start, ref_stop, query_start, query_stop, score, errors) or None.
     Follows SURVEY 8(c) R1-R7 with the full matrix.
     """
     m, n = len(ref), len(query)
+    if wildcard_ref:
+        n_before = [sum(1 for c in ref[:i] if c in "nN") for i in range(m + 1)]     # N in ref[:i]
+        ref = [_IUPAC.get(c.upper(), 0) for c in ref]
+        query = [_ACGT.get(c.upper(), 0) for c in query]
+        same = lambda a, b: (a & b) != 0
+        eff_row = lambda length: (length - n_before[length]) if length < m else m - n_before[m]
+        eff_col = lambda length, i: (length - (n_before[i] - n_before[i - length])) if length < m else m - n_before[m]
+    else:
+        same = lambda a, b: a == b
+        eff_row = lambda length: length
+        eff_col = lambda length, i: length
     k = int(max_error_rate * m)
     max_n = n if flags & QUERY_START else min(n, m + k)
     min_n = 0 if flags & QUERY_STOP else max(0, n - m - k)
@@ -60,7 +79,7 @@ def locate(ref: str, query: str, max_error_rate: float, flags: int, min_overlap:
             new[0] = (j * indel_cost, col[0][1], col[0][2])
         for i in range(1, m + 1):
             diag, left, up = col[i - 1], col[i], new[i - 1]
-            if ref[i - 1] == query[j - 1]:
+            if same(ref[i - 1], query[j - 1]):
                 new[i] = (diag[0], diag[1] + 1, diag[2])
             else:
                 c_diag, c_del, c_ins = diag[0] + 1, left[0] + indel_cost, up[0] + indel_cost
@@ -74,7 +93,7 @@ def locate(ref: str, query: str, max_error_rate: float, flags: int, min_overlap:
         cost, score, origin = col[m]
         if cost <= k and (flags & QUERY_STOP):
             length = m + min(origin, 0)
-            ok = length >= min_overlap and cost <= length * max_error_rate
+            ok = length >= min_overlap and cost <= eff_row(length) * max_error_rate
             if ok:
                 if best is None:
                     upd = True
@@ -92,7 +111,7 @@ def locate(ref: str, query: str, max_error_rate: float, flags: int, min_overlap:
         for i in range(m, first_i - 1, -1):
             cost, score, origin = col[i]
             length = i + min(origin, 0)
-            ok = length >= min_overlap and cost <= length * max_error_rate
+            ok = length >= min_overlap and cost <= eff_col(length, i) * max_error_rate
             if ok and (best is None or score > best[0] or (score == best[0] and cost < best[1])):
                 best = (score, cost, origin, i, n)
     if best is None:

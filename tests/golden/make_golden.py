@@ -85,6 +85,34 @@ a4 = sp5["SP5_004"]
 flank_sub = list(a4)
 for p in (2, 9, 16, 45, 52):      # 5 substitutions, all in the constant flanks
     flank_sub[p] = "A" if flank_sub[p] != "A" else "C"
+# (d) adapters with IUPAC wildcards (wildcard_ref): recalled from cutadapt's tests/test_align.py
+# test_n_wildcards_not_counted_aligner_back / _front -- the 14 N do not count, so the 20-mer allows
+# int(0.1 * 6) = 0 errors -- plus hand-derived mask cases
+wild = []
+
+
+def LW(ref, query, rate, flags, mo, expect, note):
+    wild.append(dict(ref=ref, query=query, rate=rate, flags=flags, min_overlap=mo, expect=expect, note=note))
+
+
+NREF = "AGGNNNNNNNNNNNNNNTTC"
+LW(NREF, "TTC", 0.1, BACK, 3, None, "upstream KAT (back): adapter end is not a 3' overlap")
+LW(NREF, "AGG", 0.1, BACK, 3, [0, 3, 0, 3, 3, 0], "upstream KAT (back)")
+LW(NREF, "AGGCCCCCCC", 0.1, BACK, 3, [0, 10, 0, 10, 10, 0], "upstream KAT (back): N match anything")
+LW(NREF, "ATGCCCCCCC", 0.1, BACK, 3, None, "upstream KAT (back): 1 error in 3 effective characters")
+LW(NREF, "AGGCCCCCCCCCCCCCCATC", 0.1, BACK, 3, None, "upstream KAT (back): 1 error in 6 effective characters")
+LW(NREF, "CCC" + NREF.replace("N", "C") + "AAA", 0.1, BACK, 3, [0, 20, 3, 23, 20, 0], "upstream KAT (back): full")
+LW(NREF, "TTC", 0.1, FRONT, 3, [17, 20, 0, 3, 3, 0], "upstream KAT (front)")
+LW(NREF, "TGC", 0.1, FRONT, 3, None, "upstream KAT (front)")
+LW(NREF, "CCCCCCCTTC", 0.1, FRONT, 3, [10, 20, 0, 10, 10, 0], "upstream KAT (front)")
+LW(NREF, "CCCCCCCGTC", 0.1, FRONT, 3, None, "upstream KAT (front)")
+LW(NREF, "CCC" + NREF.replace("N", "C") + "AAA", 0.1, FRONT, 3, [0, 20, 3, 23, 20, 0], "upstream KAT (front): full")
+LW("ACRYACGT", "TTACGTACGTTT", 0.0, BACK, 3, [0, 8, 2, 10, 8, 0], "R = A|G, Y = C|T")
+LW("ACRYACGT", "TTACCTACGTTT", 0.0, BACK, 3, None, "C is not in R")
+LW("ACGTNCGT", "TTACGTNCGTTT", 0.0, BACK, 3, None, "a read N matches nothing, not even an adapter N")
+LW("ACGUACGT", "TTACGTACGUTT", 0.0, BACK, 3, [0, 8, 2, 10, 8, 0], "U is T on both sides")
+LW("ACGTXCGT", "TTACGTACGTTT", 0.2, BACK, 3, [0, 8, 2, 10, 6, 1], "X matches nothing: always one error")
+
 reads.append(dict(name="five_flank_substitutions", seq="".join(flank_sub) + ins, sp5="SP5_004", sp27="unknown",
                   r1=[0, 0, 59, 0, 59, 49, 5], trimmed=ins))
 reads.append(dict(name="truncated_5prime", seq=sp5["SP5_009"][20:] + ins + sp27["SP27_008"], sp5="SP5_009", sp27="SP27_008",
@@ -94,5 +122,5 @@ reads.append(dict(name="truncated_3prime", seq=sp5["SP5_009"] + ins + sp27["SP27
 
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kat.json")
 with open(out, "w") as fh:
-    json.dump(dict(source="hand-written expectations; see make_golden.py", locate=loc, reads=reads), fh, indent=1)
+    json.dump(dict(source="hand-written expectations; see make_golden.py", locate=loc, locate_wildcard=wild, reads=reads), fh, indent=1)
 print("wrote", out, len(loc), "locate vectors,", len(reads), "read vectors")

@@ -33,6 +33,47 @@ def test_golden_locate_vectors():
         assert P.locate(*args) == exp, v
 
 
+def test_golden_wildcard_vectors():
+    """Adapters with IUPAC wildcards: cutadapt's own known-answer tests for N (recalled) and
+    hand-derived mask cases, on the C oracle (banded and unpruned) and the Python restatement."""
+    with open(GOLDEN) as fh:
+        kat = json.load(fh)
+    assert len(kat["locate_wildcard"]) >= 16
+    for v in kat["locate_wildcard"]:
+        exp = tuple(v["expect"]) if v["expect"] is not None else None
+        args = (v["ref"], v["query"], v["rate"], v["flags"], v["min_overlap"], 1)
+        assert oracle.locate(*args, wildcard_ref=True) == exp, v
+        assert oracle.locate(*args, wildcard_ref=True, unpruned=True) == exp, v
+        assert P.locate(*args, wildcard_ref=True) == exp, v
+
+
+def test_wildcard_c_vs_python_random():
+    import random
+    rnd = random.Random(515)
+    n_match = 0
+    for _ in range(1500):
+        m = rnd.randint(3, 24)
+        ref = "".join(rnd.choice("ACGTACGTACGTRYSWKMBDHVNNNX") for _ in range(m))
+        inst = "".join(rnd.choice({"R": "AG", "Y": "CT", "S": "CG", "W": "AT", "K": "GT", "M": "AC", "B": "CGT",
+                                   "D": "AGT", "H": "ACT", "V": "ACG", "N": "ACGT", "X": "ACGT"}.get(c, c)) for c in ref)
+        cut = rnd.choice([inst, inst[rnd.randint(0, m - 1):], inst[:rnd.randint(1, m)]])
+        if rnd.random() < 0.5 and cut:
+            p = rnd.randrange(len(cut))
+            cut = cut[:p] + rnd.choice(["", rnd.choice("ACGTNU"), cut[p] + rnd.choice("ACGT")]) + cut[p + 1:]
+        q = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(0, 12))) + cut + \
+            "".join(rnd.choice("ACGT") for _ in range(rnd.randint(0, 12)))
+        if rnd.random() < 0.3:
+            q = cut
+        rate = rnd.choice([0.0, 0.1, 0.2, 0.34])
+        flags = rnd.choice([FRONT, BACK, FRONT, BACK, PREFIX, SUFFIX, 15])
+        mo, ic = rnd.randint(1, 5), rnd.choice([1, 1, 100000])
+        a = oracle.locate(ref, q, rate, flags, mo, ic, wildcard_ref=True)
+        assert a == oracle.locate(ref, q, rate, flags, mo, ic, wildcard_ref=True, unpruned=True) \
+            == P.locate(ref, q, rate, flags, mo, ic, wildcard_ref=True), (ref, q, rate, flags, mo, ic)
+        n_match += a is not None
+    assert n_match > 300
+
+
 def test_golden_read_vectors():
     with open(GOLDEN) as fh:
         kat = json.load(fh)
