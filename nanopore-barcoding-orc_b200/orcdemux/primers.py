@@ -33,6 +33,7 @@ from . import engine as E
 from . import synth
 from .lib import MATCH_DTYPE, ORC_BACK, ORC_FRONT
 
+MAX_PER_PASS = 16                                # adapters per GPU pass (csrc/orc_core.cuh MAX_AD)
 Record = Tuple[str, str, Optional[str]]          # name (header without @ or >), sequence, qualities or None
 
 
@@ -246,10 +247,12 @@ def run(opt, device: int = 0):
                 g[0].append(all_names[-1]); g[1].append(b_); g[2].append(pos)
         kinds, ms, poss = [], [], []
         for (kind, _), (nm, sq, ps) in groups.items():
-            kinds.append(kind)
-            poss.append(np.array(ps, dtype=np.int64))
-            ms.append(_match_batches([E.Round(nm, sq, kind, e, ov, indels, False)], recs, device)[0]
-                      if recs else np.zeros(0, MATCH_DTYPE))
+            for lo in range(0, len(nm), MAX_PER_PASS):          # the kernels take up to 16 adapters per round
+                hi = lo + MAX_PER_PASS
+                kinds.append(kind)
+                poss.append(np.array(ps[lo:hi], dtype=np.int64))
+                ms.append(_match_batches([E.Round(nm[lo:hi], sq[lo:hi], kind, e, ov, indels, False)], recs, device)[0]
+                          if recs else np.zeros(0, MATCH_DTYPE))
         best, bpos = select_best(ms, poss)
         out = list(recs)
         for g, kind in enumerate(kinds):

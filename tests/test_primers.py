@@ -171,5 +171,17 @@ def test_linked_primers_cli_gpu(tmp_path, capsys):
             exp3.append((name, seq[best[0][3]:] if best[1] == oracle.FRONT else seq[:best[0][2]], None))
     assert primers.read_sequences(str(out3))[0] == exp3
     assert sum(1 for a, b in zip(exp3, recs) if a[1] != b[1]) > 300
+    # more adapters than one GPU pass takes: 20 plain 5' adapters, the real one last
+    out4 = tmp_path / "many.fasta"
+    decoys = ["".join(rnd.choice("ACGT") for _ in range(20)) for _ in range(19)]
+    argv = ["-j", "8"] + [x for d in decoys for x in ("-g", d)] + ["-g", plain, "-o", str(out4), str(src)]
+    assert cli.main(argv) == 0
+    fs = oracle.AdapterSet(decoys + [plain], oracle.FRONT, 0.1, 3)
+    exp4 = []
+    for name, seq, _ in recs:
+        m = fs.best_of(seq.upper())
+        exp4.append((name, seq[m[1][3]:] if m else seq, None))
+    assert primers.read_sequences(str(out4))[0] == exp4
     # refused shapes exit 2
     assert cli.main(["--rc", "-g", "%s...%s" % (FWD, REV), "-o", str(out2), str(src)]) == 2
+    assert cli.main(["-g", "^" + FWD, "-o", str(out2), str(src)]) == 2
