@@ -12,7 +12,7 @@ PyTorch is used for pinned host buffers only.  All arithmetic is in liborcdemux.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import numpy as np

@@ -1,12 +1,11 @@
 """Primer-trimming mode of the command line (one output file; 04_cleaning_primers.sh call shapes):
 host logic on the CPU, the whole path on the GPU against the oracle's per-adapter matches."""
-import os
 import random
 
 import numpy as np
 import pytest
 
-import helpers as H
+import helpers  # noqa: F401  (puts the repo and the package on sys.path)
 import oracle
 from orcdemux import cli, primers
 from orcdemux.lib import MATCH_DTYPE
