@@ -122,6 +122,82 @@ def test_select_and_trim():
     assert out[1][1] == "ABC" and out[0][1] == "ABCDEFGHIJKLMNOP"
 
 
+def _oracle_match_batches(rounds, recs, device, batch=1 << 16):
+    """Stand-in for primers._match_batches in the CPU tests: the same per-round match records, from
+    the oracle instead of the GPU (round 2 sees what round 1 left, like the engine)."""
+    outs = [np.zeros(len(recs), dtype=MATCH_DTYPE) for _ in rounds]
+    for o in outs:
+        o["adapter"] = -1
+    for r, (_, seq, _q) in enumerate(recs):
+        rest = seq
+        for k, rd in enumerate(rounds):
+            front = rd.type == 0
+            st = oracle.AdapterSet(rd.sequences, oracle.FRONT if front else oracle.BACK, rd.max_error_rate, rd.min_overlap)
+            m = st.best_of(rest.upper())
+            if m is None:
+                break
+            a, t = m
+            o = outs[k][r]
+            o["adapter"], o["ref_start"], o["ref_stop"], o["query_start"], o["query_stop"], o["score"], o["errors"] = (a,) + t
+            rest = rest[t[3]:] if front else rest[:t[2]]
+    return outs
+
+
+def test_run_routing_on_cpu(tmp_path, monkeypatch):
+    """primers.run end to end with the oracle standing in for the GPU passes: output routing
+    (--untrimmed-output, --discard-untrimmed, everything in one file), groups by adapter type and
+    wildcard class, more than 16 adapters of one kind."""
+    monkeypatch.setattr(primers, "_match_batches", _oracle_match_batches)
+    rnd = random.Random(5)
+    pairs = [("1", FWD, REV), ("2", FWD2, REV2)]
+    recs = _consensus(rnd, 120, pairs)
+    src = tmp_path / "in.fasta"
+    primers.write_sequences(str(src), recs, "fasta")
+    exp = _expected(recs, pairs)
+    base = ["-g", "%s...%s" % (FWD, REV), "-g", "%s...%s" % (FWD2, REV2)]
+    t, u = tmp_path / "t.fasta", tmp_path / "u.fasta"
+    c = primers.run(cli.parse_cutadapt_argv(base + ["--untrimmed-output", str(u), "-o", str(t), str(src)]))
+    assert primers.read_sequences(str(t))[0] == [x for x in exp if x is not None]
+    assert primers.read_sequences(str(u))[0] == [r for r, x in zip(recs, exp) if x is None]
+    assert c["n_in"] == len(recs) and c["n_with"] == c["n_written"] == sum(x is not None for x in exp)
+    assert sum(c["per_adapter"].values()) == c["n_with"]
+    c = primers.run(cli.parse_cutadapt_argv(base + ["--discard-untrimmed", "-o", str(t), str(src)]))
+    assert primers.read_sequences(str(t))[0] == [x for x in exp if x is not None]
+    c = primers.run(cli.parse_cutadapt_argv(base + ["-o", str(t), str(src)]))
+    assert primers.read_sequences(str(t))[0] == [x if x is not None else r for r, x in zip(recs, exp)]
+    assert c["n_written"] == len(recs)
+    # plain adapters of both kinds and wildcard classes, 18 of one kind: best over all in command-line order
+    decoys = ["".join(rnd.choice("ACGT") for _ in range(18)) for _ in range(17)]
+    ads = [(FWD, oracle.FRONT), (REV, oracle.BACK)] + [(d, oracle.FRONT) for d in decoys] + [(FWD2, oracle.FRONT), (REV2, oracle.BACK)]
+    argv = [x for s_, w in ads for x in ("-g" if w == oracle.FRONT else "-a", s_)] + ["-o", str(t), str(src)]
+    primers.run(cli.parse_cutadapt_argv(argv))
+    sets = [oracle.AdapterSet([s_], w, 0.1, 3) for s_, w in ads]
+    exp2 = []
+    for name, seq, _ in recs:
+        best = None
+        for (s_, w), st in zip(ads, sets):
+            m = st.match(0, seq.upper())
+            if m is not None and (best is None or m[4] > best[0][4] or (m[4] == best[0][4] and m[5] < best[0][5])):
+                best = (m, w)
+        exp2.append((name, seq if best is None else (seq[best[0][3]:] if best[1] == oracle.FRONT else seq[:best[0][2]]), None))
+    assert primers.read_sequences(str(t))[0] == exp2
+    # FASTQ in, FASTQ out, qualities trimmed with the bases
+    fq = tmp_path / "in.fastq"
+    primers.write_sequences(str(fq), [(n, s_, "".join(chr(33 + (i % 40)) for i in range(len(s_)))) for n, s_, _ in recs[:20]], "fastq")
+    primers.run(cli.parse_cutadapt_argv(["-g", FWD, "-o", str(tmp_path / "o.fastq"), str(fq)]))
+    got = primers.read_sequences(str(tmp_path / "o.fastq"))[0]
+    src_fq = primers.read_sequences(str(fq))[0]
+    for (n, s_, q), (n0, s0, q0) in zip(got, src_fq):
+        assert n == n0 and len(s_) == len(q) and s0.endswith(s_) and q0.endswith(q)
+    with pytest.raises(primers.Unsupported):
+        primers.run(cli.parse_cutadapt_argv(["--rc", "-g", FWD, "-o", str(t), str(src)]))
+    # empty input: empty outputs, no GPU pass
+    empty = tmp_path / "empty.fasta"
+    empty.write_text("")
+    c = primers.run(cli.parse_cutadapt_argv(base + ["--untrimmed-output", str(u), "-o", str(t), str(empty)]))
+    assert c["n_in"] == 0 and t.read_text() == "" and u.read_text() == ""
+
+
 @pytest.mark.gpu
 def test_linked_primers_cli_gpu(tmp_path, capsys):
     """04_cleaning_primers.sh round 1 and round 2 through the command line on the GPU."""
