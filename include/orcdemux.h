@@ -53,7 +53,8 @@ typedef struct orc_round_params {
     int32_t type;                   /* ORC_FRONT (-g), ORC_BACK (-a); ORC_PREFIX (-g ^) / ORC_SUFFIX (-a ...$)
                                        only with indels == 0 (Hamming fast path, up to 64 adapters) */
     const char *const *names;       /* [n_adapters] header.split()[0]; may be NULL */
-    const char *const *sequences;   /* [n_adapters] NUL-terminated, <= ORC_MAX_ADAPTER_LEN, ACGT */
+    const char *const *sequences;   /* [n_adapters] NUL-terminated, <= ORC_MAX_ADAPTER_LEN; ACGT, or IUPAC codes (cutadapt's
+                                       adapter wildcards) in every adapter of every round */
     double max_error_rate;          /* -e  (values >= 1 are absolute error counts, as in cutadapt) */
     int32_t min_overlap;            /* -O  (cutadapt default 3) */
     int32_t indels;                 /* 1; 0 == --no-indels */
