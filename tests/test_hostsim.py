@@ -331,6 +331,26 @@ def test_iupac_adapter_sets():
         H.run_hostsim([(["ACGTACGT"], oracle.FRONT, 0.1, 3, 1), (["ACGNACGT"], oracle.BACK, 0.1, 3, 1)], one)
 
 
+def test_iupac_degenerate_adapters():
+    """Adapters made of N only (effective length 0: no errors allowed, everything matches), of X only
+    (nothing matches), 64 N, wildcards at either end."""
+    rnd = random.Random(1)
+    recs = []
+    for i in range(300):
+        s = "".join(rnd.choice("ACGTN") for _ in range(rnd.randint(0, 60)))
+        recs.append(("r%d" % i, s, "I" * len(s)))
+    rs = synth.from_records(recs)
+    for f, b in ((["NNNN"], ["NNNNNN"]), (["X"], ["XX"]), (["N" * 24, "ACGN"], ["NACGT", "N" * 64]),
+                 (["XACGT", "ACGTX"], ["NX", "XN"])):
+        for e, ov, rc in ((0.0, 1, 1), (0.1, 3, 0), (0.5, 1, 1)):
+            rounds = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
+            rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=4)
+            for fm in (0, 2):
+                m0, m1, lo, ln, rcv, nt = H.run_hostsim(rounds, rs, fm)
+                assert H.diff_matches(rec0, m0)[1] == 0 and H.diff_matches(rec1, m1)[1] == 0, (f, b, e, ov, rc, fm)
+                assert np.array_equal(olen, ln)
+
+
 def test_unsupported_is_refused():
     rs = synth.from_records([("x", "ACGT", "IIII")])
     with pytest.raises(RuntimeError, match="unsupported"):
