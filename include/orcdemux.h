@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define ORC_MAX_ROUNDS 2
-#define ORC_MAX_ADAPTERS 16      /* unanchored adapters per round (x2 orientations = one warp) */
+#define ORC_MAX_ADAPTERS 32      /* unanchored adapters per round (x2 orientations = 64 lanes) */
 #define ORC_MAX_ANCHORED 64      /* anchored no-indel adapters per round */
 #define ORC_MAX_ADAPTER_LEN 64   /* one 64-bit Myers word */
 

@@ -75,6 +75,7 @@ struct Slot {
     uint64_t *h_bin_counts = nullptr, *h_bin_offsets = nullptr;
     unsigned long long *h_cells = nullptr;
     uint8_t *h_fastq = nullptr;
+    size_t cap_pairs = 0;                    // entries of d_tasks / d_results (see alloc_slot)
     cudaEvent_t ev[EV_COUNT] = {};
 };
 
@@ -98,6 +99,7 @@ struct orc_ctx {
     std::vector<uint64_t> total_counts;
     std::string err;
     int scan_blocks = 0, resolve_blocks = 0, filter_blocks = 0;
+    int na_max = 1;                  // most adapters of an unanchored round (sizes the pair arenas)
     size_t sort_tmp_bytes = 0;
 };
 
@@ -125,7 +127,18 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
 {
     const size_t R = ctx->max_reads, B = (size_t)ctx->max_bytes;
     const size_t n_chunks = (R + BIN_CHUNK - 1) / BIN_CHUNK;
-    const size_t n_tasks = R * MAX_LANES;
+    // Pair arenas (Task / PairResult, 32 bytes each): the worst case is every (read, direction, adapter) pair
+    // holding a candidate, 2 * na per read; real data has about 1.4 per read and round.  Slots start with
+    // room for 4 per read (and never less than 65536, so small batches of adversarial reads fit outright);
+    // a batch that needs more is caught by its counters in orc_wait(), which grows the arenas to the worst
+    // case and runs the batch again (grow_pair_arenas).
+    const size_t worst = std::max<size_t>(R * 2 * (size_t)ctx->na_max, 2 * R);
+    size_t n_tasks = std::min(worst, std::max<size_t>(4 * R, 65536));
+    if (const char *e = getenv("ORC_PAIR_CAP")) {       // tests: force the overflow path
+        const size_t floor_ = (ctx->anchored[0] || ctx->anchored[1]) ? 2 * R : 1;
+        n_tasks = std::min(worst, std::max<size_t>((size_t)atoll(e), floor_));
+    }
+    s.cap_pairs = n_tasks;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_COUNT; i++) CK(cudaEventCreate(&s.ev[i]));
     CK(dalloc(&s.d_seq, B + 64));
@@ -145,7 +158,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_wins, 2 * R));
     CK(dalloc(&s.d_seedwins, 2 * R));
     CK(dalloc(&s.d_tasks, n_tasks));
-    CK(dalloc(&s.d_jobs, 2 * R * MAX_AD));
+    CK(dalloc(&s.d_jobs, 2 * R * (size_t)ctx->na_max));
     CK(dalloc(&s.d_results, n_tasks));
     CK(dalloc(&s.d_counters, 16));
     CK(dalloc(&s.d_cells, 6));
@@ -241,6 +254,8 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
             build_seed_table(ctx->h_tab[r], ctx->h_seed[r], !(off && off[0] == '1'));
         }
     }
+    for (int r = 0; r < p->n_rounds; r++)
+        if (!ctx->anchored[r] && ctx->h_tab[r].n_adapters > ctx->na_max) ctx->na_max = ctx->h_tab[r].n_adapters;
     ctx->n_bins = ctx->h_tab[0].n_adapters + 1;
     if (p->n_rounds == 2) ctx->n_bins *= ctx->h_tab[1].n_adapters + 1;
     if (ctx->n_bins > MAX_BINS) { ctx->err = "unsupported: more than 512 bins"; return ORC_EINVAL; }
@@ -377,6 +392,21 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
         }
         bases += b->lengths[r];
     }
+    if (s.has_names && b->n_reads) {
+        // the header lines: inside the text (raw FASTQ layout) or inside the names blob, never past it
+        const uint64_t bound = names_alias ? b->n_bytes : name_bytes;
+        for (uint32_t r = 0; r < b->n_reads; r++) {
+            uint64_t len;
+            if (b->name_lengths) len = b->name_lengths[r];
+            else {
+                if (b->name_offsets[r + 1] < b->name_offsets[r]) { ctx->err = "name_offsets must not decrease"; return ORC_EINVAL; }
+                len = b->name_offsets[r + 1] - b->name_offsets[r];
+            }
+            if (b->name_offsets[r] > bound || len > bound - b->name_offsets[r]) {
+                ctx->err = "read name extends past the names blob"; return ORC_EINVAL;
+            }
+        }
+    }
     s.in_bases = bases;
     s.len_bits = 1;
     while (s.len_bits < 32 && (((uint64_t)max_len + 2) >> s.len_bits) != 0) s.len_bits++;
@@ -489,13 +519,13 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
                     s.d_cells + 4 + r);
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_results,
-                s.d_tasks, s.d_best_key, cnt, prefilter ? s.d_jobs : nullptr);
+                s.d_tasks, s.d_best_key, cnt, prefilter ? s.d_jobs : nullptr, (uint32_t)s.cap_pairs);
         }
         if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         if (n) {
             if (!ctx->anchored[r])
                 resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2,
-                                                                   s.d_results, s.d_best_key);
+                                                                   s.d_results, s.d_best_key, (uint32_t)s.cap_pairs);
             SelectArgs A;
             A.tab = ctx->d_tab[r];
             A.views_in = s.d_views[r];
@@ -575,6 +605,25 @@ extern "C" int orc_download(orc_ctx *ctx, int slot)
     return ORC_OK;
 }
 
+// More candidate pairs than the slot's arenas hold (counters [8r + 1] count every pair, stored or not):
+// the results of such a launch are incomplete.  Grow the arenas to the worst case; the caller runs the
+// batch again (it is still resident).  Returns 1 if it grew them, 0 if nothing overflowed.
+static int grow_pair_arenas(orc_ctx *ctx, Slot &s, const uint32_t *counters)
+{
+    bool over = false;
+    for (int r = 0; r < ctx->n_rounds; r++) over = over || counters[8 * r + 1] > s.cap_pairs;
+    if (!over) return 0;
+    const size_t R = ctx->max_reads;
+    const size_t worst = std::max<size_t>(R * 2 * (size_t)ctx->na_max, 2 * R);
+    CK(cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_tasks); cudaFree(s.d_results);
+    s.d_tasks = nullptr; s.d_results = nullptr;
+    CK(dalloc(&s.d_tasks, worst));
+    CK(dalloc(&s.d_results, worst));
+    s.cap_pairs = worst;
+    return 1;
+}
+
 extern "C" int orc_submit(orc_ctx *ctx, int slot, const orc_batch *batch)
 {
     int rc = orc_upload(ctx, slot, batch);
@@ -602,6 +651,17 @@ extern "C" int orc_wait(orc_ctx *ctx, int slot, orc_result *out)
     CK(cudaSetDevice(ctx->device));
     // the FASTQ size is only known once the header has landed
     CK(cudaEventSynchronize(s.ev[EV_HDR]));
+    {
+        const int grew = grow_pair_arenas(ctx, s, s.h_counters);
+        if (grew < 0) return grew;
+        if (grew) {                 // rare: run the resident batch again with worst-case arenas
+            s.state = SLOT_UPLOADED;
+            int rc = orc_launch(ctx, slot);
+            if (rc == ORC_OK) rc = orc_download(ctx, slot);
+            if (rc != ORC_OK) return rc;
+            CK(cudaEventSynchronize(s.ev[EV_HDR]));
+        }
+    }
     const uint64_t fq = s.has_names ? s.h_bin_offsets[ctx->n_bins] : 0;
     if (fq > ctx->fastq_cap) { ctx->err = "internal: FASTQ output exceeds its arena"; return ORC_ECAPACITY; }
     if (fq) CK(cudaMemcpyAsync(s.h_fastq, s.d_fastq, fq, cudaMemcpyDeviceToHost, s.stream));
@@ -653,6 +713,13 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     unsigned long long cells[6];
     CK(cudaMemcpy(counters, s.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cells, s.d_cells, sizeof(cells), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < ctx->n_rounds; r++)
+        if (counters[8 * r + 1] > s.cap_pairs) {
+            // a launch-only caller (device-resident timing) never passes orc_wait(), which would have grown
+            // the arenas and run the batch again
+            ctx->err = "candidate-pair arena overflow in the last launch: call orc_download()/orc_wait() once";
+            return ORC_ECAPACITY;
+        }
     uint64_t emit_bytes = 0;
     CK(cudaMemcpy(&emit_bytes, s.d_bin_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 4u + (s.has_names ? 1u : 0u)) : 2u;
@@ -733,8 +800,10 @@ extern "C" int64_t orc_fastq_index(const uint8_t *text, uint64_t n_bytes, uint32
             got++;
         }
         if (got < 4) {
-            if (final && got > 0) {
-                // tolerate a trailing blank line, reject a truncated record
+            if (final) {
+                // no more text follows: tolerate trailing blank lines, reject anything else -- a record cut off
+                // anywhere, also in the middle of its header line (got == 0), is a truncated input, as it is
+                // for dnaio ("Premature end of file")
                 bool blank = true;
                 for (uint64_t i = pos; i < n_bytes; i++) if (text[i] != '\n' && text[i] != '\r') blank = false;
                 if (!blank) return fail("truncated record at end of input", (uint64_t)n);

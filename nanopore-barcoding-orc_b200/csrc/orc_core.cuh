@@ -41,9 +41,9 @@
 
 namespace orc {
 
-constexpr int MAX_AD = 16;          // adapters per round
+constexpr int MAX_AD = 32;          // adapters per round
 constexpr int MAX_M = 64;           // adapter length (one 64-bit word)
-constexpr int MAX_LANES = 32;       // 2 orientations x MAX_AD
+constexpr int MAX_LANES = 64;       // 2 orientations x MAX_AD
 constexpr int INF_COST = 1 << 20;
 constexpr int TYPE_FRONT = 0, TYPE_BACK = 1;
 
@@ -74,8 +74,9 @@ struct RoundTable {
     // comp(adapter[m-1-q]) (zero nibbles behind) -- what a direction-1 lane compares raw codes with
     uint32_t code4[MAX_AD][12];
     uint32_t rcode4[MAX_AD][12];
-    uint64_t peq[16][MAX_LANES];    // [read code][lane]: match bits, row i at bit 64-m+i-1,
-                                    // the 64-m low padding bits always 1
+    uint64_t peq[MAX_LANES / 32][16][32];   // [lane / 32][read code][lane % 32]: match bits, row i at bit 64-m+i-1,
+                                    // the 64-m low padding bits always 1.  Banks of 32 lanes: one PRMT builds
+                                    // the byte offset code*256 + (lane%32)*8 inside a bank
     uint64_t pv0[MAX_LANES];        // vertical deltas of column 0 (R2)
     int32_t d0[MAX_LANES];          // D[m][0]
     // shared-prefix trigger filter (stage 1 of the scan)
@@ -110,6 +111,12 @@ struct RoundTable {
 
 // A read (or what a previous round left of it) as a window of the packed code array:
 // element p of the view is code[lo+p], or, if rc is set, comp(code[lo+len-1-p]).
+// the 64-bit match table of a lane's bank (scan_window / resolve_columns add code*256 + (lane%32)*8)
+ORC_HD const char *peq_bank(const RoundTable &T, int lane)
+{
+    return reinterpret_cast<const char *>(&T.peq[lane >> 5][0][0]);
+}
+
 struct View {
     uint64_t lo;        // absolute index into the flat code / seq / qual arrays
     uint32_t len;
@@ -419,7 +426,7 @@ struct SeedTable {
     int32_t kt, m_max, pad_[2];
     uint32_t key[SEED_SLOTS];       // SEED_EMPTY: free slot
     uint32_t val[SEED_SLOTS];       // first list entry | count << 16
-    uint32_t list[SEED_LIST_MAX];   // adapter mask (16 bits) | piece << 16 | direction << 20
+    uint32_t list[SEED_LIST_MAX];   // piece << 16 | direction << 20
 };
 
 struct SeedWins {                   // the seed windows of one (read, direction), increasing, disjoint
@@ -983,7 +990,7 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
     int D;
     if (s == 0) { Pv = pv0; D = d0; }            // R2: the true column 0
     else { Pv = ~pad; D = m; }                   // restart: cost i
-    const uint32_t lane8 = (uint32_t)lane * 8u;
+    const uint32_t lane8 = (uint32_t)(lane & 31) * 8u;           // peq_base is the lane's bank (peq_bank())
     // PRMT selectors: result byte0 <- lane8.byte0, byte1 <- code byte b, bytes 2,3 <- 0
     uint32_t sel0, sel1, sel2, sel3;
     if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
@@ -1369,8 +1376,8 @@ ORC_HD void resolve_columns(const uint32_t *W, uint64_t lo, uint32_t len, Resolv
     const int ubw = C.ubw;
     const bool narrow = C.narrow != 0;
     // eight columns per packed word, table address by PRMT, as in scan_window
-    const char *peq_base = reinterpret_cast<const char *>(C.peq_lane - C.lane);
-    const uint32_t lane8 = (uint32_t)C.lane * 8u;
+    const char *peq_base = reinterpret_cast<const char *>(C.peq_lane - (C.lane & 31));
+    const uint32_t lane8 = (uint32_t)(C.lane & 31) * 8u;
     uint32_t sel0, sel1, sel2, sel3;
     if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
     else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
@@ -1509,7 +1516,7 @@ ORC_HD void resolve_begin(const uint32_t *W, const View &v, const RoundTable &T,
     C.dir = (int)t.lane / T.n_adapters;
     C.m = T.m[a]; C.k = T.k[a]; C.min_ov = T.min_ov[a];
     C.kmax = T.kmax[a];
-    C.peq_lane = &T.peq[0][t.lane];
+    C.peq_lane = &T.peq[t.lane >> 5][0][t.lane & 31];
     C.lane = (int)t.lane;
     C.code4 = T.code4[a]; C.rcode4 = T.rcode4[a];
     C.n = (int)v.len;

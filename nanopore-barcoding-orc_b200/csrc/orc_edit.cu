@@ -115,9 +115,13 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
     ECK(cudaMemcpy(d_pa.p, pair_a, 4ull * n_pairs, cudaMemcpyHostToDevice));
     ECK(cudaMemcpy(d_pb.p, pair_b, 4ull * n_pairs, cudaMemcpyHostToDevice));
     ECK(cudaMemcpy(d_todo.p, order.data(), 4ull * n_pairs, cudaMemcpyHostToDevice));
-    cudaEvent_t e0, e1;
-    ECK(cudaEventCreate(&e0));
-    ECK(cudaEventCreate(&e1));
+    struct Ev {                      // destroyed on every return path, like DevBuf
+        cudaEvent_t e = nullptr;
+        ~Ev() { if (e) cudaEventDestroy(e); }
+    } ev0, ev1;
+    ECK(cudaEventCreate(&ev0.e));
+    ECK(cudaEventCreate(&ev1.e));
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     ECK(cudaEventRecord(e0, 0));
     for (int cls = 0; cls < N_CLS; cls++) {
         const uint32_t nt = (uint32_t)(cls_begin[cls + 1] - cls_begin[cls]);
@@ -152,8 +156,6 @@ extern "C" int orc_edit_distances(int device, const uint8_t *seqs, const uint64_
     float ms = 0.0f;
     ECK(cudaEventElapsedTime(&ms, e0, e1));
     if (kernel_ms) *kernel_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     ECK(cudaMemcpy(dist, d_out.p, 4ull * n_pairs, cudaMemcpyDeviceToHost));
     return ORC_OK;
 }

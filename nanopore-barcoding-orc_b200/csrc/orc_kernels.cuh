@@ -282,7 +282,7 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
             const uint32_t *__restrict__ wcols_sorted, const uint32_t *__restrict__ item_order,
             uint32_t n_items, PairResult *__restrict__ results, Task *__restrict__ work,
             unsigned long long *__restrict__ best_key, uint32_t *__restrict__ counters,
-            const uint32_t *__restrict__ jobs)
+            const uint32_t *__restrict__ jobs, uint32_t cap_pairs)
 {
     __shared__ __align__(16) RoundTable T;
     {
@@ -295,7 +295,6 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
     const uint32_t na = (uint32_t)T.n_adapters;
     // with a job list (stage 2a ran) the jobs are its entries, else every pair of every item
     const uint32_t n_jobs = jobs ? counters[5] : n_items * na;
-    const char *peq_base = reinterpret_cast<const char *>(&T.peq[0][0]);
     const int type = T.type;
     uint32_t *job_counter = counters + 0, *res_count = counters + 1, *work_count = counters + 2;
 
@@ -335,7 +334,7 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                 uint4 *dst = reinterpret_cast<uint4 *>(&wl);
                 dst[0] = src[0]; dst[1] = src[1];
             }
-            scan_lane(W, v.lo, v.len, dir, &wl, peq_base, tl, T.pv0[tl], T.d0[tl], m, T.k[a], T.kmax[a],
+            scan_lane(W, v.lo, v.len, dir, &wl, peq_bank(T, tl), tl, T.pv0[tl], T.d0[tl], m, T.k[a], T.kmax[a],
                       T.min_ov[a], type, L, T.indels, T.code4[a], T.rcode4[a], T.chunk_lut);
             has = L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2;
             need = has && L.need != 0;
@@ -352,13 +351,20 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                 if (lane == 0) wb = atomicAdd(work_count, (uint32_t)__popc(mn));
                 wb = __shfl_sync(0xffffffffu, wb, 0);
             }
+            // A pair beyond the arenas is dropped: the final res_count (>= work_count) says so to the host,
+            // which then runs the batch again with worst-case arenas (orc_api.cu grow_pair_arenas).  The
+            // work position and the result slot come from two counters that other warps interleave, so each
+            // is checked on its own; a task whose result has no slot is marked so that the resolver skips it.
+            const uint32_t wpos = wb + (uint32_t)__popc(mn & lanemask_lt());
             if (need) {
-                Task t;
-                t.read = r; t.lane = (uint32_t)(a + (int)na * (int)(item & 1u));
-                t.jf = L.h.jf; t.jl = L.h.jl; t.i1 = L.h.i1; t.i2 = L.h.i2;
-                t.slot = slot; t.pad_ = 0;
-                work[wb + (uint32_t)__popc(mn & lanemask_lt())] = t;
-            } else if (has) {
+                if (wpos < cap_pairs) {
+                    Task t;
+                    t.read = r; t.lane = (uint32_t)(a + (int)na * (int)(item & 1u));
+                    t.jf = L.h.jf; t.jl = L.h.jl; t.i1 = L.h.i1; t.i2 = L.h.i2;
+                    t.slot = slot < cap_pairs ? slot : 0xFFFFFFFFu; t.pad_ = 0;
+                    work[wpos] = t;
+                }
+            } else if (has && slot < cap_pairs) {
                 PairResult res;
                 best_to_result(L.best, m, (int)n, res);
                 results[slot] = res;
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(128)
 resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                const View *__restrict__ views, const Task *__restrict__ work,
                const uint32_t *__restrict__ work_count, PairResult *__restrict__ results,
-               unsigned long long *__restrict__ best_key)
+               unsigned long long *__restrict__ best_key, uint32_t cap_pairs)
 {
     // Only the head of the table (everything up to and including peq) is used here; the rest
     // stays out of shared memory so that L1 keeps more room for the local-memory column rings.
@@ -387,7 +393,7 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     }
     __syncthreads();
     const RoundTable &T = *reinterpret_cast<const RoundTable *>(s_tab);
-    const uint32_t n = *work_count;
+    const uint32_t n = min(*work_count, cap_pairs);
     ColRing ring;
     // every lane of a warp makes the same number of trips, so the warp can be brought back together
     // between the column scan (lanes differ in length) and the walks (which then start together)
@@ -395,12 +401,15 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
     for (uint32_t base = first; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t t = base + lane;
-        const bool act = t < n;
+        bool act = t < n;
         Task task;
         View v;
         ResolveCtx C;
         if (act) {
             task = work[t];
+            act = task.slot != 0xFFFFFFFFu;          // its result had no slot (arena overflow): skipped
+        }
+        if (act) {
             v = views[task.read];
             resolve_begin(W, v, T, task, C, ring);
         }

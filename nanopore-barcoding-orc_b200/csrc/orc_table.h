@@ -120,7 +120,7 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
             uint64_t bits = pad;
             for (int i = 0; i < m; i++)
                 if (T.code[a][i] & cc) bits |= 1ull << (64 - m + i);
-            T.peq[c][lane] = bits;
+            T.peq[lane >> 5][c][lane & 31] = bits;
         }
         // R2: FRONT column 0 costs are all 0; BACK column 0 cost is i
         T.pv0[lane] = (type == TYPE_FRONT) ? 0ull : ~pad;
@@ -260,10 +260,11 @@ inline void build_seed_table(const RoundTable &T, SeedTable &S, bool enable)
                     key |= c << (4 * u);
                 }
                 const uint32_t info = ((uint32_t)t << 16) | ((uint32_t)d << 20);
+                // which adapters own a piece is never looked at (a superfluous window only costs time):
+                // one entry per distinct (key, piece, direction)
                 int f = -1;
-                for (int i = 0; i < n_ent; i++) if (ents[i].key == key && (ents[i].info & 0x1F0000u) == info) f = i;
-                if (f >= 0) ents[f].info |= 1u << a;
-                else { ents[n_ent].key = key; ents[n_ent].info = info | (1u << a); n_ent++; }
+                for (int i = 0; i < n_ent; i++) if (ents[i].key == key && ents[i].info == info) f = i;
+                if (f < 0) { ents[n_ent].key = key; ents[n_ent].info = info; n_ent++; }
             }
     // group the entries by key
     uint32_t keys[2 * MAX_AD * (MAX_M / 8)];

@@ -62,12 +62,9 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
     import torch
     dt = np.dtype(dtype)
     t = torch.empty(max(int(n), 1) * dt.itemsize, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
-    arr = t.numpy().view(dt)[:n]
-    _KEEP[id(arr)] = t
-    return arr
-
-
-_KEEP = {}
+    # the ndarray's base chain ends in the tensor, so the page-locked block lives exactly as long as
+    # the array (or any view of it) does
+    return t.numpy().view(dt)[:n]
 
 
 def pin_readset(rs):

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "liborcdemux.so")
 
 ORC_MAX_ROUNDS = 2
-ORC_MAX_ADAPTERS = 16
+ORC_MAX_ADAPTERS = 32
 ORC_MAX_ADAPTER_LEN = 64
 ORC_FRONT, ORC_BACK, ORC_PREFIX, ORC_SUFFIX = 0, 1, 2, 3
 ORC_OK, ORC_EINVAL, ORC_ECUDA, ORC_ECAPACITY, ORC_ESTATE = 0, -1, -2, -3, -4

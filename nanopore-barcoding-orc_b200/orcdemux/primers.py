@@ -33,7 +33,7 @@ from . import engine as E
 from . import synth
 from .lib import MATCH_DTYPE, ORC_BACK, ORC_FRONT
 
-MAX_PER_PASS = 16                                # adapters per GPU pass (csrc/orc_core.cuh MAX_AD)
+MAX_PER_PASS = 32                                # adapters per GPU pass (csrc/orc_core.cuh MAX_AD)
 Record = Tuple[str, str, Optional[str]]          # name (header without @ or >), sequence, qualities or None
 
 

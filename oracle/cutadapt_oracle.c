@@ -84,6 +84,22 @@ static void init_tables(void)
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
+/* Per-thread scratch buffers that only ever grow: Aligner.locate, the reverse-complementer and the batch
+ * driver each need a few read-sized arrays per call, and one malloc/free pair per call showed up in the
+ * CPU baseline.  Slot s of the calling thread, at least n bytes. */
+enum { SCR_LOCATE = 0, SCR_UP, SCR_RC, SCR_TMP_S, SCR_TMP_Q, SCR_SLOTS };
+static __thread unsigned char *scr_buf[SCR_SLOTS];
+static __thread size_t scr_cap[SCR_SLOTS];
+static unsigned char *scratch(int slot, size_t n)
+{
+    if (scr_cap[slot] < n) {
+        free(scr_buf[slot]);
+        scr_cap[slot] = n + n / 2 + 64;
+        scr_buf[slot] = (unsigned char *)malloc(scr_cap[slot]);
+    }
+    return scr_buf[slot];
+}
+
 /*
  * Aligner.locate (cutadapt 4.9 _align.pyx).  ref/query are the raw (upper-cased)
  * strings; translation by the IUPAC/ACGT tables happens here like in _set_reference /
@@ -99,7 +115,7 @@ static int locate_core(const char *ref_in, int m, const char *query_in, int n,
     unsigned char s1[ORA_MAX_ADAPTER + 1];
     int n_counts[ORA_MAX_ADAPTER + 2];
     entry_t column[ORA_MAX_ADAPTER + 2];
-    unsigned char *s2 = (unsigned char *)malloc((size_t)n + 1);
+    unsigned char *s2 = scratch(SCR_LOCATE, (size_t)n + 1);
     int start_in_reference = flags & REF_START;
     int start_in_query = flags & QUERY_START;
     int stop_in_reference = flags & REF_END;
@@ -248,7 +264,6 @@ static int locate_core(const char *ref_in, int m, const char *query_in, int n,
             }
         }
     }
-    free(s2);
     if (best.cost == m + n + 1) return 0;
     int start1, start2;
     if (best.origin >= 0) { start1 = 0; start2 = best.origin; }
@@ -484,8 +499,8 @@ void oracle_round_read(const ora_adapter *adapters, int n_adapters, int revcomp,
                        char *out_seq, char *out_qual, int *out_n, ora_match *rec)
 {
     init_tables();
-    char *up = (char *)malloc((size_t)n + 1);
-    char *rc = (char *)malloc((size_t)n + 1);
+    char *up = (char *)scratch(SCR_UP, (size_t)n + 1);
+    char *rc = (char *)scratch(SCR_RC, (size_t)n + 1);
     int fwd[6], rev[6];
     upper_copy(up, seq, n);
     int fa = oracle_best_of(adapters, n_adapters, up, n, fwd);
@@ -533,7 +548,6 @@ void oracle_round_read(const ora_adapter *adapters, int n_adapters, int revcomp,
         }
         *out_n = L;
     }
-    free(up); free(rc);
 }
 
 /* ------------------------------------------------------------------------------------
@@ -561,7 +575,7 @@ static void *batch_worker(void *arg)
     for (uint32_t r = J->lo; r < J->hi; r++) {
         uint64_t off = J->offsets[r];
         int n = (int)J->lengths[r];
-        char *tmp_s = (char *)malloc((size_t)n + 1), *tmp_q = (char *)malloc((size_t)n + 1);
+        char *tmp_s = (char *)scratch(SCR_TMP_S, (size_t)n + 1), *tmp_q = (char *)scratch(SCR_TMP_Q, (size_t)n + 1);
         int n1 = 0;
         oracle_round_read(J->adapters[0], J->n_adapters[0], J->revcomp[0], J->seq + off, J->qual + off, n,
                           tmp_s, tmp_q, &n1, &J->rec[0][r]);
@@ -583,8 +597,8 @@ static void *batch_worker(void *arg)
             memcpy(J->out_qual + off, tmp_q, (size_t)n1);
             J->out_len[r] = (uint32_t)n1;
         }
-        free(tmp_s); free(tmp_q);
     }
+    for (int i = 0; i < SCR_SLOTS; i++) { free(scr_buf[i]); scr_buf[i] = NULL; scr_cap[i] = 0; }   /* the thread ends here */
     return NULL;
 }
 

@@ -124,7 +124,7 @@ extern "C" int hostsim_demux(int n_rounds,
                                             R.kmax[a], R.min_ov[a], R.first_mask)) continue;
                 g_kept[rd]++;
                 LaneScan L;
-                scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, (const char *)&R.peq[0][0], lane,
+                scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, peq_bank(R, lane), lane,
                           R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, L,
                           R.indels, R.code4[a], R.rcode4[a], R.chunk_lut);
                 if (L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2) {

@@ -357,3 +357,32 @@ def test_unsupported_is_refused():
         H.run_hostsim([(["ACGZ"], oracle.FRONT, 0.1, 3, 1)], rs)
     with pytest.raises(RuntimeError, match="unsupported"):
         H.run_hostsim([(["A" * 65], oracle.FRONT, 0.1, 3, 1)], rs)
+
+
+def test_up_to_32_adapters_and_config4_unanchored_arm():
+    """More than 16 adapters per round (two banks of 32 lanes in the 64-bit match table), and BASELINE
+    configs[3]'s second arm: `-g file:M13_variable_indices_all.fa` unanchored WITH indels (24 x 17-mers,
+    k = 1, no shared flank -> no stage-1 filter) on the reads of the anchored arm."""
+    rnd = random.Random(3232)
+    var = [s for _, s in m13.variable_all()]
+    assert len(var) == 24
+    rs = synth.generate(3000, 300, 600, seed=1004, anchored=True)
+    for rc in (1, 0):
+        rec0, _ = _compare([(var, oracle.FRONT, 0.1, 3, rc)], rs)
+        assert (rec0["adapter"] >= 16).sum() > 100 and (rec0["adapter"] >= 0).mean() > 0.5
+    _compare([(var, oracle.BACK, 0.1, 3, 1)], _adversarial_reads(rnd, var, var, 1500))
+    for trial in range(6):
+        nf, nb = rnd.randint(17, 32), rnd.randint(17, 32)
+        mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([8, 17, 20, 33, 57, 64])))
+        shared = mk()[:rnd.choice([4, 14, 25])]
+        f = [((shared if rnd.random() < 0.8 else "") + mk())[:64] for _ in range(nf)]
+        b = [((shared if rnd.random() < 0.8 else "") + mk())[:64] for _ in range(nb)]
+        e = rnd.choice([0.0, 0.1, 0.1, 0.2])
+        rounds = [(f, oracle.FRONT, e, 3, 1), (b, oracle.BACK, e, 3, 1)]
+        if trial % 2:
+            rounds = rounds[::-1]
+        rec0, rec1 = _compare(rounds, _adversarial_reads(rnd, f, b, 400), threads=4)
+        assert (rec0["adapter"] >= 16).sum() > 0
+    one = synth.from_records([("x", "ACGT", "IIII")])
+    with pytest.raises(RuntimeError, match="unsupported"):
+        H.run_hostsim([(["ACGTACGT"] * 33, oracle.FRONT, 0.1, 3, 1)], one)

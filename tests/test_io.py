@@ -113,3 +113,27 @@ def test_writer_order_members_and_empty_bins(tmp_path, reads):
 def test_writer_errors(tmp_path):
     with pytest.raises(OSError, match="cannot create"):
         F.BinWriters([str(tmp_path / "no" / "such" / "dir.fastq.gz")], 5, 2)
+
+
+def test_truncated_header_is_an_error():
+    """text cut off in the middle of a header line ("...IIII\\n@b", no newline) used to index one
+    read and report success; dnaio raises on such input."""
+    import ctypes as C
+    from orcdemux import lib as LIB
+    L = LIB.load()
+    for tail, ok in ((b"", True), (b"\n\n", True), (b"@b", False), (b"@b\nAC", False), (b"@b\nAC\n+\n", False)):
+        text = np.frombuffer(b"@a\nACGT\n+\nIIII\n" + tail, dtype=np.uint8).copy()
+        so, qo, no = (np.zeros(4, np.uint64) for _ in range(3))
+        ln, nl = np.zeros(4, np.uint32), np.zeros(4, np.uint32)
+        used = C.c_uint64(0)
+        err = C.create_string_buffer(256)
+        n = L.orc_fastq_index(text.ctypes.data, text.shape[0], 4, 1, so.ctypes.data, ln.ctypes.data, qo.ctypes.data,
+                              no.ctypes.data, nl.ctypes.data, C.byref(used), err, 256)
+        if ok:
+            assert n == 1 and used.value == text.shape[0], (tail, n, err.value)
+        else:
+            assert n == LIB.ORC_EINVAL and (b"truncated" in err.value or b"differ in length" in err.value), (tail, n, err.value)
+        # not final: the partial record is simply left for the next call
+        n = L.orc_fastq_index(text.ctypes.data, text.shape[0], 4, 0, so.ctypes.data, ln.ctypes.data, qo.ctypes.data,
+                              no.ctypes.data, nl.ctypes.data, C.byref(used), err, 256)
+        assert n == 1 and used.value == 15
