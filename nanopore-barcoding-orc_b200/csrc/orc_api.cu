@@ -16,7 +16,6 @@
 #include <vector>
 
 #include "../../include/orcdemux.h"
-#include <cub/device/device_radix_sort.cuh>
 
 #include "orc_kernels.cuh"
 #include "orc_table.h"
@@ -33,6 +32,14 @@ static_assert(ORC_MAX_ADAPTERS == MAX_AD, "adapter limit");
 namespace {
 
 enum { EV_START = 0, EV_H2D, EV_PACK, EV_TRIG0, EV_SCAN0, EV_RES0, EV_TRIG1, EV_SCAN1, EV_RES1, EV_BIN, EV_EMIT, EV_HDR, EV_END, EV_T0, EV_T1, EV_COUNT };
+// d_counters: 16 per-round counters, then for round r and ordering o (0: reads by length, 1: items by
+// window columns) a histogram and a cursor array of SORT_BUCKETS words each
+constexpr size_t N_COUNTERS = 16 + 2 * 2 * 2 * (size_t)SORT_BUCKETS;
+static inline uint32_t *sort_hist(uint32_t *counters, int round, int ordering, int cursor)
+{
+    return counters + 16 + (size_t)(((round * 2 + ordering) * 2 + cursor)) * SORT_BUCKETS;
+}
+
 enum { SLOT_IDLE = 0, SLOT_UPLOADED, SLOT_LAUNCHED, SLOT_DOWNLOADING };
 
 struct Slot {
@@ -40,7 +47,6 @@ struct Slot {
     int state = SLOT_IDLE;
     uint32_t n_reads = 0;
     uint64_t n_bytes = 0, name_bytes = 0, in_bases = 0;
-    int len_bits = 32;                       // bits needed for the longest read of the batch (+1)
     bool has_names = false;
     bool did_h2d = false, did_kernels = false, did_d2h = false, fresh_upload = false;
     // device
@@ -53,16 +59,16 @@ struct Slot {
     uint32_t *d_lengths = nullptr;
     View *d_views[3] = {nullptr, nullptr, nullptr};
     Match *d_match[2] = {nullptr, nullptr};
-    uint32_t *d_wcols = nullptr, *d_wcols_sorted = nullptr, *d_item_in = nullptr, *d_item_order = nullptr;
+    uint32_t *d_wcols = nullptr, *d_wcols_sorted = nullptr, *d_item_order = nullptr;
     unsigned long long *d_best_key = nullptr;
-    uint32_t *d_key_in = nullptr, *d_key_out = nullptr, *d_val_in = nullptr, *d_order = nullptr;
-    void *d_sort_tmp = nullptr;
+    uint32_t *d_order = nullptr;             // reads in order of decreasing view length (stage 1)
     WinList *d_wins = nullptr;
     SeedWins *d_seedwins = nullptr;  // stage 1s: seed windows per (read, direction)
     Task *d_tasks = nullptr;
     uint32_t *d_jobs = nullptr;              // stage 2a survivors: job numbers (item * n_adapters + adapter)
     PairResult *d_results = nullptr;
-    uint32_t *d_counters = nullptr;          // [0..1] work counters, [2..3] task counts
+    uint32_t *d_counters = nullptr;          // [0..15] per-round counters, then the size-class histograms and cursors
+                                             // of the two orderings of each round (N_COUNTERS words, zeroed per launch)
     unsigned long long *d_cells = nullptr;   // [0..1] sum of view lengths entering each round, [2..3] window columns,
                                              // [4..5] cells stage 2b updated (rows x columns of the pairs that passed 2a)
     int32_t *d_bin = nullptr;
@@ -75,6 +81,7 @@ struct Slot {
     uint64_t *h_bin_counts = nullptr, *h_bin_offsets = nullptr;
     unsigned long long *h_cells = nullptr;
     uint8_t *h_fastq = nullptr;
+    uint32_t n_launches = 0;                 // own kernels of the last orc_launch()
     size_t cap_pairs = 0;                    // entries of d_tasks / d_results (see alloc_slot)
     cudaEvent_t ev[EV_COUNT] = {};
 };
@@ -98,9 +105,8 @@ struct orc_ctx {
     std::vector<Slot> slots;
     std::vector<uint64_t> total_counts;
     std::string err;
-    int scan_blocks = 0, resolve_blocks = 0, filter_blocks = 0;
+    int scan_blocks = 0, resolve_blocks = 0, filter_blocks = 0, band_blocks[2] = {0, 0};
     int na_max = 1;                  // most adapters of an unanchored round (sizes the pair arenas)
-    size_t sort_tmp_bytes = 0;
 };
 
 #define CK(call)                                                                          \
@@ -151,16 +157,15 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     for (int i = 0; i < 3; i++) CK(dalloc(&s.d_views[i], R));
     for (int i = 0; i < 2; i++) CK(dalloc(&s.d_match[i], R));
     CK(dalloc(&s.d_wcols, 2 * R)); CK(dalloc(&s.d_wcols_sorted, 2 * R));
-    CK(dalloc(&s.d_item_in, 2 * R)); CK(dalloc(&s.d_item_order, 2 * R));
+    CK(dalloc(&s.d_item_order, 2 * R));
     CK(dalloc(&s.d_best_key, 2 * R));
-    CK(dalloc(&s.d_key_in, R)); CK(dalloc(&s.d_key_out, R)); CK(dalloc(&s.d_val_in, R)); CK(dalloc(&s.d_order, R));
-    CK(cudaMalloc(&s.d_sort_tmp, ctx->sort_tmp_bytes + 64));
+    CK(dalloc(&s.d_order, R));
     CK(dalloc(&s.d_wins, 2 * R));
     CK(dalloc(&s.d_seedwins, 2 * R));
-    CK(dalloc(&s.d_tasks, n_tasks));
+    CK(dalloc(&s.d_tasks, 2 * n_tasks));           // front half: band resolver, back half: wide resolver
     CK(dalloc(&s.d_jobs, 2 * R * (size_t)ctx->na_max));
     CK(dalloc(&s.d_results, n_tasks));
-    CK(dalloc(&s.d_counters, 16));
+    CK(dalloc(&s.d_counters, N_COUNTERS));
     CK(dalloc(&s.d_cells, 6));
     CK(dalloc(&s.d_bin, R));
     CK(dalloc(&s.d_out_len, R));
@@ -196,10 +201,10 @@ static void free_slot(Slot &s)
     cudaFree(s.d_lengths); cudaFree(s.d_qual_offsets); cudaFree(s.d_name_lengths);
     for (int i = 0; i < 3; i++) cudaFree(s.d_views[i]);
     for (int i = 0; i < 2; i++) { cudaFree(s.d_match[i]); cudaFreeHost(s.h_match[i]); }
-    cudaFree(s.d_wcols); cudaFree(s.d_wcols_sorted); cudaFree(s.d_item_in); cudaFree(s.d_item_order);
+    cudaFree(s.d_wcols); cudaFree(s.d_wcols_sorted); cudaFree(s.d_item_order);
     cudaFree(s.d_best_key); cudaFree(s.d_tasks); cudaFree(s.d_results); cudaFree(s.d_jobs);
-    cudaFree(s.d_key_in); cudaFree(s.d_key_out); cudaFree(s.d_val_in); cudaFree(s.d_order);
-    cudaFree(s.d_sort_tmp); cudaFree(s.d_wins); cudaFree(s.d_seedwins);
+    cudaFree(s.d_order);
+    cudaFree(s.d_wins); cudaFree(s.d_seedwins);
     cudaFree(s.d_counters); cudaFree(s.d_cells); cudaFree(s.d_bin); cudaFree(s.d_out_len);
     cudaFree(s.d_rec_bytes); cudaFree(s.d_hist_cnt); cudaFree(s.d_hist_bytes);
     cudaFree(s.d_bin_counts); cudaFree(s.d_bin_offsets); cudaFree(s.d_bin_bytes);
@@ -302,9 +307,13 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         if (cap > 0 && occ > cap) occ = cap;
     }
     ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
-    {
-        uint32_t *nk = nullptr;
-        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, ctx->sort_tmp_bytes, nk, nk, nk, nk, 2 * (int)ctx->max_reads));
+    CK(cudaFuncSetAttribute(resolve_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)band_smem_bytes(MAX_LANES)));
+    for (int r = 0; r < p->n_rounds; r++) {
+        if (ctx->anchored[r]) continue;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_band_kernel, BAND_THREADS,
+                                                         band_smem_bytes(ctx->h_tab[r].n_lanes)));
+        ctx->band_blocks[r] = ctx->sm_count * (occ > 0 ? occ : 1);
     }
     ctx->slots.resize((size_t)ctx->n_slots);
     for (auto &s : ctx->slots) {
@@ -383,9 +392,7 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
     s.n_bytes = b->n_bytes;
     s.name_bytes = name_bytes;
     uint64_t bases = 0;
-    uint32_t max_len = 0;
     for (uint32_t r = 0; r < b->n_reads; r++) {
-        if (b->lengths[r] > max_len) max_len = b->lengths[r];
         if (b->offsets[r] + b->lengths[r] > b->n_bytes ||
             (b->qual_offsets && b->qual_offsets[r] + b->lengths[r] > b->n_bytes)) {
             ctx->err = "read extends past n_bytes"; return ORC_EINVAL;
@@ -408,8 +415,6 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
         }
     }
     s.in_bases = bases;
-    s.len_bits = 1;
-    while (s.len_bits < 32 && (((uint64_t)max_len + 2) >> s.len_bits) != 0) s.len_bits++;
     CK(cudaEventRecord(s.ev[EV_START], s.stream));
     s.u_qual = s.d_qual; s.u_names = s.d_names; s.u_qual_offsets = nullptr; s.u_name_lengths = nullptr;
     if (b->n_reads) {
@@ -454,22 +459,24 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     if (s.state == SLOT_IDLE) { ctx->err = "orc_launch on a slot without an uploaded batch"; return ORC_ESTATE; }
     CK(cudaSetDevice(ctx->device));
     const uint32_t n = s.n_reads;
+    uint32_t nl = 0;                             // own kernels launched (CUB's are not counted)
     uint32_t *W = s.d_codes_alloc + GUARD_WORDS;
     cudaStream_t st = s.stream;
-    CK(cudaMemsetAsync(s.d_counters, 0, 16 * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(s.d_counters, 0, N_COUNTERS * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(s.d_cells, 0, 6 * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));       // kernels start here (re-recorded when launched alone)
     s.did_h2d = s.fresh_upload;                  // h2d_ms is only meaningful right after an upload
     s.fresh_upload = false;
     s.did_d2h = false;
     if (n) {
-        init_views_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_offsets, s.d_lengths, n, s.d_views[0]);
+        init_views_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_offsets, s.d_lengths, n, s.d_views[0],
+                                                           sort_hist(s.d_counters, 0, 0, 0)); nl++;
         bool need_codes = false;        // anchored rounds read the ASCII bases directly
         for (int r = 0; r < ctx->n_rounds; r++) need_codes = need_codes || !ctx->anchored[r];
         if (need_codes) {
             const uint64_t n16 = (s.n_bytes + 15) / 16;
             const int pack_blocks = (int)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16);
-            pack_kernel<<<pack_blocks, 256, 0, st>>>(s.d_seq, W, n16, ctx->d_pack_lut);
+            pack_kernel<<<pack_blocks, 256, 0, st>>>(s.d_seq, W, n16, ctx->d_pack_lut); nl++;
         }
     }
     CK(cudaEventRecord(s.ev[EV_PACK], st));
@@ -484,50 +491,58 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
             CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
             anchored_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_anch[r], s.d_seq, ctx->d_comp_lut, s.d_views[r],
-                                                                prev, n, s.d_results, s.d_best_key);
+                                                                prev, n, s.d_results, s.d_best_key); nl++;
             CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         } else if (n) {
             CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
             // stage 1: (with a usable shared prefix) order the reads by length and let one 32-bit
             // scan of the prefix per (read, direction) mark the column windows stage 2 must look at
-            size_t tmp = ctx->sort_tmp_bytes;
+            const uint32_t sort_blocks_n = (n + SORT_BUCKETS - 1) / SORT_BUCKETS;
             if (filter) {
-                sort_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_views[r], prev, n, s.d_key_in, s.d_val_in);
-                CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_key_in, s.d_key_out, s.d_val_in,
-                                                             s.d_order, (int)n, 0, s.len_bits, st));
+                bucket_scatter_kernel<true><<<sort_blocks_n, 256, 0, st>>>(
+                    s.d_views[r], prev, nullptr, n, sort_hist(s.d_counters, r, 0, 0), sort_hist(s.d_counters, r, 0, 1),
+                    s.d_order, nullptr); nl++;
             }
             const bool seeded = filter && ctx->h_seed[r].on != 0;
-            if (seeded)
+            if (seeded) {
                 seed_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_seed[r], W, s.d_views[r], prev, s.d_order, n,
-                                                            s.d_seedwins);
+                                                            s.d_seedwins); nl++;
+            }
             trigger_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], prev,
                                                                filter ? s.d_order : nullptr, n, s.d_wins,
-                                                               s.d_wcols, s.d_item_in, s.d_cells + 2 + r,
-                                                               seeded ? s.d_seedwins : nullptr);
+                                                               s.d_wcols, s.d_cells + 2 + r,
+                                                               seeded ? s.d_seedwins : nullptr,
+                                                               sort_hist(s.d_counters, r, 1, 0)); nl++;
             // order the (read, direction) items by the columns they have to scan
-            tmp = ctx->sort_tmp_bytes;
-            CK(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_wcols, s.d_wcols_sorted, s.d_item_in,
-                                                         s.d_item_order, 2 * (int)n, 0, s.len_bits, st));
+            bucket_scatter_kernel<false><<<(2 * n + SORT_BUCKETS - 1) / SORT_BUCKETS, 256, 0, st>>>(
+                nullptr, nullptr, s.d_wcols, 2 * n, sort_hist(s.d_counters, r, 1, 0), sort_hist(s.d_counters, r, 1, 1),
+                s.d_item_order, s.d_wcols_sorted); nl++;
         }
         if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
         if (n && !ctx->anchored[r]) {
             // stage 2a drops the pairs that cannot hold a candidate, stage 2b scans the rest
             const bool prefilter = ctx->h_tab[r].indels != 0;
-            if (prefilter)
+            if (prefilter) {
                 filter_kernel<<<ctx->filter_blocks, SCAN_THREADS, 0, st>>>(
                     ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_jobs, cnt,
-                    s.d_cells + 4 + r);
+                    s.d_cells + 4 + r); nl++;
+            }
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_results,
-                s.d_tasks, s.d_best_key, cnt, prefilter ? s.d_jobs : nullptr, (uint32_t)s.cap_pairs);
+                s.d_tasks, s.d_best_key, cnt, prefilter ? s.d_jobs : nullptr, (uint32_t)s.cap_pairs); nl++;
         }
         if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         if (n) {
-            if (!ctx->anchored[r])
-                resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2,
-                                                                   s.d_results, s.d_best_key, (uint32_t)s.cap_pairs);
+            if (!ctx->anchored[r]) {
+                resolve_band_kernel<<<ctx->band_blocks[r], BAND_THREADS, band_smem_bytes(ctx->h_tab[r].n_lanes), st>>>(
+                    ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2, s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
+                resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r],
+                                                                   s.d_tasks + s.cap_pairs, cnt + 3,
+                                                                   s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
+            }
             SelectArgs A;
-            A.tab = ctx->d_tab[r];
+            A.type = ctx->h_tab[r].type;
+            A.revcomp = ctx->h_tab[r].revcomp;
             A.views_in = s.d_views[r];
             A.views_out = s.d_views[r + 1];
             A.prev = prev;
@@ -546,7 +561,8 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             A.out_len = s.d_out_len;
             A.rec_bytes = s.d_rec_bytes;
             A.next_bases = (r + 1 < ctx->n_rounds) ? s.d_cells + r + 1 : nullptr;
-            select_kernel<<<(n + 127) / 128, 128, 0, st>>>(A);
+            A.next_len_hist = (r + 1 < ctx->n_rounds) ? sort_hist(s.d_counters, r + 1, 0, 0) : nullptr;
+            select_kernel<<<(n + 127) / 128, 128, 0, st>>>(A); nl++;
         }
         CK(cudaEventRecord(s.ev[r == 0 ? EV_RES0 : EV_RES1], st));
     }
@@ -558,23 +574,24 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     const uint32_t n_chunks = (n + BIN_CHUNK - 1) / BIN_CHUNK;
     if (n) {
         bin_count_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(s.d_bin, s.d_rec_bytes, n, ctx->n_bins, n_chunks,
-                                                            s.d_hist_cnt, s.d_hist_bytes);
+                                                            s.d_hist_cnt, s.d_hist_bytes); nl++;
     }
-    bin_scan_kernel<<<ctx->n_bins, 256, 0, st>>>(n_chunks, s.d_hist_cnt, s.d_hist_bytes, s.d_bin_counts, s.d_bin_bytes);
-    bin_offsets_kernel<<<1, 32, 0, st>>>(ctx->n_bins, s.d_bin_bytes, s.d_bin_offsets);
+    bin_scan_kernel<<<ctx->n_bins, 256, 0, st>>>(n_chunks, s.d_hist_cnt, s.d_hist_bytes, s.d_bin_counts, s.d_bin_bytes); nl++;
+    bin_offsets_kernel<<<1, 32, 0, st>>>(ctx->n_bins, s.d_bin_bytes, s.d_bin_offsets); nl++;
     if (n) {
         bin_place_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(s.d_bin, s.d_rec_bytes, n, ctx->n_bins, n_chunks,
-                                                            s.d_hist_bytes, s.d_bin_offsets, s.d_dest);
+                                                            s.d_hist_bytes, s.d_bin_offsets, s.d_dest); nl++;
     }
     CK(cudaEventRecord(s.ev[EV_BIN], st));
     if (n && s.has_names) {
         emit_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(s.d_seq, s.u_qual, s.u_names, s.d_name_offsets,
                                                        s.u_name_lengths, s.d_offsets, s.u_qual_offsets,
                                                        s.d_views[ctx->n_rounds], s.d_dest, n, ctx->d_comp_lut,
-                                                       s.d_fastq);
+                                                       s.d_fastq); nl++;
     }
     CK(cudaEventRecord(s.ev[EV_EMIT], st));
     CK(cudaGetLastError());
+    s.n_launches = nl;
     s.state = SLOT_LAUNCHED;
     s.did_kernels = true;
     return ORC_OK;
@@ -618,7 +635,7 @@ static int grow_pair_arenas(orc_ctx *ctx, Slot &s, const uint32_t *counters)
     CK(cudaStreamSynchronize(s.stream));
     cudaFree(s.d_tasks); cudaFree(s.d_results);
     s.d_tasks = nullptr; s.d_results = nullptr;
-    CK(dalloc(&s.d_tasks, worst));
+    CK(dalloc(&s.d_tasks, 2 * worst));
     CK(dalloc(&s.d_results, worst));
     s.cap_pairs = worst;
     return 1;
@@ -722,18 +739,9 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
         }
     uint64_t emit_bytes = 0;
     CK(cudaMemcpy(&emit_bytes, s.d_bin_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    t->kernel_launches = s.n_reads ? (2u + 3u * (uint32_t)ctx->n_rounds + 4u + (s.has_names ? 1u : 0u)) : 2u;
-    if (s.n_reads)
-        for (int r = 0; r < ctx->n_rounds; r++) {   // trigger (+ sort_keys); CUB's own launches are not counted
-            t->kernel_launches += ctx->anchored[r] ? 0u : (ctx->h_tab[r].use_filter ? 2u : 1u);
-            if (!ctx->anchored[r] && ctx->h_tab[r].use_filter && ctx->h_seed[r].on) t->kernel_launches += 1u;   // seed_kernel
-        }
-    if (s.n_reads)
-        for (int r = 0; r < ctx->n_rounds; r++)
-            if (ctx->anchored[r]) t->kernel_launches -= 1u;   // anchored + select instead of scan + resolve + select
-            else if (ctx->h_tab[r].indels) t->kernel_launches += 1u;   // stage 2a (filter_kernel)
+    t->kernel_launches = s.n_launches;
     for (int r = 0; r < ctx->n_rounds; r++) {
-        t->n_tasks[r] = counters[8 * r + 2];
+        t->n_tasks[r] = counters[8 * r + 2] + counters[8 * r + 3];
         t->n_candidates[r] = counters[8 * r + 1];
         const RoundTable &T = ctx->h_tab[r];
         // algorithmic cells: pairs * m * n summed over the reads entering the round

@@ -969,13 +969,17 @@ struct LaneScan {
     Best best;
     int32_t need;       // a candidate with cost > 0 was seen: the resolver decides
     int32_t broke;      // R5 hit its early exit (exact full match) while settling inline
+    int32_t c5, c6;     // D[m][jf] and D[i1][n]: the costs the band resolver counts on from
 };
+
+// Task.pad_: bit 0 = TASK_WIDE, bits 8..13 = D[m][jf], bits 16..21 = D[i1][n]
+ORC_HD int32_t task_anchors(const LaneScan &L) { return (int32_t)(((uint32_t)L.c5 & 63u) << 8 | ((uint32_t)L.c6 & 63u) << 16); }
 
 ORC_HD void lane_scan_init(LaneScan &L, int m, int n)
 {
     L.h.jf = 0x7fffffff; L.h.jl = -1; L.h.i1 = 0x7fffffff; L.h.i2 = -1;
     L.best.ref_stop = m; L.best.query_stop = n; L.best.cost = m + n + 1; L.best.origin = 0; L.best.score = 0;
-    L.need = 0; L.broke = 0;
+    L.need = 0; L.broke = 0; L.c5 = 0; L.c6 = 0;
 }
 
 // Stage 2: columns s+1 .. e of one pair.
@@ -1041,7 +1045,7 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
                     const int j = (int)s + 8 * q + t + 1;
                     const int lmax = imin(m, j + D);
                     if (lmax >= min_ov && D <= (int)kmax[lmax]) {
-                        L.h.jf = imin(L.h.jf, j);
+                        if (j < L.h.jf) { L.h.jf = j; L.c5 = D; }
                         L.h.jl = j;
                         if (j == n) last_d = D;
                         if (D == 0) {
@@ -1069,7 +1073,7 @@ ORC_HD void scan_window(const uint32_t *__restrict__ W, uint64_t lo, uint32_t le
             const int bit = 64 - m + i - 1;
             cum += (int)((Pv >> bit) & 1u) - (int)((Mv >> bit) & 1u);
             if (i >= min_ov && cum <= (int)kmax[i]) {
-                L.h.i1 = imin(L.h.i1, i);
+                if (i < L.h.i1) { L.h.i1 = i; L.c6 = cum; }
                 L.h.i2 = i;
                 if (cum == 0) zero_rows |= 1ull << (i - 1);
                 else L.need = 1;
@@ -1568,15 +1572,425 @@ ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, 
 }
 
 // ------------------------------------------------------------------------------------
+// The band resolver: the same re-scan and the same walks, on 8 bytes per column.
+//
+// What a walk needs at a cell (i, j) whose characters differ (cost d >= 1, known) is cutadapt's choice
+// among its three predecessors (R3).  The cell's cost is the minimum of the three candidates, all of
+// which are >= d, so
+//   * the diagonal wins (first in cutadapt's order) iff D[i-1][j-1] == d - 1, i.e. iff the cell's
+//     diagonal delta is 1 -- the complement of Hyyro's "diagonal zero" vector D0 = Xh | Mv;
+//   * otherwise the insertion (up) wins iff D[i-1][j] == d - 1, i.e. iff the vertical delta is +1 -- Pv;
+//   * otherwise the deletion (left).
+// Every move from such a cell lowers the cost by exactly one and a match keeps it, so no cost is ever
+// looked up: two bits per cell decide.  (A scan restarted at ws > 0 over-estimates costs elsewhere, but a
+// predecessor with the true cost d - 1 lies on an optimal path to the candidate and is exact, and one
+// whose true cost is >= d stays >= d: both bits are those of the true matrix at every cell a walk visits.)
+//
+// A path with at most k errors stays within k diagonals of where it ends, so per column only the rows
+// around the end cells' diagonals matter: with end cells on diagonals dlo..dhi (column minus row), column
+// j keeps the 32 rows from j - (dhi + k + 1) upwards of Pv and D0 -- 8 bytes, against the 16 of the
+// whole vectors -- and needs no costs.  That fits shared memory (BAND_COLS columns per thread), which is
+// what the whole exercise is for: the 2 KB per-thread ring of the wide resolver lives in local memory.
+// Tasks whose end cells span more than 30 - 2k diagonals, or whose scan is longer than BAND_COLS columns,
+// keep the wide resolver above.
+// ------------------------------------------------------------------------------------
+constexpr int BAND_COLS = 96;           // columns of one scan, entry 0 unused
+constexpr uint32_t TASK_WIDE = 1u;      // Task.pad_ bit 0: not eligible for the band resolver
+
+struct alignas(8) BandEntry { uint32_t pv, d0; };
+struct BandRing {                       // entry c of this thread: p[c * stride]
+    BandEntry *p;
+    int32_t stride;
+};
+
+// Geometry of a task's scans (what resolve_begin derives from the hull).
+struct ResolveGeo {
+    int32_t has5, has6, r6lo, r6hi, ws6;
+    int32_t ws, we, jf, jl, r6, join, second;       // the first scan
+};
+
+ORC_HD void resolve_geometry(int type, int m, int k, int n, const Task &t, ResolveGeo &G)
+{
+    const bool has5 = t.jf <= t.jl;
+    const bool has6 = (type == TYPE_BACK) ? (t.i1 <= t.i2) : (has5 && t.jl == n);   // FRONT: only cell (m, n)
+    G.has5 = has5 ? 1 : 0; G.has6 = has6 ? 1 : 0;
+    G.r6lo = (type == TYPE_BACK) ? t.i1 : m;
+    G.r6hi = (type == TYPE_BACK) ? t.i2 : m;
+    G.ws6 = imax(0, n - G.r6hi - k - 1);
+    G.ws = 0; G.we = 0; G.jf = 1; G.jl = 0; G.r6 = 0; G.join = 0; G.second = 0;
+    if (has5) {
+        G.ws = imax(0, t.jf - m - k - 1);
+        const bool join = has6 && (G.ws6 <= t.jl + 1 || (G.ws == 0 && G.ws6 == 0));
+        G.join = join ? 1 : 0;
+        G.second = (has6 && !join) ? 1 : 0;
+        G.we = join ? n : t.jl; G.jf = t.jf; G.jl = t.jl; G.r6 = join ? 1 : 0;
+    } else if (has6) {
+        G.ws = G.ws6; G.we = n; G.r6 = 1;
+    }
+}
+
+// May one scan (columns ws+1..we, R5 candidates jf..jl, R6 rows r6lo..r6hi if r6) use the band ring?
+// boff = dhi + k + 1: cell (i, j) is bit boff - (j - i) of column j's window.
+ORC_HD bool band_scan_ok(int m, int k, int n, int ws, int we, int jf, int jl, bool r6, int r6lo, int r6hi, int &boff)
+{
+    int dlo = 0x3fffffff, dhi = -0x3fffffff;
+    if (jf <= jl) { dlo = jf - m; dhi = jl - m; }
+    if (r6 && we == n) {
+        const int lo = n - imin(r6hi, m), hi = n - imax(r6lo, 1);
+        if (lo <= hi) { dlo = imin(dlo, lo); dhi = imax(dhi, hi); }
+    }
+    boff = 0;
+    if (k > 14) return false;                           // hull costs are kept in four bits, 15 = none
+    if (dlo > dhi) return we - ws < BAND_COLS;          // nothing to walk from
+    if ((dhi - dlo) + 2 * k + 3 > 32) return false;     // one spare row on either side
+    if (we - ws >= BAND_COLS) return false;
+    boff = dhi + k + 1;
+    return true;
+}
+
+ORC_HD bool task_band_ok(int type, int m, int k, int n, const Task &t)
+{
+    ResolveGeo G;
+    resolve_geometry(type, m, k, n, t, G);
+    int boff;
+    if (!G.has5 && !G.has6) return true;
+    if (!band_scan_ok(m, k, n, G.ws, G.we, G.jf, G.jl, G.r6 != 0, G.r6lo, G.r6hi, boff)) return false;
+    if (G.second && !band_scan_ok(m, k, n, G.ws6, n, 1, 0, true, G.r6lo, G.r6hi, boff)) return false;
+    return true;
+}
+
+// bits s .. s+31 of x; positions below bit 0 or above bit 63 read as zero (s may be negative)
+ORC_HD uint32_t band_window(uint64_t x, int s)
+{
+    const int sp = imin(imax(s, -32), 64) + 32;         // 0 .. 96
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    const int w = sp >> 5;
+    const uint32_t a = w == 0 ? 0u : (w == 1 ? lo : (w == 2 ? hi : 0u));
+    const uint32_t b = w == 0 ? lo : (w == 1 ? hi : 0u);
+    return funnel_r(a, b, (uint32_t)(sp & 31));
+}
+
+struct BandCtx {
+    const char *peq_base;               // the lane's bank of the 64-bit match table
+    const uint32_t *code4, *rcode4;
+    const uint8_t *kmax;
+    int32_t dir, lane, m, k, min_ov, n, type;
+    int32_t c5, c6;                     // D[m][jf], D[i1][n] (from the scan, exact)
+    ResolveGeo G;
+    // the scan in progress
+    int32_t ws, we, jf, jl, r6, narrow, ubw, broke, boff;
+    int32_t top_j, traced_j, traced_score, traced_origin;
+    uint64_t hc0, hc1;                  // D[m][j] of the hull columns jf .. jf+31, four bits each (15: above k)
+    uint32_t vpn, vnn;                  // vertical deltas of column we in its band rows
+    Best best;
+};
+
+ORC_HD int band_hull_cost(const BandCtx &C, int j)
+{
+    const int q = j - C.jf;
+    return (int)(((q < 16 ? C.hc0 : C.hc1) >> (4 * (q & 15))) & 15ull);
+}
+
+// One step of the walk at a cell whose characters differ: cutadapt's predecessor from the two stored bits.
+ORC_HD void band_step(const BandRing &R, int ws, int boff, int &i, int &j, int &d, int &score)
+{
+    const BandEntry e = R.p[(j - ws) * R.stride];
+    const uint32_t b = (uint32_t)(boff - (j - i));
+    if (!((e.d0 >> b) & 1u)) { score -= 1; --i; --j; }          // diagonal delta 1: mismatch
+    else if ((e.pv >> b) & 1u) { score -= 2; --i; }             // vertical delta +1: insertion
+    else { score -= 2; --j; }                                   // deletion
+    --d;
+}
+
+ORC_HD void band_trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir,
+                            const uint32_t *code4, const uint32_t *rcode4, int m, int type, int ws,
+                            const BandRing &R, int boff, int i, int j, int d, int &score_out, int &origin_out)
+{
+    int score = 0, origin = 0;
+    for (;;) {
+        if (i == 0) { origin = j; break; }
+        if (j == 0) { origin = (type == TYPE_FRONT) ? -i : 0; break; }
+        if (j <= ws) { origin = j; break; }          // unreachable for a genuine candidate
+        const int avail = imin(16, imin(i, j - ws));
+        const uint64_t r = nib16(W, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
+        const uint64_t a = nib16(dir ? rcode4 : code4, dir ? (int64_t)(m - i) : (int64_t)i);
+        uint64_t x = r & a;
+        x |= x >> 1; x |= x >> 2;
+        uint64_t mis = ~x & 0x1111111111111111ull;
+        if (dir) mis = brev64(mis);
+        const int run = imin(clz64(mis) >> 2, avail);
+        score += run; i -= run; j -= run;
+        if (run == avail) continue;
+        band_step(R, ws, boff, i, j, d, score);
+    }
+    score_out = score;
+    origin_out = origin;
+}
+
+ORC_HD void band_trace_back_group(uint32_t mask, bool on, const uint32_t *W, uint64_t lo, uint32_t len, int dir,
+                                  const uint32_t *code4, const uint32_t *rcode4, int m, int type, int ws,
+                                  const BandRing &R, int boff, int i, int j, int d, int &score_out, int &origin_out)
+{
+    int score = 0, origin = 0;
+    while (ORC_ANY(mask, on)) {
+        if (on) {
+            if (i == 0) { origin = j; on = false; }
+            else if (j == 0) { origin = (type == TYPE_FRONT) ? -i : 0; on = false; }
+            else if (j <= ws) { origin = j; on = false; }
+            else {
+                const int avail = imin(16, imin(i, j - ws));
+                const uint64_t r = nib16(W, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
+                const uint64_t a = nib16(dir ? rcode4 : code4, dir ? (int64_t)(m - i) : (int64_t)i);
+                uint64_t x = r & a;
+                x |= x >> 1; x |= x >> 2;
+                uint64_t mis = ~x & 0x1111111111111111ull;
+                if (dir) mis = brev64(mis);
+                const int run = imin(clz64(mis) >> 2, avail);
+                score += run; i -= run; j -= run;
+                if (run < avail) band_step(R, ws, boff, i, j, d, score);
+            }
+        }
+    }
+    score_out = score;
+    origin_out = origin;
+}
+
+// Columns ws+1..we of one scan into the band ring.
+//
+// The recurrence itself runs on the band only (Hyyro's diagonal band): the 32-bit vectors hold rows
+// j - boff .. j - boff + 31 of column j, so from one column to the next every row moves down one bit
+// (VP, VN >>= 1) and a new row enters at the top.  Its vertical delta in the previous column is taken as
+// +1, the largest it can be, and the first band row ignores its upper neighbour (no carry into the add):
+// both only ever over-estimate costs outside the diagonals a path with <= k errors can use, so every cell
+// on such a path -- and both of its decision bits -- is exact, by the argument used for restarted scans.
+// Rows below row 1 stand for row 0 (cost 0 in every column): their match bits read as 1 and their deltas
+// stay 0, like the padding bits of the 64-bit table.  What comes out per column, VP and D0, is already
+// the ring entry.
+//
+// Costs are not a popcount away here (row 0 is not in the band), and none is needed by the walks.  The
+// hull columns' D[m][j] start from the scan's D[m][jf] (Task anchors) and follow the horizontal deltas of
+// row m; R5 then runs as in resolve_columns (narrow hull: note the best bound; otherwise walk on the spot).
+ORC_HD void band_columns(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, const BandRing &R)
+{
+    const int m = C.m, n = C.n, k = C.k, ws = C.ws, we = C.we, jf = C.jf, jl = C.jl, dir = C.dir, boff = C.boff;
+    C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
+    C.narrow = (jf <= jl && (jl - jf) + 2 * k <= m / 2) ? 1 : 0;
+    C.top_j = -1;
+    C.broke = 0;
+    C.hc0 = ~0ull; C.hc1 = ~0ull;
+    int top_ub = -(1 << 20);
+    C.ubw = (ws == 0 && C.type == TYPE_BACK) ? 1 : 2;
+    const int ubw = C.ubw;
+    const bool narrow = C.narrow != 0;
+    uint32_t VP, VN = 0;
+    if (ws == 0 && C.type == TYPE_FRONT) VP = 0;                // R2: column 0 of a 5' adapter costs 0 in every row
+    else {
+        const int z = 1 - (ws - boff);                          // first band position of column ws that is a real row
+        VP = z <= 0 ? 0xFFFFFFFFu : (z >= 32 ? 0u : (0xFFFFFFFFu << z));
+    }
+    const char *peq_base = C.peq_base;
+    const uint32_t lane8 = (uint32_t)(C.lane & 31) * 8u;
+    uint32_t sel0, sel1, sel2, sel3;
+    if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
+    else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
+    ChunkReader rd;
+    rd.init(W, lo, len, dir, (uint32_t)ws);
+    const int ncols = we - ws;
+    const int nchunks = (ncols + 7) >> 3;
+    const int sbase = 63 - m - boff + ws;                       // vector bit of band position 0, column ws
+    uint32_t HP = 0, HN = 0;
+    auto column = [&](uint32_t A, uint32_t B, int t, int c) {
+        const uint32_t src = (t & 1) ? B : A;
+        const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
+        const uint64_t Eq64 = *reinterpret_cast<const uint64_t *>(peq_base + byte_perm(src, lane8, sel));
+        const uint32_t Eq = ~band_window(~Eq64, sbase + c);     // rows below the table read as matches
+        VP = (VP >> 1) | 0x80000000u;
+        VN >>= 1;
+        const uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+        HP = VN | ~(D0 | VP);
+        HN = D0 & VP;
+        const uint32_t X = HP << 1;
+        VP = (HN << 1) | ~(D0 | X);
+        VN = D0 & X;
+        BandEntry e;
+        e.pv = VP; e.d0 = D0;
+        R.p[c * R.stride] = e;
+    };
+    int D = C.c5;
+    for (int q = 0; q < nchunks; q++) {
+        uint32_t A, B;
+        rd.next(A, B);
+        const int ncol = imin(8, ncols - 8 * q);
+        const int jb = ws + 8 * q;
+        if (ncol == 8 && (jb + 8 < jf || jb + 1 > jl)) {
+#pragma unroll
+            for (int t = 0; t < 8; t++) column(A, B, t, 8 * q + t + 1);
+            continue;
+        }
+#pragma unroll 1
+        for (int t = 0; t < ncol; t++) {
+            const int j = jb + t + 1;
+            column(A, B, t, j - ws);
+            if (j < jf || j > jl) continue;
+            if (j > jf) {                                       // D[m][j] along row m, band position boff - (j - m)
+                const uint32_t bm = (uint32_t)(boff - (j - m));
+                D += (int)((HP >> bm) & 1u) - (int)((HN >> bm) & 1u);
+            }
+            if (D <= k) {
+                const int lmax = imin(m, j + D);
+                if (lmax >= C.min_ov && D <= (int)C.kmax[lmax]) {
+                    const int ub = lmax - ubw * D;
+                    {   // D[m][j] of the candidate columns: the narrow hull's walks and R6's cell (m, n) read them
+                        const int hq = j - jf;                  // < 32 for every band-eligible hull
+                        const uint64_t clr = ~(15ull << (4 * (hq & 15)));
+                        const uint64_t put = (uint64_t)D << (4 * (hq & 15));
+                        if (hq < 16) C.hc0 = (C.hc0 & clr) | put; else C.hc1 = (C.hc1 & clr) | put;
+                    }
+                    if (narrow) {
+                        if (ub > top_ub) { top_ub = ub; C.top_j = j; }
+                    } else if (C.best.cost == m + n + 1 || ub > C.best.score) {
+                        Cell c;
+                        c.cost = D;
+                        band_trace_back(W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, boff, m, j, D, c.score, c.origin);
+                        C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin;
+                        if (r5_update(C.best, m, n, c, j, C.min_ov, C.kmax)) { C.broke = 1; return; }
+                    }
+                }
+            }
+        }
+    }
+    C.vpn = VP; C.vnn = VN;             // column we (column n when the scan reached it)
+}
+
+ORC_HD void band_finish(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, const BandRing &R,
+                        uint32_t mask, bool grouped)
+{
+    const int m = C.m, n = C.n, k = C.k, ws = C.ws, dir = C.dir, ubw = C.ubw;
+    Best &best = C.best;
+    if (grouped) {
+        bool more = !C.broke && C.narrow && C.top_j >= 0;
+        int q = C.jf - 1;
+        while (ORC_ANY(mask, more)) {
+            int j = 0, Dj = 0;
+            bool have = false;
+            if (more) {
+                for (; q <= C.jl && !have; q++) {
+                    j = q < C.jf ? C.top_j : q;
+                    Dj = band_hull_cost(C, j);
+                    if (q < C.jf) { have = true; continue; }
+                    if (j == C.top_j || Dj > k) continue;       // 15 marks "not a candidate"
+                    const int lmax = imin(m, j + Dj);
+                    const int ub = lmax - ubw * Dj;
+                    have = best.cost == m + n + 1 || ub > best.score || (ub == best.score && j < best.query_stop);
+                }
+                if (!have) more = false;
+            }
+            Cell c;
+            c.cost = Dj; c.score = 0; c.origin = 0;
+            band_trace_back_group(mask, have, W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, C.boff, m, j, Dj,
+                                  c.score, c.origin);
+            if (have) {
+                if (j == n) { C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin; }
+                const int length = m + imin(c.origin, 0);
+                if (length >= C.min_ov && c.cost <= (int)C.kmax[KMAX_R5 + length] &&
+                    (best.cost == m + n + 1 || c.score > best.score || (c.score == best.score && j < best.query_stop))) {
+                    best.score = c.score; best.cost = c.cost; best.origin = c.origin; best.ref_stop = m; best.query_stop = j;
+                }
+            }
+        }
+        if (!C.broke && C.narrow && best.cost == 0 && best.origin >= 0) C.broke = 1;     // R5's early exit
+    }
+    if (C.broke) return;
+    if (C.r6 && C.we == n && n > ws) {
+        // R6: rows r6hi..r6lo of column n, top row first like cutadapt.  D[i][n] counts on from the scan's
+        // D[r6lo][n] (3' adapters) or is the last hull column's cost (5' adapters: the single cell (m, n)).
+        const int ilo = imax(C.G.r6lo, 1), ihi = imin(C.G.r6hi, m);
+        int Dtop = 0;
+        if (C.type == TYPE_FRONT) Dtop = band_hull_cost(C, n);  // only reached with jl == n
+        else {
+            Dtop = C.c6;
+            for (int i = ilo + 1; i <= ihi; i++) {
+                const uint32_t b = (uint32_t)(i - (n - C.boff));
+                Dtop += (int)((C.vpn >> b) & 1u) - (int)((C.vnn >> b) & 1u);
+            }
+        }
+        int Di = Dtop;
+        for (int i = ihi; i >= ilo; i--) {
+            if (i < ihi) {                                      // D[i][n] = D[i+1][n] - the vertical delta of row i+1
+                const uint32_t b = (uint32_t)(i + 1 - (n - C.boff));
+                Di -= (int)((C.vpn >> b) & 1u) - (int)((C.vnn >> b) & 1u);
+            }
+            if (Di > k) continue;
+            const int lmax = (C.type == TYPE_FRONT) ? imin(i, n + Di) : i;
+            if (!(lmax >= C.min_ov && Di <= (int)C.kmax[lmax])) continue;
+            const int ub = lmax - ubw * Di;
+            if (ub < best.score || (ub == best.score && Di >= best.cost)) continue;
+            Cell c;
+            c.cost = Di;
+            if (i == m && C.traced_j == n) { c.score = C.traced_score; c.origin = C.traced_origin; }
+            else band_trace_back(W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, C.boff, i, n, Di, c.score, c.origin);
+            r6_update(best, n, c, i, C.min_ov, C.kmax);
+        }
+    }
+}
+
+ORC_HD void band_begin(const uint32_t *W, const View &v, const RoundTable &T, const Task &t,
+                       BandCtx &C, const BandRing &R, const char *peq_base)
+{
+    const int a = (int)t.lane % T.n_adapters;
+    C.dir = (int)t.lane / T.n_adapters;
+    C.m = T.m[a]; C.k = T.k[a]; C.min_ov = T.min_ov[a];
+    C.kmax = T.kmax[a];
+    C.peq_base = peq_base;
+    C.lane = (int)t.lane;
+    C.code4 = T.code4[a]; C.rcode4 = T.rcode4[a];
+    C.n = (int)v.len;
+    C.type = T.type;
+    const int m = C.m, n = C.n;
+    C.best.ref_stop = m; C.best.query_stop = n; C.best.cost = m + n + 1; C.best.origin = 0; C.best.score = 0;
+    resolve_geometry(T.type, m, C.k, n, t, C.G);
+    C.broke = 0; C.narrow = 0; C.top_j = -1; C.ubw = 2; C.boff = 0;
+    C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
+    C.hc0 = C.hc1 = ~0ull; C.vpn = C.vnn = 0;
+    C.c5 = (int)((uint32_t)t.pad_ >> 8) & 63; C.c6 = (int)((uint32_t)t.pad_ >> 16) & 63;
+    C.ws = C.G.ws; C.we = C.G.we; C.jf = C.G.jf; C.jl = C.G.jl; C.r6 = C.G.r6;
+    if (C.G.has5 || C.G.has6) {
+        band_scan_ok(m, C.k, n, C.ws, C.we, C.jf, C.jl, C.r6 != 0, C.G.r6lo, C.G.r6hi, C.boff);
+        band_columns(W, v.lo, v.len, C, R);
+    }
+}
+
+ORC_HD void band_end(const uint32_t *W, const View &v, BandCtx &C, PairResult &res, const BandRing &R,
+                     uint32_t mask = 0xffffffffu)
+{
+    band_finish(W, v.lo, v.len, C, R, mask, true);
+    if (C.G.second && !C.broke) {
+        C.ws = C.G.ws6; C.we = C.n; C.jf = 1; C.jl = 0; C.r6 = 1;
+        band_scan_ok(C.m, C.k, C.n, C.ws, C.we, 1, 0, true, C.G.r6lo, C.G.r6hi, C.boff);
+        band_columns(W, v.lo, v.len, C, R);
+        band_finish(W, v.lo, v.len, C, R, mask, false);
+    }
+    best_to_result(C.best, C.m, C.n, res);
+}
+
+ORC_HD void band_resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, const Task &t,
+                              PairResult &res, const BandRing &R)
+{
+    BandCtx C;
+    band_begin(W, v, T, t, C, R, peq_bank(T, (int)t.lane));
+    band_end(W, v, C, res, R);
+}
+
+// ------------------------------------------------------------------------------------
 // select_read: R9, R10 from the per-orientation winners of R8.  key[o] is the maximum of
 // pack_key() over the pairs of logical orientation o that matched (0 = none).
 // ------------------------------------------------------------------------------------
-ORC_HD void select_read(const RoundTable &T, const View &v, const uint64_t key[2], const PairResult *results,
+ORC_HD void select_read(int type, int revcomp, const View &v, const uint64_t key[2], const PairResult *results,
                         Match &out, View &next)
 {
     const int fs = key[0] ? (int)(key[0] >> 44) - 512 : 0;
     const int rs = key[1] ? (int)(key[1] >> 44) - 512 : 0;
-    const int o = (T.revcomp && rs > fs) ? 1 : 0;          // R9: strictly higher score
+    const int o = (revcomp && rs > fs) ? 1 : 0;            // R9: strictly higher score
     next = v;
     const uint32_t eff = (v.rc & 1u) ^ (uint32_t)o;
     if (!key[o]) {
@@ -1595,7 +2009,7 @@ ORC_HD void select_read(const RoundTable &T, const View &v, const uint64_t key[2
     // R10: FRONT keeps [query_stop, n), BACK keeps [0, query_start) of the chosen orientation
     const uint32_t n = v.len;
     uint32_t a0, b0;
-    if (T.type == TYPE_FRONT) { a0 = (uint32_t)r.query_stop; b0 = n; }
+    if (type == TYPE_FRONT) { a0 = (uint32_t)r.query_stop; b0 = n; }
     else { a0 = 0; b0 = (uint32_t)r.query_start; }
     if (b0 < a0) b0 = a0;
     next.len = b0 - a0;

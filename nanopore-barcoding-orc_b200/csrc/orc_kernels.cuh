@@ -63,30 +63,106 @@ pack_kernel(const uint8_t *__restrict__ seq, uint32_t *__restrict__ codes, uint6
     }
 }
 
-__global__ void init_views_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ lengths,
-                                  uint32_t n_reads, View *__restrict__ views)
+// ------------------------------------------------------------------------------------
+// Ordering by size.  Stage 1 visits the reads in order of decreasing view length and stage 2 the
+// (read, direction) items in order of decreasing window columns, so that the lanes of a warp run loops of
+// about the same length.  Neither needs a total order: a counting sort over SORT_BUCKETS size classes
+// (exact below 1024, steps of 64 above) does, with the histogram taken by the kernel that produces the
+// sizes (init_views_kernel / select_kernel for the lengths, trigger_kernel for the columns) and one
+// scatter kernel per ordering.
+constexpr int SORT_BUCKETS = 2048;
+__device__ __forceinline__ uint32_t sort_bucket(uint32_t key)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    View v;
-    v.lo = offsets[r];
-    v.len = lengths[r];
-    v.rc = 0;
-    views[r] = v;
+    return key < 1024u ? key : 1024u + min((key - 1024u) >> 6, 1023u);
 }
 
-// ------------------------------------------------------------------------------------
-// Stage 1 of the scan.  Reads are visited in order of decreasing view length (order[] comes
-// from a radix sort of the lengths), two threads per read (one per storage direction), so the
-// 32 lanes of a warp walk 16 reads of nearly the same length.
-__global__ void sort_keys_kernel(const View *__restrict__ views, const Match *__restrict__ prev,
-                                 uint32_t n_reads, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+// hist[bucket] += 1 for every lane with valid set: one atomic per distinct bucket of the warp.
+// Every lane of the warp must call it.
+__device__ __forceinline__ void hist_add(uint32_t *__restrict__ hist, uint32_t bucket, bool valid)
+{
+    const uint32_t act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        const uint32_t peers = __match_any_sync(act, bucket);
+        if ((threadIdx.x & 31u) == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(hist + bucket, (uint32_t)__popc(peers));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+init_views_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ lengths,
+                  uint32_t n_reads, View *__restrict__ views, uint32_t *__restrict__ len_hist)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const bool skip = prev != nullptr && prev[r].adapter < 0;
-    keys[r] = skip ? 0u : views[r].len;
-    vals[r] = r;
+    const bool valid = r < n_reads;
+    View v;
+    v.lo = 0; v.len = 0; v.rc = 0;
+    if (valid) {
+        v.lo = offsets[r];
+        v.len = lengths[r];
+        views[r] = v;
+    }
+    hist_add(len_hist, sort_bucket(v.len), valid);
+}
+
+// Element e goes to position (elements of larger classes) + (its rank inside its class); the rank comes from
+// a block-local count plus one reservation per (block, class) on the class cursor, so the order inside a
+// class is arbitrary -- it only decides which thread works on which read, never a result.
+// FROM_VIEWS: the key of read e is its view length, 0 if the previous round left it unassigned.
+template <bool FROM_VIEWS>
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(const View *__restrict__ views, const Match *__restrict__ prev,
+                      const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ hist,
+                      uint32_t *__restrict__ cursor, uint32_t *__restrict__ order_out,
+                      uint32_t *__restrict__ keys_out)
+{
+    constexpr int PER = SORT_BUCKETS / 256;
+    __shared__ uint32_t s_base[SORT_BUCKETS], s_cnt[SORT_BUCKETS], s_blk[SORT_BUCKETS];
+    __shared__ uint32_t s_warp[8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // s_base[b] = number of elements in classes above b (descending order)
+    uint32_t h[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { h[i] = hist[tid * PER + i]; sum += h[i]; s_cnt[tid * PER + i] = 0; }
+    uint32_t inc = sum;                      // inclusive suffix sum over the threads
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, inc, d);
+        if (lane + d < 32) inc += t;
+    }
+    if (lane == 0) s_warp[w] = inc;
+    __syncthreads();
+    uint32_t above = inc - sum;              // classes of higher threads of this warp
+    for (int i = w + 1; i < 8; i++) above += s_warp[i];
+#pragma unroll
+    for (int i = PER - 1; i >= 0; i--) { s_base[tid * PER + i] = above; above += h[i]; }
+    __syncthreads();
+    uint32_t key[PER], rank[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const uint32_t e = blockIdx.x * SORT_BUCKETS + i * 256 + tid;
+        key[i] = 0; rank[i] = 0;
+        if (e < n) {
+            if (FROM_VIEWS) key[i] = (prev != nullptr && prev[e].adapter < 0) ? 0u : views[e].len;
+            else key[i] = keys[e];
+            rank[i] = atomicAdd(&s_cnt[sort_bucket(key[i])], 1u);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const uint32_t c = s_cnt[tid * PER + i];
+        if (c) s_blk[tid * PER + i] = atomicAdd(cursor + tid * PER + i, c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const uint32_t e = blockIdx.x * SORT_BUCKETS + i * 256 + tid;
+        if (e < n) {
+            const uint32_t b = sort_bucket(key[i]);
+            const uint32_t pos = s_base[b] + s_blk[b] + rank[i];
+            order_out[pos] = e;
+            if (keys_out) keys_out[pos] = key[i];
+        }
+    }
 }
 
 // Stage 1s: one thread per read (in length order), both directions in one pass over the packed
@@ -124,8 +200,9 @@ __global__ void __launch_bounds__(128)
 trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                const View *__restrict__ views, const Match *__restrict__ prev,
                const uint32_t *__restrict__ order, uint32_t n_reads, WinList *__restrict__ wins,
-               uint32_t *__restrict__ wcols, uint32_t *__restrict__ item_ids,
-               unsigned long long *__restrict__ col_sum, const SeedWins *__restrict__ seedwins)
+               uint32_t *__restrict__ wcols,
+               unsigned long long *__restrict__ col_sum, const SeedWins *__restrict__ seedwins,
+               uint32_t *__restrict__ col_hist)
 {
     __shared__ __align__(16) uint32_t s_peq32[16][64];
     __shared__ __align__(16) uint32_t s_peq32s[16][64];
@@ -185,13 +262,13 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
         const uint32_t sum = __reduce_add_sync(0xffffffffu, cols);
         if ((threadIdx.x & 31) == 0 && sum) atomicAdd(col_sum, (unsigned long long)sum);
     }
+    hist_add(col_hist, sort_bucket(cols), valid);      // the size classes of the stage-2 ordering
     if (!valid) return;
     const uint32_t item = r * 2u + (uint32_t)dir;
     uint4 *dst = reinterpret_cast<uint4 *>(wins + item);
     const uint4 *src = reinterpret_cast<const uint4 *>(&wl);
     dst[0] = src[0]; dst[1] = src[1];
     wcols[item] = cols;
-    item_ids[item] = item;
 }
 
 // ------------------------------------------------------------------------------------
@@ -296,7 +373,7 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
     // with a job list (stage 2a ran) the jobs are its entries, else every pair of every item
     const uint32_t n_jobs = jobs ? counters[5] : n_items * na;
     const int type = T.type;
-    uint32_t *job_counter = counters + 0, *res_count = counters + 1, *work_count = counters + 2;
+    uint32_t *job_counter = counters + 0, *res_count = counters + 1, *work_count = counters + 2, *wide_count = counters + 3;
 
     for (;;) {
         uint32_t base = 0;
@@ -345,23 +422,34 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
             if (lane == 0) rb = atomicAdd(res_count, (uint32_t)__popc(mh));
             rb = __shfl_sync(0xffffffffu, rb, 0);
             const uint32_t slot = rb + (uint32_t)__popc(mh & lanemask_lt());
-            const uint32_t mn = __ballot_sync(0xffffffffu, need);
-            uint32_t wb = 0;
+            // tasks for the band resolver go to the front half of `work`, the few it cannot take (end
+            // cells spread over too many diagonals, very long scans) to the back half
+            const bool wide = need && !task_band_ok(type, m, T.k[a], (int)n,
+                                                    Task{r, 0u, L.h.jf, L.h.jl, L.h.i1, L.h.i2, 0u, 0});
+            const uint32_t mn = __ballot_sync(0xffffffffu, need && !wide);
+            const uint32_t mw = __ballot_sync(0xffffffffu, wide);
+            uint32_t wb = 0, xb = 0;
             if (mn) {
                 if (lane == 0) wb = atomicAdd(work_count, (uint32_t)__popc(mn));
                 wb = __shfl_sync(0xffffffffu, wb, 0);
             }
-            // A pair beyond the arenas is dropped: the final res_count (>= work_count) says so to the host,
-            // which then runs the batch again with worst-case arenas (orc_api.cu grow_pair_arenas).  The
-            // work position and the result slot come from two counters that other warps interleave, so each
+            if (mw) {
+                if (lane == 0) xb = atomicAdd(wide_count, (uint32_t)__popc(mw));
+                xb = __shfl_sync(0xffffffffu, xb, 0);
+            }
+            // A pair beyond the arenas is dropped: the final res_count (>= the task counts) says so to the
+            // host, which then runs the batch again with worst-case arenas (orc_api.cu grow_pair_arenas).  The
+            // work position and the result slot come from counters that other warps interleave, so each
             // is checked on its own; a task whose result has no slot is marked so that the resolver skips it.
-            const uint32_t wpos = wb + (uint32_t)__popc(mn & lanemask_lt());
+            const uint32_t wpos = wide ? cap_pairs + xb + (uint32_t)__popc(mw & lanemask_lt())
+                                       : wb + (uint32_t)__popc(mn & lanemask_lt());
             if (need) {
-                if (wpos < cap_pairs) {
+                if (wpos < (wide ? 2u * cap_pairs : cap_pairs)) {
                     Task t;
                     t.read = r; t.lane = (uint32_t)(a + (int)na * (int)(item & 1u));
                     t.jf = L.h.jf; t.jl = L.h.jl; t.i1 = L.h.i1; t.i2 = L.h.i2;
-                    t.slot = slot < cap_pairs ? slot : 0xFFFFFFFFu; t.pad_ = 0;
+                    t.slot = slot < cap_pairs ? slot : 0xFFFFFFFFu;
+                    t.pad_ = task_anchors(L) | (wide ? (int32_t)TASK_WIDE : 0);
                     work[wpos] = t;
                 }
             } else if (has && slot < cap_pairs) {
@@ -431,6 +519,71 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------
+// The band resolver (orc_core.cuh band_*): one thread per task, its column ring (8 bytes per column) in
+// shared memory, entry c of thread t at ring[c * BAND_THREADS + t]: the lanes of a warp scan in lockstep
+// and store one contiguous 256-byte row per column, and a 64-bit access of any 16 lanes to any rows hits
+// 16 different bank pairs, so the walks read without conflicts as well.  Only the banks of the 64-bit match
+// table that the round uses are staged next to the ring; the acceptance limits and the packed adapter
+// codes, touched a few times per task, are read through L1 from the table in global memory.
+constexpr int BAND_THREADS = 64;
+inline size_t band_smem_bytes(int n_lanes)
+{
+    return (size_t)((n_lanes + 31) / 32) * 4096u + (size_t)BAND_COLS * BAND_THREADS * sizeof(BandEntry);
+}
+
+__global__ void __launch_bounds__(BAND_THREADS)
+resolve_band_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
+                    const View *__restrict__ views, const Task *__restrict__ work,
+                    const uint32_t *__restrict__ work_count, PairResult *__restrict__ results,
+                    unsigned long long *__restrict__ best_key, uint32_t cap_pairs)
+{
+    extern __shared__ __align__(16) unsigned char s_band[];
+    const int n_banks = (tab->n_lanes + 31) / 32;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&tab->peq[0][0][0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_band);
+        for (int i = threadIdx.x; i < n_banks * 256; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const RoundTable &T = *tab;
+    BandRing ring;
+    ring.p = reinterpret_cast<BandEntry *>(s_band + (size_t)n_banks * 4096u) + threadIdx.x;
+    ring.stride = BAND_THREADS;
+    const uint32_t n = min(*work_count, cap_pairs);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    for (uint32_t base = first; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t t = base + lane;
+        bool act = t < n;
+        Task task;
+        View v;
+        BandCtx C;
+        if (act) {
+            task = work[t];
+            act = task.slot != 0xFFFFFFFFu;          // its result had no slot (arena overflow): skipped
+        }
+        if (act) {
+            v = views[task.read];
+            band_begin(W, v, T, task, C, ring, reinterpret_cast<const char *>(s_band) + (size_t)(task.lane >> 5) * 4096u);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, act);      // also the meeting point
+        if (act) {
+            PairResult res;
+            res.has = 0; res.ref_start = res.ref_stop = res.query_start = res.query_stop = 0;
+            res.score = res.errors = 0; res.pad_ = 0;
+            band_end(W, v, C, res, ring, mask);
+            results[task.slot] = res;
+            if (res.has) {
+                const int a = (int)task.lane % T.n_adapters;
+                const int o = ((int)task.lane / T.n_adapters) ^ (int)(v.rc & 1u);
+                atomicMax(best_key + (size_t)task.read * 2 + o,
+                          (unsigned long long)pack_key(res.score, res.errors, a, task.slot));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Anchored no-indel round: one thread per (read, orientation); touches m bytes per read.
 __global__ void __launch_bounds__(128)
 anchored_kernel(const AnchoredTable *__restrict__ tab, const uint8_t *__restrict__ seq,
@@ -465,7 +618,7 @@ anchored_kernel(const AnchoredTable *__restrict__ tab, const uint8_t *__restrict
 // ------------------------------------------------------------------------------------
 // select: also derives, after the last round, the bin id and the FASTQ record size.
 struct SelectArgs {
-    const RoundTable *tab;
+    int type, revcomp;          // of the round (RoundTable.type / .revcomp)
     const View *views_in;
     View *views_out;
     const Match *prev;          // matches of the previous round (nullptr in round 1)
@@ -482,17 +635,11 @@ struct SelectArgs {
     int32_t *bin;
     uint32_t *out_len, *rec_bytes;
     unsigned long long *next_bases;   // sum of the view lengths that enter the next round (or nullptr)
+    uint32_t *next_len_hist;          // size classes of those lengths for the next round's ordering (or nullptr)
 };
 
 __global__ void __launch_bounds__(128) select_kernel(SelectArgs A)
 {
-    __shared__ __align__(16) RoundTable T;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.tab);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
-        for (int i = threadIdx.x; i < (int)(sizeof(RoundTable) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = r < A.n_reads;
     View v;
@@ -507,13 +654,15 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs A)
         uint64_t key[2];
         key[0] = A.best_key[(size_t)r * 2];
         key[1] = A.best_key[(size_t)r * 2 + 1];
-        select_read(T, v, key, A.results, mt, next);
+        select_read(A.type, A.revcomp, v, key, A.results, mt, next);
     }
     if (A.next_bases != nullptr) {
         const uint32_t add = (valid && mt.adapter >= 0) ? next.len : 0u;
         const uint32_t sum = __reduce_add_sync(0xffffffffu, add);
         if ((threadIdx.x & 31) == 0 && sum) atomicAdd(A.next_bases, (unsigned long long)sum);
     }
+    if (A.next_len_hist != nullptr)     // what bucket_scatter_kernel<true> will read as this read's key
+        hist_add(A.next_len_hist, sort_bucket(mt.adapter >= 0 ? next.len : 0u), valid);
     if (!valid) return;
     A.out[r] = mt;
     A.views_out[r] = next;

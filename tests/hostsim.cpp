@@ -17,7 +17,9 @@
 
 using namespace orc;
 
-static uint64_t g_pairs[2], g_kept[2], g_seeded[2];
+static uint64_t g_pairs[2], g_kept[2], g_seeded[2], g_band, g_wide;
+// tasks resolved by the band resolver / the wide one
+extern "C" void hostsim_resolved(uint64_t *out) { out[0] = g_band; out[1] = g_wide; }
 extern "C" void hostsim_stats(uint64_t *out) { out[0] = g_pairs[0]; out[1] = g_kept[0]; out[2] = g_pairs[1]; out[3] = g_kept[1]; }
 // reads whose stage 1 went through the seed table, per round
 extern "C" void hostsim_seeded(uint64_t *out) { out[0] = g_seeded[0]; out[1] = g_seeded[1]; }
@@ -72,6 +74,9 @@ extern "C" int hostsim_demux(int n_rounds,
     for (uint64_t i = 0; i < n_bytes; i++) W[i >> 3] |= (uint32_t)lut[seq[i]] << ((i & 7) * 4);
 
     ColRing *ring = new ColRing;
+    BandEntry *band = new BandEntry[BAND_COLS];
+    BandRing bring; bring.p = band; bring.stride = 1;
+    const bool force_wide = (filter_mode_in & 8) != 0;
     n_tasks[0] = n_tasks[1] = 0;
     n_columns[0] = n_columns[1] = 0;
     for (uint32_t r = 0; r < n_reads; r++) {
@@ -92,7 +97,7 @@ extern "C" int hostsim_demux(int n_rounds,
                     results.push_back(pr);
                 }
                 View next;
-                select_read(R, v, keys, results.data(), *out[rd], next);
+                select_read(R.type, R.revcomp, v, keys, results.data(), *out[rd], next);
                 v = next;
                 if (out[rd]->adapter < 0) break;
                 continue;
@@ -134,7 +139,15 @@ extern "C" int hostsim_demux(int n_rounds,
                     } else {
                         Task t; t.read = r; t.lane = (uint32_t)lane;
                         t.jf = L.h.jf; t.jl = L.h.jl; t.i1 = L.h.i1; t.i2 = L.h.i2; t.slot = (uint32_t)results.size();
-                        resolve_pair(W, v, R, t, pr, *ring);
+                        t.pad_ = task_anchors(L);
+                        // what scan_kernel decides per task: the band resolver when the task fits it
+                        if (!force_wide && task_band_ok(R.type, R.m[a], R.k[a], (int)v.len, t)) {
+                            band_resolve_pair(W, v, R, t, pr, bring);
+                            g_band++;
+                        } else {
+                            resolve_pair(W, v, R, t, pr, *ring);
+                            g_wide++;
+                        }
                         n_tasks[rd]++;
                     }
                     if (pr.has) {
@@ -145,13 +158,14 @@ extern "C" int hostsim_demux(int n_rounds,
                 }
             }
             View next;
-            select_read(R, v, keys, results.data(), *out[rd], next);
+            select_read(R.type, R.revcomp, v, keys, results.data(), *out[rd], next);
             v = next;
             if (out[rd]->adapter < 0) break;     // 02:75-80: "unknown" never enters round 2
         }
         out_lo[r] = v.lo; out_len[r] = v.len; out_rc[r] = v.rc;
     }
     delete ring;
+    delete[] band;
     delete[] T;
     delete[] AT;
     delete[] ST;

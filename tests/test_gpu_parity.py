@@ -21,17 +21,27 @@ def _engine(n_reads, n_bytes, **kw):
 def _expected_fastq(rs, rec0, rec1, oseq, oqual, olen, n_bins, bin_of):
     """Per-bin FASTQ bytes the reference pipeline would leave on disk (input order kept)."""
     bins = [[] for _ in range(n_bins)]
+    names, noff = rs.names.tobytes(), rs.name_offsets.tolist()
+    sq, ql = oseq.tobytes(), oqual.tobytes()
+    a0 = rec0["adapter"].tolist()
+    a1 = rec1["adapter"].tolist() if rec1 is not None else None
+    rc0 = ((rec0["adapter"] >= 0) & (rec0["is_rc"] != 0)).tolist()
+    rc1 = ((rec1["adapter"] >= 0) & (rec1["is_rc"] != 0)).tolist() if rec1 is not None else None
+    offs, lens = rs.offsets.tolist(), olen.tolist()
     for r in range(rs.n_reads):
-        name = rs.read(r)[0]
-        if rec0["adapter"][r] >= 0 and rec0["is_rc"][r]:
-            name += " rc"
-        if rec1 is not None and rec1["adapter"][r] >= 0 and rec1["is_rc"][r]:
-            name += " rc"
-        o, L = int(rs.offsets[r]), int(olen[r])
-        b = bin_of(int(rec0["adapter"][r]), int(rec1["adapter"][r]) if rec1 is not None else -1)
-        bins[b].append(b"@" + name.encode() + b"\n" + oseq[o:o + L].tobytes() + b"\n+\n" +
-                       oqual[o:o + L].tobytes() + b"\n")
+        name = names[noff[r]:noff[r + 1]]
+        if rc0[r]:
+            name += b" rc"
+        if rc1 is not None and rc1[r]:
+            name += b" rc"
+        o, L = offs[r], lens[r]
+        b = bin_of(a0[r], a1[r] if a1 is not None else -1)
+        bins[b].append(b"@" + name + b"\n" + sq[o:o + L] + b"\n+\n" + ql[o:o + L] + b"\n")
     return [b"".join(x) for x in bins]
+
+
+FULL = os.environ.get("ORC_TEST_FULL", "1") == "1"      # 0: the BASELINE-size tests run on 1/16 of their reads
+NCPU = os.cpu_count() or 8
 
 
 def _check(rs, eng=None):
@@ -121,7 +131,7 @@ def test_slots_and_resident_relaunch():
         assert ra.fastq.tobytes() == ra2.fastq.tobytes()
         assert np.array_equal(ra.bin, ra2.bin)
         t = eng.timings(0)
-        assert t["kernel_launches"] == 21 and t["total_ms"] > 0      # 19 + one seed_kernel per round
+        assert t["kernel_launches"] >= 15 and t["total_ms"] > 0      # counted launch by launch in orc_launch
         tot = eng.counts()
         assert int(tot.sum()) == 2 * a.n_reads + b.n_reads
     finally:
@@ -130,9 +140,11 @@ def test_slots_and_resident_relaunch():
     _check(b)
 
 
-def test_full_size_properties():
-    """BASELINE config 2 size (1M reads): size-independent invariants instead of the oracle."""
-    rs = synth.generate(1 << 20, 300, 900, seed=1002)
+def test_config2_full_size_every_read():
+    """BASELINE configs[1] at its full size (1 Mi COI reads, seed 1002): the oracle on EVERY read -- all eight
+    match fields of both rounds, trimmed length, bin, and the bytes of all 169 bins -- plus the
+    size-independent invariants."""
+    rs = synth.generate((1 << 20) if FULL else (1 << 16), 300, 900, seed=1002, workers=min(8, NCPU))
     eng = _engine(rs.n_reads, rs.seq.shape[0], want_matches=True)
     try:
         res = eng.run(rs)
@@ -157,17 +169,93 @@ def test_full_size_properties():
         assert np.all(alen >= 3)
     # unknown in round 1 never enters round 2
     assert np.all(m1["adapter"][m0["adapter"] < 0] == -1)
-    # sampled oracle parity on 4096 reads spread over the batch
-    idx = np.arange(0, n, n // 4096)[:4096]
-    recs = [rs.read(int(i)) for i in idx]
-    sub = synth.from_records(recs)
-    rec0, rec1, _, _, olen = H.run_oracle(H.m13_rounds(), sub)
-    assert H.diff_matches(rec0, m0[idx])[1] == 0
-    assert H.diff_matches(rec1, m1[idx])[1] == 0
+    # the oracle on every read
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(H.m13_rounds(), rs, n_threads=NCPU)
+    idx, nbad = H.diff_matches(rec0, m0)
+    assert nbad == 0, ("round 1", nbad, idx)
+    idx, nbad = H.diff_matches(rec1, m1)
+    assert nbad == 0, ("round 2", nbad, idx)
+    assert np.array_equal(res.out_len, olen)
+    exp_bin = ((rec0["adapter"] + 1) + 13 * (rec1["adapter"] + 1)).astype(np.int32)
+    assert np.array_equal(res.bin, exp_bin)
+    exp = _expected_fastq(rs, rec0, rec1, oseq, oqual, olen, 169, lambda a, b: (a + 1) + 13 * (b + 1))
+    for b in range(169):
+        assert res.bin_bytes(b) == exp[b], "bin %d bytes differ" % b
     # truth agreement is high (not exact: errors can push a read to unknown)
     t5 = rs.truth["sp5"]
     ok = (m0["adapter"] + 1 == t5) | (t5 == 0)
     assert ok.mean() > 0.95
+
+
+def test_config3_rrna_256k_every_read():
+    """BASELINE configs[2] (rRNA-cistron reads 1-3.5 kb, seed 1003) on 256 Ki reads, the oracle on every read
+    (the full 10 M reads would keep the CPU oracle busy for about an hour; SURVEY 8d allows a subsample)."""
+    rs = synth.generate((1 << 18) if FULL else (1 << 14), 1000, 3500, seed=1003, workers=min(8, NCPU))
+    with _engine(rs.n_reads, rs.seq.shape[0], want_matches=True) as eng:
+        res = eng.run(rs)
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(H.m13_rounds(), rs, n_threads=NCPU)
+    idx, nbad = H.diff_matches(rec0, res.matches[0])
+    assert nbad == 0, ("round 1", nbad, idx)
+    idx, nbad = H.diff_matches(rec1, res.matches[1])
+    assert nbad == 0, ("round 2", nbad, idx)
+    assert np.array_equal(res.out_len, olen)
+    exp = _expected_fastq(rs, rec0, rec1, oseq, oqual, olen, 169, lambda a, b: (a + 1) + 13 * (b + 1))
+    for b in range(169):
+        assert res.bin_bytes(b) == exp[b], "bin %d bytes differ" % b
+
+
+def test_config4_both_arms_full_size():
+    """BASELINE configs[3] on 1 Mi reads (seed 1004, bare index at offset 0), BOTH arms against the oracle on
+    every read: `-g ^file:M13_variable_indices_all.fa --no-indels` (anchored Hamming path) and
+    `-g file:M13_variable_indices_all.fa` (24 unanchored adapters with indels: the 64-bit scan, two lane banks)."""
+    import oracle
+    from orcdemux import m13
+    from orcdemux.lib import ORC_FRONT, ORC_PREFIX
+    var = m13.variable_all()
+    names, seqs = [n for n, _ in var], [s for _, s in var]
+    rs = synth.generate((1 << 20) if FULL else (1 << 16), 300, 900, seed=1004, anchored=True, workers=min(8, NCPU))
+    for kind, okind, indels in ((ORC_PREFIX, oracle.PREFIX, False), (ORC_FRONT, oracle.FRONT, True)):
+        rnd = E.Round(names, seqs, kind, 0.1, 3, indels, True)
+        with E.Engine([rnd], max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]), n_slots=1) as eng:
+            res = eng.run(rs)
+            assert eng.n_bins == 25
+        sets = [(oracle.AdapterSet(seqs, okind, 0.1, 3, indels=indels), 1)]
+        rec0, _, oseq, oqual, olen = oracle.demux_batch(sets, rs.seq, rs.qual, rs.offsets, rs.lengths, n_threads=NCPU)
+        idx, nbad = H.diff_matches(rec0, res.matches[0])
+        assert nbad == 0, (kind, nbad, idx)
+        assert np.array_equal(res.out_len, olen)
+        assert np.array_equal(res.bin, (rec0["adapter"] + 1).astype(np.int32))
+        exp = _expected_fastq(rs, rec0, None, oseq, oqual, olen, 25, lambda a, b: a + 1)
+        for b in range(25):
+            assert res.bin_bytes(b) == exp[b], "arm %d bin %d bytes differ" % (kind, b)
+        assert (rec0["adapter"] >= 0).mean() > 0.5 and (rec0["adapter"] >= 16).sum() > 1000
+
+
+def test_pair_arena_overflow_is_rerun():
+    """A batch with more candidate pairs than the slot's arenas hold is detected by its counters and run again
+    with worst-case arenas (orc_api.cu grow_pair_arenas): same results as without the squeeze."""
+    import random
+    import test_hostsim as TH
+    rnd = random.Random(31)
+    f = [s for _, s in synth.m13.sp5_forward()]
+    b = [s for _, s in synth.m13.sp27_reverse_rc()]
+    rs = TH._adversarial_reads(rnd, f, b, 4000)
+    ref = _check(rs)
+    os.environ["ORC_PAIR_CAP"] = "64"
+    try:
+        eng = _engine(rs.n_reads, rs.seq.shape[0], n_slots=2)
+    finally:
+        os.environ.pop("ORC_PAIR_CAP", None)
+    try:
+        got = _check(rs, eng)           # first run overflows and is repeated inside orc_wait
+        assert got.fastq.tobytes() == ref.fastq.tobytes()
+        eng.submit(1, rs)               # the second slot grows on its own
+        again = eng.wait(1)
+        assert again.fastq.tobytes() == ref.fastq.tobytes()
+        again = eng.run(rs)             # the grown arenas are kept
+        assert again.fastq.tobytes() == ref.fastq.tobytes()
+    finally:
+        eng.close()
 
 
 def test_anchored_hamming_path_config4():
@@ -200,7 +288,7 @@ def test_anchored_hamming_path_config4():
 
 def test_adversarial_and_random_adapter_sets():
     """The kernels (not only their host simulation) on adversarial reads and random adapter sets:
-    shared prefixes of any length (trigger filter on or off), 1..16 adapters of 3..64 nt, error
+    shared prefixes of any length (trigger filter on or off), 1..32 adapters of 3..64 nt, error
     rates up to 0.4, both adapter types in either round order, with and without --rc."""
     import random
     import oracle
@@ -208,7 +296,8 @@ def test_adversarial_and_random_adapter_sets():
     from orcdemux.lib import ORC_BACK, ORC_FRONT
     rnd = random.Random(2024)
     for trial in range(10):
-        nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
+        nf = rnd.randint(1, 32)
+        nb = rnd.randint(1, min(32, 512 // (nf + 1) - 1))        # at most 512 bins (MAX_BINS)
         mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice([3, 8, 17, 20, 33, 57, 64])))
         shared = mk()[:rnd.choice([4, 10, 17, 25, 32])]
         f = [((shared if rnd.random() < 0.8 else "") + mk())[:64] for _ in range(nf)]
@@ -298,6 +387,7 @@ def test_seeded_stage1_random_adapter_sets():
         rounds = [E.Round([str(i) for i in range(len(x[0]))], x[0], ORC_FRONT if x[1] == oracle.FRONT else ORC_BACK,
                           x[2], x[3], True, bool(x[4])) for x in spec]
         rec = H.run_oracle(spec, rs)
+        seen = {}
         for no_seed in ("0", "1"):
             os.environ["ORC_NO_SEED"] = no_seed
             try:
@@ -309,9 +399,8 @@ def test_seeded_stage1_random_adapter_sets():
             assert H.diff_matches(rec[0], res.matches[0])[1] == 0, (trial, no_seed, "round 1")
             assert H.diff_matches(rec[1], res.matches[1])[1] == 0, (trial, no_seed, "round 2")
             assert np.array_equal(res.out_len, rec[4])
-            if no_seed == "1":
-                assert launches == 19
-        # (with seeds the count is 19 + the rounds whose table could be built: checked for M13 above)
+            seen[no_seed] = launches
+        assert 0 <= seen["0"] - seen["1"] <= 2          # one seed_kernel per round whose table could be built
 
 
 def test_long_reads_and_capacity_errors():

@@ -9,7 +9,7 @@ iupac = len(sys.argv) > 3 and sys.argv[3] == "iupac"     # every adapter gets IU
 rnd = random.Random(seed)
 t0=time.time(); total=0
 for trial in range(trials):
-    nf, nb = rnd.randint(1, 16), rnd.randint(1, 16)
+    nf, nb = rnd.randint(1, 32), rnd.randint(1, 32)
     long_only = rnd.random() < 0.45       # long adapters at low error rates: stage 1 goes through the seed table
     lens = [40, 48, 57, 59, 64, 64] if long_only else [3, 5, 8, 12, 17, 20, 33, 40, 57, 64]
     mk = lambda: "".join(rnd.choice("ACGT") for _ in range(rnd.choice(lens)))
@@ -73,4 +73,6 @@ for trial in range(trials):
 import ctypes
 sd = (ctypes.c_uint64 * 2)()
 H.hostsim().hostsim_seeded(sd)
-print("ok seed",seed,"reads",total,"seeded (read, round) passes",sd[0],sd[1],"time",time.time()-t0)
+rb = (ctypes.c_uint64 * 2)()
+H.hostsim().hostsim_resolved(rb)
+print("ok seed",seed,"reads",total,"seeded (read, round) passes",sd[0],sd[1],"resolver tasks band/wide",rb[0],rb[1],"time",time.time()-t0)
