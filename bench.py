@@ -4,29 +4,42 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (B200, liborcdemux.so)
     python bench.py --impl reference [...]                       the reference's CPU path
 
-A "step" is one pass of the whole hot path (pack, round-1 scan/resolve/select, round-2
-scan/resolve/select, bin partition, FASTQ emit) over one batch of synthetic reads.  At N=1
-the workload is BASELINE configs[1]: 1 Mi synthetic COI-length reads (300-900 nt, seed 1002),
-full two-round demux + trim.  With N>1 (torchrun, one rank per GPU) every rank runs its own
-shard of the same size (weak scaling, seeds (1005<<32)+rank as in SURVEY 8d config 5); the
-only collective is the final per-bin count gather (all_reduce of n_bins counters).
+A "step" is one pass of the whole hot path (pack, round-1 seed/trigger/filter/scan/resolve/select,
+round 2 the same, bin partition, FASTQ emit) over one batch of 1 Mi synthetic reads.
 
-`value`   reads/s with the batch resident in HBM (kernels only), CUDA events on the library's
-          stream, max over ranks.
-`e2e`     the same metric through the C ABI with host buffers: every step copies the inputs
-          from pinned host memory and the results (FASTQ text, bins, matches) back.
-`roofline` for the dominant kernel (the bit-parallel scan): algorithmic DP cells per second
-          against the INT32 ALU-pipe peak measured on this GPU by orc_measure_int32_peak().
-`cpu_baseline` / `--impl reference`: the reference's own implementation of this path is
-          cutadapt 4.9, which is neither vendored in the reference nor installable here, so the
-          CPU arm is the oracle's C restatement of it ("port"), all host threads.
+N = 1   BASELINE configs[1]: 1 Mi synthetic COI-length reads (300-900 nt, numpy generator, seed 1002), full
+        two-round demux + trim; the line also carries short runs of configs[2] and configs[3] (`extra_configs`).
+N > 1   BASELINE configs[4] (torchrun, one rank per GPU): every step of every rank is a DISTINCT shard of 1 Mi
+        reads of the same read model, made on the GPU by orc_synth() with seed (1005 << 32) + shard, shard =
+        rank + world * step, until 100 M reads exist in total (later steps revisit the rank's shards).  All
+        shards are resident in HBM before the timed region.  No data-path collective; the 169 per-bin
+        counters are all-reduced at the end, and every rank checks the bins of a sampled part of one of its
+        shards against the CPU oracle.
+
+`value`   reads/s with the batches resident in HBM (kernels only), CUDA events on the library's stream, max
+          over ranks.
+`e2e`     the same metric through the C ABI with host buffers: every step copies its inputs from pinned host
+          memory and its results (the FASTQ text of the 96 bins the reference script keeps, bin ids, trimmed
+          lengths, counters) back.  `e2e.link` says how much of the host<->device ceiling measured in the same
+          run (all ranks copying at once) that is.
+`roofline`  the kernel that takes the largest share of the step, against its own roof; `roofline_kernels`
+          lists every kernel.  DP kernels: DP cells (or seed probes) really executed x ALU-pipe instructions
+          per cell column (counted in the SASS, profiles/README.md) against the LOP3 issue rate measured in
+          this run by orc_measure_int32_peak().  The exact filters skip most of the algorithmic cells
+          (2 * 12 * m * n per read and round); that factor is `algorithmic_speedup`, not a
+          roofline fraction.  Copy kernels: algorithmic bytes against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` / `--impl reference`: real cutadapt if one is on PATH / importable / under baseline/_ref
+          (kind "reference"), else the oracle's C restatement of it (kind "port"), all host threads.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -41,13 +54,13 @@ for p in (ROOT, PKG):
 METRIC = "reads/sec demuxed (2-round SP5xSP27)"
 METRIC_R1 = "reads/sec demuxed (round 1, SP5 5' indices)"        # --config 1 only
 UNIT = "reads/s"
-# ALU-pipe instructions per DP column of one (read, adapter, orientation) pair in
-# scan_kernel's inner loop, counted in the SASS (profiles/README.md); a column is m cells.
-SCAN_ALU_INSTR_PER_COLUMN = 24.0
-# DRAM traffic of the scan stages (seed_kernel + trigger_kernel + filter_kernel + scan_kernel, both rounds)
-# per read, from the ncu --set full capture profiles/r1n_main_raw.csv (dram__bytes_read.sum +
-# dram__bytes_write.sum of the eight launches at 262 144 COI reads, divided by the reads)
-SCAN_DRAM_BYTES_PER_READ = 3.157e3
+TARGET_READS = 100_000_000          # BASELINE configs[4]
+
+# ALU-pipe instructions (LOP3 / IADD3 / SHF / PRMT / ISETP ...; IMAD runs on the FMA pipe) per column of the
+# inner loops, counted in the SASS of this build (profiles/README.md, "SASS counts"), and the rows a column
+# step updates.  peak cells/s of a kernel = measured LOP3 lane-op/s / ALU instructions per column x rows.
+ALU_PER_COLUMN = {"filter": 12.0, "scan": 24.0, "resolve_band": 20.0, "seed": 2.25}
+ROWS = {"filter": 32.0, "scan": None, "resolve_band": 32.0, "seed": 1.0}      # scan: the adapter length m
 
 
 def parse_args():
@@ -62,12 +75,15 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
+    ap.add_argument("--no-extra", action="store_true", help="skip the short configs[2] / configs[3] runs")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json configs[]: 1 = round 1 only (SP5 5' demux) on 100 k reads, the reference's "
-                         "own CPU-runnable case; 2 = 1 Mi COI reads two-round (default, the metric's config), "
+                         "own CPU-runnable case; 2 = 1 Mi COI reads two-round (default at N = 1, the metric's config), "
                          "3 = rRNA-cistron reads 1-3.5 kb two-round, 4 = anchored --no-indels Hamming path "
-                         "(24 M13 variable indices) on reads with the bare index at offset 0")
+                         "(24 M13 variable indices) on reads with the bare index at offset 0, 5 = distinct shards "
+                         "made on the GPU (the default under torchrun)")
     ap.add_argument("--sub-batches", type=int, default=8)
+    ap.add_argument("--oracle-sample", type=int, default=32768, help="reads of one shard per rank checked against the oracle (config 5)")
     a = ap.parse_args()
     if a.config == 1 and a.reads == 1 << 20:
         a.reads = 100000
@@ -139,16 +155,95 @@ def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured"
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- CPU arms
+def find_real_cutadapt():
+    """(kind, handle): a real cutadapt executable (not this repo's shim) or an importable package; else (None, None)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    shim_dir = os.path.realpath(os.path.join(PKG, "bin"))
+    for d in os.environ.get("PATH", "").split(os.pathsep) + [os.path.join(ref, "bin")]:
+        if not d or os.path.realpath(d) == shim_dir:
+            continue
+        p = os.path.join(d, "cutadapt")
+        if os.path.isfile(p) and os.access(p, os.X_OK):
+            try:
+                with open(p, "rb") as fh:
+                    if b"orcdemux" in fh.read(4096):
+                        continue
+            except OSError:
+                continue
+            return "exe", [p]
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.append(ref)
+    try:
+        import importlib.util
+        if importlib.util.find_spec("cutadapt") is not None:
+            return "module", [sys.executable, "-m", "cutadapt"]
+    except Exception:
+        pass
+    return None, None
+
+
+def real_cutadapt_arm(cmd, rs, sub_n, threads, steps, warmup, n_rounds):
+    """Time the reference script's own command lines (02_cutadapt_loop.sh:64-72, 91-103) with a real cutadapt on
+    the first sub_n reads, uncompressed FASTQ on /dev/shm (the I/O-light variant of SURVEY 8d)."""
+    from orcdemux import m13, synth
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix="orc_ref_", dir=base)
+    try:
+        recs = [rs.read(r) for r in range(sub_n)]
+        sub = synth.from_records(recs)
+        inp = os.path.join(tmp, "pychopped_ds.fastq")
+        with open(inp, "wb") as fh:
+            fh.write(sub.to_fastq_bytes())
+        fwd, rev = os.path.join(tmp, "fwd.fa"), os.path.join(tmp, "rev.fa")
+        with open(fwd, "w") as fh:
+            fh.write("".join(">%s\n%s\n" % x for x in m13.sp5_forward()))
+        with open(rev, "w") as fh:
+            fh.write("".join(">%s\n%s\n" % x for x in m13.sp27_reverse_rc()))
+        times = []
+        for it in range(warmup + steps):
+            for d in ("SP5", "SP27"):
+                shutil.rmtree(os.path.join(tmp, d), ignore_errors=True)
+                os.makedirs(os.path.join(tmp, d))
+            t0 = time.perf_counter()
+            subprocess.run(cmd + ["--action=trim", "-e", "0.1", "-j", str(threads), "--rc", "-g", "file:" + fwd,
+                                  "-o", os.path.join(tmp, "SP5", "{name}_ds.fastq"), inp,
+                                  "--json=" + os.path.join(tmp, "SP5", "r1.json")], check=True,
+                           stdout=subprocess.DEVNULL)
+            if n_rounds > 1:
+                for nm, _ in m13.sp5_forward():
+                    subprocess.run(cmd + ["--action=trim", "-e", "0.1", "-j", str(threads), "--rc", "-a", "file:" + rev,
+                                          "-o", os.path.join(tmp, "SP27", "{name}_%s_ds.fastq" % nm),
+                                          os.path.join(tmp, "SP5", nm + "_ds.fastq"),
+                                          "--json=" + os.path.join(tmp, "SP27", nm + ".json")], check=True,
+                                   stdout=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        return times
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def cpu_arm(rs, n_sample, threads, steps, warmup, n_rounds=2):
-    """Time the oracle's C restatement of cutadapt on the first n_sample reads."""
+    """-> (reads, times, kind, how): real cutadapt when there is one, else the oracle's C restatement, on the
+    first n_sample reads."""
+    sub_n = min(n_sample, rs.n_reads)
+    kind, cmd = find_real_cutadapt()
+    if kind is not None:
+        try:
+            times = real_cutadapt_arm(cmd, rs, sub_n, threads, steps, warmup, n_rounds)
+            return sub_n, times, "reference", "real cutadapt (%s) -j %d, the script's own command lines, uncompressed FASTQ on /dev/shm" % (" ".join(cmd), threads)
+        except Exception as e:          # a broken install must not take the bench line down
+            sys.stderr.write("real cutadapt failed (%s): falling back to the port\n" % e)
     import oracle
     from orcdemux import m13
-    sub_n = min(n_sample, rs.n_reads)
+    oracle.build()
     end = int(rs.offsets[sub_n - 1] + rs.lengths[sub_n - 1]) if sub_n else 0
     seq, qual = rs.seq[:end], rs.qual[:end]
     off, ln = rs.offsets[:sub_n], rs.lengths[:sub_n]
@@ -161,7 +256,192 @@ def cpu_arm(rs, n_sample, threads, steps, warmup, n_rounds=2):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return sub_n, times
+    return sub_n, times, "port", ("oracle/cutadapt_oracle.c (restated cutadapt 4.9: Ukkonen-banded DP, no k-mer prefilter, "
+                                  "gcc -O3 -march=x86-64-v3, scratch buffers hoisted, %d pthreads); cutadapt itself is not "
+                                  "vendored in the reference and not installed here" % threads)
+
+
+# --------------------------------------------------------------------------- pieces of our arm
+def scripts_final_tree_drop(n5=12, n27=12):
+    """drop_bins of the tree 02_cutadapt_loop.sh leaves (02:107-119): no 'unknown' of either round, no SP27_009..012."""
+    drop = np.zeros((n5 + 1) * (n27 + 1), dtype=np.uint8)
+    for b in range(drop.shape[0]):
+        i5, i27 = b % (n5 + 1) - 1, b // (n5 + 1) - 1
+        if i5 < 0 or i27 < 0 or i27 >= 8:
+            drop[b] = 1
+    return drop
+
+
+def split_subbatches(E, synth, rs, n_sub):
+    """A ReadSet cut into n_sub contiguous sub-batches in pinned memory (what a FASTQ reader hands over)."""
+    per = (rs.n_reads + n_sub - 1) // n_sub
+    subs = []
+    for i in range(n_sub):
+        lo, hi = i * per, min(rs.n_reads, (i + 1) * per)
+        if lo >= hi:
+            break
+        b0 = int(rs.offsets[lo])
+        b1 = int(rs.offsets[hi - 1]) + int(rs.lengths[hi - 1])
+        n0, n1 = int(rs.name_offsets[lo]), int(rs.name_offsets[hi])
+        off = E.pinned_empty(hi - lo, np.uint64)
+        off[...] = rs.offsets[lo:hi] - np.uint64(b0)
+        noff = E.pinned_empty(hi - lo + 1, np.uint64)
+        noff[...] = rs.name_offsets[lo:hi + 1] - np.uint64(n0)
+        subs.append(synth.ReadSet(rs.seq[b0:b1], rs.qual[b0:b1], off, rs.lengths[lo:hi], rs.names[n0:n1], noff, {}))
+    return subs, per
+
+
+def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches, S=4):
+    """`steps` steps through orc_submit/orc_wait with host buffers; step k streams the sub-batches of
+    step_batches[k % len(step_batches)] over S slots.  -> (seconds, h2d bytes per step, d2h bytes per step,
+    reads, cumulative counts)."""
+    per = max(x.n_reads for sb in step_batches for x in sb)
+    eng = E.Engine(rounds, device=device, max_reads=per,
+                   max_bytes=max(int(x.seq.shape[0]) for sb in step_batches for x in sb) + 64,
+                   max_name_bytes=max(int(x.names.shape[0]) for sb in step_batches for x in sb) + 64, n_slots=S,
+                   emit_fastq=True, want_matches=want_matches, drop_bins=drop)
+    h2d = sum(int(x.seq.nbytes + x.qual.nbytes + x.offsets.nbytes + x.lengths.nbytes + x.names.nbytes +
+                  x.name_offsets.nbytes) for x in step_batches[0])
+    state = {"inflight": [], "k": 0, "reads": 0, "d2h": 0}
+
+    def take(slot):
+        r = eng.wait(slot, copy=False)
+        state["reads"] += r.n_reads
+        state["d2h"] += int(r.fastq.nbytes + r.bin.nbytes + r.out_len.nbytes + r.bin_counts.nbytes +
+                            r.bin_offsets.nbytes + sum(m.nbytes for m in r.matches))
+
+    def pump(sub):
+        if len(state["inflight"]) == S:
+            take(state["inflight"].pop(0))
+        slot = state["k"] % S
+        eng.submit(slot, sub)
+        state["inflight"].append(slot)
+        state["k"] += 1
+
+    def drain():
+        while state["inflight"]:
+            take(state["inflight"].pop(0))
+
+    for sub in step_batches[0]:                 # warm the copy paths: one untimed step
+        pump(sub)
+    drain()
+    state.update(reads=0, d2h=0)
+    barrier()
+    w0 = time.perf_counter()
+    for k in range(steps):
+        for sub in step_batches[k % len(step_batches)]:
+            pump(sub)
+    drain()
+    barrier()
+    secs = time.perf_counter() - w0
+    counts = eng.counts().astype(np.int64)
+    eng.close()
+    return secs, h2d, state["d2h"] // max(steps, 1), state["reads"], counts
+
+
+def measure_link(torch, barrier, n_bytes=1 << 29):
+    """Host<->device copy ceiling of THIS rank while every rank does the same (pinned 512 MiB blocks):
+    H2D alone, D2H alone, both directions at once (GB/s per direction)."""
+    a = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    b = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    d2 = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    out = {}
+    for name in ("h2d", "d2h", "both"):
+        best = None
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            if name in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d.copy_(a, non_blocking=True)
+            if name in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    b.copy_(d2, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if rep and (best is None or dt < best):
+                best = dt
+        out[name + "_gbs"] = n_bytes / best / 1e9
+    return out
+
+
+def kernel_table(t, rounds, alu_peak, hbm, hbm_how, m_rows, seed_columns):
+    """roofline_kernels: every kernel of the last step with its time, share and roof."""
+    rows = []
+    total = t["total_ms"]
+    n_rounds = len(rounds)
+
+    def add(name, ms, bound=None, achieved=None, peak=None, unit=None, how=None):
+        if ms <= 0:
+            return
+        r = {"kernel": name, "ms": ms, "share": ms / total if total else None, "bound": bound,
+             "achieved": achieved, "peak": peak, "unit": unit,
+             "frac": (achieved / peak) if (achieved is not None and peak) else None}
+        if how:
+            r["how"] = how
+        rows.append(r)
+
+    def alu(name, key, ms, cols_times_rows, rows_per_col):
+        peak = alu_peak / ALU_PER_COLUMN[key] * rows_per_col / 1e9
+        add(name, ms, "int32_alu", cols_times_rows / (ms * 1e-3) / 1e9 if ms > 0 else None, peak, "GCUPS",
+            "executed cells / time vs LOP3 rate / %.4g ALU-pipe instr per column x %.4g rows" % (ALU_PER_COLUMN[key], rows_per_col))
+
+    add("pack_kernel", t["pack_ms"], "hbm", t["pack_bytes"] / (t["pack_ms"] * 1e-3) / 1e9 if t["pack_ms"] > 0 else None,
+        hbm, "GB/s", "1.5 B per input byte; " + hbm_how)
+    for r in range(n_rounds):
+        k = t["kernel_ms"][r]
+        tag = " r%d" % (r + 1)
+        add("bucket_scatter_kernel<reads>" + tag, k["sort_reads"], "hbm")
+        if k["seed"] > 0:
+            alu("seed_kernel" + tag, "seed", k["seed"], float(seed_columns[r]), 1.0)
+        add("trigger_kernel" + tag, k["trigger"], "int32_alu")
+        add("bucket_scatter_kernel<items>" + tag, k["sort_items"], "hbm")
+        if k["filter"] > 0:
+            # every adapter's block rows over the window columns (pairs that pass leave early: an upper bound)
+            block_rows = float(sum(min(32, len(q)) for q in rounds[r].sequences))
+            alu("filter_kernel" + tag, "filter", k["filter"], block_rows * float(t["window_columns"][r]), 32.0)
+        if k["scan"] > 0 and t["cells_2b"][r]:
+            alu("scan_kernel" + tag, "scan", k["scan"], float(t["cells_2b"][r]), m_rows[r])
+        add("resolve_band_kernel" + tag, k["resolve_band"], "int32_alu")
+        add("resolve_kernel (wide)" + tag, k["resolve_wide"], "latency")
+        add("select_kernel" + tag, k["select"], "hbm")
+    add("bin_count/scan/offsets/place", t["bin_ms"], "hbm")
+    add("emit_kernel", t["emit_ms"], "hbm", t["emit_bytes"] / (t["emit_ms"] * 1e-3) / 1e9 if t["emit_ms"] > 0 else None,
+        hbm, "GB/s", "every FASTQ byte read once and written once; " + hbm_how)
+    return rows
+
+
+def device_resident(E, eng, rs_list, steps, warmup, barrier, sampler):
+    """K launches over the resident batches (slot k % len); device time on the library's stream."""
+    n = len(rs_list)
+    for k in range(warmup):
+        eng.launch(k % n)
+    for s in range(n):
+        eng.sync(s)
+    barrier()
+    if sampler:
+        sampler.start()
+    # the slots have their own streams: time on slot 0's stream and make the launches of the other slots
+    # part of it by running them in order (sync before the next slot starts)
+    wall0 = time.perf_counter()
+    dev_ms = 0.0
+    if n == 1:
+        eng.timer_start(0)
+        for _ in range(steps):
+            eng.launch(0)
+        dev_ms = eng.timer_stop(0)
+    else:
+        for k in range(steps):
+            s = k % n
+            eng.timer_start(s)
+            eng.launch(s)
+            dev_ms += eng.timer_stop(s)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    clocks = sampler.stop() if sampler else None
+    return dev_ms, wall_ms, clocks
 
 
 def main():
@@ -183,6 +463,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_gpus = max(args.gpus, world)
     ncpu = os.cpu_count() or 1
+    if world > 1 and args.config == 2:
+        args.config = 5
 
     from orcdemux import synth
 
@@ -190,14 +472,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        import oracle
-        oracle.build()
         threads = ncpu
         one_round = args.config == 1
         n_sample = args.cpu_sample or (100000 if one_round else 16384)
-        rs = synth.generate(n_sample, args.len_min, args.len_max, seed=1001 if one_round else 1002, workers=min(8, ncpu))
+        seed = 1001 if one_round else (1005 << 32 if args.config == 5 else 1002)
+        rs = synth.generate(n_sample, args.len_min, args.len_max, seed=seed, workers=min(8, ncpu))
         warm = min(args.warmup, 1)
-        sub_n, times = cpu_arm(rs, n_sample, threads, args.steps, warm, 1 if one_round else 2)
+        sub_n, times, kind, how = cpu_arm(rs, n_sample, threads, args.steps, warm, 1 if one_round else 2)
         ms = 1e3 * float(np.mean(times))
         val = sub_n / float(np.mean(times))
         line = {
@@ -207,14 +488,12 @@ def main():
             "config": {"workload": ("configs[0]: round-1 SP5 5' demux (-g file:M13_amplicon_indices_forward.fa -e 0.1 --rc), "
                                     "%d synthetic reads %d-%d nt, seed 1001" % (sub_n, args.len_min, args.len_max))
                        if one_round else
-                       "configs[1]: two-round SP5->SP27 demux + trim, synthetic COI reads %d-%d nt, "
-                       "seed 1002; each step = the first %d reads of the 1 Mi-read workload"
-                       % (args.len_min, args.len_max, sub_n),
-                       "reads_per_step": sub_n, "note": "cutadapt 4.9 is not vendored in the reference and not "
-                       "installable here: this arm is the restated-cutadapt CPU baseline (oracle/cutadapt_oracle.c, "
-                       "Ukkonen-banded DP, pthreads), not upstream cutadapt"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "first %d reads of the workload, %d timed passes" % (sub_n, args.steps)},
+                       "%s: two-round SP5->SP27 demux + trim, synthetic COI reads %d-%d nt; each step = %d reads "
+                       "of the workload's read model (numpy generator, seed %d)"
+                       % ("configs[4]" if args.config == 5 else "configs[1]", args.len_min, args.len_max, sub_n, seed),
+                       "reads_per_step": sub_n, "cpu_arm": how},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "%d reads of the workload, %d timed passes; %s" % (sub_n, args.steps, how)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         if one_round:       # algorithmic cells of round 1: 2 orientations x 12 adapters x 59 rows x bases
@@ -256,205 +535,238 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    seed = {1: 1001, 2: 1002, 3: 1003, 4: 1004}[args.config] if world == 1 else (1005 << 32) + rank
-    workers = max(1, min(16, ncpu // max(world, 1)))
-    t0 = time.perf_counter()
-    rs = synth.generate(args.reads, args.len_min, args.len_max, seed=seed, workers=workers,
-                        anchored=(args.config == 4))
-    if args.config == 4:
+    def run_config(config, reads, len_min, len_max, steps, warmup, full):
+        """One workload: device-resident value, e2e, stage split.  `full` adds clocks, the kernel table inputs."""
         from orcdemux import m13
         from orcdemux.lib import ORC_PREFIX
-        var = m13.variable_all()
-        rounds = [E.Round([n for n, _ in var], [q for _, q in var], ORC_PREFIX, 0.1, 3, False, True)]
-    elif args.config == 1:
-        rounds = E.m13_rounds()[:1]
-    else:
-        rounds = E.m13_rounds()
-    gen_s = time.perf_counter() - t0
-    rs = E.pin_readset(rs)
-    n_bytes = int(rs.seq.shape[0])
-    n_slots = 1
-    eng = E.Engine(rounds, device=local_rank, max_reads=rs.n_reads, max_bytes=n_bytes,
-                   max_name_bytes=int(rs.names.shape[0]) + 64, n_slots=n_slots, emit_fastq=True, want_matches=True)
-
-    # ---- device-resident: `value`
-    eng.upload(0, rs)
-    eng.sync(0)
-    for _ in range(args.warmup):
-        eng.launch(0)
-    eng.sync(0)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    eng.timer_start(0)
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.launch(0)
-    dev_ms = eng.timer_stop(0)          # device time of exactly K steps on the library's stream
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - wall0)
-    clocks = sampler.stop()
-    t = eng.timings(0)                  # stage split of the last step
-    cells = float(sum(t["cells"]))
-    scan_ms = float(sum(t["scan_ms"]) + sum(t["trigger_ms"]))
-    stage = {"pack_ms": t["pack_ms"], "trigger_ms": t["trigger_ms"], "scan_ms": t["scan_ms"], "resolve_ms": t["resolve_ms"],
-             "bin_ms": t["bin_ms"], "emit_ms": t["emit_ms"], "total_ms": t["total_ms"], "n_tasks": t["n_tasks"]}
-    launches = int(t["kernel_launches"]) * args.steps
-
-    tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    max_ms = float(tm.item())
-    value = (args.reads * world * args.steps) / (max_ms * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers: `e2e`
-    # The step's reads are streamed as SUB sub-batches through S slots (what a FASTQ reader does):
-    # the H2D copy of one sub-batch overlaps the kernels of the previous and the D2H of the one
-    # before.  Every input byte is copied from pinned host memory and every result byte (FASTQ
-    # text, bins, lengths, match records) is copied back, every step.
-    e2e = None
-    eng.close()
-    if not args.no_e2e:
-        SUB, S = max(1, args.sub_batches), 4
-        per = (args.reads + SUB - 1) // SUB
-        subs = []
-        for i in range(SUB):
-            lo, hi = i * per, min(args.reads, (i + 1) * per)
-            if lo >= hi:
-                break
-            b0 = int(rs.offsets[lo])
-            b1 = int(rs.offsets[hi - 1]) + int(rs.lengths[hi - 1])
-            n0, n1 = int(rs.name_offsets[lo]), int(rs.name_offsets[hi])
-            off = E.pinned_empty(hi - lo, np.uint64)
-            off[...] = rs.offsets[lo:hi] - np.uint64(b0)
-            noff = E.pinned_empty(hi - lo + 1, np.uint64)
-            noff[...] = rs.name_offsets[lo:hi + 1] - np.uint64(n0)
-            subs.append(synth.ReadSet(rs.seq[b0:b1], rs.qual[b0:b1], off, rs.lengths[lo:hi], rs.names[n0:n1], noff, {}))
-        eng2 = E.Engine(rounds, device=local_rank, max_reads=per,
-                        max_bytes=max(int(x.seq.shape[0]) for x in subs) + 64,
-                        max_name_bytes=max(int(x.names.shape[0]) for x in subs) + 64, n_slots=S,
-                        emit_fastq=True, want_matches=True)
-        h2d = sum(int(x.seq.nbytes + x.qual.nbytes + x.offsets.nbytes + x.lengths.nbytes + x.names.nbytes +
-                      x.name_offsets.nbytes) for x in subs)
-        state = {"inflight": [], "k": 0, "reads": 0, "d2h": 0}
-
-        def pump(sub):
-            if len(state["inflight"]) == S:
-                r = eng2.wait(state["inflight"].pop(0), copy=False)
-                state["reads"] += int(r.bin_counts.sum())
-                state["d2h"] += int(r.fastq.nbytes + r.bin.nbytes + r.out_len.nbytes + r.bin_counts.nbytes +
-                                    r.bin_offsets.nbytes + sum(m.nbytes for m in r.matches))
-            slot = state["k"] % S
-            eng2.submit(slot, sub)
-            state["inflight"].append(slot)
-            state["k"] += 1
-
-        def drain():
-            while state["inflight"]:
-                r = eng2.wait(state["inflight"].pop(0), copy=False)
-                state["reads"] += int(r.bin_counts.sum())
-                state["d2h"] += int(r.fastq.nbytes + r.bin.nbytes + r.out_len.nbytes + r.bin_counts.nbytes +
-                                    r.bin_offsets.nbytes + sum(m.nbytes for m in r.matches))
-
-        for sub in subs:                            # warm the copy paths: one untimed step
-            pump(sub)
-        drain()
-        state.update(reads=0, d2h=0)
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            for sub in subs:
-                pump(sub)
-        drain()
-        barrier()
-        e2e_s = time.perf_counter() - w0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        out = {}
+        t0 = time.perf_counter()
+        if config == 4:
+            var = m13.variable_all()
+            rounds = [E.Round([n for n, _ in var], [q for _, q in var], ORC_PREFIX, 0.1, 3, False, True)]
+        elif config == 1:
+            rounds = E.m13_rounds()[:1]
+        else:
+            rounds = E.m13_rounds()
+        drop = scripts_final_tree_drop() if len(rounds) == 2 else None
+        oracle_check = None
+        if config == 5:
+            # distinct shards made on the GPU, all resident before the timed region
+            per_rank = max(1, min(steps, -(-TARGET_READS // (reads * world))))
+            shard_ids = [rank + world * k for k in range(per_rank)]
+            eng = E.Engine(rounds, device=local_rank, max_reads=reads, max_bytes=int(reads * (len_max + 72)),
+                           max_name_bytes=24 * reads, n_slots=per_rank, emit_fastq=True, want_matches=False,
+                           drop_bins=drop)
+            for s, sid in enumerate(shard_ids):
+                eng.synth(s, (1005 << 32) + sid, reads, len_min, len_max)
+            for s in range(per_rank):
+                eng.sync(s)
+            out["gen_s"] = time.perf_counter() - t0
+            rs_list = [None] * per_rank
+            seed_desc = "(1005 << 32) + shard, shard = rank + %d * step, %d shards per rank" % (world, per_rank)
+            n_bytes = None
+        else:
+            seed = {1: 1001, 2: 1002, 3: 1003, 4: 1004}[config]
+            workers = max(1, min(16, ncpu // max(world, 1)))
+            rs = synth.generate(reads, len_min, len_max, seed=seed, workers=workers, anchored=(config == 4))
+            out["gen_s"] = time.perf_counter() - t0
+            rs = E.pin_readset(rs)
+            n_bytes = int(rs.seq.shape[0])
+            eng = E.Engine(rounds, device=local_rank, max_reads=rs.n_reads, max_bytes=n_bytes,
+                           max_name_bytes=int(rs.names.shape[0]) + 64, n_slots=1, emit_fastq=True, want_matches=False,
+                           drop_bins=drop)
+            eng.upload(0, rs)
+            eng.sync(0)
+            rs_list = [rs]
+            seed_desc = str(seed)
+        sampler = ClockSampler(local_rank) if full else None
+        dev_ms, wall_ms, clocks = device_resident(E, eng, rs_list, steps, warmup, barrier, sampler)
+        t = eng.timings(0)
+        tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        assert state["reads"] == args.steps * args.reads
-        e2e = {"value": (args.reads * world * args.steps) / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": state["d2h"] // args.steps,
-               "ms_per_step": 1e3 * float(te.item()) / args.steps,
-               "note": "each step streamed as %d sub-batches over %d slots/streams (copies overlap kernels); "
-                       "pipeline fill and drain are inside the timed region; host clock between device syncs "
-                       "because the region includes host-side calls" % (len(subs), S)}
-        counts_np = eng2.counts().astype(np.int64)
-        eng2.close()
-    else:
-        counts_np = None
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        max_ms = float(tm.item())
+        out.update(value=(reads * world * steps) / (max_ms * 1e-3), ms_per_step=max_ms / steps,
+                   wall_ms_per_step=wall_ms / steps, clocks=clocks, timings=t, seed=seed_desc, n_bytes=n_bytes,
+                   launches=int(t["kernel_launches"]) * steps, rounds=rounds, n_slots=len(rs_list))
+        # ---- sampled oracle check of one shard per rank (config 5) and host copies for the e2e leg
+        host_batches = None
+        if config == 5:
+            import oracle
+            k = len(rs_list) // 2
+            eng.launch(k)
+            eng.download(k)
+            res = eng.wait(k)
+            shard = eng.export(k)               # the generated reads, as the host sees them
+            ns = min(args.oracle_sample, shard.n_reads)
+            end = int(shard.offsets[ns - 1] + shard.lengths[ns - 1])
+            sets = [(oracle.AdapterSet(r.sequences, oracle.FRONT if i == 0 else oracle.BACK, 0.1, 3), 1) for i, r in enumerate(rounds)]
+            os.sched_setaffinity(0, all_cpus)
+            t1 = time.perf_counter()
+            rec0, rec1, _, _, olen = oracle.demux_batch(sets, shard.seq[:end], shard.qual[:end], shard.offsets[:ns],
+                                                        shard.lengths[:ns], n_threads=max(1, ncpu // world))
+            exp_bin = (rec0["adapter"] + 1) + 13 * (rec1["adapter"] + 1)
+            exp_bin = np.where(drop[exp_bin] != 0, -1, exp_bin).astype(np.int32)
+            ok = bool(np.array_equal(res.bin[:ns], exp_bin) and np.array_equal(res.out_len[:ns], olen))
+            exp_counts = np.bincount(exp_bin[exp_bin >= 0], minlength=169)
+            got_counts = np.bincount(res.bin[:ns][res.bin[:ns] >= 0], minlength=169)
+            oracle_check = {"shard": shard_ids[k], "reads": ns, "bins_equal": ok,
+                            "counts_equal": bool(np.array_equal(exp_counts, got_counts)),
+                            "seconds": time.perf_counter() - t1,
+                            "binned_of_sample": int(got_counts.sum())}
+            if not (ok and oracle_check["counts_equal"]):
+                raise SystemExit("rank %d: shard %d differs from the oracle" % (rank, shard_ids[k]))
+            host_batches = [E.pin_readset(shard)]
+            if len(rs_list) > 1:
+                eng.launch(0); eng.download(0); eng.wait(0)
+                host_batches.append(E.pin_readset(eng.export(0)))
+        else:
+            host_batches = rs_list
+        eng.close()
+        out["oracle_check"] = oracle_check
+        # ---- end to end through the C ABI with host buffers
+        if not args.no_e2e:
+            step_batches = [split_subbatches(E, synth, hb, max(1, args.sub_batches))[0] for hb in host_batches]
+            e_steps = steps if full else max(2, min(steps, 5))
+            secs, h2d, d2h, n_done, counts = run_e2e(E, rounds, local_rank, step_batches, e_steps, barrier, drop,
+                                                     want_matches=False)
+            te = torch.tensor([secs], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            assert n_done == e_steps * reads, (n_done, e_steps, reads)
+            out["e2e"] = {"value": (reads * world * e_steps) / float(te.item()), "unit": UNIT,
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
+                          "ms_per_step": 1e3 * float(te.item()) / e_steps,
+                          "note": "each step streamed as %d sub-batches over 4 slots/streams (copies overlap kernels); "
+                                  "pipeline fill and drain are inside the timed region; output = the FASTQ text of the "
+                                  "bins the reference script keeps (02:107-119: no unknown, no SP27_009..012) + bin id "
+                                  "and trimmed length per read; match records off" % len(step_batches[0])}
+            out["counts"] = counts
+        else:
+            out["e2e"] = None
+            out["counts"] = None
+        return out
+
+    main_cfg = run_config(args.config, args.reads, args.len_min, args.len_max, args.steps, args.warmup, True)
+    t = main_cfg["timings"]
+    rounds = main_cfg["rounds"]
 
     # ---- the only collective: per-bin count gather
+    counts_np = main_cfg["counts"]
     counts = torch.from_numpy(counts_np if counts_np is not None else np.zeros(1, np.int64)).cuda()
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     total_reads_binned = int(counts.sum().item())
+    checks = None
+    if main_cfg["oracle_check"] is not None:
+        oc = main_cfg["oracle_check"]
+        flags = torch.tensor([int(oc["bins_equal"] and oc["counts_equal"]), oc["reads"]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.SUM)
+        checks = {"ranks_equal_to_oracle": int(flags[0].item()), "ranks": world, "reads_checked": int(flags[1].item()),
+                  "rank0": oc}
 
-    # ---- roofline of the dominant kernel
+    # ---- host link ceiling under the same N ranks
+    link = measure_link(torch, barrier) if not args.no_e2e else None
+    if link is not None and main_cfg["e2e"] is not None:
+        e = main_cfg["e2e"]
+        per_rank_s = e["ms_per_step"] * 1e-3
+        e["link"] = dict(link, h2d_used_gbs=e["h2d_bytes_per_step"] / per_rank_s / 1e9,
+                         d2h_used_gbs=e["d2h_bytes_per_step"] / per_rank_s / 1e9,
+                         frac_of_both=max(e["h2d_bytes_per_step"], e["d2h_bytes_per_step"]) / per_rank_s / 1e9 / link["both_gbs"],
+                         note="ceilings = this rank's pinned 512 MiB copies while all %d ranks copy at once (GB/s per "
+                              "direction); frac_of_both = the busier direction of the e2e leg / the bidirectional ceiling" % world)
+
     roofline = None
-    cpu_baseline = None
     extra = {}
     if rank == 0:
         alu_peak, sm_clk = E.measure_int32_peak(local_rank, 0)
         mix_peak, _ = E.measure_int32_peak(local_rank, 1)
-        m_rows = 59.0
-        peak_gcups = alu_peak / SCAN_ALU_INSTR_PER_COLUMN * m_rows / 1e9
-        ach_gcups = cells / (scan_ms * 1e-3) / 1e9
-        exe_gcups = float(sum(t["cells_executed"])) / (scan_ms * 1e-3) / 1e9
-        roofline = {"bound": "int32_alu",
-                    "kernel": "scan = seed_kernel + trigger_kernel (stage 1) + filter_kernel (stage 2a) + scan_kernel (stage 2b), both rounds",
-                    "achieved": ach_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": ach_gcups / peak_gcups,
-                    "traffic": SCAN_DRAM_BYTES_PER_READ * args.reads if args.config == 2 else None,
-                    "traffic_how": "ncu dram bytes of the scan launches per read (profiles/r1n_main_raw.csv) x reads; "
-                                   "ALU-bound kernels: traffic is the packed codes read once per stage, far below HBM limits",
-                    "executed": {"achieved": exe_gcups, "frac": exe_gcups / peak_gcups,
-                                 "note": "DP cells the kernels really update; the rest of the algorithmic cells "
-                                         "(2*12*m*n per read and round, SURVEY 8d) are skipped exactly by the "
-                                         "seed filter (stage 1, no DP cells at all in its main pass) and the "
-                                         "32-row block test (stage 2a), which is why `frac` exceeds 1"},
-                    "peak_how": "measured LOP3 issue rate %.3g lane-op/s (orc_measure_int32_peak mode 0, this GPU, this "
-                                "run) / %.0f ALU-pipe instr per 64-bit Myers column x %d rows = what an exhaustive "
-                                "per-pair scan can reach; LOP3+IMAD mix: %.3g" %
-                                (alu_peak, SCAN_ALU_INSTR_PER_COLUMN, int(m_rows), mix_peak),
-                    "cells_per_step": cells, "scan_ms": scan_ms}
         hbm, how = hbm_peak()
-        extra["roofline_hbm"] = [
-            {"kernel": "pack_kernel", "bound": "hbm", "achieved": t["pack_bytes"] / (t["pack_ms"] * 1e-3) / 1e9,
-             "peak": hbm, "unit": "GB/s", "frac": t["pack_bytes"] / (t["pack_ms"] * 1e-3) / 1e9 / hbm,
-             "peak_how": "of " + how},
-            {"kernel": "emit_kernel", "bound": "hbm", "achieved": t["emit_bytes"] / (t["emit_ms"] * 1e-3) / 1e9,
-             "peak": hbm, "unit": "GB/s", "frac": t["emit_bytes"] / (t["emit_ms"] * 1e-3) / 1e9 / hbm,
-             "peak_how": "of " + how}]
-        extra["gcups"] = cells * args.steps * world / (max_ms * 1e-3) / 1e9 if world == 1 else None
+        m_rows = [float(np.mean([len(s) for s in r.sequences])) for r in rounds]
+        # seed probes: one per base of the reads entering the round (both directions in one pass)
+        seed_cols = [t["cells"][r] / (2.0 * sum(len(s) for s in rounds[r].sequences)) if rounds[r].sequences else 0.0
+                     for r in range(len(rounds))]
+        table = kernel_table(t, rounds, alu_peak, hbm, how, m_rows, seed_cols)
+        extra["roofline_kernels"] = table
+        rated = [r for r in table if r["frac"] is not None]
+        top = max(rated, key=lambda r: r["ms"]) if rated else None
+        cells = float(sum(t["cells"]))
+        executed = float(sum(t["cells_executed"]))
+        dp_ms = float(sum(t["scan_ms"]) + sum(t["trigger_ms"]))
+        if top is not None:
+            roofline = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"],
+                        "unit": top["unit"], "frac": top["frac"], "ms": top["ms"], "share_of_step": top["share"],
+                        "traffic": None,
+                        "traffic_how": "see profiles/README.md (ncu --set full of the same build): DP kernels read the packed "
+                                       "codes once per stage, far below HBM limits",
+                        "how": top.get("how"),
+                        "peak_how": "LOP3 issue rate %.4g lane-op/s measured in this run on this GPU (orc_measure_int32_peak "
+                                    "mode 0; LOP3+IMAD mix %.4g); HBM: %s" % (alu_peak, mix_peak, how),
+                        "executed": {"cells_per_step": executed, "gcups": executed / (dp_ms * 1e-3) / 1e9 if dp_ms else None,
+                                     "note": "DP cells stages 1-2b really update per step, over their summed time"},
+                        "algorithmic_speedup": cells / executed if executed else None,
+                        "algorithmic_cells_per_step": cells}
+        extra["gcups"] = cells * args.steps * world / (main_cfg["ms_per_step"] * args.steps * 1e-3) / 1e9
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config != 4:
-        import oracle
-        oracle.build()
-        n_s = args.cpu_sample or 16384
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config in (1, 2, 3):
         os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core
-        sub_n, times = cpu_arm(rs, n_s, ncpu, 2, 1, 1 if args.config == 1 else 2)
-        cpu_baseline = {"value": sub_n / float(np.mean(times)), "unit": UNIT, "cores": ncpu, "kind": "port",
-                        "sample": "first %d reads of the workload, one warm-up and two timed passes, %d threads "
-                                  "(restated-cutadapt CPU baseline, not upstream cutadapt)" % (sub_n, ncpu)}
+        seed = {1: 1001, 2: 1002, 3: 1003}[args.config]
+        n_s = args.cpu_sample or (16384 if args.config != 3 else 4096)
+        rs_cpu = synth.generate(n_s, args.len_min, args.len_max, seed=seed, workers=min(8, ncpu))
+        sub_n, times, kind, how_cpu = cpu_arm(rs_cpu, n_s, ncpu, 2, 1, 1 if args.config == 1 else 2)
+        cpu_baseline = {"value": sub_n / float(np.mean(times)), "unit": UNIT, "cores": ncpu, "kind": kind,
+                        "sample": "first %d reads of the workload, one warm-up and two timed passes; %s" % (sub_n, how_cpu)}
+
+    # ---- short runs of the other single-GPU configs, so that they are driver-run numbers too
+    if world == 1 and args.config == 2 and not args.no_extra:
+        ex = {}
+        for cfg, reads, lo, hi in ((3, 1 << 18, 1000, 3500), (4, 1 << 20, 300, 900)):
+            r = run_config(cfg, reads, lo, hi, 5, 3, False)
+            ex["configs[%d]" % (cfg - 1)] = {
+                "workload": {3: "two-round demux on %d synthetic rRNA-cistron reads (%d-%d nt), seed 1003",
+                             4: "anchored --no-indels Hamming path, 24 M13 variable indices, %d reads (%d-%d nt), seed 1004"}[cfg]
+                            % (reads, lo, hi),
+                "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": 5, "warmup": 3,
+                "e2e": r["e2e"], "gpu_launches": r["launches"],
+                "stages_ms": {k: r["timings"][k] for k in ("pack_ms", "trigger_ms", "scan_ms", "resolve_ms", "bin_ms", "emit_ms", "total_ms")}}
+        extra["extra_configs"] = ex
 
     if rank == 0:
+        reads = args.reads
+        stage = {"pack_ms": t["pack_ms"], "trigger_ms": t["trigger_ms"], "scan_ms": t["scan_ms"], "resolve_ms": t["resolve_ms"],
+                 "bin_ms": t["bin_ms"], "emit_ms": t["emit_ms"], "total_ms": t["total_ms"], "n_tasks": t["n_tasks"],
+                 "n_tasks_wide": t["n_tasks_wide"], "n_pairs_2b": t["n_pairs_2b"], "kernel_ms": t["kernel_ms"]}
+        workload = {1: "configs[0]: round-1 SP5 5' demux + trim only, %d synthetic reads (%d-%d nt) per GPU, "
+                       "-g file:M13_amplicon_indices_forward.fa -e 0.1 --rc",
+                    2: "configs[1]: full two-round SP5->SP27 combinatorial demux + trim on %d synthetic "
+                       "COI-length reads (%d-%d nt) per GPU, -e 0.1 -O 3 --rc, 12+12 M13 indices",
+                    3: "configs[2]: two-round demux on %d synthetic rRNA-cistron reads (%d-%d nt) per GPU",
+                    4: "configs[3]: anchored --no-indels Hamming path, 24 M13 variable indices, %d reads "
+                       "(%d-%d nt) per GPU, index at read offset 0",
+                    5: "configs[4]: two-round demux sharded over the GPUs, %d reads (%d-%d nt) per shard and step, "
+                       "distinct shards made on the GPU"}[args.config] % (reads, args.len_min, args.len_max)
+        cfg = {"workload": workload, "reads_per_gpu_per_step": reads, "seed": main_cfg["seed"],
+               "l2": "inputs larger than L2 (%.2f GB of inputs and packed codes resident per step)"
+                     % (2.5 * (main_cfg["n_bytes"] or reads * (args.len_min + args.len_max) // 2) / 1e9),
+               "parallelism": "reads sharded by batch, no data-path collective; all_reduce of %d bin counters at the end"
+                              % int(counts.numel())}
+        if args.config == 5:
+            distinct = main_cfg["n_slots"] * world * reads
+            cfg["distinct_reads_total"] = distinct
+            cfg["reads_processed_in_timed_region"] = args.steps * world * reads
+            cfg["target_reads"] = TARGET_READS
         line = {
-            "metric": METRIC_R1 if args.config == 1 else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "metric": METRIC_R1 if args.config == 1 else METRIC, "value": main_cfg["value"], "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_cfg["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": {1: "configs[0]: round-1 SP5 5' demux + trim only, %d synthetic reads (%d-%d nt) per GPU, "
-                                       "-g file:M13_amplicon_indices_forward.fa -e 0.1 --rc",
-                                    2: "configs[1]: full two-round SP5->SP27 combinatorial demux + trim on %d synthetic "
-                                       "COI-length reads (%d-%d nt) per GPU, -e 0.1 -O 3 --rc, 12+12 M13 indices",
-                                    3: "configs[2]: two-round demux on %d synthetic rRNA-cistron reads (%d-%d nt) per GPU",
-                                    4: "configs[3]: anchored --no-indels Hamming path, 24 M13 variable indices, %d reads "
-                                       "(%d-%d nt) per GPU, index at read offset 0"}[args.config]
-                                   % (args.reads, args.len_min, args.len_max),
-                       "reads_per_gpu": args.reads, "seed": seed, "l2": "inputs larger than L2 (%.2f GB resident "
-                       "per step)" % (2.5 * n_bytes / 1e9), "parallelism": "reads sharded by batch, no data-path "
-                       "collective; all_reduce of %d bin counters at the end" % int(counts.numel())},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "stages_ms_last_step": stage, "wall_ms_per_step": wall_ms / args.steps,
-            "reads_binned_all_ranks": total_reads_binned, "gen_s": gen_s, "cpu_affinity": numa,
+            "config": cfg, "clocks": main_cfg["clocks"], "e2e": main_cfg["e2e"], "gpu_launches": main_cfg["launches"],
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "stages_ms_last_step": stage,
+            "wall_ms_per_step": main_cfg["wall_ms_per_step"], "reads_binned_all_ranks": total_reads_binned,
+            "oracle_check": checks, "gen_s": main_cfg["gen_s"], "cpu_affinity": numa,
+            "verify_open": "parity unpinned: no real cutadapt 4.9 here; SURVEY VERIFY-1..15 stay open until "
+                           "tests/test_cutadapt_diff.py runs somewhere (it skips without cutadapt)",
         }
         line.update(extra)
         emit(line)

@@ -123,6 +123,10 @@ typedef struct orc_result {
     uint64_t fastq_bytes;
 } orc_result;
 
+/* kernels of one round, in launch order (orc_timings.kernel_ms) */
+enum { ORC_K_SORT_READS = 0, ORC_K_SEED, ORC_K_TRIGGER, ORC_K_SORT_ITEMS, ORC_K_FILTER, ORC_K_SCAN,
+       ORC_K_RESOLVE_BAND, ORC_K_RESOLVE_WIDE, ORC_K_SELECT, ORC_N_KERNELS };
+
 /* Device time of the stages of the last orc_launch()/orc_submit() on a slot, from CUDA
  * events recorded on the ctx's own stream (milliseconds), and launch counts. */
 typedef struct orc_timings {
@@ -140,6 +144,12 @@ typedef struct orc_timings {
     uint64_t cells[ORC_MAX_ROUNDS];   /* algorithmic DP cells: pairs * m * n   */
     uint64_t cells_executed[ORC_MAX_ROUNDS]; /* DP cells the two scan stages really updated */
     uint64_t pack_bytes, emit_bytes;  /* algorithmic bytes moved by pack / emit */
+    /* per kernel of each round (ORC_K_*), device time between events recorded around every launch */
+    float kernel_ms[ORC_MAX_ROUNDS][ORC_N_KERNELS];
+    uint64_t window_columns[ORC_MAX_ROUNDS]; /* columns stage 2 looks at, summed over the (read, direction) items */
+    uint64_t cells_2b[ORC_MAX_ROUNDS];       /* DP cells of stage 2b: m x window columns of the pairs that passed 2a */
+    uint32_t n_pairs_2b[ORC_MAX_ROUNDS];     /* pairs that passed stage 2a */
+    uint32_t n_tasks_wide[ORC_MAX_ROUNDS];   /* resolver tasks the band resolver could not take */
 } orc_timings;
 
 orc_ctx *orc_create(const orc_params *params, char *err, size_t err_len);
@@ -243,6 +253,21 @@ enum { ORC_EDIT_NW = 0, ORC_EDIT_HW = 1 };
 int orc_edit_distances(int device, const uint8_t *seqs, const uint64_t *offsets, const uint32_t *lengths,
                        uint32_t n_seqs, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n_pairs,
                        int mode, uint32_t *dist, float *kernel_ms, char *err, size_t err_len);
+
+/*
+ * Synthetic input (benchmarks and tests; the reference ships no reads).  orc_synth() makes n_reads ONT-like
+ * reads of the SURVEY 8d read model -- 5' adapter of round 1 + random insert + 3' adapter of round 2, iid
+ * sequencing errors, truncations, missing adapters, reverse-complemented reads, total length uniform in
+ * [len_min, len_max] -- on the device, straight into the slot, which is then in the state orc_upload() leaves
+ * it in (orc_launch / orc_download / orc_wait follow).  Deterministic in (seed, n_reads, len_min, len_max).
+ * Needs two rounds of plain unanchored adapters and emit_fastq.  orc_resident() gives the sizes of the batch
+ * resident in a slot, orc_export() copies it to host buffers in the separate-blob layout of orc_batch
+ * (name_offsets: n_reads + 1 entries), e.g. to hand the same bytes to a CPU checker.
+ */
+int orc_synth(orc_ctx *ctx, int slot, uint64_t seed, uint32_t n_reads, uint32_t len_min, uint32_t len_max);
+int orc_resident(orc_ctx *ctx, int slot, uint32_t *n_reads, uint64_t *n_bytes, uint64_t *name_bytes);
+int orc_export(orc_ctx *ctx, int slot, uint8_t *seq, uint8_t *qual, uint64_t *offsets, uint32_t *lengths,
+               uint8_t *names, uint64_t *name_offsets);
 
 /* pinned host memory for callers that do not bring their own */
 void *orc_host_alloc(size_t bytes);

@@ -18,6 +18,7 @@
 #include "../../include/orcdemux.h"
 
 #include "orc_kernels.cuh"
+#include "orc_synth.cuh"
 #include "orc_table.h"
 
 using namespace orc;
@@ -84,6 +85,7 @@ struct Slot {
     uint32_t n_launches = 0;                 // own kernels of the last orc_launch()
     size_t cap_pairs = 0;                    // entries of d_tasks / d_results (see alloc_slot)
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t evk[ORC_MAX_ROUNDS][ORC_N_KERNELS + 1] = {};   // [r][0]: before the round's first kernel, [r][1 + K]: after kernel K
 };
 
 }  // namespace
@@ -102,6 +104,8 @@ struct orc_ctx {
     AnchoredTable *d_anch[2] = {nullptr, nullptr};
     bool anchored[2] = {false, false};
     uint8_t *d_pack_lut = nullptr, *d_comp_lut = nullptr, *d_drop = nullptr;
+    SynthTable *d_synth = nullptr;   // orc_synth(): built on first use
+    uint64_t *d_synth_totals = nullptr;
     std::vector<Slot> slots;
     std::vector<uint64_t> total_counts;
     std::string err;
@@ -147,6 +151,8 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     s.cap_pairs = n_tasks;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_COUNT; i++) CK(cudaEventCreate(&s.ev[i]));
+    for (int r = 0; r < ORC_MAX_ROUNDS; r++)
+        for (int i = 0; i <= ORC_N_KERNELS; i++) CK(cudaEventCreate(&s.evk[r][i]));
     CK(dalloc(&s.d_seq, B + 64));
     CK(dalloc(&s.d_qual, B + 64));
     CK(dalloc(&s.d_codes_alloc, B / 8 + 16 + 2 * GUARD_WORDS));
@@ -189,7 +195,8 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
         CK(dalloc(&s.d_name_offsets, R + 1));
         CK(dalloc(&s.d_name_lengths, R));
         CK(dalloc(&s.d_fastq, (size_t)ctx->fastq_cap));
-        CK(halloc(&s.h_fastq, (size_t)ctx->fastq_cap));
+        // h_fastq (page-locked, as large as the device arena) is allocated by the first orc_wait() that has
+        // text to fetch: slots that are only ever launched (device-resident shards) never pay for it
     }
     return ORC_OK;
 }
@@ -211,6 +218,8 @@ static void free_slot(Slot &s)
     cudaFreeHost(s.h_bin); cudaFreeHost(s.h_out_len); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_cells);
     cudaFreeHost(s.h_bin_counts); cudaFreeHost(s.h_bin_offsets); cudaFreeHost(s.h_fastq);
     for (int i = 0; i < EV_COUNT; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    for (int r = 0; r < ORC_MAX_ROUNDS; r++)
+        for (int i = 0; i <= ORC_N_KERNELS; i++) if (s.evk[r][i]) cudaEventDestroy(s.evk[r][i]);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -308,11 +317,11 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     }
     ctx->resolve_blocks = ctx->sm_count * (occ > 0 ? occ : 1);
     CK(cudaFuncSetAttribute(resolve_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)band_smem_bytes(MAX_LANES)));
+                            (int)band_smem_bytes(MAX_LANES, MAX_AD)));
     for (int r = 0; r < p->n_rounds; r++) {
         if (ctx->anchored[r]) continue;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_band_kernel, BAND_THREADS,
-                                                         band_smem_bytes(ctx->h_tab[r].n_lanes)));
+                                                         band_smem_bytes(ctx->h_tab[r].n_lanes, ctx->h_tab[r].n_adapters)));
         ctx->band_blocks[r] = ctx->sm_count * (occ > 0 ? occ : 1);
     }
     ctx->slots.resize((size_t)ctx->n_slots);
@@ -348,6 +357,7 @@ extern "C" void orc_destroy(orc_ctx *ctx)
     }
     for (int r = 0; r < 2; r++) { cudaFree(ctx->d_tab[r]); cudaFree(ctx->d_anch[r]); cudaFree(ctx->d_seed[r]); }
     cudaFree(ctx->d_pack_lut); cudaFree(ctx->d_comp_lut); cudaFree(ctx->d_drop);
+    cudaFree(ctx->d_synth); cudaFree(ctx->d_synth_totals);
     delete ctx;
 }
 
@@ -451,6 +461,112 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
     return ORC_OK;
 }
 
+// Synthetic reads made on the device (orc_synth.cuh), left in the slot exactly as orc_upload() would
+// leave an uploaded batch.
+extern "C" int orc_synth(orc_ctx *ctx, int slot, uint64_t seed, uint32_t n_reads, uint32_t len_min, uint32_t len_max)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    Slot &s = *sp;
+    if (ctx->n_rounds != 2 || ctx->anchored[0] || ctx->anchored[1] || ctx->h_tab[0].wild || ctx->h_tab[1].wild) {
+        ctx->err = "orc_synth needs two rounds of plain (ACGT, unanchored) adapters: the read model is 5' adapter + insert + 3' adapter";
+        return ORC_EINVAL;
+    }
+    if (!ctx->emit_fastq) { ctx->err = "orc_synth needs emit_fastq (it also makes the read names)"; return ORC_EINVAL; }
+    if (n_reads == 0 || n_reads > ctx->max_reads) { ctx->err = "orc_synth: n_reads exceeds max_reads"; return ORC_ECAPACITY; }
+    if (len_min < 1 || len_max < len_min) { ctx->err = "orc_synth: bad length range"; return ORC_EINVAL; }
+    // a first plausibility check on the mean read; the exact total is checked before anything is written
+    if ((uint64_t)n_reads * (((uint64_t)len_min + len_max) / 2) > ctx->max_bytes) {
+        ctx->err = "orc_synth: max_bytes too small for n_reads reads of (len_min + len_max) / 2 bases on average";
+        return ORC_ECAPACITY;
+    }
+    if ((uint64_t)n_reads * 24 > ctx->max_name_bytes) { ctx->err = "orc_synth: max_name_bytes too small (24 per read)"; return ORC_ECAPACITY; }
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_synth) {
+        SynthTable T;
+        memset(&T, 0, sizeof(T));
+        auto letter = [](uint8_t mask) -> uint8_t { return mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; };
+        T.n5 = ctx->h_tab[0].n_adapters; T.n27 = ctx->h_tab[1].n_adapters;
+        for (int a = 0; a < T.n5; a++) {
+            T.m5[a] = ctx->h_tab[0].m[a];
+            for (int i = 0; i < T.m5[a]; i++) T.a5[a][i] = letter(ctx->h_tab[0].code[a][i]);
+        }
+        for (int a = 0; a < T.n27; a++) {
+            T.m27[a] = ctx->h_tab[1].m[a];
+            for (int i = 0; i < T.m27[a]; i++) T.a27[a][i] = letter(ctx->h_tab[1].code[a][i]);
+        }
+        CK(dalloc(&ctx->d_synth, 1));
+        CK(cudaMemcpy(ctx->d_synth, &T, sizeof(T), cudaMemcpyHostToDevice));
+        CK(dalloc(&ctx->d_synth_totals, 2));
+    }
+    cudaStream_t st = s.stream;
+    SynthArgs A;
+    A.seed = seed; A.n_reads = n_reads; A.len_min = len_min; A.len_max = len_max;
+    const uint32_t warp_blocks = (n_reads + 7) / 8;         // 8 warps per block, one warp per read
+    CK(cudaEventRecord(s.ev[EV_START], st));
+    synth_lengths_kernel<<<warp_blocks, 256, 0, st>>>(ctx->d_synth, A, s.d_lengths, s.d_out_len, s.d_name_lengths);
+    synth_offsets_kernel<<<1, 1024, 0, st>>>(s.d_lengths, s.d_name_lengths, n_reads, s.d_offsets, s.d_name_offsets,
+                                             ctx->d_synth_totals);
+    CK(cudaGetLastError());
+    uint64_t totals[2] = {0, 0};
+    CK(cudaMemcpyAsync(totals, ctx->d_synth_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (totals[0] > ctx->max_bytes || totals[1] > ctx->max_name_bytes) {
+        ctx->err = "orc_synth: the generated reads exceed max_bytes / max_name_bytes";
+        s.state = SLOT_IDLE;
+        return ORC_ECAPACITY;
+    }
+    synth_write_kernel<<<warp_blocks, 256, 0, st>>>(ctx->d_synth, A, s.d_lengths, s.d_out_len, s.d_offsets,
+                                                    s.d_name_offsets, s.d_seq, s.d_qual, s.d_names);
+    CK(cudaGetLastError());
+    s.n_reads = n_reads;
+    s.n_bytes = totals[0];
+    s.name_bytes = totals[1];
+    s.in_bases = totals[0];
+    s.has_names = true;
+    s.u_qual = s.d_qual; s.u_names = s.d_names; s.u_qual_offsets = nullptr; s.u_name_lengths = nullptr;
+    CK(cudaEventRecord(s.ev[EV_H2D], st));
+    s.state = SLOT_UPLOADED;
+    s.did_h2d = false; s.fresh_upload = false; s.did_kernels = false; s.did_d2h = false;
+    return ORC_OK;
+}
+
+// Size of the batch resident in a slot (separate-blob layout), for orc_export().
+extern "C" int orc_resident(orc_ctx *ctx, int slot, uint32_t *n_reads, uint64_t *n_bytes, uint64_t *name_bytes)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    if (sp->state == SLOT_IDLE) { ctx->err = "no batch resident in this slot"; return ORC_ESTATE; }
+    if (n_reads) *n_reads = sp->n_reads;
+    if (n_bytes) *n_bytes = sp->n_bytes;
+    if (name_bytes) *name_bytes = sp->name_bytes;
+    return ORC_OK;
+}
+
+// Copies the resident batch of a slot back to host buffers in the separate-blob layout of orc_batch
+// (sizes from orc_resident(); name_offsets has n_reads + 1 entries).  For batches made by orc_synth().
+extern "C" int orc_export(orc_ctx *ctx, int slot, uint8_t *seq, uint8_t *qual, uint64_t *offsets, uint32_t *lengths,
+                          uint8_t *names, uint64_t *name_offsets)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp) return ORC_EINVAL;
+    Slot &s = *sp;
+    if (s.state == SLOT_IDLE) { ctx->err = "no batch resident in this slot"; return ORC_ESTATE; }
+    if (s.u_qual != s.d_qual || s.u_name_lengths != nullptr || !s.has_names) {
+        ctx->err = "orc_export handles the separate-blob layout with names only"; return ORC_EINVAL;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = s.stream;
+    if (seq) CK(cudaMemcpyAsync(seq, s.d_seq, s.n_bytes, cudaMemcpyDeviceToHost, st));
+    if (qual) CK(cudaMemcpyAsync(qual, s.d_qual, s.n_bytes, cudaMemcpyDeviceToHost, st));
+    if (offsets) CK(cudaMemcpyAsync(offsets, s.d_offsets, sizeof(uint64_t) * s.n_reads, cudaMemcpyDeviceToHost, st));
+    if (lengths) CK(cudaMemcpyAsync(lengths, s.d_lengths, sizeof(uint32_t) * s.n_reads, cudaMemcpyDeviceToHost, st));
+    if (names) CK(cudaMemcpyAsync(names, s.d_names, s.name_bytes, cudaMemcpyDeviceToHost, st));
+    if (name_offsets) CK(cudaMemcpyAsync(name_offsets, s.d_name_offsets, sizeof(uint64_t) * (s.n_reads + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ORC_OK;
+}
+
 extern "C" int orc_launch(orc_ctx *ctx, int slot)
 {
     Slot *sp = get_slot(ctx, slot);
@@ -483,63 +599,75 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     for (int r = 0; r < ctx->n_rounds; r++) {
         const Match *prev = r == 0 ? nullptr : s.d_match[r - 1];
         const bool filter = ctx->h_tab[r].use_filter != 0;
-        // per round: [0] stage-2b job counter, [1] result slots, [2] resolver tasks, [4] stage-2a job
-        // counter, [5] pairs that passed stage 2a
+        const bool anch = ctx->anchored[r];
+        // per round: [0] stage-2b job counter, [1] result slots, [2] band-resolver tasks, [3] wide-resolver tasks,
+        // [4] stage-2a job counter, [5] pairs that passed stage 2a
         uint32_t *cnt = s.d_counters + 8 * r;
-        if (n && ctx->anchored[r]) {
-            // anchored adapters without indels: Hamming compare of the anchored end, no alignment
-            CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
-            CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
-            anchored_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_anch[r], s.d_seq, ctx->d_comp_lut, s.d_views[r],
-                                                                prev, n, s.d_results, s.d_best_key); nl++;
-            CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
-        } else if (n) {
-            CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
-            // stage 1: (with a usable shared prefix) order the reads by length and let one 32-bit
-            // scan of the prefix per (read, direction) mark the column windows stage 2 must look at
-            const uint32_t sort_blocks_n = (n + SORT_BUCKETS - 1) / SORT_BUCKETS;
-            if (filter) {
-                bucket_scatter_kernel<true><<<sort_blocks_n, 256, 0, st>>>(
-                    s.d_views[r], prev, nullptr, n, sort_hist(s.d_counters, r, 0, 0), sort_hist(s.d_counters, r, 0, 1),
-                    s.d_order, nullptr); nl++;
-            }
-            const bool seeded = filter && ctx->h_seed[r].on != 0;
-            if (seeded) {
-                seed_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_seed[r], W, s.d_views[r], prev, s.d_order, n,
-                                                            s.d_seedwins); nl++;
-            }
+        // an event after every kernel of the round, launched or not (orc_timings.kernel_ms)
+        auto mark = [&](int k) -> cudaError_t { return cudaEventRecord(s.evk[r][k + 1], st); };
+        if (n) CK(cudaMemsetAsync(s.d_best_key, 0, sizeof(unsigned long long) * 2 * n, st));
+        CK(cudaEventRecord(s.evk[r][0], st));
+        // stage 1: (with a usable shared flank) visit the reads in order of decreasing length; exact 8-mer
+        // seeds and the read-end tests mark the column windows stage 2 must look at
+        if (n && !anch && filter) {
+            bucket_scatter_kernel<true><<<(n + SORT_BUCKETS - 1) / SORT_BUCKETS, 256, 0, st>>>(
+                s.d_views[r], prev, nullptr, n, sort_hist(s.d_counters, r, 0, 0), sort_hist(s.d_counters, r, 0, 1),
+                s.d_order, nullptr); nl++;
+        }
+        CK(mark(ORC_K_SORT_READS));
+        const bool seeded = !anch && filter && ctx->h_seed[r].on != 0;
+        if (n && seeded) {
+            seed_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_seed[r], W, s.d_views[r], prev, s.d_order, n,
+                                                        s.d_seedwins); nl++;
+        }
+        CK(mark(ORC_K_SEED));
+        if (n && !anch) {
             trigger_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r], prev,
                                                                filter ? s.d_order : nullptr, n, s.d_wins,
                                                                s.d_wcols, s.d_cells + 2 + r,
                                                                seeded ? s.d_seedwins : nullptr,
                                                                sort_hist(s.d_counters, r, 1, 0)); nl++;
+        }
+        CK(mark(ORC_K_TRIGGER));
+        if (n && !anch) {
             // order the (read, direction) items by the columns they have to scan
             bucket_scatter_kernel<false><<<(2 * n + SORT_BUCKETS - 1) / SORT_BUCKETS, 256, 0, st>>>(
                 nullptr, nullptr, s.d_wcols, 2 * n, sort_hist(s.d_counters, r, 1, 0), sort_hist(s.d_counters, r, 1, 1),
                 s.d_item_order, s.d_wcols_sorted); nl++;
         }
-        if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
-        if (n && !ctx->anchored[r]) {
-            // stage 2a drops the pairs that cannot hold a candidate, stage 2b scans the rest
-            const bool prefilter = ctx->h_tab[r].indels != 0;
-            if (prefilter) {
-                filter_kernel<<<ctx->filter_blocks, SCAN_THREADS, 0, st>>>(
-                    ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_jobs, cnt,
-                    s.d_cells + 4 + r); nl++;
-            }
+        CK(mark(ORC_K_SORT_ITEMS));
+        CK(cudaEventRecord(s.ev[r == 0 ? EV_TRIG0 : EV_TRIG1], st));
+        // stage 2a drops the pairs that cannot hold a candidate, stage 2b scans the rest
+        const bool prefilter = !anch && ctx->h_tab[r].indels != 0;
+        if (n && prefilter) {
+            filter_kernel<<<ctx->filter_blocks, SCAN_THREADS, 0, st>>>(
+                ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_jobs, cnt,
+                s.d_cells + 4 + r); nl++;
+        }
+        CK(mark(ORC_K_FILTER));
+        if (n && anch) {
+            // anchored adapters without indels: Hamming compare of the anchored end, no alignment
+            anchored_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_anch[r], s.d_seq, ctx->d_comp_lut, s.d_views[r],
+                                                                prev, n, s.d_results, s.d_best_key); nl++;
+        } else if (n) {
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_results,
                 s.d_tasks, s.d_best_key, cnt, prefilter ? s.d_jobs : nullptr, (uint32_t)s.cap_pairs); nl++;
         }
-        if (!(n && ctx->anchored[r])) CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
+        CK(mark(ORC_K_SCAN));
+        CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
+        if (n && prefilter) {           // --no-indels settles every candidate in the scan: no tasks
+            resolve_band_kernel<<<ctx->band_blocks[r], BAND_THREADS, band_smem_bytes(ctx->h_tab[r].n_lanes, ctx->h_tab[r].n_adapters), st>>>(
+                ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2, s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
+        }
+        CK(mark(ORC_K_RESOLVE_BAND));
+        if (n && prefilter) {
+            resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r],
+                                                               s.d_tasks + s.cap_pairs, cnt + 3,
+                                                               s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
+        }
+        CK(mark(ORC_K_RESOLVE_WIDE));
         if (n) {
-            if (!ctx->anchored[r]) {
-                resolve_band_kernel<<<ctx->band_blocks[r], BAND_THREADS, band_smem_bytes(ctx->h_tab[r].n_lanes), st>>>(
-                    ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2, s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
-                resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r],
-                                                                   s.d_tasks + s.cap_pairs, cnt + 3,
-                                                                   s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
-            }
             SelectArgs A;
             A.type = ctx->h_tab[r].type;
             A.revcomp = ctx->h_tab[r].revcomp;
@@ -561,9 +689,10 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             A.out_len = s.d_out_len;
             A.rec_bytes = s.d_rec_bytes;
             A.next_bases = (r + 1 < ctx->n_rounds) ? s.d_cells + r + 1 : nullptr;
-            A.next_len_hist = (r + 1 < ctx->n_rounds) ? sort_hist(s.d_counters, r + 1, 0, 0) : nullptr;
+            A.next_len_hist = (r + 1 < ctx->n_rounds && !ctx->anchored[r + 1]) ? sort_hist(s.d_counters, r + 1, 0, 0) : nullptr;
             select_kernel<<<(n + 127) / 128, 128, 0, st>>>(A); nl++;
         }
+        CK(mark(ORC_K_SELECT));
         CK(cudaEventRecord(s.ev[r == 0 ? EV_RES0 : EV_RES1], st));
     }
     if (ctx->n_rounds == 1) {
@@ -681,6 +810,7 @@ extern "C" int orc_wait(orc_ctx *ctx, int slot, orc_result *out)
     }
     const uint64_t fq = s.has_names ? s.h_bin_offsets[ctx->n_bins] : 0;
     if (fq > ctx->fastq_cap) { ctx->err = "internal: FASTQ output exceeds its arena"; return ORC_ECAPACITY; }
+    if (fq && !s.h_fastq) CK(halloc(&s.h_fastq, (size_t)ctx->fastq_cap));
     if (fq) CK(cudaMemcpyAsync(s.h_fastq, s.d_fastq, fq, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.ev[EV_END], s.stream));
     CK(cudaStreamSynchronize(s.stream));
@@ -766,6 +896,13 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
         t->cells_executed[r] = (T.use_filter ? rows1 * (T.revcomp ? 2ull : 1ull) * bases : 0ull) +
                                (T.indels ? bsum * (uint64_t)cells[2 + r] + (uint64_t)cells[4 + r]
                                          : msum * (uint64_t)cells[2 + r]);
+    }
+    for (int r = 0; r < ctx->n_rounds; r++) {
+        for (int k = 0; k < ORC_N_KERNELS; k++) CK(cudaEventElapsedTime(&t->kernel_ms[r][k], s.evk[r][k], s.evk[r][k + 1]));
+        t->window_columns[r] = (uint64_t)cells[2 + r];
+        t->cells_2b[r] = (uint64_t)cells[4 + r];
+        t->n_pairs_2b[r] = counters[8 * r + 5];
+        t->n_tasks_wide[r] = counters[8 * r + 3];
     }
     t->pack_bytes = s.n_bytes + s.n_bytes / 2;
     t->emit_bytes = 2 * emit_bytes;    // every FASTQ byte is read once and written once

@@ -61,14 +61,12 @@ struct RoundTable {
     int32_t m[MAX_AD];              // adapter length
     int32_t k[MAX_AD];              // int(max_error_rate * m)
     int32_t min_ov[MAX_AD];         // min(min_overlap, m)
-    uint8_t kmax[MAX_AD][MAX_M + 8];// kmax[a][L] = max cost with cost <= L * rate (fp64, R5/R6); with N wildcards in a
-                                    // 5' adapter the larger of the two tables below: what every pruning test reads
-    // The exact limits of the last-row test (R5) and the last-column test (R6): _align.pyx takes different N
-    // counts off the overlap length in the two.  They differ from kmax only for 5' adapters with N wildcards.
-    // r5_update / r6_update find them at a fixed distance behind the kmax row they are handed (KMAX_R5 / KMAX_R6),
-    // so the three arrays must stay adjacent, also in the shared-memory copies of the table head.
-    uint8_t kmax_r5[MAX_AD][MAX_M + 8];
-    uint8_t kmax_r6[MAX_AD][MAX_M + 8];
+    // kmax[a][0][L] = max cost with cost <= L * rate (fp64, R5/R6); with N wildcards in a 5' adapter the larger of
+    // the two exact tables behind it -- what every pruning test reads.  kmax[a][1] / kmax[a][2]: the exact limits
+    // of the last-row test (R5) and the last-column test (R6): _align.pyx takes different N counts off the overlap
+    // length in the two; they differ from kmax[a][0] only for 5' adapters with N wildcards.  r5_update / r6_update
+    // find them KMAX_R5 / KMAX_R6 bytes behind the row they are handed (also in compact copies of an adapter's rows).
+    uint8_t kmax[MAX_AD][3][MAX_M + 8];
     // the same, 8 codes per word, for the resolver's 16-cells-at-a-time diagonal walk:
     // code4: nibble 16+q = adapter[q] (16 zero nibbles in front); rcode4: nibble q =
     // comp(adapter[m-1-q]) (zero nibbles behind) -- what a direction-1 lane compares raw codes with
@@ -235,9 +233,7 @@ ORC_HD uint64_t nib16(const uint32_t *A, int64_t idx)
 
 
 // distance from kmax[a] to kmax_r5[a] / kmax_r6[a]
-constexpr int KMAX_R5 = MAX_AD * (MAX_M + 8), KMAX_R6 = 2 * KMAX_R5;
-static_assert(offsetof(RoundTable, kmax_r5) == offsetof(RoundTable, kmax) + KMAX_R5 &&
-              offsetof(RoundTable, kmax_r6) == offsetof(RoundTable, kmax) + KMAX_R6, "kmax, kmax_r5, kmax_r6 must be adjacent");
+constexpr int KMAX_R5 = MAX_M + 8, KMAX_R6 = 2 * KMAX_R5;
 
 // cutadapt's running best match of one Aligner.locate call (R5-R7) and one DP cell.
 struct Best { int32_t score, cost, origin, ref_stop, query_stop; };
@@ -362,6 +358,28 @@ struct ChunkReader {
         const uint32_t x = funnel_r(lo_, hi_, sh);
         A = (x >> shA) & 0x0F0F0F0Fu;
         B = (x >> shB) & 0x0F0F0F0Fu;
+    }
+};
+
+// The same with the next word already on its way while the current chunk is worked on (one word past the
+// range is read: guard words).
+struct ChunkReaderAhead {
+    ChunkReader r;
+    uint32_t pre;
+    ORC_HD void init(const uint32_t *W_, uint64_t lo, uint32_t len, int dir, uint32_t p0)
+    {
+        r.init(W_, lo, len, dir, p0);
+        pre = *r.p;
+    }
+    ORC_HD void next(uint32_t &A, uint32_t &B)
+    {
+        const uint32_t nw = pre;
+        if (!r.dir_) { r.lo_ = r.hi_; r.hi_ = nw; r.p += 1; }
+        else         { r.hi_ = r.lo_; r.lo_ = nw; r.p -= 1; }
+        pre = *r.p;
+        const uint32_t x = funnel_r(r.lo_, r.hi_, r.sh);
+        A = (x >> r.shA) & 0x0F0F0F0Fu;
+        B = (x >> r.shB) & 0x0F0F0F0Fu;
     }
 };
 
@@ -1519,7 +1537,7 @@ ORC_HD void resolve_begin(const uint32_t *W, const View &v, const RoundTable &T,
     const int a = (int)t.lane % T.n_adapters;
     C.dir = (int)t.lane / T.n_adapters;
     C.m = T.m[a]; C.k = T.k[a]; C.min_ov = T.min_ov[a];
-    C.kmax = T.kmax[a];
+    C.kmax = T.kmax[a][0];
     C.peq_lane = &T.peq[t.lane >> 5][0][t.lane & 31];
     C.lane = (int)t.lane;
     C.code4 = T.code4[a]; C.rcode4 = T.rcode4[a];
@@ -1594,14 +1612,73 @@ ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, 
 // Tasks whose end cells span more than 30 - 2k diagonals, or whose scan is longer than BAND_COLS columns,
 // keep the wide resolver above.
 // ------------------------------------------------------------------------------------
-constexpr int BAND_COLS = 96;           // columns of one scan, entry 0 unused
+constexpr int BAND_COLS = 80;           // columns of one scan, entry 0 unused
+constexpr int BAND_CODE_WORDS = 16;     // packed read codes a scan and its walks touch: BAND_COLS + 16 before + 24 behind
 constexpr uint32_t TASK_WIDE = 1u;      // Task.pad_ bit 0: not eligible for the band resolver
 
 struct alignas(8) BandEntry { uint32_t pv, d0; };
+// What the band resolver reads of one adapter, compact (the kernel keeps one per adapter of the round in
+// shared memory; RoundTable spreads the same over arrays sized for MAX_AD adapters)
+struct BandAdapter {
+    int32_t m, k, min_ov, pad_;
+    uint32_t code4[12], rcode4[12];
+    uint8_t kmax[3][MAX_M + 8];         // RoundTable.kmax[a]: pruning limits, R5 limits, R6 limits
+};
 struct BandRing {                       // entry c of this thread: p[c * stride]
     BandEntry *p;
     int32_t stride;
+    // the packed codes of the read around the scan, copied once per scan (16 loads in flight together) so that
+    // neither the column loop nor the walks wait for global memory: word w0 + i of the code array at cw[i * stride]
+    uint32_t *cw;
+    int64_t w0;
 };
+
+// 16 consecutive codes starting at code index idx, from the ring's copy
+ORC_HD uint64_t band_nib16(const BandRing &R, int64_t idx)
+{
+    const int w = (int)((idx >> 3) - R.w0);
+    const uint32_t sh = (uint32_t)(idx & 7) * 4u;
+    const uint32_t a = R.cw[w * R.stride], b = R.cw[(w + 1) * R.stride], c = R.cw[(w + 2) * R.stride];
+    return (uint64_t)funnel_r(a, b, sh) | ((uint64_t)funnel_r(b, c, sh) << 32);
+}
+
+// ChunkReader over the ring's copy of the codes
+struct BandReader {
+    const uint32_t *cw;
+    int32_t stride, w, dir_;
+    uint32_t lo_, hi_, sh, shA, shB;
+    ORC_HD void init(const BandRing &R, uint64_t lo, uint32_t len, int dir, uint32_t p0)
+    {
+        const int64_t s = dir ? (int64_t)lo + (int64_t)len - 8 - (int64_t)p0 : (int64_t)lo + (int64_t)p0;
+        cw = R.cw; stride = R.stride; dir_ = dir;
+        w = (int)((s >> 3) - R.w0);
+        sh = (uint32_t)(s & 7) * 4u;
+        shA = dir ? 4u : 0u;
+        shB = dir ? 0u : 4u;
+        if (!dir) { hi_ = cw[w * stride]; w += 1; lo_ = 0; }
+        else      { lo_ = cw[(w + 1) * stride]; hi_ = 0; }
+    }
+    ORC_HD void next(uint32_t &A, uint32_t &B)
+    {
+        const uint32_t nw = cw[w * stride];
+        if (!dir_) { lo_ = hi_; hi_ = nw; w += 1; }
+        else       { hi_ = lo_; lo_ = nw; w -= 1; }
+        const uint32_t x = funnel_r(lo_, hi_, sh);
+        A = (x >> shA) & 0x0F0F0F0Fu;
+        B = (x >> shB) & 0x0F0F0F0Fu;
+    }
+};
+
+// Copy the code words one scan (columns ws+1..we of the view, lane direction dir) and its walks read.
+ORC_HD void band_load_codes(const uint32_t *W, uint64_t lo, uint32_t len, int dir, int ws, int we, BandRing &R)
+{
+    // lowest code index touched: direction 0 walks look 16 codes back from column ws + 1; direction 1 reads
+    // upwards from the code of column we
+    const int64_t first = dir ? (int64_t)lo + (int64_t)len - we : (int64_t)lo + ws - 16;
+    R.w0 = first >> 3;                  // arithmetic shift: floors also below zero (guard words in front)
+#pragma unroll
+    for (int i = 0; i < BAND_CODE_WORDS; i++) R.cw[i * R.stride] = W[R.w0 + i];
+}
 
 // Geometry of a task's scans (what resolve_begin derives from the hull).
 struct ResolveGeo {
@@ -1659,19 +1736,27 @@ ORC_HD bool task_band_ok(int type, int m, int k, int n, const Task &t)
     return true;
 }
 
-// bits s .. s+31 of x; positions below bit 0 or above bit 63 read as zero (s may be negative)
-ORC_HD uint32_t band_window(uint64_t x, int s)
+ORC_HD void band_adapter_fill(const RoundTable &T, int a, BandAdapter &B)
 {
-    const int sp = imin(imax(s, -32), 64) + 32;         // 0 .. 96
-    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-    const int w = sp >> 5;
-    const uint32_t a = w == 0 ? 0u : (w == 1 ? lo : (w == 2 ? hi : 0u));
-    const uint32_t b = w == 0 ? lo : (w == 1 ? hi : 0u);
-    return funnel_r(a, b, (uint32_t)(sp & 31));
+    B.m = T.m[a]; B.k = T.k[a]; B.min_ov = T.min_ov[a]; B.pad_ = 0;
+    for (int i = 0; i < 12; i++) { B.code4[i] = T.code4[a][i]; B.rcode4[i] = T.rcode4[a][i]; }
+    for (int t = 0; t < 3; t++)
+        for (int i = 0; i < MAX_M + 8; i++) B.kmax[t][i] = T.kmax[a][t][i];
+}
+
+// The band resolver's own match table: per (lane bank, read code, lane % 32) four words {ones, low word,
+// high word, zeros} of the lane's 64-bit match vector, so that the 32 band rows of any column -- rows below
+// the adapter read as matches (they stand for row 0), rows above it as mismatches -- are two adjacent words
+// and one funnel shift away: entry at code * 512 + (lane % 32) * 16 inside a bank of BAND_BANK_BYTES.
+constexpr int BAND_BANK_BYTES = 16 * 32 * 16;
+ORC_HD void band_table_entry(const RoundTable &T, int bank, int code, int l, uint32_t out[4])
+{
+    const uint64_t v = T.peq[bank][code][l];
+    out[0] = 0xFFFFFFFFu; out[1] = (uint32_t)v; out[2] = (uint32_t)(v >> 32); out[3] = 0u;
 }
 
 struct BandCtx {
-    const char *peq_base;               // the lane's bank of the 64-bit match table
+    const char *peq_base;               // the lane's bank of the band match table (band_table_entry)
     const uint32_t *code4, *rcode4;
     const uint8_t *kmax;
     int32_t dir, lane, m, k, min_ov, n, type;
@@ -1712,7 +1797,7 @@ ORC_HD void band_trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int di
         if (j == 0) { origin = (type == TYPE_FRONT) ? -i : 0; break; }
         if (j <= ws) { origin = j; break; }          // unreachable for a genuine candidate
         const int avail = imin(16, imin(i, j - ws));
-        const uint64_t r = nib16(W, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
+        const uint64_t r = band_nib16(R, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
         const uint64_t a = nib16(dir ? rcode4 : code4, dir ? (int64_t)(m - i) : (int64_t)i);
         uint64_t x = r & a;
         x |= x >> 1; x |= x >> 2;
@@ -1739,7 +1824,7 @@ ORC_HD void band_trace_back_group(uint32_t mask, bool on, const uint32_t *W, uin
             else if (j <= ws) { origin = j; on = false; }
             else {
                 const int avail = imin(16, imin(i, j - ws));
-                const uint64_t r = nib16(W, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
+                const uint64_t r = band_nib16(R, dir ? (int64_t)lo + (int64_t)len - j : (int64_t)lo + j - 16);
                 const uint64_t a = nib16(dir ? rcode4 : code4, dir ? (int64_t)(m - i) : (int64_t)i);
                 uint64_t x = r & a;
                 x |= x >> 1; x |= x >> 2;
@@ -1767,21 +1852,14 @@ ORC_HD void band_trace_back_group(uint32_t mask, bool on, const uint32_t *W, uin
 // stay 0, like the padding bits of the 64-bit table.  What comes out per column, VP and D0, is already
 // the ring entry.
 //
-// Costs are not a popcount away here (row 0 is not in the band), and none is needed by the walks.  The
-// hull columns' D[m][j] start from the scan's D[m][jf] (Task anchors) and follow the horizontal deltas of
-// row m; R5 then runs as in resolve_columns (narrow hull: note the best bound; otherwise walk on the spot).
-ORC_HD void band_columns(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, const BandRing &R)
+// The column loop is the same for every lane and every column (the lanes of a warp differ only in its
+// length).  Costs are not a popcount away here (row 0 is not in the band), and none is needed by the walks;
+// for the hull columns' D[m][j] every ring entry also carries the horizontal delta of row m in the two
+// bits no walk reads (bit 31 of both words: the band keeps a spare row on either side), and band_hull()
+// counts on from the scan's D[m][jf] (Task anchors) afterwards.
+ORC_HD void band_columns(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, BandRing &R)
 {
-    const int m = C.m, n = C.n, k = C.k, ws = C.ws, we = C.we, jf = C.jf, jl = C.jl, dir = C.dir, boff = C.boff;
-    C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
-    C.narrow = (jf <= jl && (jl - jf) + 2 * k <= m / 2) ? 1 : 0;
-    C.top_j = -1;
-    C.broke = 0;
-    C.hc0 = ~0ull; C.hc1 = ~0ull;
-    int top_ub = -(1 << 20);
-    C.ubw = (ws == 0 && C.type == TYPE_BACK) ? 1 : 2;
-    const int ubw = C.ubw;
-    const bool narrow = C.narrow != 0;
+    const int m = C.m, ws = C.ws, we = C.we, dir = C.dir, boff = C.boff;
     uint32_t VP, VN = 0;
     if (ws == 0 && C.type == TYPE_FRONT) VP = 0;                // R2: column 0 of a 5' adapter costs 0 in every row
     else {
@@ -1793,73 +1871,94 @@ ORC_HD void band_columns(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &
     uint32_t sel0, sel1, sel2, sel3;
     if (!dir) { sel0 = 0x5504u; sel1 = 0x5514u; sel2 = 0x5524u; sel3 = 0x5534u; }
     else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
-    ChunkReader rd;
-    rd.init(W, lo, len, dir, (uint32_t)ws);
+    band_load_codes(W, lo, len, dir, ws, we, R);
+    BandReader rd;
+    rd.init(R, lo, len, dir, (uint32_t)ws);
     const int ncols = we - ws;
     const int nchunks = (ncols + 7) >> 3;
-    const int sbase = 63 - m - boff + ws;                       // vector bit of band position 0, column ws
-    uint32_t HP = 0, HN = 0;
+    // band position 0 of column ws + c is vector bit 63 - m - boff + ws + c; the table has 32 rows of ones in
+    // front of the vector (hence + 32), clamped to [0, 95]: below, everything matches; above, nothing does
+    const int sp0 = 63 - m - boff + ws + 32;
+    // row m is band position boff - (j - m) of column j
+    const int bm0 = boff + m - ws;
     auto column = [&](uint32_t A, uint32_t B, int t, int c) {
         const uint32_t src = (t & 1) ? B : A;
         const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
-        const uint64_t Eq64 = *reinterpret_cast<const uint64_t *>(peq_base + byte_perm(src, lane8, sel));
-        const uint32_t Eq = ~band_window(~Eq64, sbase + c);     // rows below the table read as matches
+        const int sp = imin(imax(sp0 + c, 0), 95);
+        const uint32_t *e = reinterpret_cast<const uint32_t *>(peq_base + 2u * byte_perm(src, lane8, sel)) + (sp >> 5);
+        const uint32_t Eq = funnel_r(e[0], e[1], (uint32_t)sp & 31u);
         VP = (VP >> 1) | 0x80000000u;
         VN >>= 1;
         const uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
-        HP = VN | ~(D0 | VP);
-        HN = D0 & VP;
+        const uint32_t HP = VN | ~(D0 | VP);
+        const uint32_t HN = D0 & VP;
         const uint32_t X = HP << 1;
         VP = (HN << 1) | ~(D0 | X);
         VN = D0 & X;
-        BandEntry e;
-        e.pv = VP; e.d0 = D0;
-        R.p[c * R.stride] = e;
+        const uint32_t bm = (uint32_t)(bm0 - c) & 31u;          // meaningful on the hull columns only
+        BandEntry en;
+        en.pv = (VP & 0x7FFFFFFFu) | (((HP >> bm) & 1u) << 31);
+        en.d0 = (D0 & 0x7FFFFFFFu) | (((HN >> bm) & 1u) << 31);
+        R.p[c * R.stride] = en;
     };
-    int D = C.c5;
     for (int q = 0; q < nchunks; q++) {
         uint32_t A, B;
         rd.next(A, B);
         const int ncol = imin(8, ncols - 8 * q);
-        const int jb = ws + 8 * q;
-        if (ncol == 8 && (jb + 8 < jf || jb + 1 > jl)) {
+        if (ncol == 8) {
 #pragma unroll
             for (int t = 0; t < 8; t++) column(A, B, t, 8 * q + t + 1);
-            continue;
-        }
-#pragma unroll 1
-        for (int t = 0; t < ncol; t++) {
-            const int j = jb + t + 1;
-            column(A, B, t, j - ws);
-            if (j < jf || j > jl) continue;
-            if (j > jf) {                                       // D[m][j] along row m, band position boff - (j - m)
-                const uint32_t bm = (uint32_t)(boff - (j - m));
-                D += (int)((HP >> bm) & 1u) - (int)((HN >> bm) & 1u);
-            }
-            if (D <= k) {
-                const int lmax = imin(m, j + D);
-                if (lmax >= C.min_ov && D <= (int)C.kmax[lmax]) {
-                    const int ub = lmax - ubw * D;
-                    {   // D[m][j] of the candidate columns: the narrow hull's walks and R6's cell (m, n) read them
-                        const int hq = j - jf;                  // < 32 for every band-eligible hull
-                        const uint64_t clr = ~(15ull << (4 * (hq & 15)));
-                        const uint64_t put = (uint64_t)D << (4 * (hq & 15));
-                        if (hq < 16) C.hc0 = (C.hc0 & clr) | put; else C.hc1 = (C.hc1 & clr) | put;
-                    }
-                    if (narrow) {
-                        if (ub > top_ub) { top_ub = ub; C.top_j = j; }
-                    } else if (C.best.cost == m + n + 1 || ub > C.best.score) {
-                        Cell c;
-                        c.cost = D;
-                        band_trace_back(W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, boff, m, j, D, c.score, c.origin);
-                        C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin;
-                        if (r5_update(C.best, m, n, c, j, C.min_ov, C.kmax)) { C.broke = 1; return; }
-                    }
-                }
-            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) if (t < ncol) column(A, B, t, 8 * q + t + 1);
         }
     }
     C.vpn = VP; C.vnn = VN;             // column we (column n when the scan reached it)
+}
+
+// R5 over the hull columns jf..jl of the scan just stored, exactly as resolve_columns does it while it
+// scans: D[m][j] from the anchor and the stored deltas of row m; narrow hull: note the costs and the
+// candidate with the best bound (band_finish walks them); otherwise walk on the spot, in column order.
+ORC_HD void band_hull(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, const BandRing &R)
+{
+    const int m = C.m, n = C.n, k = C.k, ws = C.ws, jf = C.jf, jl = C.jl, dir = C.dir, boff = C.boff;
+    C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
+    C.narrow = (jf <= jl && (jl - jf) + 2 * k <= m / 2) ? 1 : 0;
+    C.top_j = -1;
+    C.broke = 0;
+    C.hc0 = ~0ull; C.hc1 = ~0ull;
+    int top_ub = -(1 << 20);
+    C.ubw = (ws == 0 && C.type == TYPE_BACK) ? 1 : 2;
+    const int ubw = C.ubw;
+    const bool narrow = C.narrow != 0;
+    int D = C.c5;
+    for (int j = jf; j <= jl; j++) {
+        if (j > jf) {
+            const BandEntry e = R.p[(j - ws) * R.stride];
+            D += (int)(e.pv >> 31) - (int)(e.d0 >> 31);
+        }
+        if (D > k) continue;
+        const int lmax = imin(m, j + D);
+        if (!(lmax >= C.min_ov && D <= (int)C.kmax[lmax])) continue;
+        const int ub = lmax - ubw * D;
+        {   // D[m][j] of the candidate columns: the narrow hull's walks and R6's cell (m, n) read them
+            const int hq = j - jf;                              // < 32 for every band-eligible hull
+            const uint64_t clr = ~(15ull << (4 * (hq & 15)));
+            const uint64_t put = (uint64_t)D << (4 * (hq & 15));
+            if (hq < 16) C.hc0 = (C.hc0 & clr) | put; else C.hc1 = (C.hc1 & clr) | put;
+        }
+        if (narrow) {
+            if (ub > top_ub) { top_ub = ub; C.top_j = j; }      // highest bound, leftmost
+        } else if (C.best.cost == m + n + 1 || ub > C.best.score) {
+            // a candidate that cannot beat the best so far cannot change it (every R5 update after the
+            // first needs a strictly higher score)
+            Cell c;
+            c.cost = D;
+            band_trace_back(W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, boff, m, j, D, c.score, c.origin);
+            C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin;
+            if (r5_update(C.best, m, n, c, j, C.min_ov, C.kmax)) { C.broke = 1; return; }
+        }
+    }
 }
 
 ORC_HD void band_finish(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, const BandRing &R,
@@ -1934,21 +2033,21 @@ ORC_HD void band_finish(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C
     }
 }
 
-ORC_HD void band_begin(const uint32_t *W, const View &v, const RoundTable &T, const Task &t,
-                       BandCtx &C, const BandRing &R, const char *peq_base)
+ORC_HD void band_begin(const uint32_t *W, const View &v, int type, int n_adapters, const BandAdapter *ads,
+                       const Task &t, BandCtx &C, BandRing &R, const char *peq_base)
 {
-    const int a = (int)t.lane % T.n_adapters;
-    C.dir = (int)t.lane / T.n_adapters;
-    C.m = T.m[a]; C.k = T.k[a]; C.min_ov = T.min_ov[a];
-    C.kmax = T.kmax[a];
+    const BandAdapter &A = ads[(int)t.lane % n_adapters];
+    C.dir = (int)t.lane / n_adapters;
+    C.m = A.m; C.k = A.k; C.min_ov = A.min_ov;
+    C.kmax = A.kmax[0];
     C.peq_base = peq_base;
     C.lane = (int)t.lane;
-    C.code4 = T.code4[a]; C.rcode4 = T.rcode4[a];
+    C.code4 = A.code4; C.rcode4 = A.rcode4;
     C.n = (int)v.len;
-    C.type = T.type;
+    C.type = type;
     const int m = C.m, n = C.n;
     C.best.ref_stop = m; C.best.query_stop = n; C.best.cost = m + n + 1; C.best.origin = 0; C.best.score = 0;
-    resolve_geometry(T.type, m, C.k, n, t, C.G);
+    resolve_geometry(type, m, C.k, n, t, C.G);
     C.broke = 0; C.narrow = 0; C.top_j = -1; C.ubw = 2; C.boff = 0;
     C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
     C.hc0 = C.hc1 = ~0ull; C.vpn = C.vnn = 0;
@@ -1960,24 +2059,28 @@ ORC_HD void band_begin(const uint32_t *W, const View &v, const RoundTable &T, co
     }
 }
 
-ORC_HD void band_end(const uint32_t *W, const View &v, BandCtx &C, PairResult &res, const BandRing &R,
+ORC_HD void band_end(const uint32_t *W, const View &v, BandCtx &C, PairResult &res, BandRing &R,
                      uint32_t mask = 0xffffffffu)
 {
+    band_hull(W, v.lo, v.len, C, R);
     band_finish(W, v.lo, v.len, C, R, mask, true);
     if (C.G.second && !C.broke) {
         C.ws = C.G.ws6; C.we = C.n; C.jf = 1; C.jl = 0; C.r6 = 1;
         band_scan_ok(C.m, C.k, C.n, C.ws, C.we, 1, 0, true, C.G.r6lo, C.G.r6hi, C.boff);
         band_columns(W, v.lo, v.len, C, R);
+        band_hull(W, v.lo, v.len, C, R);
         band_finish(W, v.lo, v.len, C, R, mask, false);
     }
     best_to_result(C.best, C.m, C.n, res);
 }
 
-ORC_HD void band_resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, const Task &t,
-                              PairResult &res, const BandRing &R)
+// band_table: the table band_table_entry() describes, all banks of the round; ads: one BandAdapter per
+// adapter (the host simulation builds both per round)
+ORC_HD void band_resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, const BandAdapter *ads, const Task &t,
+                              PairResult &res, BandRing &R, const char *band_table)
 {
     BandCtx C;
-    band_begin(W, v, T, t, C, R, peq_bank(T, (int)t.lane));
+    band_begin(W, v, T.type, T.n_adapters, ads, t, C, R, band_table + (size_t)(t.lane >> 5) * BAND_BANK_BYTES);
     band_end(W, v, C, res, R);
 }
 

@@ -284,13 +284,13 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
 {
     __shared__ __align__(16) uint32_t s_peq32b[16][64];
     __shared__ uint32_t s_first_mask[MAX_M + 32];
-    __shared__ uint8_t s_kmax[MAX_AD][MAX_M + 8];
+    __shared__ uint8_t s_kmax[MAX_AD][MAX_M + 8];     // the pruning limits (kmax[a][0])
     __shared__ int s_k[MAX_AD], s_min_ov[MAX_AD], s_lb[MAX_AD], s_m[MAX_AD];
     __shared__ int s_na, s_type;
     for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32b[0][0])[i] = (&tab->peq32b[0][0])[i];
     for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_mask[i] = tab->first_mask[i];
     for (int i = threadIdx.x; i < MAX_AD * (MAX_M + 8); i += blockDim.x)
-        (&s_kmax[0][0])[i] = tab->kmax[i / (MAX_M + 8)][i % (MAX_M + 8)];
+        (&s_kmax[0][0])[i] = tab->kmax[i / (MAX_M + 8)][0][i % (MAX_M + 8)];
     if (threadIdx.x < MAX_AD) {
         s_k[threadIdx.x] = tab->k[threadIdx.x];
         s_min_ov[threadIdx.x] = tab->min_ov[threadIdx.x];
@@ -411,7 +411,7 @@ scan_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                 uint4 *dst = reinterpret_cast<uint4 *>(&wl);
                 dst[0] = src[0]; dst[1] = src[1];
             }
-            scan_lane(W, v.lo, v.len, dir, &wl, peq_bank(T, tl), tl, T.pv0[tl], T.d0[tl], m, T.k[a], T.kmax[a],
+            scan_lane(W, v.lo, v.len, dir, &wl, peq_bank(T, tl), tl, T.pv0[tl], T.d0[tl], m, T.k[a], T.kmax[a][0],
                       T.min_ov[a], type, L, T.indels, T.code4[a], T.rcode4[a], T.chunk_lut);
             has = L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2;
             need = has && L.need != 0;
@@ -526,10 +526,12 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
 // table that the round uses are staged next to the ring; the acceptance limits and the packed adapter
 // codes, touched a few times per task, are read through L1 from the table in global memory.
 constexpr int BAND_THREADS = 64;
-inline size_t band_smem_bytes(int n_lanes)
+inline size_t band_smem_bytes(int n_lanes, int n_adapters)
 {
-    return (size_t)((n_lanes + 31) / 32) * 4096u + (size_t)BAND_COLS * BAND_THREADS * sizeof(BandEntry);
+    return (size_t)((n_lanes + 31) / 32) * BAND_BANK_BYTES + (size_t)n_adapters * sizeof(BandAdapter) +
+           (size_t)BAND_COLS * BAND_THREADS * sizeof(BandEntry) + (size_t)BAND_CODE_WORDS * BAND_THREADS * sizeof(uint32_t);
 }
+static_assert(sizeof(BandAdapter) % 8 == 0, "the ring behind the adapter table must stay 8-byte aligned");
 
 __global__ void __launch_bounds__(BAND_THREADS)
 resolve_band_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
@@ -538,17 +540,20 @@ resolve_band_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restri
                     unsigned long long *__restrict__ best_key, uint32_t cap_pairs)
 {
     extern __shared__ __align__(16) unsigned char s_band[];
-    const int n_banks = (tab->n_lanes + 31) / 32;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&tab->peq[0][0][0]);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_band);
-        for (int i = threadIdx.x; i < n_banks * 256; i += blockDim.x) dst[i] = src[i];
+    const int n_banks = (tab->n_lanes + 31) / 32, na = tab->n_adapters, type = tab->type;
+    for (int i = threadIdx.x; i < n_banks * 16 * 32; i += blockDim.x) {     // the band's own match table
+        uint32_t e[4];
+        band_table_entry(*tab, i >> 9, (i >> 5) & 15, i & 31, e);
+        reinterpret_cast<uint4 *>(s_band)[i] = make_uint4(e[0], e[1], e[2], e[3]);
     }
+    BandAdapter *s_ads = reinterpret_cast<BandAdapter *>(s_band + (size_t)n_banks * BAND_BANK_BYTES);
+    for (int a = threadIdx.x; a < na; a += blockDim.x) band_adapter_fill(*tab, a, s_ads[a]);
     __syncthreads();
-    const RoundTable &T = *tab;
     BandRing ring;
-    ring.p = reinterpret_cast<BandEntry *>(s_band + (size_t)n_banks * 4096u) + threadIdx.x;
+    ring.p = reinterpret_cast<BandEntry *>(s_ads + na) + threadIdx.x;
     ring.stride = BAND_THREADS;
+    ring.cw = reinterpret_cast<uint32_t *>(reinterpret_cast<BandEntry *>(s_ads + na) + BAND_COLS * BAND_THREADS) + threadIdx.x;
+    ring.w0 = 0;
     const uint32_t n = min(*work_count, cap_pairs);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
@@ -564,7 +569,8 @@ resolve_band_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restri
         }
         if (act) {
             v = views[task.read];
-            band_begin(W, v, T, task, C, ring, reinterpret_cast<const char *>(s_band) + (size_t)(task.lane >> 5) * 4096u);
+            band_begin(W, v, type, na, s_ads, task, C, ring,
+                       reinterpret_cast<const char *>(s_band) + (size_t)(task.lane >> 5) * BAND_BANK_BYTES);
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, act);      // also the meeting point
         if (act) {
@@ -574,8 +580,8 @@ resolve_band_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restri
             band_end(W, v, C, res, ring, mask);
             results[task.slot] = res;
             if (res.has) {
-                const int a = (int)task.lane % T.n_adapters;
-                const int o = ((int)task.lane / T.n_adapters) ^ (int)(v.rc & 1u);
+                const int a = (int)task.lane % na;
+                const int o = ((int)task.lane / na) ^ (int)(v.rc & 1u);
                 atomicMax(best_key + (size_t)task.read * 2 + o,
                           (unsigned long long)pack_key(res.score, res.errors, a, task.slot));
             }

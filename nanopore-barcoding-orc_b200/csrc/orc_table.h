@@ -103,9 +103,9 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
             int c5 = (int)floor(eff5 * rate), c6 = (int)floor(eff6 * rate);
             c5 = c5 < 0 ? 0 : (c5 > 255 ? 255 : c5);
             c6 = c6 < 0 ? 0 : (c6 > 255 ? 255 : c6);
-            T.kmax_r5[a][L] = (uint8_t)c5;
-            T.kmax_r6[a][L] = (uint8_t)c6;
-            T.kmax[a][L] = (uint8_t)(c5 > c6 ? c5 : c6);
+            T.kmax[a][1][L] = (uint8_t)c5;
+            T.kmax[a][2][L] = (uint8_t)c6;
+            T.kmax[a][0][L] = (uint8_t)(c5 > c6 ? c5 : c6);
         }
     }
     if (n_wild != 0 && n_wild != n_adapters)
@@ -181,7 +181,7 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
         int v = 0;
         for (int a = 0; a < n_adapters; a++) {
             const int l = L < T.m[a] ? L : T.m[a];
-            if (T.kmax[a][l] > v) v = T.kmax[a][l];
+            if (T.kmax[a][0][l] > v) v = T.kmax[a][0][l];
         }
         T.kmax_any[L] = (uint8_t)v;
     }

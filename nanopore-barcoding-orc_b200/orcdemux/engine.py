@@ -188,6 +188,26 @@ class Engine:
         b = self._batch(rs)
         self._check(self._L.orc_upload(self._ctx, slot, C.byref(b)), "orc_upload")
 
+    def synth(self, slot: int, seed: int, n_reads: int, len_min: int = 300, len_max: int = 900):
+        """Make a shard of synthetic reads on the device (orc_synth): the slot then holds it like an upload."""
+        self._inflight[slot] = None
+        self._check(self._L.orc_synth(self._ctx, slot, seed, n_reads, len_min, len_max), "orc_synth")
+
+    def export(self, slot: int):
+        """The batch resident in a slot as a synth.ReadSet on the host (orc_export)."""
+        from .synth import ReadSet
+        n, nb, nn = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.orc_resident(self._ctx, slot, C.byref(n), C.byref(nb), C.byref(nn)), "orc_resident")
+        seq = np.empty(nb.value, np.uint8)
+        qual = np.empty(nb.value, np.uint8)
+        off = np.empty(n.value, np.uint64)
+        ln = np.empty(n.value, np.uint32)
+        names = np.empty(nn.value, np.uint8)
+        noff = np.empty(n.value + 1, np.uint64)
+        self._check(self._L.orc_export(self._ctx, slot, seq.ctypes.data, qual.ctypes.data, off.ctypes.data,
+                                       ln.ctypes.data, names.ctypes.data, noff.ctypes.data), "orc_export")
+        return ReadSet(seq, qual, off, ln, names, noff, {})
+
     def launch(self, slot: int):
         self._check(self._L.orc_launch(self._ctx, slot), "orc_launch")
 
@@ -231,7 +251,11 @@ class Engine:
         return dict(pack_ms=t.pack_ms, trigger_ms=list(t.trigger_ms), scan_ms=list(t.scan_ms), resolve_ms=list(t.resolve_ms), bin_ms=t.bin_ms,
                     emit_ms=t.emit_ms, total_ms=t.total_ms, h2d_ms=t.h2d_ms, d2h_ms=t.d2h_ms,
                     kernel_launches=t.kernel_launches, n_tasks=list(t.n_tasks), n_candidates=list(t.n_candidates), cells=list(t.cells), cells_executed=list(t.cells_executed),
-                    pack_bytes=t.pack_bytes, emit_bytes=t.emit_bytes)
+                    pack_bytes=t.pack_bytes, emit_bytes=t.emit_bytes,
+                    kernel_ms=[{nm: float(t.kernel_ms[r][i]) for i, nm in enumerate(_lib.KERNEL_NAMES)}
+                               for r in range(len(self.rounds))],
+                    window_columns=list(t.window_columns), cells_2b=list(t.cells_2b),
+                    n_pairs_2b=list(t.n_pairs_2b), n_tasks_wide=list(t.n_tasks_wide))
 
     def timer_start(self, slot: int = 0):
         self._check(self._L.orc_timer_start(self._ctx, slot), "orc_timer_start")

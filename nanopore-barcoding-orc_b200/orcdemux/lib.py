@@ -17,6 +17,8 @@ SO_PATH = os.path.join(_HERE, "liborcdemux.so")
 ORC_MAX_ROUNDS = 2
 ORC_MAX_ADAPTERS = 32
 ORC_MAX_ADAPTER_LEN = 64
+KERNEL_NAMES = ["sort_reads", "seed", "trigger", "sort_items", "filter", "scan", "resolve_band", "resolve_wide", "select"]
+ORC_N_KERNELS = len(KERNEL_NAMES)
 ORC_FRONT, ORC_BACK, ORC_PREFIX, ORC_SUFFIX = 0, 1, 2, 3
 ORC_OK, ORC_EINVAL, ORC_ECUDA, ORC_ECAPACITY, ORC_ESTATE = 0, -1, -2, -3, -4
 
@@ -26,7 +28,7 @@ EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_sub
            "orc_fastq_index", "orc_host_alloc", "orc_host_free", "orc_measure_int32_peak", "orc_version",
            "orc_reader_open", "orc_reader_next", "orc_reader_release", "orc_reader_error", "orc_reader_close",
            "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close",
-           "orc_edit_distances"]
+           "orc_edit_distances", "orc_synth", "orc_resident", "orc_export"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -70,7 +72,10 @@ class Timings(C.Structure):
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("n_tasks", C.c_uint32 * ORC_MAX_ROUNDS),
                 ("n_candidates", C.c_uint32 * ORC_MAX_ROUNDS),
-                ("cells", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_executed", C.c_uint64 * ORC_MAX_ROUNDS), ("pack_bytes", C.c_uint64), ("emit_bytes", C.c_uint64)]
+                ("cells", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_executed", C.c_uint64 * ORC_MAX_ROUNDS), ("pack_bytes", C.c_uint64), ("emit_bytes", C.c_uint64),
+                ("kernel_ms", (C.c_float * ORC_N_KERNELS) * ORC_MAX_ROUNDS),
+                ("window_columns", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_2b", C.c_uint64 * ORC_MAX_ROUNDS),
+                ("n_pairs_2b", C.c_uint32 * ORC_MAX_ROUNDS), ("n_tasks_wide", C.c_uint32 * ORC_MAX_ROUNDS)]
 
 
 class TextBatchC(C.Structure):
@@ -148,6 +153,12 @@ def load():
     L.orc_edit_distances.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                      C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_char_p, C.c_size_t]
     L.orc_edit_distances.restype = C.c_int
+    L.orc_synth.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.orc_synth.restype = C.c_int
+    L.orc_resident.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.orc_resident.restype = C.c_int
+    L.orc_export.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    L.orc_export.restype = C.c_int
     L.orc_version.argtypes = []
     L.orc_version.restype = C.c_char_p
     _lib = L

@@ -75,8 +75,21 @@ extern "C" int hostsim_demux(int n_rounds,
 
     ColRing *ring = new ColRing;
     BandEntry *band = new BandEntry[BAND_COLS];
-    BandRing bring; bring.p = band; bring.stride = 1;
+    uint32_t band_codes[BAND_CODE_WORDS];
+    BandRing bring; bring.p = band; bring.stride = 1; bring.cw = band_codes; bring.w0 = 0;
     const bool force_wide = (filter_mode_in & 8) != 0;
+    std::vector<uint32_t> band_tab[2];
+    std::vector<BandAdapter> band_ads[2];
+    for (int rd = 0; rd < n_rounds; rd++) {
+        band_ads[rd].resize(MAX_AD);
+        if (!anch[rd]) for (int a = 0; a < T[rd].n_adapters; a++) band_adapter_fill(T[rd], a, band_ads[rd][a]);
+        band_tab[rd].assign((size_t)(MAX_LANES / 32) * BAND_BANK_BYTES / 4, 0u);
+        if (!anch[rd])
+            for (int bank = 0; bank < MAX_LANES / 32; bank++)
+                for (int c = 0; c < 16; c++)
+                    for (int l = 0; l < 32; l++)
+                        band_table_entry(T[rd], bank, c, l, &band_tab[rd][((size_t)bank * 16 * 32 + (size_t)c * 32 + l) * 4]);
+    }
     n_tasks[0] = n_tasks[1] = 0;
     n_columns[0] = n_columns[1] = 0;
     for (uint32_t r = 0; r < n_reads; r++) {
@@ -126,11 +139,11 @@ extern "C" int hostsim_demux(int n_rounds,
                 g_pairs[rd]++;
                 if (R.indels && !block_test(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr,
                                             (const char *)&R.peq32b[0][0], lane, R.block_len[a], R.k[a], R.type,
-                                            R.kmax[a], R.min_ov[a], R.first_mask)) continue;
+                                            R.kmax[a][0], R.min_ov[a], R.first_mask)) continue;
                 g_kept[rd]++;
                 LaneScan L;
                 scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, peq_bank(R, lane), lane,
-                          R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a], R.min_ov[a], R.type, L,
+                          R.pv0[lane], R.d0[lane], R.m[a], R.k[a], R.kmax[a][0], R.min_ov[a], R.type, L,
                           R.indels, R.code4[a], R.rcode4[a], R.chunk_lut);
                 if (L.h.jf <= L.h.jl || L.h.i1 <= L.h.i2) {
                     PairResult pr; memset(&pr, 0, sizeof(pr));
@@ -142,7 +155,7 @@ extern "C" int hostsim_demux(int n_rounds,
                         t.pad_ = task_anchors(L);
                         // what scan_kernel decides per task: the band resolver when the task fits it
                         if (!force_wide && task_band_ok(R.type, R.m[a], R.k[a], (int)v.len, t)) {
-                            band_resolve_pair(W, v, R, t, pr, bring);
+                            band_resolve_pair(W, v, R, band_ads[rd].data(), t, pr, bring, (const char *)band_tab[rd].data());
                             g_band++;
                         } else {
                             resolve_pair(W, v, R, t, pr, *ring);

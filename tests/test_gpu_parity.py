@@ -437,3 +437,46 @@ def test_no_indels_unanchored_gpu():
     assert H.diff_matches(rec1, res.matches[1])[1] == 0
     assert np.array_equal(res.out_len, olen)
     assert t["n_tasks"] == [0, 0]
+
+
+def test_device_generated_shards_config5():
+    """BASELINE configs[4]'s input path: shards made on the GPU by orc_synth (seed = (1005 << 32) + shard) are
+    deterministic, distinct, follow the read model, and demultiplex exactly like the oracle says for the
+    very bytes orc_export hands back."""
+    n = (1 << 17) if FULL else (1 << 14)
+    eng = E.Engine(E.m13_rounds(), max_reads=n, max_bytes=n * 980, max_name_bytes=24 * n, n_slots=2,
+                   emit_fastq=True, want_matches=True)
+    try:
+        eng.synth(0, (1005 << 32) + 3, n, 300, 900)
+        eng.synth(1, (1005 << 32) + 4, n, 300, 900)
+        a, b = eng.export(0), eng.export(1)
+        assert a.n_reads == n and b.n_reads == n
+        assert a.seq.shape[0] != b.seq.shape[0] or not np.array_equal(a.seq, b.seq)
+        L = a.lengths.astype(np.int64)
+        assert L.min() >= 150 and L.max() <= 1000 and 560 < L.mean() < 640
+        assert np.array_equal(a.offsets[1:], np.cumsum(L[:-1]).astype(np.uint64)) and int(a.offsets[0]) == 0
+        assert set(np.unique(a.seq).tolist()) <= set(b"ACGTN") and a.qual.min() >= 33 + 5 and a.qual.max() <= 33 + 40
+        assert a.read(0)[0] == "r0 ch=0" and a.read(1)[0] == "r1" and a.read(7)[0] == "r7 ch=7"
+        eng.launch(0)
+        eng.download(0)
+        res = eng.wait(0)
+        rec0, rec1, oseq, oqual, olen = H.run_oracle(H.m13_rounds(), a, n_threads=NCPU)
+        idx, nbad = H.diff_matches(rec0, res.matches[0])
+        assert nbad == 0, ("round 1", nbad, idx)
+        idx, nbad = H.diff_matches(rec1, res.matches[1])
+        assert nbad == 0, ("round 2", nbad, idx)
+        assert np.array_equal(res.out_len, olen)
+        exp = _expected_fastq(a, rec0, rec1, oseq, oqual, olen, 169, lambda x, y: (x + 1) + 13 * (y + 1))
+        for bb in range(169):
+            assert res.bin_bytes(bb) == exp[bb], "bin %d bytes differ" % bb
+        # the read model: most reads carry both adapters, about a tenth are reverse-complemented
+        assert (rec0["adapter"] >= 0).mean() > 0.85 and 0.05 < rec0["is_rc"].mean() < 0.15
+        valid = (rec0["adapter"] >= 0) & (rec1["adapter"] >= 0)
+        assert valid.mean() > 0.75 and len(np.unique(rec0["adapter"][valid])) == 12 and len(np.unique(rec1["adapter"][valid])) == 12
+        eng.synth(1, (1005 << 32) + 3, n, 300, 900)         # same seed: the same bytes
+        c = eng.export(1)
+        assert np.array_equal(a.seq, c.seq) and np.array_equal(a.qual, c.qual) and np.array_equal(a.names, c.names)
+        with pytest.raises(E.OrcError, match="max_reads"):
+            eng.synth(0, 1, n + 1, 300, 900)
+    finally:
+        eng.close()
