@@ -45,6 +45,8 @@ enum { SLOT_IDLE = 0, SLOT_UPLOADED, SLOT_LAUNCHED, SLOT_DOWNLOADING };
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;             // the wide resolver runs here, beside the band resolver
+    cudaEvent_t ev_fork[ORC_MAX_ROUNDS] = {}, ev_join[ORC_MAX_ROUNDS] = {}, ev_w0[ORC_MAX_ROUNDS] = {};
     int state = SLOT_IDLE;
     uint32_t n_reads = 0;
     uint64_t n_bytes = 0, name_bytes = 0, in_bases = 0;
@@ -150,6 +152,12 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     }
     s.cap_pairs = n_tasks;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+    for (int r = 0; r < ORC_MAX_ROUNDS; r++) {
+        CK(cudaEventCreateWithFlags(&s.ev_fork[r], cudaEventDisableTiming));
+        CK(cudaEventCreate(&s.ev_join[r]));
+        CK(cudaEventCreate(&s.ev_w0[r]));
+    }
     for (int i = 0; i < EV_COUNT; i++) CK(cudaEventCreate(&s.ev[i]));
     for (int r = 0; r < ORC_MAX_ROUNDS; r++)
         for (int i = 0; i <= ORC_N_KERNELS; i++) CK(cudaEventCreate(&s.evk[r][i]));
@@ -220,6 +228,12 @@ static void free_slot(Slot &s)
     for (int i = 0; i < EV_COUNT; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
     for (int r = 0; r < ORC_MAX_ROUNDS; r++)
         for (int i = 0; i <= ORC_N_KERNELS; i++) if (s.evk[r][i]) cudaEventDestroy(s.evk[r][i]);
+    for (int r = 0; r < ORC_MAX_ROUNDS; r++) {
+        if (s.ev_fork[r]) cudaEventDestroy(s.ev_fork[r]);
+        if (s.ev_join[r]) cudaEventDestroy(s.ev_join[r]);
+        if (s.ev_w0[r]) cudaEventDestroy(s.ev_w0[r]);
+    }
+    if (s.side) cudaStreamDestroy(s.side);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -585,7 +599,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     s.fresh_upload = false;
     s.did_d2h = false;
     if (n) {
-        init_views_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_offsets, s.d_lengths, n, s.d_views[0],
+        init_views_kernel<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)ctx->sm_count * 8), 256, 0, st>>>(s.d_offsets, s.d_lengths, n, s.d_views[0],
                                                            sort_hist(s.d_counters, 0, 0, 0)); nl++;
         bool need_codes = false;        // anchored rounds read the ASCII bases directly
         for (int r = 0; r < ctx->n_rounds; r++) need_codes = need_codes || !ctx->anchored[r];
@@ -657,15 +671,21 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         CK(mark(ORC_K_SCAN));
         CK(cudaEventRecord(s.ev[r == 0 ? EV_SCAN0 : EV_SCAN1], st));
         if (n && prefilter) {           // --no-indels settles every candidate in the scan: no tasks
-            resolve_band_kernel<<<ctx->band_blocks[r], BAND_THREADS, band_smem_bytes(ctx->h_tab[r].n_lanes, ctx->h_tab[r].n_adapters), st>>>(
+            // the few tasks the band resolver cannot take run beside it on the slot's side stream: their
+            // kernel is all latency (one trip per warp), which the band resolver's work hides
+            CK(cudaEventRecord(s.ev_fork[r], st));
+            CK(cudaStreamWaitEvent(s.side, s.ev_fork[r], 0));
+            CK(cudaEventRecord(s.ev_w0[r], s.side));
+            resolve_kernel<<<ctx->resolve_blocks, 128, 0, s.side>>>(ctx->d_tab[r], W, s.d_views[r],
+                                                                   s.d_tasks + s.cap_pairs, cnt + 3,
+                                                                   s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
+            CK(cudaEventRecord(s.ev_join[r], s.side));
+            resolve_band_kernel<<<ctx->band_blocks[r], BAND_THREADS,
+                                  band_smem_bytes(ctx->h_tab[r].n_lanes, ctx->h_tab[r].n_adapters), st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_tasks, cnt + 2, s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
         }
         CK(mark(ORC_K_RESOLVE_BAND));
-        if (n && prefilter) {
-            resolve_kernel<<<ctx->resolve_blocks, 128, 0, st>>>(ctx->d_tab[r], W, s.d_views[r],
-                                                               s.d_tasks + s.cap_pairs, cnt + 3,
-                                                               s.d_results, s.d_best_key, (uint32_t)s.cap_pairs); nl++;
-        }
+        if (n && prefilter) CK(cudaStreamWaitEvent(st, s.ev_join[r], 0));
         CK(mark(ORC_K_RESOLVE_WIDE));
         if (n) {
             SelectArgs A;
@@ -690,7 +710,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             A.rec_bytes = s.d_rec_bytes;
             A.next_bases = (r + 1 < ctx->n_rounds) ? s.d_cells + r + 1 : nullptr;
             A.next_len_hist = (r + 1 < ctx->n_rounds && !ctx->anchored[r + 1]) ? sort_hist(s.d_counters, r + 1, 0, 0) : nullptr;
-            select_kernel<<<(n + 127) / 128, 128, 0, st>>>(A); nl++;
+            select_kernel<<<std::min<uint32_t>((n + 127) / 128, (uint32_t)ctx->sm_count * 16), 128, 0, st>>>(A); nl++;
         }
         CK(mark(ORC_K_SELECT));
         CK(cudaEventRecord(s.ev[r == 0 ? EV_RES0 : EV_RES1], st));
@@ -899,6 +919,8 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     }
     for (int r = 0; r < ctx->n_rounds; r++) {
         for (int k = 0; k < ORC_N_KERNELS; k++) CK(cudaEventElapsedTime(&t->kernel_ms[r][k], s.evk[r][k], s.evk[r][k + 1]));
+        // (RESOLVE_WIDE: the wide resolver runs on the side stream beside the band resolver; this interval is what
+        // is left of it after the band resolver has finished)
         t->window_columns[r] = (uint64_t)cells[2 + r];
         t->cells_2b[r] = (uint64_t)cells[4 + r];
         t->n_pairs_2b[r] = counters[8 * r + 5];

@@ -76,6 +76,17 @@ __device__ __forceinline__ uint32_t sort_bucket(uint32_t key)
     return key < 1024u ? key : 1024u + min((key - 1024u) >> 6, 1023u);
 }
 
+// Read lengths only need classes of similar loop length: steps of 16 up to 4096, steps of 256 above.  Few
+// classes let a block count in shared memory and add its totals once at its end (LEN_CLASSES atomics per
+// block at most), instead of a million atomics on a few hundred hot addresses.
+constexpr int LEN_CLASSES = 512;
+__device__ __forceinline__ uint32_t len_bucket(uint32_t len)
+{
+    return len < 4096u ? len >> 4 : 256u + min((len - 4096u) >> 8, 255u);
+}
+template <bool LEN>
+__device__ __forceinline__ uint32_t class_of(uint32_t key) { return LEN ? len_bucket(key) : sort_bucket(key); }
+
 // hist[bucket] += 1 for every lane with valid set: one atomic per distinct bucket of the warp.
 // Every lane of the warp must call it.
 __device__ __forceinline__ void hist_add(uint32_t *__restrict__ hist, uint32_t bucket, bool valid)
@@ -91,16 +102,20 @@ __global__ void __launch_bounds__(256)
 init_views_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ lengths,
                   uint32_t n_reads, View *__restrict__ views, uint32_t *__restrict__ len_hist)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = r < n_reads;
-    View v;
-    v.lo = 0; v.len = 0; v.rc = 0;
-    if (valid) {
+    __shared__ uint32_t s_hist[LEN_CLASSES];
+    for (int i = threadIdx.x; i < LEN_CLASSES; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
+        View v;
         v.lo = offsets[r];
         v.len = lengths[r];
+        v.rc = 0;
         views[r] = v;
+        atomicAdd(&s_hist[len_bucket(v.len)], 1u);
     }
-    hist_add(len_hist, sort_bucket(v.len), valid);
+    __syncthreads();
+    for (int i = threadIdx.x; i < LEN_CLASSES; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(len_hist + i, s_hist[i]);
 }
 
 // Element e goes to position (elements of larger classes) + (its rank inside its class); the rank comes from
@@ -143,7 +158,7 @@ bucket_scatter_kernel(const View *__restrict__ views, const Match *__restrict__ 
         if (e < n) {
             if (FROM_VIEWS) key[i] = (prev != nullptr && prev[e].adapter < 0) ? 0u : views[e].len;
             else key[i] = keys[e];
-            rank[i] = atomicAdd(&s_cnt[sort_bucket(key[i])], 1u);
+            rank[i] = atomicAdd(&s_cnt[class_of<FROM_VIEWS>(key[i])], 1u);
         }
     }
     __syncthreads();
@@ -157,7 +172,7 @@ bucket_scatter_kernel(const View *__restrict__ views, const Match *__restrict__ 
     for (int i = 0; i < PER; i++) {
         const uint32_t e = blockIdx.x * SORT_BUCKETS + i * 256 + tid;
         if (e < n) {
-            const uint32_t b = sort_bucket(key[i]);
+            const uint32_t b = class_of<FROM_VIEWS>(key[i]);
             const uint32_t pos = s_base[b] + s_blk[b] + rank[i];
             order_out[pos] = e;
             if (keys_out) keys_out[pos] = key[i];
@@ -646,46 +661,58 @@ struct SelectArgs {
 
 __global__ void __launch_bounds__(128) select_kernel(SelectArgs A)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = r < A.n_reads;
-    View v;
-    v.lo = 0; v.len = 0; v.rc = 0;
-    if (valid) v = A.views_in[r];
-    Match mt;
-    View next = v;
-    if (!valid || (A.prev != nullptr && A.prev[r].adapter < 0)) {
-        mt.adapter = -1; mt.is_rc = 0;
-        mt.ref_start = mt.ref_stop = mt.query_start = mt.query_stop = mt.score = mt.errors = 0;
-    } else {
-        uint64_t key[2];
-        key[0] = A.best_key[(size_t)r * 2];
-        key[1] = A.best_key[(size_t)r * 2 + 1];
-        select_read(A.type, A.revcomp, v, key, A.results, mt, next);
+    __shared__ uint32_t s_hist[LEN_CLASSES];
+    if (A.next_len_hist != nullptr) {
+        for (int i = threadIdx.x; i < LEN_CLASSES; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
     }
-    if (A.next_bases != nullptr) {
-        const uint32_t add = (valid && mt.adapter >= 0) ? next.len : 0u;
-        const uint32_t sum = __reduce_add_sync(0xffffffffu, add);
-        if ((threadIdx.x & 31) == 0 && sum) atomicAdd(A.next_bases, (unsigned long long)sum);
-    }
-    if (A.next_len_hist != nullptr)     // what bucket_scatter_kernel<true> will read as this read's key
-        hist_add(A.next_len_hist, sort_bucket(mt.adapter >= 0 ? next.len : 0u), valid);
-    if (!valid) return;
-    A.out[r] = mt;
-    A.views_out[r] = next;
-    if (A.last_round) {
-        int b;
-        if (A.round_index == 0) b = mt.adapter + 1;
-        else b = (A.match0[r].adapter + 1) + (A.n_ad0 + 1) * (mt.adapter + 1);
-        if (A.drop_bins[b]) b = -1;
-        A.bin[r] = b;
-        A.out_len[r] = next.len;
-        uint32_t rb = 0;
-        if (b >= 0 && A.name_offsets != nullptr) {
-            const uint32_t nl = A.name_lengths ? A.name_lengths[r]
-                                               : (uint32_t)(A.name_offsets[r + 1] - A.name_offsets[r]);
-            rb = 1u + nl + 3u * (next.rc >> 8) + 1u + next.len + 3u + next.len + 1u;   // @name[ rc]*\nSEQ\n+\nQUAL\n
+    const uint32_t n_pad = (A.n_reads + 31u) & ~31u;        // whole warps make every trip (warp reductions inside)
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += gridDim.x * blockDim.x) {
+        const bool valid = r < A.n_reads;
+        View v;
+        v.lo = 0; v.len = 0; v.rc = 0;
+        if (valid) v = A.views_in[r];
+        Match mt;
+        View next = v;
+        if (!valid || (A.prev != nullptr && A.prev[r].adapter < 0)) {
+            mt.adapter = -1; mt.is_rc = 0;
+            mt.ref_start = mt.ref_stop = mt.query_start = mt.query_stop = mt.score = mt.errors = 0;
+        } else {
+            uint64_t key[2];
+            key[0] = A.best_key[(size_t)r * 2];
+            key[1] = A.best_key[(size_t)r * 2 + 1];
+            select_read(A.type, A.revcomp, v, key, A.results, mt, next);
         }
-        A.rec_bytes[r] = rb;
+        if (A.next_bases != nullptr) {
+            const uint32_t add = (valid && mt.adapter >= 0) ? next.len : 0u;
+            const uint32_t sum = __reduce_add_sync(0xffffffffu, add);
+            if ((threadIdx.x & 31) == 0 && sum) atomicAdd(A.next_bases, (unsigned long long)sum);
+        }
+        if (!valid) continue;
+        if (A.next_len_hist != nullptr)     // what bucket_scatter_kernel<true> will read as this read's key
+            atomicAdd(&s_hist[len_bucket(mt.adapter >= 0 ? next.len : 0u)], 1u);
+        A.out[r] = mt;
+        A.views_out[r] = next;
+        if (A.last_round) {
+            int b;
+            if (A.round_index == 0) b = mt.adapter + 1;
+            else b = (A.match0[r].adapter + 1) + (A.n_ad0 + 1) * (mt.adapter + 1);
+            if (A.drop_bins[b]) b = -1;
+            A.bin[r] = b;
+            A.out_len[r] = next.len;
+            uint32_t rb = 0;
+            if (b >= 0 && A.name_offsets != nullptr) {
+                const uint32_t nl = A.name_lengths ? A.name_lengths[r]
+                                                   : (uint32_t)(A.name_offsets[r + 1] - A.name_offsets[r]);
+                rb = 1u + nl + 3u * (next.rc >> 8) + 1u + next.len + 3u + next.len + 1u;   // @name[ rc]*\nSEQ\n+\nQUAL\n
+            }
+            A.rec_bytes[r] = rb;
+        }
+    }
+    if (A.next_len_hist != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < LEN_CLASSES; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(A.next_len_hist + i, s_hist[i]);
     }
 }
 
