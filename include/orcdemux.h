@@ -215,6 +215,11 @@ typedef struct orc_text_batch {
 
 orc_reader *orc_reader_open(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
                             int pinned, char *err, size_t err_len);
+/* the same with the number of inflate threads given: a .gz written by orc_writer (its members carry a size
+ * field) is inflated member by member on that many threads; any other input is read by one zlib stream.
+ * orc_reader_open() picks half the host's hardware threads, at most 8. */
+orc_reader *orc_reader_open_threads(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
+                                    int pinned, int inflate_threads, char *err, size_t err_len);
 int orc_reader_next(orc_reader *r, orc_text_batch *out);
 int orc_reader_release(orc_reader *r, int buffer);
 const char *orc_reader_error(orc_reader *r);
@@ -223,7 +228,9 @@ void orc_reader_close(orc_reader *r);
 /*
  * Writer: one file per bin (paths[b] == NULL: bin not written), all created by orc_writer_open()
  * even if they stay empty (the reference's round-2 loop lists them, 02_cutadapt_loop.sh:75-85);
- * a path ending in ".gz" is written as gzip members of `level`, deflated by `threads` workers.
+ * a path ending in ".gz" is written as gzip members of `level`, deflated by `threads` workers; every member
+ * carries an FEXTRA subfield "OC" with its own size (BGZF's idea, 32-bit), which lets orc_reader inflate such
+ * files on several threads and which every other gzip reader skips.
  * orc_writer_write() queues the bin-major FASTQ text of one batch (orc_result.fastq /
  * bin_offsets) and returns a ticket >= 0 at once; the text must stay untouched until
  * orc_writer_wait(ticket) returns.  Files receive their batches in submission order.
@@ -232,6 +239,12 @@ void orc_reader_close(orc_reader *r);
 typedef struct orc_writer orc_writer;
 orc_writer *orc_writer_open(const char *const *paths, int n_bins, int level, int threads, char *err,
                             size_t err_len);
+/* orc_writer_set_index(w, 1) before the first write: orc_writer_close() also leaves PATH.idx beside every bin
+ * file, (ticket, bytes) as two little-endian uint64 per chunk in file order -- what merging the part files
+ * of several GPUs' ranks into one file in batch order needs (orcdemux/cli.py).  orc_empty_gzip_member():
+ * the empty member a bin without reads consists of (returns its length, 0 on failure; cap >= 40). */
+int orc_writer_set_index(orc_writer *w, int on);
+size_t orc_empty_gzip_member(uint8_t *out, size_t cap, int level);
 int64_t orc_writer_write(orc_writer *w, const uint8_t *fastq, const uint64_t *bin_offsets);
 int orc_writer_wait(orc_writer *w, int64_t ticket);
 const char *orc_writer_error(orc_writer *w);

@@ -19,6 +19,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -65,10 +66,194 @@ struct ReaderBuf {
     uint32_t n_reads = 0;
 };
 
+// Every gzip member this library writes carries an FEXTRA subfield "OC" with its own total size (header +
+// deflate stream + trailer) -- BGZF's idea with a 32-bit size -- so that a reader can find the members without
+// inflating them and inflate them in parallel (orc_reader does; any other gzip reader skips the field).
+constexpr size_t GZ_EXTRA_LEN = 8, GZ_SIZE_AT = 16;     // 10 header bytes, XLEN, then SI1 SI2 LEN(2) size(4)
+
+
+// ------------------------------------------------------------------------------------ member-parallel inflate
+// A .gz whose members carry this library's "OC" size field (everything orc_writer writes, e.g. the round-1
+// bins that round 2 reads back, 02_cutadapt_loop.sh:94-102) is inflated member by member on a thread
+// pool: the headers are hopped over with the size field, the uncompressed size is the trailer's ISIZE, and
+// the text comes out in file order.  A member without the field ends the parallel part; the rest of the
+// file is then read through zlib's gzread from that offset on.
+struct Member {
+    uint64_t off = 0, clen = 0;
+    uint32_t isize = 0;
+    uint8_t *out = nullptr;
+    bool done = false;
+    std::string err;
+};
+
+struct MemberSource {
+    int fd = -1;
+    uint64_t file_size = 0, pos = 0;
+    bool parallel_done = false;         // no further member with a size field
+    gzFile tail = nullptr;              // serial reader of the rest
+    std::vector<std::thread> pool;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::deque<Member *> order, jobs;
+    size_t max_inflight = 8;
+    bool stop = false;
+    Member *cur = nullptr;
+    uint64_t cur_pos = 0;
+    std::string err;
+
+    // the size field of the member at `at`, 0 if it has none
+    static uint64_t member_size(int fd, uint64_t at, uint64_t file_size)
+    {
+        uint8_t h[20];
+        if (at + 20 > file_size || pread(fd, h, 20, (off_t)at) != 20) return 0;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+        if (h[10] != GZ_EXTRA_LEN || h[11] != 0 || h[12] != 'O' || h[13] != 'C' || h[14] != 4 || h[15] != 0) return 0;
+        const uint64_t n = (uint64_t)h[16] | ((uint64_t)h[17] << 8) | ((uint64_t)h[18] << 16) | ((uint64_t)h[19] << 24);
+        return (n >= 28 && at + n <= file_size) ? n : 0;
+    }
+
+    static bool probe(const char *path)
+    {
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) return false;
+        const off_t end = lseek(fd, 0, SEEK_END);
+        const bool ok = end > 0 && member_size(fd, 0, (uint64_t)end) != 0;
+        close(fd);
+        return ok;
+    }
+
+    void worker()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_job.wait(lk, [&] { return stop || !jobs.empty(); });
+            if (stop) return;
+            Member *m = jobs.front();
+            jobs.pop_front();
+            lk.unlock();
+            std::vector<uint8_t> in(m->clen);
+            std::string why;
+            if (pread(fd, in.data(), m->clen, (off_t)m->off) != (ssize_t)m->clen) why = "short read of a gzip member";
+            if (why.empty()) {
+                m->out = (uint8_t *)malloc(m->isize ? m->isize : 1);
+                z_stream zs;
+                memset(&zs, 0, sizeof zs);
+                if (!m->out || inflateInit2(&zs, 15 + 16) != Z_OK) why = "out of memory";
+                else {
+                    zs.next_in = in.data();
+                    zs.avail_in = (uInt)m->clen;
+                    zs.next_out = m->out;
+                    zs.avail_out = m->isize;
+                    const int rc = inflate(&zs, Z_FINISH);
+                    if (rc != Z_STREAM_END || zs.total_out != m->isize) why = "corrupt gzip member";
+                    inflateEnd(&zs);
+                }
+            }
+            lk.lock();
+            m->err = why;
+            m->done = true;
+            cv_done.notify_all();
+        }
+    }
+
+    bool start(const char *path, int threads)
+    {
+        fd = open(path, O_RDONLY);
+        if (fd < 0) return false;
+        file_size = (uint64_t)lseek(fd, 0, SEEK_END);
+        if (threads < 1) threads = 1;
+        max_inflight = (size_t)threads * 2;
+        for (int t = 0; t < threads; t++) pool.emplace_back([this] { worker(); });
+        return true;
+    }
+
+    void dispatch()         // mu held
+    {
+        while (!parallel_done && order.size() < max_inflight) {
+            if (pos >= file_size) { parallel_done = true; break; }
+            const uint64_t n = member_size(fd, pos, file_size);
+            uint8_t tr[4];
+            if (!n || pread(fd, tr, 4, (off_t)(pos + n - 4)) != 4) { parallel_done = true; break; }
+            Member *m = new Member();
+            m->off = pos;
+            m->clen = n;
+            m->isize = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+            pos += n;
+            order.push_back(m);
+            jobs.push_back(m);
+            cv_job.notify_one();
+        }
+    }
+
+    // like gzread: up to `want` bytes, 0 at the end of the input, -1 on error (err set)
+    int64_t read(uint8_t *dst, uint64_t want)
+    {
+        uint64_t got = 0;
+        while (got < want) {
+            if (!cur) {
+                std::unique_lock<std::mutex> lk(mu);
+                dispatch();
+                if (order.empty()) {
+                    lk.unlock();
+                    if (pos >= file_size) break;                        // clean end
+                    if (!tail) {                                        // a foreign member: serial from here on
+                        if (lseek(fd, (off_t)pos, SEEK_SET) < 0 || !(tail = gzdopen(dup(fd), "rb"))) {
+                            err = "cannot continue reading the input";
+                            return -1;
+                        }
+                        gzbuffer(tail, 1u << 20);
+                    }
+                    uint64_t w = want - got;
+                    if (w > (1u << 30)) w = 1u << 30;
+                    const int g = gzread(tail, dst + got, (unsigned)w);
+                    if (g < 0) { err = "reading the input: gzread failed"; return -1; }
+                    if (g == 0) {
+                        int zerr = Z_OK;
+                        gzerror(tail, &zerr);
+                        if (zerr != Z_OK && zerr != Z_STREAM_END) { err = "reading the input: truncated gzip stream"; return -1; }
+                        pos = file_size;
+                        break;
+                    }
+                    got += (uint64_t)g;
+                    continue;
+                }
+                Member *m = order.front();
+                cv_done.wait(lk, [&] { return m->done; });
+                order.pop_front();
+                dispatch();
+                if (!m->err.empty()) { err = "reading the input: " + m->err; free(m->out); delete m; return -1; }
+                cur = m;
+                cur_pos = 0;
+            }
+            const uint64_t n = std::min<uint64_t>(want - got, (uint64_t)cur->isize - cur_pos);
+            memcpy(dst + got, cur->out + cur_pos, n);
+            got += n;
+            cur_pos += n;
+            if (cur_pos == cur->isize) { free(cur->out); delete cur; cur = nullptr; }
+        }
+        return (int64_t)got;
+    }
+
+    ~MemberSource()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+            cv_job.notify_all();
+        }
+        for (std::thread &t : pool) t.join();
+        for (Member *m : order) { free(m->out); delete m; }
+        if (cur) { free(cur->out); delete cur; }
+        if (tail) gzclose(tail);
+        if (fd >= 0) close(fd);
+    }
+};
+
 }  // namespace
 
 struct orc_reader {
     gzFile gz = nullptr;
+    MemberSource *members = nullptr;    // set instead of gz for files orc_writer wrote
     uint32_t max_reads = 0;
     uint64_t max_bytes = 0;
     std::vector<ReaderBuf> bufs;
@@ -116,18 +301,25 @@ struct orc_reader {
             while (fill < max_bytes && !eof) {
                 uint64_t want = max_bytes - fill;
                 if (want > (1u << 30)) want = 1u << 30;
-                int got = gzread(gz, rb.text + fill, (unsigned)want);
-                if (got < 0) {
-                    int zerr = 0;
-                    const char *msg = gzerror(gz, &zerr);
-                    return fail(std::string("reading the input: ") + (msg ? msg : "gzread failed"));
-                }
-                if (got == 0) {
-                    int zerr = Z_OK;
-                    const char *msg = gzerror(gz, &zerr);       // a truncated .gz ends "cleanly" with Z_BUF_ERROR
-                    if (zerr != Z_OK && zerr != Z_STREAM_END)
-                        return fail(std::string("reading the input: ") + (msg && *msg ? msg : "truncated gzip stream"));
-                    eof = true;
+                int64_t got;
+                if (members) {
+                    got = members->read(rb.text + fill, want);
+                    if (got < 0) return fail(members->err);
+                    if (got == 0) eof = true;
+                } else {
+                    got = gzread(gz, rb.text + fill, (unsigned)want);
+                    if (got < 0) {
+                        int zerr = 0;
+                        const char *msg = gzerror(gz, &zerr);
+                        return fail(std::string("reading the input: ") + (msg ? msg : "gzread failed"));
+                    }
+                    if (got == 0) {
+                        int zerr = Z_OK;
+                        const char *msg = gzerror(gz, &zerr);       // a truncated .gz ends "cleanly" with Z_BUF_ERROR
+                        if (zerr != Z_OK && zerr != Z_STREAM_END)
+                            return fail(std::string("reading the input: ") + (msg && *msg ? msg : "truncated gzip stream"));
+                        eof = true;
+                    }
                 }
                 fill += (uint64_t)got;
                 {
@@ -166,6 +358,14 @@ struct orc_reader {
 extern "C" orc_reader *orc_reader_open(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
                                        int pinned, char *err, size_t err_len)
 {
+    unsigned hw = std::thread::hardware_concurrency();
+    return orc_reader_open_threads(path, max_reads, max_bytes, n_buffers, pinned, (int)(hw > 16 ? 8 : (hw > 1 ? hw / 2 : 1)),
+                                   err, err_len);
+}
+
+extern "C" orc_reader *orc_reader_open_threads(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
+                                               int pinned, int inflate_threads, char *err, size_t err_len)
+{
     if (!path || !max_reads || max_bytes < 16 || n_buffers < 1 || n_buffers > 64) {
         set_err(err, err_len, "orc_reader_open: bad argument");
         return nullptr;
@@ -173,14 +373,23 @@ extern "C" orc_reader *orc_reader_open(const char *path, uint32_t max_reads, uin
     orc_reader *r = new orc_reader();
     r->max_reads = max_reads;
     r->max_bytes = max_bytes;
-    if (strcmp(path, "-") == 0) r->gz = gzdopen(dup(0), "rb");
-    else r->gz = gzopen(path, "rb");        // transparent for files that are not gzip
-    if (!r->gz) {
-        set_err(err, err_len, std::string("cannot open ") + path + ": " + strerror(errno));
-        delete r;
-        return nullptr;
+    if (strcmp(path, "-") != 0 && inflate_threads > 0 && MemberSource::probe(path)) {
+        r->members = new MemberSource();
+        if (!r->members->start(path, inflate_threads)) {
+            delete r->members;
+            r->members = nullptr;
+        }
     }
-    gzbuffer(r->gz, 1u << 20);
+    if (!r->members) {
+        if (strcmp(path, "-") == 0) r->gz = gzdopen(dup(0), "rb");
+        else r->gz = gzopen(path, "rb");        // transparent for files that are not gzip
+        if (!r->gz) {
+            set_err(err, err_len, std::string("cannot open ") + path + ": " + strerror(errno));
+            delete r;
+            return nullptr;
+        }
+        gzbuffer(r->gz, 1u << 20);
+    }
     r->bufs.resize(n_buffers);
     bool ok = true;
     for (int b = 0; b < n_buffers && ok; b++) {
@@ -251,6 +460,7 @@ extern "C" void orc_reader_close(orc_reader *r)
     }
     if (r->th.joinable()) r->th.join();
     if (r->gz) gzclose(r->gz);
+    delete r->members;
     for (ReaderBuf &rb : r->bufs) {
         host_free(rb.text, rb.pinned[0]);
         host_free(rb.off, rb.pinned[1]);
@@ -282,7 +492,14 @@ struct BinFile {
     bool writing = false;           // one thread at a time appends to the file
     uint64_t bytes_in = 0;
     std::deque<Chunk *> q;          // submission order == file order
+    std::string path;
+    std::vector<uint64_t> log;      // (ticket, bytes written) per chunk, in file order
 };
+
+void put_member_size(uint8_t *member, size_t total)
+{
+    for (int i = 0; i < 4; i++) member[GZ_SIZE_AT + i] = (uint8_t)(total >> (8 * i));
+}
 
 }  // namespace
 
@@ -310,8 +527,16 @@ struct orc_writer {
         }
     }
 
+    bool index_files = false;       // orc_writer_set_index: leave PATH.idx beside every bin file
+
     bool deflate_chunk(z_stream &zs, bool &zs_ready, Chunk *c, std::string &why)
     {
+        static uint8_t extra[GZ_EXTRA_LEN] = {'O', 'C', 4, 0, 0, 0, 0, 0};
+        gz_header head;
+        memset(&head, 0, sizeof head);
+        head.os = 255;
+        head.extra = extra;
+        head.extra_len = (uInt)GZ_EXTRA_LEN;
         if (!zs_ready) {
             memset(&zs, 0, sizeof zs);
             if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
@@ -322,7 +547,11 @@ struct orc_writer {
         } else {
             deflateReset(&zs);
         }
-        size_t bound = deflateBound(&zs, (uLong)c->len) + 64;
+        if (deflateSetHeader(&zs, &head) != Z_OK) {
+            why = "deflateSetHeader failed";
+            return false;
+        }
+        size_t bound = deflateBound(&zs, (uLong)c->len) + 64 + GZ_EXTRA_LEN + 2;
         c->out = (uint8_t *)malloc(bound);
         if (!c->out) {
             why = "out of memory";
@@ -337,6 +566,7 @@ struct orc_writer {
             return false;
         }
         c->out_len = bound - zs.avail_out;
+        put_member_size(c->out, c->out_len);
         return true;
     }
 
@@ -391,6 +621,8 @@ struct orc_writer {
                     bool wok = !w->out || write_all(bf.fd, w->out, w->out_len);
                     free(w->out);
                     lk.lock();
+                    bf.log.push_back((uint64_t)w->ticket);
+                    bf.log.push_back((uint64_t)w->out_len);
                     if (!wok) set_error(std::string("write failed: ") + strerror(errno));
                     delete w;
                     unwritten--;
@@ -403,6 +635,39 @@ struct orc_writer {
         if (zs_ready) deflateEnd(&zs);
     }
 };
+
+// An empty gzip member in this library's format (with the size field).  Returns its length, 0 on failure.
+extern "C" size_t orc_empty_gzip_member(uint8_t *out, size_t cap, int level)
+{
+    static uint8_t extra[GZ_EXTRA_LEN] = {'O', 'C', 4, 0, 0, 0, 0, 0};
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    gz_header head;
+    memset(&head, 0, sizeof head);
+    head.os = 255;
+    head.extra = extra;
+    head.extra_len = (uInt)GZ_EXTRA_LEN;
+    if (cap < 40 || deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return 0;
+    size_t n = 0;
+    if (deflateSetHeader(&zs, &head) == Z_OK) {
+        zs.next_out = out;
+        zs.avail_out = (uInt)cap;
+        if (deflate(&zs, Z_FINISH) == Z_STREAM_END) {
+            n = cap - zs.avail_out;
+            put_member_size(out, n);
+        }
+    }
+    deflateEnd(&zs);
+    return n;
+}
+
+extern "C" int orc_writer_set_index(orc_writer *w, int on)
+{
+    if (!w) return ORC_EINVAL;
+    std::lock_guard<std::mutex> lk(w->mu);
+    w->index_files = on != 0;
+    return ORC_OK;
+}
 
 extern "C" orc_writer *orc_writer_open(const char *const *paths, int n_bins, int level, int threads, char *err,
                                        size_t err_len)
@@ -427,6 +692,7 @@ extern "C" orc_writer *orc_writer_open(const char *const *paths, int n_bins, int
         }
         size_t n = strlen(paths[b]);
         w->bins[b].fd = fd;
+        w->bins[b].path = paths[b];
         w->bins[b].gz = n >= 3 && strcmp(paths[b] + n - 3, ".gz") == 0;
     }
     if (threads < 1) threads = 1;
@@ -501,18 +767,18 @@ extern "C" int orc_writer_close(orc_writer *w, uint64_t *bytes_per_bin)
         if (bf.fd < 0) continue;
         if (bf.gz && bf.bytes_in == 0) {
             // an empty but valid .gz, as xopen leaves for a bin without reads
-            z_stream zs;
-            memset(&zs, 0, sizeof zs);
             uint8_t out[64];
-            if (deflateInit2(&zs, w->level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) == Z_OK) {
-                zs.next_out = out;
-                zs.avail_out = sizeof out;
-                deflate(&zs, Z_FINISH);
-                if (!orc_writer::write_all(bf.fd, out, sizeof out - zs.avail_out)) rc = ORC_EINVAL;
-                deflateEnd(&zs);
-            }
+            const size_t n = orc_empty_gzip_member(out, sizeof out, w->level);
+            if (!n || !orc_writer::write_all(bf.fd, out, n)) rc = ORC_EINVAL;
         }
         if (close(bf.fd) != 0 && !rc) rc = ORC_EINVAL;
+        if (w->index_files) {
+            // (ticket, bytes) of every chunk in file order: what merging the part files of several ranks
+            // into one file in batch order needs (orcdemux/cli.py)
+            FILE *fh = fopen((bf.path + ".idx").c_str(), "wb");
+            if (!fh || (bf.log.size() && fwrite(bf.log.data(), sizeof(uint64_t), bf.log.size(), fh) != bf.log.size())) rc = rc ? rc : ORC_EINVAL;
+            if (fh && fclose(fh) != 0 && !rc) rc = ORC_EINVAL;
+        }
     }
     delete w;
     return rc;

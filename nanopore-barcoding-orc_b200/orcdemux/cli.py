@@ -342,10 +342,12 @@ def _batch_shape():
     return reads, max(1 << 20, min(1 << 28, reads * 4096))
 
 
-def _stream(reader, eng, writers, slots, on_result):
+def _stream(reader, eng, writers, slots, on_result, rank=0, world=1):
     """reader -> GPU -> writers with `slots` batches between the stages: while batch k is on the
     GPU the bins of batches k-1 and k-2 are being deflated and the reader inflates k+1, k+2.
-    A slot is submitted again only after the writer has let go of its result buffers."""
+    A slot is submitted again only after the writer has let go of its result buffers.
+    With world > 1 this rank only takes the batches dealt to it (shard.owner_of_batch): batch ids count
+    the reader's batches, which are the same on every rank."""
     tickets = [None] * slots
     pending = []
 
@@ -355,7 +357,9 @@ def _stream(reader, eng, writers, slots, on_result):
         tickets[slot] = writers.write_batch(res)
 
     k = 0
-    for tb in reader:
+    for batch_id, tb in enumerate(reader):
+        if world > 1 and batch_id % world != rank:
+            continue
         slot = k % slots
         if tickets[slot] is not None:
             writers.wait(tickets[slot])
@@ -380,7 +384,7 @@ def run_single_round(opt, argv, device=0) -> int:
     t0 = time.time()
     (max_reads, max_bytes), slots = _batch_shape(), 3
     threads = max(2, min(os.cpu_count() or 2, opt["cores"] if opt["cores"] > 0 else (os.cpu_count() or 2)))
-    reader = F.FastqReader(opt["inputs"][0], max_reads, max_bytes, keep=3, ahead=2)
+    reader = F.FastqReader(opt["inputs"][0], max_reads, max_bytes, keep=3, ahead=2, threads=threads)
     paths = [opt["out"].replace("{name}", "unknown")] + [opt["out"].replace("{name}", n) for n in names]
     writers = F.BinWriters(paths, opt["level"], threads=threads)
     n_in = bp_in = bp_out = n_with = n_rc = 0
@@ -460,7 +464,23 @@ def run_two_round(args: List[str], device=0) -> int:
     ap.add_argument("--no-gzip", action="store_true")
     ap.add_argument("-j", type=int, default=8)
     ap.add_argument("--compression-level", type=int, default=1, help="gzip level of the bin files (cutadapt 4.x default: 1)")
+    ap.add_argument("--gpus", type=int, default=1,
+                    help="GPUs of this node to shard the batches over, one process each (the same happens under "
+                         "torchrun, whose RANK / WORLD_SIZE are honoured)")
     a = ap.parse_args(args)
+    from . import shard
+    rank, world, local_rank = shard.dist_env()
+    if world == 1 and a.gpus > 1:
+        # no torchrun around us: be the launcher; the ranks run this same command
+        return shard.spawn_ranks(a.gpus, ["two-round"] + list(args))
+    share = False
+    if world > 1:
+        # one GPU per rank; with fewer GPUs than ranks (a test box) ranks share devices and the count gather
+        # goes over gloo, because NCCL wants a device per rank
+        import torch
+        n_dev = max(1, torch.cuda.device_count())
+        share = world > n_dev
+        device = local_rank % n_dev
     n5, s5 = F.read_adapters_fasta(a.sp5)
     n27, s27 = F.read_adapters_fasta(a.sp27)
     ds = dataset_name(a.input)
@@ -483,8 +503,11 @@ def run_two_round(args: List[str], device=0) -> int:
             continue
         paths[b] = os.path.join(outdir, "SP27", "%s_%s_%s%s" % (nm27, nm5, ds, ext))
     (max_reads, max_bytes), slots = _batch_shape(), 3
-    reader = F.FastqReader(a.input, max_reads, max_bytes, keep=3, ahead=2)
-    writers = F.BinWriters(paths, a.compression_level, threads=max(2, min(os.cpu_count() or 2, a.j)))
+    threads = max(2, min(os.cpu_count() or 2, a.j) // max(world, 1))
+    reader = F.FastqReader(a.input, max_reads, max_bytes, keep=3, ahead=2, threads=threads)
+    # with several ranks every rank writes part files (+ an index of their chunks); rank 0 stitches them
+    my_paths = [shard.part_path(p, rank) if (p and world > 1) else p for p in paths]
+    writers = F.BinWriters(my_paths, a.compression_level, threads=threads, index=world > 1)
     t0 = time.time()
     n_in = 0
 
@@ -496,17 +519,29 @@ def run_two_round(args: List[str], device=0) -> int:
         with E.Engine(rounds, device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
                       emit_fastq=True, want_matches=False, drop_bins=drop) as eng:
             try:
-                _stream(reader, eng, writers, slots, on_result)
+                _stream(reader, eng, writers, slots, on_result, rank, world)
             finally:
                 writers.close()         # drains: the result buffers belong to the engine
-            counts = eng.counts()
+            counts = eng.counts().astype(np.int64)
     finally:
         writers.close()
         reader.close()
-    with open(os.path.join(outdir, "SP27", "orcdemux_%s.json" % ds), "w") as fh:
-        json.dump({"dataset": ds, "reads": n_in, "elapsed_seconds": time.time() - t0,
-                   "bins": {os.path.basename(p): int(counts[b]) for b, p in enumerate(paths) if p}}, fh, indent=1)
-    print("Demultiplexing complete! %d reads, results in: %s" % (n_in, outdir))
+    if world > 1:
+        # the only exchanges: the per-bin count gather, and a barrier before the part files are stitched
+        import torch.distributed as dist
+        shard.init_process_group(not share, local_rank)
+        tot = shard.gather_counts(np.concatenate([counts, [n_in]]))
+        counts, n_in = tot[:-1], int(tot[-1])
+        dist.barrier()
+        if rank == 0:
+            shard.merge_part_files(paths, world, a.compression_level)
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        with open(os.path.join(outdir, "SP27", "orcdemux_%s.json" % ds), "w") as fh:
+            json.dump({"dataset": ds, "reads": n_in, "elapsed_seconds": time.time() - t0, "gpus": world,
+                       "bins": {os.path.basename(p): int(counts[b]) for b, p in enumerate(paths) if p}}, fh, indent=1)
+        print("Demultiplexing complete! %d reads on %d GPU%s, results in: %s" % (n_in, world, "s" if world > 1 else "", outdir))
     return 0
 
 

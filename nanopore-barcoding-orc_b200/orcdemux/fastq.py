@@ -74,12 +74,16 @@ class FastqReader:
     valid; older ones go back to the reader, which owns `keep + ahead` buffers."""
 
     def __init__(self, path: str, max_reads: int = 1 << 18, max_bytes: int = 1 << 28, keep: int = 3,
-                 ahead: int = 2, pinned: bool = True):
+                 ahead: int = 2, pinned: bool = True, threads: int = 0):
         self._L = _lib.load()
         self.path, self.max_reads, self.max_bytes, self.keep = path, max_reads, max_bytes, max(1, keep)
         err = C.create_string_buffer(512)
-        self._r = self._L.orc_reader_open(os.fsencode(path), max_reads, max_bytes, self.keep + max(1, ahead),
-                                          int(pinned), err, 512)
+        if threads > 0:         # inflate threads for member-structured input (files orc_writer wrote)
+            self._r = self._L.orc_reader_open_threads(os.fsencode(path), max_reads, max_bytes, self.keep + max(1, ahead),
+                                                      int(pinned), int(threads), err, 512)
+        else:
+            self._r = self._L.orc_reader_open(os.fsencode(path), max_reads, max_bytes, self.keep + max(1, ahead),
+                                              int(pinned), err, 512)
         if not self._r:
             raise OSError(err.value.decode(errors="replace"))
         self._held: List[int] = []
@@ -126,14 +130,17 @@ class BinWriters:
     """One output file per bin name, created up front (orc_writer_*, csrc/orc_io.cpp): gzip
     members are deflated by a native thread pool while the GPU works on the next batches."""
 
-    def __init__(self, paths: List[Optional[str]], compresslevel: int = 5, threads: int = 8):
+    def __init__(self, paths: List[Optional[str]], compresslevel: int = 5, threads: int = 8, index: bool = False):
         self._L = _lib.load()
         self.paths = paths
+        self.level = compresslevel
         arr = (C.c_char_p * len(paths))(*[os.fsencode(p) if p is not None else None for p in paths])
         err = C.create_string_buffer(512)
         self._w = self._L.orc_writer_open(arr, len(paths), int(compresslevel), int(threads), err, 512)
         if not self._w:
             raise OSError(err.value.decode(errors="replace"))
+        if index:               # PATH.idx beside every file: (ticket, bytes) per chunk (multi-GPU merge)
+            self._L.orc_writer_set_index(self._w, 1)
         self._live = {}
         self.bytes_written = [0] * len(paths)
 

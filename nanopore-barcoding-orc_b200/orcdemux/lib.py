@@ -28,7 +28,8 @@ EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_sub
            "orc_fastq_index", "orc_host_alloc", "orc_host_free", "orc_measure_int32_peak", "orc_version",
            "orc_reader_open", "orc_reader_next", "orc_reader_release", "orc_reader_error", "orc_reader_close",
            "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close",
-           "orc_edit_distances", "orc_synth", "orc_resident", "orc_export"]
+           "orc_edit_distances", "orc_synth", "orc_resident", "orc_export",
+           "orc_reader_open_threads", "orc_writer_set_index", "orc_empty_gzip_member"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -132,6 +133,12 @@ def load():
     L.orc_measure_int32_peak.restype = C.c_double
     L.orc_reader_open.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.orc_reader_open.restype = C.c_void_p
+    L.orc_reader_open_threads.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.orc_reader_open_threads.restype = C.c_void_p
+    L.orc_writer_set_index.argtypes = [C.c_void_p, C.c_int]
+    L.orc_writer_set_index.restype = C.c_int
+    L.orc_empty_gzip_member.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    L.orc_empty_gzip_member.restype = C.c_size_t
     L.orc_reader_next.argtypes = [C.c_void_p, C.POINTER(TextBatchC)]
     L.orc_reader_next.restype = C.c_int
     L.orc_reader_release.argtypes = [C.c_void_p, C.c_int]

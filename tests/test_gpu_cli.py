@@ -118,6 +118,115 @@ def test_reference_script_flow_and_fused(tmp_path):
     assert json.load(open(out3 / "SP27" / ("orcdemux_%s.json" % ds)))["reads"] == rs.n_reads
 
 
+def test_two_round_on_two_ranks_equals_one(tmp_path):
+    """`two-round --gpus 2`: the batches of the input are dealt to two ranks (two GPUs when the box has them,
+    else both on the one GPU), every rank writes part files, rank 0 stitches them in batch order.  The tree
+    must equal the one-GPU tree byte for byte after decompression, and so must the counts."""
+    rs = synth.generate(9000, 300, 900, seed=78)
+    ds = "s2"
+    (tmp_path / "pychopped").mkdir()
+    infile = tmp_path / "pychopped" / ("pychopped_%s.fastq" % ds)
+    infile.write_bytes(rs.to_fastq_bytes())
+    fwd, rev, _ = m13.write_tables(str(tmp_path / "adapters"))
+    env = dict(os.environ, PYTHONPATH=H.PKG, ORCDEMUX_BATCH_READS="800")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    trees = {}
+    for gpus in (1, 2, 3):
+        out = tmp_path / ("demuxed%d" % gpus)
+        r = subprocess.run([sys.executable, "-m", "orcdemux.cli", "two-round", str(infile), "--sp5", fwd, "--sp27", rev,
+                            "--outdir", str(out), "--gpus", str(gpus), "-j", "4"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        files = sorted(os.listdir(out / "SP27"))
+        assert len([f for f in files if f.endswith(".fastq.gz")]) == 96 and not [f for f in files if ".part" in f]
+        trees[gpus] = {f: _read_gz(out / "SP27" / f) for f in files if f.endswith(".fastq.gz")}
+        rep = json.load(open(out / "SP27" / ("orcdemux_%s.json" % ds)))
+        assert rep["reads"] == rs.n_reads and rep["gpus"] == gpus
+        trees[(gpus, "bins")] = rep["bins"]
+    expected, _ = _expected_tree(rs, ds)
+    assert {"SP27/" + k: v for k, v in trees[1].items()} == expected
+    assert trees[2] == trees[1] and trees[3] == trees[1]
+    assert trees[(2, "bins")] == trees[(1, "bins")] == trees[(3, "bins")]
+
+
+def test_json_report_equals_report_built_from_oracle_records(tmp_path):
+    """N1: the --json of a GPU run (read counts, per-adapter totals, matches on the reverse complement,
+    trimmed-length histograms by error count, bases preceding 3' matches) against the same statistics built
+    here from the ORACLE's match records, for both invocation shapes of the script."""
+    shim = os.path.join(H.PKG, "bin", "cutadapt")
+    fwd, rev, _ = m13.write_tables(str(tmp_path / "adapters"))
+    rs = synth.generate(8000, 300, 900, seed=31)
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(H.m13_rounds(), rs)
+    infile = tmp_path / "in.fastq"
+    infile.write_bytes(rs.to_fastq_bytes())
+    (tmp_path / "SP5").mkdir()
+    r = subprocess.run([shim, "--action=trim", "-e", "0.1", "-j", "4", "--rc", "-g", "file:" + fwd,
+                        "-o", str(tmp_path / "SP5" / "{name}.fastq"), str(infile), "--json=" + str(tmp_path / "r1.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rep = json.load(open(tmp_path / "r1.json"))
+    L = rs.lengths.astype(np.int64)
+
+    def check(rep, rec, in_len, names, seqs, front, adjacent=None):
+        has = rec["adapter"] >= 0
+        assert rep["read_counts"]["input"] == rec.shape[0] and rep["read_counts"]["output"] == rec.shape[0]
+        assert rep["read_counts"]["read1_with_adapter"] == int(has.sum())
+        assert rep["read_counts"]["reverse_complemented"] == int((rec["is_rc"] != 0).sum())
+        assert rep["basepair_counts"]["input"] == int(in_len.sum())
+        removed = np.where(has, rec["query_stop"] if front else in_len - rec["query_start"], 0)
+        assert rep["basepair_counts"]["output"] == int((in_len - removed).sum())
+        for a, ad in enumerate(rep["adapters_read1"]):
+            sel = rec["adapter"] == a
+            assert ad["name"] == names[a] and ad["total_matches"] == int(sel.sum())
+            assert ad["on_reverse_complement"] == int((rec["is_rc"][sel] != 0).sum())
+            end = ad["five_prime_end"] if front else ad["three_prime_end"]
+            assert (ad["three_prime_end"] if front else ad["five_prime_end"]) is None
+            assert end["sequence"] == seqs[a] and end["matches"] == int(sel.sum()) and end["error_rate"] == 0.1
+            hist = {}
+            for q, e in zip(removed[sel].tolist(), rec["errors"][sel].tolist()):
+                hist.setdefault(q, {}).setdefault(e, 0)
+                hist[q][e] += 1
+            assert {t["len"]: {e: c for e, c in enumerate(t["counts"]) if c} for t in end["trimmed_lengths"]} == hist, names[a]
+            for t in end["trimmed_lengths"]:
+                assert abs(t["expect"] - rec.shape[0] * 0.25 ** min(t["len"], len(seqs[a]))) < 1e-6 * max(1.0, t["expect"])
+            if adjacent is not None:
+                assert end["adjacent_bases"] == adjacent[a], names[a]
+
+    n5 = [n for n, _ in m13.sp5_forward()]
+    s5 = [q for _, q in m13.sp5_forward()]
+    check(rep, rec0, L, n5, s5, True)
+    # round 2 on one of the round-1 bins: reads of that bin as round 1 left them (the oracle's view of them)
+    a0 = int(np.bincount(rec0["adapter"][rec0["adapter"] >= 0]).argmax())
+    sel = np.flatnonzero(rec0["adapter"] == a0)
+    (tmp_path / "SP27").mkdir()
+    r = subprocess.run([shim, "--action=trim", "-e", "0.1", "-j", "4", "--rc", "-a", "file:" + rev,
+                        "-o", str(tmp_path / "SP27" / "{name}.fastq"), str(tmp_path / "SP5" / (n5[a0] + ".fastq")),
+                        "--json=" + str(tmp_path / "r2.json")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rep2 = json.load(open(tmp_path / "r2.json"))
+    in2 = (L - rec0["query_stop"])[sel]
+    sub1 = rec1[sel]
+    # the base before a 3' match, in the orientation that matched: rebuild the round-1 output of each read
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    adjacent = [{"A": 0, "C": 0, "G": 0, "T": 0, "": 0} for _ in range(12)]
+    for i, m in zip(sel.tolist(), sub1):
+        if m["adapter"] < 0:
+            continue
+        o = int(rs.offsets[i])
+        s = rs.seq[o:o + int(L[i])]
+        if rec0["is_rc"][i]:
+            s = np.array([comp.get(int(c), int(c)) for c in s[::-1]], dtype=np.uint8)
+        s = s[int(rec0["query_stop"][i]):]
+        if m["is_rc"]:
+            s = np.array([comp.get(int(c), int(c)) for c in s[::-1]], dtype=np.uint8)
+        q = int(m["query_start"])
+        base = chr(int(s[q - 1])) if q > 0 else ""
+        adjacent[int(m["adapter"])][base if base in "ACGT" else ""] += 1
+    n27 = [n for n, _ in m13.sp27_reverse_rc()]
+    s27 = [q for _, q in m13.sp27_reverse_rc()]
+    check(rep2, sub1, in2, n27, s27, False, adjacent)
+
+
 def test_unsupported_exits_2(tmp_path):
     shim = os.path.join(H.PKG, "bin", "cutadapt")
     r = subprocess.run([shim, "-m", "20", "-g", "ACGT", "-o", str(tmp_path / "{name}.fq"), "in.fq"],

@@ -137,3 +137,46 @@ def test_truncated_header_is_an_error():
         n = L.orc_fastq_index(text.ctypes.data, text.shape[0], 4, 0, so.ctypes.data, ln.ctypes.data, qo.ctypes.data,
                               no.ctypes.data, nl.ctypes.data, C.byref(used), err, 256)
         assert n == 1 and used.value == 15
+
+
+def test_member_parallel_inflate_and_index_sidecar(tmp_path, reads):
+    """Files orc_writer wrote carry a size field per gzip member: orc_reader inflates them on several threads and
+    returns the same text as one zlib stream would; python's gzip reads them too; PATH.idx lists the chunks;
+    a foreign member in the middle hands the rest of the file to the serial reader; a cut file is an error."""
+    rs, raw = reads
+    cut = [0, len(raw) // 5, len(raw) // 2, 3 * len(raw) // 4, len(raw)]
+    # cut at record boundaries so that every batch holds whole records
+    cut = [0] + [raw.index(b"\n@r", c) + 1 for c in cut[1:-1]] + [len(raw)]
+    paths = [str(tmp_path / "a.fastq.gz"), str(tmp_path / "empty.fastq.gz")]
+    w = F.BinWriters(paths, 1, threads=3, index=True)
+    w._L.orc_writer_set_index(w._w, 1)
+    tickets = [w.write_batch(_Res([raw[a:b], b""])) for a, b in zip(cut[:-1], cut[1:])]
+    for t in tickets:
+        w.wait(t)
+    w.close()
+    blob = open(paths[0], "rb").read()
+    assert gzip.decompress(blob) == raw and gzip.decompress(open(paths[1], "rb").read()) == b""
+    idx = np.fromfile(paths[0] + ".idx", dtype="<u8").reshape(-1, 2)
+    assert int(idx[:, 1].sum()) == len(blob) and list(idx[:, 0]) == sorted(idx[:, 0]) and set(idx[:, 0]) == set(tickets)
+    assert np.fromfile(paths[1] + ".idx", dtype="<u8").size == 0
+    # the size field: FEXTRA, subfield OC, the member's own length
+    assert blob[3] & 4 and blob[12:14] == b"OC" and int.from_bytes(blob[16:20], "little") == int(idx[0, 1])
+
+    def text_of(path, threads):
+        with F.FastqReader(path, max_reads=700, max_bytes=1 << 20, keep=2, ahead=2, pinned=False, threads=threads) as rd:
+            return b"".join(tb.text[:tb.n_bytes].tobytes() for tb in rd)
+
+    for threads in (1, 4):
+        assert text_of(paths[0], threads) == raw
+    assert text_of(paths[1], 4) == b""
+    # our members, then two foreign ones, then ours again: everything after the first foreign member is read serially
+    mixed = tmp_path / "mixed.fastq.gz"
+    k = int(idx[0, 1])
+    a, b = cut[1], cut[2]
+    mixed.write_bytes(blob[:k] + gzip.compress(raw[a:b], 1) + gzip.compress(raw[b:cut[3]], 6))
+    first = gzip.decompress(blob[:k])
+    assert text_of(str(mixed), 4) == first + raw[a:cut[3]]
+    trunc = tmp_path / "trunc.fastq.gz"
+    trunc.write_bytes(blob[:len(blob) - 9])
+    with pytest.raises(ValueError, match="input"):
+        text_of(str(trunc), 4)
