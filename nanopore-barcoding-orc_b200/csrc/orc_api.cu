@@ -656,7 +656,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         if (n && prefilter) {
             filter_kernel<<<ctx->filter_blocks, SCAN_THREADS, 0, st>>>(
                 ctx->d_tab[r], W, s.d_views[r], s.d_wins, s.d_wcols_sorted, s.d_item_order, 2 * n, s.d_jobs, cnt,
-                s.d_cells + 4 + r); nl++;
+                s.d_cells + 4 + r, getenv("ORC_NO_TRIM") ? 0 : 1); nl++;
         }
         CK(mark(ORC_K_FILTER));
         if (n && anch) {

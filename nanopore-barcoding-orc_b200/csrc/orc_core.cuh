@@ -291,7 +291,7 @@ ORC_HD void r6_update(Best &b, int n, const Cell &c, int i, int min_ov, const ui
 struct ScanHull { int32_t jf, jl, i1, i2; };
 
 constexpr int MAX_WIN = 3;
-struct WinList {                    // windows of one (read, direction), increasing, disjoint
+struct alignas(16) WinList {        // windows of one (read, direction), increasing, disjoint; moved as two 16-byte words
     uint32_t n;
     uint32_t s[MAX_WIN], e[MAX_WIN];   // columns s+1 .. e are scanned; s == 0 is the true column 0
     uint32_t flags;                    // bit 0: a last-column cell (i, n) with i <= 32 may be a candidate (3' rounds)
@@ -447,7 +447,7 @@ struct SeedTable {
     uint32_t list[SEED_LIST_MAX];   // piece << 16 | direction << 20
 };
 
-struct SeedWins {                   // the seed windows of one (read, direction), increasing, disjoint
+struct alignas(16) SeedWins {       // the seed windows of one (read, direction), increasing, disjoint; moved as 16-byte words
     uint32_t n;
     uint32_t s[MAX_WIN], e[MAX_WIN];
     uint32_t all;                   // too many hits to keep apart: this (read, direction) takes the flank scan
@@ -884,9 +884,17 @@ ORC_HD uint32_t win_columns(const WinList &w)
 // Away from the true column 0 the columns run without bookkeeping, as in stage 1: the cost is a
 // popcount away and moves by at most one per column, so (Da + Db - c) / 2 bounds it between two
 // columns c apart.  Passing a pair that has no candidate only costs time.
+//
+// The block does not need the whole window either.  Every window that starts after column 0 starts at least
+// kt + 1 columns before the earliest alignment it was opened for begins (seeds: 2kt + 1 before the seed's
+// diagonal; flank triggers: Lp + kt + 1 before the trigger), so a 5' candidate (m, j) lies at j >= s + m + 1
+// and its part on B -- the last Lb rows -- begins at or after j - Lb - k: the first m - Lb - kt columns of
+// the window cannot matter to B (a restarted scan is exact for what begins after its start).  Likewise every
+// window that ends before the read does ends at least m_max - Lp + kt columns after its last trigger, and a
+// path of a 3' adapter has crossed row Lb by then with m - Lb - kt columns to spare.  `trim` = m - Lb - kt.
 ORC_HD bool block_test(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                        const WinList *wl, const char *peq32b_base, int lane, int Lb, int k, int type,
-                       const uint8_t *kmax, int min_ov, const uint32_t *first_mask)
+                       const uint8_t *kmax, int min_ov, const uint32_t *first_mask, int trim = 0)
 {
     if (Lb <= 0) return true;
     const uint32_t n = len;
@@ -897,7 +905,11 @@ ORC_HD bool block_test(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len
     else      { sel0 = 0x5534u; sel1 = 0x5524u; sel2 = 0x5514u; sel3 = 0x5504u; }
     const uint32_t nw = wl ? wl->n : 1u;
     for (uint32_t w = 0; w < nw; w++) {
-        const uint32_t s = wl ? wl->s[w] : 0u, e = wl ? wl->e[w] : n;
+        uint32_t s = wl ? wl->s[w] : 0u, e = wl ? wl->e[w] : n;
+        if (trim > 0) {
+            if (type == TYPE_FRONT) { if (s > 0u) s = s + (uint32_t)trim < e ? s + (uint32_t)trim : e; }
+            else if (e < n) e = e > s + (uint32_t)trim ? e - (uint32_t)trim : s;
+        }
         const bool free0 = s == 0u && type == TYPE_FRONT;
         uint32_t Pv, Mv = 0;
         int D;

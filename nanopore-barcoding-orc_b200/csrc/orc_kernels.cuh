@@ -295,13 +295,13 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
               const View *__restrict__ views, const WinList *__restrict__ wins,
               const uint32_t *__restrict__ wcols_sorted, const uint32_t *__restrict__ item_order,
               uint32_t n_items, uint32_t *__restrict__ jobs, uint32_t *__restrict__ counters,
-              unsigned long long *__restrict__ cells_2b)
+              unsigned long long *__restrict__ cells_2b, int trim_on)
 {
     __shared__ __align__(16) uint32_t s_peq32b[16][64];
     __shared__ uint32_t s_first_mask[MAX_M + 32];
     __shared__ uint8_t s_kmax[MAX_AD][MAX_M + 8];     // the pruning limits (kmax[a][0])
     __shared__ int s_k[MAX_AD], s_min_ov[MAX_AD], s_lb[MAX_AD], s_m[MAX_AD];
-    __shared__ int s_na, s_type;
+    __shared__ int s_na, s_type, s_trim;      // s_trim: k_max + 1 when the windows come from stage 1 (0: whole reads)
     for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32b[0][0])[i] = (&tab->peq32b[0][0])[i];
     for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_mask[i] = tab->first_mask[i];
     for (int i = threadIdx.x; i < MAX_AD * (MAX_M + 8); i += blockDim.x)
@@ -312,7 +312,7 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
         s_lb[threadIdx.x] = tab->block_len[threadIdx.x];
         s_m[threadIdx.x] = tab->m[threadIdx.x];
     }
-    if (threadIdx.x == 0) { s_na = tab->n_adapters; s_type = tab->type; }
+    if (threadIdx.x == 0) { s_na = tab->n_adapters; s_type = tab->type; s_trim = (tab->use_filter && trim_on) ? tab->k_max + 1 : 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t na = (uint32_t)s_na;
@@ -347,7 +347,7 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
                 dst[0] = src[0]; dst[1] = src[1];
             }
             keep = block_test(W, v.lo, v.len, dir, &wl, base_b, a + (int)na * dir, s_lb[a], s_k[a], type,
-                              s_kmax[a], s_min_ov[a], s_first_mask);
+                              s_kmax[a], s_min_ov[a], s_first_mask, s_trim ? s_m[a] - s_lb[a] - s_trim + 1 : 0);
         }
         const uint32_t mk = __ballot_sync(0xffffffffu, keep);
         if (mk) {

@@ -139,7 +139,8 @@ extern "C" int hostsim_demux(int n_rounds,
                 g_pairs[rd]++;
                 if (R.indels && !block_test(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr,
                                             (const char *)&R.peq32b[0][0], lane, R.block_len[a], R.k[a], R.type,
-                                            R.kmax[a][0], R.min_ov[a], R.first_mask)) continue;
+                                            R.kmax[a][0], R.min_ov[a], R.first_mask,
+                                            R.use_filter ? R.m[a] - R.block_len[a] - R.k_max : 0)) continue;
                 g_kept[rd]++;
                 LaneScan L;
                 scan_lane(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr, peq_bank(R, lane), lane,
