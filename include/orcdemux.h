@@ -39,6 +39,8 @@ typedef struct orc_ctx orc_ctx;   /* opaque; one per GPU */
 /* adapter types == cutadapt's -g / -a / -g ^ / -a ...$ (adapters.py Front/Back/Prefix/SuffixAdapter) */
 enum { ORC_FRONT = 0, ORC_BACK = 1, ORC_PREFIX = 2, ORC_SUFFIX = 3 };
 
+enum { ORC_ACTION_TRIM = 0, ORC_ACTION_RETAIN = 1 };
+
 enum {
     ORC_OK = 0,
     ORC_EINVAL = -1,       /* bad argument / unsupported option */
@@ -59,6 +61,8 @@ typedef struct orc_round_params {
     int32_t min_overlap;            /* -O  (cutadapt default 3) */
     int32_t indels;                 /* 1; 0 == --no-indels */
     int32_t revcomp;                /* --rc */
+    int32_t action;                 /* ORC_ACTION_TRIM (--action=trim, 0) or ORC_ACTION_RETAIN (--action=retain: the
+                                       read is cut at the far side of the match, the adapter itself stays) */
 } orc_round_params;
 
 typedef struct orc_params {

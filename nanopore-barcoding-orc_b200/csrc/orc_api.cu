@@ -276,6 +276,8 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
             why = build_round_table(ctx->h_tab[r], rp.n_adapters, rp.type, rp.sequences,
                                     rp.max_error_rate, rp.min_overlap, rp.indels, rp.revcomp);
         if (!why.empty()) { ctx->err = why; return ORC_EINVAL; }
+        if (rp.action != ORC_ACTION_TRIM && rp.action != ORC_ACTION_RETAIN) { ctx->err = "unsupported: action must be trim or retain"; return ORC_EINVAL; }
+        ctx->h_tab[r].action = rp.action;
         ctx->h_seed[r].on = 0;
         if (!ctx->anchored[r]) {
             const char *off = getenv("ORC_NO_SEED");        // A/B measurements: keep the flank scan
@@ -691,6 +693,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             SelectArgs A;
             A.type = ctx->h_tab[r].type;
             A.revcomp = ctx->h_tab[r].revcomp;
+            A.action = ctx->h_tab[r].action;
             A.views_in = s.d_views[r];
             A.views_out = s.d_views[r + 1];
             A.prev = prev;

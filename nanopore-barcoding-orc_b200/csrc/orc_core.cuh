@@ -57,7 +57,8 @@ struct RoundTable {
     int32_t revcomp;                // --rc
     int32_t min_overlap;            // -O, not yet clamped per adapter
     int32_t n_lanes;                // 2 * n_adapters
-    int32_t pad_[3];
+    int32_t action;                 // 0: trim, 1: retain (select_read)
+    int32_t pad_[2];
     int32_t m[MAX_AD];              // adapter length
     int32_t k[MAX_AD];              // int(max_error_rate * m)
     int32_t min_ov[MAX_AD];         // min(min_overlap, m)
@@ -2100,8 +2101,10 @@ ORC_HD void band_resolve_pair(const uint32_t *W, const View &v, const RoundTable
 // select_read: R9, R10 from the per-orientation winners of R8.  key[o] is the maximum of
 // pack_key() over the pairs of logical orientation o that matched (0 = none).
 // ------------------------------------------------------------------------------------
+// action 0: --action=trim (the adapter and what lies beyond it go); 1: --action=retain (the adapter stays:
+// AdapterCutter's "retain" keeps read[match.rstart:] of a 5' match and read[:match.rstop] of a 3' match)
 ORC_HD void select_read(int type, int revcomp, const View &v, const uint64_t key[2], const PairResult *results,
-                        Match &out, View &next)
+                        Match &out, View &next, int action = 0)
 {
     const int fs = key[0] ? (int)(key[0] >> 44) - 512 : 0;
     const int rs = key[1] ? (int)(key[1] >> 44) - 512 : 0;
@@ -2124,8 +2127,8 @@ ORC_HD void select_read(int type, int revcomp, const View &v, const uint64_t key
     // R10: FRONT keeps [query_stop, n), BACK keeps [0, query_start) of the chosen orientation
     const uint32_t n = v.len;
     uint32_t a0, b0;
-    if (type == TYPE_FRONT) { a0 = (uint32_t)r.query_stop; b0 = n; }
-    else { a0 = 0; b0 = (uint32_t)r.query_start; }
+    if (type == TYPE_FRONT) { a0 = (uint32_t)(action ? r.query_start : r.query_stop); b0 = n; }
+    else { a0 = 0; b0 = (uint32_t)(action ? r.query_stop : r.query_start); }
     if (b0 < a0) b0 = a0;
     next.len = b0 - a0;
     next.lo = eff ? v.lo + (n - b0) : v.lo + a0;

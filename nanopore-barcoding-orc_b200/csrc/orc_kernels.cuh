@@ -639,7 +639,7 @@ anchored_kernel(const AnchoredTable *__restrict__ tab, const uint8_t *__restrict
 // ------------------------------------------------------------------------------------
 // select: also derives, after the last round, the bin id and the FASTQ record size.
 struct SelectArgs {
-    int type, revcomp;          // of the round (RoundTable.type / .revcomp)
+    int type, revcomp, action;  // of the round (RoundTable.type / .revcomp / .action)
     const View *views_in;
     View *views_out;
     const Match *prev;          // matches of the previous round (nullptr in round 1)
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelectArgs A)
             uint64_t key[2];
             key[0] = A.best_key[(size_t)r * 2];
             key[1] = A.best_key[(size_t)r * 2 + 1];
-            select_read(A.type, A.revcomp, v, key, A.results, mt, next);
+            select_read(A.type, A.revcomp, v, key, A.results, mt, next, A.action);
         }
         if (A.next_bases != nullptr) {
             const uint32_t add = (valid && mt.adapter >= 0) ? next.len : 0u;

@@ -135,8 +135,8 @@ def parse_cutadapt_argv(argv: List[str]):
         else:
             opt["inputs"].append(a)
         i += 1
-    if opt["action"] != "trim":
-        raise Unsupported("--action=%s (only trim)" % opt["action"])
+    if opt["action"] not in ("trim", "retain"):
+        raise Unsupported("--action=%s (trim and retain are built)" % opt["action"])
     if len(opt["inputs"]) != 1:
         raise Unsupported("exactly one (single-end) input file is expected, got %d" % len(opt["inputs"]))
     if not opt["out"]:
@@ -145,6 +145,8 @@ def parse_cutadapt_argv(argv: List[str]):
         # one output file: the primer-trimming call shapes of 04_cleaning_primers.sh (orcdemux/primers.py)
         if not (opt["g"] or opt["a"]):
             raise Unsupported("no adapters given")
+        if opt["action"] != "trim":
+            raise Unsupported("--action=%s with a single output file" % opt["action"])
         return opt
     if opt["untrimmed_output"] or opt["discard_untrimmed"]:
         raise Unsupported("--untrimmed-output / --discard-untrimmed together with a {name} template")
@@ -380,7 +382,7 @@ def run_single_round(opt, argv, device=0) -> int:
         raise Unsupported("anchored adapters need --no-indels (the indel variant is not built)")
     if anchored:
         kind = ORC_PREFIX if kind == ORC_FRONT else ORC_SUFFIX
-    rnd = E.Round(names, seqs, kind, opt["e"], opt["O"], opt["indels"], opt["rc"])
+    rnd = E.Round(names, seqs, kind, opt["e"], opt["O"], opt["indels"], opt["rc"], opt["action"])
     t0 = time.time()
     (max_reads, max_bytes), slots = _batch_shape(), 3
     threads = max(2, min(os.cpu_count() or 2, opt["cores"] if opt["cores"] > 0 else (os.cpu_count() or 2)))
@@ -550,6 +552,9 @@ def main(argv: Optional[List[str]] = None) -> int:
     try:
         if argv and argv[0] == "two-round":
             return run_two_round(argv[1:])
+        if argv and argv[0] == "orient":
+            from . import orient
+            return orient.main(argv[1:])
         if argv and argv[0] in ("--version",):
             print("4.9 (orcdemux)")
             return 0

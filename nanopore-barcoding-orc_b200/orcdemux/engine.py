@@ -31,12 +31,15 @@ class Round:
     min_overlap: int = 3            # -O
     indels: bool = True             # not --no-indels
     revcomp: bool = True            # --rc
+    action: str = "trim"            # --action=trim | retain (keep the adapter, cut what lies beyond it)
 
     def __post_init__(self):
         # parser.read_adapters_fasta + adapters.SingleAdapter.__init__: upper(), U -> T
         self.sequences = [s.upper().replace("U", "T") for s in self.sequences]
         if len(self.names) != len(self.sequences):
             raise ValueError("names and sequences differ in length")
+        if self.action not in ("trim", "retain"):
+            raise ValueError("action must be trim or retain")
 
 
 @dataclass
@@ -112,6 +115,7 @@ class Engine:
             rp.min_overlap = r.min_overlap
             rp.indels = int(r.indels)
             rp.revcomp = int(r.revcomp)
+            rp.action = _lib.ORC_ACTION_RETAIN if r.action == "retain" else _lib.ORC_ACTION_TRIM
         self.n_bins = 1
         for r in rounds:
             self.n_bins *= len(r.sequences) + 1

@@ -20,6 +20,7 @@ ORC_MAX_ADAPTER_LEN = 64
 KERNEL_NAMES = ["sort_reads", "seed", "trigger", "sort_items", "filter", "scan", "resolve_band", "resolve_wide", "select"]
 ORC_N_KERNELS = len(KERNEL_NAMES)
 ORC_FRONT, ORC_BACK, ORC_PREFIX, ORC_SUFFIX = 0, 1, 2, 3
+ORC_ACTION_TRIM, ORC_ACTION_RETAIN = 0, 1
 ORC_OK, ORC_EINVAL, ORC_ECUDA, ORC_ECAPACITY, ORC_ESTATE = 0, -1, -2, -3, -4
 
 # every symbol include/orcdemux.h declares
@@ -41,7 +42,7 @@ class RoundParams(C.Structure):
     _fields_ = [("n_adapters", C.c_int32), ("type", C.c_int32),
                 ("names", C.POINTER(C.c_char_p)), ("sequences", C.POINTER(C.c_char_p)),
                 ("max_error_rate", C.c_double), ("min_overlap", C.c_int32),
-                ("indels", C.c_int32), ("revcomp", C.c_int32)]
+                ("indels", C.c_int32), ("revcomp", C.c_int32), ("action", C.c_int32)]
 
 
 class Params(C.Structure):
