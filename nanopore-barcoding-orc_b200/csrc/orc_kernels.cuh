@@ -853,6 +853,50 @@ __device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8
     if (done + (uint32_t)lane < n) dst[done + lane] = src[done + lane];
 }
 
+// The same with 16-byte stores: the destination is written in aligned 16-byte words, each assembled from the
+// two aligned source words it straddles by four funnel shifts; which four of the eight loaded 32-bit words
+// are involved depends on the copy's source/destination phase only, so the choice is the same for every
+// lane.  Head and tail bytes singly.  src may be over-read by up to 31 bytes (the blobs have 64 bytes of slack).
+__device__ __forceinline__ uint4 shift16(const uint4 lo, const uint4 hi, uint32_t a, uint32_t b)
+{
+    uint4 r;
+    switch (a) {                    // a = source phase / 4 (warp-uniform), b = (source phase % 4) * 8
+    case 0: r.x = __funnelshift_r(lo.x, lo.y, b); r.y = __funnelshift_r(lo.y, lo.z, b);
+            r.z = __funnelshift_r(lo.z, lo.w, b); r.w = __funnelshift_r(lo.w, hi.x, b); break;
+    case 1: r.x = __funnelshift_r(lo.y, lo.z, b); r.y = __funnelshift_r(lo.z, lo.w, b);
+            r.z = __funnelshift_r(lo.w, hi.x, b); r.w = __funnelshift_r(hi.x, hi.y, b); break;
+    case 2: r.x = __funnelshift_r(lo.z, lo.w, b); r.y = __funnelshift_r(lo.w, hi.x, b);
+            r.z = __funnelshift_r(hi.x, hi.y, b); r.w = __funnelshift_r(hi.y, hi.z, b); break;
+    default: r.x = __funnelshift_r(lo.w, hi.x, b); r.y = __funnelshift_r(hi.x, hi.y, b);
+            r.z = __funnelshift_r(hi.y, hi.z, b); r.w = __funnelshift_r(hi.z, hi.w, b); break;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void warp_copy16(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                            uint32_t n, int lane)
+{
+    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u));
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    const uint32_t nq = (n - head) >> 4;
+    const uint8_t *sp = src + head;
+    const uint32_t ph = (uint32_t)((uintptr_t)sp & 15u);
+    const uint32_t a = ph >> 2, b = (ph & 3u) * 8u;
+    const uint4 *sa = reinterpret_cast<const uint4 *>((uintptr_t)sp & ~(uintptr_t)15);
+    uint4 *da = reinterpret_cast<uint4 *>(dst + head);
+    for (uint32_t q = lane; q < nq; q += 64) {
+        const uint32_t q1 = q + 32u;
+        const bool two = q1 < nq;
+        const uint4 l0 = sa[q], h0 = sa[q + 1];
+        uint4 l1 = make_uint4(0, 0, 0, 0), h1 = l1;
+        if (two) { l1 = sa[q1]; h1 = sa[q1 + 1]; }
+        da[q] = shift16(l0, h0, a, b);
+        if (two) da[q1] = shift16(l1, h1, a, b);
+    }
+    const uint32_t done = head + 16u * nq;
+    if (done + (uint32_t)lane < n) dst[done + lane] = src[done + lane];
+}
+
 // The same in reverse: dst[i] = f(src[n - 1 - i]) with f = the complement table (bases) or the
 // identity (qualities, comp == nullptr).  Output word w holds the source bytes e, e-1, e-2, e-3
 // (e = n - 1 - head - 4w): an unaligned 4-byte window read as above, bytes swapped.
@@ -894,7 +938,10 @@ __device__ __forceinline__ void warp_copy_rev(uint8_t *__restrict__ dst, const u
     }
 }
 
-// One warp per read: '@' name [' rc']* '\n' seq '\n' '+' '\n' qual '\n'
+// '@' name [' rc']* '\n' seq '\n' '+' '\n' qual '\n' of every read that has a destination.
+// A warp takes 32 consecutive reads at a time: every lane loads the placement and the view of one of them
+// (coalesced, one round of latency for 32 reads, and reads without a destination -- dropped bins -- cost
+// nothing more), then the warp copies the records one after the other, the fields handed round by shuffles.
 __global__ void __launch_bounds__(256, 8)
 emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
             const uint8_t *__restrict__ names, const uint64_t *__restrict__ name_offsets,
@@ -909,41 +956,60 @@ emit_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = warp; r < n_reads; r += n_warps) {
-        const uint64_t d = dest[r];
-        if (d == ~0ull) continue;
-        const View v = views[r];
-        const uint64_t n0 = name_offsets[r];
-        const uint32_t nl = name_lengths ? name_lengths[r] : (uint32_t)(name_offsets[r + 1] - n0);
-        const uint32_t nrc = v.rc >> 8;
-        const uint32_t L = v.len;
-        uint8_t *o = out + d;
-        if (lane == 0) o[0] = '@';
-        warp_copy(o + 1, names + n0, nl, lane);
-        o += 1 + nl;
-        for (uint32_t i = lane; i < 3 * nrc; i += 32) o[i] = (i % 3 == 0) ? ' ' : (i % 3 == 1) ? 'r' : 'c';
-        o += 3 * nrc;
-        if (lane == 0) o[0] = '\n';
-        o += 1;
-        const uint8_t *s = seq + v.lo;
-        const uint8_t *q = qual + v.lo + (qual_offsets ? qual_offsets[r] - offsets[r] : 0ull);
-        if (v.rc & 1u) {
-            warp_copy_rev(o, s, L, lane, comp);
-            warp_copy_rev(o + L + 3, q, L, lane, nullptr);
-        } else {
-            warp_copy(o, s, L, lane);
-            warp_copy(o + L + 3, q, L, lane);
-            if (nrc >= 2u) {
-                // reverse-complemented in both rounds: dnaio's table sends U to A and A to T, so a read
-                // that is back in its own orientation has T where it had U
-                __syncwarp();
-                for (uint32_t i = lane; i < L; i += 32) {
-                    const uint8_t c = s[i];
-                    if (c == 'U' || c == 'u') o[i] = (uint8_t)(c - 1);
-                }
+    for (uint32_t base = warp * 32u; base < n_reads; base += n_warps * 32u) {
+        const uint32_t r = base + (uint32_t)lane;
+        unsigned long long my_d = ~0ull, my_lo = 0, my_n0 = 0, my_qd = 0;
+        uint32_t my_len = 0, my_rc = 0, my_nl = 0;
+        if (r < n_reads) {
+            my_d = dest[r];
+            if (my_d != ~0ull) {
+                const View v = views[r];
+                my_lo = v.lo; my_len = v.len; my_rc = v.rc;
+                my_n0 = name_offsets[r];
+                my_nl = name_lengths ? name_lengths[r] : (uint32_t)(name_offsets[r + 1] - my_n0);
+                my_qd = qual_offsets ? qual_offsets[r] - offsets[r] : 0ull;
             }
         }
-        if (lane == 0) { o[L] = '\n'; o[L + 1] = '+'; o[L + 2] = '\n'; o[2 * L + 3] = '\n'; }
+        uint32_t todo = __ballot_sync(0xffffffffu, my_d != ~0ull);
+        while (todo) {
+            const int src_lane = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            const unsigned long long d = __shfl_sync(0xffffffffu, my_d, src_lane);
+            const unsigned long long lo = __shfl_sync(0xffffffffu, my_lo, src_lane);
+            const unsigned long long n0 = __shfl_sync(0xffffffffu, my_n0, src_lane);
+            const unsigned long long qd = __shfl_sync(0xffffffffu, my_qd, src_lane);
+            const uint32_t L = __shfl_sync(0xffffffffu, my_len, src_lane);
+            const uint32_t rc = __shfl_sync(0xffffffffu, my_rc, src_lane);
+            const uint32_t nl = __shfl_sync(0xffffffffu, my_nl, src_lane);
+            const uint32_t nrc = rc >> 8;
+            uint8_t *o = out + d;
+            if (lane == 0) o[0] = '@';
+            warp_copy(o + 1, names + n0, nl, lane);
+            o += 1 + nl;
+            for (uint32_t i = lane; i < 3 * nrc; i += 32) o[i] = (i % 3 == 0) ? ' ' : (i % 3 == 1) ? 'r' : 'c';
+            o += 3 * nrc;
+            if (lane == 0) o[0] = '\n';
+            o += 1;
+            const uint8_t *s = seq + lo;
+            const uint8_t *q = qual + lo + qd;
+            if (rc & 1u) {
+                warp_copy_rev(o, s, L, lane, comp);
+                warp_copy_rev(o + L + 3, q, L, lane, nullptr);
+            } else {
+                warp_copy16(o, s, L, lane);
+                warp_copy16(o + L + 3, q, L, lane);
+                if (nrc >= 2u) {
+                    // reverse-complemented in both rounds: dnaio's table sends U to A and A to T, so a read
+                    // that is back in its own orientation has T where it had U
+                    __syncwarp();
+                    for (uint32_t i = lane; i < L; i += 32) {
+                        const uint8_t c = s[i];
+                        if (c == 'U' || c == 'u') o[i] = (uint8_t)(c - 1);
+                    }
+                }
+            }
+            if (lane == 0) { o[L] = '\n'; o[L + 1] = '+'; o[L + 2] = '\n'; o[2 * L + 3] = '\n'; }
+        }
     }
 }
 
