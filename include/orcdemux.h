@@ -176,6 +176,11 @@ int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *out);
  * second one, waits for it and returns the device time between them (milliseconds) */
 int orc_timer_start(orc_ctx *ctx, int slot);
 int orc_timer_stop(orc_ctx *ctx, int slot, float *ms);
+/* the same over ALL slots: device time of everything launched on any slot between the two calls (every slot's
+ * stream waits for the begin event, the end event waits for every stream) -- for throughput measurements with
+ * several resident batches in flight, whose kernels overlap as they do in the submit/wait pipeline */
+int orc_span_begin(orc_ctx *ctx);
+int orc_span_end(orc_ctx *ctx, float *ms);
 /* cumulative reads per bin over every batch waited on so far ([n_bins]) */
 int orc_counts(orc_ctx *ctx, uint64_t *bins);
 

@@ -106,6 +106,8 @@ struct orc_ctx {
     AnchoredTable *d_anch[2] = {nullptr, nullptr};
     bool anchored[2] = {false, false};
     uint8_t *d_pack_lut = nullptr, *d_comp_lut = nullptr, *d_drop = nullptr;
+    cudaEvent_t ev_span[2] = {nullptr, nullptr};   // orc_span_begin / orc_span_end
+    std::vector<cudaEvent_t> ev_span_slot;
     SynthTable *d_synth = nullptr;   // orc_synth(): built on first use
     uint64_t *d_synth_totals = nullptr;
     std::vector<Slot> slots;
@@ -374,6 +376,8 @@ extern "C" void orc_destroy(orc_ctx *ctx)
     for (int r = 0; r < 2; r++) { cudaFree(ctx->d_tab[r]); cudaFree(ctx->d_anch[r]); cudaFree(ctx->d_seed[r]); }
     cudaFree(ctx->d_pack_lut); cudaFree(ctx->d_comp_lut); cudaFree(ctx->d_drop);
     cudaFree(ctx->d_synth); cudaFree(ctx->d_synth_totals);
+    for (int i = 0; i < 2; i++) if (ctx->ev_span[i]) cudaEventDestroy(ctx->ev_span[i]);
+    for (cudaEvent_t e : ctx->ev_span_slot) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -1026,6 +1030,40 @@ extern "C" int orc_timer_stop(orc_ctx *ctx, int slot, float *ms)
     CK(cudaEventRecord(sp->ev[EV_T1], sp->stream));
     CK(cudaEventSynchronize(sp->ev[EV_T1]));
     CK(cudaEventElapsedTime(ms, sp->ev[EV_T0], sp->ev[EV_T1]));
+    return ORC_OK;
+}
+
+// Device time of everything launched on ANY slot between the two calls: the streams of all slots wait for the
+// begin event, and the end event waits for all of them.  For throughput measurements with several resident
+// batches in flight (their kernels overlap, as they do in the submit/wait pipeline).
+extern "C" int orc_span_begin(orc_ctx *ctx)
+{
+    if (!ctx) return ORC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->ev_span[0]) {
+        CK(cudaEventCreate(&ctx->ev_span[0]));
+        CK(cudaEventCreate(&ctx->ev_span[1]));
+        ctx->ev_span_slot.assign((size_t)ctx->n_slots, nullptr);
+        for (auto &e : ctx->ev_span_slot) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    for (auto &s : ctx->slots) CK(cudaStreamSynchronize(s.stream));
+    CK(cudaEventRecord(ctx->ev_span[0], ctx->slots[0].stream));
+    for (size_t i = 1; i < ctx->slots.size(); i++) CK(cudaStreamWaitEvent(ctx->slots[i].stream, ctx->ev_span[0], 0));
+    return ORC_OK;
+}
+
+extern "C" int orc_span_end(orc_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return ORC_EINVAL;
+    if (!ctx->ev_span[0]) { ctx->err = "orc_span_end without orc_span_begin"; return ORC_ESTATE; }
+    CK(cudaSetDevice(ctx->device));
+    for (size_t i = 1; i < ctx->slots.size(); i++) {
+        CK(cudaEventRecord(ctx->ev_span_slot[i], ctx->slots[i].stream));
+        CK(cudaStreamWaitEvent(ctx->slots[0].stream, ctx->ev_span_slot[i], 0));
+    }
+    CK(cudaEventRecord(ctx->ev_span[1], ctx->slots[0].stream));
+    CK(cudaEventSynchronize(ctx->ev_span[1]));
+    CK(cudaEventElapsedTime(ms, ctx->ev_span[0], ctx->ev_span[1]));
     return ORC_OK;
 }
 

@@ -269,6 +269,15 @@ class Engine:
         self._check(self._L.orc_timer_stop(self._ctx, slot, C.byref(ms)), "orc_timer_stop")
         return float(ms.value)
 
+    def span_begin(self):
+        """Start a device-time span over all slots (orc_span_begin)."""
+        self._check(self._L.orc_span_begin(self._ctx), "orc_span_begin")
+
+    def span_end(self) -> float:
+        ms = C.c_float(0.0)
+        self._check(self._L.orc_span_end(self._ctx, C.byref(ms)), "orc_span_end")
+        return float(ms.value)
+
     def counts(self) -> np.ndarray:
         out = np.zeros(self.n_bins, dtype=np.uint64)
         self._check(self._L.orc_counts(self._ctx, out.ctypes.data), "orc_counts")
