@@ -1,16 +1,26 @@
 // orc_kernels.cuh -- the sm_100a kernels of the demultiplexer (included by orc_api.cu).
 //
 //   pack_kernel        ASCII bases -> 4-bit codes, flat (code index == byte index).  HBM-bound.
-//   init_views_kernel  view 0 of every read = the whole read, forward.
-//   scan_kernel        one warp per read, one lane per (adapter, orientation) pair:
-//                      Myers/Hyyro bit-parallel semi-global scan (orc_core.cuh scan_lane),
-//                      index table (Peq) staged in shared memory, candidate pairs appended
-//                      to a task list with a warp ballot.  INT32-ALU-bound: this is the
-//                      kernel the roofline in bench.py is about.
-//   resolve_kernel     one thread per candidate pair: cutadapt's exact recurrence on the
-//                      band of diagonals around the candidates (orc_core.cuh resolve_pair).
+//   init_views_kernel  view 0 of every read = the whole read, forward; length classes for the ordering.
+//   bucket_scatter_kernel  counting sort by size class (reads by view length, items by window columns).
+//   per round:
+//   seed_kernel        stage 1s, one thread per read: exact 8-mer pieces of the adapters looked up in a
+//                      perfect hash in shared memory -> windows of the whole-adapter alignments.
+//   trigger_kernel     stage 1, one thread per (read, direction): the windows at the read's ends (or the
+//                      whole flank scan when the round has no seed table), merged with the seed windows.
+//   filter_kernel      stage 2a, one lane per (read, direction, adapter): 32-row Myers block test over the
+//                      window columns; survivors appended to a job list.  INT32-ALU-bound, the largest
+//                      share of the step.
+//   scan_kernel        stage 2b, one lane per surviving pair: the 64-bit Myers/Hyyro semi-global scan
+//                      (orc_core.cuh scan_lane), table in shared memory; pairs whose candidates all cost 0
+//                      are settled here, the others become resolver tasks.
+//   resolve_band_kernel  one thread per task: the diagonals around the candidates, 8-byte column entries
+//                      in shared memory (orc_core.cuh band_*); cutadapt's score/origin by walking back.
+//   resolve_kernel     the same for the few tasks whose candidates spread over too many diagonals
+//                      (128-bit column ring in local memory), on a side stream next to the band resolver.
+//   anchored_kernel    anchored --no-indels rounds instead of all of the above.
 //   select_kernel      best of the adapters, --rc choice, trim -> next view, bin id.
-//   bin_count/scan/place, emit_kernel
+//   bin_count/scan/offsets/place, emit_kernel
 //                      stable multi-way partition of the trimmed reads into their
 //                      SP5 x SP27 bins and assembly of the FASTQ records.  HBM-bound.
 #pragma once
