@@ -1619,17 +1619,33 @@ ORC_HD void resolve_pair(const uint32_t *W, const View &v, const RoundTable &T, 
 //
 // A path with at most k errors stays within k diagonals of where it ends, so per column only the rows
 // around the end cells' diagonals matter: with end cells on diagonals dlo..dhi (column minus row), column
-// j keeps the 32 rows from j - (dhi + k + 1) upwards of Pv and D0 -- 8 bytes, against the 16 of the
-// whole vectors -- and needs no costs.  That fits shared memory (BAND_COLS columns per thread), which is
-// what the whole exercise is for: the 2 KB per-thread ring of the wide resolver lives in local memory.
+// j needs the 32 rows from j - (dhi + k + 1) upwards of Pv and D0, and no costs.
+//
+// A walk looks at a column only where its path meets a cell whose characters differ -- at most k times --
+// so the columns are not kept at all: the ring holds the scan's state (VP, VN on the band, 8 bytes) after
+// every BAND_CKPT-th column, and band_step() re-runs the one to BAND_CKPT columns from the checkpoint in
+// front of the cell it asks about (a few dozen instructions, a handful of times per task, against the
+// ~2000 of the scan).  With a checkpoint every second column that is 320 bytes of ring and 64 bytes of
+// read codes per thread in shared memory, 16 warps per SM -- the first band resolver's 640-byte ring (one
+// entry per column) held the kernel at 8; the wide resolver's 2 KB ring lives in local memory.  Measured
+// per 1 Mi COI reads (rounds 1 + 2): every column 0.64 + 0.46 ms, every 2nd 0.56 + 0.38, every 4th
+// 0.61 + 0.42 (the walks of a warp run in lockstep, so a re-run costs a warp instruction stream for the
+// few lanes that need it), every 8th 0.73 + 0.49.
 // Tasks whose end cells span more than 30 - 2k diagonals, or whose scan is longer than BAND_COLS columns,
 // keep the wide resolver above.
 // ------------------------------------------------------------------------------------
-constexpr int BAND_COLS = 80;           // columns of one scan, entry 0 unused
+constexpr int BAND_COLS = 80;           // columns of one scan (column 0 = the scan's start state)
+#ifndef ORC_BAND_CKPT_LOG
+#define ORC_BAND_CKPT_LOG 1
+#endif
+constexpr int BAND_CKPT_LOG = ORC_BAND_CKPT_LOG;
+constexpr int BAND_CKPT = 1 << BAND_CKPT_LOG;           // the state after columns 0, 2, 4, ... is kept
+constexpr int BAND_ENTRIES = BAND_COLS / BAND_CKPT;     // a scan has at most BAND_COLS - 1 columns
+static_assert(BAND_CKPT <= 8 && BAND_COLS % BAND_CKPT == 0, "band_columns stores checkpoints inside its chunks of 8 columns");
 constexpr int BAND_CODE_WORDS = 16;     // packed read codes a scan and its walks touch: BAND_COLS + 16 before + 24 behind
 constexpr uint32_t TASK_WIDE = 1u;      // Task.pad_ bit 0: not eligible for the band resolver
 
-struct alignas(8) BandEntry { uint32_t pv, d0; };
+struct alignas(8) BandEntry { uint32_t vp, vn; };      // the band's vertical deltas after a checkpoint column
 // What the band resolver reads of one adapter, compact (the kernel keeps one per adapter of the round in
 // shared memory; RoundTable spreads the same over arrays sized for MAX_AD adapters)
 struct BandAdapter {
@@ -1637,7 +1653,7 @@ struct BandAdapter {
     uint32_t code4[12], rcode4[12];
     uint8_t kmax[3][MAX_M + 8];         // RoundTable.kmax[a]: pruning limits, R5 limits, R6 limits
 };
-struct BandRing {                       // entry c of this thread: p[c * stride]
+struct BandRing {                       // checkpoint q (the state after column q * BAND_CKPT) of this thread: p[q * stride]
     BandEntry *p;
     int32_t stride;
     // the packed codes of the read around the scan, copied once per scan (16 loads in flight together) so that
@@ -1780,6 +1796,8 @@ struct BandCtx {
     int32_t top_j, traced_j, traced_score, traced_origin;
     uint64_t hc0, hc1;                  // D[m][j] of the hull columns jf .. jf+31, four bits each (15: above k)
     uint32_t vpn, vnn;                  // vertical deltas of column we in its band rows
+    uint32_t hull_p, hull_n;            // horizontal deltas of row m in the hull columns: bit j - jf
+    int32_t sp0;                        // band position 0 of column ws + c in the match table: sp0 + c
     Best best;
 };
 
@@ -1789,18 +1807,52 @@ ORC_HD int band_hull_cost(const BandCtx &C, int j)
     return (int)(((q < 16 ? C.hc0 : C.hc1) >> (4 * (q & 15))) & 15ull);
 }
 
-// One step of the walk at a cell whose characters differ: cutadapt's predecessor from the two stored bits.
-ORC_HD void band_step(const BandRing &R, int ws, int boff, int &i, int &j, int &d, int &score)
+// x << s, 0 for s >= 32 (and for "negative" s)
+ORC_HD uint32_t shl32(uint32_t x, uint32_t s) { return s < 32u ? x << s : 0u; }
+
+// The 32 band rows of the match vector for read code `code` in column ws + c.
+ORC_HD uint32_t band_eq(const char *peq_base, uint32_t code_lane, int sp0, int c)
 {
-    const BandEntry e = R.p[(j - ws) * R.stride];
-    const uint32_t b = (uint32_t)(boff - (j - i));
-    if (!((e.d0 >> b) & 1u)) { score -= 1; --i; --j; }          // diagonal delta 1: mismatch
-    else if ((e.pv >> b) & 1u) { score -= 2; --i; }             // vertical delta +1: insertion
+    const int sp = imin(imax(sp0 + c, 0), 95);
+    const uint32_t *e = reinterpret_cast<const uint32_t *>(peq_base + 2u * code_lane) + (sp >> 5);
+    return funnel_r(e[0], e[1], (uint32_t)sp & 31u);
+}
+
+// One column of the band recurrence (see band_columns): VP, VN of the previous column in, of this one out.
+ORC_HD void band_advance(uint32_t Eq, uint32_t &VP, uint32_t &VN, uint32_t &D0, uint32_t &HP, uint32_t &HN)
+{
+    VP = (VP >> 1) | 0x80000000u;
+    VN >>= 1;
+    D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+    HP = VN | ~(D0 | VP);
+    HN = D0 & VP;
+    const uint32_t X = HP << 1;
+    VP = (HN << 1) | ~(D0 | X);
+    VN = D0 & X;
+}
+
+// One step of the walk at a cell whose characters differ: cutadapt's predecessor from two bits of column j,
+// which is re-run from the checkpoint in front of it.
+ORC_HD void band_step(const BandCtx &C, const BandRing &R, uint64_t lo, uint32_t len, int &i, int &j, int &d, int &score)
+{
+    const int c = j - C.ws;                                     // >= 1
+    const int base = (c - 1) & ~(BAND_CKPT - 1);
+    const BandEntry e = R.p[(base >> BAND_CKPT_LOG) * R.stride];
+    uint32_t VP = e.vp, VN = e.vn, D0 = 0, HP, HN;
+    const uint32_t lane8 = (uint32_t)(C.lane & 31) * 8u;        // band_eq doubles it: entries of 16 bytes
+    for (int cc = base + 1; cc <= c; cc++) {
+        const int64_t idx = C.dir ? (int64_t)lo + (int64_t)len - (C.ws + cc) : (int64_t)lo + (C.ws + cc) - 1;
+        const uint32_t code = (R.cw[(int)((idx >> 3) - R.w0) * R.stride] >> ((uint32_t)(idx & 7) * 4u)) & 15u;
+        band_advance(band_eq(C.peq_base, (code << 8) | lane8, C.sp0, cc), VP, VN, D0, HP, HN);
+    }
+    const uint32_t b = (uint32_t)(C.boff - (j - i));
+    if (!((D0 >> b) & 1u)) { score -= 1; --i; --j; }            // diagonal delta 1: mismatch
+    else if ((VP >> b) & 1u) { score -= 2; --i; }               // vertical delta +1: insertion
     else { score -= 2; --j; }                                   // deletion
     --d;
 }
 
-ORC_HD void band_trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int dir,
+ORC_HD void band_trace_back(const BandCtx &C, const uint32_t *W, uint64_t lo, uint32_t len, int dir,
                             const uint32_t *code4, const uint32_t *rcode4, int m, int type, int ws,
                             const BandRing &R, int boff, int i, int j, int d, int &score_out, int &origin_out)
 {
@@ -1819,13 +1871,13 @@ ORC_HD void band_trace_back(const uint32_t *W, uint64_t lo, uint32_t len, int di
         const int run = imin(clz64(mis) >> 2, avail);
         score += run; i -= run; j -= run;
         if (run == avail) continue;
-        band_step(R, ws, boff, i, j, d, score);
+        band_step(C, R, lo, len, i, j, d, score);
     }
     score_out = score;
     origin_out = origin;
 }
 
-ORC_HD void band_trace_back_group(uint32_t mask, bool on, const uint32_t *W, uint64_t lo, uint32_t len, int dir,
+ORC_HD void band_trace_back_group(const BandCtx &C, uint32_t mask, bool on, const uint32_t *W, uint64_t lo, uint32_t len, int dir,
                                   const uint32_t *code4, const uint32_t *rcode4, int m, int type, int ws,
                                   const BandRing &R, int boff, int i, int j, int d, int &score_out, int &origin_out)
 {
@@ -1845,7 +1897,7 @@ ORC_HD void band_trace_back_group(uint32_t mask, bool on, const uint32_t *W, uin
                 if (dir) mis = brev64(mis);
                 const int run = imin(clz64(mis) >> 2, avail);
                 score += run; i -= run; j -= run;
-                if (run < avail) band_step(R, ws, boff, i, j, d, score);
+                if (run < avail) band_step(C, R, lo, len, i, j, d, score);
             }
         }
     }
@@ -1853,7 +1905,7 @@ ORC_HD void band_trace_back_group(uint32_t mask, bool on, const uint32_t *W, uin
     origin_out = origin;
 }
 
-// Columns ws+1..we of one scan into the band ring.
+// Columns ws+1..we of one scan; the state after every BAND_CKPT-th column goes to the ring.
 //
 // The recurrence itself runs on the band only (Hyyro's diagonal band): the 32-bit vectors hold rows
 // j - boff .. j - boff + 31 of column j, so from one column to the next every row moves down one bit
@@ -1862,14 +1914,12 @@ ORC_HD void band_trace_back_group(uint32_t mask, bool on, const uint32_t *W, uin
 // both only ever over-estimate costs outside the diagonals a path with <= k errors can use, so every cell
 // on such a path -- and both of its decision bits -- is exact, by the argument used for restarted scans.
 // Rows below row 1 stand for row 0 (cost 0 in every column): their match bits read as 1 and their deltas
-// stay 0, like the padding bits of the 64-bit table.  What comes out per column, VP and D0, is already
-// the ring entry.
+// stay 0, like the padding bits of the 64-bit table.
 //
 // The column loop is the same for every lane and every column (the lanes of a warp differ only in its
 // length).  Costs are not a popcount away here (row 0 is not in the band), and none is needed by the walks;
-// for the hull columns' D[m][j] every ring entry also carries the horizontal delta of row m in the two
-// bits no walk reads (bit 31 of both words: the band keeps a spare row on either side), and band_hull()
-// counts on from the scan's D[m][jf] (Task anchors) afterwards.
+// for the hull columns' D[m][j] the horizontal deltas of row m in those columns are collected in two words
+// (hull_p, hull_n: bit j - jf), and band_hull() counts on from the scan's D[m][jf] (Task anchors) afterwards.
 ORC_HD void band_columns(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, BandRing &R)
 {
     const int m = C.m, ws = C.ws, we = C.we, dir = C.dir, boff = C.boff;
@@ -1892,27 +1942,26 @@ ORC_HD void band_columns(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &
     // band position 0 of column ws + c is vector bit 63 - m - boff + ws + c; the table has 32 rows of ones in
     // front of the vector (hence + 32), clamped to [0, 95]: below, everything matches; above, nothing does
     const int sp0 = 63 - m - boff + ws + 32;
+    C.sp0 = sp0;
     // row m is band position boff - (j - m) of column j
     const int bm0 = boff + m - ws;
+    const int h0 = C.jf - ws;                                   // column c is hull column c - h0 (if C.jf <= C.jl)
+    uint32_t hull_p = 0, hull_n = 0;
+    {   BandEntry en; en.vp = VP; en.vn = VN; R.p[0] = en; }    // checkpoint 0: the scan's start state
     auto column = [&](uint32_t A, uint32_t B, int t, int c) {
         const uint32_t src = (t & 1) ? B : A;
         const uint32_t sel = (t >> 1) == 0 ? sel0 : (t >> 1) == 1 ? sel1 : (t >> 1) == 2 ? sel2 : sel3;
-        const int sp = imin(imax(sp0 + c, 0), 95);
-        const uint32_t *e = reinterpret_cast<const uint32_t *>(peq_base + 2u * byte_perm(src, lane8, sel)) + (sp >> 5);
-        const uint32_t Eq = funnel_r(e[0], e[1], (uint32_t)sp & 31u);
-        VP = (VP >> 1) | 0x80000000u;
-        VN >>= 1;
-        const uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
-        const uint32_t HP = VN | ~(D0 | VP);
-        const uint32_t HN = D0 & VP;
-        const uint32_t X = HP << 1;
-        VP = (HN << 1) | ~(D0 | X);
-        VN = D0 & X;
+        uint32_t D0, HP, HN;
+        band_advance(band_eq(peq_base, byte_perm(src, lane8, sel), sp0, c), VP, VN, D0, HP, HN);
         const uint32_t bm = (uint32_t)(bm0 - c) & 31u;          // meaningful on the hull columns only
-        BandEntry en;
-        en.pv = (VP & 0x7FFFFFFFu) | (((HP >> bm) & 1u) << 31);
-        en.d0 = (D0 & 0x7FFFFFFFu) | (((HN >> bm) & 1u) << 31);
-        R.p[c * R.stride] = en;
+        const uint32_t hq = (uint32_t)(c - h0);                 // 0..31 on the hull columns
+        hull_p |= shl32((HP >> bm) & 1u, hq);
+        hull_n |= shl32((HN >> bm) & 1u, hq);
+        if ((t & (BAND_CKPT - 1)) == BAND_CKPT - 1) {           // c = 8q + t + 1 is a multiple of BAND_CKPT
+            BandEntry en;
+            en.vp = VP; en.vn = VN;
+            R.p[(c >> BAND_CKPT_LOG) * R.stride] = en;
+        }
     };
     for (int q = 0; q < nchunks; q++) {
         uint32_t A, B;
@@ -1927,6 +1976,7 @@ ORC_HD void band_columns(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &
         }
     }
     C.vpn = VP; C.vnn = VN;             // column we (column n when the scan reached it)
+    C.hull_p = hull_p; C.hull_n = hull_n;
 }
 
 // R5 over the hull columns jf..jl of the scan just stored, exactly as resolve_columns does it while it
@@ -1946,10 +1996,7 @@ ORC_HD void band_hull(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, 
     const bool narrow = C.narrow != 0;
     int D = C.c5;
     for (int j = jf; j <= jl; j++) {
-        if (j > jf) {
-            const BandEntry e = R.p[(j - ws) * R.stride];
-            D += (int)(e.pv >> 31) - (int)(e.d0 >> 31);
-        }
+        if (j > jf) D += (int)((C.hull_p >> (j - jf)) & 1u) - (int)((C.hull_n >> (j - jf)) & 1u);
         if (D > k) continue;
         const int lmax = imin(m, j + D);
         if (!(lmax >= C.min_ov && D <= (int)C.kmax[lmax])) continue;
@@ -1967,7 +2014,7 @@ ORC_HD void band_hull(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C, 
             // first needs a strictly higher score)
             Cell c;
             c.cost = D;
-            band_trace_back(W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, boff, m, j, D, c.score, c.origin);
+            band_trace_back(C, W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, boff, m, j, D, c.score, c.origin);
             C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin;
             if (r5_update(C.best, m, n, c, j, C.min_ov, C.kmax)) { C.broke = 1; return; }
         }
@@ -1999,7 +2046,7 @@ ORC_HD void band_finish(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C
             }
             Cell c;
             c.cost = Dj; c.score = 0; c.origin = 0;
-            band_trace_back_group(mask, have, W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, C.boff, m, j, Dj,
+            band_trace_back_group(C, mask, have, W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, C.boff, m, j, Dj,
                                   c.score, c.origin);
             if (have) {
                 if (j == n) { C.traced_j = j; C.traced_score = c.score; C.traced_origin = c.origin; }
@@ -2040,7 +2087,7 @@ ORC_HD void band_finish(const uint32_t *W, uint64_t lo, uint32_t len, BandCtx &C
             Cell c;
             c.cost = Di;
             if (i == m && C.traced_j == n) { c.score = C.traced_score; c.origin = C.traced_origin; }
-            else band_trace_back(W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, C.boff, i, n, Di, c.score, c.origin);
+            else band_trace_back(C, W, lo, len, dir, C.code4, C.rcode4, m, C.type, ws, R, C.boff, i, n, Di, c.score, c.origin);
             r6_update(best, n, c, i, C.min_ov, C.kmax);
         }
     }
@@ -2063,7 +2110,7 @@ ORC_HD void band_begin(const uint32_t *W, const View &v, int type, int n_adapter
     resolve_geometry(type, m, C.k, n, t, C.G);
     C.broke = 0; C.narrow = 0; C.top_j = -1; C.ubw = 2; C.boff = 0;
     C.traced_j = -1; C.traced_score = 0; C.traced_origin = 0;
-    C.hc0 = C.hc1 = ~0ull; C.vpn = C.vnn = 0;
+    C.hc0 = C.hc1 = ~0ull; C.vpn = C.vnn = 0; C.hull_p = C.hull_n = 0; C.sp0 = 0;
     C.c5 = (int)((uint32_t)t.pad_ >> 8) & 63; C.c6 = (int)((uint32_t)t.pad_ >> 16) & 63;
     C.ws = C.G.ws; C.we = C.G.we; C.jf = C.G.jf; C.jl = C.G.jl; C.r6 = C.G.r6;
     if (C.G.has5 || C.G.has6) {

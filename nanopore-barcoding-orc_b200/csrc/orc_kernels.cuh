@@ -14,8 +14,9 @@
 //   scan_kernel        stage 2b, one lane per surviving pair: the 64-bit Myers/Hyyro semi-global scan
 //                      (orc_core.cuh scan_lane), table in shared memory; pairs whose candidates all cost 0
 //                      are settled here, the others become resolver tasks.
-//   resolve_band_kernel  one thread per task: the diagonals around the candidates, 8-byte column entries
-//                      in shared memory (orc_core.cuh band_*); cutadapt's score/origin by walking back.
+//   resolve_band_kernel  one thread per task: the diagonals around the candidates, scan checkpoints (8 bytes
+//                      every 2nd column) in shared memory (orc_core.cuh band_*); cutadapt's score/origin
+//                      by walking back, the column a walk asks about re-run from its checkpoint.
 //   resolve_kernel     the same for the few tasks whose candidates spread over too many diagonals
 //                      (128-bit column ring in local memory), on a side stream next to the band resolver.
 //   anchored_kernel    anchored --no-indels rounds instead of all of the above.
@@ -544,21 +545,28 @@ resolve_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------
-// The band resolver (orc_core.cuh band_*): one thread per task, its column ring (8 bytes per column) in
-// shared memory, entry c of thread t at ring[c * BAND_THREADS + t]: the lanes of a warp scan in lockstep
-// and store one contiguous 256-byte row per column, and a 64-bit access of any 16 lanes to any rows hits
-// 16 different bank pairs, so the walks read without conflicts as well.  Only the banks of the 64-bit match
+// The band resolver (orc_core.cuh band_*): one thread per task, its ring of scan checkpoints (8 bytes after
+// every BAND_CKPT-th column) in shared memory, entry q of thread t at ring[q * BAND_THREADS + t]: the lanes of
+// a warp scan in lockstep and store one contiguous 256-byte row per checkpoint, and a 64-bit access of any 16
+// lanes to any rows hits 16 different bank pairs, so the walks read without conflicts as well.  Only the banks of the 64-bit match
 // table that the round uses are staged next to the ring; the acceptance limits and the packed adapter
 // codes, touched a few times per task, are read through L1 from the table in global memory.
-constexpr int BAND_THREADS = 64;
+#ifndef ORC_BAND_THREADS
+#define ORC_BAND_THREADS 256
+#endif
+constexpr int BAND_THREADS = ORC_BAND_THREADS;
 inline size_t band_smem_bytes(int n_lanes, int n_adapters)
 {
     return (size_t)((n_lanes + 31) / 32) * BAND_BANK_BYTES + (size_t)n_adapters * sizeof(BandAdapter) +
-           (size_t)BAND_COLS * BAND_THREADS * sizeof(BandEntry) + (size_t)BAND_CODE_WORDS * BAND_THREADS * sizeof(uint32_t);
+           (size_t)BAND_ENTRIES * BAND_THREADS * sizeof(BandEntry) + (size_t)BAND_CODE_WORDS * BAND_THREADS * sizeof(uint32_t);
 }
 static_assert(sizeof(BandAdapter) % 8 == 0, "the ring behind the adapter table must stay 8-byte aligned");
 
+#ifdef ORC_BAND_MINBLOCKS
+__global__ void __launch_bounds__(BAND_THREADS, ORC_BAND_MINBLOCKS)
+#else
 __global__ void __launch_bounds__(BAND_THREADS)
+#endif
 resolve_band_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W,
                     const View *__restrict__ views, const Task *__restrict__ work,
                     const uint32_t *__restrict__ work_count, PairResult *__restrict__ results,
@@ -577,7 +585,7 @@ resolve_band_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restri
     BandRing ring;
     ring.p = reinterpret_cast<BandEntry *>(s_ads + na) + threadIdx.x;
     ring.stride = BAND_THREADS;
-    ring.cw = reinterpret_cast<uint32_t *>(reinterpret_cast<BandEntry *>(s_ads + na) + BAND_COLS * BAND_THREADS) + threadIdx.x;
+    ring.cw = reinterpret_cast<uint32_t *>(reinterpret_cast<BandEntry *>(s_ads + na) + BAND_ENTRIES * BAND_THREADS) + threadIdx.x;
     ring.w0 = 0;
     const uint32_t n = min(*work_count, cap_pairs);
     const uint32_t lane = threadIdx.x & 31u;

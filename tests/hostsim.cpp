@@ -74,7 +74,7 @@ extern "C" int hostsim_demux(int n_rounds,
     for (uint64_t i = 0; i < n_bytes; i++) W[i >> 3] |= (uint32_t)lut[seq[i]] << ((i & 7) * 4);
 
     ColRing *ring = new ColRing;
-    BandEntry *band = new BandEntry[BAND_COLS];
+    BandEntry *band = new BandEntry[BAND_ENTRIES];
     uint32_t band_codes[BAND_CODE_WORDS];
     BandRing bring; bring.p = band; bring.stride = 1; bring.cw = band_codes; bring.w0 = 0;
     const bool force_wide = (filter_mode_in & 8) != 0;
