@@ -83,6 +83,9 @@ def parse_args():
                          "(24 M13 variable indices) on reads with the bare index at offset 0, 5 = distinct shards "
                          "made on the GPU (the default under torchrun)")
     ap.add_argument("--sub-batches", type=int, default=8)
+    ap.add_argument("--qual-copy", action="store_true",
+                    help="e2e leg: copy the quality strings to the device whole instead of letting the emit kernel "
+                         "read what it needs of them from the pinned host buffer (orc_params.qual_zero_copy)")
     ap.add_argument("--resident", type=int, default=2,
                     help="batches resident in HBM whose steps are in flight together on their own streams (device-resident leg)")
     ap.add_argument("--oracle-sample", type=int, default=32768, help="reads of one shard per rank checked against the oracle (config 5)")
@@ -293,22 +296,28 @@ def split_subbatches(E, synth, rs, n_sub):
     return subs, per
 
 
-def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches, S=4):
+def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches, S=4, zero_copy=True):
     """`steps` steps through orc_submit/orc_wait with host buffers; step k streams the sub-batches of
     step_batches[k % len(step_batches)] over S slots.  -> (seconds, h2d bytes per step, d2h bytes per step,
-    reads, cumulative counts)."""
+    reads, cumulative counts, bytes of h2d that the emit kernel read in place).
+
+    zero_copy: orc_params.qual_zero_copy -- the quality strings are not copied to the device; the emit kernel
+    reads the trimmed qualities of the reads whose bin is kept straight from the pinned host buffer.  Those
+    bytes cross PCIe all the same and are counted in h2d (from the results of the untimed warm-up step)."""
     per = max(x.n_reads for sb in step_batches for x in sb)
     eng = E.Engine(rounds, device=device, max_reads=per,
                    max_bytes=max(int(x.seq.shape[0]) for sb in step_batches for x in sb) + 64,
                    max_name_bytes=max(int(x.names.shape[0]) for sb in step_batches for x in sb) + 64, n_slots=S,
-                   emit_fastq=True, want_matches=want_matches, drop_bins=drop)
-    h2d = sum(int(x.seq.nbytes + x.qual.nbytes + x.offsets.nbytes + x.lengths.nbytes + x.names.nbytes +
-                  x.name_offsets.nbytes) for x in step_batches[0])
-    state = {"inflight": [], "k": 0, "reads": 0, "d2h": 0}
+                   emit_fastq=True, want_matches=want_matches, drop_bins=drop, qual_zero_copy=zero_copy)
+    h2d = sum(int(x.seq.nbytes + (0 if zero_copy else x.qual.nbytes) + x.offsets.nbytes + x.lengths.nbytes +
+                  x.names.nbytes + x.name_offsets.nbytes) for x in step_batches[0])
+    state = {"inflight": [], "k": 0, "reads": 0, "d2h": 0, "in_place": 0, "warm": True}
 
     def take(slot):
         r = eng.wait(slot, copy=False)
         state["reads"] += r.n_reads
+        if state["warm"] and zero_copy:         # quality bytes the emit kernel fetched from host memory
+            state["in_place"] += int(r.out_len[r.bin >= 0].sum())
         state["d2h"] += int(r.fastq.nbytes + r.bin.nbytes + r.out_len.nbytes + r.bin_counts.nbytes +
                             r.bin_offsets.nbytes + sum(m.nbytes for m in r.matches))
 
@@ -327,7 +336,7 @@ def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches,
     for sub in step_batches[0]:                 # warm the copy paths: one untimed step
         pump(sub)
     drain()
-    state.update(reads=0, d2h=0)
+    state.update(reads=0, d2h=0, warm=False)
     barrier()
     w0 = time.perf_counter()
     for k in range(steps):
@@ -338,7 +347,7 @@ def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches,
     secs = time.perf_counter() - w0
     counts = eng.counts().astype(np.int64)
     eng.close()
-    return secs, h2d, state["d2h"] // max(steps, 1), state["reads"], counts
+    return secs, h2d + state["in_place"], state["d2h"] // max(steps, 1), state["reads"], counts, state["in_place"]
 
 
 def measure_link(torch, barrier, n_bytes=1 << 29):
@@ -627,8 +636,9 @@ def main():
         if not args.no_e2e:
             step_batches = [split_subbatches(E, synth, hb, max(1, args.sub_batches))[0] for hb in host_batches]
             e_steps = steps if full else max(2, min(steps, 5))
-            secs, h2d, d2h, n_done, counts = run_e2e(E, rounds, local_rank, step_batches, e_steps, barrier, drop,
-                                                     want_matches=False)
+            zc = not args.qual_copy
+            secs, h2d, d2h, n_done, counts, in_place = run_e2e(E, rounds, local_rank, step_batches, e_steps, barrier, drop,
+                                                               want_matches=False, zero_copy=zc)
             te = torch.tensor([secs], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -639,7 +649,12 @@ def main():
                           "note": "each step streamed as %d sub-batches over 4 slots/streams (copies overlap kernels); "
                                   "pipeline fill and drain are inside the timed region; output = the FASTQ text of the "
                                   "bins the reference script keeps (02:107-119: no unknown, no SP27_009..012) + bin id "
-                                  "and trimmed length per read; match records off" % len(step_batches[0])}
+                                  "and trimmed length per read; match records off" % len(step_batches[0]) +
+                                  ("; the quality strings are NOT copied to the device: the emit kernel reads the trimmed "
+                                   "qualities of the kept reads in place from the pinned host buffer (orc_params."
+                                   "qual_zero_copy), %d of the h2d bytes per step" % in_place if zc else
+                                   "; quality strings copied to the device whole (--qual-copy)"),
+                          "h2d_in_place_bytes_per_step": in_place}
             out["counts"] = counts
         else:
             out["e2e"] = None

@@ -76,6 +76,12 @@ typedef struct orc_params {
     int32_t emit_fastq;             /* build bin-major FASTQ text on the device */
     int32_t want_matches;           /* return the per-read match records */
     const uint8_t *drop_bins;       /* optional [n_bins]: 1 = do not emit that bin (02:110-118) */
+    int32_t qual_zero_copy;         /* 1 = with emit_fastq and the separate-blob layout, the qualities are NOT copied to
+                                       the device: emit_kernel reads the bytes it needs (the trimmed qualities of the reads
+                                       whose bin is kept) straight from the caller's buffer over PCIe.  The buffer must be
+                                       page-locked (orc_host_alloc, cudaHostAlloc/cudaHostRegister, torch pin_memory) and
+                                       its allocation must extend 64 bytes beyond qual + n_bytes (16-byte loads over-read);
+                                       a batch whose qual buffer is not page-locked is copied as before */
 } orc_params;
 
 /*
@@ -154,6 +160,10 @@ typedef struct orc_timings {
     uint64_t cells_2b[ORC_MAX_ROUNDS];       /* DP cells of stage 2b: m x window columns of the pairs that passed 2a */
     uint32_t n_pairs_2b[ORC_MAX_ROUNDS];     /* pairs that passed stage 2a */
     uint32_t n_tasks_wide[ORC_MAX_ROUNDS];   /* resolver tasks the band resolver could not take */
+    /* when things happened on the device, milliseconds since orc_create(): H2D copies start, kernels start,
+     * emit_kernel starts, emit_kernel ends, D2H copies end (0 where that part did not run) -- the timeline of a
+     * pipelined orc_submit()/orc_wait() loop over several slots */
+    float timeline_ms[5];
 } orc_timings;
 
 orc_ctx *orc_create(const orc_params *params, char *err, size_t err_len);
@@ -299,6 +309,10 @@ void orc_host_free(void *p);
  * second (the DP kernel's roofline denominator).  mode 0: LOP3 only (the ALU
  * pipe the Myers recurrence lives on); mode 1: LOP3 + IMAD mix (ALU and FMA pipes together) */
 double orc_measure_int32_peak(int device, int mode, double *sm_clock_mhz);
+/* GB/s of kernel loads from PINNED host memory: every warp reads `chunk` of every `stride` bytes (multiples of
+ * 16) of host[0 .. bytes) with 16-byte loads per lane, like emit_kernel's record copies (the ceiling of
+ * orc_params.qual_zero_copy).  -2 if the buffer is not pinned, -1 on other failures. */
+double orc_probe_hostread(int device, const void *host, uint64_t bytes, uint32_t chunk, uint64_t stride);
 
 const char *orc_version(void);
 

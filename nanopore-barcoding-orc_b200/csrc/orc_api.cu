@@ -54,7 +54,8 @@ struct Slot {
     bool did_h2d = false, did_kernels = false, did_d2h = false, fresh_upload = false;
     // device
     uint8_t *d_seq = nullptr, *d_qual = nullptr, *d_names = nullptr, *d_fastq = nullptr;
-    uint8_t *u_qual = nullptr, *u_names = nullptr;      // what the kernels use (may alias d_seq)
+    uint8_t *u_qual = nullptr, *u_names = nullptr;      // what the kernels use (may alias d_seq, or the caller's pinned buffer)
+    bool qual_in_place = false;                         // u_qual is the caller's page-locked buffer (orc_params.qual_zero_copy)
     uint64_t *d_qual_offsets = nullptr, *u_qual_offsets = nullptr;
     uint32_t *d_name_lengths = nullptr, *u_name_lengths = nullptr;
     uint32_t *d_codes_alloc = nullptr;
@@ -95,7 +96,8 @@ struct Slot {
 struct orc_ctx {
     int device = 0;
     int n_rounds = 1, n_slots = 1, n_bins = 1, sm_count = 148;
-    int emit_fastq = 1, want_matches = 1;
+    int emit_fastq = 1, want_matches = 1, qual_zero_copy = 0;
+    int emit_zc_blocks = 8;                  // emit_kernel blocks per SM when it reads the qualities from host memory (measured: 8 > 4 > 2 > 1)
     uint32_t max_reads = 0;
     uint64_t max_bytes = 0, max_name_bytes = 0, fastq_cap = 0;
     RoundTable h_tab[2];
@@ -107,6 +109,7 @@ struct orc_ctx {
     bool anchored[2] = {false, false};
     uint8_t *d_pack_lut = nullptr, *d_comp_lut = nullptr, *d_drop = nullptr;
     cudaEvent_t ev_span[2] = {nullptr, nullptr};   // orc_span_begin / orc_span_end
+    cudaEvent_t ev_ref = nullptr;                  // recorded in orc_create: origin of orc_timings.timeline_ms
     std::vector<cudaEvent_t> ev_span_slot;
     SynthTable *d_synth = nullptr;   // orc_synth(): built on first use
     uint64_t *d_synth_totals = nullptr;
@@ -263,6 +266,8 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     ctx->n_slots = p->n_slots < 1 ? 1 : p->n_slots;
     ctx->emit_fastq = p->emit_fastq ? 1 : 0;
     ctx->want_matches = p->want_matches ? 1 : 0;
+    ctx->qual_zero_copy = p->qual_zero_copy ? 1 : 0;
+    if (const char *e = getenv("ORC_EMIT_ZC_BLOCKS")) ctx->emit_zc_blocks = std::min(8, std::max(1, atoi(e)));
     ctx->max_reads = p->max_reads;
     ctx->max_bytes = (p->max_bytes + 63) & ~63ull;
     ctx->max_name_bytes = p->max_name_bytes ? p->max_name_bytes : 64;
@@ -347,6 +352,9 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         int rc = alloc_slot(ctx, s);
         if (rc != ORC_OK) return rc;
     }
+    CK(cudaEventCreate(&ctx->ev_ref));
+    CK(cudaEventRecord(ctx->ev_ref, ctx->slots[0].stream));
+    CK(cudaEventSynchronize(ctx->ev_ref));
     return ORC_OK;
 }
 
@@ -377,6 +385,7 @@ extern "C" void orc_destroy(orc_ctx *ctx)
     cudaFree(ctx->d_pack_lut); cudaFree(ctx->d_comp_lut); cudaFree(ctx->d_drop);
     cudaFree(ctx->d_synth); cudaFree(ctx->d_synth_totals);
     for (int i = 0; i < 2; i++) if (ctx->ev_span[i]) cudaEventDestroy(ctx->ev_span[i]);
+    if (ctx->ev_ref) cudaEventDestroy(ctx->ev_ref);
     for (cudaEvent_t e : ctx->ev_span_slot) if (e) cudaEventDestroy(e);
     delete ctx;
 }
@@ -449,8 +458,20 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
     s.u_qual = s.d_qual; s.u_names = s.d_names; s.u_qual_offsets = nullptr; s.u_name_lengths = nullptr;
     if (b->n_reads) {
         CK(cudaMemcpyAsync(s.d_seq, b->seq, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
+        s.qual_in_place = false;
         if (b->qual == b->seq) s.u_qual = s.d_seq;       // raw FASTQ text: one blob, uploaded once
-        else CK(cudaMemcpyAsync(s.d_qual, b->qual, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
+        else {
+            if (ctx->qual_zero_copy && s.has_names) {
+                // page-locked memory is mapped into the device's address space (UVA): emit_kernel reads it in place
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, b->qual) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+                    s.u_qual = static_cast<uint8_t *>(at.devicePointer);
+                    s.qual_in_place = true;
+                } else cudaGetLastError();
+            }
+            if (!s.qual_in_place)
+                CK(cudaMemcpyAsync(s.d_qual, b->qual, b->n_bytes, cudaMemcpyHostToDevice, s.stream));
+        }
         CK(cudaMemcpyAsync(s.d_offsets, b->offsets, sizeof(uint64_t) * b->n_reads, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.d_lengths, b->lengths, sizeof(uint32_t) * b->n_reads, cudaMemcpyHostToDevice, s.stream));
         if (b->qual_offsets) {
@@ -740,7 +761,10 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     }
     CK(cudaEventRecord(s.ev[EV_BIN], st));
     if (n && s.has_names) {
-        emit_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(s.d_seq, s.u_qual, s.u_names, s.d_name_offsets,
+        // (qualities read in place from host memory: the kernel then runs at PCIe speed; smaller grids that
+        // would leave thread slots to the other slots' kernels measured slower, ORC_EMIT_ZC_BLOCKS)
+        const int emit_blocks = ctx->sm_count * (s.qual_in_place ? ctx->emit_zc_blocks : 8);
+        emit_kernel<<<emit_blocks, 256, 0, st>>>(s.d_seq, s.u_qual, s.u_names, s.d_name_offsets,
                                                        s.u_name_lengths, s.d_offsets, s.u_qual_offsets,
                                                        s.d_views[ctx->n_rounds], s.d_dest, n, ctx->d_comp_lut,
                                                        s.d_fastq); nl++;
@@ -882,6 +906,14 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     CK(el(EV_H2D, EV_EMIT, &t->total_ms));
     if (s.did_h2d) CK(el(EV_START, EV_H2D, &t->h2d_ms));
     if (s.did_d2h) CK(el(EV_EMIT, EV_END, &t->d2h_ms));
+    {
+        auto at = [&](int e, float *dst) -> cudaError_t { return cudaEventElapsedTime(dst, ctx->ev_ref, s.ev[e]); };
+        if (s.did_h2d) CK(at(EV_START, &t->timeline_ms[0]));
+        CK(at(EV_H2D, &t->timeline_ms[1]));
+        CK(at(EV_BIN, &t->timeline_ms[2]));
+        CK(at(EV_EMIT, &t->timeline_ms[3]));
+        if (s.did_d2h) CK(at(EV_END, &t->timeline_ms[4]));
+    }
     // counters need a device read when the caller never downloaded
     uint32_t counters[16];
     unsigned long long cells[6];
@@ -1065,6 +1097,66 @@ extern "C" int orc_span_end(orc_ctx *ctx, float *ms)
     CK(cudaEventSynchronize(ctx->ev_span[1]));
     CK(cudaEventElapsedTime(ms, ctx->ev_span[0], ctx->ev_span[1]));
     return ORC_OK;
+}
+
+// Bandwidth of kernel loads from pinned HOST memory (what emit_kernel does with the qualities when
+// orc_params.qual_zero_copy is set): every warp reads `chunk` bytes out of every `stride` bytes with 16-byte
+// loads per lane, like the record copies of emit_kernel.  Returns GB/s of the bytes asked for, < 0 on failure.
+__global__ void __launch_bounds__(256) hostread_probe_kernel(const uint8_t *__restrict__ src, uint64_t n_chunks,
+                                                             uint32_t chunk, uint64_t stride, uint32_t *out, int dup)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t acc = 0;
+    for (uint64_t c = warp; c < n_chunks; c += n_warps) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(src + c * stride);
+        for (uint32_t q = lane; q < chunk / 16u; q += 32u) {
+            const uint4 v = p[q];
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+            if (dup) {                          // every unit also by the neighbouring lane, as a realigning copy does
+                const uint4 w = p[q + 1];
+                acc ^= w.x + w.y + w.z + w.w;
+            }
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;       // keeps the loads alive
+}
+
+extern "C" double orc_probe_hostread(int device, const void *host, uint64_t bytes, uint32_t chunk, uint64_t stride)
+{
+    const int dup = getenv("ORC_PROBE_DUP") ? 1 : 0;
+    if (!host || chunk < 16 || (chunk & 15u) || stride < chunk || (stride & 15u) || bytes < stride) return -1.0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError();
+        return -2.0;                            // not pinned / not mapped
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return -1.0;
+    const uint64_t n_chunks = bytes / stride;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(a);
+        hostread_probe_kernel<<<prop.multiProcessorCount * 8, 256>>>(static_cast<const uint8_t *>(at.devicePointer), n_chunks,
+                                                                    chunk, stride, d, dup);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { best = -1.f; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    if (best <= 0) return -1.0;
+    return (double)n_chunks * chunk / (best * 1e-3) / 1e9;
 }
 
 extern "C" double orc_measure_int32_peak(int device, int mode, double *sm_clock_mhz)

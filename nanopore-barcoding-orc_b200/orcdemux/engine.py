@@ -64,10 +64,11 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
     """A numpy array over page-locked memory (torch owns the allocation)."""
     import torch
     dt = np.dtype(dtype)
-    t = torch.empty(max(int(n), 1) * dt.itemsize, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    # 64 bytes of slack behind the data: the kernels' 16-byte loads may over-read a buffer they read in place
+    t = torch.empty(max(int(n), 1) * dt.itemsize + 64, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
     # the ndarray's base chain ends in the tensor, so the page-locked block lives exactly as long as
     # the array (or any view of it) does
-    return t.numpy().view(dt)[:n]
+    return t.numpy()[:max(int(n), 1) * dt.itemsize].view(dt)[:n]
 
 
 def pin_readset(rs):
@@ -89,7 +90,10 @@ class Engine:
     def __init__(self, rounds: Sequence[Round], device: int = 0, max_reads: int = 1 << 20,
                  max_bytes: int = 1 << 30, max_name_bytes: int = 0, n_slots: int = 2,
                  emit_fastq: bool = True, want_matches: bool = True,
-                 drop_bins: Optional[np.ndarray] = None):
+                 drop_bins: Optional[np.ndarray] = None, qual_zero_copy: bool = False):
+        """qual_zero_copy: the qualities of a submitted batch stay in the caller's page-locked buffer and the
+        emit kernel reads what it needs of them over PCIe (orc_params.qual_zero_copy; buffers from
+        pinned_empty() / pin_readset() qualify: page-locked, 64 bytes of slack behind the data)."""
         if not 1 <= len(rounds) <= _lib.ORC_MAX_ROUNDS:
             raise ValueError("1 or 2 rounds")
         self._L = _lib.load()
@@ -125,6 +129,7 @@ class Engine:
         p.n_slots = n_slots
         p.emit_fastq = int(emit_fastq)
         p.want_matches = int(want_matches)
+        p.qual_zero_copy = int(qual_zero_copy)
         if drop_bins is not None:
             d = np.ascontiguousarray(drop_bins, dtype=np.uint8)
             if d.shape[0] != self.n_bins:
@@ -259,7 +264,7 @@ class Engine:
                     kernel_ms=[{nm: float(t.kernel_ms[r][i]) for i, nm in enumerate(_lib.KERNEL_NAMES)}
                                for r in range(len(self.rounds))],
                     window_columns=list(t.window_columns), cells_2b=list(t.cells_2b),
-                    n_pairs_2b=list(t.n_pairs_2b), n_tasks_wide=list(t.n_tasks_wide))
+                    n_pairs_2b=list(t.n_pairs_2b), n_tasks_wide=list(t.n_tasks_wide), timeline_ms=list(t.timeline_ms))
 
     def timer_start(self, slot: int = 0):
         self._check(self._L.orc_timer_start(self._ctx, slot), "orc_timer_start")

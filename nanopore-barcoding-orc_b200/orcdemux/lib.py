@@ -30,7 +30,7 @@ EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_sub
            "orc_reader_open", "orc_reader_next", "orc_reader_release", "orc_reader_error", "orc_reader_close",
            "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close",
            "orc_edit_distances", "orc_synth", "orc_resident", "orc_export",
-           "orc_reader_open_threads", "orc_writer_set_index", "orc_empty_gzip_member", "orc_span_begin", "orc_span_end"]
+           "orc_reader_open_threads", "orc_writer_set_index", "orc_empty_gzip_member", "orc_span_begin", "orc_span_end", "orc_probe_hostread"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -50,7 +50,7 @@ class Params(C.Structure):
                 ("rounds", RoundParams * ORC_MAX_ROUNDS),
                 ("max_reads", C.c_uint32), ("max_bytes", C.c_uint64), ("max_name_bytes", C.c_uint64),
                 ("n_slots", C.c_int32), ("emit_fastq", C.c_int32), ("want_matches", C.c_int32),
-                ("drop_bins", C.c_void_p)]
+                ("drop_bins", C.c_void_p), ("qual_zero_copy", C.c_int32)]
 
 
 class Batch(C.Structure):
@@ -77,7 +77,8 @@ class Timings(C.Structure):
                 ("cells", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_executed", C.c_uint64 * ORC_MAX_ROUNDS), ("pack_bytes", C.c_uint64), ("emit_bytes", C.c_uint64),
                 ("kernel_ms", (C.c_float * ORC_N_KERNELS) * ORC_MAX_ROUNDS),
                 ("window_columns", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_2b", C.c_uint64 * ORC_MAX_ROUNDS),
-                ("n_pairs_2b", C.c_uint32 * ORC_MAX_ROUNDS), ("n_tasks_wide", C.c_uint32 * ORC_MAX_ROUNDS)]
+                ("n_pairs_2b", C.c_uint32 * ORC_MAX_ROUNDS), ("n_tasks_wide", C.c_uint32 * ORC_MAX_ROUNDS),
+                ("timeline_ms", C.c_float * 5)]
 
 
 class TextBatchC(C.Structure):
@@ -136,6 +137,8 @@ def load():
     L.orc_span_end.restype = C.c_int
     L.orc_measure_int32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.orc_measure_int32_peak.restype = C.c_double
+    L.orc_probe_hostread.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64]
+    L.orc_probe_hostread.restype = C.c_double
     L.orc_reader_open.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.orc_reader_open.restype = C.c_void_p
     L.orc_reader_open_threads.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]

@@ -140,6 +140,54 @@ def test_slots_and_resident_relaunch():
     _check(b)
 
 
+def test_qualities_read_in_place_from_pinned_host_memory():
+    """orc_params.qual_zero_copy: the quality strings are not copied to the device, emit_kernel reads them in
+    place from the caller's page-locked buffer.  Same bytes as the copying path and as the oracle -- for a
+    whole pinned batch, for sub-batches that are views into one pinned buffer (arbitrary alignment of the
+    quality pointer, the last one ending where the buffer's slack begins), with dropped bins, and for a
+    pageable buffer (copied as before)."""
+    rs = synth.generate(6000, 300, 900, seed=31)
+    ref = _check(rs)                                            # copying path, checked against the oracle
+    pinned = E.pin_readset(rs)
+    drop = np.zeros(169, dtype=np.uint8)
+    drop[0::13] = 1                                             # no SP5 match
+    drop[:13] = 1                                               # no SP27 match
+    for zc_rs in (pinned, rs):                                  # page-locked: in place; pageable: falls back to the copy
+        eng = _engine(rs.n_reads, rs.seq.shape[0], qual_zero_copy=True)
+        try:
+            res = eng.run(zc_rs)
+            assert res.fastq.tobytes() == ref.fastq.tobytes()
+            assert np.array_equal(res.bin, ref.bin) and np.array_equal(res.out_len, ref.out_len)
+        finally:
+            eng.close()
+    # sub-batches as views of the pinned blobs, two in flight, with dropped bins
+    n_sub = 5
+    per = (rs.n_reads + n_sub - 1) // n_sub
+    engs = [_engine(per, rs.seq.shape[0], n_slots=2, drop_bins=drop, qual_zero_copy=z) for z in (False, True)]
+    try:
+        outs = [[], []]
+        for i in range(n_sub):
+            lo, hi = i * per, min(rs.n_reads, (i + 1) * per)
+            b0 = int(pinned.offsets[lo])
+            b1 = int(pinned.offsets[hi - 1]) + int(pinned.lengths[hi - 1])
+            n0, n1 = int(pinned.name_offsets[lo]), int(pinned.name_offsets[hi])
+            off = E.pinned_empty(hi - lo, np.uint64)
+            off[...] = pinned.offsets[lo:hi] - np.uint64(b0)
+            noff = E.pinned_empty(hi - lo + 1, np.uint64)
+            noff[...] = pinned.name_offsets[lo:hi + 1] - np.uint64(n0)
+            sub = synth.ReadSet(pinned.seq[b0:b1], pinned.qual[b0:b1], off, pinned.lengths[lo:hi], pinned.names[n0:n1], noff, {})
+            for k, eng in enumerate(engs):
+                eng.submit(i % 2, sub)
+                r = eng.wait(i % 2)
+                outs[k].append((r.fastq.tobytes(), r.bin.copy(), r.bin_offsets.copy()))
+        for a, b in zip(*outs):
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert any((a[1] < 0).any() for a in outs[1]) and any(len(a[0]) for a in outs[1])
+    finally:
+        for eng in engs:
+            eng.close()
+
+
 def test_config2_full_size_every_read():
     """BASELINE configs[1] at its full size (1 Mi COI reads, seed 1002): the oracle on EVERY read -- all eight
     match fields of both rounds, trimmed length, bin, and the bytes of all 169 bins -- plus the

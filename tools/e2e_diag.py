@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Per-sub-batch device times inside the pipelined e2e leg (orc_submit / orc_wait over S slots), with the
+qualities copied or read in place: where does a step's time go?"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "nanopore-barcoding-orc_b200")]
+import numpy as np
+import bench
+from orcdemux import engine as E, synth
+
+COMBOS = [tuple(int(v) for v in c.split("x")) for c in os.environ.get("COMBOS", "4x8").split(",")]
+STEPS = 6
+rs = E.pin_readset(synth.generate(1 << 20, 300, 900, seed=1002, workers=16))
+drop = bench.scripts_final_tree_drop()
+for S, NSUB, zc in [(s_, n_, z) for s_, n_ in COMBOS for z in ((False, True) if os.environ.get('BOTH') else (True,))]:
+    subs, per = bench.split_subbatches(E, synth, rs, NSUB)
+    eng = E.Engine(E.m13_rounds(), device=0, max_reads=per, max_bytes=max(int(x.seq.shape[0]) for x in subs) + 64,
+                   max_name_bytes=max(int(x.names.shape[0]) for x in subs) + 64, n_slots=S, emit_fastq=True,
+                   want_matches=False, drop_bins=drop, qual_zero_copy=zc)
+    acc = {"h2d_ms": [], "total_ms": [], "emit_ms": [], "d2h_ms": [], "host_submit_ms": [], "host_wait_ms": []}
+    tl = []
+    infl = []
+    def take(slot):
+        t0 = time.perf_counter(); eng.wait(slot, copy=False); acc["host_wait_ms"].append(1e3 * (time.perf_counter() - t0))
+        # (no eng.timings() here: its synchronous cudaMemcpy of the counters queues behind the pending copies
+        # of the other slots and stalls this thread -- the timeline below is read once, after the loop)
+    k = 0
+    for rep in range(STEPS + 1):
+        if rep == 1:
+            while infl: take(infl.pop(0))
+            for v in acc.values(): v.clear()
+            import torch; torch.cuda.synchronize(); w0 = time.perf_counter()
+        for sub in subs:
+            if len(infl) == S: take(infl.pop(0))
+            t0 = time.perf_counter(); eng.submit(k % S, sub); acc["host_submit_ms"].append(1e3 * (time.perf_counter() - t0))
+            infl.append(k % S); k += 1
+    while infl: take(infl.pop(0))
+    secs = time.perf_counter() - w0
+    print("S=%d NSUB=%d " % (S, NSUB) + "zero_copy=%s  %.2f ms/step  %.1f M reads/s  per sub-batch (mean ms): %s" % (
+        zc, 1e3 * secs / STEPS, STEPS * rs.n_reads / secs / 1e6,
+        "  ".join("%s %.3f" % (n, float(np.mean(v))) for n, v in acc.items())))
+    for slot in range(S):
+        t = eng.timings(slot)
+        for k_ in ("h2d_ms", "total_ms", "emit_ms", "d2h_ms"): acc[k_].append(t[k_])
+        tl.append((slot, t["timeline_ms"]))
+    tl.sort(key=lambda e: e[1][0])
+    if os.environ.get('TIMELINE'):
+        t0 = tl[0][1][0]
+        for slot, x in tl:
+            print('   slot %d  h2d %7.2f-%7.2f  kernels -%7.2f  emit -%7.2f  d2h -%7.2f' % (slot, x[0] - t0, x[1] - t0, x[2] - t0, x[3] - t0, x[4] - t0))
+    eng.close()
