@@ -712,8 +712,7 @@ def main():
             roofline = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"],
                         "unit": top["unit"], "frac": top["frac"], "ms": top["ms"], "share_of_step": top["share"],
                         "traffic": None,
-                        "traffic_how": "see profiles/README.md (ncu --set full of the same build): DP kernels read the packed "
-                                       "codes once per stage, far below HBM limits",
+                        "traffic_how": "no ncu capture on file for this kernel at this batch size (profiles/r2y_traffic.json)",
                         "how": top.get("how"),
                         "peak_how": "LOP3 issue rate %.4g lane-op/s measured in this run on this GPU (orc_measure_int32_peak "
                                     "mode 0; LOP3+IMAD mix %.4g); HBM: %s" % (alu_peak, mix_peak, how),
@@ -721,6 +720,18 @@ def main():
                                      "note": "DP cells stages 1-2b really update per step, over their summed time"},
                         "algorithmic_speedup": cells / executed if executed else None,
                         "algorithmic_cells_per_step": cells}
+            # DRAM bytes per launch from the committed ncu capture of the same kernel at the same batch size
+            try:
+                with open(os.path.join(ROOT, "profiles", "r2y_traffic.json")) as fh:
+                    cap = json.load(fh)
+                k = cap["kernels"].get(top["kernel"])
+                if k and cap["reads_per_launch"] == args.reads and args.config in (2, 5):
+                    roofline["traffic"] = k["dram_read"] + k["dram_write"]
+                    roofline["traffic_how"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, %s; an INT32-bound "
+                                               "kernel: %.0f GB/s of DRAM traffic while it runs" %
+                                               (cap["how"], roofline["traffic"] / (k["duration_us"] * 1e-6) / 1e9))
+            except (OSError, ValueError, KeyError):
+                pass
         extra["gcups"] = cells * args.steps * world / (main_cfg["ms_per_step"] * args.steps * 1e-3) / 1e9
 
     cpu_baseline = None

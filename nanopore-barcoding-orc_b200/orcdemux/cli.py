@@ -336,12 +336,52 @@ class EndStats:
         return out
 
 
-def _batch_shape():
-    """(reads, bytes) of one batch; ORCDEMUX_BATCH_READS shrinks it (tests, small-memory hosts)."""
-    reads = int(os.environ.get("ORCDEMUX_BATCH_READS", 1 << 18))
+def _batch_shape(path: Optional[str] = None):
+    """(reads, bytes) of one batch; ORCDEMUX_BATCH_READS shrinks it (tests, small-memory hosts).
+
+    A small input gets small batches: the engine's device arenas and the page-locked buffers of reader and
+    engine are sized by the batch, and page-locking memory costs about a second per gigabyte here (measured
+    with ORCDEMUX_TIMING=1: of the 4.3 s of one round-2 call on a 100 MB bin, 3.8 s went into creating and
+    releasing 1.3 GB of reader buffers) -- which the twelve round-2 calls of the script (02:94-102) pay twelve
+    times.  So a batch is about a quarter of the input (at least 8 MB, at most 256 MB of text): a few batches
+    in flight over the three slots, buffers in proportion to the work.  The estimate of the text size (four
+    times a .gz) only has to be roughly right: the reader cuts batches by what fits."""
+    env = os.environ.get("ORCDEMUX_BATCH_READS")
+    reads = int(env) if env else 1 << 18
     if reads < 1:
         raise Unsupported("ORCDEMUX_BATCH_READS must be positive")
-    return reads, max(1 << 20, min(1 << 28, reads * 4096))
+    nbytes = max(1 << 20, min(1 << 28, reads * 4096))
+    if not env and path:
+        try:
+            size = os.path.getsize(path)
+        except OSError:
+            size = None
+        if size is not None:
+            text = size * (4 if path.endswith(".gz") else 1)
+            want = max(1 << 23, min(1 << 28, (text // 4 + (1 << 20)) & ~((1 << 20) - 1)))
+            if want < nbytes:
+                nbytes = want
+                reads = max(1 << 12, nbytes >> 10)
+    return reads, nbytes
+
+
+class _Phases:
+    """ORCDEMUX_TIMING=1: wall time of the phases of one invocation on stderr (where do the seconds of a small
+    call go: interpreter and library start-up, engine and buffers, streaming, closing the writers)."""
+    def __init__(self):
+        self.on = os.environ.get("ORCDEMUX_TIMING") == "1"
+        self.t = time.time()
+        self.parts = []
+
+    def mark(self, name):
+        if self.on:
+            now = time.time()
+            self.parts.append("%s %.3f s" % (name, now - self.t))
+            self.t = now
+
+    def done(self):
+        if self.on:
+            sys.stderr.write("orcdemux timing: " + ", ".join(self.parts) + "\n")
 
 
 def _stream(reader, eng, writers, slots, on_result, rank=0, world=1):
@@ -384,7 +424,8 @@ def run_single_round(opt, argv, device=0) -> int:
         kind = ORC_PREFIX if kind == ORC_FRONT else ORC_SUFFIX
     rnd = E.Round(names, seqs, kind, opt["e"], opt["O"], opt["indels"], opt["rc"], opt["action"])
     t0 = time.time()
-    (max_reads, max_bytes), slots = _batch_shape(), 3
+    ph = _Phases()
+    (max_reads, max_bytes), slots = _batch_shape(opt["inputs"][0]), 3
     threads = max(2, min(os.cpu_count() or 2, opt["cores"] if opt["cores"] > 0 else (os.cpu_count() or 2)))
     reader = F.FastqReader(opt["inputs"][0], max_reads, max_bytes, keep=3, ahead=2, threads=threads)
     paths = [opt["out"].replace("{name}", "unknown")] + [opt["out"].replace("{name}", n) for n in names]
@@ -405,16 +446,22 @@ def run_single_round(opt, argv, device=0) -> int:
         per += np.bincount(m["adapter"][has], minlength=len(names))
         stats.add(m, tb.lengths[:res.n_reads], tb)
 
+    ph.mark("reader + writers")
     try:
         with E.Engine([rnd], device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
                       emit_fastq=True, want_matches=True) as eng:
+            ph.mark("engine (%d reads, %d MB per batch)" % (max_reads, max_bytes >> 20))
             try:
                 _stream(reader, eng, writers, slots, on_result)
+                ph.mark("stream")
             finally:
                 writers.close()         # drains: the result buffers belong to the engine
+                ph.mark("writers closed")
     finally:
         writers.close()
         reader.close()
+    ph.mark("engine closed")
+    ph.done()
     rep = _report(n_in, bp_in, bp_out, n_with, n_rc, names, per, time.time() - t0, argv)
     rep["input"]["path1"] = opt["inputs"][0]
     rep["adapters_read1"] = stats.as_json(n_in)
@@ -504,7 +551,7 @@ def run_two_round(args: List[str], device=0) -> int:
             drop[b] = 1
             continue
         paths[b] = os.path.join(outdir, "SP27", "%s_%s_%s%s" % (nm27, nm5, ds, ext))
-    (max_reads, max_bytes), slots = _batch_shape(), 3
+    (max_reads, max_bytes), slots = _batch_shape(a.input), 3
     threads = max(2, min(os.cpu_count() or 2, a.j) // max(world, 1))
     reader = F.FastqReader(a.input, max_reads, max_bytes, keep=3, ahead=2, threads=threads)
     # with several ranks every rank writes part files (+ an index of their chunks); rank 0 stitches them

@@ -94,11 +94,13 @@ def main():
     cmds = [[shim, "--action=trim", "-e", "0.1", "-j", str(a.j), "--rc", "-g", "file:" + fwd,
              "-o", os.path.join(out, "SP5", "{name}_%s.fastq.gz" % ds), inputs["gz"],
              "--json=" + os.path.join(out, "SP5", "cutadapt_SP5_%s.json" % ds)]]
-    r = subprocess.run(cmds[0], capture_output=True, text=True)
+    tenv = dict(os.environ, ORCDEMUX_TIMING="1")
+    r = subprocess.run(cmds[0], capture_output=True, text=True, env=tenv)
     if r.returncode != 0:
         sys.stderr.write(r.stderr)
         return 1
     r1_s = time.time() - t0
+    phases = [l for l in r.stderr.splitlines() if l.startswith("orcdemux timing")][:1]
     ids = sorted(f[:-len("_%s.fastq.gz" % ds)] for f in os.listdir(os.path.join(out, "SP5")) if f.endswith(".fastq.gz"))
     ids = [i for i in ids if "unknown" not in i]
     for ident in ids:
@@ -106,14 +108,16 @@ def main():
                             "-o", os.path.join(out, "SP27", "{name}_%s_%s.fastq.gz" % (ident, ds)),
                             os.path.join(out, "SP5", "%s_%s.fastq.gz" % (ident, ds)),
                             "--json=" + os.path.join(out, "SP27", "%s_%s.json" % (ident, ds))],
-                           capture_output=True, text=True)
+                           capture_output=True, text=True, env=tenv)
         if r.returncode != 0:
             sys.stderr.write(r.stderr)
             return 1
+        if len(phases) < 2:
+            phases += [l for l in r.stderr.splitlines() if l.startswith("orcdemux timing")][:1]
     wall = time.time() - t0
     print(json.dumps({"variant": "script flow through the shim: 1 x round 1 + %d x round 2 (02:64-72, 94-102), gz in, gz out" % len(ids),
                       "reads": a.reads, "process_wall_s": wall, "round1_wall_s": r1_s, "reads_per_s": a.reads / wall,
-                      "host_threads": a.j}), flush=True)
+                      "host_threads": a.j, "phases_round1_and_first_round2": phases}), flush=True)
     shutil.rmtree(a.dir, ignore_errors=True)
     return 0
 
