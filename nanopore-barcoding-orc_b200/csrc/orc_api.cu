@@ -688,7 +688,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         CK(mark(ORC_K_FILTER));
         if (n && anch) {
             // anchored adapters without indels: Hamming compare of the anchored end, no alignment
-            anchored_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(ctx->d_anch[r], s.d_seq, ctx->d_comp_lut, s.d_views[r],
+            anchored_kernel<<<std::min<uint32_t>((2 * n + 127) / 128, (uint32_t)ctx->sm_count * 16), 128, 0, st>>>(ctx->d_anch[r], s.d_seq, ctx->d_comp_lut, s.d_views[r],
                                                                 prev, n, s.d_results, s.d_best_key); nl++;
         } else if (n) {
             scan_kernel<<<ctx->scan_blocks, SCAN_THREADS, 0, st>>>(

@@ -92,9 +92,11 @@ struct RoundTable {
     int32_t min_ov_min;             // smallest min_ov of the round
     uint8_t kmax_any[MAX_M + 8];    // max over the adapters of kmax[a][L]
     uint32_t peq32s[16][64];        // like peq32, for the shared suffix (5' rounds only)
-    // 5' rounds: bit c of first_mask[j] = an alignment that starts in column 0, ends in column j
-    // and costs c could be acceptable for some adapter (c <= k_max < 16 when the filter is on)
-    uint32_t first_mask[MAX_M + 32];
+    // 5' rounds: first_lim[j] = the largest cost c <= k_max with which an alignment that starts in column 0 and
+    // ends in column j could be acceptable for some adapter (it aligns at most min(m_max, j + c) adapter
+    // characters), -1 if there is none.  A scan whose cost in column j is D can only be looking at such an
+    // alignment if D <= first_lim[j] (the alignment's cost is >= D).
+    int8_t first_lim[MAX_M + 32];
     // chunk_lut[P | M << 4], P / M = the Ph / Mh top bits of four consecutive columns (oldest in
     // bit 3): low nibble = 4 + the lowest prefix sum of the four deltas, high nibble = 4 + their sum
     uint8_t chunk_lut[256];
@@ -563,7 +565,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                          uint32_t ext, uint32_t back, WinList &out,
                          const char *suffix_base = nullptr, int Ls = 0,
                          const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0, int m_min = 0,
-                         int sfx_primary = 0, const uint32_t *first_mask = nullptr,
+                         int sfx_primary = 0, const int8_t *first_lim = nullptr,
                          const uint8_t *lut = nullptr, const SeedWins *seeded = nullptr)
 {
     const uint32_t n = len;
@@ -600,7 +602,7 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
         const uint32_t wmax = (uint32_t)(m_max + kt);
         const uint32_t w0 = wmax < n ? wmax : n;
         bool need = true;
-        if (suffix_base != nullptr && Ls > 0 && first_mask != nullptr) {
+        if (suffix_base != nullptr && Ls > 0 && first_lim != nullptr) {
             need = false;
             uint32_t sPv = 0, sMv = 0;
             int sD = 0;
@@ -625,8 +627,8 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                         sPv = Mh | ~(Xv | Ph);
                         sMv = Ph & Xv;
                         // an alignment ending here has cost c >= sD and aligns at most
-                        // min(m_max, j + c) adapter characters: first_mask[j] has the costs that pass
-                        if (sD <= kt && (first_mask[c0 + t + 1] >> sD) != 0u) need = true;
+                        // min(m_max, j + c) adapter characters: first_lim[j] is the largest cost that passes
+                        if (sD <= (int)first_lim[c0 + t + 1]) need = true;
                     }
                 }
             }
@@ -876,7 +878,7 @@ ORC_HD uint32_t win_columns(const WinList &w)
 //    same column.  If the window starts at the true column 0 the alignment may begin inside B
 //    (the read starts within the adapter): B's column 0 is free as well (cost 0 in every row),
 //    and for the first columns, where nearly any cost is "<= k", the acceptance limit of the
-//    alignment's largest possible length decides instead (first_mask, the loosest of the round).
+//    alignment's largest possible length decides instead (first_lim, the loosest of the round).
 //  * 3' adapter, B = its first Lb rows, the same rows of the same matrix (same start costs).  A
 //    path to (m, j) or to a last-column cell (i, n) with i > Lb crosses row Lb inside the window
 //    at cost <= k; a last-column cell with i <= Lb is a cell of B's matrix itself and is tested
@@ -895,7 +897,7 @@ ORC_HD uint32_t win_columns(const WinList &w)
 // path of a 3' adapter has crossed row Lb by then with m - Lb - kt columns to spare.  `trim` = m - Lb - kt.
 ORC_HD bool block_test(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len, int dir,
                        const WinList *wl, const char *peq32b_base, int lane, int Lb, int k, int type,
-                       const uint8_t *kmax, int min_ov, const uint32_t *first_mask, int trim = 0)
+                       const uint8_t *kmax, int min_ov, const int8_t *first_lim, int trim = 0)
 {
     if (Lb <= 0) return true;
     const uint32_t n = len;
@@ -940,7 +942,7 @@ ORC_HD bool block_test(const uint32_t *__restrict__ W, uint64_t lo, uint32_t len
                         Ph <<= 1; Mh <<= 1;
                         Pv = Mh | ~(Xv | Ph);
                         Mv = Ph & Xv;
-                        if (D <= k && (first_mask[8 * q + t + 1] >> D) != 0u) return true;
+                        if (D <= imin(k, (int)first_lim[8 * q + t + 1])) return true;
                     }
                 }
                 continue;
@@ -2195,6 +2197,9 @@ struct AnchoredTable {
     int32_t suffix;                 // 0: 5' anchored (prefix), 1: 3' anchored (suffix)
     int32_t revcomp;
     int32_t indexed;                // dict semantics (>= 2 adapters, one length, every k <= 2)
+    int32_t one_length;             // every adapter has m[0] characters: the packed comparison below applies
+    int32_t pad_;
+    uint64_t nib[MAX_ANCH][4];      // the adapter as one-hot nibbles (A1 C2 G4 T8), 16 characters per word, 0 behind m
     int32_t m[MAX_ANCH];
     int32_t k[MAX_ANCH];            // int(rate * m)
     uint8_t seq[MAX_ANCH][MAX_M];   // upper-case ASCII
@@ -2210,30 +2215,52 @@ ORC_HD int anchored_match(const uint8_t *seq, const uint8_t *comp, const View &v
     res.has = 0; res.pad_ = 0;
     res.ref_start = res.ref_stop = res.query_start = res.query_stop = res.score = res.errors = 0;
     int best = -1, best_score = 0, best_e = 0, best_m = 0;
-    bool use_index = T.indexed != 0;
-    if (use_index) {
-        const int L = T.m[0];
-        if (n < L) return -1;
+    bool use_index = T.indexed != 0;            // (build_anchored_table: indexed implies one_length)
+    // One length for all adapters (the M13 indices): the anchored end of the read is gathered ONCE as one-hot
+    // nibbles, and every adapter is one AND + fold + popcount per 16 characters away -- a character matches iff
+    // the nibbles share their bit (anything but ACGT has none, like the ASCII comparison against ACGT adapters).
+    uint64_t rn0 = 0, rn1 = 0, rn2 = 0, rn3 = 0;
+    if (T.one_length) {
+        const int m = T.m[0];
+        if (n < m) return -1;
         bool has_n = false, other = false;
-        for (int i = 0; i < L; i++) {
-            const int p = T.suffix ? n - L + i : i;
+        for (int i = 0; i < m; i++) {
+            const int p = T.suffix ? n - m + i : i;
             uint8_t c = eff ? comp[seq[v.lo + (uint64_t)(n - 1 - p)]] : seq[v.lo + (uint64_t)p];
             if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+            const uint64_t code = c == 'A' ? 1u : c == 'C' ? 2u : c == 'G' ? 4u : c == 'T' ? 8u : 0u;
             if (c == 'N') has_n = true;
-            else if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) other = true;
+            else if (code == 0u) other = true;
+            const uint64_t put = code << (4 * (i & 15));
+            if (i < 16) rn0 |= put; else if (i < 32) rn1 |= put; else if (i < 48) rn2 |= put; else rn3 |= put;
         }
-        if (has_n) use_index = false;           // "N" in the affix: the plain comparer loop decides
-        else if (other) return -1;              // not a key of the dict
+        if (use_index) {
+            if (has_n) use_index = false;       // "N" in the affix: the plain comparer loop decides
+            else if (other) return -1;          // not a key of the dict
+        }
     }
     for (int a = 0; a < T.n_adapters; a++) {
         const int m = T.m[a];
         if (n < m) continue;                    // anchored adapters need the whole adapter (min_overlap = m)
         int e = 0;
-        for (int i = 0; i < m; i++) {
-            const int p = T.suffix ? n - m + i : i;
-            uint8_t c = eff ? comp[seq[v.lo + (uint64_t)(n - 1 - p)]] : seq[v.lo + (uint64_t)p];
-            if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
-            e += (c != T.seq[a][i]);
+        if (T.one_length) {
+            int matches = 0;
+            const uint64_t rn[4] = {rn0, rn1, rn2, rn3};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                if (16 * w >= m) break;
+                uint64_t x = rn[w] & T.nib[a][w];
+                x |= x >> 1; x |= x >> 2;
+                matches += popc64(x & 0x1111111111111111ull);
+            }
+            e = m - matches;
+        } else {
+            for (int i = 0; i < m; i++) {
+                const int p = T.suffix ? n - m + i : i;
+                uint8_t c = eff ? comp[seq[v.lo + (uint64_t)(n - 1 - p)]] : seq[v.lo + (uint64_t)p];
+                if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+                e += (c != T.seq[a][i]);
+            }
         }
         if (e > T.k[a]) continue;
         bool take;

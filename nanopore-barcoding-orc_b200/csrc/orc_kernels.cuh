@@ -233,7 +233,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
     __shared__ __align__(16) uint32_t s_peq32[16][64];
     __shared__ __align__(16) uint32_t s_peq32s[16][64];
     __shared__ uint8_t s_kmax_any[MAX_M + 8];
-    __shared__ uint32_t s_first_mask[MAX_M + 32];
+    __shared__ int8_t s_first_lim[MAX_M + 32];
     __shared__ uint8_t s_lut[256];
     __shared__ int s_par[8];
     __shared__ int s_mmin, s_sfxp;
@@ -243,7 +243,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
         (&s_peq32s[0][0])[i] = (&tab->peq32s[0][0])[i];
     }
     for (int i = threadIdx.x; i < MAX_M + 8; i += blockDim.x) s_kmax_any[i] = tab->kmax_any[i];
-    for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_mask[i] = tab->first_mask[i];
+    for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_lim[i] = tab->first_lim[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = tab->chunk_lut[i];
     if (threadIdx.x == 0) {
         s_par[0] = tab->lcp; s_par[1] = tab->k_max; s_par[2] = tab->m_max; s_par[3] = tab->type;
@@ -272,7 +272,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                              (int)(2u * (threadIdx.x & 31u)) + dir, Lp, kt, type, (uint32_t)(m_max - Lp + kt),
                              (uint32_t)(Lp + kt + 1), wl,
                              s_par[6] > 0 ? reinterpret_cast<const char *>(&s_peq32s[0][0]) : nullptr,
-                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp, s_first_mask, s_lut,
+                             s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp, s_first_lim, s_lut,
                              seedwins ? seedwins + (2u * r + (uint32_t)dir) : nullptr);
                 cols = win_columns(wl);
             } else {
@@ -309,12 +309,12 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
               unsigned long long *__restrict__ cells_2b, int trim_on)
 {
     __shared__ __align__(16) uint32_t s_peq32b[16][64];
-    __shared__ uint32_t s_first_mask[MAX_M + 32];
+    __shared__ int8_t s_first_lim[MAX_M + 32];
     __shared__ uint8_t s_kmax[MAX_AD][MAX_M + 8];     // the pruning limits (kmax[a][0])
     __shared__ int s_k[MAX_AD], s_min_ov[MAX_AD], s_lb[MAX_AD], s_m[MAX_AD];
     __shared__ int s_na, s_type, s_trim;      // s_trim: k_max + 1 when the windows come from stage 1 (0: whole reads)
     for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) (&s_peq32b[0][0])[i] = (&tab->peq32b[0][0])[i];
-    for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_mask[i] = tab->first_mask[i];
+    for (int i = threadIdx.x; i < MAX_M + 32; i += blockDim.x) s_first_lim[i] = tab->first_lim[i];
     for (int i = threadIdx.x; i < MAX_AD * (MAX_M + 8); i += blockDim.x)
         (&s_kmax[0][0])[i] = tab->kmax[i / (MAX_M + 8)][0][i % (MAX_M + 8)];
     if (threadIdx.x < MAX_AD) {
@@ -358,7 +358,7 @@ filter_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ W
                 dst[0] = src[0]; dst[1] = src[1];
             }
             keep = block_test(W, v.lo, v.len, dir, &wl, base_b, a + (int)na * dir, s_lb[a], s_k[a], type,
-                              s_kmax[a], s_min_ov[a], s_first_mask, s_trim ? s_m[a] - s_lb[a] - s_trim + 1 : 0);
+                              s_kmax[a], s_min_ov[a], s_first_lim, s_trim ? s_m[a] - s_lb[a] - s_trim + 1 : 0);
         }
         const uint32_t mk = __ballot_sync(0xffffffffu, keep);
         if (mk) {
@@ -641,18 +641,19 @@ anchored_kernel(const AnchoredTable *__restrict__ tab, const uint8_t *__restrict
         for (int i = threadIdx.x; i < 256; i += blockDim.x) comp[i] = comp_lut_g[i];
     }
     __syncthreads();
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= 2u * n_reads) return;
-    const uint32_t r = p >> 1;
-    const int o = (int)(p & 1u);
-    if (prev != nullptr && prev[r].adapter < 0) return;
-    if (o == 1 && !T.revcomp) return;
-    const View v = views[r];
-    PairResult res;
-    const int a = anchored_match(seq, comp, v, o, T, res);
-    if (a >= 0) {
-        results[p] = res;
-        best_key[p] = (unsigned long long)pack_key(res.score, res.errors, a, p);
+    // grid-stride: the table (6.7 KB) is staged once per block, not once per 128 items
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < 2u * n_reads; p += gridDim.x * blockDim.x) {
+        const uint32_t r = p >> 1;
+        const int o = (int)(p & 1u);
+        if (prev != nullptr && prev[r].adapter < 0) continue;
+        if (o == 1 && !T.revcomp) continue;
+        const View v = views[r];
+        PairResult res;
+        const int a = anchored_match(seq, comp, v, o, T, res);
+        if (a >= 0) {
+            results[p] = res;
+            best_key[p] = (unsigned long long)pack_key(res.score, res.errors, a, p);
+        }
     }
 }
 
@@ -836,11 +837,25 @@ bin_place_kernel(const int32_t *__restrict__ bin, const uint32_t *__restrict__ r
         const int b = r < n_reads ? bin[r] : -1;
         const unsigned long long nb = (b >= 0) ? rec_bytes[r] : 0ull;
         unsigned long long d = ~0ull;
-        // input order inside a bin: lanes take their slot one after the other
-        for (int l = 0; l < 32; l++) {
-            if (lane == l && b >= 0) { d = s_cur[w][b]; s_cur[w][b] = d + nb; }
-            __syncwarp();
+        // input order inside a bin: the lanes that hold reads of the same bin (match-any ballot) take their
+        // places by a prefix sum of the record sizes of the peers in front of them; the last peer moves the
+        // bin's cursor on for the next 32 reads
+        const uint32_t have = __ballot_sync(0xffffffffu, b >= 0);
+        if (b >= 0) {
+            const uint32_t peers = __match_any_sync(have, b);
+            unsigned long long before = 0, total = 0;
+            for (uint32_t m = peers; m; m &= m - 1u) {
+                const int src = __ffs((int)m) - 1;
+                const unsigned long long v = __shfl_sync(peers, nb, src);
+                if (src < lane) before += v;
+                total += v;
+            }
+            const unsigned long long cur = s_cur[w][b];
+            d = cur + before;
+            __syncwarp(peers);
+            if (lane == 31 - __clz((int)peers)) s_cur[w][b] = cur + total;
         }
+        __syncwarp();
         if (r < n_reads) dest[r] = d;
     }
 }

@@ -136,7 +136,7 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
                 if (T.code[a][first + i] & cc) bits |= 1u << (32 - Lb + i);
             T.peq32b[c][lane] = bits;
         }
-        // with k >= Lb a path may cross the block for free; with k_max >= 32 first_mask has no room
+        // with k >= Lb a path may cross the block for free; with k_max >= 32 the first-column limits have no room
         T.block_len[a] = (indels && T.k[a] < Lb && T.k[a] < 16) ? Lb : 0;
     }
     // longest common prefix of the adapters (as code masks), capped at one 32-bit word
@@ -195,12 +195,12 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
             T.chunk_lut[P | (M << 4)] = (uint8_t)((low + 4) | ((sum + 4) << 4));
         }
     for (int j = 0; j < MAX_M + 32; j++) {
-        uint32_t bits = 0;
+        int lim = -1;
         for (int c = 0; c <= T.k_max && c < 32; c++) {
             const int lmax = (j + c < T.m_max) ? j + c : T.m_max;
-            if (lmax >= T.min_ov_min && c <= (int)T.kmax_any[lmax]) bits |= 1u << c;
+            if (lmax >= T.min_ov_min && c <= (int)T.kmax_any[lmax]) lim = c;
         }
-        T.first_mask[j] = bits;
+        T.first_lim[j] = (int8_t)lim;
     }
     if (T.use_filter && lcs > 0) {
         const uint32_t pad32 = (lcs == 32) ? 0u : ((1u << (32 - lcs)) - 1u);
@@ -325,6 +325,7 @@ inline std::string build_anchored_table(AnchoredTable &A, RoundTable &T, int n_a
             if (c == 'U') c = 'T';
             if (base_code(c) < 0) return "unsupported: adapter characters other than ACGT (IUPAC wildcards)";
             A.seq[a][i] = (uint8_t)c;
+            A.nib[a][i >> 4] |= (uint64_t)(c == 'A' ? 1u : c == 'C' ? 2u : c == 'G' ? 4u : 8u) << (4 * (i & 15));
         }
         double rate = max_errors;
         if (rate >= 1.0) rate /= m;
@@ -336,6 +337,7 @@ inline std::string build_anchored_table(AnchoredTable &A, RoundTable &T, int n_a
     if (n_adapters >= 2 && small_k && !one_length)
         return "unsupported: anchored adapters of several lengths (cutadapt's multi-length index)";
     A.indexed = (n_adapters >= 2 && small_k && one_length) ? 1 : 0;
+    A.one_length = one_length ? 1 : 0;
     T.n_adapters = n_adapters;
     T.type = suffix ? TYPE_BACK : TYPE_FRONT;       // which side the selection trims
     T.revcomp = revcomp ? 1 : 0;

@@ -127,7 +127,7 @@ extern "C" int hostsim_demux(int n_rounds,
                     trigger_lane(W, v.lo, v.len, dir, (const char *)&R.peq32[0][0], dir, R.lcp, R.k_max, R.type,
                                  (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + R.k_max + 1), wl[dir],
                                  R.lcs > 0 ? (const char *)&R.peq32s[0][0] : nullptr, R.lcs,
-                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary, R.first_mask, R.chunk_lut,
+                                 R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary, R.first_lim, R.chunk_lut,
                                  ST[rd].on ? &sw[dir] : nullptr);
                     n_columns[rd] += win_columns(wl[dir]);
                 }
@@ -139,7 +139,7 @@ extern "C" int hostsim_demux(int n_rounds,
                 g_pairs[rd]++;
                 if (R.indels && !block_test(W, v.lo, v.len, dir, R.use_filter ? &wl[dir] : nullptr,
                                             (const char *)&R.peq32b[0][0], lane, R.block_len[a], R.k[a], R.type,
-                                            R.kmax[a][0], R.min_ov[a], R.first_mask,
+                                            R.kmax[a][0], R.min_ov[a], R.first_lim,
                                             R.use_filter ? R.m[a] - R.block_len[a] - R.k_max : 0)) continue;
                 g_kept[rd]++;
                 LaneScan L;

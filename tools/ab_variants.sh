@@ -15,7 +15,7 @@ for v in $pkg/_build/variants/lib_*.so; do
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 k=d['stages_ms_last_step']['kernel_ms']
-print('$(basename $v)', round(d['value']/1e6,2), 'Mreads/s', round(d['ms_per_step'],3), 'ms', ' '.join('%s=%.3f+%.3f'%(n,k[0][n],k[1][n]) for n in k[0]), 'emit=%.3f'%d['stages_ms_last_step']['emit_ms'])
+print('$(basename $v)', round(d['value']/1e6,2), 'Mreads/s', round(d['ms_per_step'],3), 'ms', ' '.join('%s=%s'%(n,'+'.join('%.3f'%kk[n] for kk in k)) for n in k[0]), 'emit=%.3f'%d['stages_ms_last_step']['emit_ms'])
 " >> gpurun_out/ab_$tag.txt 2>&1 || tail -3 /tmp/ab.err >> gpurun_out/ab_$tag.txt
 done
 cp /tmp/lib_keep.so $lib
