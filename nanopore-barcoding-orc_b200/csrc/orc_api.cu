@@ -67,7 +67,8 @@ struct Slot {
     unsigned long long *d_best_key = nullptr;
     uint32_t *d_order = nullptr;             // reads in order of decreasing view length (stage 1)
     WinList *d_wins = nullptr;
-    SeedWins *d_seedwins = nullptr;  // stage 1s: seed windows per (read, direction)
+    SeedWins *d_seedwins = nullptr;  // stage 1s: seed windows per (segment, read, direction)
+    uint32_t max_len = 0;            // longest read of the resident batch (how many segments seed_kernel needs)
     Task *d_tasks = nullptr;
     uint32_t *d_jobs = nullptr;              // stage 2a survivors: job numbers (item * n_adapters + adapter)
     PairResult *d_results = nullptr;
@@ -180,7 +181,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     CK(dalloc(&s.d_best_key, 2 * R));
     CK(dalloc(&s.d_order, R));
     CK(dalloc(&s.d_wins, 2 * R));
-    CK(dalloc(&s.d_seedwins, 2 * R));
+    CK(dalloc(&s.d_seedwins, (size_t)SEED_SEGS_MAX * 2 * R));    // one plane of 2 * R per segment (seed_kernel)
     CK(dalloc(&s.d_tasks, 2 * n_tasks));           // front half: band resolver, back half: wide resolver
     CK(dalloc(&s.d_jobs, 2 * R * (size_t)ctx->na_max));
     CK(dalloc(&s.d_results, n_tasks));
@@ -431,12 +432,14 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
     s.n_bytes = b->n_bytes;
     s.name_bytes = name_bytes;
     uint64_t bases = 0;
+    uint32_t max_len = 0;
     for (uint32_t r = 0; r < b->n_reads; r++) {
         if (b->offsets[r] + b->lengths[r] > b->n_bytes ||
             (b->qual_offsets && b->qual_offsets[r] + b->lengths[r] > b->n_bytes)) {
             ctx->err = "read extends past n_bytes"; return ORC_EINVAL;
         }
         bases += b->lengths[r];
+        if (b->lengths[r] > max_len) max_len = b->lengths[r];
     }
     if (s.has_names && b->n_reads) {
         // the header lines: inside the text (raw FASTQ layout) or inside the names blob, never past it
@@ -454,6 +457,7 @@ extern "C" int orc_upload(orc_ctx *ctx, int slot, const orc_batch *b)
         }
     }
     s.in_bases = bases;
+    s.max_len = max_len;
     CK(cudaEventRecord(s.ev[EV_START], s.stream));
     s.u_qual = s.d_qual; s.u_names = s.d_names; s.u_qual_offsets = nullptr; s.u_name_lengths = nullptr;
     if (b->n_reads) {
@@ -564,6 +568,7 @@ extern "C" int orc_synth(orc_ctx *ctx, int slot, uint64_t seed, uint32_t n_reads
     s.n_bytes = totals[0];
     s.name_bytes = totals[1];
     s.in_bases = totals[0];
+    s.max_len = len_max;
     s.has_names = true;
     s.u_qual = s.d_qual; s.u_names = s.d_names; s.u_qual_offsets = nullptr; s.u_name_lengths = nullptr;
     CK(cudaEventRecord(s.ev[EV_H2D], st));
@@ -658,8 +663,10 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
         CK(mark(ORC_K_SORT_READS));
         const bool seeded = !anch && filter && ctx->h_seed[r].on != 0;
         if (n && seeded) {
-            seed_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_seed[r], W, s.d_views[r], prev, s.d_order, n,
-                                                        s.d_seedwins); nl++;
+            // long reads are probed in segments, one thread each (grid.y; orc_core.cuh seed_segments)
+            const dim3 seed_grid((n + 255) / 256, (unsigned)seed_segments(s.max_len));
+            seed_kernel<<<seed_grid, 256, 0, st>>>(ctx->d_seed[r], W, s.d_views[r], prev, s.d_order, n,
+                                                  s.d_seedwins, (size_t)2 * ctx->max_reads); nl++;
         }
         CK(mark(ORC_K_SEED));
         if (n && !anch) {
@@ -667,7 +674,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
                                                                filter ? s.d_order : nullptr, n, s.d_wins,
                                                                s.d_wcols, s.d_cells + 2 + r,
                                                                seeded ? s.d_seedwins : nullptr,
-                                                               sort_hist(s.d_counters, r, 1, 0)); nl++;
+                                                               sort_hist(s.d_counters, r, 1, 0), (size_t)2 * ctx->max_reads); nl++;
         }
         CK(mark(ORC_K_TRIGGER));
         if (n && !anch) {

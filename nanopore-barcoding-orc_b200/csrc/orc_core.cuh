@@ -426,6 +426,25 @@ constexpr int SEED_SHIFT = 20;          // slot = (key * mult) >> SEED_SHIFT
 constexpr int SEED_LIST_MAX = 512;
 constexpr int SEED_RAW_MAX = 12;        // raw hits kept per direction before giving up (-> scan everything)
 constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;    // no packed window ever has an all-ones nibble
+// A long read is probed in segments of SEED_SEG columns, one thread each, so that a batch of kilobase reads is
+// several waves of equal work instead of one wave that lasts as long as its longest read.  Segment g probes
+// the window positions [g * SEED_SEG, (g + 1) * SEED_SEG + m_max + kt + 8): two pieces of one occurrence lie
+// at most m_max - 8 + kt positions apart, so the segment that holds the first of them sees the second as well
+// (the rule that a hit needs a neighbour is applied per segment); hits in the overlap are reported by both
+// segments, which only repeats a window.  The last segment (SEED_SEGS_MAX - 1) takes the rest of the read.
+constexpr uint32_t SEED_SEG = 1024;
+constexpr int SEED_SEGS_MAX = 4;
+ORC_HD int seed_segments(uint32_t len)
+{
+    const uint32_t g = (len + SEED_SEG - 1u) / SEED_SEG;
+    return g < 1u ? 1 : (g > (uint32_t)SEED_SEGS_MAX ? SEED_SEGS_MAX : (int)g);
+}
+ORC_HD void seed_range(uint32_t len, int g, int n_seg, int m_max, int kt, uint32_t &a, uint32_t &b)
+{
+    a = (uint32_t)g * SEED_SEG;
+    b = (g == n_seg - 1) ? len : ((uint32_t)(g + 1) * SEED_SEG + (uint32_t)(m_max + kt + 8));
+    if (b > len) b = len;
+}
 
 
 // slot of a key: the top 12 bits of key * mult (multiply-high keeps the index arithmetic off the
@@ -470,20 +489,23 @@ ORC_HD Quad load_quad(const uint32_t *__restrict__ W, int64_t q)     // words 4q
 }
 
 // keys: the SEED_SLOTS keys alone (shared memory on the device); vals / list are only read on a hit
+// Probes the window positions [from, to) of the view (a segment, seed_range(); the whole read: 0, n); diagonals
+// and windows are in the coordinates of the whole view and clipped to it.
 ORC_HD void seed_scan(const uint32_t *__restrict__ W, uint64_t lo, uint32_t n, const uint32_t *keys,
                       const uint32_t *__restrict__ vals, uint32_t mult, const uint32_t *__restrict__ list,
-                      int need, int kt, int m_max, SeedWins out[2])
+                      int need, int kt, int m_max, SeedWins out[2], uint32_t from = 0u, uint32_t to = 0xFFFFFFFFu)
 {
     for (int d = 0; d < 2; d++) {
         out[d].n = 0; out[d].all = 0;
         for (int i = 0; i < MAX_WIN; i++) { out[d].s[i] = 0; out[d].e[i] = 0; }
     }
-    if (n < 8u) return;             // no piece fits, and no whole adapter either
+    if (to > n) to = n;
+    if (n < 8u || to < from + 8u) return;   // no piece fits (and no whole adapter either)
     int32_t rc0[2][SEED_RAW_MAX];   // diagonals of the hits, per direction, kept sorted
     int nraw[2] = {0, 0};
     // 32 columns per 16-byte load, the next load in flight while these are probed.  Windows that
     // start before lo or reach past lo + n (the neighbours' codes) are discarded when they hit.
-    const int64_t q_first = (int64_t)(lo >> 5), q_last = (int64_t)((lo + n - 8u) >> 5);
+    const int64_t q_first = (int64_t)((lo + from) >> 5), q_last = (int64_t)((lo + to - 8u) >> 5);
     Quad cur = load_quad(W, q_first);
     Quad nxt = load_quad(W, q_first + 1);       // at most one quad past the read: guard words
     for (int64_t q = q_first; q <= q_last; q++) {
@@ -512,7 +534,7 @@ ORC_HD void seed_scan(const uint32_t *__restrict__ W, uint64_t lo, uint32_t n, c
 #endif
                     mask &= mask - 1u;
                     const uint64_t pos = 32ull * (uint64_t)q + 8ull * (uint64_t)u + (uint64_t)t;
-                    if (pos < lo || pos + 8u > lo + n) continue;         // the window must lie inside the read
+                    if (pos < lo + from || pos + 8u > lo + to) continue; // the piece must lie inside the probed range
                     const uint32_t x = t ? funnel_r(a, b, 4u * (uint32_t)t) : a;
                     const uint32_t val = vals[seed_slot(x, mult)];
                     const uint32_t first = val & 0xFFFFu, cnt = val >> 16;
@@ -566,7 +588,8 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
                          const char *suffix_base = nullptr, int Ls = 0,
                          const uint8_t *kmax_any = nullptr, int min_ov_min = 1, int m_max = 0, int m_min = 0,
                          int sfx_primary = 0, const int8_t *first_lim = nullptr,
-                         const uint8_t *lut = nullptr, const SeedWins *seeded = nullptr)
+                         const uint8_t *lut = nullptr, const SeedWins *seeded = nullptr,
+                         int n_seg = 1, size_t seg_stride = 0)
 {
     const uint32_t n = len;
     out.n = 0; out.flags = 0;
@@ -710,9 +733,15 @@ ORC_HD void trigger_lane(const uint32_t *__restrict__ W, uint64_t lo, uint32_t l
     // windows of the alignments that run off an end of the read are decided here
     // (a read with more key matches than seed_scan keeps apart -- tens of kilobases of sequence --
     // takes the flank scan below instead)
-    const bool seeds = seeded != nullptr && !seeded->all;
+    // (segment g of the read at seeded[g * seg_stride]; in direction 1 the columns run the other way, so the
+    // segments come in descending order there)
+    bool seeds = seeded != nullptr;
+    for (int g = 0; seeds && g < n_seg; g++) seeds = seeded[(size_t)g * seg_stride].all == 0u;
     if (seeds)
-        for (uint32_t i = 0; i < seeded->n; i++) win_add(out, open, cs, ce, seeded->s[i], seeded->e[i]);
+        for (int q = 0; q < n_seg; q++) {
+            const SeedWins &sw = seeded[(size_t)(dir ? n_seg - 1 - q : q) * seg_stride];
+            for (uint32_t i = 0; i < sw.n; i++) win_add(out, open, cs, ce, sw.s[i], sw.e[i]);
+        }
     ChunkReader rd;
     rd.init(W, lo, len, dir, 0u);
     const int nchunks = seeds ? 0 : (int)((n + 7u) >> 3);

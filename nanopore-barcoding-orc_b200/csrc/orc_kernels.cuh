@@ -201,7 +201,7 @@ bucket_scatter_kernel(const View *__restrict__ views, const Match *__restrict__ 
 __global__ void __launch_bounds__(256, SEED_BLOCKS)
 seed_kernel(const SeedTable *__restrict__ st, const uint32_t *__restrict__ W, const View *__restrict__ views,
             const Match *__restrict__ prev, const uint32_t *__restrict__ order, uint32_t n_reads,
-            SeedWins *__restrict__ out)
+            SeedWins *__restrict__ out, size_t seg_stride)
 {
     __shared__ __align__(16) uint32_t s_key[SEED_SLOTS];
     {
@@ -215,9 +215,15 @@ seed_kernel(const SeedTable *__restrict__ st, const uint32_t *__restrict__ W, co
     const uint32_t r = order ? order[p] : p;
     if (prev != nullptr && prev[r].adapter < 0) return;     // trigger_kernel skips these reads, too
     const View v = views[r];
+    // blockIdx.y = the segment of the read this thread probes (orc_core.cuh seed_segments): reads come in
+    // length order, so the threads of a block have the same number of segments, give or take one
+    const int g = (int)blockIdx.y, n_seg = seed_segments(v.len);
+    if (g >= n_seg) return;
+    uint32_t a, b;
+    seed_range(v.len, g, n_seg, st->m_max, st->kt, a, b);
     SeedWins sw[2];
-    seed_scan(W, v.lo, v.len, s_key, st->val, st->mult, st->list, st->need, st->kt, st->m_max, sw);
-    uint4 *dst = reinterpret_cast<uint4 *>(out + 2u * r);
+    seed_scan(W, v.lo, v.len, s_key, st->val, st->mult, st->list, st->need, st->kt, st->m_max, sw, a, b);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)g * seg_stride + 2u * r);
     const uint4 *src = reinterpret_cast<const uint4 *>(&sw[0]);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
 }
@@ -228,7 +234,7 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                const uint32_t *__restrict__ order, uint32_t n_reads, WinList *__restrict__ wins,
                uint32_t *__restrict__ wcols,
                unsigned long long *__restrict__ col_sum, const SeedWins *__restrict__ seedwins,
-               uint32_t *__restrict__ col_hist)
+               uint32_t *__restrict__ col_hist, size_t seg_stride)
 {
     __shared__ __align__(16) uint32_t s_peq32[16][64];
     __shared__ __align__(16) uint32_t s_peq32s[16][64];
@@ -273,7 +279,8 @@ trigger_kernel(const RoundTable *__restrict__ tab, const uint32_t *__restrict__ 
                              (uint32_t)(Lp + kt + 1), wl,
                              s_par[6] > 0 ? reinterpret_cast<const char *>(&s_peq32s[0][0]) : nullptr,
                              s_par[6], s_kmax_any, s_par[7], m_max, s_mmin, s_sfxp, s_first_lim, s_lut,
-                             seedwins ? seedwins + (2u * r + (uint32_t)dir) : nullptr);
+                             seedwins ? seedwins + (2u * r + (uint32_t)dir) : nullptr,
+                             seed_segments(v.len), seg_stride);
                 cols = win_columns(wl);
             } else {
                 wl.n = 1; wl.s[0] = 0; wl.e[0] = v.len;     // no usable shared prefix: scan everything

@@ -116,10 +116,16 @@ extern "C" int hostsim_demux(int n_rounds,
                 continue;
             }
             WinList wl[2];
-            SeedWins sw[2];
+            // the read's segments as seed_kernel probes them: sw[segment][direction]
+            SeedWins sw[SEED_SEGS_MAX][2];
+            const int n_seg = seed_segments(v.len);
             if (R.use_filter && ST[rd].on) {
-                seed_scan(W, v.lo, v.len, ST[rd].key, ST[rd].val, ST[rd].mult, ST[rd].list, ST[rd].need, ST[rd].kt,
-                          ST[rd].m_max, sw);
+                for (int g = 0; g < n_seg; g++) {
+                    uint32_t ra, rb;
+                    seed_range(v.len, g, n_seg, ST[rd].m_max, ST[rd].kt, ra, rb);
+                    seed_scan(W, v.lo, v.len, ST[rd].key, ST[rd].val, ST[rd].mult, ST[rd].list, ST[rd].need, ST[rd].kt,
+                              ST[rd].m_max, sw[g], ra, rb);
+                }
                 g_seeded[rd]++;
             }
             if (R.use_filter) {
@@ -128,7 +134,7 @@ extern "C" int hostsim_demux(int n_rounds,
                                  (uint32_t)(R.m_max - R.lcp + R.k_max), (uint32_t)(R.lcp + R.k_max + 1), wl[dir],
                                  R.lcs > 0 ? (const char *)&R.peq32s[0][0] : nullptr, R.lcs,
                                  R.kmax_any, R.min_ov_min, R.m_max, R.m_min, R.sfx_primary, R.first_lim, R.chunk_lut,
-                                 ST[rd].on ? &sw[dir] : nullptr);
+                                 ST[rd].on ? &sw[0][dir] : nullptr, n_seg, 2);
                     n_columns[rd] += win_columns(wl[dir]);
                 }
             } else n_columns[rd] += 2ull * v.len;

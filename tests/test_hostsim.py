@@ -36,6 +36,77 @@ def test_synthetic_rrna():
     _compare(H.m13_rounds(), synth.generate(500, 1000, 3500, seed=1003))
 
 
+def test_seed_segments_of_long_reads():
+    """Reads longer than one seed segment (orc_core.cuh SEED_SEG = 1024 columns, at most four segments, the last
+    one taking the rest): adapters -- intact, with errors, reverse-complemented -- at and across every segment
+    boundary and the overlap behind it, also two of them close together on either side of a boundary, in reads
+    of two to six segments.  The segmented probe must open the same windows as the whole-read probe did."""
+    rnd = random.Random(4242)
+    f = [s for _, s in m13.sp5_forward()]
+    b = [s for _, s in m13.sp27_reverse_rc()]
+    comp = str.maketrans("ACGT", "TGCA")
+
+    def mutate(s, rate):
+        out = []
+        for c in s:
+            u = rnd.random()
+            if u < rate:
+                out.append(rnd.choice("ACGT"))
+            elif u < 1.5 * rate:
+                continue
+            elif u < 2 * rate:
+                out.append(c); out.append(rnd.choice("ACGT"))
+            else:
+                out.append(c)
+        return "".join(out)
+
+    recs = []
+    for i in range(700):
+        n = rnd.choice([1100, 1500, 2047, 2048, 2049, 2500, 3071, 3200, 4096, 4200, 5000, 6200])
+        body = [rnd.choice("ACGT") for _ in range(n)]
+        for _ in range(rnd.randint(1, 3)):
+            ad = rnd.choice(f + b)
+            if rnd.random() < 0.5:
+                ad = mutate(ad, rnd.choice([0.0, 0.03, 0.06, 0.1]))
+            if rnd.random() < 0.4:
+                ad = ad.translate(comp)[::-1]
+            edge = rnd.choice([1024, 2048, 3072, 4096]) + rnd.choice([0, 0, 72, 73, -8, 8])
+            pos = min(max(0, edge - rnd.randint(0, len(ad) + 12)), max(0, n - len(ad)))
+            body[pos:pos + len(ad)] = list(ad)
+        s = "".join(body)
+        if rnd.random() < 0.5:
+            s = rnd.choice(f) + s
+        if rnd.random() < 0.5:
+            s = s + rnd.choice(b)
+        recs.append(("s%d" % i, s, "I" * len(s)))
+    # the lemma's worst case: five substitutions leave exactly two of the seven 8-row pieces intact, and the
+    # segment boundary falls between those two -- only the overlap behind a segment keeps the pair together
+    for i in range(300):
+        ad = list(rnd.choice(f))
+        keep = sorted(rnd.sample(range(7), 2))
+        for pc in range(7):
+            if pc not in keep:
+                q = 8 * pc + rnd.randrange(8)
+                ad[q] = rnd.choice([c for c in "ACGT" if c != ad[q]])
+        ad = "".join(ad)
+        edge = rnd.choice([1024, 2048, 3072])
+        start = edge - 8 * keep[0] - rnd.randint(1, 8 * (keep[1] - keep[0]))
+        n = rnd.choice([edge + 200, edge + 1500, 4500])
+        body = [rnd.choice("ACGT") for _ in range(n)]
+        body[start:start + len(ad)] = list(ad)
+        sq = "".join(body)
+        if rnd.random() < 0.5:
+            sq = sq.translate(comp)[::-1]
+        recs.append(("w%d" % i, sq, "I" * len(sq)))
+    rs = synth.from_records(recs)
+    rec0, _ = _compare(H.m13_rounds(), rs)
+    assert int((rec0["adapter"][700:] >= 0).sum()) >= 290       # the constructed occurrences are found
+    # the flank scan instead of the seeds must agree as well (same windows, by a different route)
+    m0a, m1a, *_ = H.run_hostsim(H.m13_rounds(), rs)
+    m0b, m1b, *_ = H.run_hostsim(H.m13_rounds(), rs, filter_mode=1 | 4)
+    assert H.diff_matches(m0a, m0b)[1] == 0 and H.diff_matches(m1a, m1b)[1] == 0
+
+
 def test_no_rc_and_other_thresholds():
     rs = synth.generate(1500, 300, 600, seed=5)
     for e, ov, rc in [(0.1, 3, 0), (0.2, 5, 1), (0.0, 3, 1), (0.05, 10, 1), (0.15, 1, 1), (3, 3, 1)]:
