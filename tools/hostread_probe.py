@@ -35,3 +35,16 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 print("beside 4 GiB of cudaMemcpy H2D: kernel reads 480/608 at %.1f GB/s useful; both done in %.1f ms = %.1f GB/s total useful"
       % (g, dt * 1e3, (4 * n + 3 * (n // 608) * 480) / dt / 1e9))
+# SM-driven host reads while the copy engine moves data the OTHER way (D2H) -- the traffic pattern of an e2e
+# leg in which pack_kernel and emit_kernel read their inputs in place and only the FASTQ text is copied back
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+with torch.cuda.stream(s2):
+    for _ in range(4):
+        b.copy_(d, non_blocking=True)
+g = L.orc_probe_hostread(0, a.data_ptr(), n, 4096, 4096)
+t1 = time.perf_counter() - t0
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+print("beside 4 GiB of cudaMemcpy D2H: kernel reads contiguously at %.1f GB/s (probe returned after %.1f ms); the D2H copies took %.1f ms = %.1f GB/s"
+      % (g, t1 * 1e3, dt * 1e3, 4 * n / dt / 1e9))
