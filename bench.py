@@ -86,6 +86,9 @@ def parse_args():
     ap.add_argument("--qual-copy", action="store_true",
                     help="e2e leg: copy the quality strings to the device whole instead of letting the emit kernel "
                          "read what it needs of them from the pinned host buffer (orc_params.qual_zero_copy)")
+    ap.add_argument("--e2e-text", action="store_true",
+                    help="e2e leg: the bins come back as plain FASTQ text instead of gzip members coded on the device "
+                         "(orc_params.emit_gzip); without this flag the plain-text variant is reported beside it as e2e_text")
     ap.add_argument("--resident", type=int, default=2,
                     help="batches resident in HBM whose steps are in flight together on their own streams (device-resident leg)")
     ap.add_argument("--oracle-sample", type=int, default=32768, help="reads of one shard per rank checked against the oracle (config 5)")
@@ -296,7 +299,7 @@ def split_subbatches(E, synth, rs, n_sub):
     return subs, per
 
 
-def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches, S=4, zero_copy=True):
+def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches, S=4, zero_copy=True, gzip=False):
     """`steps` steps through orc_submit/orc_wait with host buffers; step k streams the sub-batches of
     step_batches[k % len(step_batches)] over S slots.  -> (seconds, h2d bytes per step, d2h bytes per step,
     reads, cumulative counts, bytes of h2d that the emit kernel read in place).
@@ -308,7 +311,7 @@ def run_e2e(E, rounds, device, step_batches, steps, barrier, drop, want_matches,
     eng = E.Engine(rounds, device=device, max_reads=per,
                    max_bytes=max(int(x.seq.shape[0]) for sb in step_batches for x in sb) + 64,
                    max_name_bytes=max(int(x.names.shape[0]) for sb in step_batches for x in sb) + 64, n_slots=S,
-                   emit_fastq=True, want_matches=want_matches, drop_bins=drop, qual_zero_copy=zero_copy)
+                   emit_fastq=True, want_matches=want_matches, drop_bins=drop, qual_zero_copy=zero_copy, emit_gzip=gzip)
     h2d = sum(int(x.seq.nbytes + (0 if zero_copy else x.qual.nbytes) + x.offsets.nbytes + x.lengths.nbytes +
                   x.names.nbytes + x.name_offsets.nbytes) for x in step_batches[0])
     state = {"inflight": [], "k": 0, "reads": 0, "d2h": 0, "in_place": 0, "warm": True}
@@ -637,24 +640,36 @@ def main():
             step_batches = [split_subbatches(E, synth, hb, max(1, args.sub_batches))[0] for hb in host_batches]
             e_steps = steps if full else max(2, min(steps, 5))
             zc = not args.qual_copy
-            secs, h2d, d2h, n_done, counts, in_place = run_e2e(E, rounds, local_rank, step_batches, e_steps, barrier, drop,
-                                                               want_matches=False, zero_copy=zc)
-            te = torch.tensor([secs], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            assert n_done == e_steps * reads, (n_done, e_steps, reads)
-            out["e2e"] = {"value": (reads * world * e_steps) / float(te.item()), "unit": UNIT,
-                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
-                          "ms_per_step": 1e3 * float(te.item()) / e_steps,
-                          "note": "each step streamed as %d sub-batches over 4 slots/streams (copies overlap kernels); "
-                                  "pipeline fill and drain are inside the timed region; output = the FASTQ text of the "
-                                  "bins the reference script keeps (02:107-119: no unknown, no SP27_009..012) + bin id "
-                                  "and trimmed length per read; match records off" % len(step_batches[0]) +
-                                  ("; the quality strings are NOT copied to the device: the emit kernel reads the trimmed "
-                                   "qualities of the kept reads in place from the pinned host buffer (orc_params."
-                                   "qual_zero_copy), %d of the h2d bytes per step" % in_place if zc else
-                                   "; quality strings copied to the device whole (--qual-copy)"),
-                          "h2d_in_place_bytes_per_step": in_place}
+
+            def e2e_leg(gz):
+                secs, h2d, d2h, n_done, counts, in_place = run_e2e(E, rounds, local_rank, step_batches, e_steps, barrier, drop,
+                                                                   want_matches=False, zero_copy=zc, gzip=gz)
+                te = torch.tensor([secs], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+                assert n_done == e_steps * reads, (n_done, e_steps, reads)
+                return counts, {
+                    "value": (reads * world * e_steps) / float(te.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
+                    "ms_per_step": 1e3 * float(te.item()) / e_steps,
+                    "output": "gzip members" if gz else "FASTQ text",
+                    "note": "each step streamed as %d sub-batches over 4 slots/streams (copies overlap kernels); "
+                            "pipeline fill and drain are inside the timed region; output = the bins the reference "
+                            "script keeps (02:107-119: no unknown, no SP27_009..012) + bin id and trimmed length per "
+                            "read; match records off" % len(step_batches[0]) +
+                            ("; every bin of a sub-batch comes back as one gzip member coded on the device (orc_params."
+                             "emit_gzip, csrc/orc_gz.cuh: what 02:64-72 / 02:94-102 leave on disk are .fastq.gz files), "
+                             "only the compressed bytes cross PCIe" if gz else "; the bins come back as FASTQ text") +
+                            ("; the quality strings are NOT copied to the device: the emit kernel reads the trimmed "
+                             "qualities of the kept reads in place from the pinned host buffer (orc_params."
+                             "qual_zero_copy), %d of the h2d bytes per step" % in_place if zc else
+                             "; quality strings copied to the device whole (--qual-copy)"),
+                    "h2d_in_place_bytes_per_step": in_place}
+
+            counts, out["e2e"] = e2e_leg(not args.e2e_text)
+            if not args.e2e_text and full:
+                counts_t, out["e2e_text"] = e2e_leg(False)
+                assert np.array_equal(counts, counts_t)
             out["counts"] = counts
         else:
             out["e2e"] = None
@@ -796,6 +811,8 @@ def main():
             "verify_open": "parity unpinned: no real cutadapt 4.9 here; SURVEY VERIFY-1..15 stay open until "
                            "tests/test_cutadapt_diff.py runs somewhere (it skips without cutadapt)",
         }
+        if main_cfg.get("e2e_text") is not None:
+            line["e2e_text"] = main_cfg["e2e_text"]
         line.update(extra)
         emit(line)
     if world > 1:

@@ -82,6 +82,14 @@ typedef struct orc_params {
                                        page-locked (orc_host_alloc, cudaHostAlloc/cudaHostRegister, torch pin_memory) and
                                        its allocation must extend 64 bytes beyond qual + n_bytes (16-byte loads over-read);
                                        a batch whose qual buffer is not page-locked is copied as before */
+    int32_t emit_gzip;              /* 1 = with emit_fastq, every bin of a batch comes back as ONE gzip member (what
+                                       02:64-72 / 02:94-102 leave on disk are .fastq.gz files): orc_result.fastq then holds
+                                       the members back to back, bin_offsets their byte ranges (an empty bin has an empty
+                                       range), fastq_bytes their total.  A member is a single dynamic-Huffman DEFLATE block
+                                       of literals, coded on the device (csrc/orc_gz.cuh), with the "OC" size subfield
+                                       orc_reader_* uses to inflate members in parallel; appending the members of successive
+                                       batches to a bin's file gives a valid .fastq.gz.  Only the compressed bytes cross
+                                       PCIe */
 } orc_params;
 
 /*
@@ -129,7 +137,8 @@ typedef struct orc_result {
     const uint32_t *out_len;        /* [n_reads] length of the trimmed read */
     const uint64_t *bin_counts;     /* [n_bins] reads of this batch per bin */
     const uint64_t *bin_offsets;    /* [n_bins + 1] byte ranges of the bins inside fastq */
-    const uint8_t *fastq;           /* bin-major FASTQ text, input order kept inside a bin */
+    const uint8_t *fastq;           /* bin-major FASTQ text, input order kept inside a bin (orc_params.emit_gzip: that
+                                       text as one gzip member per bin) */
     uint64_t fastq_bytes;
 } orc_result;
 
@@ -164,6 +173,8 @@ typedef struct orc_timings {
      * emit_kernel starts, emit_kernel ends, D2H copies end (0 where that part did not run) -- the timeline of a
      * pipelined orc_submit()/orc_wait() loop over several slots */
     float timeline_ms[5];
+    float gzip_ms;                  /* emit_gzip: the bins' FASTQ text -> gzip members (0 if off) */
+    uint64_t gzip_bytes;            /* emit_gzip: bytes of the members of this batch */
 } orc_timings;
 
 orc_ctx *orc_create(const orc_params *params, char *err, size_t err_len);
@@ -265,6 +276,10 @@ orc_writer *orc_writer_open(const char *const *paths, int n_bins, int level, int
 int orc_writer_set_index(orc_writer *w, int on);
 size_t orc_empty_gzip_member(uint8_t *out, size_t cap, int level);
 int64_t orc_writer_write(orc_writer *w, const uint8_t *fastq, const uint64_t *bin_offsets);
+/* the same for a batch that comes back as gzip members (orc_params.emit_gzip): members = orc_result.fastq,
+ * member_offsets = orc_result.bin_offsets.  A .gz bin file receives its member as it is (no host deflate), a
+ * plain file the inflated text. */
+int64_t orc_writer_write_members(orc_writer *w, const uint8_t *members, const uint64_t *member_offsets);
 int orc_writer_wait(orc_writer *w, int64_t ticket);
 const char *orc_writer_error(orc_writer *w);
 int orc_writer_close(orc_writer *w, uint64_t *bytes_per_bin);

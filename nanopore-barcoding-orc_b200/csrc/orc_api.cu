@@ -18,6 +18,7 @@
 #include "../../include/orcdemux.h"
 
 #include "orc_kernels.cuh"
+#include "orc_gz.cuh"
 #include "orc_synth.cuh"
 #include "orc_table.h"
 
@@ -29,10 +30,11 @@ static_assert(sizeof(Task) == 32, "Task layout");
 static_assert(sizeof(PairResult) == 32, "PairResult layout");
 static_assert(sizeof(WinList) == 32, "WinList layout");
 static_assert(ORC_MAX_ADAPTERS == MAX_AD, "adapter limit");
+static_assert(MAX_BINS_GZ == MAX_BINS, "bins of the gzip encoder");
 
 namespace {
 
-enum { EV_START = 0, EV_H2D, EV_PACK, EV_TRIG0, EV_SCAN0, EV_RES0, EV_TRIG1, EV_SCAN1, EV_RES1, EV_BIN, EV_EMIT, EV_HDR, EV_END, EV_T0, EV_T1, EV_COUNT };
+enum { EV_START = 0, EV_H2D, EV_PACK, EV_TRIG0, EV_SCAN0, EV_RES0, EV_TRIG1, EV_SCAN1, EV_RES1, EV_BIN, EV_EMIT, EV_HDR, EV_END, EV_T0, EV_T1, EV_GZ, EV_COUNT };
 // d_counters: 16 per-round counters, then for round r and ordering o (0: reads by length, 1: items by
 // window columns) a histogram and a cursor array of SORT_BUCKETS words each
 constexpr size_t N_COUNTERS = 16 + 2 * 2 * 2 * (size_t)SORT_BUCKETS;
@@ -86,6 +88,13 @@ struct Slot {
     uint64_t *h_bin_counts = nullptr, *h_bin_offsets = nullptr;
     unsigned long long *h_cells = nullptr;
     uint8_t *h_fastq = nullptr;
+    // orc_params.emit_gzip (orc_gz.cuh): the bins of the batch as gzip members
+    uint8_t *d_gz = nullptr;
+    GzTable *d_gz_table = nullptr;
+    unsigned long long *d_gz_hist = nullptr;
+    uint32_t *d_gz_chunk_base = nullptr, *d_gz_chunk_bits = nullptr, *d_gz_chunk_crc = nullptr, *d_gz_member_crc = nullptr;
+    uint64_t *d_gz_chunk_bitoff = nullptr, *d_gz_member_bits = nullptr, *d_gz_member_bytes = nullptr, *d_gz_offsets = nullptr;
+    uint64_t *h_gz_offsets = nullptr;
     uint32_t n_launches = 0;                 // own kernels of the last orc_launch()
     size_t cap_pairs = 0;                    // entries of d_tasks / d_results (see alloc_slot)
     cudaEvent_t ev[EV_COUNT] = {};
@@ -97,7 +106,8 @@ struct Slot {
 struct orc_ctx {
     int device = 0;
     int n_rounds = 1, n_slots = 1, n_bins = 1, sm_count = 148;
-    int emit_fastq = 1, want_matches = 1, qual_zero_copy = 0;
+    int emit_fastq = 1, want_matches = 1, qual_zero_copy = 0, emit_gzip = 0;
+    uint64_t gz_cap = 0, gz_max_chunks = 0;  // bytes of a slot's gzip arena, chunks of its text at most
     int emit_zc_blocks = 8;                  // emit_kernel blocks per SM when it reads the qualities from host memory (measured: 8 > 4 > 2 > 1)
     uint32_t max_reads = 0;
     uint64_t max_bytes = 0, max_name_bytes = 0, fastq_cap = 0;
@@ -209,6 +219,26 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
         CK(dalloc(&s.d_name_offsets, R + 1));
         CK(dalloc(&s.d_name_lengths, R));
         CK(dalloc(&s.d_fastq, (size_t)ctx->fastq_cap));
+        if (ctx->emit_gzip) {
+            CK(dalloc(&s.d_gz, (size_t)ctx->gz_cap));
+            CK(dalloc(&s.d_gz_table, 1));
+            CK(dalloc(&s.d_gz_hist, 256));
+            CK(dalloc(&s.d_gz_chunk_base, (size_t)ctx->n_bins + 1));
+            CK(dalloc(&s.d_gz_chunk_bits, (size_t)ctx->gz_max_chunks));
+            CK(dalloc(&s.d_gz_chunk_crc, (size_t)ctx->gz_max_chunks));
+            CK(dalloc(&s.d_gz_chunk_bitoff, (size_t)ctx->gz_max_chunks));
+            CK(dalloc(&s.d_gz_member_bits, (size_t)ctx->n_bins));
+            CK(dalloc(&s.d_gz_member_bytes, (size_t)ctx->n_bins));
+            CK(dalloc(&s.d_gz_member_crc, (size_t)ctx->n_bins));
+            CK(dalloc(&s.d_gz_offsets, (size_t)ctx->n_bins + 1));
+            CK(halloc(&s.h_gz_offsets, (size_t)ctx->n_bins + 1));
+            GzTable *T = new GzTable();
+            memset(T, 0, sizeof(GzTable));
+            gz_fill_crc_tables(*T);
+            const cudaError_t e = cudaMemcpy(s.d_gz_table, T, sizeof(GzTable), cudaMemcpyHostToDevice);
+            delete T;
+            CK(e);
+        }
         // h_fastq (page-locked, as large as the device arena) is allocated by the first orc_wait() that has
         // text to fetch: slots that are only ever launched (device-resident shards) never pay for it
     }
@@ -218,6 +248,9 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
 static void free_slot(Slot &s)
 {
     cudaFree(s.d_seq); cudaFree(s.d_qual); cudaFree(s.d_names); cudaFree(s.d_fastq);
+    cudaFree(s.d_gz); cudaFree(s.d_gz_table); cudaFree(s.d_gz_hist); cudaFree(s.d_gz_chunk_base); cudaFree(s.d_gz_chunk_bits);
+    cudaFree(s.d_gz_chunk_crc); cudaFree(s.d_gz_chunk_bitoff); cudaFree(s.d_gz_member_bits); cudaFree(s.d_gz_member_bytes);
+    cudaFree(s.d_gz_member_crc); cudaFree(s.d_gz_offsets); cudaFreeHost(s.h_gz_offsets);
     cudaFree(s.d_codes_alloc); cudaFree(s.d_offsets); cudaFree(s.d_name_offsets); cudaFree(s.d_dest);
     cudaFree(s.d_lengths); cudaFree(s.d_qual_offsets); cudaFree(s.d_name_lengths);
     for (int i = 0; i < 3; i++) cudaFree(s.d_views[i]);
@@ -268,6 +301,7 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     ctx->emit_fastq = p->emit_fastq ? 1 : 0;
     ctx->want_matches = p->want_matches ? 1 : 0;
     ctx->qual_zero_copy = p->qual_zero_copy ? 1 : 0;
+    ctx->emit_gzip = (p->emit_gzip && p->emit_fastq) ? 1 : 0;
     if (const char *e = getenv("ORC_EMIT_ZC_BLOCKS")) ctx->emit_zc_blocks = std::min(8, std::max(1, atoi(e)));
     ctx->max_reads = p->max_reads;
     ctx->max_bytes = (p->max_bytes + 63) & ~63ull;
@@ -305,6 +339,14 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         }
     ctx->total_counts.assign((size_t)ctx->n_bins, 0);
     ctx->fastq_cap = ctx->max_name_bytes + 2 * ctx->max_bytes + 16ull * ctx->max_reads + 64;
+    // literals-only Huffman coding never needs much more than 8 bits per byte; frame and block header per member
+    ctx->gz_cap = (ctx->fastq_cap + ctx->fastq_cap / 32 + 256ull * (uint64_t)ctx->n_bins + 64 + 15) & ~15ull;
+    ctx->gz_max_chunks = ctx->fastq_cap / GZ_CHUNK + (uint64_t)ctx->n_bins + 2;
+    if (ctx->emit_gzip && ctx->gz_cap >= (1ull << 32)) {
+        // a member's "OC" size field and its ISIZE are 32 bits wide
+        ctx->err = "emit_gzip needs batches under 4 GiB of FASTQ text (smaller max_bytes)";
+        return ORC_EINVAL;
+    }
     for (int r = 0; r < p->n_rounds; r++) {
         CK(dalloc(&ctx->d_tab[r], 1));
         CK(cudaMemcpy(ctx->d_tab[r], &ctx->h_tab[r], sizeof(RoundTable), cudaMemcpyHostToDevice));
@@ -777,6 +819,26 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
                                                        s.d_fastq); nl++;
     }
     CK(cudaEventRecord(s.ev[EV_EMIT], st));
+    if (n && s.has_names && ctx->emit_gzip) {
+        // the bins as gzip members (orc_gz.cuh): histogram -> the batch's Huffman code -> bits and CRC per
+        // 512-byte chunk -> per member: bit offsets, CRC, size -> where the members go -> the codes
+        const int nb = ctx->n_bins;
+        const uint64_t *total = s.d_bin_offsets + nb;
+        CK(cudaMemsetAsync(s.d_gz_hist, 0, 256 * sizeof(unsigned long long), st));
+        gz_hist_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(s.d_fastq, total, s.d_gz_hist); nl++;
+        gz_table_kernel<<<1, 32, 0, st>>>(s.d_gz_hist, s.d_gz_table, nb, s.d_bin_offsets, s.d_gz_chunk_base); nl++;
+        gz_measure_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
+                                                            s.d_gz_chunk_bits, s.d_gz_chunk_crc); nl++;
+        gz_member_kernel<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
+                                                               s.d_gz_chunk_bits, s.d_gz_chunk_crc, s.d_gz_chunk_bitoff,
+                                                               s.d_gz_member_bits, s.d_gz_member_crc, s.d_gz_member_bytes); nl++;
+        gz_offsets_kernel<<<1, 32, 0, st>>>(nb, s.d_gz_member_bytes, s.d_gz_offsets); nl++;
+        gz_zero_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(s.d_gz_offsets, nb, ctx->gz_cap, reinterpret_cast<uint4 *>(s.d_gz)); nl++;
+        gz_encode_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
+                                                           s.d_gz_chunk_bitoff, s.d_gz_member_bits, s.d_gz_member_crc,
+                                                           s.d_gz_member_bytes, s.d_gz_offsets, ctx->gz_cap, s.d_gz); nl++;
+    }
+    CK(cudaEventRecord(s.ev[EV_GZ], st));
     CK(cudaGetLastError());
     s.n_launches = nl;
     s.state = SLOT_LAUNCHED;
@@ -797,6 +859,8 @@ extern "C" int orc_download(orc_ctx *ctx, int slot)
     CK(cudaMemcpyAsync(s.h_bin_offsets, s.d_bin_offsets, sizeof(uint64_t) * (ctx->n_bins + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, st));
+    if (ctx->emit_gzip && n && s.has_names)
+        CK(cudaMemcpyAsync(s.h_gz_offsets, s.d_gz_offsets, sizeof(uint64_t) * (ctx->n_bins + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_HDR], st));
     if (n) {
         CK(cudaMemcpyAsync(s.h_bin, s.d_bin, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
@@ -866,10 +930,12 @@ extern "C" int orc_wait(orc_ctx *ctx, int slot, orc_result *out)
             CK(cudaEventSynchronize(s.ev[EV_HDR]));
         }
     }
-    const uint64_t fq = s.has_names ? s.h_bin_offsets[ctx->n_bins] : 0;
-    if (fq > ctx->fastq_cap) { ctx->err = "internal: FASTQ output exceeds its arena"; return ORC_ECAPACITY; }
-    if (fq && !s.h_fastq) CK(halloc(&s.h_fastq, (size_t)ctx->fastq_cap));
-    if (fq) CK(cudaMemcpyAsync(s.h_fastq, s.d_fastq, fq, cudaMemcpyDeviceToHost, s.stream));
+    const bool gz = ctx->emit_gzip && s.has_names && s.n_reads;     // the bins come back as gzip members
+    if (s.has_names && s.h_bin_offsets[ctx->n_bins] > ctx->fastq_cap) { ctx->err = "internal: FASTQ output exceeds its arena"; return ORC_ECAPACITY; }
+    const uint64_t fq = !s.has_names ? 0 : gz ? s.h_gz_offsets[ctx->n_bins] : s.h_bin_offsets[ctx->n_bins];
+    if (gz && fq > ctx->gz_cap) { ctx->err = "internal: gzip output exceeds its arena"; return ORC_ECAPACITY; }
+    if (fq && !s.h_fastq) CK(halloc(&s.h_fastq, (size_t)std::max(ctx->fastq_cap, ctx->emit_gzip ? ctx->gz_cap : 0)));
+    if (fq) CK(cudaMemcpyAsync(s.h_fastq, gz ? s.d_gz : s.d_fastq, fq, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.ev[EV_END], s.stream));
     CK(cudaStreamSynchronize(s.stream));
     s.did_d2h = true;
@@ -883,7 +949,7 @@ extern "C" int orc_wait(orc_ctx *ctx, int slot, orc_result *out)
         out->bin = s.h_bin;
         out->out_len = s.h_out_len;
         out->bin_counts = s.h_bin_counts;
-        out->bin_offsets = s.h_bin_offsets;
+        out->bin_offsets = gz ? s.h_gz_offsets : s.h_bin_offsets;
         out->fastq = s.h_fastq;
         out->fastq_bytes = fq;
     }
@@ -910,9 +976,10 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     CK(el(EV_SCAN1, EV_RES1, &t->resolve_ms[1]));
     CK(el(EV_RES1, EV_BIN, &t->bin_ms));
     CK(el(EV_BIN, EV_EMIT, &t->emit_ms));
-    CK(el(EV_H2D, EV_EMIT, &t->total_ms));
+    CK(el(EV_EMIT, EV_GZ, &t->gzip_ms));
+    CK(el(EV_H2D, EV_GZ, &t->total_ms));
     if (s.did_h2d) CK(el(EV_START, EV_H2D, &t->h2d_ms));
-    if (s.did_d2h) CK(el(EV_EMIT, EV_END, &t->d2h_ms));
+    if (s.did_d2h) CK(el(EV_GZ, EV_END, &t->d2h_ms));
     {
         auto at = [&](int e, float *dst) -> cudaError_t { return cudaEventElapsedTime(dst, ctx->ev_ref, s.ev[e]); };
         if (s.did_h2d) CK(at(EV_START, &t->timeline_ms[0]));
@@ -974,6 +1041,8 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     }
     t->pack_bytes = s.n_bytes + s.n_bytes / 2;
     t->emit_bytes = 2 * emit_bytes;    // every FASTQ byte is read once and written once
+    if (ctx->emit_gzip && s.n_reads && s.has_names)
+        CK(cudaMemcpy(&t->gzip_bytes, s.d_gz_offsets + ctx->n_bins, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return ORC_OK;
 }
 

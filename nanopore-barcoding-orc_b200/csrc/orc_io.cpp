@@ -484,6 +484,7 @@ struct Chunk {
     uint8_t *out = nullptr;         // deflated member (or nullptr for plain files: src is copied)
     size_t out_len = 0;
     bool done = false;
+    bool member = false;            // src is a finished gzip member (orc_writer_write_members)
 };
 
 struct BinFile {
@@ -570,6 +571,29 @@ struct orc_writer {
         return true;
     }
 
+    // a member of orc_writer_write_members() headed for a plain (not .gz) file
+    static bool inflate_member(Chunk *c, std::string &why)
+    {
+        if (c->len < 18) { why = "gzip member too short"; return false; }
+        uint32_t isize = 0;
+        for (int i = 0; i < 4; i++) isize |= (uint32_t)c->src[c->len - 4 + i] << (8 * i);
+        c->out = (uint8_t *)malloc(isize ? isize : 1);
+        if (!c->out) { why = "out of memory"; return false; }
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, 15 + 16) != Z_OK) { why = "inflateInit2 failed"; return false; }
+        zs.next_in = const_cast<Bytef *>(c->src);
+        zs.avail_in = (uInt)c->len;
+        zs.next_out = c->out;
+        zs.avail_out = (uInt)isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        const bool ok = rc == Z_STREAM_END && zs.avail_out == 0;
+        inflateEnd(&zs);
+        if (!ok) { why = "gzip member does not inflate to its ISIZE"; return false; }
+        c->out_len = isize;
+        return true;
+    }
+
     static bool write_all(int fd, const uint8_t *p, size_t n)
     {
         while (n) {
@@ -598,7 +622,9 @@ struct orc_writer {
             lk.unlock();
             std::string why;
             bool ok = true;
-            if (bf.gz) {
+            if (c->member && !bf.gz) {
+                ok = inflate_member(c, why);
+            } else if (bf.gz && !c->member) {
                 ok = deflate_chunk(zs, zs_ready, c, why);
             } else {
                 c->out = (uint8_t *)malloc(c->len ? c->len : 1);
@@ -726,6 +752,43 @@ extern "C" int64_t orc_writer_write(orc_writer *w, const uint8_t *fastq, const u
             w->pending.back()++;
             w->unwritten++;
         }
+    }
+    w->cv_task.notify_all();
+    return ticket;
+}
+
+// The bins of one batch as finished gzip members (orc_params.emit_gzip: orc_result.fastq / bin_offsets): a .gz
+// bin file receives its member as it is, a plain one the inflated text.  A member's text is under 4 GiB (its
+// ISIZE counts the bytes of the bin).
+extern "C" int64_t orc_writer_write_members(orc_writer *w, const uint8_t *members, const uint64_t *member_offsets)
+{
+    if (!w || !member_offsets) return ORC_EINVAL;
+    std::lock_guard<std::mutex> lk(w->mu);
+    if (w->error) return w->error;
+    for (size_t b = 0; b < w->bins.size(); b++) {
+        const uint64_t lo = member_offsets[b], hi = member_offsets[b + 1];
+        if (hi < lo || (hi > lo && (!members || hi - lo < 28 || members[lo] != 0x1f || members[lo + 1] != 0x8b))) return ORC_EINVAL;
+    }
+    int64_t ticket = w->next_ticket++;
+    w->pending.push_back(0);
+    for (size_t b = 0; b < w->bins.size(); b++) {
+        BinFile &bf = w->bins[b];
+        if (bf.fd < 0) continue;
+        const uint64_t lo = member_offsets[b], hi = member_offsets[b + 1];
+        if (hi <= lo) continue;
+        uint32_t isize = 0;
+        for (int i = 0; i < 4; i++) isize |= (uint32_t)members[hi - 4 + i] << (8 * i);
+        bf.bytes_in += isize;
+        Chunk *c = new Chunk();
+        c->bin = (int)b;
+        c->src = members + lo;
+        c->len = (size_t)(hi - lo);
+        c->ticket = ticket;
+        c->member = true;
+        bf.q.push_back(c);
+        w->tasks.push_back(c);
+        w->pending.back()++;
+        w->unwritten++;
     }
     w->cv_task.notify_all();
     return ticket;

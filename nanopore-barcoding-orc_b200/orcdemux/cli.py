@@ -396,7 +396,7 @@ def _stream(reader, eng, writers, slots, on_result, rank=0, world=1):
     def drain(slot, tb):
         res = eng.wait(slot, copy=False)
         on_result(res, tb)
-        tickets[slot] = writers.write_batch(res)
+        tickets[slot] = writers.write_batch(res, members=eng.emit_gzip)
 
     k = 0
     for batch_id, tb in enumerate(reader):
@@ -513,6 +513,9 @@ def run_two_round(args: List[str], device=0) -> int:
     ap.add_argument("--no-gzip", action="store_true")
     ap.add_argument("-j", type=int, default=8)
     ap.add_argument("--compression-level", type=int, default=1, help="gzip level of the bin files (cutadapt 4.x default: 1)")
+    ap.add_argument("--host-gzip", action="store_true",
+                    help="deflate the bin files with zlib on the host threads; default: the GPU codes every bin of a "
+                         "batch as a gzip member (dynamic Huffman, literals only) and only those bytes come back")
     ap.add_argument("--gpus", type=int, default=1,
                     help="GPUs of this node to shard the batches over, one process each (the same happens under "
                          "torchrun, whose RANK / WORLD_SIZE are honoured)")
@@ -566,7 +569,8 @@ def run_two_round(args: List[str], device=0) -> int:
 
     try:
         with E.Engine(rounds, device=device, max_reads=max_reads, max_bytes=max_bytes, n_slots=slots,
-                      emit_fastq=True, want_matches=False, drop_bins=drop) as eng:
+                      emit_fastq=True, want_matches=False, drop_bins=drop,
+                      emit_gzip=not (a.no_gzip or a.host_gzip)) as eng:
             try:
                 _stream(reader, eng, writers, slots, on_result, rank, world)
             finally:

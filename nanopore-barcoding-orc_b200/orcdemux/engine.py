@@ -90,8 +90,10 @@ class Engine:
     def __init__(self, rounds: Sequence[Round], device: int = 0, max_reads: int = 1 << 20,
                  max_bytes: int = 1 << 30, max_name_bytes: int = 0, n_slots: int = 2,
                  emit_fastq: bool = True, want_matches: bool = True,
-                 drop_bins: Optional[np.ndarray] = None, qual_zero_copy: bool = False):
-        """qual_zero_copy: the qualities of a submitted batch stay in the caller's page-locked buffer and the
+                 drop_bins: Optional[np.ndarray] = None, qual_zero_copy: bool = False, emit_gzip: bool = False):
+        """emit_gzip: every bin of a batch comes back as one gzip member made on the device
+        (orc_params.emit_gzip): BatchResult.fastq holds the members, bin_offsets their byte ranges.
+        qual_zero_copy: the qualities of a submitted batch stay in the caller's page-locked buffer and the
         emit kernel reads what it needs of them over PCIe (orc_params.qual_zero_copy; buffers from
         pinned_empty() / pin_readset() qualify: page-locked, 64 bytes of slack behind the data)."""
         if not 1 <= len(rounds) <= _lib.ORC_MAX_ROUNDS:
@@ -130,6 +132,8 @@ class Engine:
         p.emit_fastq = int(emit_fastq)
         p.want_matches = int(want_matches)
         p.qual_zero_copy = int(qual_zero_copy)
+        p.emit_gzip = int(emit_gzip)
+        self.emit_gzip = bool(emit_gzip and emit_fastq)
         if drop_bins is not None:
             d = np.ascontiguousarray(drop_bins, dtype=np.uint8)
             if d.shape[0] != self.n_bins:
@@ -264,7 +268,8 @@ class Engine:
                     kernel_ms=[{nm: float(t.kernel_ms[r][i]) for i, nm in enumerate(_lib.KERNEL_NAMES)}
                                for r in range(len(self.rounds))],
                     window_columns=list(t.window_columns), cells_2b=list(t.cells_2b),
-                    n_pairs_2b=list(t.n_pairs_2b), n_tasks_wide=list(t.n_tasks_wide), timeline_ms=list(t.timeline_ms))
+                    n_pairs_2b=list(t.n_pairs_2b), n_tasks_wide=list(t.n_tasks_wide), timeline_ms=list(t.timeline_ms),
+                    gzip_ms=t.gzip_ms, gzip_bytes=t.gzip_bytes)
 
     def timer_start(self, slot: int = 0):
         self._check(self._L.orc_timer_start(self._ctx, slot), "orc_timer_start")

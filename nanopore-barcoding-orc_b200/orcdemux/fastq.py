@@ -144,12 +144,14 @@ class BinWriters:
         self._live = {}
         self.bytes_written = [0] * len(paths)
 
-    def write_batch(self, result) -> int:
+    def write_batch(self, result, members: bool = False) -> int:
         """Queue every bin's FASTQ text of one BatchResult; returns a ticket.  The result's
-        buffers must not be reused (no new submit on its slot) before wait(ticket)."""
+        buffers must not be reused (no new submit on its slot) before wait(ticket).
+        members: the result comes from an Engine(emit_gzip=True): its bins are finished gzip members, which
+        .gz files receive as they are (orc_writer_write_members)."""
         off = np.ascontiguousarray(result.bin_offsets, dtype=np.uint64)
-        t = int(self._L.orc_writer_write(self._w, result.fastq.ctypes.data if result.fastq.size else None,
-                                         off.ctypes.data))
+        put = self._L.orc_writer_write_members if members else self._L.orc_writer_write
+        t = int(put(self._w, result.fastq.ctypes.data if result.fastq.size else None, off.ctypes.data))
         if t < 0:
             raise OSError("orc_writer_write: " + self._L.orc_writer_error(self._w).decode(errors="replace"))
         self._live[t] = (result, off)

@@ -30,7 +30,7 @@ EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_sub
            "orc_reader_open", "orc_reader_next", "orc_reader_release", "orc_reader_error", "orc_reader_close",
            "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close",
            "orc_edit_distances", "orc_synth", "orc_resident", "orc_export",
-           "orc_reader_open_threads", "orc_writer_set_index", "orc_empty_gzip_member", "orc_span_begin", "orc_span_end", "orc_probe_hostread"]
+           "orc_reader_open_threads", "orc_writer_set_index", "orc_empty_gzip_member", "orc_span_begin", "orc_span_end", "orc_probe_hostread", "orc_writer_write_members"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -50,7 +50,7 @@ class Params(C.Structure):
                 ("rounds", RoundParams * ORC_MAX_ROUNDS),
                 ("max_reads", C.c_uint32), ("max_bytes", C.c_uint64), ("max_name_bytes", C.c_uint64),
                 ("n_slots", C.c_int32), ("emit_fastq", C.c_int32), ("want_matches", C.c_int32),
-                ("drop_bins", C.c_void_p), ("qual_zero_copy", C.c_int32)]
+                ("drop_bins", C.c_void_p), ("qual_zero_copy", C.c_int32), ("emit_gzip", C.c_int32)]
 
 
 class Batch(C.Structure):
@@ -78,7 +78,7 @@ class Timings(C.Structure):
                 ("kernel_ms", (C.c_float * ORC_N_KERNELS) * ORC_MAX_ROUNDS),
                 ("window_columns", C.c_uint64 * ORC_MAX_ROUNDS), ("cells_2b", C.c_uint64 * ORC_MAX_ROUNDS),
                 ("n_pairs_2b", C.c_uint32 * ORC_MAX_ROUNDS), ("n_tasks_wide", C.c_uint32 * ORC_MAX_ROUNDS),
-                ("timeline_ms", C.c_float * 5)]
+                ("timeline_ms", C.c_float * 5), ("gzip_ms", C.c_float), ("gzip_bytes", C.c_uint64)]
 
 
 class TextBatchC(C.Structure):
@@ -159,6 +159,8 @@ def load():
     L.orc_writer_open.restype = C.c_void_p
     L.orc_writer_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_writer_write.restype = C.c_int64
+    L.orc_writer_write_members.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_writer_write_members.restype = C.c_int64
     L.orc_writer_wait.argtypes = [C.c_void_p, C.c_int64]
     L.orc_writer_wait.restype = C.c_int
     L.orc_writer_error.argtypes = [C.c_void_p]

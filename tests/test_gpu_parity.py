@@ -188,6 +188,62 @@ def test_qualities_read_in_place_from_pinned_host_memory():
             eng.close()
 
 
+def test_bins_as_gzip_members_made_on_the_device(tmp_path):
+    """orc_params.emit_gzip: every bin of a batch comes back as one gzip member coded by the gz_* kernels
+    (csrc/orc_gz.cuh).  zlib must inflate every member to exactly the bytes the plain path emits for that bin
+    (which _check compares with the oracle), CRC-32 / ISIZE / the "OC" size field must hold, with dropped bins,
+    empty bins, an empty batch, two slots in flight -- and the writer must put the members into .gz files as
+    they are and into plain files inflated."""
+    import gzip
+    import zlib
+    from test_gz import check_members
+    from orcdemux import fastq as F
+    rs = synth.generate(20000, 300, 900, seed=33)
+    ref = _check(rs)
+    drop = np.zeros(169, dtype=np.uint8)
+    drop[0::13] = 1
+    drop[:13] = 1
+    plain = _engine(rs.n_reads, rs.seq.shape[0], drop_bins=drop)
+    gz = _engine(rs.n_reads, rs.seq.shape[0], drop_bins=drop, emit_gzip=True, n_slots=2, want_matches=False)
+    try:
+        want = plain.run(rs)
+        got = gz.run(rs)
+        pieces = [want.fastq[int(want.bin_offsets[b]):int(want.bin_offsets[b + 1])].tobytes() for b in range(169)]
+        assert sum(len(p) for p in pieces) > 0 and any(len(p) == 0 for p in pieces)
+        check_members(got.fastq.tobytes(), got.bin_offsets, pieces)
+        assert np.array_equal(got.bin, want.bin) and np.array_equal(got.bin_counts, want.bin_counts)
+        t = gz.timings(0)
+        assert t["gzip_bytes"] == got.fastq.shape[0] and t["gzip_ms"] > 0
+        assert got.fastq.shape[0] < 0.62 * want.fastq.shape[0]
+        # the writer: members as they are into .gz files, inflated into plain ones
+        paths = [None if drop[b] else str(tmp_path / ("bin%03d.fastq%s" % (b, ".gz" if b % 2 else ""))) for b in range(169)]
+        w = F.BinWriters(paths, 1, threads=4)
+        t0 = w.write_batch(got, members=True)
+        w.wait(t0)
+        # a second batch (slot 1) appended to the same files
+        sub = synth.generate(5000, 300, 900, seed=34)
+        gz.submit(1, sub)
+        got2 = gz.wait(1)
+        want2 = plain.run(sub)
+        pieces2 = [want2.fastq[int(want2.bin_offsets[b]):int(want2.bin_offsets[b + 1])].tobytes() for b in range(169)]
+        check_members(got2.fastq.tobytes(), got2.bin_offsets, pieces2)
+        w.wait(w.write_batch(got2, members=True))
+        w.close()
+        for b, path in enumerate(paths):
+            if path is None:
+                continue
+            data = gzip.open(path, "rb").read() if path.endswith(".gz") else open(path, "rb").read()
+            assert data == pieces[b] + pieces2[b], path
+        assert w.bytes_written[14] == len(pieces[14]) + len(pieces2[14])
+        # an empty batch: no members at all
+        e = gz.run(synth.from_records([]))
+        assert e.fastq.shape[0] == 0 and int(e.bin_offsets[-1]) == 0
+    finally:
+        plain.close()
+        gz.close()
+    assert ref.n_reads == rs.n_reads
+
+
 def test_config2_full_size_every_read():
     """BASELINE configs[1] at its full size (1 Mi COI reads, seed 1002): the oracle on EVERY read -- all eight
     match fields of both rounds, trimmed length, bin, and the bytes of all 169 bins -- plus the

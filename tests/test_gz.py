@@ -1,0 +1,116 @@
+"""The device-side gzip encoder (csrc/orc_gz.cuh), run on the CPU through tests/gzsim.cpp: every member must be
+what zlib and Python's gzip module accept, decompress to the bin's bytes, and carry the library's "OC" size
+field (orc_io.cpp finds members by it).  The `-m gpu` test in tests/test_gpu_parity.py repeats the round trip
+on the kernels' output."""
+import ctypes as C
+import gzip
+import os
+import random
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import helpers as H
+from orcdemux import synth
+
+_SO = os.path.join(H.ROOT, "tests", "_build", "libgzsim.so")
+_SRC = os.path.join(H.ROOT, "tests", "gzsim.cpp")
+_HDR = os.path.join(H.PKG, "csrc", "orc_gz.cuh")
+
+
+def _lib():
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(_SRC), os.path.getmtime(_HDR)):
+        subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-o", _SO, _SRC], check=True)
+    L = C.CDLL(_SO)
+    L.gzsim_compress.restype = C.c_longlong
+    L.gzsim_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    return L
+
+
+def check_members(gz: bytes, gz_offsets, pieces):
+    """Every member: header with the size field, zlib inflates it to the piece, CRC and ISIZE hold."""
+    for m, piece in enumerate(pieces):
+        a, b = int(gz_offsets[m]), int(gz_offsets[m + 1])
+        if len(piece) == 0:
+            assert a == b
+            continue
+        mem = gz[a:b]
+        assert mem[:4] == b"\x1f\x8b\x08\x04" and mem[10:16] == b"\x08\x00OC\x04\x00"
+        assert int.from_bytes(mem[16:20], "little") == b - a
+        d = zlib.decompressobj(31)
+        out = d.decompress(mem)
+        assert d.eof and d.unused_data == b"" and out == piece, "member %d" % m
+        assert int.from_bytes(mem[-8:-4], "little") == zlib.crc32(piece)
+        assert int.from_bytes(mem[-4:], "little") == len(piece) & 0xFFFFFFFF
+    whole = b"".join(gz[int(gz_offsets[m]):int(gz_offsets[m + 1])] for m in range(len(pieces)))
+    assert gzip.decompress(whole) == b"".join(pieces) if whole else True      # members concatenate to a gzip file
+
+
+def _compress(pieces):
+    L = _lib()
+    text = np.frombuffer(b"".join(pieces) + b"\0" * 64, dtype=np.uint8).copy()
+    offs = np.zeros(len(pieces) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(p) for p in pieces])
+    cap = (int(offs[-1]) * 2 + 4096 * (len(pieces) + 1) + 3) & ~3
+    out = np.zeros(cap, dtype=np.uint8)
+    gzo = np.zeros(len(pieces) + 1, dtype=np.uint64)
+    lens = np.zeros(257, dtype=np.uint8)
+    n = L.gzsim_compress(text.ctypes.data, offs.ctypes.data, len(pieces), out.ctypes.data, cap, gzo.ctypes.data, lens.ctypes.data)
+    assert n >= 0 and n == int(gzo[-1])
+    return out[:n].tobytes(), gzo, lens
+
+
+def test_fastq_bins_round_trip_through_zlib():
+    rs = synth.generate(3000, 300, 900, seed=11)
+    text = rs.to_fastq_bytes()
+    rnd = random.Random(5)
+    cuts = sorted(rnd.sample(range(1, len(text)), 40))
+    cuts = [0] + cuts[:10] + [cuts[10]] * 3 + cuts[10:] + [len(text)]         # a few empty bins among them
+    pieces = [text[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    gz, gzo, lens = _compress(pieces)
+    check_members(gz, gzo, pieces)
+    assert lens[ord("A")] <= 4 and lens[256] >= 1                            # bases get short codes
+    ratio = len(gz) / len(text)
+    zl = len(zlib.compress(text, 5)) / len(text)
+    assert ratio < 0.62 and ratio < zl * 1.12, (ratio, zl)                   # literals-only costs little on FASTQ
+
+
+def test_sizes_around_chunk_and_word_boundaries():
+    rnd = random.Random(7)
+    pieces = []
+    for n in [1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 500, 511, 512, 513, 1023, 1024, 1025, 1536, 4096, 4097, 10000]:
+        pieces.append(bytes(rnd.choice(b"ACGTN@+\n!#%I") for _ in range(n)))
+        pieces.append(b"")
+    gz, gzo, _ = _compress(pieces)
+    check_members(gz, gzo, pieces)
+
+
+def test_all_byte_values_and_long_codes():
+    rnd = random.Random(9)
+    # every byte value, with weights that fall by a factor of two each: a Huffman tree deeper than 15 before
+    # the limit is applied
+    data = bytearray()
+    for b in range(256):
+        data += bytes([b]) * max(1, (1 << 22) >> min(b, 22))
+    rnd.shuffle(data)
+    data = bytes(data)
+    pieces = [data[:100000], data[100000:100007], data[100007:]]
+    gz, gzo, lens = _compress(pieces)
+    assert int(lens.max()) <= 15 and int((lens[:256] > 0).sum()) == 256
+    check_members(gz, gzo, pieces)
+    # a batch with a single distinct byte, and an empty batch
+    gz, gzo, lens = _compress([b"A" * 5000, b"", b"A"])
+    check_members(gz, gzo, [b"A" * 5000, b"", b"A"])
+    gz, gzo, lens = _compress([b"", b""])
+    assert len(gz) == 0
+
+
+def test_one_large_member():
+    rnd = np.random.default_rng(3)
+    data = rnd.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=3_000_000).tobytes()
+    gz, gzo, _ = _compress([data])
+    check_members(gz, gzo, [data])
+    assert len(gz) < 0.29 * len(data)                                         # two bits per base (one of the four takes three: the end-of-block code needs a leaf)
