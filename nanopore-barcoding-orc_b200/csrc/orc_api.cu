@@ -92,8 +92,8 @@ struct Slot {
     uint8_t *d_gz = nullptr;
     GzTable *d_gz_table = nullptr;
     unsigned long long *d_gz_hist = nullptr;
-    uint32_t *d_gz_chunk_base = nullptr, *d_gz_chunk_bits = nullptr, *d_gz_chunk_crc = nullptr, *d_gz_member_crc = nullptr;
-    uint64_t *d_gz_chunk_bitoff = nullptr, *d_gz_member_bits = nullptr, *d_gz_member_bytes = nullptr, *d_gz_offsets = nullptr;
+    uint32_t *d_gz_chunk_base = nullptr, *d_gz_chunk_local = nullptr, *d_gz_tile_bits = nullptr, *d_gz_member_crc = nullptr;
+    uint64_t *d_gz_tile_off = nullptr, *d_gz_member_pos = nullptr, *d_gz_member_bits = nullptr, *d_gz_member_bytes = nullptr, *d_gz_offsets = nullptr;
     uint64_t *h_gz_offsets = nullptr;
     uint32_t n_launches = 0;                 // own kernels of the last orc_launch()
     size_t cap_pairs = 0;                    // entries of d_tasks / d_results (see alloc_slot)
@@ -224,9 +224,10 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
             CK(dalloc(&s.d_gz_table, 1));
             CK(dalloc(&s.d_gz_hist, 256));
             CK(dalloc(&s.d_gz_chunk_base, (size_t)ctx->n_bins + 1));
-            CK(dalloc(&s.d_gz_chunk_bits, (size_t)ctx->gz_max_chunks));
-            CK(dalloc(&s.d_gz_chunk_crc, (size_t)ctx->gz_max_chunks));
-            CK(dalloc(&s.d_gz_chunk_bitoff, (size_t)ctx->gz_max_chunks));
+            CK(dalloc(&s.d_gz_chunk_local, (size_t)ctx->gz_max_chunks));
+            CK(dalloc(&s.d_gz_tile_bits, (size_t)ctx->gz_max_chunks / GZ_TILE + 2));
+            CK(dalloc(&s.d_gz_tile_off, (size_t)ctx->gz_max_chunks / GZ_TILE + 2));
+            CK(dalloc(&s.d_gz_member_pos, (size_t)ctx->n_bins));
             CK(dalloc(&s.d_gz_member_bits, (size_t)ctx->n_bins));
             CK(dalloc(&s.d_gz_member_bytes, (size_t)ctx->n_bins));
             CK(dalloc(&s.d_gz_member_crc, (size_t)ctx->n_bins));
@@ -248,8 +249,8 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
 static void free_slot(Slot &s)
 {
     cudaFree(s.d_seq); cudaFree(s.d_qual); cudaFree(s.d_names); cudaFree(s.d_fastq);
-    cudaFree(s.d_gz); cudaFree(s.d_gz_table); cudaFree(s.d_gz_hist); cudaFree(s.d_gz_chunk_base); cudaFree(s.d_gz_chunk_bits);
-    cudaFree(s.d_gz_chunk_crc); cudaFree(s.d_gz_chunk_bitoff); cudaFree(s.d_gz_member_bits); cudaFree(s.d_gz_member_bytes);
+    cudaFree(s.d_gz); cudaFree(s.d_gz_table); cudaFree(s.d_gz_hist); cudaFree(s.d_gz_chunk_base); cudaFree(s.d_gz_chunk_local);
+    cudaFree(s.d_gz_tile_bits); cudaFree(s.d_gz_tile_off); cudaFree(s.d_gz_member_pos); cudaFree(s.d_gz_member_bits); cudaFree(s.d_gz_member_bytes);
     cudaFree(s.d_gz_member_crc); cudaFree(s.d_gz_offsets); cudaFreeHost(s.h_gz_offsets);
     cudaFree(s.d_codes_alloc); cudaFree(s.d_offsets); cudaFree(s.d_name_offsets); cudaFree(s.d_dest);
     cudaFree(s.d_lengths); cudaFree(s.d_qual_offsets); cudaFree(s.d_name_lengths);
@@ -820,23 +821,24 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     }
     CK(cudaEventRecord(s.ev[EV_EMIT], st));
     if (n && s.has_names && ctx->emit_gzip) {
-        // the bins as gzip members (orc_gz.cuh): histogram -> the batch's Huffman code -> bits and CRC per
-        // 512-byte chunk -> per member: bit offsets, CRC, size -> where the members go -> the codes
+        // the bins as gzip members (orc_gz.cuh): sampled histogram -> the batch's Huffman code -> bits per chunk
+        // (prefix sums per tile) and the members' CRCs -> where tiles and members start -> the codes
         const int nb = ctx->n_bins;
         const uint64_t *total = s.d_bin_offsets + nb;
         CK(cudaMemsetAsync(s.d_gz_hist, 0, 256 * sizeof(unsigned long long), st));
-        gz_hist_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(s.d_fastq, total, s.d_gz_hist); nl++;
-        gz_table_kernel<<<1, 32, 0, st>>>(s.d_gz_hist, s.d_gz_table, nb, s.d_bin_offsets, s.d_gz_chunk_base); nl++;
-        gz_measure_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
-                                                            s.d_gz_chunk_bits, s.d_gz_chunk_crc); nl++;
-        gz_member_kernel<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
-                                                               s.d_gz_chunk_bits, s.d_gz_chunk_crc, s.d_gz_chunk_bitoff,
-                                                               s.d_gz_member_bits, s.d_gz_member_crc, s.d_gz_member_bytes); nl++;
-        gz_offsets_kernel<<<1, 32, 0, st>>>(nb, s.d_gz_member_bytes, s.d_gz_offsets); nl++;
+        CK(cudaMemsetAsync(s.d_gz_member_crc, 0, (size_t)nb * sizeof(uint32_t), st));
+        gz_hist_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(s.d_fastq, total, s.d_gz_hist); nl++;
+        gz_table_kernel<<<1, 512, 0, st>>>(s.d_gz_hist, s.d_gz_table, nb, s.d_bin_offsets, s.d_gz_chunk_base); nl++;
+        gz_measure_kernel<<<ctx->sm_count * 8, GZ_TILE, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
+                                                                s.d_gz_chunk_local, s.d_gz_tile_bits, s.d_gz_member_crc); nl++;
+        gz_layout_kernel<<<1, 1024, 0, st>>>(s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table, s.d_gz_chunk_local,
+                                             s.d_gz_tile_bits, s.d_gz_tile_off, s.d_gz_member_pos, s.d_gz_member_bits,
+                                             s.d_gz_member_bytes, s.d_gz_offsets); nl++;
         gz_zero_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(s.d_gz_offsets, nb, ctx->gz_cap, reinterpret_cast<uint4 *>(s.d_gz)); nl++;
-        gz_encode_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
-                                                           s.d_gz_chunk_bitoff, s.d_gz_member_bits, s.d_gz_member_crc,
-                                                           s.d_gz_member_bytes, s.d_gz_offsets, ctx->gz_cap, s.d_gz); nl++;
+        gz_encode_kernel<<<ctx->sm_count * 16, 128, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
+                                                           s.d_gz_chunk_local, s.d_gz_tile_off, s.d_gz_member_pos,
+                                                           s.d_gz_member_bits, s.d_gz_member_crc, s.d_gz_member_bytes,
+                                                           s.d_gz_offsets, ctx->gz_cap, s.d_gz); nl++;
     }
     CK(cudaEventRecord(s.ev[EV_GZ], st));
     CK(cudaGetLastError());

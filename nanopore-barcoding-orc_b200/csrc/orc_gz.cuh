@@ -8,10 +8,11 @@
 //
 // A member holds ONE dynamic-Huffman DEFLATE block of literals only (no LZ77 matches: bases and qualities of
 // nanopore reads hardly repeat, zlib's own matches gain a few per cent on them): the code is built per batch
-// from the byte histogram of the batch's whole FASTQ text, so every member of the batch carries the same block
+// from a sampled byte histogram of the batch's FASTQ text, so every member of the batch carries the same block
 // header.  Encoding is then a table look-up per byte; where a byte's bits go is a prefix sum of code lengths,
-// taken per 512-byte chunk, per member, per batch.  CRC-32 of a member = the chunks' CRCs folded with the
-// "append n zero bytes" operator (zlib's crc32_combine), whose matrices for n = 2^k come from the host.
+// taken per chunk of GZ_CHUNK bytes (one thread), per tile of GZ_TILE chunks (one block), per batch.  CRC-32 of a
+// member = the xor of its chunks' CRCs, each moved past the bytes behind it with the "append n zero bytes"
+// operator (zlib's crc32_combine; its matrices for n = 2^k come from the host).
 //
 // Everything that computes is ORC_HD so that tests/gzsim.cpp can run the same code on the CPU and hand the
 // members to zlib (tests/test_gz.py); the kernels at the end only distribute the work.
@@ -22,7 +23,11 @@
 
 namespace orc {
 
-constexpr int GZ_CHUNK = 512;               // bytes of text per encoding thread (chunks are 512-aligned in the text)
+#ifndef GZ_CHUNK_BYTES
+#define GZ_CHUNK_BYTES 1024
+#endif
+constexpr int GZ_CHUNK = GZ_CHUNK_BYTES;    // bytes of text per encoding thread (chunks are GZ_CHUNK-aligned in the text)
+constexpr int GZ_TILE = 256;                // chunks per block-wide prefix sum (gz_measure_kernel)
 constexpr int GZ_HEADER_BYTES = 20;         // 10 + XLEN + "OC" subfield with the member's size (orc_io.cpp GZ_SIZE_AT)
 constexpr int GZ_TRAILER_BYTES = 8;         // CRC-32, ISIZE
 constexpr int GZ_HDR_WORDS = 44;            // block header: 3 + 5 + 5 + 4 + 19 * 3 + 258 * 5 = 1364 bits at most
@@ -35,7 +40,9 @@ struct GzTable {
     uint8_t pad_;
     uint32_t hdr_nbits;
     uint32_t hdr[GZ_HDR_WORDS];     // BFINAL BTYPE HLIT HDIST HCLEN, the code-length code, the 258 code lengths
-    uint32_t crc_tab[256];          // CRC-32 (0xEDB88320) byte table
+    uint32_t sym[257];              // code[b] | len[b] << 16: one look-up per byte in the kernels
+    uint32_t crc_tab[4][256];       // CRC-32 (0xEDB88320): [0] the byte table, [k] = [0] moved past k zero bytes
+                                    // (slicing-by-4: four independent look-ups per 32-bit word)
     uint32_t crc_pow[32][32];       // crc_pow[k]: the operator "append 2^k zero bytes" on a CRC, as a 32 x 32 bit matrix
 };
 
@@ -52,8 +59,10 @@ inline void gz_fill_crc_tables(GzTable &T)
     for (uint32_t n = 0; n < 256; n++) {
         uint32_t c = n;
         for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-        T.crc_tab[n] = c;
+        T.crc_tab[0][n] = c;
     }
+    for (uint32_t n = 0; n < 256; n++)
+        for (int k = 1; k < 4; k++) T.crc_tab[k][n] = T.crc_tab[0][T.crc_tab[k - 1][n] & 255u] ^ (T.crc_tab[k - 1][n] >> 8);
     // the operator for one zero BIT, squared three times = one zero byte, squared on = 2^k bytes
     uint32_t odd[32], even[32];
     odd[0] = 0xEDB88320u;
@@ -95,96 +104,163 @@ ORC_HD void gz_put(uint32_t *w, uint32_t &pos, uint32_t val, int nbits)
     pos += (uint32_t)nbits;
 }
 
-// The batch's code from its byte histogram (one thread: at most 257 symbols).  Code lengths are limited to 15
-// bits by flattening the weights and building again, which keeps the code complete (inflate rejects codes
-// that are not).  At least two symbols get a code, so that the code is never a single one-bit code.
-struct GzWork {             // scratch of gz_build_table (shared memory on the device)
-    unsigned long long w[257], nw[2 * 257];
-    int parent[2 * 257], leaf_of[257], depth[257];
-    uint8_t alive[2 * 257];
+// The batch's code from a byte histogram.  The histogram is a SAMPLE of the text (gz_hist_kernel), so every byte
+// value gets a code whether it was seen or not: weight = count + 1.  The unseen ones end up with 14- or 15-bit
+// codes and take about 0.01 of the code space; any table made this way codes any text, and the code is complete
+// (inflate rejects codes that are not).
+struct GzWork {             // scratch of the table build (shared memory on the device)
+    unsigned long long w[257];          // weights by symbol
+    unsigned long long nw[2 * 257];     // weights by node: the leaves in ascending order, then the inner nodes as made
+    int order[257];                     // symbols by ascending (weight, symbol)
+    int parent[2 * 257], node_depth[2 * 257], depth[257];
+    int num[16], next_code[16], first_rank[16];     // codes per length, first code of a length, see gz_build_from_sorted
+    uint32_t hdr[GZ_HDR_WORDS];
 };
-ORC_HD void gz_build_table(const unsigned long long *hist, GzTable &T, GzWork &K)
+// weight of symbol s: sampled count + 1 (end of block: 1)
+ORC_HD unsigned long long gz_weight(const unsigned long long *hist, int s) { return s < 256 ? hist[s] + 1ull : 1ull; }
+// where symbol s stands among the 257 by ascending (weight, symbol): one thread per symbol on the device
+ORC_HD int gz_rank(const unsigned long long *w, int s)
 {
-    unsigned long long *w = K.w;
-    for (int b = 0; b < 256; b++) w[b] = hist[b];
-    w[GZ_EOB] = 1;
-    {
-        int n = 0, first = -1;
-        for (int b = 0; b < 256; b++) if (w[b]) { n++; if (first < 0) first = b; }
-        if (n == 0) w['\n'] = 1;            // an empty batch still has a valid (unused) code: EOB and one literal
-    }
-    int *depth = K.depth;
-    for (;;) {
-        // Huffman by repeated selection of the two lightest nodes (n <= 257: a few ten thousand steps at worst)
-        unsigned long long *nw = K.nw;
-        int *parent = K.parent, *leaf_of = K.leaf_of;
-        uint8_t *alive = K.alive;
-        int n_nodes = 0;
-        for (int s = 0; s < 257; s++) {
-            leaf_of[s] = -1;
-            if (w[s]) { leaf_of[s] = n_nodes; nw[n_nodes] = w[s]; parent[n_nodes] = -1; alive[n_nodes] = 1; n_nodes++; }
-        }
-        int n_alive = n_nodes;
-        while (n_alive > 1) {
-            int a = -1, b = -1;
-            for (int i = 0; i < n_nodes; i++) {
-                if (!alive[i]) continue;
-                if (a < 0 || nw[i] < nw[a]) { b = a; a = i; }
-                else if (b < 0 || nw[i] < nw[b]) b = i;
-            }
-            nw[n_nodes] = nw[a] + nw[b];
-            parent[n_nodes] = -1;
-            alive[n_nodes] = 1;
-            parent[a] = parent[b] = n_nodes;
-            alive[a] = alive[b] = 0;
-            n_nodes++;
-            n_alive--;
-        }
-        int deepest = 0;
-        for (int s = 0; s < 257; s++) {
-            depth[s] = 0;
-            if (leaf_of[s] < 0) continue;
-            int d = 0;
-            for (int i = leaf_of[s]; parent[i] >= 0; i = parent[i]) d++;
-            depth[s] = d;
-            if (d > deepest) deepest = d;
-        }
-        if (deepest <= 15) break;
-        for (int s = 0; s < 257; s++) if (w[s]) w[s] = (w[s] >> 2) + 1;     // flatter weights, shallower tree
-    }
-    // canonical codes (RFC 1951, 3.2.2)
-    int bl_count[16], next_code[16];
-    for (int i = 0; i < 16; i++) bl_count[i] = 0;
-    for (int s = 0; s < 257; s++) if (depth[s]) bl_count[depth[s]]++;
-    int code = 0;
-    next_code[0] = 0;
-    for (int bits = 1; bits < 16; bits++) { code = (code + bl_count[bits - 1]) << 1; next_code[bits] = code; }
-    for (int s = 0; s < 257; s++) {
-        T.len[s] = (uint8_t)depth[s];
-        T.code[s] = depth[s] ? (uint16_t)gz_rev((uint32_t)next_code[depth[s]]++, depth[s]) : (uint16_t)0;
-    }
-    T.pad_ = 0;
-    // the block header.  The code-length code is a fixed complete code: the lengths 0..12 take four bits
-    // (codes 0..12), the lengths 13..15 and the three repeat symbols five bits (codes 26..31); the lengths are
-    // then written one by one, without the repeat symbols (about 140 bytes per member).
-    for (int i = 0; i < GZ_HDR_WORDS; i++) T.hdr[i] = 0;
-    uint32_t pos = 0;
-    gz_put(T.hdr, pos, 1u, 1);              // BFINAL
-    gz_put(T.hdr, pos, 2u, 2);              // BTYPE = dynamic Huffman
-    gz_put(T.hdr, pos, 0u, 5);              // HLIT: 257 literal/length codes
-    gz_put(T.hdr, pos, 0u, 5);              // HDIST: 1 distance code (of length 0: there are no matches)
-    gz_put(T.hdr, pos, 15u, 4);             // HCLEN: all 19 code-length codes
-    const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-    for (int i = 0; i < 19; i++) gz_put(T.hdr, pos, order[i] <= 12 ? 4u : 5u, 3);
-    for (int s = 0; s < 258; s++) {
-        const int v = s < 257 ? depth[s] : 0;       // s == 257: the distance code
-        if (v <= 12) gz_put(T.hdr, pos, gz_rev((uint32_t)v, 4), 4);
-        else gz_put(T.hdr, pos, gz_rev((uint32_t)(26 + (v - 13)), 5), 5);
-    }
-    T.hdr_nbits = pos;
+    int r = 0;
+    const unsigned long long ws = w[s];
+    for (int t = 0; t < 257; t++) r += (w[t] < ws || (w[t] == ws && t < s)) ? 1 : 0;
+    return r;
+}
+// or a 32-bit word (words of the output at the borders of a chunk are shared with its neighbours; so are the words
+// of the block header while the table is built)
+ORC_HD void gz_or(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    if (v) atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+ORC_HD void gz_or_bits(uint32_t *w, uint32_t pos, uint32_t val, int nbits)
+{
+    const uint32_t i = pos >> 5, sh = pos & 31u;
+    gz_or(w + i, val << sh);
+    if (sh + (uint32_t)nbits > 32u) gz_or(w + i + 1, val >> (32u - sh));
+}
+ORC_HD void gz_count(int *p)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, 1);
+#else
+    ++*p;
+#endif
 }
 
-// Chunk k of the member whose text is [start, end): the part of it inside the 512-aligned block k of the text
+// K.w and K.order filled.  Written for `nt` threads (tid = 0 .. nt-1) that meet at sync(): a block on the device,
+// one thread with a sync that does nothing on the host.  Huffman over the sorted leaves with two queues (the
+// inner nodes come out in ascending weight, so the two lightest nodes are always at the heads; this part is
+// serial), depths top-down.  Then only the NUMBER of codes of every length is kept: lengths above 15 count as 15,
+// and while the code is over-subscribed one 15-bit code is taken away and a shorter code is split into two longer
+// ones (which pays for one 15-bit code, as in zlib / miniz); the lengths go back to the symbols longest first in
+// ascending weight.  Canonical codes (RFC 1951, 3.2.2) and the block header: the code-length code is a fixed
+// complete code -- the lengths 0..12 take four bits (codes 0..12), the lengths 13..15 and the three repeat
+// symbols five bits (codes 26..31) -- and the lengths are written one by one, without the repeat symbols (about
+// 150 bytes per member).
+constexpr uint32_t GZ_HDR_FIXED_BITS = 3 + 5 + 5 + 4 + 19 * 3;
+struct GzNoSync { ORC_HD void operator()() const {} };
+#if defined(__CUDACC__)
+struct GzBlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+#endif
+template <typename Sync>
+ORC_HD void gz_build_from_sorted(GzTable &T, GzWork &K, int tid, int nt, Sync sync)
+{
+    const int n = 257;
+    int *num = K.num, *next_code = K.next_code, *depth = K.depth;
+    for (int i = tid; i < n; i += nt) K.nw[i] = K.w[K.order[i]];
+    for (int i = tid; i < GZ_HDR_WORDS; i += nt) K.hdr[i] = 0;
+    for (int l = tid; l < 16; l += nt) num[l] = 0;
+    sync();
+    if (tid == 0) {
+        unsigned long long *nw = K.nw;
+        int *parent = K.parent;
+        int leaf = 0, inner = n, made = n;              // heads of the two queues, next node to make
+        while (made < 2 * n - 1) {
+            int pick[2];
+            for (int j = 0; j < 2; j++) {
+                const bool take_leaf = leaf < n && (inner >= made || nw[leaf] <= nw[inner]);
+                pick[j] = take_leaf ? leaf++ : inner++;
+            }
+            nw[made] = nw[pick[0]] + nw[pick[1]];
+            parent[pick[0]] = parent[pick[1]] = made;
+            made++;
+        }
+        K.node_depth[2 * n - 2] = 0;
+        for (int i = 2 * n - 3; i >= n; i--) K.node_depth[i] = K.node_depth[parent[i]] + 1;
+    }
+    sync();
+    for (int i = tid; i < n; i += nt) {
+        const int d = K.node_depth[K.parent[i]] + 1;
+        gz_count(num + (d > 15 ? 15 : d));
+    }
+    sync();
+    if (tid == 0) {
+        uint32_t kraft = 0;                             // in units of 2^-15
+        for (int l = 1; l <= 15; l++) kraft += (uint32_t)num[l] << (15 - l);
+        while (kraft > (1u << 15)) {
+            num[15]--;
+            for (int l = 14; l >= 1; l--)
+                if (num[l]) { num[l]--; num[l + 1] += 2; break; }
+            kraft--;
+        }
+        // K.first_rank[l]: the first of the symbols, in ascending weight, that gets length l
+        int acc = 0;
+        for (int l = 15; l >= 1; l--) { K.first_rank[l] = acc; acc += num[l]; }
+        int code = 0;
+        next_code[0] = 0;
+        num[0] = 0;
+        for (int bits = 1; bits < 16; bits++) { code = (code + num[bits - 1]) << 1; next_code[bits] = code; }
+        uint32_t pos = 0;
+        gz_put(K.hdr, pos, 1u, 1);              // BFINAL
+        gz_put(K.hdr, pos, 2u, 2);              // BTYPE = dynamic Huffman
+        gz_put(K.hdr, pos, 0u, 5);              // HLIT: 257 literal/length codes
+        gz_put(K.hdr, pos, 0u, 5);              // HDIST: 1 distance code (of length 0: there are no matches)
+        gz_put(K.hdr, pos, 15u, 4);             // HCLEN: all 19 code-length codes
+        const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        for (int i = 0; i < 19; i++) gz_put(K.hdr, pos, order[i] <= 12 ? 4u : 5u, 3);
+    }
+    sync();
+    for (int i = tid; i < n; i += nt) {
+        int l = 15;
+        while (l > 1 && !(i >= K.first_rank[l] && i < K.first_rank[l] + num[l])) l--;
+        depth[K.order[i]] = l;
+    }
+    sync();
+    for (int s = tid; s < 258; s += nt) {
+        const int d = s < 257 ? depth[s] : 0;           // s == 257: the one distance code, unused
+        int same = 0;
+        uint32_t pos = GZ_HDR_FIXED_BITS;
+        for (int t = 0; t < s; t++) {
+            const int dt = depth[t];
+            same += dt == d ? 1 : 0;
+            pos += dt <= 12 ? 4u : 5u;
+        }
+        if (s < 257) {
+            const uint32_t c = gz_rev((uint32_t)(next_code[d] + same), d);
+            T.len[s] = (uint8_t)d;
+            T.code[s] = (uint16_t)c;
+            T.sym[s] = c | ((uint32_t)d << 16);
+        }
+        if (d <= 12) gz_or_bits(K.hdr, pos, gz_rev((uint32_t)d, 4), 4);
+        else gz_or_bits(K.hdr, pos, gz_rev((uint32_t)(26 + (d - 13)), 5), 5);
+        if (s == 257) { T.hdr_nbits = pos + 4u; T.pad_ = 0; }
+    }
+    sync();
+    for (int i = tid; i < GZ_HDR_WORDS; i += nt) T.hdr[i] = K.hdr[i];
+}
+// the whole build on one thread (host simulation)
+inline void gz_build_table(const unsigned long long *hist, GzTable &T, GzWork &K)
+{
+    for (int s = 0; s < 257; s++) K.w[s] = gz_weight(hist, s);
+    for (int s = 0; s < 257; s++) K.order[gz_rank(K.w, s)] = s;
+    gz_build_from_sorted(T, K, 0, 1, GzNoSync());
+}
+
+// Chunk k of the member whose text is [start, end): the part of it inside the GZ_CHUNK-aligned block k of the text
 // counted from the block that holds `start`.
 ORC_HD uint32_t gz_member_chunks(uint64_t start, uint64_t end)
 {
@@ -198,50 +274,84 @@ ORC_HD void gz_chunk_range(uint64_t start, uint64_t end, uint32_t k, uint64_t &l
     hi = a + GZ_CHUNK < end ? a + GZ_CHUNK : end;
 }
 
-// Bits the chunk's bytes take, and their CRC-32.
-ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint8_t *len,
-                             const uint32_t *crc_tab, uint32_t &bits, uint32_t &crc_out)
+// The histogram looks at one 16-byte vector of the text in GZ_SAMPLE (and at the tail behind the last vector).
+constexpr int GZ_SAMPLE = 16;
+
+#if defined(__CUDACC__)
+typedef uint4 gz_vec16;
+#else
+struct alignas(16) gz_vec16 { uint32_t x, y, z, w; };     // the host simulation's stand-in for uint4
+#endif
+
+// Bits the chunk's bytes take, and their CRC-32.  sym: GzTable.sym, crc_tab: GzTable.crc_tab (both in shared
+// memory on the device).  16 bytes at a time between the first and the last 16-byte boundary of the chunk (the
+// text starts at a 16-byte-aligned address).
+ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint32_t *sym,
+                             const uint32_t (*crc_tab)[256], uint32_t &bits, uint32_t &crc_out)
 {
     uint32_t nb = 0, crc = 0xFFFFFFFFu;
-    for (uint64_t p = lo; p < hi; p++) {
+    uint64_t p = lo;
+    for (; p < hi && (p & 15u); p++) {
         const uint8_t c = text[p];
-        nb += len[c];
-        crc = crc_tab[(crc ^ c) & 255u] ^ (crc >> 8);
+        nb += sym[c] >> 16;
+        crc = crc_tab[0][(crc ^ c) & 255u] ^ (crc >> 8);
+    }
+    for (; p + 16 <= hi; p += 16) {
+        const gz_vec16 q = *reinterpret_cast<const gz_vec16 *>(text + p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++) {
+            const uint32_t x = w[k];
+            nb += (sym[x & 255u] >> 16) + (sym[(x >> 8) & 255u] >> 16) + (sym[(x >> 16) & 255u] >> 16) + (sym[x >> 24] >> 16);
+            crc ^= x;
+            crc = crc_tab[3][crc & 255u] ^ crc_tab[2][(crc >> 8) & 255u] ^ crc_tab[1][(crc >> 16) & 255u] ^ crc_tab[0][crc >> 24];
+        }
+    }
+    for (; p < hi; p++) {
+        const uint8_t c = text[p];
+        nb += sym[c] >> 16;
+        crc = crc_tab[0][(crc ^ c) & 255u] ^ (crc >> 8);
     }
     bits = nb;
     crc_out = crc ^ 0xFFFFFFFFu;
 }
 
-// or a 32-bit word into the output (words at the borders of a chunk are shared with its neighbours)
-ORC_HD void gz_or(uint32_t *p, uint32_t v)
-{
-#if defined(__CUDA_ARCH__)
-    if (v) atomicOr(p, v);
-#else
-    *p |= v;
-#endif
-}
-
 // The chunk's bytes as codes, from bit `bit0` of the (zeroed) output on.
-ORC_HD void gz_chunk_encode(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint16_t *code,
-                            const uint8_t *len, uint64_t bit0, uint32_t *__restrict__ out)
+ORC_HD void gz_chunk_encode(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint32_t *sym,
+                            uint64_t bit0, uint32_t *__restrict__ out)
 {
     uint64_t wi = bit0 >> 5;
     uint32_t fill = (uint32_t)(bit0 & 31u);
     uint64_t acc = 0;
     bool first = true;          // the first word may hold bits of the chunk in front: or, do not store
-    for (uint64_t p = lo; p < hi; p++) {
-        const uint8_t c = text[p];
-        acc |= (uint64_t)code[c] << fill;
-        fill += len[c];
-        if (fill >= 32u) {
-            if (first) { gz_or(out + wi, (uint32_t)acc); first = false; }
-            else out[wi] = (uint32_t)acc;
-            wi++;
-            acc >>= 32;
-            fill -= 32u;
+    // fill < 32 whenever a word has been taken out; two codes add 30 bits at most, so acc holds them
+#define GZ_TAKE_WORD()                                                                  \
+    if (fill >= 32u) {                                                                  \
+        if (first) { gz_or(out + wi, (uint32_t)acc); first = false; }                   \
+        else out[wi] = (uint32_t)acc;                                                   \
+        wi++; acc >>= 32; fill -= 32u;                                                  \
+    }
+#define GZ_BYTE(c)                                                                      \
+    { const uint32_t e = sym[c]; acc |= (uint64_t)(e & 0xFFFFu) << fill; fill += e >> 16; }
+    uint64_t p = lo;
+    for (; p < hi && (p & 15u); p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD(); }
+    for (; p + 16 <= hi; p += 16) {
+        const gz_vec16 q = *reinterpret_cast<const gz_vec16 *>(text + p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++) {
+            const uint32_t x = w[k];
+            GZ_BYTE(x & 255u); GZ_BYTE((x >> 8) & 255u); GZ_TAKE_WORD();
+            GZ_BYTE((x >> 16) & 255u); GZ_BYTE(x >> 24); GZ_TAKE_WORD();
         }
     }
+    for (; p < hi; p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD(); }
+#undef GZ_BYTE
+#undef GZ_TAKE_WORD
     if (fill) gz_or(out + wi, (uint32_t)acc);
 }
 
@@ -289,40 +399,55 @@ ORC_HD void gz_member_frame(const GzTable &T, uint8_t *out_bytes, uint64_t membe
 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------ kernels
-// hist[b] += occurrences of byte b in text[0, *total)
+// hist[b] += occurrences of byte b in the sampled vectors of text[0, *total) (every GZ_SAMPLE-th 16-byte vector)
+// and in the tail behind the last whole vector
 __global__ void __launch_bounds__(256)
 gz_hist_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ total, unsigned long long *__restrict__ hist)
 {
-    __shared__ uint32_t s_h[256];
-    s_h[threadIdx.x] = 0;
+    __shared__ uint32_t s_h[8][256];            // one histogram per warp: fewer same-address atomics
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&s_h[0][0])[i] = 0;
     __syncthreads();
+    uint32_t *h = s_h[threadIdx.x >> 5];
     const uint64_t n16 = *total >> 4;
+    const uint64_t n_samples = (n16 + GZ_SAMPLE - 1) / GZ_SAMPLE;
     const uint4 *t4 = reinterpret_cast<const uint4 *>(text);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 v = t4[i];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = t4[i * GZ_SAMPLE];
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            atomicAdd(&s_h[w[k] & 255u], 1u); atomicAdd(&s_h[(w[k] >> 8) & 255u], 1u);
-            atomicAdd(&s_h[(w[k] >> 16) & 255u], 1u); atomicAdd(&s_h[w[k] >> 24], 1u);
+            atomicAdd(&h[w[k] & 255u], 1u); atomicAdd(&h[(w[k] >> 8) & 255u], 1u);
+            atomicAdd(&h[(w[k] >> 16) & 255u], 1u); atomicAdd(&h[w[k] >> 24], 1u);
         }
     }
     if (blockIdx.x == 0)
-        for (uint64_t p = (n16 << 4) + threadIdx.x; p < *total; p += blockDim.x) atomicAdd(&s_h[text[p]], 1u);
+        for (uint64_t p = (n16 << 4) + threadIdx.x; p < *total; p += blockDim.x) atomicAdd(&h[text[p]], 1u);
     __syncthreads();
-    if (s_h[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)s_h[threadIdx.x]);
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += s_h[k][threadIdx.x];
+    if (sum) atomicAdd(hist + threadIdx.x, (unsigned long long)sum);
 }
 
-// one thread: the code of the batch; chunk_base[m] = chunks of the members in front of member m
-__global__ void gz_table_kernel(const unsigned long long *__restrict__ hist, GzTable *__restrict__ T, int n_members,
-                                const uint64_t *__restrict__ bin_offsets, uint32_t *__restrict__ chunk_base)
+// one block: the code of the batch; chunk_base[m] = chunks of the members in front of member m
+__global__ void __launch_bounds__(512)
+gz_table_kernel(const unsigned long long *__restrict__ hist, GzTable *__restrict__ T, int n_members,
+                const uint64_t *__restrict__ bin_offsets, uint32_t *__restrict__ chunk_base)
 {
     __shared__ GzWork K;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    gz_build_table(hist, *T, K);
-    uint32_t acc = 0;
-    for (int m = 0; m < n_members; m++) { chunk_base[m] = acc; acc += gz_member_chunks(bin_offsets[m], bin_offsets[m + 1]); }
-    chunk_base[n_members] = acc;
+    __shared__ uint32_t s_chunks[MAX_BINS_GZ];
+    const int t = threadIdx.x;
+    if (t < 257) K.w[t] = gz_weight(hist, t);
+    for (int m = t; m < n_members; m += blockDim.x) s_chunks[m] = gz_member_chunks(bin_offsets[m], bin_offsets[m + 1]);
+    __syncthreads();
+    if (t < 257) K.order[gz_rank(K.w, t)] = t;
+    if (t == 257) {
+        uint32_t acc = 0;
+        for (int m = 0; m < n_members; m++) { chunk_base[m] = acc; acc += s_chunks[m]; }
+        chunk_base[n_members] = acc;
+    }
+    __syncthreads();
+    gz_build_from_sorted(*T, K, t, (int)blockDim.x, GzBlockSync());
 }
 
 __device__ __forceinline__ int gz_member_of(const uint32_t *s_base, int n_members, uint32_t c)
@@ -335,84 +460,116 @@ __device__ __forceinline__ int gz_member_of(const uint32_t *s_base, int n_member
     return lo;
 }
 
-// one thread per chunk: its bits and its CRC
-__global__ void __launch_bounds__(128)
+// exclusive prefix sum over the threads of a block (blockDim.x a multiple of 32, <= 1024); total: the block's sum
+template <typename V>
+__device__ __forceinline__ V gz_block_scan(V v, V *s_warp /* [33] */, V &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    V incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const V o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    __syncthreads();                    // s_warp may still be read from the scan before
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        V w = lane < n_warps ? s_warp[lane] : (V)0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const V o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        if (lane < n_warps) s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + incl - v;
+}
+
+// One thread per chunk, tiles of GZ_TILE chunks per block: the chunk's bits as an exclusive sum inside its tile
+// (chunk_local) and the tile's sum (tile_bits); the chunk's CRC moved to where the chunk stands in its member
+// (past the bytes behind it) and xor-ed into the member's CRC -- crc32_combine is linear, so the order in which
+// the chunks arrive does not matter.  member_crc must be zero before.
+__global__ void __launch_bounds__(GZ_TILE)
 gz_measure_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ bin_offsets, int n_members,
                   const uint32_t *__restrict__ chunk_base, const GzTable *__restrict__ T,
-                  uint32_t *__restrict__ chunk_bits, uint32_t *__restrict__ chunk_crc)
+                  uint32_t *__restrict__ chunk_local, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ member_crc)
 {
     __shared__ uint32_t s_base[MAX_BINS_GZ + 1];
-    __shared__ uint32_t s_crc[256];
-    __shared__ uint8_t s_len[257];
+    __shared__ uint32_t s_crc[4][256];
+    __shared__ uint32_t s_pow[32][32];
+    __shared__ uint32_t s_sym[257];
+    __shared__ uint32_t s_warp[33];
     for (int i = threadIdx.x; i <= n_members; i += blockDim.x) s_base[i] = chunk_base[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = T->crc_tab[i];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) s_len[i] = T->len[i];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_crc[0][0])[i] = (&T->crc_tab[0][0])[i];
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) (&s_pow[0][0])[i] = (&T->crc_pow[0][0])[i];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) s_sym[i] = T->sym[i];
     __syncthreads();
     const uint32_t n_chunks = s_base[n_members];
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
-        const int m = gz_member_of(s_base, n_members, c);
-        uint64_t lo, hi;
-        gz_chunk_range(bin_offsets[m], bin_offsets[m + 1], c - s_base[m], lo, hi);
-        uint32_t bits, crc;
-        gz_chunk_measure(text, lo, hi, s_len, s_crc, bits, crc);
-        chunk_bits[c] = bits;
-        chunk_crc[c] = crc;
+    const uint32_t n_tiles = (n_chunks + GZ_TILE - 1) / GZ_TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t c = tile * GZ_TILE + threadIdx.x;
+        uint32_t bits = 0;
+        if (c < n_chunks) {
+            const int m = gz_member_of(s_base, n_members, c);
+            const uint64_t end = bin_offsets[m + 1];
+            uint64_t lo, hi;
+            gz_chunk_range(bin_offsets[m], end, c - s_base[m], lo, hi);
+            uint32_t crc;
+            gz_chunk_measure(text, lo, hi, s_sym, s_crc, bits, crc);
+            const uint32_t moved = gz_crc_shift(s_pow, crc, end - hi);
+            if (moved) atomicXor(member_crc + m, moved);
+        }
+        uint32_t total;
+        const uint32_t before = gz_block_scan(bits, s_warp, total);
+        if (c < n_chunks) chunk_local[c] = before;
+        if (threadIdx.x == 0) tile_bits[tile] = total;
     }
 }
 
-// one warp per member: where its chunks' bits start (exclusive sums), its CRC, its size
-__global__ void __launch_bounds__(128)
-gz_member_kernel(const uint64_t *__restrict__ bin_offsets, int n_members, const uint32_t *__restrict__ chunk_base,
-                 const GzTable *__restrict__ T, const uint32_t *__restrict__ chunk_bits, const uint32_t *__restrict__ chunk_crc,
-                 uint64_t *__restrict__ chunk_bitoff, uint64_t *__restrict__ member_bits, uint32_t *__restrict__ member_crc,
-                 uint64_t *__restrict__ member_bytes)
+// One block: where the tiles' bits start (tile_off, exclusive; tile_off[n_tiles] = all bits), then per member
+// where its bits start in that count (member_pos), how many they are, its size as a gzip member, and where the
+// members go in the output (gz_offsets[n_members] = all of them).  A bin without text gets no member.
+__global__ void __launch_bounds__(1024)
+gz_layout_kernel(const uint64_t *__restrict__ bin_offsets, int n_members, const uint32_t *__restrict__ chunk_base,
+                 const GzTable *__restrict__ T, const uint32_t *__restrict__ chunk_local, const uint32_t *__restrict__ tile_bits,
+                 uint64_t *__restrict__ tile_off, uint64_t *__restrict__ member_pos, uint64_t *__restrict__ member_bits,
+                 uint64_t *__restrict__ member_bytes, uint64_t *__restrict__ gz_offsets)
 {
-    const int lane = threadIdx.x & 31;
-    const int m = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (m >= n_members) return;
-    const uint64_t start = bin_offsets[m], end = bin_offsets[m + 1];
-    const uint32_t c0 = chunk_base[m], n = chunk_base[m + 1] - c0;
-    if (n == 0) {
-        if (lane == 0) { member_bits[m] = 0; member_crc[m] = 0; member_bytes[m] = 0; }
-        return;
+    __shared__ unsigned long long s_warp[33];
+    __shared__ unsigned long long s_pos[MAX_BINS_GZ + 1];
+    const uint32_t n_chunks = chunk_base[n_members];
+    const uint32_t n_tiles = (n_chunks + GZ_TILE - 1) / GZ_TILE;
+    const uint32_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t t0 = min(n_tiles, threadIdx.x * per), t1 = min(n_tiles, t0 + per);
+    unsigned long long sum = 0;
+    for (uint32_t t = t0; t < t1; t++) sum += tile_bits[t];
+    unsigned long long all_bits;
+    unsigned long long run = gz_block_scan(sum, s_warp, all_bits);
+    for (uint32_t t = t0; t < t1; t++) { tile_off[t] = run; run += tile_bits[t]; }
+    if (threadIdx.x == 0) tile_off[n_tiles] = all_bits;
+    __syncthreads();                    // tile_off is read back below
+    for (int m = threadIdx.x; m <= n_members; m += blockDim.x) {
+        const uint32_t c = chunk_base[m];
+        s_pos[m] = (m < n_members && c < n_chunks) ? tile_off[c / GZ_TILE] + chunk_local[c] : all_bits;
     }
-    // lane l takes the chunks [l * per, (l + 1) * per): sums and CRC of its run, then the runs in order
-    const uint32_t per = (n + 31u) / 32u;
-    const uint32_t k0 = min(n, (uint32_t)lane * per), k1 = min(n, k0 + per);
-    unsigned long long sum = 0, bytes = 0;
-    uint32_t crc = 0;
-    for (uint32_t k = k0; k < k1; k++) {
-        uint64_t lo, hi;
-        gz_chunk_range(start, end, k, lo, hi);
-        sum += chunk_bits[c0 + k];
-        crc = gz_crc_shift(T->crc_pow, crc, hi - lo) ^ chunk_crc[c0 + k];
-        bytes += hi - lo;
+    __syncthreads();
+    unsigned long long bytes = 0;
+    const int m = threadIdx.x;          // n_members <= MAX_BINS_GZ <= blockDim.x
+    if (m < n_members) {
+        const unsigned long long bits = s_pos[m + 1] - s_pos[m];
+        bytes = bin_offsets[m + 1] > bin_offsets[m] ? gz_member_bytes(*T, bits) : 0ull;
+        member_pos[m] = s_pos[m];
+        member_bits[m] = bits;
+        member_bytes[m] = bytes;
     }
-    unsigned long long before = 0, total = 0;
-    uint32_t crc_all = 0;
-    for (int l = 0; l < 32; l++) {
-        const unsigned long long s_l = __shfl_sync(0xffffffffu, sum, l);
-        const unsigned long long b_l = __shfl_sync(0xffffffffu, bytes, l);
-        const uint32_t c_l = __shfl_sync(0xffffffffu, crc, l);
-        if (l < lane) before += s_l;
-        total += s_l;
-        if (lane == 0 && b_l) crc_all = gz_crc_shift(T->crc_pow, crc_all, b_l) ^ c_l;
-    }
-    unsigned long long run = before;
-    for (uint32_t k = k0; k < k1; k++) {
-        chunk_bitoff[c0 + k] = run;
-        run += chunk_bits[c0 + k];
-    }
-    if (lane == 0) { member_bits[m] = total; member_crc[m] = crc_all; member_bytes[m] = gz_member_bytes(*T, total); }
-}
-
-// one thread: where the members go (gz_offsets[n_members] = all of them)
-__global__ void gz_offsets_kernel(int n_members, const uint64_t *__restrict__ member_bytes, uint64_t *__restrict__ gz_offsets)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long acc = 0;
-    for (int m = 0; m < n_members; m++) { gz_offsets[m] = acc; acc += member_bytes[m]; }
-    gz_offsets[n_members] = acc;
+    unsigned long long all_bytes;
+    const unsigned long long off = gz_block_scan(bytes, s_warp, all_bytes);
+    if (m < n_members) gz_offsets[m] = off;
+    if (m == 0) gz_offsets[n_members] = all_bytes;
 }
 
 // zeroes out[0, gz_offsets[n_members]) rounded up to 16 bytes: everything below is written by OR
@@ -429,15 +586,15 @@ gz_zero_kernel(const uint64_t *__restrict__ gz_offsets, int n_members, uint64_t 
 __global__ void __launch_bounds__(128)
 gz_encode_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ bin_offsets, int n_members,
                  const uint32_t *__restrict__ chunk_base, const GzTable *__restrict__ T,
-                 const uint64_t *__restrict__ chunk_bitoff, const uint64_t *__restrict__ member_bits,
+                 const uint32_t *__restrict__ chunk_local, const uint64_t *__restrict__ tile_off,
+                 const uint64_t *__restrict__ member_pos, const uint64_t *__restrict__ member_bits,
                  const uint32_t *__restrict__ member_crc, const uint64_t *__restrict__ member_bytes,
                  const uint64_t *__restrict__ gz_offsets, uint64_t cap_bytes, uint8_t *__restrict__ out)
 {
     __shared__ uint32_t s_base[MAX_BINS_GZ + 1];
-    __shared__ uint16_t s_code[257];
-    __shared__ uint8_t s_len[257];
+    __shared__ uint32_t s_sym[257];
     for (int i = threadIdx.x; i <= n_members; i += blockDim.x) s_base[i] = chunk_base[i];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) { s_code[i] = T->code[i]; s_len[i] = T->len[i]; }
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) s_sym[i] = T->sym[i];
     __syncthreads();
     if (gz_offsets[n_members] > cap_bytes) return;         // orc_wait() reports it
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,12 +602,13 @@ gz_encode_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ 
         gz_member_frame(*T, out, gz_offsets[gid], member_bytes[gid], member_bits[gid], member_crc[gid],
                         bin_offsets[gid + 1] - bin_offsets[gid]);
     const uint32_t n_chunks = s_base[n_members];
+    const uint32_t hdr_nbits = T->hdr_nbits;
     for (uint32_t c = gid; c < n_chunks; c += gridDim.x * blockDim.x) {
         const int m = gz_member_of(s_base, n_members, c);
         uint64_t lo, hi;
         gz_chunk_range(bin_offsets[m], bin_offsets[m + 1], c - s_base[m], lo, hi);
-        const uint64_t bit0 = 8u * (gz_offsets[m] + GZ_HEADER_BYTES) + T->hdr_nbits + chunk_bitoff[c];
-        gz_chunk_encode(text, lo, hi, s_code, s_len, bit0, reinterpret_cast<uint32_t *>(out));
+        const uint64_t bit0 = 8u * (gz_offsets[m] + GZ_HEADER_BYTES) + hdr_nbits + (tile_off[c / GZ_TILE] + chunk_local[c] - member_pos[m]);
+        gz_chunk_encode(text, lo, hi, s_sym, bit0, reinterpret_cast<uint32_t *>(out));
     }
 }
 #endif  // __CUDACC__

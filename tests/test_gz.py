@@ -81,7 +81,7 @@ def test_fastq_bins_round_trip_through_zlib():
 def test_sizes_around_chunk_and_word_boundaries():
     rnd = random.Random(7)
     pieces = []
-    for n in [1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 500, 511, 512, 513, 1023, 1024, 1025, 1536, 4096, 4097, 10000]:
+    for n in [1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, 500, 511, 512, 513, 1023, 1024, 1025, 1536, 2047, 2048, 2049, 4096, 4097, 10000]:
         pieces.append(bytes(rnd.choice(b"ACGTN@+\n!#%I") for _ in range(n)))
         pieces.append(b"")
     gz, gzo, _ = _compress(pieces)

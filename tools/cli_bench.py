@@ -64,7 +64,8 @@ def main():
     write_s = time.time() - t0
     sys.stderr.write("generated %d reads in %.1f s, wrote both inputs in %.1f s (%.0f MB text, %.0f MB gz)\n" %
                      (a.reads, gen_s, write_s, raw.size / 1e6, os.path.getsize(inputs["gz"]) / 1e6))
-    for variant, inp, extra, tag in (("two-round: fastq.gz (own members) -> 96 x fastq.gz", inputs["gz"], [], "gz"),
+    for variant, inp, extra, tag in (("two-round: fastq.gz (own members) -> 96 x fastq.gz (members coded on the GPU)", inputs["gz"], [], "gz"),
+                                     ("two-round: fastq.gz (own members) -> 96 x fastq.gz (--host-gzip: zlib on the host threads)", inputs["gz"], ["--host-gzip"], "gzh"),
                                      ("two-round: fastq.gz (foreign, one stream) -> 96 x fastq.gz", inputs["foreign"], [], "foreign"),
                                      ("two-round: fastq -> 96 x fastq (no gzip)", inputs["plain"], ["--no-gzip"], "plain")):
         out = os.path.join(a.dir, "demuxed_" + tag)
@@ -76,14 +77,15 @@ def main():
         if r.returncode != 0:
             sys.stderr.write(r.stderr)
             return 1
-        ds = {"gz": "bench", "foreign": "benchf", "plain": "benchp"}[tag]
+        ds = {"gz": "bench", "gzh": "bench", "foreign": "benchf", "plain": "benchp"}[tag]
         rep = json.load(open(os.path.join(out, "SP27", "orcdemux_%s.json" % ds)))
         binned = sum(rep["bins"].values())
         print(json.dumps({"variant": variant, "reads": rep["reads"], "reads_in_valid_bins": binned,
                           "pipeline_s": rep["elapsed_seconds"], "process_wall_s": wall,
                           "reads_per_s": rep["reads"] / rep["elapsed_seconds"],
                           "input_text_MB_per_s": raw.size / 1e6 / rep["elapsed_seconds"],
-                          "host_threads": a.j}), flush=True)
+                          "host_threads": a.j,
+                          "output_MB": sum(os.path.getsize(os.path.join(out, "SP27", f)) for f in os.listdir(os.path.join(out, "SP27"))) / 1e6}), flush=True)
     # the script's flow: round 1 once, round 2 on each of the twelve SP5 bins (13 processes, 13 engine set-ups)
     shim = os.path.join(PKG, "bin", "cutadapt")
     out = os.path.join(a.dir, "demuxed_script")
