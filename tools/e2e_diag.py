@@ -12,11 +12,14 @@ COMBOS = [tuple(int(v) for v in c.split("x")) for c in os.environ.get("COMBOS", 
 STEPS = 6
 rs = E.pin_readset(synth.generate(1 << 20, 300, 900, seed=1002, workers=16))
 drop = bench.scripts_final_tree_drop()
+if os.environ.get('DROPALL'):
+    drop[:] = 1             # nothing emitted: the H2D side and the matching kernels alone
+GZ = bool(os.environ.get('GZ'))
 for S, NSUB, zc in [(s_, n_, z) for s_, n_ in COMBOS for z in ((False, True) if os.environ.get('BOTH') else (True,))]:
     subs, per = bench.split_subbatches(E, synth, rs, NSUB)
     eng = E.Engine(E.m13_rounds(), device=0, max_reads=per, max_bytes=max(int(x.seq.shape[0]) for x in subs) + 64,
                    max_name_bytes=max(int(x.names.shape[0]) for x in subs) + 64, n_slots=S, emit_fastq=True,
-                   want_matches=False, drop_bins=drop, qual_zero_copy=zc)
+                   want_matches=False, drop_bins=drop, qual_zero_copy=zc, emit_gzip=GZ)
     acc = {"h2d_ms": [], "total_ms": [], "emit_ms": [], "d2h_ms": [], "host_submit_ms": [], "host_wait_ms": []}
     tl = []
     infl = []
