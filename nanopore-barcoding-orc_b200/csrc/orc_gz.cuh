@@ -274,8 +274,16 @@ ORC_HD void gz_chunk_range(uint64_t start, uint64_t end, uint32_t k, uint64_t &l
     hi = a + GZ_CHUNK < end ? a + GZ_CHUNK : end;
 }
 
-// The histogram looks at one 16-byte vector of the text in GZ_SAMPLE (and at the tail behind the last vector).
-constexpr int GZ_SAMPLE = 16;
+// The histogram looks at one 16-byte vector of the text in GZ_SAMPLE: the first 128 bytes (GZ_RUN vectors, one DRAM
+// line) of every 128 * GZ_SAMPLE bytes, and the tail behind the last vector.
+constexpr int GZ_SAMPLE = 16, GZ_RUN = 8;
+// the i-th sampled vector (i < gz_n_samples(n16)) of a text of n16 whole vectors
+ORC_HD uint64_t gz_n_samples(uint64_t n16)
+{
+    const uint64_t period = (uint64_t)GZ_RUN * GZ_SAMPLE, rest = n16 % period;
+    return n16 / period * GZ_RUN + (rest < (uint64_t)GZ_RUN ? rest : (uint64_t)GZ_RUN);
+}
+ORC_HD uint64_t gz_sample_at(uint64_t i) { return i / GZ_RUN * ((uint64_t)GZ_RUN * GZ_SAMPLE) + i % GZ_RUN; }
 
 #if defined(__CUDACC__)
 typedef uint4 gz_vec16;
@@ -399,8 +407,8 @@ ORC_HD void gz_member_frame(const GzTable &T, uint8_t *out_bytes, uint64_t membe
 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------ kernels
-// hist[b] += occurrences of byte b in the sampled vectors of text[0, *total) (every GZ_SAMPLE-th 16-byte vector)
-// and in the tail behind the last whole vector
+// hist[b] += occurrences of byte b in the sampled vectors of text[0, *total) (gz_sample_at) and in the tail behind
+// the last whole vector
 __global__ void __launch_bounds__(256)
 gz_hist_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ total, unsigned long long *__restrict__ hist)
 {
@@ -409,10 +417,10 @@ gz_hist_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ to
     __syncthreads();
     uint32_t *h = s_h[threadIdx.x >> 5];
     const uint64_t n16 = *total >> 4;
-    const uint64_t n_samples = (n16 + GZ_SAMPLE - 1) / GZ_SAMPLE;
+    const uint64_t n_samples = gz_n_samples(n16);
     const uint4 *t4 = reinterpret_cast<const uint4 *>(text);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 v = t4[i * GZ_SAMPLE];
+        const uint4 v = t4[gz_sample_at(i)];
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {

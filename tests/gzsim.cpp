@@ -22,8 +22,8 @@ extern "C" long long gzsim_compress(const uint8_t *text, const uint64_t *bin_off
     std::vector<unsigned long long> hist(256, 0);
     {                                                                                 // gz_hist_kernel
         const uint64_t total = bin_offsets[n_bins], n16 = total >> 4;
-        for (uint64_t i = 0; i < n16; i += GZ_SAMPLE)
-            for (int k = 0; k < 16; k++) hist[text[16 * i + k]]++;
+        for (uint64_t i = 0; i < gz_n_samples(n16); i++)
+            for (int k = 0; k < 16; k++) hist[text[16 * gz_sample_at(i) + k]]++;
         for (uint64_t p = n16 << 4; p < total; p++) hist[text[p]]++;
     }
     gz_build_table(hist.data(), T, K);                                                // gz_table_kernel
