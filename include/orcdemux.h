@@ -32,7 +32,10 @@ extern "C" {
 #define ORC_MAX_ROUNDS 2
 #define ORC_MAX_ADAPTERS 32      /* unanchored adapters per round (x2 orientations = 64 lanes) */
 #define ORC_MAX_ANCHORED 64      /* anchored no-indel adapters per round */
-#define ORC_MAX_ADAPTER_LEN 64   /* one 64-bit Myers word */
+#define ORC_MAX_ADAPTER_LEN 64   /* one 64-bit Myers word: the bit-parallel path */
+#define ORC_MAX_LONG_ADAPTER_LEN 256 /* a 5' / 3' round that holds an adapter over 64 nt runs cutadapt's recurrence cell by
+                                        cell on the GPU (long_kernel): exact, far slower, at most ORC_MAX_LONG_ADAPTERS */
+#define ORC_MAX_LONG_ADAPTERS 16
 
 typedef struct orc_ctx orc_ctx;   /* opaque; one per GPU */
 
@@ -55,7 +58,7 @@ typedef struct orc_round_params {
     int32_t type;                   /* ORC_FRONT (-g), ORC_BACK (-a); ORC_PREFIX (-g ^) / ORC_SUFFIX (-a ...$)
                                        only with indels == 0 (Hamming fast path, up to 64 adapters) */
     const char *const *names;       /* [n_adapters] header.split()[0]; may be NULL */
-    const char *const *sequences;   /* [n_adapters] NUL-terminated, <= ORC_MAX_ADAPTER_LEN; ACGT, or IUPAC codes (cutadapt's
+    const char *const *sequences;   /* [n_adapters] NUL-terminated, <= ORC_MAX_ADAPTER_LEN (ORC_MAX_LONG_ADAPTER_LEN, see there); ACGT, or IUPAC codes (cutadapt's
                                        adapter wildcards) in every adapter of every round */
     double max_error_rate;          /* -e  (values >= 1 are absolute error counts, as in cutadapt) */
     int32_t min_overlap;            /* -O  (cutadapt default 3) */

@@ -30,6 +30,7 @@ static_assert(sizeof(Task) == 32, "Task layout");
 static_assert(sizeof(PairResult) == 32, "PairResult layout");
 static_assert(sizeof(WinList) == 32, "WinList layout");
 static_assert(ORC_MAX_ADAPTERS == MAX_AD, "adapter limit");
+static_assert(ORC_MAX_LONG_ADAPTER_LEN == MAX_M_LONG && ORC_MAX_LONG_ADAPTERS == MAX_AD_LONG, "long-adapter limits");
 static_assert(MAX_BINS_GZ == MAX_BINS, "bins of the gzip encoder");
 
 namespace {
@@ -118,6 +119,10 @@ struct orc_ctx {
     AnchoredTable h_anch[2];
     AnchoredTable *d_anch[2] = {nullptr, nullptr};
     bool anchored[2] = {false, false};
+    LongTable h_long[2];
+    LongTable *d_long[2] = {nullptr, nullptr};
+    bool longr[2] = {false, false};         // a round with an adapter over 64 nt (long_kernel)
+    bool special[2] = {false, false};       // anchored or long: the round does not take the bit-parallel pipeline
     uint8_t *d_pack_lut = nullptr, *d_comp_lut = nullptr, *d_drop = nullptr;
     cudaEvent_t ev_span[2] = {nullptr, nullptr};   // orc_span_begin / orc_span_end
     cudaEvent_t ev_ref = nullptr;                  // recorded in orc_create: origin of orc_timings.timeline_ms
@@ -163,7 +168,7 @@ static int alloc_slot(orc_ctx *ctx, Slot &s)
     const size_t worst = std::max<size_t>(R * 2 * (size_t)ctx->na_max, 2 * R);
     size_t n_tasks = std::min(worst, std::max<size_t>(4 * R, 65536));
     if (const char *e = getenv("ORC_PAIR_CAP")) {       // tests: force the overflow path
-        const size_t floor_ = (ctx->anchored[0] || ctx->anchored[1]) ? 2 * R : 1;
+        const size_t floor_ = (ctx->special[0] || ctx->special[1]) ? 2 * R : 1;
         n_tasks = std::min(worst, std::max<size_t>((size_t)atoll(e), floor_));
     }
     s.cap_pairs = n_tasks;
@@ -312,9 +317,14 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         if (rp.sequences == nullptr) { ctx->err = "round without adapter sequences"; return ORC_EINVAL; }
         std::string why;
         ctx->anchored[r] = (rp.type == ORC_PREFIX || rp.type == ORC_SUFFIX);
+        ctx->longr[r] = !ctx->anchored[r] && rp.n_adapters >= 1 && round_is_long(rp.n_adapters, rp.sequences);
+        ctx->special[r] = ctx->anchored[r] || ctx->longr[r];
         if (ctx->anchored[r])
             why = build_anchored_table(ctx->h_anch[r], ctx->h_tab[r], rp.n_adapters, rp.type == ORC_SUFFIX,
                                        rp.sequences, rp.max_error_rate, rp.indels, rp.revcomp);
+        else if (ctx->longr[r])
+            why = build_long_table(ctx->h_long[r], ctx->h_tab[r], rp.n_adapters, rp.type, rp.sequences,
+                                   rp.max_error_rate, rp.min_overlap, rp.indels, rp.revcomp);
         else
             why = build_round_table(ctx->h_tab[r], rp.n_adapters, rp.type, rp.sequences,
                                     rp.max_error_rate, rp.min_overlap, rp.indels, rp.revcomp);
@@ -322,13 +332,13 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         if (rp.action != ORC_ACTION_TRIM && rp.action != ORC_ACTION_RETAIN) { ctx->err = "unsupported: action must be trim or retain"; return ORC_EINVAL; }
         ctx->h_tab[r].action = rp.action;
         ctx->h_seed[r].on = 0;
-        if (!ctx->anchored[r]) {
+        if (!ctx->special[r]) {
             const char *off = getenv("ORC_NO_SEED");        // A/B measurements: keep the flank scan
             build_seed_table(ctx->h_tab[r], ctx->h_seed[r], !(off && off[0] == '1'));
         }
     }
     for (int r = 0; r < p->n_rounds; r++)
-        if (!ctx->anchored[r] && ctx->h_tab[r].n_adapters > ctx->na_max) ctx->na_max = ctx->h_tab[r].n_adapters;
+        if (!ctx->special[r] && ctx->h_tab[r].n_adapters > ctx->na_max) ctx->na_max = ctx->h_tab[r].n_adapters;
     ctx->n_bins = ctx->h_tab[0].n_adapters + 1;
     if (p->n_rounds == 2) ctx->n_bins *= ctx->h_tab[1].n_adapters + 1;
     if (ctx->n_bins > MAX_BINS) { ctx->err = "unsupported: more than 512 bins"; return ORC_EINVAL; }
@@ -351,13 +361,17 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     for (int r = 0; r < p->n_rounds; r++) {
         CK(dalloc(&ctx->d_tab[r], 1));
         CK(cudaMemcpy(ctx->d_tab[r], &ctx->h_tab[r], sizeof(RoundTable), cudaMemcpyHostToDevice));
-        if (!ctx->anchored[r] && ctx->h_seed[r].on) {
+        if (!ctx->special[r] && ctx->h_seed[r].on) {
             CK(dalloc(&ctx->d_seed[r], 1));
             CK(cudaMemcpy(ctx->d_seed[r], &ctx->h_seed[r], sizeof(SeedTable), cudaMemcpyHostToDevice));
         }
         if (ctx->anchored[r]) {
             CK(dalloc(&ctx->d_anch[r], 1));
             CK(cudaMemcpy(ctx->d_anch[r], &ctx->h_anch[r], sizeof(AnchoredTable), cudaMemcpyHostToDevice));
+        }
+        if (ctx->longr[r]) {
+            CK(dalloc(&ctx->d_long[r], 1));
+            CK(cudaMemcpy(ctx->d_long[r], &ctx->h_long[r], sizeof(LongTable), cudaMemcpyHostToDevice));
         }
     }
     uint8_t lut[256];
@@ -386,7 +400,7 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     CK(cudaFuncSetAttribute(resolve_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)band_smem_bytes(MAX_LANES, MAX_AD)));
     for (int r = 0; r < p->n_rounds; r++) {
-        if (ctx->anchored[r]) continue;
+        if (ctx->special[r]) continue;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resolve_band_kernel, BAND_THREADS,
                                                          band_smem_bytes(ctx->h_tab[r].n_lanes, ctx->h_tab[r].n_adapters)));
         ctx->band_blocks[r] = ctx->sm_count * (occ > 0 ? occ : 1);
@@ -425,7 +439,7 @@ extern "C" void orc_destroy(orc_ctx *ctx)
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
-    for (int r = 0; r < 2; r++) { cudaFree(ctx->d_tab[r]); cudaFree(ctx->d_anch[r]); cudaFree(ctx->d_seed[r]); }
+    for (int r = 0; r < 2; r++) { cudaFree(ctx->d_tab[r]); cudaFree(ctx->d_anch[r]); cudaFree(ctx->d_long[r]); cudaFree(ctx->d_seed[r]); }
     cudaFree(ctx->d_pack_lut); cudaFree(ctx->d_comp_lut); cudaFree(ctx->d_drop);
     cudaFree(ctx->d_synth); cudaFree(ctx->d_synth_totals);
     for (int i = 0; i < 2; i++) if (ctx->ev_span[i]) cudaEventDestroy(ctx->ev_span[i]);
@@ -556,8 +570,8 @@ extern "C" int orc_synth(orc_ctx *ctx, int slot, uint64_t seed, uint32_t n_reads
     Slot *sp = get_slot(ctx, slot);
     if (!sp) return ORC_EINVAL;
     Slot &s = *sp;
-    if (ctx->n_rounds != 2 || ctx->anchored[0] || ctx->anchored[1] || ctx->h_tab[0].wild || ctx->h_tab[1].wild) {
-        ctx->err = "orc_synth needs two rounds of plain (ACGT, unanchored) adapters: the read model is 5' adapter + insert + 3' adapter";
+    if (ctx->n_rounds != 2 || ctx->special[0] || ctx->special[1] || ctx->h_tab[0].wild || ctx->h_tab[1].wild) {
+        ctx->err = "orc_synth needs two rounds of plain (ACGT, unanchored, <= 64 nt) adapters: the read model is 5' adapter + insert + 3' adapter";
         return ORC_EINVAL;
     }
     if (!ctx->emit_fastq) { ctx->err = "orc_synth needs emit_fastq (it also makes the read names)"; return ORC_EINVAL; }
@@ -688,7 +702,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     for (int r = 0; r < ctx->n_rounds; r++) {
         const Match *prev = r == 0 ? nullptr : s.d_match[r - 1];
         const bool filter = ctx->h_tab[r].use_filter != 0;
-        const bool anch = ctx->anchored[r];
+        const bool anch = ctx->special[r];      // none of the scan stages below
         // per round: [0] stage-2b job counter, [1] result slots, [2] band-resolver tasks, [3] wide-resolver tasks,
         // [4] stage-2a job counter, [5] pairs that passed stage 2a
         uint32_t *cnt = s.d_counters + 8 * r;
@@ -736,7 +750,11 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
                 s.d_cells + 4 + r, getenv("ORC_NO_TRIM") ? 0 : 1); nl++;
         }
         CK(mark(ORC_K_FILTER));
-        if (n && anch) {
+        if (n && ctx->longr[r]) {
+            // adapters over 64 nt: cutadapt's recurrence as it is, one thread per (read, orientation)
+            long_kernel<<<std::min<uint32_t>((2 * n + 127) / 128, (uint32_t)ctx->sm_count * 8), 128, 0, st>>>(
+                ctx->d_long[r], W, s.d_views[r], prev, n, s.d_results, s.d_best_key); nl++;
+        } else if (n && anch) {
             // anchored adapters without indels: Hamming compare of the anchored end, no alignment
             anchored_kernel<<<std::min<uint32_t>((2 * n + 127) / 128, (uint32_t)ctx->sm_count * 16), 128, 0, st>>>(ctx->d_anch[r], s.d_seq, ctx->d_comp_lut, s.d_views[r],
                                                                 prev, n, s.d_results, s.d_best_key); nl++;
@@ -787,7 +805,7 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             A.out_len = s.d_out_len;
             A.rec_bytes = s.d_rec_bytes;
             A.next_bases = (r + 1 < ctx->n_rounds) ? s.d_cells + r + 1 : nullptr;
-            A.next_len_hist = (r + 1 < ctx->n_rounds && !ctx->anchored[r + 1]) ? sort_hist(s.d_counters, r + 1, 0, 0) : nullptr;
+            A.next_len_hist = (r + 1 < ctx->n_rounds && !ctx->special[r + 1]) ? sort_hist(s.d_counters, r + 1, 0, 0) : nullptr;
             select_kernel<<<std::min<uint32_t>((n + 127) / 128, (uint32_t)ctx->sm_count * 16), 128, 0, st>>>(A); nl++;
         }
         CK(mark(ORC_K_SELECT));
@@ -1011,6 +1029,14 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
         const RoundTable &T = ctx->h_tab[r];
         // algorithmic cells: pairs * m * n summed over the reads entering the round
         uint64_t msum = 0;
+        if (ctx->longr[r]) {
+            // every cell of every pair (Ukkonen's cut-off aside)
+            uint64_t ml = 0;
+            for (int a = 0; a < ctx->h_long[r].n_adapters; a++) ml += (uint64_t)ctx->h_long[r].m[a];
+            const uint64_t bases = (r == 0) ? s.in_bases : (uint64_t)cells[1];
+            t->cells[r] = t->cells_executed[r] = (T.revcomp ? 2ull : 1ull) * ml * bases;
+            continue;
+        }
         if (ctx->anchored[r]) {
             // Hamming path: m characters per adapter and orientation, independent of the read length
             for (int a = 0; a < ctx->h_anch[r].n_adapters; a++) msum += (uint64_t)ctx->h_anch[r].m[a];

@@ -2312,4 +2312,105 @@ ORC_HD int anchored_match(const uint8_t *seq, const uint8_t *comp, const View &v
     return best;
 }
 
+// ------------------------------------------------------------------------------------
+// Adapters longer than one 64-bit word ("adapters > 64 nt"): a round that holds one takes this
+// path instead of the bit-parallel scan.  It is cutadapt's own recurrence, cell by cell (_align.pyx
+// Aligner.locate: R2 first column, R3 cell rule with its tie order match / mismatch / insertion / deletion,
+// R4 Ukkonen's `last`, R5 last-row test with the early stop, R6 last-column test over whatever the column
+// holds above `last`), one column of (cost, score, origin) entries per thread -- exact by construction and
+// slow (m x n cells per pair where the bit-parallel path skips 96 % of them): long adapters are rare, and
+// a pipeline that meets one should not have to leave the GPU.
+// ------------------------------------------------------------------------------------
+constexpr int MAX_M_LONG = 256, MAX_AD_LONG = 16;
+struct LongTable {
+    int32_t n_adapters, type, revcomp, indels;
+    int32_t m[MAX_AD_LONG], k[MAX_AD_LONG], min_ov[MAX_AD_LONG];
+    uint8_t code[MAX_AD_LONG][MAX_M_LONG];          // 4-bit IUPAC masks (A1 C2 G4 T8)
+    // largest cost that is acceptable for an overlap of L adapter characters, (double)cost <= effective length *
+    // rate taken in fp64 on the host: kmax5 for the last-row test (R5), kmax6 for the last-column test (R6) --
+    // they differ only for 5' adapters with N wildcards (see build_round_table)
+    uint8_t kmax5[MAX_AD_LONG][MAX_M_LONG + 4];
+    uint8_t kmax6[MAX_AD_LONG][MAX_M_LONG + 4];
+};
+struct LongCell { int32_t cost, score, origin; };
+
+// Aligner.locate of adapter a against the view in storage direction dir.  col: m + 1 entries of scratch.
+ORC_HD void long_locate(const uint32_t *W, const View &v, int dir, const LongTable &T, int a, LongCell *col,
+                        PairResult &res)
+{
+    const int m = T.m[a], k = T.k[a], n = (int)v.len, min_ov = T.min_ov[a];
+    const int ic = T.indels ? 1 : 100000;                   // --no-indels prices them out (_align.pyx)
+    const bool front = T.type == TYPE_FRONT;
+    const uint8_t *code = T.code[a], *kmax5 = T.kmax5[a], *kmax6 = T.kmax6[a];
+    for (int i = 0; i <= m; i++) {                          // R2: both adapter types may start anywhere in the read
+        col[i].score = 0;
+        if (front) { col[i].cost = 0; col[i].origin = -i; }       // ... and a 5' adapter anywhere in itself
+        else { col[i].cost = i * ic; col[i].origin = 0; }
+    }
+    Best best;
+    best.ref_stop = m; best.query_stop = n; best.cost = m + n + 1; best.origin = 0; best.score = 0;
+    int last = front ? m : imin(m, k + 1);                  // R4
+    for (int j = 1; j <= n; j++) {
+        LongCell diag = col[0];
+        col[0].origin = j;
+        LongCell up = col[0];
+        const uint32_t rc = lane_code(W, v.lo, v.len, dir, j - 1);
+        for (int i = 1; i <= last; i++) {
+            const LongCell cur = col[i];
+            LongCell nw;
+            if (code[i - 1] & rc) {
+                nw.cost = diag.cost; nw.origin = diag.origin; nw.score = diag.score + 1;
+            } else {
+                const int c_diag = diag.cost + 1, c_del = cur.cost + ic, c_ins = up.cost + ic;
+                if (c_diag <= c_del && c_diag <= c_ins) { nw.cost = c_diag; nw.origin = diag.origin; nw.score = diag.score - 1; }
+                else if (c_ins <= c_del) { nw.cost = c_ins; nw.origin = up.origin; nw.score = up.score - 2; }
+                else { nw.cost = c_del; nw.origin = cur.origin; nw.score = cur.score - 2; }
+            }
+            diag = cur;
+            col[i] = nw;
+            up = nw;
+        }
+        while (last >= 0 && col[last].cost > k) last--;
+        if (last < m) { last++; continue; }
+        // R5: the last row holds a cell within k errors
+        const LongCell c = col[m];
+        const int length = m + imin(c.origin, 0);
+        if (!(length >= min_ov && c.cost <= (int)kmax5[length])) continue;
+        const int best_length = m + imin(best.origin, 0);
+        if (best.cost == m + n + 1 || (c.origin <= best.origin + m / 2 && c.score > best.score) ||
+            (length > best_length && c.score > best.score)) {
+            best.score = c.score; best.cost = c.cost; best.origin = c.origin; best.ref_stop = m; best.query_stop = j;
+            if (c.cost == 0 && c.origin >= 0) break;        // exact full match: cutadapt stops scanning
+        }
+    }
+    // R6: the last column -- the column as it stands (after an early stop too, as in _align.pyx; rows above
+    // `last` hold what an earlier column left there), every row of a 3' adapter, row m of a 5' adapter
+    for (int i = m; i >= (front ? m : 0); i--) {
+        const LongCell c = col[i];
+        const int length = i + imin(c.origin, 0);
+        if (!(length >= min_ov && c.cost <= (int)kmax6[length])) continue;
+        if (c.score > best.score || (c.score == best.score && c.cost < best.cost)) {
+            best.score = c.score; best.cost = c.cost; best.origin = c.origin; best.ref_stop = i; best.query_stop = n;
+        }
+    }
+    best_to_result(best, m, n, res);
+}
+
+// Best adapter (R8: score, then fewer errors, then file order) for logical orientation o of the view.
+// Returns the adapter index or -1 and fills res.
+ORC_HD int long_match(const uint32_t *W, const View &v, int o, const LongTable &T, LongCell *col, PairResult &res)
+{
+    const int dir = (int)((v.rc & 1u) ^ (uint32_t)o);
+    int best = -1;
+    res.has = 0; res.pad_ = 0;
+    res.ref_start = res.ref_stop = res.query_start = res.query_stop = res.score = res.errors = 0;
+    for (int a = 0; a < T.n_adapters; a++) {
+        PairResult r;
+        long_locate(W, v, dir, T, a, col, r);
+        if (!r.has) continue;
+        if (best < 0 || r.score > res.score || (r.score == res.score && r.errors < res.errors)) { best = a; res = r; }
+    }
+    return best;
+}
+
 }  // namespace orc

@@ -20,6 +20,7 @@
 //   resolve_kernel     the same for the few tasks whose candidates spread over too many diagonals
 //                      (128-bit column ring in local memory), on a side stream next to the band resolver.
 //   anchored_kernel    anchored --no-indels rounds instead of all of the above.
+//   long_kernel        rounds with adapters over 64 nt instead of all of the above (cutadapt's recurrence as it is).
 //   select_kernel      best of the adapters, --rc choice, trim -> next view, bin id.
 //   bin_count/scan/offsets/place, emit_kernel
 //                      stable multi-way partition of the trimmed reads into their
@@ -657,6 +658,37 @@ anchored_kernel(const AnchoredTable *__restrict__ tab, const uint8_t *__restrict
         const View v = views[r];
         PairResult res;
         const int a = anchored_match(seq, comp, v, o, T, res);
+        if (a >= 0) {
+            results[p] = res;
+            best_key[p] = (unsigned long long)pack_key(res.score, res.errors, a, p);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// A round with adapters over 64 nt (LongTable): one thread per (read, orientation) runs cutadapt's recurrence
+// for every adapter, its column in local memory.
+__global__ void __launch_bounds__(128)
+long_kernel(const LongTable *__restrict__ tab, const uint32_t *__restrict__ W, const View *__restrict__ views,
+            const Match *__restrict__ prev, uint32_t n_reads, PairResult *__restrict__ results,
+            unsigned long long *__restrict__ best_key)
+{
+    __shared__ __align__(16) LongTable T;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(LongTable) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    LongCell col[MAX_M_LONG + 1];
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < 2u * n_reads; p += gridDim.x * blockDim.x) {
+        const uint32_t r = p >> 1;
+        const int o = (int)(p & 1u);
+        if (prev != nullptr && prev[r].adapter < 0) continue;
+        if (o == 1 && !T.revcomp) continue;
+        const View v = views[r];
+        PairResult res;
+        const int a = long_match(W, v, o, T, col, res);
         if (a >= 0) {
             results[p] = res;
             best_key[p] = (unsigned long long)pack_key(res.score, res.errors, a, p);

@@ -302,6 +302,79 @@ inline void build_seed_table(const RoundTable &T, SeedTable &S, bool enable)
     S.on = 1; S.need = need; S.mult = mult; S.n_list = n_list; S.kt = T.k_max; S.m_max = T.m_max;
 }
 
+// A 5' / 3' round with an adapter of more than MAX_M characters (LongTable, orc_core.cuh): the same quantities as
+// build_round_table takes from cutadapt -- k = int(rate * m), min_overlap clamped to m, the fp64 acceptance limits
+// per overlap length with the N counts of R5 / R6 -- for up to MAX_AD_LONG adapters of up to MAX_M_LONG characters.
+// Also fills the few RoundTable fields the selection kernel reads.
+inline bool round_is_long(int n_adapters, const char *const *sequences)
+{
+    for (int a = 0; a < n_adapters; a++)
+        if (sequences[a] && strlen(sequences[a]) > (size_t)MAX_M) return true;
+    return false;
+}
+inline std::string build_long_table(LongTable &L, RoundTable &T, int n_adapters, int type, const char *const *sequences,
+                                    double max_errors, int min_overlap, int indels, int revcomp)
+{
+    memset(&L, 0, sizeof(L));
+    memset(&T, 0, sizeof(T));
+    if (n_adapters < 1 || n_adapters > MAX_AD_LONG)
+        return "unsupported: between 1 and " + std::to_string(MAX_AD_LONG) + " adapters in a round with adapters over 64 nt";
+    if (type != TYPE_FRONT && type != TYPE_BACK)
+        return "unsupported: only regular 5' (-g) and 3' (-a) adapters take the edit-distance path";
+    if (min_overlap < 1) return "min_overlap must be >= 1";
+    L.n_adapters = n_adapters; L.type = type; L.revcomp = revcomp ? 1 : 0; L.indels = indels ? 1 : 0;
+    int n_wild = 0;
+    for (int a = 0; a < n_adapters; a++) {
+        const char *s = sequences[a];
+        const int m = (int)strlen(s);
+        if (m < 1 || m > MAX_M_LONG) return "unsupported: adapter length must be 1.." + std::to_string(MAX_M_LONG);
+        L.m[a] = m;
+        std::vector<int> n_counts((size_t)m + 1, 0);
+        bool wild = false;
+        int nN = 0;
+        for (int i = 0; i < m; i++) {
+            char c = s[i];
+            if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+            if (c == 'U') c = 'T';
+            if (c == 'I') c = 'N';
+            const int code = iupac_code(c);
+            if (code < 0) return "unsupported: adapter character outside the IUPAC alphabet";
+            L.code[a][i] = (uint8_t)code;
+            n_counts[(size_t)i] = nN;
+            if (base_code(c) < 0) wild = true;
+            if (c == 'N') nN++;
+        }
+        n_counts[(size_t)m] = nN;
+        if (wild) n_wild++;
+        double rate = max_errors;
+        if (rate >= 1.0) {                          // absolute error count (adapters.py)
+            if (m - nN < 1) return "unsupported: an absolute error count for an adapter made of N only";
+            rate /= (m - nN);
+        }
+        if (!(rate >= 0.0) || rate >= 1.0) return "unsupported: error rate must be in [0, 1) for every adapter";
+        L.k[a] = (int)(rate * m);
+        if (L.k[a] > 63) return "unsupported: more than 63 errors allowed in one adapter";       // pack_key()
+        L.min_ov[a] = min_overlap < m ? min_overlap : m;
+        for (int len = 0; len <= m; len++) {
+            const int eff5 = len - n_counts[(size_t)len];
+            const int eff6 = (type == TYPE_BACK) ? eff5 : len - (n_counts[(size_t)m] - n_counts[(size_t)(m - len)]);
+            int c5 = (int)floor(eff5 * rate), c6 = (int)floor(eff6 * rate);
+            L.kmax5[a][len] = (uint8_t)(c5 < 0 ? 0 : (c5 > 255 ? 255 : c5));
+            L.kmax6[a][len] = (uint8_t)(c6 < 0 ? 0 : (c6 > 255 ? 255 : c6));
+        }
+    }
+    if (n_wild != 0 && n_wild != n_adapters)
+        return "unsupported: adapters with and without IUPAC wildcards in one round";
+    T.n_adapters = n_adapters;
+    T.type = type;
+    T.revcomp = revcomp ? 1 : 0;
+    T.indels = indels ? 1 : 0;
+    T.min_overlap = min_overlap;
+    T.wild = n_wild ? 1 : 0;
+    T.n_lanes = 0;
+    return "";
+}
+
 // Anchored, no-indel round (ORC_PREFIX / ORC_SUFFIX).  Also fills the few RoundTable fields the
 // selection kernel reads (type as trimming side, revcomp, n_adapters).
 inline std::string build_anchored_table(AnchoredTable &A, RoundTable &T, int n_adapters, int suffix,

@@ -35,12 +35,18 @@ extern "C" int hostsim_demux(int n_rounds,
     const int filter_mode = filter_mode_in & 3;
     RoundTable *T = new RoundTable[2];
     AnchoredTable *AT = new AnchoredTable[2];
+    LongTable *LT = new LongTable[2];
     bool anch[2] = {type0 >= 2, n_rounds > 1 && type1 >= 2};
+    // a round with an adapter over 64 nt takes cutadapt's recurrence as it is (long_kernel on the device)
+    const bool longr[2] = {!anch[0] && round_is_long(n_ad0, seq0), n_rounds > 1 && !anch[1] && round_is_long(n_ad1, seq1)};
     std::string e = anch[0] ? build_anchored_table(AT[0], T[0], n_ad0, type0 == 3, seq0, e0, 0, rc0)
+                  : longr[0] ? build_long_table(LT[0], T[0], n_ad0, type0, seq0, e0, ov0, indels, rc0)
                             : build_round_table(T[0], n_ad0, type0, seq0, e0, ov0, indels, rc0, filter_mode);
     if (e.empty() && n_rounds > 1)
         e = anch[1] ? build_anchored_table(AT[1], T[1], n_ad1, type1 == 3, seq1, e1, 0, rc1)
+          : longr[1] ? build_long_table(LT[1], T[1], n_ad1, type1, seq1, e1, ov1, indels, rc1)
                     : build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, indels, rc1, filter_mode);
+    for (int rd = 0; rd < 2; rd++) anch[rd] = anch[rd] || longr[rd];     // below: "not the bit-parallel pipeline"
     // filter_mode bit 2 (value 4) keeps the flank scan of stage 1 although seeds would be usable
     SeedTable *ST = new SeedTable[2];
     for (int rd = 0; rd < n_rounds; rd++) {
@@ -54,6 +60,7 @@ extern "C" int hostsim_demux(int n_rounds,
         err[err_len - 1] = 0;
         delete[] T;
         delete[] AT;
+        delete[] LT;
         delete[] ST;
         return -1;
     }
@@ -62,6 +69,7 @@ extern "C" int hostsim_demux(int n_rounds,
         err[err_len - 1] = 0;
         delete[] T;
         delete[] AT;
+        delete[] LT;
         delete[] ST;
         return -1;
     }
@@ -92,6 +100,7 @@ extern "C" int hostsim_demux(int n_rounds,
     }
     n_tasks[0] = n_tasks[1] = 0;
     n_columns[0] = n_columns[1] = 0;
+    std::vector<LongCell> long_col(MAX_M_LONG + 1);
     for (uint32_t r = 0; r < n_reads; r++) {
         View v; v.lo = offsets[r]; v.len = lengths[r]; v.rc = 0;
         Match *out[2] = {&m0[r], &m1[r]};
@@ -103,9 +112,10 @@ extern "C" int hostsim_demux(int n_rounds,
             uint64_t keys[2] = {0, 0};
             if (anch[rd]) {
                 for (int o = 0; o < 2; o++) {
-                    if (o == 1 && !AT[rd].revcomp) continue;
+                    if (o == 1 && !R.revcomp) continue;
                     PairResult pr;
-                    const int a = anchored_match(seq, comp_lut, v, o, AT[rd], pr);
+                    const int a = longr[rd] ? long_match(W, v, o, LT[rd], long_col.data(), pr)
+                                            : anchored_match(seq, comp_lut, v, o, AT[rd], pr);
                     if (a >= 0) keys[o] = pack_key(pr.score, pr.errors, a, (uint32_t)results.size());
                     results.push_back(pr);
                 }
@@ -188,6 +198,7 @@ extern "C" int hostsim_demux(int n_rounds,
     delete[] band;
     delete[] T;
     delete[] AT;
+    delete[] LT;
     delete[] ST;
     return 0;
 }

@@ -474,6 +474,54 @@ def test_iupac_adapter_sets_gpu():
         E.Engine([E.Round(["a", "b"], ["ACGTACGT", "ACGNACGT"], ORC_BACK, 0.1, 3, True, True)], max_reads=16, max_bytes=1024)
 
 
+def test_adapters_over_64_nt_gpu():
+    """SURVEY 8f N4 "adapters > 64 nt": a round that holds one runs long_kernel (cutadapt's recurrence cell by
+    cell) instead of the bit-parallel scan.  Matches, trimmed lengths and the FASTQ bytes of every bin against
+    the oracle: both rounds long, a long round beside the M13 round, plain and IUPAC adapters, with and without
+    indels, --rc on and off."""
+    import random
+    import oracle
+    import test_hostsim as TH
+    from orcdemux import m13
+    from orcdemux.lib import ORC_BACK, ORC_FRONT
+    rnd = random.Random(6402)
+    hits = 0
+    for trial in range(8):
+        wild = trial % 3 == 2
+        f, b = TH._long_sets(rnd, wild)
+        e = rnd.choice([0.0, 0.1, 0.1, 0.2, 0.3])
+        ov = rnd.choice([1, 3, 3, 10, 70])
+        rc = rnd.choice([0, 1, 1])
+        indels = trial % 4 != 3
+        if trial % 5 == 1 and not wild:
+            b = [s for _, s in m13.sp27_reverse_rc()]
+        if trial % 5 == 4 and not wild:
+            f = [s for _, s in m13.sp5_forward()]
+        plain = lambda x: "".join(c if c in "ACGT" else rnd.choice("ACGT") for c in x)
+        rs = TH._adversarial_reads(rnd, [plain(x) for x in f], [plain(x) for x in b], 1200)
+        spec = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
+        rounds = [E.Round([str(i) for i in range(len(x[0]))], x[0], ORC_FRONT if x[1] == oracle.FRONT else ORC_BACK,
+                          x[2], x[3], indels, bool(x[4])) for x in spec]
+        with E.Engine(rounds, max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]) + 64,
+                      max_name_bytes=int(rs.names.shape[0]) + 64, n_slots=1, emit_fastq=True, want_matches=True) as eng:
+            res = eng.run(rs)
+            rec0, rec1, oseq, oqual, olen = H.run_oracle(spec, rs, indels=indels)
+            idx, nbad = H.diff_matches(rec0, res.matches[0])
+            assert nbad == 0, (trial, "round 1", idx[:3])
+            idx, nbad = H.diff_matches(rec1, res.matches[1])
+            assert nbad == 0, (trial, "round 2", idx[:3])
+            assert np.array_equal(res.out_len, olen)
+            exp = _expected_fastq(rs, rec0, rec1, oseq, oqual, olen, eng.n_bins, eng.bin_id)
+            for bb in range(eng.n_bins):
+                assert res.bin_bytes(bb) == exp[bb], "trial %d bin %d bytes differ" % (trial, bb)
+            t = eng.timings(0)
+            assert t["cells"][0] > 0
+        hits += int((rec0["adapter"] >= 0).sum()) + int((rec1["adapter"] >= 0).sum())
+    assert hits > 5000
+    with pytest.raises(E.OrcError, match="unsupported"):
+        E.Engine([E.Round(["a"], ["A" * 257], ORC_BACK, 0.1, 3, True, True)], max_reads=16, max_bytes=1024)
+
+
 def test_seeded_stage1_random_adapter_sets():
     """Adapter sets stage 1 can seed (long adapters, long shared prefix, low error rates; pieces per
     adapter minus errors 1 or 2) through the kernels, with and without the seed table."""

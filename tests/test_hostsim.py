@@ -427,7 +427,7 @@ def test_unsupported_is_refused():
     with pytest.raises(RuntimeError, match="unsupported"):
         H.run_hostsim([(["ACGZ"], oracle.FRONT, 0.1, 3, 1)], rs)
     with pytest.raises(RuntimeError, match="unsupported"):
-        H.run_hostsim([(["A" * 65], oracle.FRONT, 0.1, 3, 1)], rs)
+        H.run_hostsim([(["A" * 257], oracle.FRONT, 0.1, 3, 1)], rs)
 
 
 def test_up_to_32_adapters_and_config4_unanchored_arm():
@@ -457,3 +457,50 @@ def test_up_to_32_adapters_and_config4_unanchored_arm():
     one = synth.from_records([("x", "ACGT", "IIII")])
     with pytest.raises(RuntimeError, match="unsupported"):
         H.run_hostsim([(["ACGTACGT"] * 33, oracle.FRONT, 0.1, 3, 1)], one)
+
+
+def _long_sets(rnd, wild=False):
+    alphabet = "ACGT" if not wild else "ACGTACGTACGTRYKMSWBDHVN"
+    mk = lambda lo, hi: "".join(rnd.choice(alphabet) for _ in range(rnd.randint(lo, hi)))
+    nf, nb = rnd.randint(1, 5), rnd.randint(1, 5)
+    # every round holds at least one adapter over 64 nt; short ones ride along
+    f = [mk(65, 200)] + [mk(rnd.choice([12, 40, 65, 90]), 130) for _ in range(nf - 1)]
+    b = [mk(65, 256)] + [mk(rnd.choice([12, 40, 65, 90]), 130) for _ in range(nb - 1)]
+    rnd.shuffle(f)
+    rnd.shuffle(b)
+    return f, b
+
+
+def test_adapters_over_64_nt():
+    """SURVEY 8f N4 "adapters > 64 nt": a round that holds one runs cutadapt's recurrence cell by cell
+    (orc_core.cuh long_locate / long_match, long_kernel on the device).  Against the oracle: random sets of 1-5
+    adapters of up to 256 nt per round (plain, and with IUPAC wildcards), both rounds long or a long round beside
+    a bit-parallel one, with and without indels, --rc on and off, error rates up to 0.3 and as absolute counts."""
+    rnd = random.Random(6401)
+    hits = 0
+    for trial in range(10):
+        wild = trial % 3 == 2
+        f, b = _long_sets(rnd, wild)
+        e = rnd.choice([0.0, 0.1, 0.1, 0.2, 0.3, 5])
+        ov = rnd.choice([1, 3, 3, 10, 70])
+        rc = rnd.choice([0, 1, 1])
+        indels = trial % 4 != 3
+        plain = lambda x: "".join(c if c in "ACGT" else rnd.choice("ACGT") for c in x)
+        if trial % 5 == 1:          # a long 5' round in front of the M13 3' round
+            b = [s for _, s in m13.sp27_reverse_rc()] if not wild else ["ACGTNRYACGTTGCAAC", "TTGACNNRGATTACAGG"]
+        if trial % 5 == 4:          # the M13 5' round in front of a long 3' round
+            f = [s for _, s in m13.sp5_forward()] if not wild else ["ACGTNRYACGTTGCAAC", "TTGACNNRGATTACAGG"]
+        rs = _adversarial_reads(rnd, [plain(x) for x in f], [plain(x) for x in b], 250)
+        rounds = [(f, oracle.FRONT, e, ov, rc), (b, oracle.BACK, e, ov, rc)]
+        rec0, rec1, oseq, oqual, olen = H.run_oracle(rounds, rs, n_threads=4, indels=indels)
+        m0, m1, lo, ln, rcs, nt = H.run_hostsim(rounds, rs, indels=int(indels))
+        assert H.diff_matches(rec0, m0)[1] == 0, ("round 1", trial)
+        assert H.diff_matches(rec1, m1)[1] == 0, ("round 2", trial)
+        assert np.array_equal(olen, ln)
+        hits += int((rec0["adapter"] >= 0).sum()) + int((rec1["adapter"] >= 0).sum())
+    assert hits > 1500
+    # limits: 257 nt, 17 adapters in a long round
+    with pytest.raises(RuntimeError, match="unsupported"):
+        H.run_hostsim([(["A" * 257], oracle.FRONT, 0.1, 3, 1)], synth.from_records([("r", "ACGT", "IIII")]))
+    with pytest.raises(RuntimeError, match="unsupported"):
+        H.run_hostsim([(["ACGT" * 20] * 17, oracle.FRONT, 0.1, 3, 1)], synth.from_records([("r", "ACGT", "IIII")]))
