@@ -670,6 +670,25 @@ def main():
             if not args.e2e_text and full:
                 counts_t, out["e2e_text"] = e2e_leg(False)
                 assert np.array_equal(counts, counts_t)
+            if full and rank == 0 and not args.e2e_text and len(rounds) == 2:
+                # device time of the gzip stage on one whole resident batch (it is not part of `value`)
+                hb = host_batches[0]
+                with E.Engine(rounds, device=local_rank, max_reads=hb.n_reads, max_bytes=int(hb.seq.shape[0]) + 64,
+                              max_name_bytes=int(hb.names.shape[0]) + 64, n_slots=1, emit_fastq=True,
+                              want_matches=False, drop_bins=drop, emit_gzip=True) as gz:
+                    gz.run(hb)
+                    for _ in range(3):
+                        gz.launch(0)
+                        gz.sync(0)
+                    tg = gz.timings(0)
+                text = tg["emit_bytes"] // 2
+                out["gzip_stage"] = {"ms": tg["gzip_ms"], "text_bytes": text, "member_bytes": tg["gzip_bytes"],
+                                     "ratio": tg["gzip_bytes"] / max(text, 1), "emit_ms": tg["emit_ms"],
+                                     "text_gbs": text / (tg["gzip_ms"] * 1e-3) / 1e9 if tg["gzip_ms"] > 0 else None,
+                                     "note": "gz_hist / gz_table / gz_measure / gz_layout / gz_zero / gz_encode "
+                                             "(csrc/orc_gz.cuh) behind one step of %d reads, device time between "
+                                             "events; shared-memory-pipe bound (one code and one CRC look-up per "
+                                             "byte), hidden behind the copies in e2e" % hb.n_reads}
             out["counts"] = counts
         else:
             out["e2e"] = None
@@ -813,6 +832,8 @@ def main():
         }
         if main_cfg.get("e2e_text") is not None:
             line["e2e_text"] = main_cfg["e2e_text"]
+        if main_cfg.get("gzip_stage") is not None:
+            line["gzip_stage"] = main_cfg["gzip_stage"]
         line.update(extra)
         emit(line)
     if world > 1:
