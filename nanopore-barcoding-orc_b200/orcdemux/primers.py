@@ -34,6 +34,7 @@ from . import synth
 from .lib import MATCH_DTYPE, ORC_BACK, ORC_FRONT
 
 MAX_PER_PASS = 32                                # adapters per GPU pass (csrc/orc_core.cuh MAX_AD)
+MAX_PER_PASS_LONG = 16                           # of adapters over 64 nt (MAX_AD_LONG)
 Record = Tuple[str, str, Optional[str]]          # name (header without @ or >), sequence, qualities or None
 
 
@@ -233,7 +234,7 @@ def run(opt, device: int = 0):
         from .cli import _parse_adapter_specs
         order = opt["order"] or ["g"] * len(opt["g"]) + ["a"] * len(opt["a"])
         it = {"g": iter(opt["g"]), "a": iter(opt["a"])}
-        groups = {}                         # (adapter type, has wildcards) -> names, sequences, positions
+        groups = {}                         # (adapter type, has wildcards, over 64 nt) -> names, sequences, positions
         all_names = []
         for t in order:
             kind = ORC_FRONT if t == "g" else ORC_BACK
@@ -243,12 +244,14 @@ def run(opt, device: int = 0):
             for a_, b_ in zip(nm, sq):
                 pos = len(all_names)
                 all_names.append(str(pos + 1) if (a_ == "1" and len(nm) == 1) else a_)
-                g = groups.setdefault((kind, any(c not in "ACGT" for c in b_)), ([], [], []))
+                g = groups.setdefault((kind, any(c not in "ACGT" for c in b_), len(b_) > 64), ([], [], []))
                 g[0].append(all_names[-1]); g[1].append(b_); g[2].append(pos)
         kinds, ms, poss = [], [], []
-        for (kind, _), (nm, sq, ps) in groups.items():
-            for lo in range(0, len(nm), MAX_PER_PASS):          # the kernels take up to 16 adapters per round
-                hi = lo + MAX_PER_PASS
+        for (kind, _, long_), (nm, sq, ps) in groups.items():
+            # the kernels take up to 32 adapters per round, 16 of those over 64 nt (the cell-by-cell path)
+            per = MAX_PER_PASS_LONG if long_ else MAX_PER_PASS
+            for lo in range(0, len(nm), per):
+                hi = lo + per
                 kinds.append(kind)
                 poss.append(np.array(ps[lo:hi], dtype=np.int64))
                 ms.append(_match_batches([E.Round(nm[lo:hi], sq[lo:hi], kind, e, ov, indels, False)], recs, device)[0]
