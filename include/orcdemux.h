@@ -196,6 +196,10 @@ int orc_download(orc_ctx *ctx, int slot);
 int orc_sync(orc_ctx *ctx, int slot);
 
 int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *out);
+/* when the stages of the batch last waited for on a slot finished on the device, milliseconds since orc_create():
+ * out6 = {stream reached the upload, H2D copies done, matching + binning kernels done, emit_kernel done, gzip stage
+ * done, D2H copies done}.  Event queries only: usable inside a pipelined submit / wait loop, after orc_wait(). */
+int orc_get_timeline(orc_ctx *ctx, int slot, float *out6);
 /* a CUDA-event stopwatch on the slot's stream: start records an event, stop records a
  * second one, waits for it and returns the device time between them (milliseconds) */
 int orc_timer_start(orc_ctx *ctx, int slot);

@@ -1074,6 +1074,25 @@ extern "C" int orc_get_timings(orc_ctx *ctx, int slot, orc_timings *t)
     return ORC_OK;
 }
 
+// When the stages of the batch last waited for on a slot finished on the device, milliseconds since orc_create():
+// [0] the slot's stream reached the upload, [1] H2D copies done, [2] matching and binning kernels done,
+// [3] emit_kernel done, [4] gzip stage done, [5] D2H copies done.  Event queries only (no device read, unlike
+// orc_get_timings): safe to call inside a pipelined submit / wait loop after orc_wait() of that slot.
+extern "C" int orc_get_timeline(orc_ctx *ctx, int slot, float *out6)
+{
+    Slot *sp = get_slot(ctx, slot);
+    if (!sp || !out6) return ORC_EINVAL;
+    Slot &s = *sp;
+    for (int i = 0; i < 6; i++) out6[i] = 0.0f;
+    if (!s.did_kernels || !s.did_d2h) { ctx->err = "orc_get_timeline: no finished batch on this slot"; return ORC_ESTATE; }
+    const int evs[6] = {EV_START, EV_H2D, EV_BIN, EV_EMIT, EV_GZ, EV_END};
+    for (int i = 0; i < 6; i++) {
+        if (i == 0 && !s.did_h2d) continue;
+        CK(cudaEventElapsedTime(&out6[i], ctx->ev_ref, s.ev[evs[i]]));
+    }
+    return ORC_OK;
+}
+
 extern "C" int orc_counts(orc_ctx *ctx, uint64_t *bins)
 {
     if (!ctx || !bins) return ORC_EINVAL;
@@ -1227,6 +1246,50 @@ __global__ void __launch_bounds__(256) hostread_probe_kernel(const uint8_t *__re
     if (acc == 0x12345678u) out[0] = acc;       // keeps the loads alive
 }
 
+// The same reads as bulk asynchronous copies (cp.async.bulk, the TMA's 1-D mode) into shared memory and on into
+// device memory: one lane per warp issues them, two buffers per warp, an mbarrier per buffer.  ORC_PROBE_BULK=1.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(256) hostread_bulk_kernel(const uint8_t *__restrict__ src, uint64_t n_chunks, uint32_t chunk,
+                                                            uint64_t stride, uint8_t *__restrict__ dst)
+{
+    extern __shared__ __align__(128) uint8_t bulk_smem[];       // [warp][2][chunk]
+    __shared__ __align__(8) uint64_t bars[8][2];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    if (lane != 0) return;
+    for (int b = 0; b < 2; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[w][b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint8_t *buf[2] = {bulk_smem + (size_t)w * 2 * chunk, bulk_smem + (size_t)w * 2 * chunk + chunk};
+    uint32_t phase[2] = {0, 0};
+    auto issue = [&](uint64_t c, int b) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[w][b])), "r"(chunk) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(buf[b])), "l"(src + c * stride), "r"(chunk), "r"(smem_u32(&bars[w][b])) : "memory");
+    };
+    uint64_t c = warp;
+    int b = 0;
+    if (c < n_chunks) issue(c, 0);
+    for (; c < n_chunks; c += n_warps, b ^= 1) {
+        const uint64_t nxt = c + n_warps;
+        if (nxt < n_chunks) {
+            // the other buffer's store to global must have read it before the next load lands there
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            issue(nxt, b ^ 1);
+        }
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(smem_u32(&bars[w][b])), "r"(phase[b]) : "memory");
+        phase[b] ^= 1u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(dst + c * (uint64_t)chunk), "r"(smem_u32(buf[b])), "r"(chunk) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 extern "C" double orc_probe_hostread(int device, const void *host, uint64_t bytes, uint32_t chunk, uint64_t stride)
 {
     const int dup = getenv("ORC_PROBE_DUP") ? 1 : 0;
@@ -1246,8 +1309,18 @@ extern "C" double orc_probe_hostread(int device, const void *host, uint64_t byte
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     float best = 1e30f;
+    const int bulk = getenv("ORC_PROBE_BULK") ? atoi(getenv("ORC_PROBE_BULK")) : 0;
+    uint8_t *d_bulk = nullptr;
+    if (bulk) {
+        if (cudaMalloc(&d_bulk, (size_t)n_chunks * chunk) != cudaSuccess) return -1.0;
+        cudaFuncSetAttribute(hostread_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (int)chunk);
+    }
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(a);
+        if (bulk)       // `bulk` blocks per SM, 8 warps each, two buffers of `chunk` bytes per warp
+            hostread_bulk_kernel<<<prop.multiProcessorCount * bulk, 256, 16 * (size_t)chunk>>>(
+                static_cast<const uint8_t *>(at.devicePointer), n_chunks, chunk, stride, d_bulk);
+        else
         hostread_probe_kernel<<<prop.multiProcessorCount * 8, 256>>>(static_cast<const uint8_t *>(at.devicePointer), n_chunks,
                                                                     chunk, stride, d, dup);
         cudaEventRecord(b);
@@ -1259,6 +1332,8 @@ extern "C" double orc_probe_hostread(int device, const void *host, uint64_t byte
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     cudaFree(d);
+    cudaFree(d_bulk);
+    if (cudaGetLastError() != cudaSuccess) return -3.0;
     if (best <= 0) return -1.0;
     return (double)n_chunks * chunk / (best * 1e-3) / 1e9;
 }

@@ -271,6 +271,13 @@ class Engine:
                     n_pairs_2b=list(t.n_pairs_2b), n_tasks_wide=list(t.n_tasks_wide), timeline_ms=list(t.timeline_ms),
                     gzip_ms=t.gzip_ms, gzip_bytes=t.gzip_bytes)
 
+    def timeline(self, slot: int = 0):
+        """Device times (ms since the engine was made) at which the stages of the batch last waited for on the slot
+        finished: upload reached, H2D done, matching done, emit done, gzip done, D2H done (orc_get_timeline)."""
+        out = (C.c_float * 6)()
+        self._check(self._L.orc_get_timeline(self._ctx, slot, out), "orc_get_timeline")
+        return [float(x) for x in out]
+
     def timer_start(self, slot: int = 0):
         self._check(self._L.orc_timer_start(self._ctx, slot), "orc_timer_start")
 

@@ -23,8 +23,12 @@ for S, NSUB, zc in [(s_, n_, z) for s_, n_ in COMBOS for z in ((False, True) if 
     acc = {"h2d_ms": [], "total_ms": [], "emit_ms": [], "d2h_ms": [], "host_submit_ms": [], "host_wait_ms": []}
     tl = []
     infl = []
+    full_tl = []
+    w_ref = time.perf_counter()
     def take(slot):
-        t0 = time.perf_counter(); eng.wait(slot, copy=False); acc["host_wait_ms"].append(1e3 * (time.perf_counter() - t0))
+        t0 = time.perf_counter(); eng.wait(slot, copy=False); t1 = time.perf_counter(); acc["host_wait_ms"].append(1e3 * (t1 - t0))
+        if os.environ.get('FULLTL'):
+            full_tl.append(eng.timeline(slot) + [1e3 * (t0 - w_ref), 1e3 * (t1 - w_ref)])
         # (no eng.timings() here: its synchronous cudaMemcpy of the counters queues behind the pending copies
         # of the other slots and stalls this thread -- the timeline below is read once, after the loop)
     k = 0
@@ -51,4 +55,15 @@ for S, NSUB, zc in [(s_, n_, z) for s_, n_ in COMBOS for z in ((False, True) if 
         t0 = tl[0][1][0]
         for slot, x in tl:
             print('   slot %d  h2d %7.2f-%7.2f  kernels -%7.2f  emit -%7.2f  d2h -%7.2f' % (slot, x[0] - t0, x[1] - t0, x[2] - t0, x[3] - t0, x[4] - t0))
+    if os.environ.get('FULLTL'):
+        # every sub-batch of the last steps in the order they were waited for: when its stages ended on the device
+        # (ms since the first one shown), how long each engine was busy between consecutive ends, and when the host
+        # entered / left orc_wait (host clock, own origin)
+        rows = full_tl[-3 * NSUB:]
+        o = rows[0][0]
+        print('   sub   h2d_start  h2d_end   match_end  emit_end   gz_end    d2h_end  | h2d_end-prev  d2h_end-prev | host wait in..out')
+        for i, x in enumerate(rows):
+            p_ = rows[i - 1] if i else x
+            print('   %3d  %9.2f %9.2f %9.2f %9.2f %9.2f %9.2f  | %8.2f %12.2f   | %9.2f %9.2f' % (
+                i, x[0] - o, x[1] - o, x[2] - o, x[3] - o, x[4] - o, x[5] - o, x[1] - p_[1], x[5] - p_[5], x[6], x[7]))
     eng.close()
