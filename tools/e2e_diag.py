@@ -32,6 +32,39 @@ for S, NSUB, zc in [(s_, n_, z) for s_, n_ in COMBOS for z in ((False, True) if 
         # (no eng.timings() here: its synchronous cudaMemcpy of the counters queues behind the pending copies
         # of the other slots and stalls this thread -- the timeline below is read once, after the loop)
     k = 0
+    if os.environ.get('THREADS'):
+        # one thread submits, another waits: ctypes drops the GIL inside the calls, so the D2H side no longer holds
+        # up the next upload (slots are handed over through two queues)
+        import queue, threading
+        free, busy = queue.Queue(), queue.Queue()
+        for sl in range(S):
+            free.put(sl)
+        def waiter():
+            while True:
+                sl = busy.get()
+                if sl is None:
+                    return
+                eng.wait(sl, copy=False)
+                free.put(sl)
+        for rep in range(STEPS + 1):
+            if rep == 1:
+                busy.join() if False else None
+                while free.qsize() < S:
+                    time.sleep(0.0005)
+                import torch; torch.cuda.synchronize(); w0 = time.perf_counter()
+            if rep == 0:
+                th = threading.Thread(target=waiter); th.start()
+            for sub in subs:
+                sl = free.get()
+                eng.submit(sl, sub)
+                busy.put(sl)
+        while free.qsize() < S:
+            time.sleep(0.0005)
+        secs = time.perf_counter() - w0
+        busy.put(None); th.join()
+        print("S=%d NSUB=%d zero_copy=%s THREADS  %.2f ms/step  %.1f M reads/s" % (S, NSUB, zc, 1e3 * secs / STEPS, STEPS * rs.n_reads / secs / 1e6))
+        eng.close()
+        continue
     for rep in range(STEPS + 1):
         if rep == 1:
             while infl: take(infl.pop(0))
