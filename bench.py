@@ -676,7 +676,25 @@ def main():
                 with E.Engine(rounds, device=local_rank, max_reads=hb.n_reads, max_bytes=int(hb.seq.shape[0]) + 64,
                               max_name_bytes=int(hb.names.shape[0]) + 64, n_slots=1, emit_fastq=True,
                               want_matches=False, drop_bins=drop, emit_gzip=True) as gz:
-                    gz.run(hb)
+                    rg = gz.run(hb)
+                    # every 8th bin of the whole batch inflated by zlib and compared with the text path's bytes
+                    import zlib
+                    with E.Engine(rounds, device=local_rank, max_reads=hb.n_reads, max_bytes=int(hb.seq.shape[0]) + 64,
+                                  max_name_bytes=int(hb.names.shape[0]) + 64, n_slots=1, emit_fastq=True,
+                                  want_matches=False, drop_bins=drop) as tx:
+                        rt = tx.run(hb)
+                    checked = 0
+                    for b_ in range(0, rt.bin_offsets.shape[0] - 1, 8):
+                        a0, a1 = int(rg.bin_offsets[b_]), int(rg.bin_offsets[b_ + 1])
+                        t0_, t1_ = int(rt.bin_offsets[b_]), int(rt.bin_offsets[b_ + 1])
+                        if t1_ == t0_:
+                            assert a1 == a0
+                            continue
+                        dz = zlib.decompressobj(31)
+                        if dz.decompress(rg.fastq[a0:a1].tobytes()) != rt.fastq[t0_:t1_].tobytes() or not dz.eof:
+                            raise SystemExit("gzip member of bin %d does not inflate to the bin's text" % b_)
+                        checked += 1
+                    del rg, rt
                     for _ in range(3):
                         gz.launch(0)
                         gz.sync(0)
@@ -685,6 +703,7 @@ def main():
                 out["gzip_stage"] = {"ms": tg["gzip_ms"], "text_bytes": text, "member_bytes": tg["gzip_bytes"],
                                      "ratio": tg["gzip_bytes"] / max(text, 1), "emit_ms": tg["emit_ms"],
                                      "text_gbs": text / (tg["gzip_ms"] * 1e-3) / 1e9 if tg["gzip_ms"] > 0 else None,
+                                     "bins_inflated_and_compared": checked,
                                      "note": "gz_hist / gz_table / gz_measure / gz_layout / gz_zero / gz_encode "
                                              "(csrc/orc_gz.cuh) behind one step of %d reads, device time between "
                                              "events; shared-memory-pipe bound (one code and one CRC look-up per "
