@@ -320,3 +320,35 @@ def test_cli_anchored_and_no_indels(tmp_path):
                        oqual[int(rs2.offsets[i]):int(rs2.offsets[i]) + int(olen[i])].tobytes() + b"\n"
                        for i in np.flatnonzero(rec0["adapter"] == a))
         assert _read_gz(out2 / (nm + ".fastq.gz")) == exp, nm
+
+
+def test_two_round_on_empty_and_tiny_inputs(tmp_path):
+    """The fused command (members coded on the GPU by default, and with --host-gzip) on an empty input and on a
+    single read: all 96 files exist, every one is a valid .gz, the read lands where the oracle puts it."""
+    fwd, rev, _ = m13.write_tables(str(tmp_path / "adapters"))
+    one = synth.generate(40, 300, 900, seed=9)
+    rec0, rec1, oseq, oqual, olen = H.run_oracle(H.m13_rounds(), one)
+    keep = [i for i in range(one.n_reads) if rec0["adapter"][i] >= 0 and 0 <= rec1["adapter"][i] < 8][:1]
+    assert keep
+    i = keep[0]
+    name, sq, ql = one.read(i)
+    cases = {"empty": b"", "one": ("@%s\n%s\n+\n%s\n" % (name, sq, ql)).encode()}
+    for tag, text in cases.items():
+        for extra in ([], ["--host-gzip"]):
+            (tmp_path / "pychopped").mkdir(exist_ok=True)
+            infile = tmp_path / "pychopped" / ("pychopped_%s.fastq" % tag)
+            infile.write_bytes(text)
+            out = tmp_path / ("demuxed_%s_%d" % (tag, len(extra)))
+            r = subprocess.run([sys.executable, "-m", "orcdemux.cli", "two-round", str(infile), "--sp5", fwd, "--sp27", rev,
+                                "--outdir", str(out)] + extra, capture_output=True, text=True,
+                               env=dict(os.environ, PYTHONPATH=H.PKG))
+            assert r.returncode == 0, r.stderr
+            files = sorted(glob.glob(str(out / "SP27" / "*.fastq.gz")))
+            assert len(files) == 96
+            total = b"".join(_read_gz(f) for f in files)
+            if tag == "empty":
+                assert total == b""
+            else:
+                o, L = int(one.offsets[i]), int(olen[i])
+                nm = name + (" rc" if rec0["is_rc"][i] else "") + (" rc" if rec1["is_rc"][i] else "")
+                assert total == b"@" + nm.encode() + b"\n" + oseq[o:o + L].tobytes() + b"\n+\n" + oqual[o:o + L].tobytes() + b"\n"

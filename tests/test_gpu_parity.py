@@ -244,6 +244,33 @@ def test_bins_as_gzip_members_made_on_the_device(tmp_path):
     assert ref.n_reads == rs.n_reads
 
 
+def test_gzip_members_other_shapes():
+    """emit_gzip beyond the COI two-round case: one round (13 bins, nothing dropped), kilobase reads, one read of
+    120 kb beside short ones (a member far larger than a tile of chunks), reads with lower case / N / IUPAC bytes,
+    and batches reusing one slot with different sizes (stale bytes behind a smaller batch must not leak)."""
+    import zlib
+    from test_gz import check_members
+    import random
+    rnd = random.Random(77)
+    long_read = "".join(rnd.choice("ACGT") for _ in range(120000))
+    odd = [("o%d" % i, "".join(rnd.choice("ACGTNacgtnRYKM") for _ in range(rnd.randint(1, 700))), None) for i in range(300)]
+    odd = [(n, q, "".join(chr(33 + rnd.randint(0, 60)) for _ in q)) for n, q, _ in odd]
+    sets = [synth.generate(3000, 1000, 3500, seed=1003),
+            synth.from_records([("long", long_read, "I" * len(long_read))] + odd),
+            synth.generate(700, 300, 900, seed=3)]
+    for rounds in (E.m13_rounds(), E.m13_rounds()[:1]):
+        cap_r = max(x.n_reads for x in sets)
+        cap_b = max(int(x.seq.shape[0]) for x in sets) + 64
+        kw = dict(device=0, max_reads=cap_r, max_bytes=cap_b, max_name_bytes=64 * cap_r, n_slots=1, want_matches=False)
+        with E.Engine(rounds, **kw) as plain, E.Engine(rounds, emit_gzip=True, **kw) as gz:
+            for rs in sets:                                         # one slot, batches of different sizes in turn
+                want, got = plain.run(rs), gz.run(rs)
+                pieces = [want.bin_bytes(b) for b in range(plain.n_bins)]
+                check_members(got.fastq.tobytes(), got.bin_offsets, pieces)
+                assert np.array_equal(got.bin_counts, want.bin_counts)
+                assert sum(len(p) for p in pieces) == int(want.bin_offsets[-1])
+
+
 def test_config2_full_size_every_read():
     """BASELINE configs[1] at its full size (1 Mi COI reads, seed 1002): the oracle on EVERY read -- all eight
     match fields of both rounds, trimmed length, bin, and the bytes of all 169 bins -- plus the
