@@ -326,41 +326,61 @@ ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint
     crc_out = crc ^ 0xFFFFFFFFu;
 }
 
-// The chunk's bytes as codes, from bit `bit0` of the (zeroed) output on.
+// The chunk's bytes as codes, from bit `bit0` of the (zeroed) output on.  The first word (it may hold bits of the
+// chunk in front) and the last one go in by OR, the words between by plain stores: byte by byte until the first
+// word is out and the text stands at a 16-byte boundary, then 16 bytes at a time with nothing but predicated
+// stores in the loop.
 ORC_HD void gz_chunk_encode(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint32_t *sym,
                             uint64_t bit0, uint32_t *__restrict__ out)
 {
-    uint64_t wi = bit0 >> 5;
+    uint32_t *w = out + (bit0 >> 5);
     uint32_t fill = (uint32_t)(bit0 & 31u);
     uint64_t acc = 0;
-    bool first = true;          // the first word may hold bits of the chunk in front: or, do not store
     // fill < 32 whenever a word has been taken out; two codes add 30 bits at most, so acc holds them
-#define GZ_TAKE_WORD()                                                                  \
-    if (fill >= 32u) {                                                                  \
-        if (first) { gz_or(out + wi, (uint32_t)acc); first = false; }                   \
-        else out[wi] = (uint32_t)acc;                                                   \
-        wi++; acc >>= 32; fill -= 32u;                                                  \
-    }
 #define GZ_BYTE(c)                                                                      \
     { const uint32_t e = sym[c]; acc |= (uint64_t)(e & 0xFFFFu) << fill; fill += e >> 16; }
+#define GZ_PAIR(c0, c1)                                                                 \
+    { const uint32_t e0 = sym[c0], e1 = sym[c1];                                        \
+      const uint32_t two = (e0 & 0xFFFFu) | ((e1 & 0xFFFFu) << (e0 >> 16));             \
+      acc |= (uint64_t)two << fill; fill += (e0 >> 16) + (e1 >> 16); }
+#define GZ_TAKE_WORD()                                                                  \
+    { const bool full = fill >= 32u;                                                    \
+      if (full) *w = (uint32_t)acc;                                                     \
+      w += full ? 1 : 0; acc = full ? acc >> 32 : acc; fill -= full ? 32u : 0u; }
     uint64_t p = lo;
-    for (; p < hi && (p & 15u); p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD(); }
+    bool first = true;
+    for (; p < hi && (first || (p & 15u)); p++) {
+        GZ_BYTE(text[p]);
+        if (fill >= 32u) {
+            if (first) { gz_or(w, (uint32_t)acc); first = false; }
+            else *w = (uint32_t)acc;
+            w++; acc >>= 32; fill -= 32u;
+        }
+    }
     for (; p + 16 <= hi; p += 16) {
         const gz_vec16 q = *reinterpret_cast<const gz_vec16 *>(text + p);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t v[4] = {q.x, q.y, q.z, q.w};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int k = 0; k < 4; k++) {
-            const uint32_t x = w[k];
-            GZ_BYTE(x & 255u); GZ_BYTE((x >> 8) & 255u); GZ_TAKE_WORD();
-            GZ_BYTE((x >> 16) & 255u); GZ_BYTE(x >> 24); GZ_TAKE_WORD();
+            const uint32_t x = v[k];
+            GZ_PAIR(x & 255u, (x >> 8) & 255u); GZ_TAKE_WORD();
+            GZ_PAIR((x >> 16) & 255u, x >> 24); GZ_TAKE_WORD();
         }
     }
-    for (; p < hi; p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD(); }
+    for (; p < hi; p++) {
+        GZ_BYTE(text[p]);
+        if (fill >= 32u) {
+            if (first) { gz_or(w, (uint32_t)acc); first = false; }
+            else *w = (uint32_t)acc;
+            w++; acc >>= 32; fill -= 32u;
+        }
+    }
 #undef GZ_BYTE
+#undef GZ_PAIR
 #undef GZ_TAKE_WORD
-    if (fill) gz_or(out + wi, (uint32_t)acc);
+    if (fill) gz_or(w, (uint32_t)acc);
 }
 
 // Per member, after its chunks were measured: the frame around the codes.  data_bits = the chunks' bits.
