@@ -350,8 +350,8 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         }
     ctx->total_counts.assign((size_t)ctx->n_bins, 0);
     ctx->fastq_cap = ctx->max_name_bytes + 2 * ctx->max_bytes + 16ull * ctx->max_reads + 64;
-    // literals-only Huffman coding never needs much more than 8 bits per byte; frame and block header per member
-    ctx->gz_cap = (ctx->fastq_cap + ctx->fastq_cap / 32 + 256ull * (uint64_t)ctx->n_bins + 64 + 15) & ~15ull;
+    // the flat code orc_wait() falls back to takes 9 bits per byte at most; frame and block header per member
+    ctx->gz_cap = (ctx->fastq_cap + ctx->fastq_cap / 8 + 256ull * (uint64_t)ctx->n_bins + 64 + 15) & ~15ull;
     ctx->gz_max_chunks = ctx->fastq_cap / GZ_CHUNK + (uint64_t)ctx->n_bins + 2;
     if (ctx->emit_gzip && ctx->gz_cap >= (1ull << 32)) {
         // a member's "OC" size field and its ISIZE are 32 bits wide
@@ -670,6 +670,32 @@ extern "C" int orc_export(orc_ctx *ctx, int slot, uint8_t *seq, uint8_t *qual, u
     return ORC_OK;
 }
 
+// The bins of the slot's FASTQ text as gzip members (orc_gz.cuh): sampled histogram -> the batch's Huffman code ->
+// bits per chunk (prefix sums per tile) and the members' CRCs -> where tiles and members start -> the codes.
+// flat: a code of 8- and 9-bit lengths instead of the histogram's (see gz_table_kernel).
+static int launch_gz(orc_ctx *ctx, Slot &s, int flat, uint32_t &nl)
+{
+    cudaStream_t st = s.stream;
+    const int nb = ctx->n_bins;
+    const uint64_t *total = s.d_bin_offsets + nb;
+    CK(cudaMemsetAsync(s.d_gz_hist, 0, 256 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(s.d_gz_member_crc, 0, (size_t)nb * sizeof(uint32_t), st));
+    if (!flat) { gz_hist_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(s.d_fastq, total, s.d_gz_hist); nl++; }
+    gz_table_kernel<<<1, 512, 0, st>>>(s.d_gz_hist, s.d_gz_table, nb, s.d_bin_offsets, s.d_gz_chunk_base, flat); nl++;
+    gz_measure_kernel<<<ctx->sm_count * 8, GZ_TILE, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
+                                                            s.d_gz_chunk_local, s.d_gz_tile_bits, s.d_gz_member_crc); nl++;
+    gz_layout_kernel<<<1, 1024, 0, st>>>(s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table, s.d_gz_chunk_local,
+                                         s.d_gz_tile_bits, s.d_gz_tile_off, s.d_gz_member_pos, s.d_gz_member_bits,
+                                         s.d_gz_member_bytes, s.d_gz_offsets); nl++;
+    gz_zero_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(s.d_gz_offsets, nb, ctx->gz_cap, reinterpret_cast<uint4 *>(s.d_gz)); nl++;
+    gz_encode_kernel<<<ctx->sm_count * 16, 128, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
+                                                        s.d_gz_chunk_local, s.d_gz_tile_off, s.d_gz_member_pos,
+                                                        s.d_gz_member_bits, s.d_gz_member_crc, s.d_gz_member_bytes,
+                                                        s.d_gz_offsets, ctx->gz_cap, s.d_gz); nl++;
+    CK(cudaGetLastError());
+    return ORC_OK;
+}
+
 extern "C" int orc_launch(orc_ctx *ctx, int slot)
 {
     Slot *sp = get_slot(ctx, slot);
@@ -839,24 +865,8 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
     }
     CK(cudaEventRecord(s.ev[EV_EMIT], st));
     if (n && s.has_names && ctx->emit_gzip) {
-        // the bins as gzip members (orc_gz.cuh): sampled histogram -> the batch's Huffman code -> bits per chunk
-        // (prefix sums per tile) and the members' CRCs -> where tiles and members start -> the codes
-        const int nb = ctx->n_bins;
-        const uint64_t *total = s.d_bin_offsets + nb;
-        CK(cudaMemsetAsync(s.d_gz_hist, 0, 256 * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(s.d_gz_member_crc, 0, (size_t)nb * sizeof(uint32_t), st));
-        gz_hist_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(s.d_fastq, total, s.d_gz_hist); nl++;
-        gz_table_kernel<<<1, 512, 0, st>>>(s.d_gz_hist, s.d_gz_table, nb, s.d_bin_offsets, s.d_gz_chunk_base); nl++;
-        gz_measure_kernel<<<ctx->sm_count * 8, GZ_TILE, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
-                                                                s.d_gz_chunk_local, s.d_gz_tile_bits, s.d_gz_member_crc); nl++;
-        gz_layout_kernel<<<1, 1024, 0, st>>>(s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table, s.d_gz_chunk_local,
-                                             s.d_gz_tile_bits, s.d_gz_tile_off, s.d_gz_member_pos, s.d_gz_member_bits,
-                                             s.d_gz_member_bytes, s.d_gz_offsets); nl++;
-        gz_zero_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(s.d_gz_offsets, nb, ctx->gz_cap, reinterpret_cast<uint4 *>(s.d_gz)); nl++;
-        gz_encode_kernel<<<ctx->sm_count * 16, 128, 0, st>>>(s.d_fastq, s.d_bin_offsets, nb, s.d_gz_chunk_base, s.d_gz_table,
-                                                           s.d_gz_chunk_local, s.d_gz_tile_off, s.d_gz_member_pos,
-                                                           s.d_gz_member_bits, s.d_gz_member_crc, s.d_gz_member_bytes,
-                                                           s.d_gz_offsets, ctx->gz_cap, s.d_gz); nl++;
+        const int rc = launch_gz(ctx, s, 0, nl);
+        if (rc != ORC_OK) return rc;
     }
     CK(cudaEventRecord(s.ev[EV_GZ], st));
     CK(cudaGetLastError());
@@ -952,8 +962,18 @@ extern "C" int orc_wait(orc_ctx *ctx, int slot, orc_result *out)
     }
     const bool gz = ctx->emit_gzip && s.has_names && s.n_reads;     // the bins come back as gzip members
     if (s.has_names && s.h_bin_offsets[ctx->n_bins] > ctx->fastq_cap) { ctx->err = "internal: FASTQ output exceeds its arena"; return ORC_ECAPACITY; }
-    const uint64_t fq = !s.has_names ? 0 : gz ? s.h_gz_offsets[ctx->n_bins] : s.h_bin_offsets[ctx->n_bins];
-    if (gz && fq > ctx->gz_cap) { ctx->err = "internal: gzip output exceeds its arena"; return ORC_ECAPACITY; }
+    uint64_t fq = !s.has_names ? 0 : gz ? s.h_gz_offsets[ctx->n_bins] : s.h_bin_offsets[ctx->n_bins];
+    if (gz && (fq > ctx->gz_cap || getenv("ORC_GZ_FORCE_FLAT"))) {
+        // the sampled histogram was so far off the batch's bytes that the members outgrew the arena (the encoder wrote
+        // nothing): code the batch again with 8- and 9-bit codes, which fit by construction
+        uint32_t nl = 0;
+        const int rc = launch_gz(ctx, s, 1, nl);
+        if (rc != ORC_OK) return rc;
+        CK(cudaMemcpyAsync(s.h_gz_offsets, s.d_gz_offsets, sizeof(uint64_t) * (ctx->n_bins + 1), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        fq = s.h_gz_offsets[ctx->n_bins];
+        if (fq > ctx->gz_cap) { ctx->err = "internal: gzip output exceeds its arena"; return ORC_ECAPACITY; }
+    }
     if (fq && !s.h_fastq) CK(halloc(&s.h_fastq, (size_t)std::max(ctx->fastq_cap, ctx->emit_gzip ? ctx->gz_cap : 0)));
     if (fq) CK(cudaMemcpyAsync(s.h_fastq, gz ? s.d_gz : s.d_fastq, fq, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.ev[EV_END], s.stream));

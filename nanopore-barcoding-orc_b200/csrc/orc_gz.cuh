@@ -460,12 +460,14 @@ gz_hist_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ to
 // one block: the code of the batch; chunk_base[m] = chunks of the members in front of member m
 __global__ void __launch_bounds__(512)
 gz_table_kernel(const unsigned long long *__restrict__ hist, GzTable *__restrict__ T, int n_members,
-                const uint64_t *__restrict__ bin_offsets, uint32_t *__restrict__ chunk_base)
+                const uint64_t *__restrict__ bin_offsets, uint32_t *__restrict__ chunk_base, int flat)
 {
     __shared__ GzWork K;
     __shared__ uint32_t s_chunks[MAX_BINS_GZ];
     const int t = threadIdx.x;
-    if (t < 257) K.w[t] = gz_weight(hist, t);
+    // flat: every symbol the same weight -- 8- and 9-bit codes, a member can then not exceed 9/8 of its text (what
+    // orc_wait() falls back to when a batch's sampled histogram was so far off its bytes that the arena overflowed)
+    if (t < 257) K.w[t] = flat ? 1ull : gz_weight(hist, t);
     for (int m = t; m < n_members; m += blockDim.x) s_chunks[m] = gz_member_chunks(bin_offsets[m], bin_offsets[m + 1]);
     __syncthreads();
     if (t < 257) K.order[gz_rank(K.w, t)] = t;

@@ -2,6 +2,7 @@
 // with loops where the kernels have threads (one iteration per chunk / per lane / per member), so that the
 // members can be handed to zlib without a GPU (tests/test_gz.py).
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -26,6 +27,11 @@ extern "C" long long gzsim_compress(const uint8_t *text, const uint64_t *bin_off
             for (int k = 0; k < 16; k++) hist[text[16 * gz_sample_at(i) + k]]++;
         for (uint64_t p = n16 << 4; p < total; p++) hist[text[p]]++;
     }
+    if (getenv("GZSIM_FLAT")) {                                                       // gz_table_kernel, flat
+        for (int t = 0; t < 257; t++) K.w[t] = 1;
+        for (int t = 0; t < 257; t++) K.order[gz_rank(K.w, t)] = t;
+        gz_build_from_sorted(T, K, 0, 1, GzNoSync());
+    } else
     gz_build_table(hist.data(), T, K);                                                // gz_table_kernel
     if (code_lengths) memcpy(code_lengths, T.len, 257);
     std::vector<uint32_t> chunk_base(n_bins + 1, 0);

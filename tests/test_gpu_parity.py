@@ -271,6 +271,25 @@ def test_gzip_members_other_shapes():
                 assert sum(len(p) for p in pieces) == int(want.bin_offsets[-1])
 
 
+def test_gzip_flat_code_fallback(monkeypatch):
+    """What orc_wait() does when the members of a batch outgrow their arena (a sampled histogram far off the
+    batch's bytes): the batch is coded again with 8- and 9-bit codes, which fit by construction.
+    ORC_GZ_FORCE_FLAT takes that path for every batch."""
+    from test_gz import check_members
+    rs = synth.generate(5000, 300, 900, seed=35)
+    with _engine(rs.n_reads, rs.seq.shape[0]) as plain, _engine(rs.n_reads, rs.seq.shape[0], emit_gzip=True) as gz:
+        want = plain.run(rs)
+        monkeypatch.setenv("ORC_GZ_FORCE_FLAT", "1")
+        got = gz.run(rs)
+        monkeypatch.delenv("ORC_GZ_FORCE_FLAT")
+        pieces = [want.bin_bytes(b) for b in range(plain.n_bins)]
+        check_members(got.fastq.tobytes(), got.bin_offsets, pieces)
+        assert 1.0 < got.fastq.shape[0] / want.fastq.shape[0] < 1.15         # 8 bits per byte and the frames
+        again = gz.run(rs)                                                    # and back to the batch's own code
+        check_members(again.fastq.tobytes(), again.bin_offsets, pieces)
+        assert again.fastq.shape[0] < 0.62 * want.fastq.shape[0]
+
+
 def test_config2_full_size_every_read():
     """BASELINE configs[1] at its full size (1 Mi COI reads, seed 1002): the oracle on EVERY read -- all eight
     match fields of both rounds, trimmed length, bin, and the bytes of all 169 bins -- plus the

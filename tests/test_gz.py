@@ -114,3 +114,18 @@ def test_one_large_member():
     gz, gzo, _ = _compress([data])
     check_members(gz, gzo, [data])
     assert len(gz) < 0.29 * len(data)                                         # two bits per base (one of the four takes three: the end-of-block code needs a leaf)
+
+
+def test_flat_code_fits_nine_eighths(monkeypatch):
+    """The fallback of orc_wait() when a batch's members outgrow their arena (gz_table_kernel flat = 1): 8- and
+    9-bit codes whatever the bytes are, so a member never exceeds 9/8 of its text plus frame and block header."""
+    monkeypatch.setenv("GZSIM_FLAT", "1")
+    rnd = np.random.default_rng(5)
+    data = rnd.integers(0, 256, size=400_000, dtype=np.uint8).tobytes()
+    pieces = [data[:1000], data[1000:250_000], b"", data[250_000:]]
+    gz, gzo, lens = _compress(pieces)
+    assert int(lens.min()) >= 8 and int(lens.max()) <= 9
+    check_members(gz, gzo, pieces)
+    for m, piece in enumerate(pieces):
+        if piece:
+            assert int(gzo[m + 1]) - int(gzo[m]) <= len(piece) * 9 // 8 + 256
