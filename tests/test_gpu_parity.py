@@ -214,6 +214,8 @@ def test_bins_as_gzip_members_made_on_the_device(tmp_path):
         assert np.array_equal(got.bin, want.bin) and np.array_equal(got.bin_counts, want.bin_counts)
         t = gz.timings(0)
         assert t["gzip_bytes"] == got.fastq.shape[0] and t["gzip_ms"] > 0
+        tl = gz.timeline(0)                 # upload reached, H2D, matching, emit, gzip, D2H: in this order
+        assert all(b >= a for a, b in zip(tl, tl[1:])) and tl[4] - tl[3] > 0
         assert got.fastq.shape[0] < 0.62 * want.fastq.shape[0]
         # the writer: members as they are into .gz files, inflated into plain ones
         paths = [None if drop[b] else str(tmp_path / ("bin%03d.fastq%s" % (b, ".gz" if b % 2 else ""))) for b in range(169)]
