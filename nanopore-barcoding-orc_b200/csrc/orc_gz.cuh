@@ -7,7 +7,7 @@
 // members in parallel).
 //
 // A member holds ONE dynamic-Huffman DEFLATE block of literals only (no LZ77 matches: bases and qualities of
-// nanopore reads hardly repeat, zlib's own matches gain a few per cent on them): the code is built per batch
+// nanopore reads hardly repeat, zlib's own matches gain about a tenth on them): the code is built per batch
 // from a sampled byte histogram of the batch's FASTQ text, so every member of the batch carries the same block
 // header.  Encoding is then a table look-up per byte; where a byte's bits go is a prefix sum of code lengths,
 // taken per chunk of GZ_CHUNK bytes (one thread), per tile of GZ_TILE chunks (one block), per batch.  CRC-32 of a
@@ -36,7 +36,7 @@ constexpr int MAX_BINS_GZ = 512;            // == MAX_BINS (orc_kernels.cuh)
 
 struct GzTable {
     uint16_t code[257];     // Huffman code of byte b (256: end of block), bit-reversed: DEFLATE packs codes MSB first
-    uint8_t len[257];       // its length in bits; 0: b does not occur in this batch
+    uint8_t len[257];       // its length in bits, 1..15 (every byte value has a code: gz_build_from_sorted)
     uint8_t pad_;
     uint32_t hdr_nbits;
     uint32_t hdr[GZ_HDR_WORDS];     // BFINAL BTYPE HLIT HDIST HCLEN, the code-length code, the 258 code lengths
