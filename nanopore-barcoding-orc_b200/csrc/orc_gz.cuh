@@ -41,8 +41,10 @@ struct GzTable {
     uint32_t hdr_nbits;
     uint32_t hdr[GZ_HDR_WORDS];     // BFINAL BTYPE HLIT HDIST HCLEN, the code-length code, the 258 code lengths
     uint32_t sym[257];              // code[b] | len[b] << 16: one look-up per byte in the kernels
-    uint32_t crc_tab[4][256];       // CRC-32 (0xEDB88320): [0] the byte table, [k] = [0] moved past k zero bytes
-                                    // (slicing-by-4: four independent look-ups per 32-bit word)
+    uint32_t crc_tab[16][256];      // CRC-32 (0xEDB88320): [0] the byte table, [k] = [0] moved past k zero bytes
+                                    // (slicing-by-16: of the sixteen look-ups per 16 bytes only the four of the first
+                                    // word depend on the running CRC, the other twelve are indexed by text bytes --
+                                    // few distinct values in FASTQ text, so few shared-memory bank conflicts)
     uint32_t crc_pow[32][32];       // crc_pow[k]: the operator "append 2^k zero bytes" on a CRC, as a 32 x 32 bit matrix
 };
 
@@ -62,7 +64,7 @@ inline void gz_fill_crc_tables(GzTable &T)
         T.crc_tab[0][n] = c;
     }
     for (uint32_t n = 0; n < 256; n++)
-        for (int k = 1; k < 4; k++) T.crc_tab[k][n] = T.crc_tab[0][T.crc_tab[k - 1][n] & 255u] ^ (T.crc_tab[k - 1][n] >> 8);
+        for (int k = 1; k < 16; k++) T.crc_tab[k][n] = T.crc_tab[0][T.crc_tab[k - 1][n] & 255u] ^ (T.crc_tab[k - 1][n] >> 8);
     // the operator for one zero BIT, squared three times = one zero byte, squared on = 2^k bytes
     uint32_t odd[32], even[32];
     odd[0] = 0xEDB88320u;
@@ -291,8 +293,8 @@ typedef uint4 gz_vec16;
 struct alignas(16) gz_vec16 { uint32_t x, y, z, w; };     // the host simulation's stand-in for uint4
 #endif
 
-// Bits the chunk's bytes take, and their CRC-32.  sym: GzTable.sym, crc_tab: GzTable.crc_tab (both in shared
-// memory on the device).  16 bytes at a time between the first and the last 16-byte boundary of the chunk (the
+// Bits the chunk's bytes take, and their CRC-32 (slicing-by-16).  sym: GzTable.sym, crc_tab: GzTable.crc_tab (both in
+// shared memory on the device).  16 bytes at a time between the first and the last 16-byte boundary of the chunk (the
 // text starts at a 16-byte-aligned address).
 ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint32_t *sym,
                              const uint32_t (*crc_tab)[256], uint32_t &bits, uint32_t &crc_out)
@@ -313,9 +315,12 @@ ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint
         for (int k = 0; k < 4; k++) {
             const uint32_t x = w[k];
             nb += (sym[x & 255u] >> 16) + (sym[(x >> 8) & 255u] >> 16) + (sym[(x >> 16) & 255u] >> 16) + (sym[x >> 24] >> 16);
-            crc ^= x;
-            crc = crc_tab[3][crc & 255u] ^ crc_tab[2][(crc >> 8) & 255u] ^ crc_tab[1][(crc >> 16) & 255u] ^ crc_tab[0][crc >> 24];
         }
+        const uint32_t x0 = crc ^ w[0];
+        crc = crc_tab[15][x0 & 255u] ^ crc_tab[14][(x0 >> 8) & 255u] ^ crc_tab[13][(x0 >> 16) & 255u] ^ crc_tab[12][x0 >> 24] ^
+              crc_tab[11][w[1] & 255u] ^ crc_tab[10][(w[1] >> 8) & 255u] ^ crc_tab[9][(w[1] >> 16) & 255u] ^ crc_tab[8][w[1] >> 24] ^
+              crc_tab[7][w[2] & 255u] ^ crc_tab[6][(w[2] >> 8) & 255u] ^ crc_tab[5][(w[2] >> 16) & 255u] ^ crc_tab[4][w[2] >> 24] ^
+              crc_tab[3][w[3] & 255u] ^ crc_tab[2][(w[3] >> 8) & 255u] ^ crc_tab[1][(w[3] >> 16) & 255u] ^ crc_tab[0][w[3] >> 24];
     }
     for (; p < hi; p++) {
         const uint8_t c = text[p];
@@ -529,12 +534,12 @@ gz_measure_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__
                   uint32_t *__restrict__ chunk_local, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ member_crc)
 {
     __shared__ uint32_t s_base[MAX_BINS_GZ + 1];
-    __shared__ uint32_t s_crc[4][256];
+    __shared__ uint32_t s_crc[16][256];
     __shared__ uint32_t s_pow[32][32];
     __shared__ uint32_t s_sym[257];
     __shared__ uint32_t s_warp[33];
     for (int i = threadIdx.x; i <= n_members; i += blockDim.x) s_base[i] = chunk_base[i];
-    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_crc[0][0])[i] = (&T->crc_tab[0][0])[i];
+    for (int i = threadIdx.x; i < 16 * 256; i += blockDim.x) (&s_crc[0][0])[i] = (&T->crc_tab[0][0])[i];
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) (&s_pow[0][0])[i] = (&T->crc_pow[0][0])[i];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) s_sym[i] = T->sym[i];
     __syncthreads();
