@@ -293,17 +293,20 @@ typedef uint4 gz_vec16;
 struct alignas(16) gz_vec16 { uint32_t x, y, z, w; };     // the host simulation's stand-in for uint4
 #endif
 
-// Bits the chunk's bytes take, and their CRC-32 (slicing-by-16).  sym: GzTable.sym, crc_tab: GzTable.crc_tab (both in
+// byte k of a word, zero-extended: one PRMT on the device
+ORC_HD uint32_t gz_byte(uint32_t x, int k) { return byte_perm(x, 0u, 0x4440u + (uint32_t)k); }
+
+// Bits the chunk's bytes take, and their CRC-32 (slicing-by-16).  len: GzTable.len, crc_tab: GzTable.crc_tab (both in
 // shared memory on the device).  16 bytes at a time between the first and the last 16-byte boundary of the chunk (the
 // text starts at a 16-byte-aligned address).
-ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint32_t *sym,
+ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint8_t *len,
                              const uint32_t (*crc_tab)[256], uint32_t &bits, uint32_t &crc_out)
 {
     uint32_t nb = 0, crc = 0xFFFFFFFFu;
     uint64_t p = lo;
     for (; p < hi && (p & 15u); p++) {
         const uint8_t c = text[p];
-        nb += sym[c] >> 16;
+        nb += len[c];
         crc = crc_tab[0][(crc ^ c) & 255u] ^ (crc >> 8);
     }
     for (; p + 16 <= hi; p += 16) {
@@ -314,17 +317,17 @@ ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint
 #endif
         for (int k = 0; k < 4; k++) {
             const uint32_t x = w[k];
-            nb += (sym[x & 255u] >> 16) + (sym[(x >> 8) & 255u] >> 16) + (sym[(x >> 16) & 255u] >> 16) + (sym[x >> 24] >> 16);
+            nb += (uint32_t)len[gz_byte(x, 0)] + len[gz_byte(x, 1)] + len[gz_byte(x, 2)] + len[gz_byte(x, 3)];
         }
         const uint32_t x0 = crc ^ w[0];
-        crc = crc_tab[15][x0 & 255u] ^ crc_tab[14][(x0 >> 8) & 255u] ^ crc_tab[13][(x0 >> 16) & 255u] ^ crc_tab[12][x0 >> 24] ^
-              crc_tab[11][w[1] & 255u] ^ crc_tab[10][(w[1] >> 8) & 255u] ^ crc_tab[9][(w[1] >> 16) & 255u] ^ crc_tab[8][w[1] >> 24] ^
-              crc_tab[7][w[2] & 255u] ^ crc_tab[6][(w[2] >> 8) & 255u] ^ crc_tab[5][(w[2] >> 16) & 255u] ^ crc_tab[4][w[2] >> 24] ^
-              crc_tab[3][w[3] & 255u] ^ crc_tab[2][(w[3] >> 8) & 255u] ^ crc_tab[1][(w[3] >> 16) & 255u] ^ crc_tab[0][w[3] >> 24];
+        crc = crc_tab[15][gz_byte(x0, 0)] ^ crc_tab[14][gz_byte(x0, 1)] ^ crc_tab[13][gz_byte(x0, 2)] ^ crc_tab[12][gz_byte(x0, 3)] ^
+              crc_tab[11][gz_byte(w[1], 0)] ^ crc_tab[10][gz_byte(w[1], 1)] ^ crc_tab[9][gz_byte(w[1], 2)] ^ crc_tab[8][gz_byte(w[1], 3)] ^
+              crc_tab[7][gz_byte(w[2], 0)] ^ crc_tab[6][gz_byte(w[2], 1)] ^ crc_tab[5][gz_byte(w[2], 2)] ^ crc_tab[4][gz_byte(w[2], 3)] ^
+              crc_tab[3][gz_byte(w[3], 0)] ^ crc_tab[2][gz_byte(w[3], 1)] ^ crc_tab[1][gz_byte(w[3], 2)] ^ crc_tab[0][gz_byte(w[3], 3)];
     }
     for (; p < hi; p++) {
         const uint8_t c = text[p];
-        nb += sym[c] >> 16;
+        nb += len[c];
         crc = crc_tab[0][(crc ^ c) & 255u] ^ (crc >> 8);
     }
     bits = nb;
@@ -335,57 +338,61 @@ ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint
 // chunk in front) and the last one go in by OR, the words between by plain stores: byte by byte until the first
 // word is out and the text stands at a 16-byte boundary, then 16 bytes at a time with nothing but predicated
 // stores in the loop.
+ORC_HD uint32_t gz_spill(uint32_t v, uint32_t sh)      // the bits of v that leave a 32-bit word when v moves up by sh < 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(v, 0u, sh);
+#else
+    return sh ? v >> (32u - sh) : 0u;
+#endif
+}
 ORC_HD void gz_chunk_encode(const uint8_t *__restrict__ text, uint64_t lo, uint64_t hi, const uint32_t *sym,
                             uint64_t bit0, uint32_t *__restrict__ out)
 {
-    uint32_t *w = out + (bit0 >> 5);
+    uint32_t *const base = out + (bit0 >> 5);
+    uint32_t wo = 0;                                    // word of `base` the accumulator's low half belongs to
     uint32_t fill = (uint32_t)(bit0 & 31u);
-    uint64_t acc = 0;
-    // fill < 32 whenever a word has been taken out; two codes add 30 bits at most, so acc holds them
+    uint32_t a_lo = 0, a_hi = 0;                        // the accumulator: fill bits, fill < 32 between the steps
+    // two codes add 30 bits at most, so the 64 bits hold them
 #define GZ_BYTE(c)                                                                      \
-    { const uint32_t e = sym[c]; acc |= (uint64_t)(e & 0xFFFFu) << fill; fill += e >> 16; }
+    { const uint32_t e = sym[c], v = e & 0xFFFFu;                                       \
+      a_hi |= gz_spill(v, fill); a_lo |= v << fill; fill += e >> 16; }
 #define GZ_PAIR(c0, c1)                                                                 \
     { const uint32_t e0 = sym[c0], e1 = sym[c1];                                        \
-      const uint32_t two = (e0 & 0xFFFFu) | ((e1 & 0xFFFFu) << (e0 >> 16));             \
-      acc |= (uint64_t)two << fill; fill += (e0 >> 16) + (e1 >> 16); }
+      const uint32_t v = (e0 & 0xFFFFu) | ((e1 & 0xFFFFu) << (e0 >> 16));               \
+      a_hi |= gz_spill(v, fill); a_lo |= v << fill; fill += (e0 >> 16) + (e1 >> 16); }
 #define GZ_TAKE_WORD()                                                                  \
     { const bool full = fill >= 32u;                                                    \
-      if (full) *w = (uint32_t)acc;                                                     \
-      w += full ? 1 : 0; acc = full ? acc >> 32 : acc; fill -= full ? 32u : 0u; }
+      if (full) base[wo] = a_lo;                                                        \
+      a_lo = full ? a_hi : a_lo; a_hi = full ? 0u : a_hi;                               \
+      wo += full ? 1u : 0u; fill -= full ? 32u : 0u; }
+#define GZ_TAKE_WORD_EDGE()                                                             \
+    if (fill >= 32u) {                                                                  \
+        if (first) { gz_or(base + wo, a_lo); first = false; }                           \
+        else base[wo] = a_lo;                                                           \
+        a_lo = a_hi; a_hi = 0u; wo++; fill -= 32u;                                      \
+    }
     uint64_t p = lo;
     bool first = true;
-    for (; p < hi && (first || (p & 15u)); p++) {
-        GZ_BYTE(text[p]);
-        if (fill >= 32u) {
-            if (first) { gz_or(w, (uint32_t)acc); first = false; }
-            else *w = (uint32_t)acc;
-            w++; acc >>= 32; fill -= 32u;
-        }
-    }
+    for (; p < hi && (first || (p & 15u)); p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD_EDGE(); }
     for (; p + 16 <= hi; p += 16) {
         const gz_vec16 q = *reinterpret_cast<const gz_vec16 *>(text + p);
-        const uint32_t v[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t v4[4] = {q.x, q.y, q.z, q.w};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int k = 0; k < 4; k++) {
-            const uint32_t x = v[k];
-            GZ_PAIR(x & 255u, (x >> 8) & 255u); GZ_TAKE_WORD();
-            GZ_PAIR((x >> 16) & 255u, x >> 24); GZ_TAKE_WORD();
+            const uint32_t x = v4[k];
+            GZ_PAIR(gz_byte(x, 0), gz_byte(x, 1)); GZ_TAKE_WORD();
+            GZ_PAIR(gz_byte(x, 2), gz_byte(x, 3)); GZ_TAKE_WORD();
         }
     }
-    for (; p < hi; p++) {
-        GZ_BYTE(text[p]);
-        if (fill >= 32u) {
-            if (first) { gz_or(w, (uint32_t)acc); first = false; }
-            else *w = (uint32_t)acc;
-            w++; acc >>= 32; fill -= 32u;
-        }
-    }
+    for (; p < hi; p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD_EDGE(); }
 #undef GZ_BYTE
 #undef GZ_PAIR
 #undef GZ_TAKE_WORD
-    if (fill) gz_or(w, (uint32_t)acc);
+#undef GZ_TAKE_WORD_EDGE
+    if (fill) gz_or(base + wo, a_lo);
 }
 
 // Per member, after its chunks were measured: the frame around the codes.  data_bits = the chunks' bits.
@@ -536,12 +543,12 @@ gz_measure_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__
     __shared__ uint32_t s_base[MAX_BINS_GZ + 1];
     __shared__ uint32_t s_crc[16][256];
     __shared__ uint32_t s_pow[32][32];
-    __shared__ uint32_t s_sym[257];
+    __shared__ uint8_t s_len[260];
     __shared__ uint32_t s_warp[33];
     for (int i = threadIdx.x; i <= n_members; i += blockDim.x) s_base[i] = chunk_base[i];
     for (int i = threadIdx.x; i < 16 * 256; i += blockDim.x) (&s_crc[0][0])[i] = (&T->crc_tab[0][0])[i];
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) (&s_pow[0][0])[i] = (&T->crc_pow[0][0])[i];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) s_sym[i] = T->sym[i];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) s_len[i] = T->len[i];
     __syncthreads();
     const uint32_t n_chunks = s_base[n_members];
     const uint32_t n_tiles = (n_chunks + GZ_TILE - 1) / GZ_TILE;
@@ -554,7 +561,7 @@ gz_measure_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__
             uint64_t lo, hi;
             gz_chunk_range(bin_offsets[m], end, c - s_base[m], lo, hi);
             uint32_t crc;
-            gz_chunk_measure(text, lo, hi, s_sym, s_crc, bits, crc);
+            gz_chunk_measure(text, lo, hi, s_len, s_crc, bits, crc);
             const uint32_t moved = gz_crc_shift(s_pow, crc, end - hi);
             if (moved) atomicXor(member_crc + m, moved);
         }

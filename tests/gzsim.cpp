@@ -45,7 +45,7 @@ extern "C" long long gzsim_compress(const uint8_t *text, const uint64_t *bin_off
         uint64_t lo, hi;
         gz_chunk_range(bin_offsets[m], bin_offsets[m + 1], c - chunk_base[m], lo, hi);
         uint32_t bits, crc;
-        gz_chunk_measure(text, lo, hi, T.sym, T.crc_tab, bits, crc);
+        gz_chunk_measure(text, lo, hi, T.len, T.crc_tab, bits, crc);
         member_crc[m] ^= gz_crc_shift(T.crc_pow, crc, bin_offsets[m + 1] - hi);
         chunk_local[c] = tile_bits[c / GZ_TILE];
         tile_bits[c / GZ_TILE] += bits;
