@@ -309,22 +309,27 @@ ORC_HD void gz_chunk_measure(const uint8_t *__restrict__ text, uint64_t lo, uint
         nb += len[c];
         crc = crc_tab[0][(crc ^ c) & 255u] ^ (crc >> 8);
     }
-    for (; p + 16 <= hi; p += 16) {
-        const gz_vec16 q = *reinterpret_cast<const gz_vec16 *>(text + p);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 4; k++) {
-            const uint32_t x = w[k];
-            nb += (uint32_t)len[gz_byte(x, 0)] + len[gz_byte(x, 1)] + len[gz_byte(x, 2)] + len[gz_byte(x, 3)];
-        }
-        const uint32_t x0 = crc ^ w[0];
-        crc = crc_tab[15][gz_byte(x0, 0)] ^ crc_tab[14][gz_byte(x0, 1)] ^ crc_tab[13][gz_byte(x0, 2)] ^ crc_tab[12][gz_byte(x0, 3)] ^
-              crc_tab[11][gz_byte(w[1], 0)] ^ crc_tab[10][gz_byte(w[1], 1)] ^ crc_tab[9][gz_byte(w[1], 2)] ^ crc_tab[8][gz_byte(w[1], 3)] ^
-              crc_tab[7][gz_byte(w[2], 0)] ^ crc_tab[6][gz_byte(w[2], 1)] ^ crc_tab[5][gz_byte(w[2], 2)] ^ crc_tab[4][gz_byte(w[2], 3)] ^
-              crc_tab[3][gz_byte(w[3], 0)] ^ crc_tab[2][gz_byte(w[3], 1)] ^ crc_tab[1][gz_byte(w[3], 2)] ^ crc_tab[0][gz_byte(w[3], 3)];
+#define GZ_MEASURE16(q)                                                                                           \
+    {                                                                                                             \
+        const uint32_t w[4] = {(q).x, (q).y, (q).z, (q).w};                                                        \
+        for (int k = 0; k < 4; k++)                                                                               \
+            nb += (uint32_t)len[gz_byte(w[k], 0)] + len[gz_byte(w[k], 1)] + len[gz_byte(w[k], 2)] + len[gz_byte(w[k], 3)]; \
+        const uint32_t x0 = crc ^ w[0];                                                                           \
+        crc = crc_tab[15][gz_byte(x0, 0)] ^ crc_tab[14][gz_byte(x0, 1)] ^ crc_tab[13][gz_byte(x0, 2)] ^ crc_tab[12][gz_byte(x0, 3)] ^ \
+              crc_tab[11][gz_byte(w[1], 0)] ^ crc_tab[10][gz_byte(w[1], 1)] ^ crc_tab[9][gz_byte(w[1], 2)] ^ crc_tab[8][gz_byte(w[1], 3)] ^ \
+              crc_tab[7][gz_byte(w[2], 0)] ^ crc_tab[6][gz_byte(w[2], 1)] ^ crc_tab[5][gz_byte(w[2], 2)] ^ crc_tab[4][gz_byte(w[2], 3)] ^ \
+              crc_tab[3][gz_byte(w[3], 0)] ^ crc_tab[2][gz_byte(w[3], 1)] ^ crc_tab[1][gz_byte(w[3], 2)] ^ crc_tab[0][gz_byte(w[3], 3)]; \
     }
+    for (; p + 16 <= hi && (p & 63u); p += 16) GZ_MEASURE16(*reinterpret_cast<const gz_vec16 *>(text + p));
+    // 64 bytes at a time, the four loads issued together: every lane walks its own chunk, so a warp's load touches 32
+    // lines -- the other three loads of the group find them in L1 while they are still there
+    for (; p + 64 <= hi; p += 64) {
+        const gz_vec16 *v = reinterpret_cast<const gz_vec16 *>(text + p);
+        const gz_vec16 q0 = v[0], q1 = v[1], q2 = v[2], q3 = v[3];
+        GZ_MEASURE16(q0); GZ_MEASURE16(q1); GZ_MEASURE16(q2); GZ_MEASURE16(q3);
+    }
+    for (; p + 16 <= hi; p += 16) GZ_MEASURE16(*reinterpret_cast<const gz_vec16 *>(text + p));
+#undef GZ_MEASURE16
     for (; p < hi; p++) {
         const uint8_t c = text[p];
         nb += len[c];
@@ -375,18 +380,22 @@ ORC_HD void gz_chunk_encode(const uint8_t *__restrict__ text, uint64_t lo, uint6
     uint64_t p = lo;
     bool first = true;
     for (; p < hi && (first || (p & 15u)); p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD_EDGE(); }
-    for (; p + 16 <= hi; p += 16) {
-        const gz_vec16 q = *reinterpret_cast<const gz_vec16 *>(text + p);
-        const uint32_t v4[4] = {q.x, q.y, q.z, q.w};
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 4; k++) {
-            const uint32_t x = v4[k];
-            GZ_PAIR(gz_byte(x, 0), gz_byte(x, 1)); GZ_TAKE_WORD();
-            GZ_PAIR(gz_byte(x, 2), gz_byte(x, 3)); GZ_TAKE_WORD();
-        }
+#define GZ_ENCODE16(q)                                                                  \
+    {                                                                                   \
+        const uint32_t v4[4] = {(q).x, (q).y, (q).z, (q).w};                              \
+        for (int k = 0; k < 4; k++) {                                                   \
+            GZ_PAIR(gz_byte(v4[k], 0), gz_byte(v4[k], 1)); GZ_TAKE_WORD();              \
+            GZ_PAIR(gz_byte(v4[k], 2), gz_byte(v4[k], 3)); GZ_TAKE_WORD();              \
+        }                                                                               \
     }
+    for (; p + 16 <= hi && (p & 63u); p += 16) GZ_ENCODE16(*reinterpret_cast<const gz_vec16 *>(text + p));
+    for (; p + 64 <= hi; p += 64) {             // the four loads of a group issued together (see gz_chunk_measure)
+        const gz_vec16 *v = reinterpret_cast<const gz_vec16 *>(text + p);
+        const gz_vec16 q0 = v[0], q1 = v[1], q2 = v[2], q3 = v[3];
+        GZ_ENCODE16(q0); GZ_ENCODE16(q1); GZ_ENCODE16(q2); GZ_ENCODE16(q3);
+    }
+    for (; p + 16 <= hi; p += 16) GZ_ENCODE16(*reinterpret_cast<const gz_vec16 *>(text + p));
+#undef GZ_ENCODE16
     for (; p < hi; p++) { GZ_BYTE(text[p]); GZ_TAKE_WORD_EDGE(); }
 #undef GZ_BYTE
 #undef GZ_PAIR
