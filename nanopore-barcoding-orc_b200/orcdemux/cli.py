@@ -512,7 +512,8 @@ def run_two_round(args: List[str], device=0) -> int:
     ap.add_argument("--keep-invalid", action="store_true", help="keep SP27_009..012 combinations")
     ap.add_argument("--no-gzip", action="store_true")
     ap.add_argument("-j", type=int, default=8)
-    ap.add_argument("--compression-level", type=int, default=1, help="gzip level of the bin files (cutadapt 4.x default: 1)")
+    ap.add_argument("--compression-level", type=int, default=1, help="gzip level of the bin files with --host-gzip (cutadapt 4.x default: 1); the members coded on the GPU "
+                         "are Huffman-only whatever the level")
     ap.add_argument("--host-gzip", action="store_true",
                     help="deflate the bin files with zlib on the host threads; default: the GPU codes every bin of a "
                          "batch as a gzip member (dynamic Huffman, literals only) and only those bytes come back")
