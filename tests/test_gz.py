@@ -129,3 +129,45 @@ def test_flat_code_fits_nine_eighths(monkeypatch):
     for m, piece in enumerate(pieces):
         if piece:
             assert int(gzo[m + 1]) - int(gzo[m]) <= len(piece) * 9 // 8 + 256
+
+
+def test_writer_takes_members_as_they_are(tmp_path):
+    """orc_writer_write_members (csrc/orc_io.cpp): the members of successive batches appended to .gz bin files as
+    they are and inflated into plain files, empty bins left as valid empty .gz, the byte counts per bin taken from
+    the members' ISIZE, a malformed member refused -- no GPU needed: the members come from the host build of the
+    encoder."""
+    from orcdemux import fastq as F
+    rs = synth.generate(1500, 300, 900, seed=21)
+    text = rs.to_fastq_bytes()
+    whole = synth.generate(300, 300, 900, seed=22).to_fastq_bytes()      # bin 0 holds whole records: read back below
+    cuts = [1000, 1000, 200000, len(text) // 2, len(text)]
+    batch1 = [whole] + [text[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    batch2 = [b"", text[:5000], b"", b"", text[5000:9000]]
+    paths = [str(tmp_path / "b0.fastq.gz"), str(tmp_path / "b1.fastq.gz"), str(tmp_path / "b2.fastq.gz"),
+             str(tmp_path / "b3.fastq"), None]
+    w = F.BinWriters(paths, 1, threads=3)
+
+    class R:
+        pass
+    for pieces in (batch1, batch2):
+        gz, gzo, _ = _compress(pieces)
+        r = R()
+        r.fastq = np.frombuffer(gz, dtype=np.uint8)
+        r.bin_offsets = gzo
+        w.wait(w.write_batch(r, members=True))
+    bad = R()
+    bad.fastq = np.frombuffer(b"not a gzip member at all, just thirty bytes..", dtype=np.uint8)
+    bad.bin_offsets = np.array([0, 40, 40, 40, 40, 40], dtype=np.uint64)
+    with pytest.raises(OSError):
+        w.write_batch(bad, members=True)
+    w.close()
+    assert gzip.open(paths[0], "rb").read() == batch1[0] + batch2[0]
+    assert gzip.open(paths[1], "rb").read() == batch1[1] + batch2[1]
+    assert gzip.open(paths[2], "rb").read() == batch1[2] + batch2[2]
+    assert open(paths[3], "rb").read() == batch1[3] + batch2[3]
+    assert w.bytes_written[:4] == [len(batch1[i]) + len(batch2[i]) for i in range(4)]
+    # what the writer left can be read back by the library's own reader (member-parallel inflate)
+    rd = F.FastqReader(paths[0], max_reads=1 << 16, max_bytes=1 << 26, keep=1, ahead=1, threads=4)
+    n = sum(tb.n_reads for tb in rd)
+    rd.close()
+    assert n == 300
