@@ -59,7 +59,9 @@ typedef struct orc_round_params {
                                        only with indels == 0 (Hamming fast path, up to 64 adapters) */
     const char *const *names;       /* [n_adapters] header.split()[0]; may be NULL */
     const char *const *sequences;   /* [n_adapters] NUL-terminated, <= ORC_MAX_ADAPTER_LEN (ORC_MAX_LONG_ADAPTER_LEN, see there); ACGT, or IUPAC codes (cutadapt's
-                                       adapter wildcards) in every adapter of every round */
+                                       adapter wildcards).  Plain and IUPAC adapters may stand side by side: all are then
+                                       compared through the IUPAC masks, which equals cutadapt's per-adapter choice except
+                                       for a read with U -- orc_wait() refuses a batch that holds one (ORC_EINVAL) */
     double max_error_rate;          /* -e  (values >= 1 are absolute error counts, as in cutadapt) */
     int32_t min_overlap;            /* -O  (cutadapt default 3) */
     int32_t indels;                 /* 1; 0 == --no-indels */

@@ -121,6 +121,8 @@ struct orc_ctx {
     bool anchored[2] = {false, false};
     LongTable h_long[2];
     LongTable *d_long[2] = {nullptr, nullptr};
+    bool need_u_check = false;              // plain and IUPAC adapters side by side: a batch whose reads hold U is refused
+    bool wild_codes = false;                // the reads are packed with U = T (some round compares through the IUPAC masks)
     bool longr[2] = {false, false};         // a round with an adapter over 64 nt (long_kernel)
     bool special[2] = {false, false};       // anchored or long: the round does not take the bit-parallel pipeline
     uint8_t *d_pack_lut = nullptr, *d_comp_lut = nullptr, *d_drop = nullptr;
@@ -331,6 +333,17 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         if (!why.empty()) { ctx->err = why; return ORC_EINVAL; }
         if (rp.action != ORC_ACTION_TRIM && rp.action != ORC_ACTION_RETAIN) { ctx->err = "unsupported: action must be trim or retain"; return ORC_EINVAL; }
         ctx->h_tab[r].action = rp.action;
+    }
+    {
+        // one code array serves every round: with IUPAC adapters anywhere, all rounds compare through the masks; the
+        // plain adapters among them differ from cutadapt's ASCII comparison only on a read with U (u_scan_kernel)
+        bool uses_codes[ORC_MAX_ROUNDS] = {};
+        for (int r = 0; r < p->n_rounds; r++) uses_codes[r] = !ctx->anchored[r];
+        ctx->need_u_check = unify_wildcards(ctx->h_tab, uses_codes, p->n_rounds);
+        ctx->wild_codes = false;
+        for (int r = 0; r < p->n_rounds; r++) ctx->wild_codes = ctx->wild_codes || (uses_codes[r] && ctx->h_tab[r].wild != 0);
+    }
+    for (int r = 0; r < p->n_rounds; r++) {
         ctx->h_seed[r].on = 0;
         if (!ctx->special[r]) {
             const char *off = getenv("ORC_NO_SEED");        // A/B measurements: keep the flank scan
@@ -342,12 +355,6 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
     ctx->n_bins = ctx->h_tab[0].n_adapters + 1;
     if (p->n_rounds == 2) ctx->n_bins *= ctx->h_tab[1].n_adapters + 1;
     if (ctx->n_bins > MAX_BINS) { ctx->err = "unsupported: more than 512 bins"; return ORC_EINVAL; }
-    // one code array serves both rounds, and the IUPAC comparison reads U as T where the plain one does not
-    for (int r = 1; r < p->n_rounds; r++)
-        if (ctx->h_tab[r].wild != ctx->h_tab[0].wild) {
-            ctx->err = "unsupported: one round with and one without IUPAC wildcards in its adapters";
-            return ORC_EINVAL;
-        }
     ctx->total_counts.assign((size_t)ctx->n_bins, 0);
     ctx->fastq_cap = ctx->max_name_bytes + 2 * ctx->max_bytes + 16ull * ctx->max_reads + 64;
     // the flat code orc_wait() falls back to takes 9 bits per byte at most; frame and block header per member
@@ -375,7 +382,7 @@ static int ctx_init(orc_ctx *ctx, const orc_params *p)
         }
     }
     uint8_t lut[256];
-    build_pack_lut(lut, ctx->h_tab[0].wild != 0);
+    build_pack_lut(lut, ctx->wild_codes);
     CK(dalloc(&ctx->d_pack_lut, 256));
     CK(cudaMemcpy(ctx->d_pack_lut, lut, 256, cudaMemcpyHostToDevice));
     build_complement_lut(lut);
@@ -723,6 +730,11 @@ extern "C" int orc_launch(orc_ctx *ctx, int slot)
             const int pack_blocks = (int)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16);
             pack_kernel<<<pack_blocks, 256, 0, st>>>(s.d_seq, W, n16, ctx->d_pack_lut); nl++;
         }
+        if (ctx->need_u_check) {
+            // counters[7]: some read holds a U (see unify_wildcards); orc_wait() refuses the batch
+            u_scan_kernel<<<std::min<uint32_t>((n + 7) / 8, (uint32_t)ctx->sm_count * 8), 256, 0, st>>>(
+                s.d_seq, s.d_offsets, s.d_lengths, n, s.d_counters + 7); nl++;
+        }
     }
     CK(cudaEventRecord(s.ev[EV_PACK], st));
     for (int r = 0; r < ctx->n_rounds; r++) {
@@ -959,6 +971,12 @@ extern "C" int orc_wait(orc_ctx *ctx, int slot, orc_result *out)
             if (rc != ORC_OK) return rc;
             CK(cudaEventSynchronize(s.ev[EV_HDR]));
         }
+    }
+    if (ctx->need_u_check && s.h_counters[7]) {
+        ctx->err = "unsupported: a read holds U, and the adapters mix plain ACGT sequences (cutadapt compares them as "
+                   "ASCII: U is not T) with IUPAC ones (compared through masks: U is T)";
+        s.state = SLOT_UPLOADED;
+        return ORC_EINVAL;
     }
     const bool gz = ctx->emit_gzip && s.has_names && s.n_reads;     // the bins come back as gzip members
     if (s.has_names && s.h_bin_offsets[ctx->n_bins] > ctx->fastq_cap) { ctx->err = "internal: FASTQ output exceeds its arena"; return ORC_ECAPACITY; }

@@ -58,7 +58,10 @@ struct RoundTable {
     int32_t min_overlap;            // -O, not yet clamped per adapter
     int32_t n_lanes;                // 2 * n_adapters
     int32_t action;                 // 0: trim, 1: retain (select_read)
-    int32_t pad_[2];
+    int32_t mixed;                  // 1: the round holds adapters with AND without IUPAC wildcards (all compared through the
+                                    // masks, which differs from cutadapt's ASCII comparison of the plain ones only for a read
+                                    // with U: orc_api.cu refuses such a batch)
+    int32_t pad_;
     int32_t m[MAX_AD];              // adapter length
     int32_t k[MAX_AD];              // int(max_error_rate * m)
     int32_t min_ov[MAX_AD];         // min(min_overlap, m)

@@ -666,6 +666,25 @@ anchored_kernel(const AnchoredTable *__restrict__ tab, const uint8_t *__restrict
 }
 
 // ------------------------------------------------------------------------------------
+// Is there a U among the bases of the batch?  One warp per read.  Only launched when plain and IUPAC adapters stand
+// side by side (unify_wildcards): such a read is the one case in which the masks and cutadapt's ASCII comparison of
+// the plain adapters disagree.
+__global__ void __launch_bounds__(256)
+u_scan_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ lengths,
+              uint32_t n_reads, uint32_t *__restrict__ flag)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    bool seen = false;
+    for (uint32_t r = warp; r < n_reads; r += n_warps) {
+        const uint8_t *s = seq + offsets[r];
+        const uint32_t len = lengths[r];
+        for (uint32_t i = lane; i < len; i += 32u) seen = seen || ((s[i] & 0xDFu) == (uint8_t)'U');
+    }
+    if (__any_sync(0xffffffffu, seen) && lane == 0) atomicOr(flag, 1u);
+}
+
+// ------------------------------------------------------------------------------------
 // A round with adapters over 64 nt (LongTable): one thread per (read, orientation) runs cutadapt's recurrence
 // for every adapter, its column in local memory.
 __global__ void __launch_bounds__(128)

@@ -108,9 +108,11 @@ inline std::string build_round_table(RoundTable &T, int n_adapters, int type, co
             T.kmax[a][0][L] = (uint8_t)(c5 > c6 ? c5 : c6);
         }
     }
-    if (n_wild != 0 && n_wild != n_adapters)
-        return "unsupported: adapters with and without IUPAC wildcards in one round";
+    // cutadapt decides per adapter: plain ones are compared as ASCII, those with wildcards through the IUPAC masks.
+    // A plain adapter is its own mask set with no N, so the masks serve a mixed round as well -- up to a read with
+    // U, which equals T only through the masks (T.mixed: orc_api.cu looks for U in the batch and refuses it)
     T.wild = n_wild ? 1 : 0;
+    T.mixed = (n_wild != 0 && n_wild != n_adapters) ? 1 : 0;
     for (int lane = 0; lane < T.n_lanes; lane++) {
         const int a = lane % n_adapters, dir = lane / n_adapters;
         const int m = T.m[a];
@@ -363,9 +365,8 @@ inline std::string build_long_table(LongTable &L, RoundTable &T, int n_adapters,
             L.kmax6[a][len] = (uint8_t)(c6 < 0 ? 0 : (c6 > 255 ? 255 : c6));
         }
     }
-    if (n_wild != 0 && n_wild != n_adapters)
-        return "unsupported: adapters with and without IUPAC wildcards in one round";
     T.n_adapters = n_adapters;
+    T.mixed = (n_wild != 0 && n_wild != n_adapters) ? 1 : 0;
     T.type = type;
     T.revcomp = revcomp ? 1 : 0;
     T.indels = indels ? 1 : 0;
@@ -373,6 +374,23 @@ inline std::string build_long_table(LongTable &L, RoundTable &T, int n_adapters,
     T.wild = n_wild ? 1 : 0;
     T.n_lanes = 0;
     return "";
+}
+
+// One code array serves every round of a ctx: if any round compares through the IUPAC masks, all of them do (reads
+// packed with U = T).  Returns whether a batch must be searched for U: some adapter of some unanchored round is plain
+// ACGT and would, in cutadapt, not take a read's U for its T.  (Anchored rounds read the ASCII bases themselves.)
+inline bool unify_wildcards(RoundTable *T, const bool *bit_parallel_or_long, int n_rounds)
+{
+    bool any_wild = false, any_plain = false;
+    for (int r = 0; r < n_rounds; r++) {
+        if (!bit_parallel_or_long[r]) continue;
+        any_wild = any_wild || T[r].wild != 0;
+        any_plain = any_plain || T[r].wild == 0 || T[r].mixed != 0;
+    }
+    if (!any_wild) return false;
+    for (int r = 0; r < n_rounds; r++)
+        if (bit_parallel_or_long[r]) T[r].wild = 1;
+    return any_plain;
 }
 
 // Anchored, no-indel round (ORC_PREFIX / ORC_SUFFIX).  Also fills the few RoundTable fields the

@@ -47,6 +47,11 @@ extern "C" int hostsim_demux(int n_rounds,
           : longr[1] ? build_long_table(LT[1], T[1], n_ad1, type1, seq1, e1, ov1, indels, rc1)
                     : build_round_table(T[1], n_ad1, type1, seq1, e1, ov1, indels, rc1, filter_mode);
     for (int rd = 0; rd < 2; rd++) anch[rd] = anch[rd] || longr[rd];     // below: "not the bit-parallel pipeline"
+    // one code array for every round (orc_api.cu ctx_init): masks everywhere if anywhere, before the seed tables
+    bool uses_codes[2] = {type0 < 2, n_rounds > 1 && type1 < 2};
+    const bool need_u_check = e.empty() && unify_wildcards(T, uses_codes, n_rounds);
+    bool wild_codes = false;
+    for (int rd = 0; e.empty() && rd < n_rounds; rd++) wild_codes = wild_codes || (uses_codes[rd] && T[rd].wild != 0);
     // filter_mode bit 2 (value 4) keeps the flank scan of stage 1 although seeds would be usable
     SeedTable *ST = new SeedTable[2];
     for (int rd = 0; rd < n_rounds; rd++) {
@@ -64,17 +69,22 @@ extern "C" int hostsim_demux(int n_rounds,
         delete[] ST;
         return -1;
     }
-    if (n_rounds > 1 && T[0].wild != T[1].wild) {
-        strncpy(err, "unsupported: one round with and one without IUPAC wildcards in its adapters", (size_t)err_len - 1);
-        err[err_len - 1] = 0;
-        delete[] T;
-        delete[] AT;
-        delete[] LT;
-        delete[] ST;
-        return -1;
+    if (need_u_check) {
+        // u_scan_kernel + orc_wait: plain and IUPAC adapters side by side, and a read with U
+        for (uint32_t r = 0; r < n_reads; r++)
+            for (uint32_t i = 0; i < lengths[r]; i++)
+                if ((seq[offsets[r] + i] & 0xDFu) == 'U') {
+                    strncpy(err, "unsupported: a read holds U, and the adapters mix plain ACGT sequences with IUPAC ones", (size_t)err_len - 1);
+                    err[err_len - 1] = 0;
+                    delete[] T;
+                    delete[] AT;
+                    delete[] LT;
+                    delete[] ST;
+                    return -1;
+                }
     }
     uint8_t lut[256];
-    build_pack_lut(lut, T[0].wild != 0);
+    build_pack_lut(lut, wild_codes);
     // flat pack with 4 guard words in front and 16 + 4 behind, like the device buffers
     const uint64_t n_words = (n_bytes + 7) / 8;
     std::vector<uint32_t> codes(n_words + 24, 0);

@@ -518,8 +518,48 @@ def test_iupac_adapter_sets_gpu():
         both = (rec0["is_rc"] == 1) & (rec1["is_rc"] == 1)
         done += int(both.sum())
     assert done > 0         # some reads were flipped twice
-    with pytest.raises(E.OrcError, match="unsupported"):
-        E.Engine([E.Round(["a", "b"], ["ACGTACGT", "ACGNACGT"], ORC_BACK, 0.1, 3, True, True)], max_reads=16, max_bytes=1024)
+
+
+def test_plain_and_iupac_adapters_side_by_side_gpu():
+    """Plain ACGT adapters beside IUPAC ones -- in one round, or one kind per round: all compared through the masks
+    (cutadapt decides per adapter; the results differ only for a read with U).  Matches, lengths and bytes against
+    the oracle; a batch with a U among its bases is refused by orc_wait (u_scan_kernel), and the slot stays usable."""
+    import random
+    import oracle
+    import test_hostsim as TH
+    from orcdemux.lib import ORC_BACK, ORC_FRONT
+    rnd = random.Random(809)
+    for trial in range(6):
+        f, b = TH._iupac_sets(rnd, n_in_front=(trial % 2 == 1))
+        pf = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([8, 17, 25, 40, 64]))) for _ in range(rnd.randint(1, 5))]
+        pb = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([8, 17, 25, 40, 64]))) for _ in range(rnd.randint(1, 5))]
+        if trial % 3 == 0:
+            f, b = (f + pf)[:16], (pb + b)[:16]
+        elif trial % 3 == 1:
+            f = pf
+        else:
+            b = pb
+        e = rnd.choice([0.0, 0.1, 0.1, 0.2])
+        spec = [(f, oracle.FRONT, e, 3, 1), (b, oracle.BACK, e, 3, 1)]
+        rs = TH._adversarial_reads(rnd, TH._instances(rnd, f), TH._instances(rnd, b), 1200)
+        rounds = [E.Round([str(i) for i in range(len(x[0]))], x[0], ORC_FRONT if x[1] == oracle.FRONT else ORC_BACK,
+                          x[2], x[3], True, True) for x in spec]
+        with E.Engine(rounds, max_reads=rs.n_reads, max_bytes=int(rs.seq.shape[0]) + 64,
+                      max_name_bytes=int(rs.names.shape[0]) + 64, n_slots=1, emit_fastq=True, want_matches=True) as eng:
+            res = eng.run(rs)
+            rec0, rec1, oseq, oqual, olen = H.run_oracle(spec, rs)
+            assert H.diff_matches(rec0, res.matches[0])[1] == 0, (trial, "round 1")
+            assert H.diff_matches(rec1, res.matches[1])[1] == 0, (trial, "round 2")
+            assert np.array_equal(res.out_len, olen)
+            exp = _expected_fastq(rs, rec0, rec1, oseq, oqual, olen, eng.n_bins, eng.bin_id)
+            for bb in range(eng.n_bins):
+                assert res.bin_bytes(bb) == exp[bb], "trial %d bin %d bytes differ" % (trial, bb)
+            if trial == 0:
+                with_u = synth.from_records([("u", "ACGUACGTTGCA" * 5, "I" * 60), ("v", "ACGTACGT", "I" * 8)])
+                with pytest.raises(E.OrcError, match="U"):
+                    eng.run(with_u)
+                again = eng.run(rs)                     # the slot is usable afterwards
+                assert np.array_equal(again.bin, res.bin)
 
 
 def test_adapters_over_64_nt_gpu():

@@ -394,12 +394,41 @@ def test_iupac_adapter_sets():
     sp = ["CATGTAATGCACGTACTTTCAGGGTNNNNNNNNNNNNNNNNNTGTAAAACGACGGCCA", "GATCAGGTGAGGCTGCGACGACTNNNNNNNNNNNNNNNNNCAGGAAACAGCTATGAC"]
     rs = _adversarial_reads(rnd, _instances(rnd, sp), _instances(rnd, sp), 600)
     _compare([(sp, oracle.BACK, 0.1, 3, 1)], rs)
-    # plain and wildcard adapters in one round, or in different rounds, are refused (U = T only for the latter)
-    one = synth.from_records([("x", "ACGT", "IIII")])
-    with pytest.raises(RuntimeError, match="unsupported"):
-        H.run_hostsim([(["ACGTACGT", "ACGNACGT"], oracle.BACK, 0.1, 3, 1)], one)
-    with pytest.raises(RuntimeError, match="unsupported"):
-        H.run_hostsim([(["ACGTACGT"], oracle.FRONT, 0.1, 3, 1), (["ACGNACGT"], oracle.BACK, 0.1, 3, 1)], one)
+
+
+def test_plain_and_iupac_adapters_side_by_side():
+    """cutadapt decides per adapter: a plain ACGT adapter is compared as ASCII, one with wildcards through the IUPAC
+    masks.  Mixed in one round, or one kind per round, all of them run through the masks here (a plain adapter is
+    its own mask set without N) -- the same results except for a read with U (T only through the masks), and a
+    batch that holds one is refused."""
+    rnd = random.Random(808)
+    hits = 0
+    for trial in range(10):
+        f, b = _iupac_sets(rnd, n_in_front=(trial % 2 == 1))
+        pf = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([8, 17, 25, 40, 64]))) for _ in range(rnd.randint(1, 5))]
+        pb = ["".join(rnd.choice("ACGT") for _ in range(rnd.choice([8, 17, 25, 40, 64]))) for _ in range(rnd.randint(1, 5))]
+        if trial % 3 == 0:          # mixed inside both rounds
+            f, b = (f + pf)[:16], (pb + b)[:16]
+            rnd.shuffle(f); rnd.shuffle(b)
+        elif trial % 3 == 1:        # a plain round in front of an IUPAC one
+            f = pf
+        else:                       # an IUPAC round in front of a plain one
+            b = pb
+        e = rnd.choice([0.0, 0.1, 0.1, 0.2])
+        ov = rnd.choice([1, 3, 5])
+        rounds = [(f, oracle.FRONT, e, ov, 1), (b, oracle.BACK, e, ov, 1)]
+        rs = _adversarial_reads(rnd, _instances(rnd, f), _instances(rnd, b), 500)
+        rec0, rec1 = _compare(rounds, rs, threads=4)
+        hits += int((rec0["adapter"] >= 0).sum()) + int((rec1["adapter"] >= 0).sum())
+    assert hits > 2000
+    # a read with U: refused when plain adapters stand beside IUPAC ones, fine when all are of one kind
+    u = synth.from_records([("x", "ACGUACGUACGT", "I" * 12)])
+    with pytest.raises(RuntimeError, match="unsupported.*U"):
+        H.run_hostsim([(["ACGTACGT", "ACGNACGT"], oracle.BACK, 0.1, 3, 1)], u)
+    with pytest.raises(RuntimeError, match="unsupported.*U"):
+        H.run_hostsim([(["ACGTACGT"], oracle.FRONT, 0.1, 3, 1), (["ACGNACGT"], oracle.BACK, 0.1, 3, 1)], u)
+    H.run_hostsim([(["ACGNACGT", "ACGRACGT"], oracle.BACK, 0.1, 3, 1)], u)
+    H.run_hostsim([(["ACGTACGT"], oracle.BACK, 0.1, 3, 1)], u)
 
 
 def test_iupac_degenerate_adapters():
