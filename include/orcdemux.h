@@ -255,12 +255,19 @@ typedef struct orc_text_batch {
 orc_reader *orc_reader_open(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
                             int pinned, char *err, size_t err_len);
 /* the same with the number of inflate threads given: a .gz written by orc_writer (its members carry a size
- * field) is inflated member by member on that many threads; any other input is read by one zlib stream.
- * orc_reader_open() picks half the host's hardware threads, at most 8. */
+ * field) is inflated member by member on that many threads; any other .gz file of 4 MiB or more -- the
+ * pychopped_<dataset>.fastq.gz that 02_cutadapt_loop.sh:64-72 reads -- is cut into chunks of its compressed
+ * bytes that the pool inflates side by side (csrc/orc_pgz.h: block starts found by trial, text in front of a
+ * chunk stood in for by markers, every chunk accepted only where it continues the one before it, CRC-32 and
+ * ISIZE of every member checked); stdin, plain text, small files and inflate_threads < 2 go through one zlib
+ * stream.  orc_reader_open() picks half the host's hardware threads, at most 8. */
 orc_reader *orc_reader_open_threads(const char *path, uint32_t max_reads, uint64_t max_bytes, int n_buffers,
                                     int pinned, int inflate_threads, char *err, size_t err_len);
 int orc_reader_next(orc_reader *r, orc_text_batch *out);
 int orc_reader_release(orc_reader *r, int buffer);
+/* 0: one zlib stream (or plain text), 1: member-parallel, 2: chunk-parallel; stats (may be NULL): text bytes
+ * the pool inflated / the reader thread inflated itself so far (mode 2) */
+int orc_reader_inflate_mode(orc_reader *r, uint64_t stats[2]);
 const char *orc_reader_error(orc_reader *r);
 void orc_reader_close(orc_reader *r);
 

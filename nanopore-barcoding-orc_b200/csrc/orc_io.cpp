@@ -3,9 +3,11 @@
 // writer of cutadapt's ParallelPipelineRunner, /root/reference/scripts/02_cutadapt_loop.sh:64-72
 // `-j 24`).
 //
-//   orc_reader   one thread inflates the input straight into a ring of page-locked text buffers
-//                and indexes the records (orc_fastq_index); the text itself is the batch that
-//                goes to the GPU (raw-text layout of orc_batch), so the host never copies a read.
+//   orc_reader   one thread fills a ring of page-locked text buffers with the inflated input and indexes
+//                the records (orc_fastq_index); the text itself is the batch that goes to the GPU
+//                (raw-text layout of orc_batch), so the host never copies a read.  The inflating is
+//                done by a thread pool where the file allows it: member by member for files of
+//                orc_writer (size fields), chunk by chunk for any other .gz (orc_pgz.h).
 //   orc_writer   one output file per bin; the bin-major FASTQ text of a batch is cut into
 //                chunks, a thread pool deflates them as independent gzip members and every file
 //                receives its members in submission order (a concatenation of gzip members is a
@@ -29,6 +31,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include "orc_pgz.h"
 
 namespace {
 
@@ -254,6 +258,7 @@ struct MemberSource {
 struct orc_reader {
     gzFile gz = nullptr;
     MemberSource *members = nullptr;    // set instead of gz for files orc_writer wrote
+    orcpgz::Source *pgz = nullptr;      // set instead of gz for any other .gz file: chunk-parallel inflate
     uint32_t max_reads = 0;
     uint64_t max_bytes = 0;
     std::vector<ReaderBuf> bufs;
@@ -305,6 +310,10 @@ struct orc_reader {
                 if (members) {
                     got = members->read(rb.text + fill, want);
                     if (got < 0) return fail(members->err);
+                    if (got == 0) eof = true;
+                } else if (pgz) {
+                    got = pgz->read(rb.text + fill, want);
+                    if (got < 0) return fail(pgz->err);
                     if (got == 0) eof = true;
                 } else {
                     got = gzread(gz, rb.text + fill, (unsigned)want);
@@ -380,7 +389,22 @@ extern "C" orc_reader *orc_reader_open_threads(const char *path, uint32_t max_re
             r->members = nullptr;
         }
     }
-    if (!r->members) {
+    // a .gz of any other origin (the pychopped_<dataset>.fastq.gz of 02_cutadapt_loop.sh:64-72): chunks of the
+    // compressed stream inflated on the pool (orc_pgz.h).  ORC_NO_PGZ=1 keeps the single zlib stream,
+    // ORC_PGZ_MIN / ORC_PGZ_CHUNK (bytes) move the smallest file and the chunk size (tests).
+    if (!r->members && strcmp(path, "-") != 0 && inflate_threads >= 2 && !getenv("ORC_NO_PGZ")) {
+        const char *e_min = getenv("ORC_PGZ_MIN"), *e_chunk = getenv("ORC_PGZ_CHUNK");
+        const size_t min_bytes = e_min ? (size_t)strtoull(e_min, nullptr, 10) : (size_t)4 << 20;
+        const size_t chunk = e_chunk ? (size_t)strtoull(e_chunk, nullptr, 10) : (size_t)1 << 20;
+        if (orcpgz::Source::probe(path, min_bytes)) {
+            r->pgz = new orcpgz::Source();
+            if (!r->pgz->start(path, inflate_threads, chunk)) {
+                delete r->pgz;
+                r->pgz = nullptr;
+            }
+        }
+    }
+    if (!r->members && !r->pgz) {
         if (strcmp(path, "-") == 0) r->gz = gzdopen(dup(0), "rb");
         else r->gz = gzopen(path, "rb");        // transparent for files that are not gzip
         if (!r->gz) {
@@ -445,6 +469,19 @@ extern "C" int orc_reader_release(orc_reader *r, int buffer)
     return ORC_OK;
 }
 
+// How the input is inflated: 0 one zlib stream (or plain text), 1 member-parallel (files of orc_writer),
+// 2 chunk-parallel (any other .gz).  stats (may be NULL): text bytes the pool decoded / the reader thread decoded
+// itself so far (mode 2 only).
+extern "C" int orc_reader_inflate_mode(orc_reader *r, uint64_t stats[2])
+{
+    if (!r) return ORC_EINVAL;
+    if (stats) {
+        stats[0] = r->pgz ? r->pgz->stat_parallel : 0;
+        stats[1] = r->pgz ? r->pgz->stat_serial : 0;
+    }
+    return r->pgz ? 2 : r->members ? 1 : 0;
+}
+
 extern "C" const char *orc_reader_error(orc_reader *r)
 {
     return r ? r->err.c_str() : "null reader";
@@ -461,6 +498,7 @@ extern "C" void orc_reader_close(orc_reader *r)
     if (r->th.joinable()) r->th.join();
     if (r->gz) gzclose(r->gz);
     delete r->members;
+    delete r->pgz;
     for (ReaderBuf &rb : r->bufs) {
         host_free(rb.text, rb.pinned[0]);
         host_free(rb.off, rb.pinned[1]);

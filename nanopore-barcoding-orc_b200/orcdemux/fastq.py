@@ -108,6 +108,12 @@ class FastqReader:
             out.bases = int(tb.total_bases)
             yield out
 
+    def inflate_mode(self):
+        """(mode, bytes inflated by the pool, bytes inflated by the reader thread): 0 one zlib stream,
+        1 member-parallel (files of orc_writer), 2 chunk-parallel (any other .gz)"""
+        st = (C.c_uint64 * 2)()
+        return int(self._L.orc_reader_inflate_mode(self._r, st)), int(st[0]), int(st[1])
+
     def close(self):
         if getattr(self, "_r", None):
             self._L.orc_reader_close(self._r)

@@ -180,3 +180,117 @@ def test_member_parallel_inflate_and_index_sidecar(tmp_path, reads):
     trunc.write_bytes(blob[:len(blob) - 9])
     with pytest.raises(ValueError, match="input"):
         text_of(str(trunc), 4)
+
+
+def _text_and_mode(path, threads, max_bytes=1 << 20):
+    with F.FastqReader(str(path), max_reads=4000, max_bytes=max_bytes, keep=2, ahead=2, pinned=False, threads=threads) as rd:
+        chunks = [tb.text[:tb.n_bytes].tobytes() for tb in rd]
+        return b"".join(chunks), rd.inflate_mode()
+
+
+@pytest.fixture(scope="module")
+def big_text():
+    """About 19 MB of FASTQ with qualities that do not repeat (gzip leaves 8-9 MB of it)."""
+    rs = synth.generate(14000, 300, 900, seed=11)
+    raw = bytearray(rs.to_fastq_bytes())
+    rng = np.random.default_rng(3)
+    off = 0
+    for i in range(rs.n_reads):            # the qualities line of every record: a random walk like a basecaller's
+        name, seq, _ = rs.read(i)
+        q0 = off + 1 + len(name) + 1 + len(seq) + 3
+        steps = rng.integers(-2, 3, len(seq))
+        raw[q0:q0 + len(seq)] = (33 + np.clip(20 + np.cumsum(steps), 2, 50)).astype(np.uint8).tobytes()
+        off = q0 + len(seq) + 1
+    assert off == len(raw)
+    return bytes(raw)
+
+
+def test_chunk_parallel_inflate_of_a_foreign_gzip(tmp_path, big_text, monkeypatch):
+    """A .gz this library did not write (02_cutadapt_loop.sh:64-72 reads pychopped_<dataset>.fastq.gz) is inflated
+    chunk by chunk on the pool (csrc/orc_pgz.h) and gives the bytes one zlib stream gives: levels 1-9, the
+    `gzip` program, chunks far smaller than a DEFLATE block (so that most block starts have to be bridged by the
+    reader thread), one thread per chunk; small files, stdin and ORC_NO_PGZ keep the zlib stream."""
+    raw = big_text
+    monkeypatch.setenv("ORC_PGZ_MIN", "1000000")
+    p = tmp_path / "in.fastq.gz"
+    for level in (1, 6, 9):
+        p.write_bytes(gzip.compress(raw, level))
+        for chunk, threads in ((1 << 20, 4), (1 << 18, 3), (30000, 8)):
+            monkeypatch.setenv("ORC_PGZ_CHUNK", str(chunk))
+            text, (mode, par, ser) = _text_and_mode(p, threads)
+            assert mode == 2 and par + ser == len(raw), (level, chunk, mode, par, ser)
+            assert text == raw, (level, chunk)
+            if chunk >= 1 << 18:
+                assert par > 0.9 * len(raw), (level, chunk, par, ser)      # the pool did the work
+    monkeypatch.setenv("ORC_PGZ_CHUNK", str(1 << 20))
+    plain = tmp_path / "x.fastq"
+    plain.write_bytes(raw)
+    subprocess.run(["gzip", "-k", "-f", str(plain)], check=True)
+    text, (mode, par, ser) = _text_and_mode(str(plain) + ".gz", 4, max_bytes=1 << 22)
+    assert mode == 2 and text == raw and ser == 0
+    # one inflate thread, the switch, a small file: one zlib stream
+    assert _text_and_mode(p, 1)[1][0] == 0
+    monkeypatch.setenv("ORC_NO_PGZ", "1")
+    text, (mode, _, _) = _text_and_mode(p, 4)
+    assert mode == 0 and text == raw
+    monkeypatch.delenv("ORC_NO_PGZ")
+    small = tmp_path / "small.fastq.gz"
+    small.write_bytes(gzip.compress(raw[:raw.index(b"\n@r", 200000) + 1], 6))
+    assert _text_and_mode(small, 4)[1][0] == 0
+
+
+def test_chunk_parallel_inflate_of_other_streams(tmp_path, big_text, monkeypatch):
+    """Members that end inside a chunk (cat a.gz b.gz ..., the usual way MinKNOW's files are joined), a header with
+    every optional field, stored and fixed-code blocks, full-flush points, bytes behind the last member."""
+    import zlib
+    raw = big_text
+    monkeypatch.setenv("ORC_PGZ_MIN", "100000")
+    monkeypatch.setenv("ORC_PGZ_CHUNK", str(1 << 19))
+    cuts = [0] + [raw.index(b"\n@r", c) + 1 for c in range(700000, len(raw) - 700000, 700000)] + [len(raw)]
+    p = tmp_path / "cat.fastq.gz"
+    p.write_bytes(b"".join(gzip.compress(raw[a:b], 6) for a, b in zip(cuts[:-1], cuts[1:])))
+    text, (mode, par, ser) = _text_and_mode(p, 4)
+    assert mode == 2 and text == raw and par > 0.9 * len(raw), (par, ser)
+    # FEXTRA + FNAME + FCOMMENT + FHCRC in front of a raw stream with sync and full flushes
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    parts = []
+    for i in range(0, len(raw), 250000):
+        parts.append(co.compress(raw[i:i + 250000]))
+        parts.append(co.flush(zlib.Z_FULL_FLUSH if (i // 250000) % 3 else zlib.Z_SYNC_FLUSH))
+    parts.append(co.flush())
+    hdr = bytes([0x1f, 0x8b, 8, 4 | 8 | 16 | 2, 0, 0, 0, 0, 0, 3]) + (5).to_bytes(2, "little") + b"ab\x01\x00z" + b"n.fq\0" + b"c\0"
+    hdr += (zlib.crc32(hdr) & 0xffff).to_bytes(2, "little")
+    p.write_bytes(hdr + b"".join(parts) + zlib.crc32(raw).to_bytes(4, "little") + (len(raw) & 0xffffffff).to_bytes(4, "little") + b"\0" * 512)
+    text, (mode, par, ser) = _text_and_mode(p, 4)
+    assert mode == 2 and text == raw
+    # fixed codes only, Huffman only, stored only (nothing for the pool to find: the reader thread decodes it)
+    part = raw[:raw.index(b"\n@r", 3000000) + 1]
+    for strategy, level in ((zlib.Z_FIXED, 6), (zlib.Z_HUFFMAN_ONLY, 6), (zlib.Z_DEFAULT_STRATEGY, 0)):
+        co = zlib.compressobj(level, zlib.DEFLATED, 31, 8, strategy)
+        p.write_bytes(co.compress(part) + co.flush())
+        text, (mode, par, ser) = _text_and_mode(p, 3)
+        assert mode == 2 and text == part, (strategy, level)
+
+
+def test_chunk_parallel_inflate_refuses_damaged_input(tmp_path, big_text, monkeypatch):
+    """A cut stream, a flipped bit in the codes, a wrong CRC-32 or length in the trailer: an error as from zlib, in
+    whatever chunk the damage lies."""
+    raw = big_text[:big_text.index(b"\n@r", 6000000) + 1]
+    good = gzip.compress(raw, 6)
+    monkeypatch.setenv("ORC_PGZ_MIN", "100000")
+    monkeypatch.setenv("ORC_PGZ_CHUNK", str(1 << 18))
+    p = tmp_path / "bad.fastq.gz"
+    rng = np.random.default_rng(5)
+    cases = [good[:len(good) // 2], good[:-5], good[:-8] + b"\0\0\0\0" + good[-4:], good[:-4] + b"\1\0\0\0"]
+    for _ in range(6):
+        b = bytearray(good)
+        b[int(rng.integers(100, len(good) - 100))] ^= 1 << int(rng.integers(0, 8))
+        cases.append(bytes(b))
+    for i, blob in enumerate(cases):
+        p.write_bytes(blob)
+        # ("reading the input: ..." from the inflate, or the indexer's complaint about text that a damaged code
+        # turned into something else -- that batch is handed on before the stream's CRC is reached, as with gzread)
+        with pytest.raises(ValueError):
+            _text_and_mode(p, 4)
+        with pytest.raises(Exception):
+            gzip.decompress(blob)
