@@ -78,7 +78,7 @@ constexpr size_t GZ_EXTRA_LEN = 8, GZ_SIZE_AT = 16;     // 10 header bytes, XLEN
 
 // ------------------------------------------------------------------------------------ member-parallel inflate
 // A .gz whose members carry this library's "OC" size field (everything orc_writer writes, e.g. the round-1
-// bins that round 2 reads back, 02_cutadapt_loop.sh:94-102) is inflated member by member on a thread
+// bins that round 2 reads back, 02_cutadapt_loop.sh:94-102) or BGZF's "BC" field (bgzip) is inflated member by member on a thread
 // pool: the headers are hopped over with the size field, the uncompressed size is the trailer's ISIZE, and
 // the text comes out in file order.  A member without the field ends the parallel part; the rest of the
 // file is then read through zlib's gzread from that offset on.
@@ -105,15 +105,29 @@ struct MemberSource {
     uint64_t cur_pos = 0;
     std::string err;
 
-    // the size field of the member at `at`, 0 if it has none
+    // the size of the member at `at` from its FEXTRA field, 0 if it says none: this library's "OC" subfield
+    // (32-bit size) or BGZF's "BC" (bgzip, htslib: 16-bit size - 1; members of at most 64 KiB)
     static uint64_t member_size(int fd, uint64_t at, uint64_t file_size)
     {
-        uint8_t h[20];
-        if (at + 20 > file_size || pread(fd, h, 20, (off_t)at) != 20) return 0;
+        uint8_t h[12 + 64];
+        if (at + 20 > file_size) return 0;
+        const size_t have = (size_t)std::min<uint64_t>(sizeof h, file_size - at);
+        if (pread(fd, h, have, (off_t)at) != (ssize_t)have) return 0;
         if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
-        if (h[10] != GZ_EXTRA_LEN || h[11] != 0 || h[12] != 'O' || h[13] != 'C' || h[14] != 4 || h[15] != 0) return 0;
-        const uint64_t n = (uint64_t)h[16] | ((uint64_t)h[17] << 8) | ((uint64_t)h[18] << 16) | ((uint64_t)h[19] << 24);
-        return (n >= 28 && at + n <= file_size) ? n : 0;
+        const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
+        if (12 + xlen > have) return 0;
+        for (size_t q = 12; q + 4 <= 12 + xlen;) {
+            const size_t len = (size_t)h[q + 2] | ((size_t)h[q + 3] << 8);
+            if (q + 4 + len > 12 + xlen) return 0;
+            uint64_t n = 0;
+            if (h[q] == 'O' && h[q + 1] == 'C' && len == 4)
+                n = (uint64_t)h[q + 4] | ((uint64_t)h[q + 5] << 8) | ((uint64_t)h[q + 6] << 16) | ((uint64_t)h[q + 7] << 24);
+            else if (h[q] == 'B' && h[q + 1] == 'C' && len == 2)
+                n = ((uint64_t)h[q + 4] | ((uint64_t)h[q + 5] << 8)) + 1;
+            if (n) return (n >= 12 + xlen + 10 && at + n <= file_size) ? n : 0;
+            q += 4 + len;
+        }
+        return 0;
     }
 
     static bool probe(const char *path)
@@ -167,6 +181,7 @@ struct MemberSource {
         file_size = (uint64_t)lseek(fd, 0, SEEK_END);
         if (threads < 1) threads = 1;
         max_inflight = (size_t)threads * 2;
+        if (member_size(fd, 0, file_size) <= (1u << 16)) max_inflight = (size_t)threads * 16;      // BGZF: small members
         for (int t = 0; t < threads; t++) pool.emplace_back([this] { worker(); });
         return true;
     }

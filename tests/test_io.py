@@ -294,3 +294,28 @@ def test_chunk_parallel_inflate_refuses_damaged_input(tmp_path, big_text, monkey
             _text_and_mode(p, 4)
         with pytest.raises(Exception):
             gzip.decompress(blob)
+
+
+def test_bgzf_members_are_inflated_in_parallel(tmp_path, reads):
+    """bgzip / htslib output: members of at most 64 KiB with the "BC" size subfield -- hopped over and inflated on
+    the pool like this library's own members."""
+    import zlib
+    _, raw = reads
+
+    def block(data):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(data) + co.flush()
+        total = 18 + len(body) + 8
+        return (bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0]) + b"BC\x02\x00" + (total - 1).to_bytes(2, "little") + body +
+                zlib.crc32(data).to_bytes(4, "little") + len(data).to_bytes(4, "little"))
+
+    blob = b"".join(block(raw[i:i + 65280]) for i in range(0, len(raw), 65280)) + block(b"")
+    assert gzip.decompress(blob) == raw
+    p = tmp_path / "in.fastq.bgz"
+    p.write_bytes(blob)
+    for threads in (1, 4):
+        text, (mode, _, _) = _text_and_mode(p, threads)
+        assert mode == 1 and text == raw
+    p.write_bytes(blob[:len(blob) // 2])
+    with pytest.raises(ValueError, match="input"):
+        _text_and_mode(p, 4)
