@@ -187,6 +187,7 @@ struct Decoder {
     Huff pre, lit, dist;
     std::vector<uint16_t> out;
     size_t op = WIN;
+    size_t max_out = (size_t)32 << 20;      // symbols after which run() stops at the next block border
 
     inline void refill()
     {
@@ -313,7 +314,9 @@ struct Decoder {
         seek(start_bit);
         for (;;) {
             const uint64_t pos = bitpos();
-            if (pos >= stop_at || pos == exact) { r.end_bit = pos; return r; }
+            // (max_out: text that inflates a thousandfold must not become gigabytes of symbols in one piece;
+            // whoever continues the chain takes up from end_bit)
+            if (pos >= stop_at || pos == exact || op - WIN >= max_out) { r.end_bit = pos; return r; }
             refill();
             if (cnt < 3) { r.err = "unexpected end of the stream"; return r; }
             const uint32_t bfinal = take(1), type = take(2);
