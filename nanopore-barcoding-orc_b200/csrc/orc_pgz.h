@@ -268,28 +268,50 @@ struct Decoder {
     const char *symbols(const Huff &L, const Huff &D, size_t avail_before)
     {
         const uint32_t *lt = L.t.data(), *dt = D.t.data();
+        uint16_t *o = out.data();
+        size_t cap = out.size();
+#define ORC_PGZ_LITLEN(e)                                                                              \
+    e = lt[buf & ((1u << LIT_PB) - 1)];                                                                \
+    if (kind_of(e) == K_SUB) e = lt[(e >> 16) + ((buf >> LIT_PB) & ((1u << (e & 0xff)) - 1))];
+#define ORC_PGZ_EAT(e)                                                                                 \
+    buf >>= (e & 0xff);                                                                                \
+    cnt -= (int)(e & 0xff);
         for (;;) {
-            if (op + 320 > out.size()) reserve(320);
-            uint16_t *o = out.data();
-            refill();
-            uint32_t e = lt[buf & ((1u << LIT_PB) - 1)];
-            if (kind_of(e) == K_SUB) e = lt[(e >> 16) + ((buf >> LIT_PB) & ((1u << (e & 0xff)) - 1))];
-            buf >>= (e & 0xff);
-            cnt -= (int)(e & 0xff);
-            const uint32_t k = kind_of(e);
-            if (k == K_LIT) {
-                o[op++] = (uint16_t)(e >> 16);
-                if (cnt < 0) return "unexpected end of the stream";
-                continue;
+            if (op + 320 > cap) {
+                reserve(320);
+                o = out.data();
+                cap = out.size();
             }
+            refill();                       // 56 bits or more: three literals, or one length / distance pair
+            uint32_t e;
+            ORC_PGZ_LITLEN(e)
+            if (kind_of(e) == K_LIT) {
+                ORC_PGZ_EAT(e)
+                o[op++] = (uint16_t)(e >> 16);
+                ORC_PGZ_LITLEN(e)
+                if (kind_of(e) == K_LIT) {
+                    ORC_PGZ_EAT(e)
+                    o[op++] = (uint16_t)(e >> 16);
+                    ORC_PGZ_LITLEN(e)
+                    if (kind_of(e) == K_LIT) {
+                        ORC_PGZ_EAT(e)
+                        o[op++] = (uint16_t)(e >> 16);
+                        if (cnt < 0) return "unexpected end of the stream";
+                        continue;
+                    }
+                }
+                if (cnt < 0) return "unexpected end of the stream";
+                refill();                   // (the bits of e are still in front)
+            }
+            ORC_PGZ_EAT(e)
+            const uint32_t k = kind_of(e);
             if (k == K_EOB) return cnt < 0 ? "unexpected end of the stream" : nullptr;
             if (k != K_BASE) return "invalid literal/length code";
             const int xl = (int)((e >> 8) & 15u);
             const size_t len = (e >> 16) + take(xl);
             uint32_t d = dt[buf & ((1u << DIST_PB) - 1)];
             if (kind_of(d) == K_SUB) d = dt[(d >> 16) + ((buf >> DIST_PB) & ((1u << (d & 0xff)) - 1))];
-            buf >>= (d & 0xff);
-            cnt -= (int)(d & 0xff);
+            ORC_PGZ_EAT(d)
             if (kind_of(d) != K_BASE) return "invalid distance code";
             const int xd = (int)((d >> 8) & 15u);
             const size_t dd = (d >> 16) + take(xd);
@@ -304,6 +326,8 @@ struct Decoder {
             }
             op += len;
         }
+#undef ORC_PGZ_LITLEN
+#undef ORC_PGZ_EAT
     }
 
     // From start_bit on, block after block, until a block ends at or behind stop_at, exactly on `exact`, or
