@@ -285,6 +285,7 @@ struct orc_reader {
     int error = 0;
     std::string err;
     std::vector<uint8_t> carry;
+    double t_read = 0, t_index = 0, t_wait_free = 0;    // reader thread: inflating / copying, indexing, waiting for a free buffer (ORC_IO_DEBUG=1)
 
     void fail(const std::string &what)
     {
@@ -308,8 +309,10 @@ struct orc_reader {
         for (;;) {
             int b;
             {
+                const double w0 = orcpgz::Source::now();
                 std::unique_lock<std::mutex> lk(mu);
                 cv_free.wait(lk, [&] { return stop || !free_q.empty(); });
+                t_wait_free += orcpgz::Source::now() - w0;
                 if (stop) return;
                 b = free_q.front();
                 free_q.pop_front();
@@ -318,6 +321,7 @@ struct orc_reader {
             uint64_t fill = carry.size();
             if (fill) memcpy(rb.text, carry.data(), fill);
             carry.clear();
+            const double r0 = orcpgz::Source::now();
             while (fill < max_bytes && !eof) {
                 uint64_t want = max_bytes - fill;
                 if (want > (1u << 30)) want = 1u << 30;
@@ -351,11 +355,14 @@ struct orc_reader {
                     if (stop) return;
                 }
             }
+            t_read += orcpgz::Source::now() - r0;
             if (fill == 0) return finish();
             uint64_t consumed = 0;
             char ebuf[256] = {0};
+            const double i0 = orcpgz::Source::now();
             int64_t n = orc_fastq_index(rb.text, fill, max_reads, eof ? 1 : 0, rb.off, rb.len, rb.qoff, rb.noff,
                                         rb.nlen, &consumed, ebuf, sizeof ebuf);
+            t_index += orcpgz::Source::now() - i0;
             if (n < 0) return fail(ebuf);
             if (n == 0) {
                 if (eof) return finish();       // nothing but blank lines
@@ -511,6 +518,11 @@ extern "C" void orc_reader_close(orc_reader *r)
         r->cv_free.notify_all();
     }
     if (r->th.joinable()) r->th.join();
+    if (getenv("ORC_IO_DEBUG"))
+        fprintf(stderr, "orc_reader: inflate mode %d, reader thread: read %.3f s (chunk-parallel: waiting %.3f, copying %.3f, own decoding %.3f), "
+                        "index %.3f s, waiting for a free buffer %.3f s\n", r->pgz ? 2 : r->members ? 1 : 0, r->t_read,
+                r->pgz ? r->pgz->stat_wait_s : 0.0, r->pgz ? r->pgz->stat_copy_s : 0.0, r->pgz ? r->pgz->stat_serial_s : 0.0,
+                r->t_index, r->t_wait_free);
     if (r->gz) gzclose(r->gz);
     delete r->members;
     delete r->pgz;

@@ -431,7 +431,9 @@ struct Chunk {
 struct Job {
     Piece piece;
     std::vector<uint8_t> lut;       // the window in front of the piece (only with markers)
-    std::vector<uint8_t> bytes;
+    std::vector<uint8_t> bytes;     // the text, unless it goes straight to its place:
+    uint8_t *dst = nullptr;         // where in the caller's buffer the piece belongs (it fits the current read())
+    size_t n_bytes = 0;
     uint32_t crc = 0;
     bool done = false;
     bool ends_member = false;
@@ -465,6 +467,9 @@ struct Source {
     std::deque<Seg> carry;              // further segments of the chunk accepted last
     // delivery (consumer thread)
     std::deque<std::shared_ptr<Job>> pending;
+    uint64_t pending_bytes = 0;         // text of the pending pieces that is not handed out yet
+    uint8_t *rd_dst = nullptr;          // the read() call under way
+    uint64_t rd_want = 0, rd_got = 0;
     size_t cur_pos = 0;
     uint32_t crc = 0;
     uint64_t delivered = 0;             // bytes of the current member handed out
@@ -579,10 +584,12 @@ struct Source {
 
     void resolve(Job &j)
     {
-        j.bytes = byte_pool.get();
-        j.bytes.resize(j.piece.n);
+        if (!j.dst) {
+            j.bytes = byte_pool.get();
+            j.bytes.resize(j.piece.n);
+        }
         const uint16_t *s = j.piece.sym.data() + WIN;
-        uint8_t *o = j.bytes.data();
+        uint8_t *o = j.dst ? j.dst : j.bytes.data();
         const size_t m = j.piece.n;
         uint32_t c = 0;
         for (size_t at = 0; at < m; at += 1u << 16) {          // sum while the bytes are in the cache
@@ -685,6 +692,11 @@ struct Source {
             if (next == NONE) finished = true;
             else P = next;
         }
+        // the pool writes the piece straight into the caller's buffer if all of it belongs to the current read()
+        // (behind what is pending in front of it); otherwise into a buffer of its own, copied when its turn comes
+        j->n_bytes = p.n;
+        if (rd_dst && rd_got + pending_bytes + p.n <= rd_want) j->dst = rd_dst + rd_got + pending_bytes;
+        pending_bytes += p.n;
         pending.push_back(j);
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -773,19 +785,30 @@ struct Source {
         return true;
     }
 
+    // no worker may still be writing into the caller's buffer when read() gives up
+    void drain_direct()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        for (auto &j : pending)
+            if (j->dst) cv_done.wait(lk, [&] { return j->done; });
+    }
+
     // like gzread: up to `want` bytes, 0 at the end of the input, -1 on error (err set; the text in front of the
     // damage has been handed out by then)
     int64_t read(uint8_t *dst, uint64_t want)
     {
-        uint64_t got = 0;
-        while (got < want) {
+        rd_dst = dst;
+        rd_want = want;
+        rd_got = 0;
+        int64_t rc = 0;
+        while (rd_got < want) {
             const bool can_advance = !finished && !failed && pending.size() < max_inflight;    // the chain runs ahead of the delivery
             if (pending.empty()) {
                 if (can_advance) {
                     if (!advance()) failed = true;
                     continue;
                 }
-                if (failed) return got ? (int64_t)got : -1;
+                if (failed && !rd_got) rc = -1;
                 break;
             }
             Job &j = *pending.front();
@@ -802,33 +825,44 @@ struct Source {
                     stat_wait_s += now() - w0;
                 }
             }
-            const double c0 = now();
-            const size_t m = (size_t)std::min<uint64_t>(want - got, j.bytes.size() - cur_pos);
-            memcpy(dst + got, j.bytes.data() + cur_pos, m);
-            got += m;
+            size_t m;
+            if (j.dst) {
+                m = j.n_bytes;              // already in its place
+            } else {
+                const double c0 = now();
+                m = (size_t)std::min<uint64_t>(want - rd_got, j.n_bytes - cur_pos);
+                memcpy(dst + rd_got, j.bytes.data() + cur_pos, m);
+                stat_copy_s += now() - c0;
+            }
+            rd_got += m;
             cur_pos += m;
-            stat_copy_s += now() - c0;
-            if (cur_pos == j.bytes.size()) {
-                crc = (uint32_t)crc32_combine(crc, j.crc, (z_off_t)j.bytes.size());
-                delivered += j.bytes.size();
+            pending_bytes -= m;
+            if (cur_pos == j.n_bytes) {
+                crc = (uint32_t)crc32_combine(crc, j.crc, (z_off_t)j.n_bytes);
+                delivered += j.n_bytes;
                 bool bad = false;
                 if (j.ends_member) {
                     bad = crc != j.want_crc || (uint32_t)delivered != j.want_n;
                     crc = 0;
                     delivered = 0;
                 }
-                byte_pool.put(std::move(j.bytes));
+                if (!j.dst) byte_pool.put(std::move(j.bytes));
                 pending.pop_front();
                 cur_pos = 0;
                 if (bad) {
                     err = "reading the input: corrupt gzip stream (CRC-32 differs)";
                     failed = true;
+                    drain_direct();
                     pending.clear();
-                    return -1;
+                    pending_bytes = 0;
+                    rc = -1;
+                    break;
                 }
             }
         }
-        return (int64_t)got;
+        if (rc < 0) drain_direct();
+        rd_dst = nullptr;
+        return rc < 0 ? rc : (int64_t)rd_got;
     }
 
     ~Source()
