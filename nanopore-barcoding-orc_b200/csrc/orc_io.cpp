@@ -22,6 +22,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -274,6 +275,7 @@ struct orc_reader {
     gzFile gz = nullptr;
     MemberSource *members = nullptr;    // set instead of gz for files orc_writer wrote
     orcpgz::Source *pgz = nullptr;      // set instead of gz for any other .gz file: chunk-parallel inflate
+    int plain_fd = -1;                  // set instead of gz for a file that is not gzip: read() straight into the buffers
     uint32_t max_reads = 0;
     uint64_t max_bytes = 0;
     std::vector<ReaderBuf> bufs;
@@ -333,6 +335,10 @@ struct orc_reader {
                 } else if (pgz) {
                     got = pgz->read(rb.text + fill, want);
                     if (got < 0) return fail(pgz->err);
+                    if (got == 0) eof = true;
+                } else if (plain_fd >= 0) {
+                    do got = ::read(plain_fd, rb.text + fill, want); while (got < 0 && errno == EINTR);
+                    if (got < 0) return fail(std::string("reading the input: ") + strerror(errno));
                     if (got == 0) eof = true;
                 } else {
                     got = gzread(gz, rb.text + fill, (unsigned)want);
@@ -426,7 +432,17 @@ extern "C" orc_reader *orc_reader_open_threads(const char *path, uint32_t max_re
             }
         }
     }
-    if (!r->members && !r->pgz) {
+    // a regular file that is not gzip (pychopper's *_pass.fastq, 01_pychopper.sh:57): no zlib in between
+    if (!r->members && !r->pgz && strcmp(path, "-") != 0) {
+        const int fd = open(path, O_RDONLY);
+        uint8_t magic[2] = {0, 0};
+        if (fd >= 0) {
+            const ssize_t k = pread(fd, magic, 2, 0);
+            if (k >= 0 && !(k == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) r->plain_fd = fd;
+            else close(fd);
+        }
+    }
+    if (!r->members && !r->pgz && r->plain_fd < 0) {
         if (strcmp(path, "-") == 0) r->gz = gzdopen(dup(0), "rb");
         else r->gz = gzopen(path, "rb");        // transparent for files that are not gzip
         if (!r->gz) {
@@ -498,8 +514,8 @@ extern "C" int orc_reader_inflate_mode(orc_reader *r, uint64_t stats[2])
 {
     if (!r) return ORC_EINVAL;
     if (stats) {
-        stats[0] = r->pgz ? r->pgz->stat_parallel : 0;
-        stats[1] = r->pgz ? r->pgz->stat_serial : 0;
+        stats[0] = r->pgz ? r->pgz->stat_parallel.load() : 0;
+        stats[1] = r->pgz ? r->pgz->stat_serial.load() : 0;
     }
     return r->pgz ? 2 : r->members ? 1 : 0;
 }
@@ -524,6 +540,7 @@ extern "C" void orc_reader_close(orc_reader *r)
                 r->pgz ? r->pgz->stat_wait_s : 0.0, r->pgz ? r->pgz->stat_copy_s : 0.0, r->pgz ? r->pgz->stat_serial_s : 0.0,
                 r->t_index, r->t_wait_free);
     if (r->gz) gzclose(r->gz);
+    if (r->plain_fd >= 0) close(r->plain_fd);
     delete r->members;
     delete r->pgz;
     for (ReaderBuf &rb : r->bufs) {

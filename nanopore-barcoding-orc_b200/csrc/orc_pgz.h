@@ -31,6 +31,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -473,7 +474,7 @@ struct Source {
     size_t cur_pos = 0;
     uint32_t crc = 0;
     uint64_t delivered = 0;             // bytes of the current member handed out
-    uint64_t stat_parallel = 0, stat_serial = 0;    // text bytes that came from the workers / from the consumer's own decoding
+    std::atomic<uint64_t> stat_parallel{0}, stat_serial{0};     // text bytes that came from the workers / from the consumer's own decoding (read by orc_reader_inflate_mode from another thread)
     double stat_wait_s = 0, stat_copy_s = 0, stat_serial_s = 0;     // consumer: waiting, copying out, own decoding
     static inline double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
