@@ -319,3 +319,44 @@ def test_bgzf_members_are_inflated_in_parallel(tmp_path, reads):
     p.write_bytes(blob[:len(blob) // 2])
     with pytest.raises(ValueError, match="input"):
         _text_and_mode(p, 4)
+
+
+def test_chunk_parallel_inflate_random_damage(tmp_path, big_text, monkeypatch):
+    """Random damage (flipped bits, cuts, zeroed and inserted stretches) to one-member and many-member files:
+    wherever python's gzip gives an error the reader gives one too, otherwise the same text; never a crash or a hang."""
+    import random
+    raw = big_text[:big_text.index(b"\n@r", 2500000) + 1]
+    one = gzip.compress(raw, 6)
+    cuts = [0] + [raw.index(b"\n@r", c) + 1 for c in range(250000, len(raw) - 250000, 250000)] + [len(raw)]
+    many = b"".join(gzip.compress(raw[a:b], 6) for a, b in zip(cuts[:-1], cuts[1:]))
+    monkeypatch.setenv("ORC_PGZ_MIN", "100000")
+    rnd = random.Random(20)
+    p = tmp_path / "d.fastq.gz"
+    refused = 0
+    for trial in range(40):
+        data = bytearray(rnd.choice([one, many]))
+        mode = rnd.choice(["flip", "cut", "zero", "insert"])
+        if mode == "flip":
+            data[rnd.randrange(len(data))] ^= 1 << rnd.randrange(8)
+        elif mode == "cut":
+            del data[rnd.randrange(100, len(data)):]
+        elif mode == "zero":
+            a = rnd.randrange(len(data) - 1)
+            b = min(len(data), a + rnd.randint(1, 3000))
+            data[a:b] = bytes(b - a)
+        else:
+            a = rnd.randrange(len(data))
+            data[a:a] = bytes(rnd.randrange(256) for _ in range(rnd.randint(1, 50)))
+        monkeypatch.setenv("ORC_PGZ_CHUNK", str(rnd.choice([30000, 1 << 17, 1 << 20])))
+        p.write_bytes(bytes(data))
+        try:
+            want = gzip.decompress(bytes(data))
+        except Exception:
+            want = None
+        if want is None:
+            refused += 1
+            with pytest.raises(ValueError):
+                _text_and_mode(p, rnd.choice([2, 5]))
+        else:
+            assert _text_and_mode(p, rnd.choice([2, 5]))[0] == want, (trial, mode)
+    assert refused >= 30
