@@ -269,6 +269,11 @@ int orc_reader_release(orc_reader *r, int buffer);
  * the pool inflated / the reader thread inflated itself so far (mode 2) */
 int orc_reader_inflate_mode(orc_reader *r, uint64_t stats[2]);
 const char *orc_reader_error(orc_reader *r);
+/* A whole gzip file (at least 64 bytes) inflated by the chunk-parallel source alone (csrc/orc_pgz.h) into
+ * out[0 .. cap): the number of bytes, ORC_ECAPACITY if they do not fit, ORC_EINVAL for a damaged stream (text in
+ * err).  chunk_bytes 0 = 1 MiB.  For tools and tests; orc_reader does the same for its batches. */
+int64_t orc_gunzip_file(const char *path, int threads, uint64_t chunk_bytes, uint8_t *out, uint64_t cap,
+                        char *err, size_t err_len);
 void orc_reader_close(orc_reader *r);
 
 /*

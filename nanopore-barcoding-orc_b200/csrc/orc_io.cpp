@@ -520,6 +520,28 @@ extern "C" int orc_reader_inflate_mode(orc_reader *r, uint64_t stats[2])
     return r->pgz ? 2 : r->members ? 1 : 0;
 }
 
+// A whole .gz file through the chunk-parallel inflate (orc_pgz.h) into out[0 .. cap): what orc_reader does with a
+// foreign .gz, without the FASTQ indexing -- for tools and for tests of streams that are not FASTQ.
+extern "C" int64_t orc_gunzip_file(const char *path, int threads, uint64_t chunk_bytes, uint8_t *out, uint64_t cap,
+                                   char *err, size_t err_len)
+{
+    if (!path || (!out && cap)) { set_err(err, err_len, "orc_gunzip_file: bad argument"); return ORC_EINVAL; }
+    orcpgz::Source src;
+    if (!src.start(path, threads, chunk_bytes ? (size_t)chunk_bytes : (size_t)1 << 20)) {
+        set_err(err, err_len, std::string("orc_gunzip_file: ") + path + " is not a gzip file that can be mapped");
+        return ORC_EINVAL;
+    }
+    uint64_t n = 0;
+    for (;;) {
+        uint8_t over;
+        const int64_t got = n < cap ? src.read(out + n, cap - n) : src.read(&over, 1);
+        if (got < 0) { set_err(err, err_len, src.err); return ORC_EINVAL; }
+        if (got == 0) return (int64_t)n;
+        if (n >= cap) { set_err(err, err_len, "orc_gunzip_file: the text does not fit"); return ORC_ECAPACITY; }
+        n += (uint64_t)got;
+    }
+}
+
 extern "C" const char *orc_reader_error(orc_reader *r)
 {
     return r ? r->err.c_str() : "null reader";

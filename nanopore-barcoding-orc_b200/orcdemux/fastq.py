@@ -132,6 +132,17 @@ class FastqReader:
             pass
 
 
+def gunzip_file(path: str, capacity: int, threads: int = 4, chunk_bytes: int = 0) -> bytes:
+    """The text of a .gz file through the chunk-parallel inflate alone (orc_gunzip_file, csrc/orc_pgz.h)."""
+    L = _lib.load()
+    out = np.empty(max(1, capacity), dtype=np.uint8)
+    err = C.create_string_buffer(512)
+    n = L.orc_gunzip_file(os.fsencode(path), int(threads), int(chunk_bytes), out.ctypes.data, int(capacity), err, 512)
+    if n < 0:
+        raise ValueError(err.value.decode(errors="replace"))
+    return out[:n].tobytes()
+
+
 class BinWriters:
     """One output file per bin name, created up front (orc_writer_*, csrc/orc_io.cpp): gzip
     members are deflated by a native thread pool while the GPU works on the next batches."""

@@ -30,7 +30,7 @@ EXPORTS = ["orc_create", "orc_destroy", "orc_last_error", "orc_n_bins", "orc_sub
            "orc_reader_open", "orc_reader_next", "orc_reader_release", "orc_reader_error", "orc_reader_close",
            "orc_writer_open", "orc_writer_write", "orc_writer_wait", "orc_writer_error", "orc_writer_close",
            "orc_edit_distances", "orc_synth", "orc_resident", "orc_export",
-           "orc_reader_open_threads", "orc_writer_set_index", "orc_empty_gzip_member", "orc_span_begin", "orc_span_end", "orc_probe_hostread", "orc_writer_write_members", "orc_get_timeline", "orc_reader_inflate_mode"]
+           "orc_reader_open_threads", "orc_writer_set_index", "orc_empty_gzip_member", "orc_span_begin", "orc_span_end", "orc_probe_hostread", "orc_writer_write_members", "orc_get_timeline", "orc_reader_inflate_mode", "orc_gunzip_file"]
 
 MATCH_DTYPE = np.dtype([
     ("adapter", "<i4"), ("is_rc", "<i4"), ("ref_start", "<i4"), ("ref_stop", "<i4"),
@@ -155,6 +155,8 @@ def load():
     L.orc_reader_release.restype = C.c_int
     L.orc_reader_inflate_mode.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.orc_reader_inflate_mode.restype = C.c_int
+    L.orc_gunzip_file.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.c_char_p, C.c_size_t]
+    L.orc_gunzip_file.restype = C.c_int64
     L.orc_reader_error.argtypes = [C.c_void_p]
     L.orc_reader_error.restype = C.c_char_p
     L.orc_reader_close.argtypes = [C.c_void_p]
