@@ -16,13 +16,19 @@
 //     chunk before it ended on -- that chain, back to the gzip header, is what makes a guessed start a real
 //     one; where it does not hold (fixed or stored blocks at the border, a block larger than a chunk, a wrong
 //     guess, the seam between two members) the consumer decodes from the known position itself until the
-//     chain closes again.  Markers are replaced through a 33 KiB look-up table built from the window the
-//     text in front left behind; CRC-32 and ISIZE of every member are checked against its trailer.
+//     chain closes again;
+//   * an accepted piece goes back to the pool: its markers are replaced through a 33 KiB look-up table built
+//     from the window the text in front left behind (the consumer resolves only a piece's last 32 KiB itself --
+//     they are the next window), the bytes are written straight into the caller's buffer when the piece fits
+//     the read() under way, and their CRC-32 is summed; the sums are combined in file order and compared, with
+//     ISIZE, to every member's trailer.  Members that begin inside a chunk (cat a.gz b.gz) are decoded on by
+//     the same worker from their own header, without markers.
 //
 // The block decoder below is this library's own (zlib has no way to start without a window); its acceptance
 // rules are zlib's (inflate.c / inftrees.c: over-subscribed and incomplete codes, missing end-of-block code,
 // distances too far back, stored-length complement), so what it accepts zlib accepts, byte for byte
-// (tests/test_io.py: files of gzip / zlib levels 0-9, several members, stored blocks, cut and damaged files).
+// (tests/test_pgz.py: streams written bit by bit and zlib's output under every strategy; tests/test_io.py: through
+// orc_reader -- gzip / zlib levels, several members, stored blocks, cut and damaged files).
 #pragma once
 #include <fcntl.h>
 #include <sys/mman.h>
