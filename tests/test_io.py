@@ -360,3 +360,21 @@ def test_chunk_parallel_inflate_random_damage(tmp_path, big_text, monkeypatch):
         else:
             assert _text_and_mode(p, rnd.choice([2, 5]))[0] == want, (trial, mode)
     assert refused >= 30
+
+
+def test_reader_closed_in_the_middle_of_a_chunk_parallel_stream(tmp_path, big_text, monkeypatch):
+    """Closing the reader while the pool is still inflating (an error further down the pipeline) returns at once."""
+    import time
+    monkeypatch.setenv("ORC_PGZ_MIN", "100000")
+    monkeypatch.setenv("ORC_PGZ_CHUNK", str(1 << 17))
+    p = tmp_path / "in.fastq.gz"
+    p.write_bytes(gzip.compress(big_text, 1))
+    for take in (0, 2):
+        rd = F.FastqReader(str(p), max_reads=2000, max_bytes=1 << 21, keep=2, ahead=2, pinned=False, threads=4)
+        it = iter(rd)
+        for _ in range(take):
+            assert next(it).n_reads > 0
+        assert rd.inflate_mode()[0] == 2
+        t0 = time.time()
+        rd.close()
+        assert time.time() - t0 < 5.0
