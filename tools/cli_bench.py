@@ -3,8 +3,8 @@
 -> D2H -> gzip deflate into 96 bin files) on synthetic COI reads, one JSON line per variant:
 
   * the fused `two-round` command on a .fastq.gz of this library's own writer (members with a size field:
-    inflated member-parallel), on a FOREIGN single-stream .fastq.gz (zlib, what `gzip` leaves: one inflate
-    thread) and on plain FASTQ;
+    inflated member-parallel), on a FOREIGN single-stream .fastq.gz (zlib, what `gzip` leaves: inflated
+    chunk-parallel by csrc/orc_pgz.h; ORC_NO_PGZ=1 in the environment gives the single zlib stream) and on plain FASTQ;
   * the reference script's own flow through the `cutadapt` shim (02_cutadapt_loop.sh:64-72 once, :94-102
     twelve times on the round-1 bins, which are member-structured because this library wrote them).
 
