@@ -112,7 +112,10 @@ def locate(ref: str, query: str, max_error_rate: float, flags: int, min_overlap:
             cost, score, origin = col[i]
             length = i + min(origin, 0)
             ok = length >= min_overlap and cost <= eff_col(length, i) * max_error_rate
-            if ok and (best is None or score > best[0] or (score == best[0] and cost < best[1])):
+            # R6 has no "best unset" clause: an unset best stands there with score 0 and cost m + n + 1, so a
+            # candidate with a negative score (error rates of 0.5 and more) does not replace it
+            b_score, b_cost = (0, m + n + 1) if best is None else (best[0], best[1])
+            if ok and (score > b_score or (score == b_score and cost < b_cost)):
                 best = (score, cost, origin, i, n)
     if best is None:
         return None
