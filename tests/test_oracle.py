@@ -170,3 +170,80 @@ def test_synthetic_truth_agreement():
     both = (rec0["adapter"] + 1 == t["sp5"]) & (t["sp27"] > 0) & has5
     assert (rec1["adapter"][both] + 1 == t["sp27"][both]).mean() > 0.95
     assert abs(rec0["is_rc"].mean() - 0.10) < 0.03
+
+
+def test_indexed_anchored_lookup_equals_a_literal_dict():
+    """SURVEY R11 read literally: a dict over every string within k mismatches of every anchored adapter (more
+    matches win a key, the later adapter wins equal matches), looked up with read[:L]; an N in the affix goes to the
+    comparer loop (R8 over PrefixComparer).  The C oracle decides the same from Hamming distances without building
+    the dict -- here the dict is built."""
+    import itertools
+    rnd = random.Random(811)
+
+    def environment(s, k):
+        out = {s: 0}
+        for d in range(1, k + 1):
+            for pos in itertools.combinations(range(len(s)), d):
+                for sub in itertools.product("ACGT", repeat=d):
+                    if all(s[p] != c for p, c in zip(pos, sub)):
+                        t = list(s)
+                        for p, c in zip(pos, sub):
+                            t[p] = c
+                        out["".join(t)] = d
+        return out
+
+    n_hit = n_fallback = 0
+    for trial in range(14):
+        L = rnd.choice([6, 9, 12, 17])
+        rate = rnd.choice([0.0, 0.1, 0.12, 0.2])
+        k = int(rate * L)
+        indexed = k <= 2                      # (with more errors cutadapt builds no index: the comparer loop decides)
+        base = "".join(rnd.choice("ACGT") for _ in range(L))
+        seqs = []
+        for _ in range(rnd.randint(2, 10)):
+            s = list(base) if rnd.random() < 0.6 else [rnd.choice("ACGT") for _ in range(L)]
+            for _k in range(rnd.randint(0, 3)):
+                s[rnd.randrange(L)] = rnd.choice("ACGT")
+            seqs.append("".join(s))
+        index = {}
+        for a, s in enumerate(seqs if indexed else []):
+            for key, e in environment(s, k).items():
+                m = L - e
+                if key in index and m < index[key][2]:
+                    continue
+                index[key] = (a, e, m)
+        suffix = trial % 2 == 1
+        recs = []
+        for i in range(300):
+            a = list(rnd.choice(seqs))
+            for _k in range(rnd.choice([0, 0, 1, 1, 2, 3])):
+                a[rnd.randrange(L)] = rnd.choice("ACGTN" if rnd.random() < 0.2 else "ACGT")
+            body = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(0, 30)))
+            s = (body + "".join(a)) if suffix else ("".join(a) + body)
+            if rnd.random() < 0.05:
+                s = s[:rnd.randint(0, L - 1)]           # shorter than the adapters: no match
+            recs.append(("r%d" % i, s, "I" * len(s)))
+        rs = synth.from_records(recs)
+        sets = [(oracle.AdapterSet(seqs, oracle.SUFFIX if suffix else oracle.PREFIX, rate, 3, indels=False), 0)]
+        rec, *_ = oracle.demux_batch(sets, rs.seq, rs.qual, rs.offsets, rs.lengths, n_threads=1)
+        for i, (_, s, _) in enumerate(recs):
+            affix = (s[len(s) - L:] if suffix else s[:L]) if len(s) >= L else None
+            if affix is None:
+                want = None
+            elif "N" in affix or not indexed:
+                n_fallback += 1
+                want = None
+                for a, ad in enumerate(seqs):
+                    matches = sum(x == y for x, y in zip(ad, affix))
+                    e = L - matches
+                    if e > int(rate * L):
+                        continue
+                    if want is None or matches - e > want[1] or (matches - e == want[1] and e < want[2]):
+                        want = (a, matches - e, e)
+            else:
+                hit = index.get(affix)
+                want = None if hit is None else (hit[0], hit[2], hit[1])
+            got = None if rec["adapter"][i] < 0 else (int(rec["adapter"][i]), int(rec["score"][i]), int(rec["errors"][i]))
+            assert got == want, (trial, seqs, rate, s, got, want)
+            n_hit += want is not None
+    assert n_hit > 1500 and n_fallback > 50
